@@ -1,0 +1,134 @@
+/* pingoo_waf.h -- C ABI of the B200 batched WAF verdict engine.
+ *
+ * Drop-in boundary for Pingoo's per-request rules / lists / GeoIP hot path.
+ * The reference has no FFI; each entry point below names the Rust-internal
+ * call it replaces (paths relative to the pingooio/pingoo tree @ eecc74d).
+ * INTEGRATION.md shows the Rust `extern "C"` block a maintainer would add.
+ *
+ * All functions return 0 on success and non-zero on failure; when `err` is
+ * non-NULL the failure text is written there (NUL-terminated, truncated to
+ * `err_cap`), and it is also available from pgw_last_error() (thread-local).
+ * There is no CPU fallback: every evaluate call runs CUDA kernels on an
+ * sm_100a device or fails.
+ */
+#ifndef PINGOO_WAF_H
+#define PINGOO_WAF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pgw_ruleset pgw_ruleset;
+
+/* rules::Action (rules/rules.rs:30-35) */
+enum { PGW_ACTION_BLOCK = 1, PGW_ACTION_CAPTCHA = 2 };
+
+/* ListType (pingoo/lists.rs:17-22) */
+enum { PGW_LIST_STRING = 0, PGW_LIST_INT = 1, PGW_LIST_IP = 2 };
+
+/* verdict word = action | rule_index << 2 ; rule_index == PGW_NO_RULE when no rule decided */
+enum { PGW_ALLOW = 0, PGW_BLOCK = 1, PGW_CAPTCHA = 2, PGW_BYPASS_CAPTCHA_API = 3 };
+#define PGW_NO_RULE 0x3FFFFFFFu
+#define PGW_VERDICT_ACTION(v) ((v) & 3u)
+#define PGW_VERDICT_RULE(v) ((v) >> 2)
+
+/* per-request flag bits (pgw_batch.flags) */
+enum {
+    PGW_FLAG_CAPTCHA_VERIFIED = 1, /* valid __pingoo_captcha_verified cookie  (listeners/http_listener.rs:222-236) */
+    PGW_FLAG_PRE_BLOCK = 2,        /* host gate already blocked the request   (http_listener.rs:159-165,196-198)   */
+    PGW_FLAG_PRE_CAPTCHA = 4,      /* cookie present but invalid              (http_listener.rs:231-235)           */
+    PGW_FLAG_BYPASS = 8            /* request addressed to /__pingoo/captcha  (http_listener.rs:200-204)           */
+};
+
+/* pingoo::rules::Rule{name, expression: Option<..>, actions}  (pingoo/rules.rs:9-14) */
+typedef struct pgw_rule_desc {
+    const char* name;
+    const char* expression;  /* NULL => the rule matches every request (pingoo/rules.rs:49-51) */
+    const uint8_t* actions;  /* PGW_ACTION_* in configuration order */
+    uint32_t n_actions;
+} pgw_rule_desc;
+
+typedef struct pgw_options {
+    int32_t max_dfa_states;        /* per scan unit; 0 = default (4096) */
+    uint64_t max_unit_table_bytes; /* per scan unit; 0 = default (96 KiB) */
+    int32_t eval_gates;            /* 1 (default): evaluate the user-agent and captcha-path gates of
+                                      http_listener.rs:196-204 inside the engine; 0: rules only */
+} pgw_options;
+
+/* One string column: concatenated bytes + n+1 offsets.  `bytes` must be 16-byte
+ * aligned and readable up to round_up(offsets[n], 16). */
+typedef struct pgw_strcol {
+    const uint8_t* bytes;
+    const uint32_t* offsets;
+} pgw_strcol;
+
+/* Columnar request batch = RequestData + ClientData (pingoo/rules.rs:16-34) for n requests. */
+typedef struct pgw_batch {
+    uint32_t n;
+    pgw_strcol host, url, path, method, user_agent;
+    const uint8_t* ip;          /* n x 16 bytes, network order; IPv4 in bytes [0,4), rest zero */
+    const uint8_t* ip_is_v6;    /* n */
+    const int32_t* remote_port; /* n */
+    const int64_t* asn;         /* n, or NULL: resolved from the loaded GeoIP db (else 0)  */
+    const uint16_t* country;    /* n, or NULL; two ASCII letters, first letter in the low byte */
+    const uint8_t* flags;       /* n, or NULL (= all zero) */
+} pgw_batch;
+
+typedef struct pgw_info {
+    uint32_t n_rules, n_atoms, n_scan_units, n_nonscan_atoms;
+    uint32_t scanned_fields_mask; /* bit f set: bytes of field f are read (host,url,path,method,user_agent = 0..4) */
+    uint32_t offset_fields_mask;  /* bit f set: offsets of field f are read */
+    uint32_t reads_ip, reads_port, reads_geo_columns;
+    uint64_t table_arena_bytes, smem_bytes;
+    uint32_t tables_in_smem, tile_requests, grid, threads;
+    uint32_t total_dfa_states, lpm_present, geoip_loaded;
+    uint64_t kernel_launches;     /* launches issued through this ruleset so far */
+    uint64_t last_h2d_bytes, last_d2h_bytes; /* bytes moved by the last pgw_evaluate_batch_host call */
+} pgw_info;
+
+/* rules::compile_expression(&str) -> Result<CompiledExpression, Error>   (rules/rules.rs:45-53) */
+int pgw_compile_expression(const char* expression, char* err, size_t err_cap);
+/* rules::validate_expression(&str) -> Result<(), Error>                  (rules/rules.rs:55-77) */
+int pgw_validate_expression(const char* expression, char* err, size_t err_cap);
+
+/* Config rule compilation: the loop of pingoo/config/config.rs:255-269.  Rule order = array order. */
+int pgw_ruleset_create(const pgw_rule_desc* rules, uint32_t n_rules, const pgw_options* options, pgw_ruleset** out,
+                       char* err, size_t err_cap);
+/* pingoo::lists::load_list on an in-memory CSV                          (pingoo/lists.rs:62-113) */
+int pgw_lists_add(pgw_ruleset* rs, const char* name, int list_type, const uint8_t* csv, size_t csv_len, char* err,
+                  size_t err_cap);
+/* GeoipDB::load on an already-decompressed .mmdb image                  (pingoo/geoip.rs:44-71) */
+int pgw_geoip_load(pgw_ruleset* rs, const uint8_t* mmdb, size_t mmdb_len, char* err, size_t err_cap);
+/* Lower rules against the loaded lists, build device tables, upload to `device`. */
+int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap);
+
+/* The per-request body of http_listener.rs:239-264 for a whole batch: context build, rule loop,
+ * action interpretation.  All pointers in `batch` and `verdict_out` are DEVICE pointers; the kernel is
+ * enqueued on `stream` (a cudaStream_t, NULL = default stream) and the call does not synchronise.
+ * Thread-safe on a finalized ruleset. */
+int pgw_evaluate_batch(const pgw_ruleset* rs, const pgw_batch* batch, uint32_t* verdict_out, void* stream);
+/* Same with HOST pointers: copies the columns to the device, evaluates, copies verdicts back, synchronises.
+ * Uses staging buffers owned by the ruleset (not thread-safe on one ruleset). */
+int pgw_evaluate_batch_host(pgw_ruleset* rs, const pgw_batch* batch, uint32_t* verdict_out);
+
+/* GeoipDB::lookup for a batch of addresses (pingoo/geoip.rs:73-91); device pointers, not-found => {0,"XX"}. */
+int pgw_geoip_lookup_batch(const pgw_ruleset* rs, const uint8_t* ip, const uint8_t* ip_is_v6, uint32_t n,
+                           uint32_t* asn_out, uint16_t* country_out, void* stream);
+
+/* Pinned (page-locked) host memory for batch columns, so the host-pointer path runs at PCIe speed. */
+void* pgw_host_alloc(size_t bytes);
+void pgw_host_free(void* p);
+
+int pgw_ruleset_info(const pgw_ruleset* rs, pgw_info* out);
+/* Human-readable compile summary / warnings (e.g. a regex that does not compile => that rule never matches). */
+size_t pgw_ruleset_describe(const pgw_ruleset* rs, char* buf, size_t cap);
+void pgw_ruleset_destroy(pgw_ruleset* rs);
+const char* pgw_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PINGOO_WAF_H */

@@ -1,0 +1,433 @@
+// extern "C" boundary (include/pingoo_waf.h): ruleset lifecycle, device upload,
+// launch planning and the device / host-pointer evaluate entry points.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pingoo_waf.h"
+#include "kernels.cuh"
+#include "ruleset.hpp"
+
+using namespace pgw;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(const std::string& msg, char* err, size_t cap) {
+    g_last_error = msg;
+    if (err && cap) {
+        size_t n = msg.size() < cap - 1 ? msg.size() : cap - 1;
+        memcpy(err, msg.data(), n);
+        err[n] = 0;
+    }
+    return 1;
+}
+
+struct DevMem {
+    std::vector<void*> ptrs;
+    template <class T>
+    const T* upload(const std::vector<T>& v, size_t pad_to = 16) {
+        size_t bytes = v.size() * sizeof(T);
+        size_t alloc = ((bytes + pad_to - 1) / pad_to) * pad_to;
+        if (alloc == 0) alloc = pad_to;
+        void* d = nullptr;
+        if (cudaMalloc(&d, alloc) != cudaSuccess) return nullptr;
+        ptrs.push_back(d);
+        cudaMemset(d, 0, alloc);
+        if (bytes && cudaMemcpy(d, v.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+        return (const T*)d;
+    }
+    void release() {
+        for (void* p : ptrs) cudaFree(p);
+        ptrs.clear();
+    }
+};
+
+struct Staging {
+    void* d = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t bytes) {
+        if (bytes <= cap) return true;
+        if (d) cudaFree(d);
+        d = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 4096;
+        if (cudaMalloc(&d, want) != cudaSuccess) return false;
+        cap = want;
+        return true;
+    }
+    void release() {
+        if (d) cudaFree(d);
+        d = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct pgw_ruleset {
+    RulesetBuilder builder;
+    HostProgram prog;
+    bool finalized = false;
+    int device = -1;
+    int sm_count = 0;
+    size_t max_smem = 0;
+    DevMem mem;
+    KParams base;  // program pointers filled in, batch fields zero
+    bool smem_tables = false;
+    uint32_t tile_log2 = 10;
+    size_t smem_bytes = 0;
+    std::atomic<uint64_t> launches{0};
+    // host-pointer path
+    Staging stage_cols[5], stage_offs[5], stage_ip, stage_v6, stage_port, stage_asn, stage_country, stage_flags, stage_verdict;
+    cudaStream_t stream = nullptr;
+    uint64_t last_h2d = 0, last_d2h = 0;
+};
+
+extern "C" {
+
+const char* pgw_last_error(void) { return g_last_error.c_str(); }
+
+int pgw_compile_expression(const char* expression, char* err, size_t err_cap) {
+    if (!expression) return fail("Expression is not valid: null", err, err_cap);
+    std::string e;
+    if (!RulesetBuilder::compile_expression(expression, e)) return fail(e, err, err_cap);
+    return 0;
+}
+
+int pgw_validate_expression(const char* expression, char* err, size_t err_cap) {
+    if (!expression) return fail("Expression is not valid: null", err, err_cap);
+    std::string e;
+    if (!RulesetBuilder::validate_expression(expression, e)) return fail(e, err, err_cap);
+    return 0;
+}
+
+int pgw_ruleset_create(const pgw_rule_desc* rules, uint32_t n_rules, const pgw_options* options, pgw_ruleset** out,
+                       char* err, size_t err_cap) {
+    if (!out) return fail("out is null", err, err_cap);
+    *out = nullptr;
+    pgw_ruleset* rs = new pgw_ruleset();
+    memset(&rs->base, 0, sizeof rs->base);
+    if (options) {
+        if (options->max_dfa_states > 0) rs->builder.options.max_dfa_states = options->max_dfa_states;
+        if (options->max_unit_table_bytes > 0) rs->builder.options.max_unit_table_bytes = (size_t)options->max_unit_table_bytes;
+        rs->builder.options.eval_gates = options->eval_gates != 0;
+    }
+    for (uint32_t i = 0; i < n_rules; ++i) {
+        std::string e;
+        if (!rs->builder.add_rule(rules[i].name, rules[i].expression, rules[i].actions, rules[i].n_actions, e)) {
+            delete rs;
+            return fail(e, err, err_cap);
+        }
+    }
+    *out = rs;
+    return 0;
+}
+
+int pgw_lists_add(pgw_ruleset* rs, const char* name, int list_type, const uint8_t* csv, size_t csv_len, char* err,
+                  size_t err_cap) {
+    if (!rs || !name) return fail("null argument", err, err_cap);
+    std::string e;
+    if (!rs->builder.add_list(name, list_type, csv, csv_len, e)) return fail(e, err, err_cap);
+    return 0;
+}
+
+int pgw_geoip_load(pgw_ruleset* rs, const uint8_t* mmdb, size_t mmdb_len, char* err, size_t err_cap) {
+    if (!rs || !mmdb) return fail("null argument", err, err_cap);
+    std::string e;
+    if (!rs->builder.load_geoip(mmdb, mmdb_len, e)) return fail(e, err, err_cap);
+    return 0;
+}
+
+int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap) {
+    if (!rs) return fail("null ruleset", err, err_cap);
+    if (rs->finalized) return fail("ruleset already finalized", err, err_cap);
+    // The device is probed first: without a CUDA device there is nothing this engine can do.
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(std::string("no CUDA device available (") + cudaGetErrorString(ce) + "); this engine has no CPU fallback", err, err_cap);
+    if (device < 0 || device >= ndev) return fail("invalid device index", err, err_cap);
+    if (const char* m = waf_configure(device, &rs->max_smem, &rs->sm_count)) return fail(std::string("CUDA: ") + m, err, err_cap);
+
+    std::string e;
+    if (!rs->builder.finalize(&rs->prog, e)) return fail(e, err, err_cap);
+    const HostProgram& H = rs->prog;
+    rs->device = device;
+
+    KParams& P = rs->base;
+    DevMem& M = rs->mem;
+    bool ok = true;
+    auto chk = [&](const void* p) { if (!p) ok = false; return p; };
+    P.units = (const UnitDesc*)chk(M.upload(H.units));
+    P.n_units = (uint32_t)H.units.size();
+    P.arena = (const uint8_t*)chk(M.upload(H.arena));
+    P.arena_bytes = (uint32_t)H.arena.size();
+    P.cls_bytes = (uint32_t)H.units.size() * 256u;
+    P.acc_idx = (const uint32_t*)chk(M.upload(H.acc_idx));
+    P.acc_atoms = (const uint16_t*)chk(M.upload(H.acc_atoms));
+    P.end_idx = (const uint32_t*)chk(M.upload(H.end_idx));
+    P.end_atoms = (const uint16_t*)chk(M.upload(H.end_atoms));
+    P.n_atoms = H.n_atoms;
+    P.atom_words = H.atom_words;
+    P.expect = (const uint32_t*)chk(M.upload(H.expect));
+    P.care = (const uint32_t*)chk(M.upload(H.care));
+    P.ns = (const NsAtom*)chk(M.upload(H.ns_atoms));
+    P.n_ns = (uint32_t)H.ns_atoms.size();
+    P.code = (const uint16_t*)chk(M.upload(H.code));
+    P.rule_off = (const uint32_t*)chk(M.upload(H.rule_off));
+    P.term = (const uint8_t*)chk(M.upload(H.term));
+    P.n_rules = H.n_rules;
+    P.ar_idx = (const uint32_t*)chk(M.upload(H.ar_idx));
+    P.ar_rules = (const uint32_t*)chk(M.upload(H.ar_rules));
+    for (int cv = 0; cv < 2; ++cv) {
+        P.dflt[cv] = (const uint32_t*)chk(M.upload(H.dflt_rules[cv]));
+        P.n_dflt[cv] = (uint32_t)H.dflt_rules[cv].size();
+        P.v0[cv] = H.v0[cv];
+    }
+    P.iset_vals = (const int64_t*)chk(M.upload(H.iset_vals));
+    P.iset_off = (const uint32_t*)chk(M.upload(H.iset_off));
+    P.cset = (const uint32_t*)chk(M.upload(H.cset_words));
+    for (int f = 0; f < 5; ++f) P.slot[f] = H.field_slot[f];
+    P.n_slots = H.n_slots;
+    P.gate_atom = H.gate_bypass_atom;
+    P.eval_gates = H.eval_gates ? 1u : 0u;
+    P.lpm_present = H.lpm.present ? 1u : 0u;
+    P.geo_loaded = H.lpm.geo_loaded ? 1u : 0u;
+    if (H.lpm.present) {
+        P.dir24 = (const uint32_t*)chk(M.upload(H.lpm.dir24));
+        P.tbl8 = (const uint32_t*)chk(M.upload(H.lpm.tbl8));
+        P.leaves = (const LpmLeaf*)chk(M.upload(H.lpm.leaves));
+        P.v6_hi = (const uint64_t*)chk(M.upload(H.lpm.v6_hi));
+        P.v6_lo = (const uint64_t*)chk(M.upload(H.lpm.v6_lo));
+        P.v6_leaf = (const uint32_t*)chk(M.upload(H.lpm.v6_leaf));
+        P.n_v6 = (uint32_t)H.lpm.v6_leaf.size();
+    }
+    if (!ok) {
+        M.release();
+        return fail(std::string("CUDA: device allocation/upload failed: ") + cudaGetErrorString(cudaGetLastError()), err, err_cap);
+    }
+
+    // launch plan: prefer DFA tables in shared memory; shrink the tile before giving that up
+    bool planned = false;
+    for (int st = 1; st >= 0 && !planned; --st) {
+        int lo = st ? 8 : 6;
+        for (int tl = 10; tl >= lo; --tl) {
+            size_t need = waf_smem_bytes(P, st != 0, (uint32_t)tl);
+            if (need <= rs->max_smem) {
+                rs->smem_tables = st != 0;
+                rs->tile_log2 = (uint32_t)tl;
+                rs->smem_bytes = need;
+                planned = true;
+                break;
+            }
+        }
+    }
+    if (!planned) {
+        M.release();
+        return fail("ruleset does not fit the shared-memory plan (too many atoms or scan units)", err, err_cap);
+    }
+    if (cudaStreamCreateWithFlags(&rs->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        M.release();
+        return fail("CUDA: stream creation failed", err, err_cap);
+    }
+    rs->finalized = true;
+    return 0;
+}
+
+static int launch_on(const pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdict_out, void* stream, std::string& e) {
+    const HostProgram& H = rs->prog;
+    KParams P = rs->base;
+    const pgw_strcol* cols[5] = {&b->host, &b->url, &b->path, &b->method, &b->user_agent};
+    for (int f = 0; f < 5; ++f) {
+        P.col[f] = cols[f]->bytes;
+        P.off[f] = cols[f]->offsets;
+        if (H.field_slot[f] >= 0 && !cols[f]->offsets) { e = std::string("batch is missing offsets for http_request.") + kFieldNames[f]; return 1; }
+        if (((H.scanned_fields_mask >> f) & 1) && !cols[f]->bytes) { e = std::string("batch is missing bytes for http_request.") + kFieldNames[f]; return 1; }
+        if (((H.scanned_fields_mask >> f) & 1) && ((uintptr_t)cols[f]->bytes & 15)) { e = std::string("bytes of http_request.") + kFieldNames[f] + " are not 16-byte aligned"; return 1; }
+    }
+    P.ip = b->ip;
+    P.is_v6 = b->ip_is_v6;
+    P.port = b->remote_port;
+    P.asn = b->asn;
+    P.country = b->country;
+    P.flags = b->flags;
+    bool geo_on_device = H.lpm.geo_loaded && H.needs_geo_cols && !(b->asn && b->country);
+    P.need_lpm = (H.needs_ip || geo_on_device) ? 1u : 0u;
+    if (P.need_lpm && (!b->ip || !b->ip_is_v6)) { e = "batch is missing client.ip columns"; return 1; }
+    if (H.needs_port && !b->remote_port) { e = "batch is missing client.remote_port"; return 1; }
+    P.verdict = verdict_out;
+    P.n = b->n;
+    P.tile_log2 = rs->tile_log2;
+    P.n_tiles = (b->n + (1u << rs->tile_log2) - 1) >> rs->tile_log2;
+    LaunchPlan plan;
+    plan.smem_tables = rs->smem_tables;
+    plan.tile_log2 = rs->tile_log2;
+    plan.smem_bytes = rs->smem_bytes;
+    plan.grid = (int)(P.n_tiles < (uint32_t)rs->sm_count ? P.n_tiles : (uint32_t)rs->sm_count);
+    if (const char* m = waf_launch(P, plan, stream)) { e = std::string("CUDA launch failed: ") + m; return 1; }
+    if (b->n) const_cast<pgw_ruleset*>(rs)->launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+int pgw_evaluate_batch(const pgw_ruleset* rs, const pgw_batch* batch, uint32_t* verdict_out, void* stream) {
+    if (!rs || !batch) return fail("null argument", nullptr, 0);
+    if (!rs->finalized) return fail("ruleset is not finalized", nullptr, 0);
+    if (batch->n && !verdict_out) return fail("verdict_out is null", nullptr, 0);
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != rs->device) cudaSetDevice(rs->device);
+    std::string e;
+    int rc = launch_on(rs, batch, verdict_out, stream, e);
+    if (cur != rs->device && cur >= 0) cudaSetDevice(cur);
+    if (rc) return fail(e, nullptr, 0);
+    return 0;
+}
+
+int pgw_evaluate_batch_host(pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdict_out) {
+    if (!rs || !b) return fail("null argument", nullptr, 0);
+    if (!rs->finalized) return fail("ruleset is not finalized", nullptr, 0);
+    if (b->n == 0) return 0;
+    if (!verdict_out) return fail("verdict_out is null", nullptr, 0);
+    cudaSetDevice(rs->device);
+    const HostProgram& H = rs->prog;
+    const uint32_t n = b->n;
+    cudaStream_t s = rs->stream;
+    pgw_batch d;
+    memset(&d, 0, sizeof d);
+    d.n = n;
+    uint64_t h2d = 0;
+    auto up = [&](Staging& st, const void* src, size_t bytes, size_t pad) -> const void* {
+        if (!st.ensure(bytes + pad)) return nullptr;
+        if (bytes && cudaMemcpyAsync(st.d, src, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return nullptr;
+        h2d += bytes;
+        return st.d;
+    };
+    const pgw_strcol* hc[5] = {&b->host, &b->url, &b->path, &b->method, &b->user_agent};
+    pgw_strcol* dc[5] = {&d.host, &d.url, &d.path, &d.method, &d.user_agent};
+    for (int f = 0; f < 5; ++f) {
+        if (H.field_slot[f] < 0) continue;
+        if (!hc[f]->offsets) return fail(std::string("batch is missing offsets for http_request.") + kFieldNames[f], nullptr, 0);
+        dc[f]->offsets = (const uint32_t*)up(rs->stage_offs[f], hc[f]->offsets, (size_t)(n + 1) * 4, 0);
+        if (!dc[f]->offsets) return fail("CUDA: staging copy failed", nullptr, 0);
+        if ((H.scanned_fields_mask >> f) & 1) {
+            if (!hc[f]->bytes) return fail(std::string("batch is missing bytes for http_request.") + kFieldNames[f], nullptr, 0);
+            size_t total = hc[f]->offsets[n];
+            dc[f]->bytes = (const uint8_t*)up(rs->stage_cols[f], hc[f]->bytes, total, 16);
+            if (!dc[f]->bytes) return fail("CUDA: staging copy failed", nullptr, 0);
+        }
+    }
+    bool geo_on_device = H.lpm.geo_loaded && H.needs_geo_cols && !(b->asn && b->country);
+    bool need_ip = H.needs_ip || geo_on_device;
+    if (need_ip) {
+        if (!b->ip || !b->ip_is_v6) return fail("batch is missing client.ip columns", nullptr, 0);
+        d.ip = (const uint8_t*)up(rs->stage_ip, b->ip, (size_t)n * 16, 0);
+        d.ip_is_v6 = (const uint8_t*)up(rs->stage_v6, b->ip_is_v6, n, 0);
+        if (!d.ip || !d.ip_is_v6) return fail("CUDA: staging copy failed", nullptr, 0);
+    }
+    if (H.needs_port) {
+        if (!b->remote_port) return fail("batch is missing client.remote_port", nullptr, 0);
+        d.remote_port = (const int32_t*)up(rs->stage_port, b->remote_port, (size_t)n * 4, 0);
+        if (!d.remote_port) return fail("CUDA: staging copy failed", nullptr, 0);
+    }
+    if (H.needs_geo_cols && b->asn && b->country) {
+        d.asn = (const int64_t*)up(rs->stage_asn, b->asn, (size_t)n * 8, 0);
+        d.country = (const uint16_t*)up(rs->stage_country, b->country, (size_t)n * 2, 0);
+        if (!d.asn || !d.country) return fail("CUDA: staging copy failed", nullptr, 0);
+    }
+    if (b->flags) {
+        d.flags = (const uint8_t*)up(rs->stage_flags, b->flags, n, 0);
+        if (!d.flags) return fail("CUDA: staging copy failed", nullptr, 0);
+    }
+    if (!rs->stage_verdict.ensure((size_t)n * 4)) return fail("CUDA: staging allocation failed", nullptr, 0);
+    std::string e;
+    if (launch_on(rs, &d, (uint32_t*)rs->stage_verdict.d, s, e)) return fail(e, nullptr, 0);
+    if (cudaMemcpyAsync(verdict_out, rs->stage_verdict.d, (size_t)n * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+        return fail("CUDA: verdict copy failed", nullptr, 0);
+    cudaError_t ce = cudaStreamSynchronize(s);
+    if (ce != cudaSuccess) return fail(std::string("CUDA: ") + cudaGetErrorString(ce), nullptr, 0);
+    rs->last_h2d = h2d;
+    rs->last_d2h = (uint64_t)n * 4;
+    return 0;
+}
+
+int pgw_geoip_lookup_batch(const pgw_ruleset* rs, const uint8_t* ip, const uint8_t* ip_is_v6, uint32_t n, uint32_t* asn_out,
+                           uint16_t* country_out, void* stream) {
+    if (!rs || !rs->finalized) return fail("ruleset is not finalized", nullptr, 0);
+    if (n && (!ip || !ip_is_v6 || !asn_out || !country_out)) return fail("null argument", nullptr, 0);
+    KParams P = rs->base;
+    if (const char* m = geoip_launch(P, ip, ip_is_v6, n, asn_out, country_out, stream)) return fail(std::string("CUDA launch failed: ") + m, nullptr, 0);
+    if (n) const_cast<pgw_ruleset*>(rs)->launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+void* pgw_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void pgw_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int pgw_ruleset_info(const pgw_ruleset* rs, pgw_info* out) {
+    if (!rs || !out) return fail("null argument", nullptr, 0);
+    memset(out, 0, sizeof *out);
+    const HostProgram& H = rs->prog;
+    out->n_rules = (uint32_t)rs->builder.n_rules();
+    if (!rs->finalized) return 0;
+    out->n_atoms = H.n_atoms;
+    out->n_scan_units = (uint32_t)H.units.size();
+    out->n_nonscan_atoms = (uint32_t)H.ns_atoms.size();
+    out->scanned_fields_mask = H.scanned_fields_mask;
+    for (int f = 0; f < 5; ++f)
+        if (H.field_slot[f] >= 0) out->offset_fields_mask |= 1u << f;
+    out->reads_ip = H.needs_ip || (H.lpm.geo_loaded && H.needs_geo_cols);
+    out->reads_port = H.needs_port;
+    out->reads_geo_columns = H.needs_geo_cols;
+    out->table_arena_bytes = H.arena.size();
+    out->smem_bytes = rs->smem_bytes;
+    out->tables_in_smem = rs->smem_tables;
+    out->tile_requests = 1u << rs->tile_log2;
+    out->grid = (uint32_t)rs->sm_count;
+    out->threads = kThreads;
+    for (auto& u : H.units) out->total_dfa_states += u.n_states;
+    out->lpm_present = H.lpm.present;
+    out->geoip_loaded = H.lpm.geo_loaded;
+    out->kernel_launches = rs->launches.load();
+    out->last_h2d_bytes = rs->last_h2d;
+    out->last_d2h_bytes = rs->last_d2h;
+    return 0;
+}
+
+size_t pgw_ruleset_describe(const pgw_ruleset* rs, char* buf, size_t cap) {
+    if (!rs) return 0;
+    std::string s = rs->finalized ? rs->prog.summary() : std::string("(not finalized)");
+    for (auto& w : rs->prog.warnings) s += "\nwarning: " + w;
+    if (buf && cap) {
+        size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+        memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return s.size();
+}
+
+void pgw_ruleset_destroy(pgw_ruleset* rs) {
+    if (!rs) return;
+    if (rs->device >= 0) cudaSetDevice(rs->device);
+    rs->mem.release();
+    for (int f = 0; f < 5; ++f) { rs->stage_cols[f].release(); rs->stage_offs[f].release(); }
+    rs->stage_ip.release(); rs->stage_v6.release(); rs->stage_port.release(); rs->stage_asn.release();
+    rs->stage_country.release(); rs->stage_flags.release(); rs->stage_verdict.release();
+    if (rs->stream) cudaStreamDestroy(rs->stream);
+    delete rs;
+}
+
+}  // extern "C"

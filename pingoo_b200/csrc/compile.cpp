@@ -1,0 +1,285 @@
+// Model -> HostProgram: DFA groups per field, rule bytecode, candidate indexes.
+#include "compile.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <functional>
+#include <sstream>
+
+#include "dfa.hpp"
+
+namespace pgw {
+namespace {
+
+void pad16(std::vector<uint8_t>& v) {
+    while (v.size() % 16) v.push_back(0);
+}
+
+// Emit postfix code for formula `n`; returns the stack depth it needs.
+int emit_code(const BoolPool& P, int n, std::vector<uint16_t>& code) {
+    const BoolNode& b = P.at(n);
+    switch (b.kind) {
+        case BoolNode::CONST: code.push_back(b.v ? OP_PUSH1 : OP_PUSH0); return 1;
+        case BoolNode::ATOM: code.push_back((uint16_t)b.a); return 1;
+        case BoolNode::NOT: {
+            int d = emit_code(P, b.a, code);
+            code.push_back(OP_NOT);
+            return d;
+        }
+        case BoolNode::AND:
+        case BoolNode::OR: {
+            std::vector<uint16_t> ca, cb;
+            int da = emit_code(P, b.a, ca), db = emit_code(P, b.b, cb);
+            // deeper operand first keeps the stack shallow
+            if (da >= db) { code.insert(code.end(), ca.begin(), ca.end()); code.insert(code.end(), cb.begin(), cb.end()); }
+            else { code.insert(code.end(), cb.begin(), cb.end()); code.insert(code.end(), ca.begin(), ca.end()); }
+            code.push_back(b.kind == BoolNode::AND ? OP_AND : OP_OR);
+            return std::max(std::max(da, db), std::min(da, db) + 1);
+        }
+    }
+    return 1;
+}
+
+void collect_atoms(const BoolPool& P, int n, bool neg, std::vector<std::pair<int, bool>>& out) {
+    const BoolNode& b = P.at(n);
+    switch (b.kind) {
+        case BoolNode::CONST: return;
+        case BoolNode::ATOM: out.emplace_back(b.a, neg); return;
+        case BoolNode::NOT: collect_atoms(P, b.a, !neg, out); return;
+        default:
+            collect_atoms(P, b.a, neg, out);
+            collect_atoms(P, b.b, neg, out);
+    }
+}
+
+uint8_t terminal_for(const std::vector<uint8_t>& actions, bool captcha_verified) {
+    // http_listener.rs:253-261: walk the actions of a matched rule in order
+    for (uint8_t a : actions) {
+        if (a == ACT_BLOCK) return V_BLOCK;
+        if (a == ACT_CAPTCHA && !captcha_verified) return V_CAPTCHA;
+    }
+    return 0;
+}
+
+}  // namespace
+
+std::string HostProgram::summary() const {
+    std::ostringstream o;
+    o << "rules=" << n_rules << " atoms=" << n_atoms << " units=" << units.size() << " arena_bytes=" << arena.size();
+    for (size_t u = 0; u < units.size(); ++u)
+        o << " [" << kFieldNames[units[u].field] << ": states=" << units[u].n_states << " classes=" << units[u].n_classes << "]";
+    o << " ns_atoms=" << ns_atoms.size() << " lpm=" << (lpm.present ? 1 : 0);
+    return o.str();
+}
+
+bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint8_t>& geo_mmdb, HostProgram* out,
+                     std::string& err) {
+    HostProgram& H = *out;
+    H = HostProgram();
+    H.eval_gates = opt.eval_gates;
+    H.warnings = M.warnings;
+    H.n_rules = (uint32_t)M.rules.size();
+
+    // ---- internal gate atom: path.starts_with("/__pingoo/captcha") (http_listener.rs:200-204)
+    if (opt.eval_gates) {
+        std::string key = "S|" + std::to_string((int)F_PATH) + "|^|17:/__pingoo/captcha";
+        auto it = M.atom_index.find(key);
+        if (it == M.atom_index.end()) {
+            AtomDesc a;
+            a.kind = AtomDesc::STR_PATTERN;
+            a.field = F_PATH;
+            a.key = key;
+            int id = (int)M.atoms.size();
+            a.nfa_start = nfa_literal(M.nfa[F_PATH], "/__pingoo/captcha", true, false, id);
+            M.atom_index[key] = id;
+            M.atoms.push_back(a);
+            H.gate_bypass_atom = id;
+        } else H.gate_bypass_atom = it->second;
+    }
+
+    if (M.atoms.size() > 0x3FFF) {
+        err = "too many distinct predicates (" + std::to_string(M.atoms.size()) + " > 16383)";
+        return false;
+    }
+    H.n_atoms = (uint32_t)M.atoms.size();
+    H.atom_words = std::max<uint32_t>(1, (H.n_atoms + 31) / 32);
+    H.expect.assign(H.atom_words, 0);
+    H.care.assign(H.atom_words, 0);
+
+    // ---- polarity statistics, atom -> rules index ---------------------------------
+    std::vector<std::vector<uint32_t>> atom_rules(H.n_atoms);
+    for (size_t r = 0; r < M.rules.size(); ++r) {
+        std::vector<std::pair<int, bool>> refs;
+        collect_atoms(M.pool, M.rules[r].formula, false, refs);
+        for (auto& pr : refs) {
+            if (pr.second) M.atoms[pr.first].neg_refs++;
+            else M.atoms[pr.first].pos_refs++;
+            if (atom_rules[pr.first].empty() || atom_rules[pr.first].back() != (uint32_t)r) atom_rules[pr.first].push_back((uint32_t)r);
+            H.care[pr.first >> 5] |= 1u << (pr.first & 31);
+        }
+    }
+    std::vector<uint8_t> expect_vals(H.n_atoms, 0);
+    for (uint32_t a = 0; a < H.n_atoms; ++a)
+        if (M.atoms[a].neg_refs > M.atoms[a].pos_refs) {
+            expect_vals[a] = 1;
+            H.expect[a >> 5] |= 1u << (a & 31);
+        }
+    H.ar_idx.assign(1, 0);
+    for (uint32_t a = 0; a < H.n_atoms; ++a) {
+        H.ar_rules.insert(H.ar_rules.end(), atom_rules[a].begin(), atom_rules[a].end());
+        H.ar_idx.push_back((uint32_t)H.ar_rules.size());
+    }
+
+    // ---- rule bytecode, terminal actions, default verdicts -----------------------
+    H.rule_off.assign(1, 0);
+    for (size_t r = 0; r < M.rules.size(); ++r) {
+        std::vector<uint16_t> code;
+        int depth = emit_code(M.pool, M.rules[r].formula, code);
+        if (depth > (int)kMaxStackDepth) {
+            err = "rule '" + M.rules[r].name + "': expression too deeply nested for the evaluator (" + std::to_string(depth) + ")";
+            return false;
+        }
+        H.code.insert(H.code.end(), code.begin(), code.end());
+        H.rule_off.push_back((uint32_t)H.code.size());
+        uint8_t t0 = terminal_for(M.rules[r].actions, false), t1 = terminal_for(M.rules[r].actions, true);
+        H.term.push_back((uint8_t)(t0 | (t1 << 2)));
+    }
+    for (int cv = 0; cv < 2; ++cv) {
+        H.v0[cv] = V_ALLOW | (kNoRule << 2);
+        bool have_v0 = false;
+        for (size_t r = 0; r < M.rules.size(); ++r) {
+            uint8_t t = (H.term[r] >> (2 * cv)) & 3;
+            if (!t) continue;
+            if (!M.pool.eval(M.rules[r].formula, expect_vals)) continue;
+            H.dflt_rules[cv].push_back((uint32_t)r);
+            if (!have_v0) { H.v0[cv] = t | ((uint32_t)r << 2); have_v0 = true; }
+            if (M.pool.is_const(M.rules[r].formula)) break;  // an unconditional rule shadows everything after it
+        }
+    }
+
+    // ---- scan units: DFA groups per field ------------------------------------------
+    bool len_feat_used[N_FIELDS] = {false, false, false, false, false};
+    static const int kFieldOrder[N_FIELDS] = {F_URL, F_USER_AGENT, F_PATH, F_HOST, F_METHOD};  // longest first
+    // arena: all class maps first, then the tables
+    struct Pending { Dfa dfa; int field; };
+    std::vector<Pending> pend;
+    for (int fo = 0; fo < N_FIELDS; ++fo) {
+        int f = kFieldOrder[fo];
+        std::vector<int> starts;
+        for (uint32_t a = 0; a < H.n_atoms; ++a)
+            if (M.atoms[a].kind == AtomDesc::STR_PATTERN && M.atoms[a].field == f) starts.push_back(M.atoms[a].nfa_start);
+        if (starts.empty()) continue;
+        DfaGroups groups;
+        int failed = -1;
+        if (!build_dfa_groups(M.nfa[f], starts, opt.max_dfa_states, opt.max_unit_table_bytes, &groups, &failed)) {
+            std::string which = "?";
+            int k = 0;
+            for (uint32_t a = 0; a < H.n_atoms; ++a)
+                if (M.atoms[a].kind == AtomDesc::STR_PATTERN && M.atoms[a].field == f) {
+                    if (k == failed) which = M.atoms[a].key;
+                    ++k;
+                }
+            err = "pattern on http_request." + std::string(kFieldNames[f]) + " needs a DFA larger than " +
+                  std::to_string(opt.max_dfa_states) + " states: " + which;
+            return false;
+        }
+        for (auto& d : groups.dfas) pend.push_back(Pending{std::move(d), f});
+        H.scanned_fields_mask |= 1u << f;
+    }
+    // class maps
+    std::vector<uint32_t> cls_offs;
+    for (auto& p : pend) {
+        cls_offs.push_back((uint32_t)H.arena.size());
+        H.arena.insert(H.arena.end(), p.dfa.classmap, p.dfa.classmap + 256);
+    }
+    H.acc_idx.clear();
+    H.end_idx.clear();
+    for (size_t u = 0; u < pend.size(); ++u) {
+        const Dfa& d = pend[u].dfa;
+        UnitDesc ud;
+        memset(&ud, 0, sizeof ud);
+        ud.field = (uint32_t)pend[u].field;
+        ud.n_classes = (uint32_t)d.n_classes;
+        ud.n_states = (uint32_t)d.n_states;
+        ud.start_state = (uint32_t)d.start;
+        ud.acc_lo = (uint32_t)d.acc_lo;
+        pad16(H.arena);
+        ud.tbl_off = (uint32_t)H.arena.size();
+        ud.cls_off = cls_offs[u];
+        const uint8_t* tb = (const uint8_t*)d.trans.data();
+        H.arena.insert(H.arena.end(), tb, tb + d.trans.size() * 2);
+        ud.acc_base = (uint32_t)H.acc_idx.size();
+        for (int s = d.acc_lo; s < d.n_states; ++s) {
+            H.acc_idx.push_back((uint32_t)H.acc_atoms.size());
+            for (int a : d.acc[s]) H.acc_atoms.push_back((uint16_t)a);
+        }
+        H.acc_idx.push_back((uint32_t)H.acc_atoms.size());
+        ud.end_base = (uint32_t)H.end_idx.size();
+        for (int s = 0; s < d.n_states; ++s) {
+            H.end_idx.push_back((uint32_t)H.end_atoms.size());
+            for (int a : d.endacc[s]) H.end_atoms.push_back((uint16_t)a);
+            if (!d.endacc[s].empty()) ud.end_any = 1;
+        }
+        H.end_idx.push_back((uint32_t)H.end_atoms.size());
+        H.units.push_back(ud);
+    }
+    pad16(H.arena);
+    if (H.acc_atoms.empty()) H.acc_atoms.push_back(0);
+    if (H.end_atoms.empty()) H.end_atoms.push_back(0);
+
+    // ---- non-scan atoms ----------------------------------------------------------------
+    H.iset_off.assign(1, 0);
+    for (auto& s : M.int_sets) {
+        H.iset_vals.insert(H.iset_vals.end(), s.begin(), s.end());
+        H.iset_off.push_back((uint32_t)H.iset_vals.size());
+    }
+    for (auto& cs : M.country_sets)
+        for (uint32_t w = 0; w < kCountryWords; ++w) {
+            uint32_t v = 0;
+            for (int b = 0; b < 32; ++b) {
+                size_t i = (size_t)w * 32 + b;
+                if (i < 676 && cs.test(i)) v |= 1u << b;
+            }
+            H.cset_words.push_back(v);
+        }
+    for (uint32_t a = 0; a < H.n_atoms; ++a) {
+        const AtomDesc& d = M.atoms[a];
+        if (d.kind == AtomDesc::STR_PATTERN) continue;
+        NsAtom n;
+        memset(&n, 0, sizeof n);
+        n.kind = d.kind;
+        n.atom = a;
+        n.feat = (uint32_t)std::max(0, d.feat);
+        n.op = (uint32_t)d.op;
+        n.cval = d.cval;
+        n.set_id = (uint32_t)std::max(0, d.set_id);
+        H.ns_atoms.push_back(n);
+        if (d.kind == AtomDesc::INT_CMP || d.kind == AtomDesc::INT_SET) {
+            if (d.feat == IF_PORT) H.needs_port = true;
+            else if (d.feat == IF_ASN) H.needs_geo_cols = true;
+            else len_feat_used[d.feat - IF_LEN0] = true;
+        }
+        if (d.kind == AtomDesc::IP_SET) H.needs_ip = true;
+        if (d.kind == AtomDesc::COUNTRY_SET) H.needs_geo_cols = true;
+    }
+    if (M.ip_sets.size() > 32) {
+        err = "more than 32 distinct Ip lists referenced by rules";
+        return false;
+    }
+
+    // ---- offset slots: scanned fields, length features, the user-agent gate --------
+    for (int f = 0; f < N_FIELDS; ++f) {
+        bool need = (H.scanned_fields_mask >> f) & 1 || len_feat_used[f] || (opt.eval_gates && f == F_USER_AGENT);
+        if (need) H.field_slot[f] = (int)H.n_slots++;
+    }
+    for (auto& u : H.units) u.field_slot = (uint32_t)H.field_slot[u.field];
+
+    // ---- LPM tables (ip lists + geoip) -------------------------------------------------
+    bool want_geo = !geo_mmdb.empty();
+    if (!M.ip_sets.empty() || want_geo) {
+        if (!build_lpm(M.ip_sets, geo_mmdb, &H.lpm, err)) return false;
+    }
+    return true;
+}
+
+}  // namespace pgw

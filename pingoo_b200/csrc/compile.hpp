@@ -1,0 +1,72 @@
+// Model (atoms + formulas) -> HostProgram (flat tables ready for upload).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "model.hpp"
+#include "program.hpp"
+
+namespace pgw {
+
+struct CompileOptions {
+    int max_dfa_states = 4096;                 // per scan unit, after minimisation
+    size_t max_unit_table_bytes = 96u << 10;   // per scan unit transition table
+    bool eval_gates = true;                    // evaluate http_listener.rs:196-204 gates inside the engine
+};
+
+struct LpmTables {
+    bool present = false;        // any ip set or geoip database loaded
+    bool geo_loaded = false;
+    std::vector<uint32_t> dir24; // [1<<24]: bit31 set -> low bits index a 256-entry block in tbl8, else leaf id
+    std::vector<uint32_t> tbl8;
+    std::vector<LpmLeaf> leaves; // leaf 0 = {asn 0, "XX", no sets}
+    // IPv6: sorted, disjoint, covering ranges; range i = [start_i, start_{i+1})
+    std::vector<uint64_t> v6_hi, v6_lo;
+    std::vector<uint32_t> v6_leaf;
+};
+
+struct HostProgram {
+    std::vector<UnitDesc> units;
+    std::vector<uint8_t> arena;  // class maps then transition tables (16-byte aligned pieces)
+    std::vector<uint32_t> acc_idx;
+    std::vector<uint16_t> acc_atoms;
+    std::vector<uint32_t> end_idx;
+    std::vector<uint16_t> end_atoms;
+    uint32_t n_atoms = 0, atom_words = 0;
+    std::vector<uint32_t> expect;  // expected atom values (perf heuristic only)
+    std::vector<uint32_t> care;    // atoms referenced by at least one rule
+    std::vector<NsAtom> ns_atoms;
+    std::vector<uint16_t> code;
+    std::vector<uint32_t> rule_off;  // n_rules + 1
+    std::vector<uint8_t> term;       // per rule: terminal action for cv=0 (bits 0-1) and cv=1 (bits 2-3)
+    std::vector<uint32_t> ar_idx, ar_rules;  // atom -> rules CSR
+    std::vector<uint32_t> dflt_rules[2];     // rules true under `expect` with a terminal action, per captcha_verified
+    uint32_t v0[2] = {0, 0};                 // verdict when every cared atom has its expected value
+    std::vector<int64_t> iset_vals;
+    std::vector<uint32_t> iset_off;
+    std::vector<uint32_t> cset_words;
+    int field_slot[N_FIELDS] = {-1, -1, -1, -1, -1};  // fields whose offsets the kernel stages
+    uint32_t n_slots = 0;
+    uint32_t scanned_fields_mask = 0;  // fields whose bytes are read (algorithmic-bytes accounting)
+    int32_t gate_bypass_atom = -1;
+    bool eval_gates = true;
+    bool needs_ip = false, needs_geo_cols = false, needs_port = false;
+    uint32_t n_rules = 0;
+    LpmTables lpm;
+    std::vector<std::string> warnings;
+    std::string summary() const;
+};
+
+// `geo_mmdb` may be empty (no database: every client is {0,"XX"}, http_listener.rs:156).
+bool compile_program(Model& model, const CompileOptions& opt, const std::vector<uint8_t>& geo_mmdb, HostProgram* out,
+                     std::string& err);
+
+// lists (pingoo/lists.rs:62-113)
+bool parse_list_csv(const std::string& name, ListType type, const uint8_t* csv, size_t len, ListData* out, std::string& err);
+bool parse_ip_network(const std::string& s, IpNet* out, std::string& err);
+
+// LPM construction (lpm.cpp)
+bool build_lpm(const std::vector<std::vector<IpNet>>& ip_sets, const std::vector<uint8_t>& geo_mmdb, LpmTables* out,
+               std::string& err);
+
+}  // namespace pgw

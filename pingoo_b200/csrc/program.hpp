@@ -1,0 +1,60 @@
+// Device program layout: what the host compiler hands to the CUDA kernels.
+// Plain-old-data only; included from both host C++ and .cu files.
+#pragma once
+#include <cstdint>
+
+namespace pgw {
+
+constexpr uint32_t kNoRule = 0x3FFFFFFFu;          // verdict rule index when no rule decided
+constexpr uint32_t kMaxStackDepth = 32;            // rule bytecode evaluation stack (one 32-bit register)
+constexpr uint32_t kCountryWords = 22;             // ceil(676 / 32)
+
+// verdict word = action | rule_index << 2
+enum VerdictAction : uint32_t { V_ALLOW = 0, V_BLOCK = 1, V_CAPTCHA = 2, V_BYPASS = 3 };
+
+// request flag bits (pgw_batch.flags)
+enum ReqFlags : uint8_t {
+    RF_CAPTCHA_VERIFIED = 1,  // valid __pingoo_captcha_verified cookie (http_listener.rs:222-236)
+    RF_PRE_BLOCK = 2,         // host-side gate decided "blocked" (e.g. non-ASCII user-agent, http_listener.rs:159-165,196-198)
+    RF_PRE_CAPTCHA = 4,       // captcha cookie present but invalid -> serve captcha (http_listener.rs:231-235)
+    RF_BYPASS = 8             // request is for the captcha API itself (http_listener.rs:200-204)
+};
+
+// rule bytecode (uint16): 0x0000..0x3FFF push atom, else opcode
+enum RuleOp : uint16_t { OP_NOT = 0x4000, OP_AND = 0x4001, OP_OR = 0x4002, OP_PUSH0 = 0x4003, OP_PUSH1 = 0x4004 };
+
+// one scan unit = one DFA over one string field
+struct UnitDesc {
+    uint32_t field;        // Field enum
+    uint32_t n_classes;    // row width (entries)
+    uint32_t n_states;
+    uint32_t start_state;
+    uint32_t acc_lo;       // states >= acc_lo fire accept events
+    uint32_t tbl_off;      // byte offset of uint16 trans[n_states][n_classes] in the table arena
+    uint32_t cls_off;      // byte offset of the 256-byte class map in the table arena
+    uint32_t acc_base;     // acc_idx[acc_base + (s - acc_lo)] .. [+1] -> range in acc_atoms
+    uint32_t end_base;     // end_idx[end_base + s] .. [+1] -> range in end_atoms
+    uint32_t end_any;      // 0 if no state of this DFA has end-of-input accepts (skip finalisation)
+    uint32_t field_slot;   // index among the fields that are actually scanned
+    uint32_t pad;
+};
+
+// predicates evaluated once per request outside the byte scan
+struct NsAtom {
+    uint32_t kind;     // AtomDesc::Kind
+    uint32_t atom;     // atom bit index
+    uint32_t feat;     // IntFeat
+    uint32_t op;       // CmpOp
+    int64_t cval;
+    uint32_t set_id;   // int set / ip set bit / country set
+    uint32_t pad;
+};
+
+struct LpmLeaf {
+    uint32_t asn;
+    uint16_t country;   // two ASCII bytes, first letter in the low byte
+    uint16_t pad;
+    uint32_t set_mask;  // bit i: address is inside ip set i
+};
+
+}  // namespace pgw

@@ -1,0 +1,754 @@
+// Rust-`regex` syntax subset -> AST -> Thompson NFA (see regex.hpp).
+#include "regex.hpp"
+
+#include <cstring>
+#include <functional>
+
+namespace pgw {
+
+int Nfa::add_set(const ByteSet& s) {
+    for (size_t i = 0; i < sets.size(); ++i)
+        if (sets[i] == s) return (int)i;
+    sets.push_back(s);
+    return (int)sets.size() - 1;
+}
+
+namespace {
+
+struct Flags {
+    bool i = false, m = false, s = false, U = false, u = true, x = false;
+};
+
+struct Ast {
+    enum Kind : uint8_t { EMPTY, SET, ASSERT, CONCAT, ALT, REPEAT } kind = EMPTY;
+    ByteSet set;
+    uint8_t ak = 0;
+    std::vector<int> kids;
+    int min = 0, max = -1;  // REPEAT; max -1 = unbounded
+};
+
+struct ParseFail {
+    RegexStatus st;
+    std::string msg;
+};
+
+static bool is_word_byte(unsigned c) {
+    return (c >= '0' && c <= '9') || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || c == '_';
+}
+
+static ByteSet perl_class(char k) {
+    ByteSet s;
+    switch (k) {
+        case 'd': s.set_range('0', '9'); break;
+        case 's':
+            s.set('\t'); s.set('\n'); s.set(0x0B); s.set(0x0C); s.set('\r'); s.set(' ');
+            break;
+        case 'w':
+            for (unsigned c = 0; c < 128; ++c)
+                if (is_word_byte(c)) s.set(c);
+            break;
+    }
+    return s;
+}
+
+static void fold_case(ByteSet& s) {
+    for (unsigned c = 'a'; c <= 'z'; ++c) {
+        unsigned C = c - 32;
+        if (s.test(c) || s.test(C)) { s.set(c); s.set(C); }
+    }
+}
+
+class Parser {
+  public:
+    Parser(const std::string& p, std::vector<Ast>& pool, RegexInfo* info) : p_(p), pool_(pool), info_(info) {}
+
+    int parse() {
+        Flags f;
+        int r = parse_alt(f, 0);
+        if (pos_ < p_.size()) {
+            // only an unmatched ')' can stop parse_alt at depth 0
+            fail(RX_INVALID, "unopened group");
+        }
+        return r;
+    }
+
+  private:
+    const std::string& p_;
+    std::vector<Ast>& pool_;
+    RegexInfo* info_;
+    size_t pos_ = 0;
+
+    [[noreturn]] void fail(RegexStatus st, const std::string& m) { throw ParseFail{st, m + " at offset " + std::to_string(pos_)}; }
+    bool eof() const { return pos_ >= p_.size(); }
+    unsigned char peek() const { return (unsigned char)p_[pos_]; }
+    unsigned char peek_at(size_t k) const { return pos_ + k < p_.size() ? (unsigned char)p_[pos_ + k] : 0; }
+
+    int mk(Ast::Kind k) {
+        pool_.emplace_back();
+        pool_.back().kind = k;
+        return (int)pool_.size() - 1;
+    }
+    int mk_set(ByteSet s, const Flags& f) {
+        if (f.i) fold_case(s);
+        int n = mk(Ast::SET);
+        pool_[n].set = s;
+        return n;
+    }
+    int mk_byte(unsigned c, const Flags& f) {
+        ByteSet s;
+        s.set(c);
+        return mk_set(s, f);
+    }
+    int mk_assert(AssertKind a) {
+        int n = mk(Ast::ASSERT);
+        pool_[n].ak = a;
+        if (a == A_WORD_B || a == A_NOT_WORD_B) info_->uses_word_boundary = true;
+        if (a == A_BOL_LINE || a == A_EOL_LINE) info_->uses_multiline = true;
+        if (a == A_BOL_TEXT || a == A_BOL_LINE) info_->uses_bol = true;
+        return n;
+    }
+    // A code point as a literal: ASCII -> one byte set; otherwise its UTF-8 bytes in sequence.
+    int mk_codepoint(uint32_t cp, const Flags& f) {
+        if (cp < 0x80) return mk_byte(cp, f);
+        if (cp > 0x10FFFF || (cp >= 0xD800 && cp <= 0xDFFF)) fail(RX_INVALID, "invalid code point");
+        unsigned char b[4];
+        int n;
+        if (cp < 0x800) { b[0] = 0xC0 | (cp >> 6); b[1] = 0x80 | (cp & 63); n = 2; }
+        else if (cp < 0x10000) { b[0] = 0xE0 | (cp >> 12); b[1] = 0x80 | ((cp >> 6) & 63); b[2] = 0x80 | (cp & 63); n = 3; }
+        else { b[0] = 0xF0 | (cp >> 18); b[1] = 0x80 | ((cp >> 12) & 63); b[2] = 0x80 | ((cp >> 6) & 63); b[3] = 0x80 | (cp & 63); n = 4; }
+        int c = mk(Ast::CONCAT);
+        Flags nf = f;
+        nf.i = false;  // non-ASCII case folding is out of scope (ASCII haystacks)
+        for (int k = 0; k < n; ++k) {
+            int leaf = mk_byte(b[k], nf);
+            pool_[c].kids.push_back(leaf);
+        }
+        return c;
+    }
+
+    void skip_ws(const Flags& f) {
+        if (!f.x) return;
+        while (!eof()) {
+            unsigned char c = peek();
+            if (c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == 0x0B || c == 0x0C) { ++pos_; continue; }
+            if (c == '#') {
+                while (!eof() && peek() != '\n') ++pos_;
+                continue;
+            }
+            break;
+        }
+    }
+
+    // alternation := concat ('|' concat)*   (stops at ')' or end)
+    int parse_alt(Flags& f, int depth) {
+        std::vector<int> branches;
+        branches.push_back(parse_concat(f, depth));
+        while (!eof() && peek() == '|') {
+            ++pos_;
+            branches.push_back(parse_concat(f, depth));
+        }
+        if (branches.size() == 1) return branches[0];
+        int a = mk(Ast::ALT);
+        pool_[a].kids = branches;
+        return a;
+    }
+
+    int parse_concat(Flags& f, int depth) {
+        std::vector<int> items;
+        for (;;) {
+            skip_ws(f);
+            if (eof()) break;
+            unsigned char c = peek();
+            if (c == '|') break;
+            if (c == ')') {
+                if (depth == 0) fail(RX_INVALID, "unopened group");
+                break;
+            }
+            if (c == '*' || c == '+' || c == '?' || c == '{') {
+                if (items.empty()) fail(RX_INVALID, "repetition operator missing expression");
+                int child = items.back();
+                int rep = parse_repeat_op(child, f);
+                items.back() = rep;
+                continue;
+            }
+            int atom = parse_atom(f, depth);
+            if (atom >= 0) items.push_back(atom);
+        }
+        if (items.empty()) return mk(Ast::EMPTY);
+        if (items.size() == 1) return items[0];
+        int cnode = mk(Ast::CONCAT);
+        pool_[cnode].kids = items;
+        return cnode;
+    }
+
+    bool parse_decimal(int* out) {
+        size_t st = pos_;
+        long v = 0;
+        while (!eof() && peek() >= '0' && peek() <= '9') {
+            v = v * 10 + (peek() - '0');
+            if (v > 100000000) fail(RX_INVALID, "repetition count too large");
+            ++pos_;
+        }
+        if (pos_ == st) return false;
+        *out = (int)v;
+        return true;
+    }
+    void skip_sp() {
+        while (!eof() && peek() == ' ') ++pos_;
+    }
+
+    int parse_repeat_op(int child, const Flags& f) {
+        int mn = 0, mx = -1;
+        unsigned char c = peek();
+        ++pos_;
+        if (c == '*') { mn = 0; mx = -1; }
+        else if (c == '+') { mn = 1; mx = -1; }
+        else if (c == '?') { mn = 0; mx = 1; }
+        else {  // '{'
+            skip_sp();
+            if (!parse_decimal(&mn)) fail(RX_INVALID, "repetition quantifier expects a valid decimal");
+            skip_sp();
+            if (eof()) fail(RX_INVALID, "unclosed counted repetition");
+            if (peek() == ',') {
+                ++pos_;
+                skip_sp();
+                if (eof()) fail(RX_INVALID, "unclosed counted repetition");
+                if (peek() == '}') mx = -1;
+                else if (!parse_decimal(&mx)) fail(RX_INVALID, "repetition quantifier expects a valid decimal");
+                skip_sp();
+            } else {
+                mx = mn;
+            }
+            if (eof() || peek() != '}') fail(RX_INVALID, "unclosed counted repetition");
+            ++pos_;
+            if (mx >= 0 && mx < mn) fail(RX_INVALID, "invalid repetition count range");
+        }
+        // lazy suffix: irrelevant for match existence
+        if (!eof() && peek() == '?') ++pos_;
+        (void)f;
+        int r = mk(Ast::REPEAT);
+        pool_[r].kids.push_back(child);
+        pool_[r].min = mn;
+        pool_[r].max = mx;
+        return r;
+    }
+
+    static int hexval(unsigned char c) {
+        if (c >= '0' && c <= '9') return c - '0';
+        if (c >= 'a' && c <= 'f') return c - 'a' + 10;
+        if (c >= 'A' && c <= 'F') return c - 'A' + 10;
+        return -1;
+    }
+
+    // after "\x" / "\u" / "\U": returns code point
+    uint32_t parse_hex(unsigned char kind) {
+        if (!eof() && peek() == '{') {
+            ++pos_;
+            uint32_t v = 0;
+            int nd = 0;
+            while (!eof() && peek() != '}') {
+                int h = hexval(peek());
+                if (h < 0) fail(RX_INVALID, "invalid hexadecimal digit");
+                v = v * 16 + h;
+                if (++nd > 8) fail(RX_INVALID, "hexadecimal literal too long");
+                ++pos_;
+            }
+            if (eof()) fail(RX_INVALID, "unclosed hexadecimal literal");
+            ++pos_;
+            if (nd == 0) fail(RX_INVALID, "empty hexadecimal literal");
+            return v;
+        }
+        int want = kind == 'x' ? 2 : kind == 'u' ? 4 : 8;
+        uint32_t v = 0;
+        for (int k = 0; k < want; ++k) {
+            if (eof()) fail(RX_INVALID, "incomplete hexadecimal literal");
+            int h = hexval(peek());
+            if (h < 0) fail(RX_INVALID, "invalid hexadecimal digit");
+            v = v * 16 + h;
+            ++pos_;
+        }
+        return v;
+    }
+
+    // Escape outcomes
+    struct Esc {
+        enum { LITERAL, CLASS, ASSERTION } kind;
+        uint32_t cp = 0;
+        ByteSet set;
+        AssertKind ak = A_WORD_B;
+    };
+
+    // pos_ is just past the backslash
+    Esc parse_escape(bool in_class, const Flags& f) {
+        if (eof()) fail(RX_INVALID, "incomplete escape sequence");
+        unsigned char c = peek();
+        ++pos_;
+        Esc e;
+        e.kind = Esc::LITERAL;
+        switch (c) {
+            case 'd': case 's': case 'w':
+                e.kind = Esc::CLASS; e.set = perl_class((char)c); return e;
+            case 'D': case 'S': case 'W':
+                e.kind = Esc::CLASS; e.set = perl_class((char)(c + 32)); e.set.negate(); return e;
+            case 'n': e.cp = '\n'; return e;
+            case 't': e.cp = '\t'; return e;
+            case 'r': e.cp = '\r'; return e;
+            case 'a': e.cp = 0x07; return e;
+            case 'f': e.cp = 0x0C; return e;
+            case 'v': e.cp = 0x0B; return e;
+            case 'x': case 'u': case 'U': e.cp = parse_hex(c); return e;
+            case 'p': case 'P': fail(RX_UNSUPPORTED, "Unicode classes (\\p) are not supported");
+            case 'A':
+                if (in_class) fail(RX_INVALID, "unrecognized escape sequence in class");
+                e.kind = Esc::ASSERTION; e.ak = A_BOL_TEXT; return e;
+            case 'z':
+                if (in_class) fail(RX_INVALID, "unrecognized escape sequence in class");
+                e.kind = Esc::ASSERTION; e.ak = A_EOL_TEXT; return e;
+            case 'b':
+                if (in_class) fail(RX_INVALID, "unrecognized escape sequence in class");
+                if (!eof() && peek() == '{') {
+                    // \b{start}, \b{end}, ... (regex >= 1.10); a literal `\b{` repetition is invalid anyway
+                    fail(RX_UNSUPPORTED, "\\b{...} word-boundary forms are not supported");
+                }
+                e.kind = Esc::ASSERTION; e.ak = A_WORD_B; return e;
+            case 'B':
+                if (in_class) fail(RX_INVALID, "unrecognized escape sequence in class");
+                e.kind = Esc::ASSERTION; e.ak = A_NOT_WORD_B; return e;
+            case '<': case '>':
+                fail(RX_UNSUPPORTED, "\\< and \\> word boundaries are not supported");
+            case ' ':
+                if (f.x) { e.cp = ' '; return e; }
+                fail(RX_INVALID, "unrecognized escape sequence");
+            default: break;
+        }
+        if (c >= '0' && c <= '9') fail(RX_INVALID, "backreferences are not supported");
+        if (c < 0x80 && !((c >= '0' && c <= '9') || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z')) && c > 0x20 && c != 0x7F) {
+            e.cp = c;  // escaped punctuation
+            return e;
+        }
+        fail(RX_INVALID, "unrecognized escape sequence");
+    }
+
+    static bool posix_class(const std::string& name, ByteSet* out) {
+        ByteSet s;
+        if (name == "alnum") { s.set_range('0', '9'); s.set_range('A', 'Z'); s.set_range('a', 'z'); }
+        else if (name == "alpha") { s.set_range('A', 'Z'); s.set_range('a', 'z'); }
+        else if (name == "ascii") { s.set_range(0, 127); }
+        else if (name == "blank") { s.set(' '); s.set('\t'); }
+        else if (name == "cntrl") { s.set_range(0, 31); s.set(127); }
+        else if (name == "digit") { s.set_range('0', '9'); }
+        else if (name == "graph") { s.set_range('!', '~'); }
+        else if (name == "lower") { s.set_range('a', 'z'); }
+        else if (name == "print") { s.set_range(' ', '~'); }
+        else if (name == "punct") { s.set_range('!', '/'); s.set_range(':', '@'); s.set_range('[', '`'); s.set_range('{', '~'); }
+        else if (name == "space") { s.set('\t'); s.set('\n'); s.set(0x0B); s.set(0x0C); s.set('\r'); s.set(' '); }
+        else if (name == "upper") { s.set_range('A', 'Z'); }
+        else if (name == "word") { s.set_range('0', '9'); s.set_range('A', 'Z'); s.set_range('a', 'z'); s.set('_'); }
+        else if (name == "xdigit") { s.set_range('0', '9'); s.set_range('A', 'F'); s.set_range('a', 'f'); }
+        else return false;
+        *out = s;
+        return true;
+    }
+
+    void skip_class_ws(const Flags& f) {
+        if (!f.x) return;
+        while (!eof()) {
+            unsigned char c = peek();
+            if (c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == 0x0B || c == 0x0C) ++pos_;
+            else break;
+        }
+    }
+
+    // one class "atom" that can be a range endpoint: returns code point; or a whole set
+    // returns true if *set_out filled (not usable as endpoint)
+    bool parse_class_item(const Flags& f, uint32_t* cp, ByteSet* set_out) {
+        unsigned char c = peek();
+        if (c == '[') {
+            // POSIX class or nested class
+            if (peek_at(1) == ':') {
+                size_t save = pos_;
+                pos_ += 2;
+                bool neg = false;
+                if (!eof() && peek() == '^') { neg = true; ++pos_; }
+                size_t st = pos_;
+                while (!eof() && peek() != ':' && peek() != ']') ++pos_;
+                if (!eof() && peek() == ':' && peek_at(1) == ']') {
+                    std::string name = p_.substr(st, pos_ - st);
+                    ByteSet s;
+                    if (posix_class(name, &s)) {
+                        pos_ += 2;
+                        if (neg) s.negate();
+                        *set_out = s;
+                        return true;
+                    }
+                }
+                pos_ = save;  // not a POSIX class: treat as nested class
+            }
+            ++pos_;
+            *set_out = parse_class_body(f);
+            return true;
+        }
+        if (c == '\\') {
+            ++pos_;
+            Esc e = parse_escape(true, f);
+            if (e.kind == Esc::CLASS) { *set_out = e.set; return true; }
+            *cp = e.cp;
+            return false;
+        }
+        // plain literal: may be a multi-byte UTF-8 char in the pattern
+        if (c < 0x80) { ++pos_; *cp = c; return false; }
+        int n = (c >= 0xF0) ? 4 : (c >= 0xE0) ? 3 : (c >= 0xC0) ? 2 : 0;
+        if (n == 0 || pos_ + n > p_.size()) fail(RX_INVALID, "invalid UTF-8 in pattern");
+        uint32_t v = c & (0xFF >> (n + 1));
+        for (int k = 1; k < n; ++k) {
+            unsigned char cc = (unsigned char)p_[pos_ + k];
+            if ((cc & 0xC0) != 0x80) fail(RX_INVALID, "invalid UTF-8 in pattern");
+            v = (v << 6) | (cc & 63);
+        }
+        pos_ += n;
+        *cp = v;
+        return false;
+    }
+
+    // union of items until a set operator or ']' ; pos_ after '[' (and after '^' handled by caller)
+    ByteSet parse_class_union(const Flags& f, bool first_item_allowed_bracket) {
+        ByteSet acc;
+        bool first = first_item_allowed_bracket;
+        for (;;) {
+            skip_class_ws(f);
+            if (eof()) fail(RX_INVALID, "unclosed character class");
+            unsigned char c = peek();
+            if (c == ']' && !first) break;
+            if ((c == '&' && peek_at(1) == '&') || (c == '-' && peek_at(1) == '-') || (c == '~' && peek_at(1) == '~')) break;
+            uint32_t lo = 0;
+            ByteSet sub;
+            bool is_set;
+            if (c == ']' && first) { ++pos_; lo = ']'; is_set = false; }
+            else if (c == '-' ) { ++pos_; lo = '-'; is_set = false; }
+            else is_set = parse_class_item(f, &lo, &sub);
+            first = false;
+            if (is_set) { acc.or_with(sub); continue; }
+            // range?
+            skip_class_ws(f);
+            if (!eof() && peek() == '-' && peek_at(1) != ']' && peek_at(1) != 0 && !(peek_at(1) == '-')) {
+                size_t save = pos_;
+                ++pos_;
+                skip_class_ws(f);
+                if (eof()) fail(RX_INVALID, "unclosed character class");
+                uint32_t hi = 0;
+                ByteSet sub2;
+                bool hs;
+                if (peek() == '[') { hs = true; }
+                else hs = parse_class_item(f, &hi, &sub2);
+                if (hs) {
+                    // "a-[" or "a-\d": Rust rejects a class as a range endpoint
+                    (void)save;
+                    fail(RX_INVALID, "invalid character class range");
+                }
+                if (hi < lo) fail(RX_INVALID, "invalid character class range");
+                for (uint32_t v = lo; v <= hi && v < 0x80; ++v) acc.set(v);
+                continue;
+            }
+            if (lo < 0x80) acc.set(lo);
+            // non-ASCII single members never match an ASCII haystack: dropped
+        }
+        return acc;
+    }
+
+    // pos_ just after '['; consumes through the closing ']'
+    ByteSet parse_class_body(const Flags& f) {
+        bool neg = false;
+        if (!eof() && peek() == '^') { neg = true; ++pos_; }
+        ByteSet acc = parse_class_union(f, true);
+        for (;;) {
+            if (eof()) fail(RX_INVALID, "unclosed character class");
+            unsigned char c = peek();
+            if (c == ']') { ++pos_; break; }
+            unsigned char op = c;  // && -- ~~
+            pos_ += 2;
+            ByteSet rhs = parse_class_union(f, false);
+            if (op == '&') { for (int k = 0; k < 4; ++k) acc.w[k] &= rhs.w[k]; }
+            else if (op == '-') { for (int k = 0; k < 4; ++k) acc.w[k] &= ~rhs.w[k]; }
+            else { for (int k = 0; k < 4; ++k) acc.w[k] ^= rhs.w[k]; }
+        }
+        // positive sets are ASCII-only by construction (bytes >= 0x80 appear only through negation)
+        ByteSet ascii;
+        ascii.set_range(0, 127);
+        for (int k = 0; k < 4; ++k) acc.w[k] &= ascii.w[k];
+        if (f.i) fold_case(acc);
+        if (neg) acc.negate();
+        return acc;
+    }
+
+    void parse_flags(Flags& f, bool* scoped) {
+        // pos_ after "(?" ; parses flags up to ')' or ':'
+        bool negate = false, any = false;
+        for (;;) {
+            if (eof()) fail(RX_INVALID, "unclosed group");
+            unsigned char c = peek();
+            if (c == ')' || c == ':') {
+                if (!any) fail(RX_INVALID, "missing flags");
+                *scoped = (c == ':');
+                ++pos_;
+                return;
+            }
+            ++pos_;
+            if (c == '-') {
+                if (negate) fail(RX_INVALID, "repeated flag negation");
+                negate = true;
+                any = false;
+                continue;
+            }
+            bool v = !negate;
+            switch (c) {
+                case 'i': f.i = v; break;
+                case 'm': f.m = v; break;
+                case 's': f.s = v; break;
+                case 'U': f.U = v; break;
+                case 'u': f.u = v; break;
+                case 'x': f.x = v; break;
+                case 'R': fail(RX_UNSUPPORTED, "CRLF mode (?R) is not supported");
+                default: fail(RX_INVALID, "unrecognized flag");
+            }
+            any = true;
+        }
+    }
+
+    // returns AST index, or -1 if the atom produced nothing (a bare flags group)
+    int parse_atom(Flags& f, int depth) {
+        unsigned char c = peek();
+        switch (c) {
+            case '(': {
+                ++pos_;
+                Flags inner = f;
+                if (!eof() && peek() == '?') {
+                    ++pos_;
+                    if (eof()) fail(RX_INVALID, "unclosed group");
+                    unsigned char d = peek();
+                    if (d == 'P' || d == '<') {
+                        // named group (?P<name>..) / (?<name>..); look-behind (?<= (?<! is rejected
+                        if (d == 'P') {
+                            ++pos_;
+                            if (eof() || peek() != '<') fail(RX_INVALID, "invalid named group");
+                        } else if (peek_at(1) == '=' || peek_at(1) == '!') {
+                            fail(RX_INVALID, "look-around is not supported");
+                        }
+                        ++pos_;
+                        size_t st = pos_;
+                        while (!eof() && peek() != '>') ++pos_;
+                        if (eof() || pos_ == st) fail(RX_INVALID, "invalid capture group name");
+                        ++pos_;
+                    } else if (d == '=' || d == '!') {
+                        fail(RX_INVALID, "look-around is not supported");
+                    } else {
+                        bool scoped = false;
+                        parse_flags(inner, &scoped);
+                        if (!scoped) {
+                            f = inner;  // (?flags) applies to the rest of the enclosing group
+                            return -1;
+                        }
+                    }
+                }
+                if (depth > 200) fail(RX_INVALID, "nesting too deep");
+                int r = parse_alt(inner, depth + 1);
+                if (eof() || peek() != ')') fail(RX_INVALID, "unclosed group");
+                ++pos_;
+                return r;
+            }
+            case '[': {
+                ++pos_;
+                ByteSet s = parse_class_body(f);
+                int n = mk(Ast::SET);
+                pool_[n].set = s;  // folding/negation already applied
+                return n;
+            }
+            case '.': {
+                ++pos_;
+                ByteSet s;
+                s.negate();  // everything
+                if (!f.s) { ByteSet nl; nl.set('\n'); for (int k = 0; k < 4; ++k) s.w[k] &= ~nl.w[k]; }
+                int n = mk(Ast::SET);
+                pool_[n].set = s;
+                return n;
+            }
+            case '^': ++pos_; return mk_assert(f.m ? A_BOL_LINE : A_BOL_TEXT);
+            case '$': ++pos_; return mk_assert(f.m ? A_EOL_LINE : A_EOL_TEXT);
+            case '\\': {
+                ++pos_;
+                Esc e = parse_escape(false, f);
+                if (e.kind == Esc::ASSERTION) return mk_assert(e.ak);
+                if (e.kind == Esc::CLASS) {
+                    // Perl classes are not affected by (?i) (already case-closed); keep bytes >= 0x80 of negations
+                    int n = mk(Ast::SET);
+                    pool_[n].set = e.set;
+                    return n;
+                }
+                return mk_codepoint(e.cp, f);
+            }
+            default: break;
+        }
+        if (c < 0x80) { ++pos_; return mk_byte(c, f); }
+        // literal non-ASCII char in the pattern
+        uint32_t cp = 0;
+        ByteSet dummy;
+        parse_class_item(f, &cp, &dummy);
+        return mk_codepoint(cp, f);
+    }
+};
+
+static bool nullable_no_assert(const std::vector<Ast>& pool, int n) {
+    const Ast& a = pool[n];
+    switch (a.kind) {
+        case Ast::EMPTY: return true;
+        case Ast::SET: return false;
+        case Ast::ASSERT: return false;
+        case Ast::CONCAT:
+            for (int k : a.kids) if (!nullable_no_assert(pool, k)) return false;
+            return true;
+        case Ast::ALT:
+            for (int k : a.kids) if (nullable_no_assert(pool, k)) return true;
+            return false;
+        case Ast::REPEAT: return a.min == 0 || nullable_no_assert(pool, a.kids[0]);
+    }
+    return false;
+}
+
+struct Emitter {
+    Nfa& nfa;
+    const std::vector<Ast>& pool;
+    size_t base;
+    int node(NfaKind k) {
+        if (nfa.nodes.size() - base > (size_t)kMaxNfaNodesPerPattern) throw ParseFail{RX_TOO_BIG, "compiled regex exceeds size limit"};
+        NfaNode n;
+        n.kind = k;
+        nfa.nodes.push_back(n);
+        return (int)nfa.nodes.size() - 1;
+    }
+    // emit `a` so that it continues to `next`; returns entry node
+    int emit(int a, int next) {
+        const Ast& A = pool[a];
+        switch (A.kind) {
+            case Ast::EMPTY: return next;
+            case Ast::SET: {
+                int n = node(N_CHAR);
+                nfa.nodes[n].set = nfa.add_set(A.set);
+                nfa.nodes[n].out = next;
+                return n;
+            }
+            case Ast::ASSERT: {
+                int n = node(N_ASSERT);
+                nfa.nodes[n].assert_kind = A.ak;
+                nfa.nodes[n].out = next;
+                return n;
+            }
+            case Ast::CONCAT: {
+                int cur = next;
+                for (size_t k = A.kids.size(); k-- > 0;) cur = emit(A.kids[k], cur);
+                return cur;
+            }
+            case Ast::ALT: {
+                // chain of splits
+                int entry = -1;
+                int prev_split = -1;
+                for (size_t k = 0; k < A.kids.size(); ++k) {
+                    int br = emit(A.kids[k], next);
+                    if (k + 1 == A.kids.size()) {
+                        if (prev_split >= 0) nfa.nodes[prev_split].out1 = br;
+                        else entry = br;
+                    } else {
+                        int s = node(N_SPLIT);
+                        nfa.nodes[s].out = br;
+                        if (prev_split >= 0) nfa.nodes[prev_split].out1 = s;
+                        else entry = s;
+                        prev_split = s;
+                    }
+                }
+                return entry;
+            }
+            case Ast::REPEAT: {
+                int child = A.kids[0];
+                int tail = next;
+                if (A.max < 0) {
+                    // x* loop
+                    int s = node(N_SPLIT);
+                    int body = emit(child, s);
+                    nfa.nodes[s].out = body;
+                    nfa.nodes[s].out1 = next;
+                    tail = s;
+                } else {
+                    for (int k = 0; k < A.max - A.min; ++k) {
+                        int s = node(N_SPLIT);
+                        int body = emit(child, tail);
+                        nfa.nodes[s].out = body;
+                        nfa.nodes[s].out1 = next;
+                        tail = s;
+                    }
+                }
+                int cur = tail;
+                for (int k = 0; k < A.min; ++k) cur = emit(child, cur);
+                return cur;
+            }
+        }
+        return next;
+    }
+};
+
+}  // namespace
+
+RegexStatus regex_compile(const std::string& pattern, int pattern_id, Nfa& nfa, int* start, RegexInfo* info,
+                          std::string& err) {
+    std::vector<Ast> pool;
+    RegexInfo local;
+    size_t nodes0 = nfa.nodes.size(), sets0 = nfa.sets.size();
+    try {
+        Parser p(pattern, pool, &local);
+        int root = p.parse();
+        local.always_true = nullable_no_assert(pool, root);
+        Emitter em{nfa, pool, nodes0};
+        int m = em.node(N_MATCH);
+        nfa.nodes[m].pattern = pattern_id;
+        *start = em.emit(root, m);
+    } catch (const ParseFail& f) {
+        nfa.nodes.resize(nodes0);
+        nfa.sets.resize(sets0);
+        err = f.msg;
+        return f.st;
+    }
+    if (info) *info = local;
+    return RX_OK;
+}
+
+int nfa_literal(Nfa& nfa, const std::string& lit, bool anchor_start, bool anchor_end, int pattern_id) {
+    auto add = [&](NfaKind k) {
+        NfaNode n;
+        n.kind = k;
+        nfa.nodes.push_back(n);
+        return (int)nfa.nodes.size() - 1;
+    };
+    int m = add(N_MATCH);
+    nfa.nodes[m].pattern = pattern_id;
+    int cur = m;
+    if (anchor_end) {
+        int a = add(N_ASSERT);
+        nfa.nodes[a].assert_kind = A_EOL_TEXT;
+        nfa.nodes[a].out = cur;
+        cur = a;
+    }
+    for (size_t k = lit.size(); k-- > 0;) {
+        ByteSet s;
+        s.set((unsigned char)lit[k]);
+        int n = add(N_CHAR);
+        nfa.nodes[n].set = nfa.add_set(s);
+        nfa.nodes[n].out = cur;
+        cur = n;
+    }
+    if (anchor_start) {
+        int a = add(N_ASSERT);
+        nfa.nodes[a].assert_kind = A_BOL_TEXT;
+        nfa.nodes[a].out = cur;
+        cur = a;
+    }
+    return cur;
+}
+
+}  // namespace pgw

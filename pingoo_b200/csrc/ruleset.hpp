@@ -1,0 +1,44 @@
+// Host-side ruleset assembly shared by the CUDA C-ABI (capi.cu) and the
+// test-only program simulator: parse rules, collect lists / GeoIP, compile.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "compile.hpp"
+
+namespace pgw {
+
+struct RuleSource {
+    std::string name;
+    bool has_expression = false;
+    std::string expression;
+    std::vector<uint8_t> actions;
+    ExprP ast;
+};
+
+class RulesetBuilder {
+  public:
+    CompileOptions options;
+
+    // rules::compile_expression (rules/rules.rs:45-53): syntax check only
+    static bool compile_expression(const std::string& src, std::string& err, ExprP* ast = nullptr);
+    // rules::validate_expression (rules/rules.rs:55-77)
+    static bool validate_expression(const std::string& src, std::string& err);
+
+    // config.rs:255-269: a rule whose expression does not compile is a fatal configuration error
+    bool add_rule(const char* name, const char* expression, const uint8_t* actions, uint32_t n_actions, std::string& err);
+    bool add_list(const char* name, int type, const uint8_t* csv, size_t len, std::string& err);
+    bool load_geoip(const uint8_t* mmdb, size_t len, std::string& err);
+    bool finalize(HostProgram* out, std::string& err);
+
+    size_t n_rules() const { return rules_.size(); }
+
+  private:
+    std::vector<RuleSource> rules_;
+    Model model_;
+    std::vector<uint8_t> mmdb_;
+    bool finalized_ = false;
+};
+
+}  // namespace pgw

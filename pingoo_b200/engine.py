@@ -1,0 +1,127 @@
+"""WafEngine: the batched replacement for the per-request rule loop.
+
+Mirrors, for a batch, what the reference does per request:
+  lists  = load_lists(config.lists)                        pingoo/lists.rs:48-60
+  geoip  = GeoipDB::load()                                 pingoo/geoip.rs:44-71
+  rules  = config.rules (compile_expression each)          pingoo/config/config.rs:255-269
+  for rule in rules: rule.match_request(ctx) -> actions    pingoo/listeners/http_listener.rs:251-264
+All evaluation happens in CUDA kernels behind the C ABI (include/pingoo_waf.h).
+"""
+import ctypes as C
+from typing import Dict, Iterable, Optional, Tuple
+
+import numpy as np
+
+from . import _ffi
+from .batch import FIELDS, RequestBatch
+from .rules import Error, ListType, Rule
+
+
+class WafEngine:
+    def __init__(self, rules: Iterable[Rule], lists: Optional[Dict[str, Tuple[ListType, bytes]]] = None,
+                 geoip_mmdb: Optional[bytes] = None, device: int = 0, eval_gates: bool = True,
+                 max_dfa_states: int = 0, max_unit_table_bytes: int = 0):
+        self._lib = _ffi.load()
+        self._h = C.c_void_p()
+        self.rules = list(rules)
+        descs = (_ffi.RuleDesc * max(1, len(self.rules)))()
+        self._keep = []
+        for i, r in enumerate(self.rules):
+            acts = (C.c_uint8 * max(1, len(r.actions)))(*[int(a) for a in r.actions])
+            self._keep.append(acts)
+            descs[i].name = r.name.encode()
+            descs[i].expression = None if r.expression is None else r.expression.encode()
+            descs[i].actions = C.cast(acts, C.POINTER(C.c_uint8))
+            descs[i].n_actions = len(r.actions)
+        opt = _ffi.Options(max_dfa_states, max_unit_table_bytes, 1 if eval_gates else 0)
+        err = C.create_string_buffer(1024)
+        if self._lib.pgw_ruleset_create(descs, len(self.rules), C.byref(opt), C.byref(self._h), err, len(err)):
+            raise Error(err.value.decode(errors="replace"))
+        for name, (ltype, csv) in (lists or {}).items():
+            if self._lib.pgw_lists_add(self._h, name.encode(), int(ltype), csv, len(csv), err, len(err)):
+                msg = err.value.decode(errors="replace")
+                self.close()
+                raise Error(msg)
+        if geoip_mmdb is not None:
+            if self._lib.pgw_geoip_load(self._h, geoip_mmdb, len(geoip_mmdb), err, len(err)):
+                msg = err.value.decode(errors="replace")
+                self.close()
+                raise Error(msg)
+        if self._lib.pgw_ruleset_finalize(self._h, device, err, len(err)):
+            msg = err.value.decode(errors="replace")
+            self.close()
+            raise Error(msg)
+        self.device = device
+
+    # ---- lifecycle ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.pgw_ruleset_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> _ffi.Info:
+        i = _ffi.Info()
+        self._lib.pgw_ruleset_info(self._h, C.byref(i))
+        return i
+
+    def describe(self) -> str:
+        n = self._lib.pgw_ruleset_describe(self._h, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        self._lib.pgw_ruleset_describe(self._h, buf, n + 1)
+        return buf.value.decode(errors="replace")
+
+    # ---- evaluation --------------------------------------------------------------------------
+    def evaluate_host(self, batch: RequestBatch) -> np.ndarray:
+        """Host columns in, host verdicts out (H2D + kernel + D2H inside the call)."""
+        out = np.empty(batch.n, dtype=np.uint32)
+        cb = batch.as_ctypes()
+        if self._lib.pgw_evaluate_batch_host(self._h, C.byref(cb), out.ctypes.data):
+            raise Error(self._lib.pgw_last_error().decode(errors="replace"))
+        return out
+
+    def to_device(self, batch: RequestBatch):
+        """Copy a host batch into torch CUDA tensors; returns (tensors, pgw_batch of device pointers)."""
+        import torch
+
+        dev = torch.device("cuda", self.device)
+        t = {}
+        cb = _ffi.Batch()
+        cb.n = batch.n
+        for f in FIELDS:
+            by, of = batch.cols[f]
+            t[f + "_b"] = torch.from_numpy(by).to(dev)
+            t[f + "_o"] = torch.from_numpy(of.view(np.int32)).to(dev)
+            sc = getattr(cb, f)
+            sc.bytes = t[f + "_b"].data_ptr()
+            sc.offsets = t[f + "_o"].data_ptr()
+        for name, arr, view in (("ip", batch.ip, None), ("ip_is_v6", batch.ip_is_v6, None), ("remote_port", batch.remote_port, None),
+                                ("asn", batch.asn, None), ("country", batch.country, np.int16), ("flags", batch.flags, None)):
+            if arr is None:
+                setattr(cb, name, None)
+                continue
+            a = arr if view is None else arr.view(view)
+            t[name] = torch.from_numpy(a).to(dev)
+            setattr(cb, name, t[name].data_ptr())
+        return t, cb
+
+    def evaluate_device(self, cbatch: _ffi.Batch, verdict_tensor, stream: int = 0):
+        """Enqueue the kernel on `stream` (cudaStream_t handle) for device-resident columns."""
+        if self._lib.pgw_evaluate_batch(self._h, C.byref(cbatch), verdict_tensor.data_ptr(), stream):
+            raise Error(self._lib.pgw_last_error().decode(errors="replace"))
+
+    def geoip_lookup_device(self, ip_t, v6_t, asn_t, cc_t, stream: int = 0):
+        n = ip_t.shape[0]
+        if self._lib.pgw_geoip_lookup_batch(self._h, ip_t.data_ptr(), v6_t.data_ptr(), n, asn_t.data_ptr(), cc_t.data_ptr(), stream):
+            raise Error(self._lib.pgw_last_error().decode(errors="replace"))
+
+
+def decode_verdict(v: int):
+    """(action, rule_index or None) from a verdict word."""
+    rule = int(v) >> 2
+    return int(v) & 3, (None if rule == _ffi.NO_RULE else rule)

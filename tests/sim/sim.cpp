@@ -1,0 +1,279 @@
+// TEST-ONLY: CPU walk over the compiled device program (HostProgram).
+//
+// This is not a product path and not the oracle.  It executes, on the CPU and
+// without CUDA, exactly the tables the host compiler would upload (DFAs, accept
+// lists, rule bytecode, candidate indexes, LPM tables), mirroring the kernel's
+// logic step by step.  `-m "not gpu"` tests use it to check the *compiler*
+// against the oracle in this GPU-less container; the GPU tests then only have
+// to establish kernel == tables.  The product library never links this file.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pingoo_waf.h"
+#include "../../pingoo_b200/csrc/ruleset.hpp"
+
+using namespace pgw;
+
+namespace {
+
+struct Sim {
+    RulesetBuilder builder;
+    HostProgram H;
+    bool finalized = false;
+    std::string last_error;
+};
+
+int fail(Sim* s, const std::string& m, char* err, size_t cap) {
+    if (s) s->last_error = m;
+    if (err && cap) {
+        size_t n = m.size() < cap - 1 ? m.size() : cap - 1;
+        memcpy(err, m.data(), n);
+        err[n] = 0;
+    }
+    return 1;
+}
+
+bool eval_rule(const HostProgram& H, uint32_t rule, const std::vector<uint32_t>& row) {
+    uint32_t st = 0;
+    for (uint32_t i = H.rule_off[rule]; i < H.rule_off[rule + 1]; ++i) {
+        uint32_t op = H.code[i];
+        if (op < 0x4000u) st = (st << 1) | ((row[op >> 5] >> (op & 31)) & 1u);
+        else if (op == OP_NOT) st ^= 1u;
+        else if (op == OP_AND) st = ((st >> 1) & ~1u) | (st & (st >> 1) & 1u);
+        else if (op == OP_OR) st = ((st >> 1) & ~1u) | ((st | (st >> 1)) & 1u);
+        else if (op == OP_PUSH0) st <<= 1;
+        else st = (st << 1) | 1u;
+    }
+    return st & 1u;
+}
+
+uint32_t lpm_lookup(const LpmTables& T, const uint8_t* ip16, bool v6) {
+    if (!v6) {
+        uint32_t a = (uint32_t)ip16[0] << 24 | (uint32_t)ip16[1] << 16 | (uint32_t)ip16[2] << 8 | ip16[3];
+        uint32_t e = T.dir24[a >> 8];
+        if (e & 0x80000000u) e = T.tbl8[((size_t)(e & 0x7FFFFFFFu) << 8) + (a & 0xFF)];
+        return e;
+    }
+    uint64_t hi = 0, lo = 0;
+    for (int k = 0; k < 8; ++k) hi = (hi << 8) | ip16[k];
+    for (int k = 8; k < 16; ++k) lo = (lo << 8) | ip16[k];
+    uint32_t l = 0, r = (uint32_t)T.v6_leaf.size();
+    while (r - l > 1) {
+        uint32_t m = (l + r) >> 1;
+        bool le = T.v6_hi[m] < hi || (T.v6_hi[m] == hi && T.v6_lo[m] <= lo);
+        if (le) l = m;
+        else r = m;
+    }
+    return T.v6_leaf[l];
+}
+
+bool geo_skip(const uint8_t* ip16, bool v6) {
+    if (!v6) return ip16[0] == 127 || (ip16[0] >> 4) == 0xE;
+    if (ip16[0] == 0xFF) return true;
+    for (int k = 0; k < 15; ++k) if (ip16[k]) return false;
+    return ip16[15] == 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+void* pgwsim_create(const pgw_rule_desc* rules, uint32_t n, const pgw_options* opt, char* err, size_t cap) {
+    Sim* s = new Sim();
+    if (opt) {
+        if (opt->max_dfa_states > 0) s->builder.options.max_dfa_states = opt->max_dfa_states;
+        if (opt->max_unit_table_bytes > 0) s->builder.options.max_unit_table_bytes = (size_t)opt->max_unit_table_bytes;
+        s->builder.options.eval_gates = opt->eval_gates != 0;
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        std::string e;
+        if (!s->builder.add_rule(rules[i].name, rules[i].expression, rules[i].actions, rules[i].n_actions, e)) {
+            fail(nullptr, e, err, cap);
+            delete s;
+            return nullptr;
+        }
+    }
+    return s;
+}
+
+int pgwsim_lists_add(void* h, const char* name, int type, const uint8_t* csv, size_t len, char* err, size_t cap) {
+    Sim* s = (Sim*)h;
+    std::string e;
+    if (!s->builder.add_list(name, type, csv, len, e)) return fail(s, e, err, cap);
+    return 0;
+}
+
+int pgwsim_geoip_load(void* h, const uint8_t* mmdb, size_t len, char* err, size_t cap) {
+    Sim* s = (Sim*)h;
+    std::string e;
+    if (!s->builder.load_geoip(mmdb, len, e)) return fail(s, e, err, cap);
+    return 0;
+}
+
+int pgwsim_finalize(void* h, char* err, size_t cap) {
+    Sim* s = (Sim*)h;
+    std::string e;
+    if (!s->builder.finalize(&s->H, e)) return fail(s, e, err, cap);
+    s->finalized = true;
+    return 0;
+}
+
+size_t pgwsim_describe(void* h, char* buf, size_t cap) {
+    Sim* s = (Sim*)h;
+    std::string d = s->H.summary();
+    for (auto& w : s->H.warnings) d += "\nwarning: " + w;
+    if (buf && cap) {
+        size_t n = d.size() < cap - 1 ? d.size() : cap - 1;
+        memcpy(buf, d.data(), n);
+        buf[n] = 0;
+    }
+    return d.size();
+}
+
+// geo lookup exactly as the kernel resolves it
+int pgwsim_geoip_lookup(void* h, const uint8_t* ip, const uint8_t* is_v6, uint32_t n, uint32_t* asn, uint16_t* country) {
+    Sim* s = (Sim*)h;
+    const HostProgram& H = s->H;
+    for (uint32_t r = 0; r < n; ++r) {
+        asn[r] = 0;
+        country[r] = (uint16_t)('X' | ('X' << 8));
+        const uint8_t* ip16 = ip + (size_t)r * 16;
+        if (H.lpm.geo_loaded && !geo_skip(ip16, is_v6[r] != 0)) {
+            const LpmLeaf& lf = H.lpm.leaves[lpm_lookup(H.lpm, ip16, is_v6[r] != 0)];
+            asn[r] = lf.asn;
+            country[r] = lf.country;
+        }
+    }
+    return 0;
+}
+
+int pgwsim_evaluate(void* h, const pgw_batch* b, uint32_t* out) {
+    Sim* s = (Sim*)h;
+    if (!s->finalized) return 1;
+    const HostProgram& H = s->H;
+    const pgw_strcol* cols[5] = {&b->host, &b->url, &b->path, &b->method, &b->user_agent};
+    const uint32_t Aw = H.atom_words;
+    std::vector<uint32_t> row(Aw);
+    for (uint32_t r = 0; r < b->n; ++r) {
+        std::fill(row.begin(), row.end(), 0);
+        // scan units
+        for (const UnitDesc& u : H.units) {
+            const uint8_t* bytes = cols[u.field]->bytes;
+            uint32_t a = cols[u.field]->offsets[r], e = cols[u.field]->offsets[r + 1];
+            const uint8_t* cls = H.arena.data() + u.cls_off;
+            const uint16_t* tbl = (const uint16_t*)(H.arena.data() + u.tbl_off);
+            uint32_t st = u.start_state;
+            for (uint32_t i = a; i < e; ++i) {
+                st = tbl[st * u.n_classes + cls[bytes[i]]];
+                if (st >= u.acc_lo) {
+                    uint32_t ci = u.acc_base + st - u.acc_lo;
+                    for (uint32_t k = H.acc_idx[ci]; k < H.acc_idx[ci + 1]; ++k) row[H.acc_atoms[k] >> 5] |= 1u << (H.acc_atoms[k] & 31);
+                }
+            }
+            if (u.end_any) {
+                uint32_t ci = u.end_base + st;
+                for (uint32_t k = H.end_idx[ci]; k < H.end_idx[ci + 1]; ++k) row[H.end_atoms[k] >> 5] |= 1u << (H.end_atoms[k] & 31);
+            }
+        }
+        // per-request predicates
+        uint32_t flags = b->flags ? b->flags[r] : 0;
+        int64_t asn = 0;
+        uint32_t country = 'X' | ('X' << 8);
+        uint32_t set_mask = 0;
+        bool geo_on_device = H.lpm.geo_loaded && H.needs_geo_cols && !(b->asn && b->country);
+        if (H.needs_ip || geo_on_device) {
+            const uint8_t* ip16 = b->ip + (size_t)r * 16;
+            bool v6 = b->ip_is_v6[r] != 0;
+            const LpmLeaf& lf = H.lpm.leaves[lpm_lookup(H.lpm, ip16, v6)];
+            set_mask = lf.set_mask;
+            if (H.lpm.geo_loaded && !b->asn && !geo_skip(ip16, v6)) { asn = lf.asn; country = lf.country; }
+        }
+        if (b->asn) asn = b->asn[r];
+        if (b->country) country = b->country[r];
+        for (const NsAtom& a : H.ns_atoms) {
+            bool v = false;
+            if (a.kind == AtomDesc::INT_CMP || a.kind == AtomDesc::INT_SET) {
+                int64_t x;
+                if (a.feat == IF_PORT) x = b->remote_port ? b->remote_port[r] : 0;
+                else if (a.feat == IF_ASN) x = asn;
+                else { int f = a.feat - IF_LEN0; x = (int64_t)(cols[f]->offsets[r + 1] - cols[f]->offsets[r]); }
+                if (a.kind == AtomDesc::INT_CMP) {
+                    switch (a.op) {
+                        case CMP_EQ: v = x == a.cval; break;
+                        case CMP_NE: v = x != a.cval; break;
+                        case CMP_LT: v = x < a.cval; break;
+                        case CMP_LE: v = x <= a.cval; break;
+                        case CMP_GT: v = x > a.cval; break;
+                        default: v = x >= a.cval; break;
+                    }
+                } else {
+                    uint32_t l = H.iset_off[a.set_id], hgh = H.iset_off[a.set_id + 1];
+                    while (l < hgh) {
+                        uint32_t m = (l + hgh) >> 1;
+                        if (H.iset_vals[m] == x) { v = true; break; }
+                        if (H.iset_vals[m] < x) l = m + 1;
+                        else hgh = m;
+                    }
+                }
+            } else if (a.kind == AtomDesc::IP_SET) {
+                v = (set_mask >> a.set_id) & 1u;
+            } else {
+                uint32_t c0 = (country & 0xFF) - 'A', c1 = ((country >> 8) & 0xFF) - 'A';
+                if (c0 < 26 && c1 < 26) {
+                    uint32_t bit = c0 * 26 + c1;
+                    v = (H.cset_words[a.set_id * kCountryWords + (bit >> 5)] >> (bit & 31)) & 1u;
+                }
+            }
+            if (v) row[a.atom >> 5] |= 1u << (a.atom & 31);
+        }
+        uint32_t cv = flags & RF_CAPTCHA_VERIFIED;
+        uint32_t verdict = 0;
+        bool decided = false;
+        if (flags & RF_PRE_BLOCK) { verdict = V_BLOCK | (kNoRule << 2); decided = true; }
+        if (!decided && H.eval_gates) {
+            uint32_t ual = b->user_agent.offsets[r + 1] - b->user_agent.offsets[r];
+            if (ual == 0 || ual >= 256) { verdict = V_BLOCK | (kNoRule << 2); decided = true; }
+        }
+        if (!decided) {
+            bool bypass = flags & RF_BYPASS;
+            if (H.eval_gates && H.gate_bypass_atom >= 0) bypass |= (row[H.gate_bypass_atom >> 5] >> (H.gate_bypass_atom & 31)) & 1u;
+            if (bypass) { verdict = V_BYPASS | (kNoRule << 2); decided = true; }
+        }
+        if (!decided && (flags & RF_PRE_CAPTCHA)) { verdict = V_CAPTCHA | (kNoRule << 2); decided = true; }
+        if (!decided) {
+            uint32_t diff = 0;
+            for (uint32_t w = 0; w < Aw; ++w) diff |= (row[w] ^ H.expect[w]) & H.care[w];
+            if (!diff) verdict = H.v0[cv];
+            else {
+                uint32_t best = kNoRule;
+                uint32_t tshift = 2 * cv;
+                for (uint32_t w = 0; w < Aw; ++w) {
+                    uint32_t x = (row[w] ^ H.expect[w]) & H.care[w];
+                    while (x) {
+                        uint32_t bit = __builtin_ctz(x);
+                        x &= x - 1;
+                        uint32_t atom = w * 32 + bit;
+                        for (uint32_t i = H.ar_idx[atom]; i < H.ar_idx[atom + 1]; ++i) {
+                            uint32_t rule = H.ar_rules[i];
+                            if (rule >= best) break;
+                            if (((H.term[rule] >> tshift) & 3u) == 0) continue;
+                            if (eval_rule(H, rule, row)) best = rule;
+                        }
+                    }
+                }
+                for (uint32_t rule : H.dflt_rules[cv]) {
+                    if (rule >= best) break;
+                    if (eval_rule(H, rule, row)) best = rule;
+                }
+                verdict = best == kNoRule ? (V_ALLOW | (kNoRule << 2)) : (((H.term[best] >> tshift) & 3u) | (best << 2));
+            }
+        }
+        out[r] = verdict;
+    }
+    return 0;
+}
+
+void pgwsim_destroy(void* h) { delete (Sim*)h; }
+
+}  // extern "C"
