@@ -1,0 +1,98 @@
+"""Shared parity scenarios: (rules, lists, mmdb, batch, eval_gates).  Used by the GPU parity tests
+(CUDA vs oracle) and by the CPU-only compiler tests (compiled tables vs oracle)."""
+import numpy as np
+
+import synth
+from pingoo_b200 import Action, ListType, Rule, pack_requests
+
+
+def config1():
+    rules, payloads, _ = synth.make_ruleset(16, config_id=1)
+    batch = synth.RequestStream(config_id=1, payloads=payloads, get_only=True).generate(0, 10_000)
+    return rules, None, None, batch, True
+
+
+def config2_sample(n=60_000, first=0, attack_rate=0.03):
+    rules, payloads, _ = synth.make_ruleset(128, config_id=2)
+    batch = synth.RequestStream(config_id=2, payloads=payloads, attack_rate=attack_rate).generate(first, n)
+    return rules, None, None, batch, True
+
+
+def rules256(n=20_000):
+    rules, payloads, _ = synth.make_ruleset(256, config_id=2)
+    batch = synth.RequestStream(config_id=2, payloads=payloads).generate(5_000, n)
+    return rules, None, None, batch, True
+
+
+def ragged():
+    rules = [
+        Rule("eq_empty", 'http_request.path == ""', [Action.CAPTCHA]),
+        Rule("end", 'http_request.url.ends_with("=")', [Action.BLOCK]),
+        Rule("re_end", 'http_request.url.matches("a+b$")', [Action.BLOCK]),
+        Rule("len", "http_request.host.length() == 0", [Action.BLOCK]),
+        Rule("word", 'http_request.url.matches("\\\\bcat\\\\b")', [Action.CAPTCHA, Action.BLOCK]),
+    ]
+    reqs = []
+    urls = ["", "/", "/x=", "aab", "aaba", "a cat", "concat", "cat", "x" * 15, "y" * 16, "z" * 17, "b" * 31 + "=", "q" * 4097 + "aab"]
+    for i, u in enumerate(urls * 7):
+        reqs.append(dict(host="" if i % 5 == 0 else "h.example", url=u, path="" if i % 3 == 0 else u[:40], method="GET",
+                         user_agent="Mozilla/5.0 t", ip="10.0.0.%d" % (i % 250), remote_port=1000 + i, flags=i % 2))
+    return rules, reqs
+
+
+def gates():
+    rules = [
+        Rule("cap_then_block", 'http_request.path.starts_with("/a")', [Action.CAPTCHA, Action.BLOCK]),
+        Rule("noop", 'http_request.path.starts_with("/b")', []),
+        Rule("cap", 'http_request.path.starts_with("/b")', [Action.CAPTCHA]),
+        Rule("always", None, [Action.CAPTCHA]),
+        Rule("never_reached", 'http_request.path.starts_with("/c")', [Action.BLOCK]),
+    ]
+    reqs = []
+    for path in ["/a", "/b", "/c", "/d", "/__pingoo/captcha/verify", "/__pingoo"]:
+        for ua in ["Mozilla/5.0", "", "x" * 255, "y" * 256]:
+            for flags in [0, 1, 2, 4, 8, 5, 9]:
+                reqs.append(dict(host="h", url=path, path=path, method="GET", user_agent=ua, ip="1.1.1.1", remote_port=1, flags=flags))
+    return rules, pack_requests(reqs)
+
+
+def lists_geo(n=30_000, n_block=3_000, n_geo=1_500):
+    csv, members = synth.make_blocklist(n_block, config_id=3)
+    mmdb, records = synth.make_geoip(n_geo, config_id=3)
+    lists = {"blocked_ips": (ListType.Ip, csv), "bad_asns": (ListType.Int, b"64512\n64513,\"x\"\n7\n"),
+             "bad_hosts": (ListType.String, b"evil.example\n bad.example ,note\n")}
+    rules, payloads, _ = synth.make_ruleset(64, config_id=3, with_lists=True)
+    rules += [Rule("hosts", 'lists["bad_hosts"].contains(http_request.host)', [Action.BLOCK]),
+              Rule("asn_big", "client.asn >= 60000 && client.remote_port > 60000", [Action.CAPTCHA]),
+              Rule("cc", '["FR", "DE", "ZZ"].contains(client.country) && client.asn != 0', [Action.CAPTCHA]),
+              Rule("missing", 'lists["nope"].contains(client.ip) || http_request.path.starts_with("/zz")', [Action.BLOCK])]
+    stream = synth.RequestStream(config_id=3, payloads=payloads, blocklist_ips=members, blocklist_rate=0.05, special_ip_rate=0.01)
+    batch = stream.generate(0, n)
+    rng = np.random.RandomState(5)
+    for i in range(0, batch.n, 3):
+        net, _ = records[rng.randint(len(records))]
+        host = int(net.network_address) + int(rng.randint(0, min(net.num_addresses, 1 << 30)))
+        raw = host.to_bytes(4 if net.version == 4 else 16, "big")
+        batch.ip[i] = np.frombuffer(raw + b"\0" * (16 - len(raw)), dtype=np.uint8)
+        batch.ip_is_v6[i] = net.version == 6
+    return rules, lists, mmdb, batch, True, records
+
+
+def geo_probe_addresses(records, seed=11):
+    rng = np.random.RandomState(seed)
+    ips, v6 = [], []
+    for net, _ in records:
+        for _ in range(3):
+            host = int(net.network_address) + int(rng.randint(0, min(net.num_addresses, 1 << 30)))
+            raw = host.to_bytes(4 if net.version == 4 else 16, "big")
+            ips.append(raw + b"\0" * (16 - len(raw)))
+            v6.append(net.version == 6)
+    for s in ["127.0.0.1", "224.0.0.1", "8.8.8.8", "255.255.255.255", "0.0.0.0", "239.1.2.3", "126.255.255.255", "128.0.0.0"]:
+        ips.append(bytes(map(int, s.split("."))) + b"\0" * 12)
+        v6.append(0)
+    for raw in [b"\0" * 15 + b"\1", b"\xff\x02" + b"\0" * 13 + b"\1", b"\x20\x01" + b"\0" * 14, b"\0" * 12 + bytes([1, 2, 3, 4]),
+                b"\0" * 10 + b"\xff\xff" + bytes([1, 2, 3, 4]), b"\xff" * 16, b"\0" * 16]:
+        ips.append(raw)
+        v6.append(1)
+    ip_np = np.frombuffer(b"".join(ips), dtype=np.uint8).reshape(-1, 16).copy()
+    return ip_np, np.array(v6, dtype=np.uint8)
