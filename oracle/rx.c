@@ -390,6 +390,8 @@ static node* parse_atom(parser* P, flags_t* f, int* produced) {
                 P->pos++;
             } else if (d == '=' || d == '!') {
                 pfail(P, RX_INVALID, "look-around is not supported");
+            } else if (d == ':') {
+                P->pos++; /* plain non-capturing group */
             } else {
                 int neg = 0, any = 0, scoped = -1;
                 while (scoped < 0) {

@@ -540,6 +540,8 @@ class Parser {
                         ++pos_;
                     } else if (d == '=' || d == '!') {
                         fail(RX_INVALID, "look-around is not supported");
+                    } else if (d == ':') {
+                        ++pos_;  // (?:...) non-capturing group
                     } else {
                         bool scoped = false;
                         parse_flags(inner, &scoped);

@@ -1,0 +1,407 @@
+"""Pinning the oracle (CPU-only).
+
+The reference has no tests or golden vectors and its arithmetic lives in crates that are not vendored
+(PARITY UNPINNED, see oracle/oracle.h).  What can be pinned is pinned here:
+  * the reference's documentation examples, with expectations derived by hand from the docs
+    (tests/golden/doc_examples.json);
+  * regex match existence against Python's `re` (an independent backtracking engine) on the shared syntax;
+  * IpNetwork parsing / containment against Python's `ipaddress`;
+  * GeoIP lookups against a straightforward Python reading of the record list;
+  * list CSV parsing and the rule-language semantics assumptions A1-A9 as known-answer tables.
+"""
+import ctypes as C
+import ipaddress
+import json
+import os
+import random
+import re
+
+import regex as _regex  # third-party backtracking engine with a match timeout
+
+import numpy as np
+import pytest
+
+import synth
+from helpers import Oracle, Sim, fmt_verdict, oracle_lib
+from pingoo_b200 import Action, ListType, Rule, _ffi, pack_requests
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def req(**kw):
+    d = dict(host="example.com", url="/", path="/", method="GET", user_agent="Mozilla/5.0 (X11)", ip="203.0.113.7", remote_port=40000,
+             asn=64500, country="FR", flags=0)
+    d.update(kw)
+    return d
+
+
+def eval_kind(expr, **kw):
+    b = pack_requests([req(**kw)])
+    cb = b.as_ctypes()
+    return oracle_lib().orc_eval_kind(expr.encode(), C.byref(cb))
+
+
+# ---- documentation examples -------------------------------------------------------------------------------
+def test_doc_examples_golden():
+    with open(os.path.join(HERE, "golden", "doc_examples.json")) as f:
+        cases = json.load(f)
+    for case in cases:
+        rules = [Rule(r["name"], r.get("expression"), [Action.from_config(a) for a in r["actions"]]) for r in case["rules"]]
+        lists = {k: (ListType.from_str(v["type"]), v["csv"].encode()) for k, v in case.get("lists", {}).items()}
+        batch = pack_requests([req(**r) for r in case["requests"]])
+        got = [fmt_verdict(v) for v in Oracle(rules, lists).evaluate(batch)]
+        assert got == case["expect"], case["source"]
+        # the product compiler's tables must agree on the same examples
+        assert [fmt_verdict(v) for v in Sim(rules, lists).evaluate(batch)] == case["expect"], case["source"]
+
+
+# ---- rule language known answers (SEMANTICS.md A1-A9) ----------------------------------------------------
+F, T, E, NB = 0, 1, 2, 3
+KAT = [
+    ('http_request.path == "/blocked"', dict(path="/blocked"), T),
+    ('http_request.path == "/blocked"', dict(path="/blocked2"), F),
+    ('http_request.path != "/x"', dict(path="/y"), T),
+    ('"GET" == http_request.method', {}, T),
+    ('http_request.path.starts_with("/.env") || http_request.path.starts_with("/.git")', dict(path="/.git/config"), T),
+    ('!http_request.user_agent.starts_with("Mozilla/") && !http_request.user_agent.contains("curl/")', dict(user_agent="Wget/1"), T),
+    ('!http_request.user_agent.starts_with("Mozilla/") && !http_request.user_agent.contains("curl/")', dict(user_agent="x curl/8"), F),
+    ('["XX"].contains(client.country)', dict(country="XX"), T),
+    ('["XX"].contains(client.country)', dict(country="FR"), F),
+    ('http_request.host.starts_with("api.")', dict(host="api.example.com"), T),
+    ('host.starts_with("api")', {}, E),                      # undeclared variable (stale docs/services.md:18)
+    ('http_request.starts_with("/api")', {}, E),             # method on a map
+    ('http_request.path.ends_with(".php")', dict(path="/a.php"), T),
+    ('http_request.url.contains("")', {}, T),
+    ('http_request.path.length() == 4', dict(path="/abc"), T),
+    ('http_request.path.length()', {}, NB),                  # non-bool result => rule does not match
+    ('client.remote_port < 1024', dict(remote_port=80), T),
+    ('client.remote_port >= 1024 && client.asn == 64500', {}, T),
+    ('client.asn > 9223372036854775806', {}, F),
+    ('client.country == "FR"', {}, T),
+    ('client.country < "FS" && client.country >= "FR"', {}, T),
+    ('client.country.matches("^F.$")', {}, T),
+    ('client.ip == client.ip', {}, T),
+    ('client.ip == "203.0.113.7"', {}, E),                   # A4/A7: Ip vs String is cross-type
+    ('client.asn == "64500"', {}, E),
+    ('1 == 1.0', {}, E),
+    ('1 + 2 * 3 == 7', {}, T),
+    ('7 / 0 == 1', {}, E),
+    ('9223372036854775807 + 1 > 0', {}, E),
+    ('-9223372036854775808 < 0', {}, T),
+    ('7 % 3 == 1 && -7 / 2 == -3', {}, T),
+    ('"a" + "b" == "ab"', {}, T),
+    ('true || host', {}, T),                                  # A5: short circuit skips the erroring operand
+    ('false && host', {}, F),
+    ('host || true', {}, E),                                  # A5: left operand error aborts
+    ('true && 1', {}, E),
+    ('!1', {}, E),
+    ('true ? http_request.method == "GET" : host', {}, T),
+    ('lists["nope"].contains(client.ip)', {}, E),             # A6
+    ('lists.contains("nope")', {}, F),
+    ('http_request.contains("host")', {}, T),
+    ('http_request["path"] == "/"', dict(path="/"), F),       # packer trims the trailing slash: path is ""
+    ('http_request["path"] == ""', dict(path="/"), T),
+    ('1 in [1, 2]', {}, E),                                   # "@in" is not provided (rules/rules.rs:67-71)
+    ('http_request.path.size() == 1', {}, E),                 # CEL's name is not in docs/rules.md:71-76
+    ('contains(http_request.path, "a")', {}, E),              # no global functions
+    ('[1, 2, 3].contains(2) && [1, 2, 3].length() == 3 && [1, 2][1] == 2', {}, T),
+    ('[1, 2][2] == 2', {}, E),
+    ('["a", 1].contains(1)', {}, T),
+    ('[1, 2].contains("1")', {}, F),                          # A2: elements of another type are simply not equal
+    ('http_request.url.matches("(?i)UNION\\\\s+select")', dict(url="/?q=union  SELECT"), T),
+    ('http_request.url.matches(r"\\bcat\\b")', dict(url="/?a=;cat "), T),
+    ('http_request.url.matches(r"\\bcat\\b")', dict(url="/?a=concat"), F),
+    ('http_request.url.matches("(")', {}, E),                 # A1: pattern does not compile -> runtime error
+    ("http_request.url.matches('a{2,1}')", {}, E),
+    ('http_request.url.matches("^/$")', dict(url="/"), T),
+    ('http_request.url.matches("x*")', {}, T),
+    ('http_request.method.matches("^(GET|HEAD)$")', dict(method="HEAD"), T),
+    ('"abc".matches("b")', {}, T),
+    ("'it''s'", {}, None),                                    # syntax error
+    ('http_request.path ==', {}, None),
+    ('', {}, None),
+]
+
+
+@pytest.mark.parametrize("expr,ctx,want", KAT)
+def test_language_known_answers(expr, ctx, want):
+    got = eval_kind(expr, **ctx)
+    assert got == (-1 if want is None else want), expr
+
+
+def test_compile_and_validate_expression():
+    L = oracle_lib()
+    err = C.create_string_buffer(256)
+    assert L.orc_compile_expression(b'http_request.path == "/x"', err, 256) == 0
+    assert L.orc_compile_expression(b'http_request.path == ', err, 256) != 0
+    assert err.value.startswith(b"Expression is not valid")
+    assert L.orc_validate_expression(b"", err, 256) != 0 and b"expression is empty" in err.value
+    assert L.orc_compile_expression(b"1 in [1]", err, 256) == 0  # compile accepts `in` ...
+    assert L.orc_validate_expression(b"1 in [1]", err, 256) != 0 and b"unknown operator: in" in err.value  # ... validate rejects it
+
+
+# ---- regex vs Python re -----------------------------------------------------------------------------------
+ATOMS = ["a", "b", "c", "x", "1", " ", "/", "%", "=", ".", "\\.", "\\d", "\\w", "\\s", "\\D", "\\W", "\\S", "[ab]", "[^a]", "[a-c1-3]",
+         "[^\\s=]", "[\\d.]", "(?:ab)", "(a|bc)", "(?i:aB)", "\\x41", "\\n", "[\\]a]", "[a\\-c]"]
+QUANT = ["", "", "", "*", "+", "?", "{2}", "{1,3}", "{0,2}", "{2,}", "*?", "+?"]
+
+
+def random_pattern(rng, depth=0):
+    n = rng.randint(1, 5)
+    parts = []
+    for _ in range(n):
+        r = rng.random()
+        if r < 0.15 and depth < 2:
+            inner = "|".join(random_pattern(rng, depth + 1) for _ in range(rng.randint(1, 3)))
+            atom = "(" + inner + ")"
+        elif r < 0.20:
+            atom = rng.choice(["\\b", "\\B"])
+            parts.append(atom)
+            continue
+        else:
+            atom = rng.choice(ATOMS)
+        parts.append(atom + rng.choice(QUANT))
+    p = "".join(parts)
+    if depth == 0:
+        if rng.random() < 0.2:
+            p = "^" + p
+        if rng.random() < 0.2:
+            p = p + "$"
+        if rng.random() < 0.25:
+            p = "(?i)" + p
+    return p
+
+
+def py_search(pre, h):
+    """re-compatible search with a timeout: random nested quantifiers can make a backtracking engine explode."""
+    try:
+        return pre.search(h, timeout=0.25) is not None
+    except TimeoutError:
+        return None
+
+
+def to_python(p):
+    # Rust `$` (no multi-line) is end of haystack only: Python's closest is \Z
+    out, i = [], 0
+    in_class = False
+    while i < len(p):
+        c = p[i]
+        if c == "\\":
+            out.append(p[i:i + 2])
+            i += 2
+            continue
+        if c == "[":
+            in_class = True
+        elif c == "]":
+            in_class = False
+        if c == "$" and not in_class:
+            out.append("\\Z")
+        else:
+            out.append(c)
+        i += 1
+    return "".join(out)
+
+
+def test_regex_against_python_re():
+    rng = random.Random(20260922)
+    L = oracle_lib()
+    alphabet = "abcABCx1 2/%=.\n_-"
+    checked = 0
+    patterns = []
+    for _ in range(1500):
+        pat = random_pattern(rng)
+        try:
+            pre = _regex.compile(to_python(pat), _regex.ASCII)
+        except (re.error, _regex.error):
+            continue
+        hays = ["", "a", "ab", "abc"] + ["".join(rng.choice(alphabet) for _ in range(rng.randint(0, 24))) for _ in range(24)]
+        pb = pat.encode()
+        for h in hays:
+            if h == "" and "\\B" in pat:
+                continue  # CPython quirk: \B never matches the empty string; Rust regex does
+            hb = h.encode()
+            got = L.orc_regex_is_match(pb, len(pb), hb, len(hb))
+            assert got in (0, 1), f"oracle rejected {pat!r}: {got}"
+            ref = py_search(pre, h)
+            if ref is None:
+                continue
+            assert got == (1 if ref else 0), f"pattern {pat!r} haystack {h!r}: oracle {got}"
+            checked += 1
+        patterns.append(pat)
+    assert checked > 20000
+    # the product's DFA compiler must agree on the same corpus (one rule per pattern, one request per haystack)
+    hays = ["", "a", "ab", "abc"] + ["".join(rng.choice(alphabet) for _ in range(rng.randint(0, 40))) for _ in range(300)]
+    batch = pack_requests([req(url=h.replace("\n", "\n")) for h in hays])
+    compiled = 0
+    for p in [q for q in patterns if len(q) <= 40][:300]:
+        if True:
+            rules = [Rule("r", "http_request.url.matches(" + json.dumps(p) + ")", [Action.BLOCK])]
+            try:
+                sim = Sim(rules, eval_gates=False)
+            except ValueError as e:
+                assert "needs a DFA larger than" in str(e)  # documented limit: loud failure, never a wrong verdict
+                continue
+            compiled += 1
+            got = sim.evaluate(batch) & 3
+            pre = _regex.compile(to_python(p), _regex.ASCII)
+            ref = [py_search(pre, h) for h in hays]
+            want = np.array([got[i] if r is None else (1 if r else 0) for i, r in enumerate(ref)], dtype=np.uint32)
+            if "\\B" in p:
+                want[0] = got[0]  # empty haystack, see above
+            assert np.array_equal(got, want), f"product DFA differs from Python re for {p!r}"
+    assert compiled > 250
+
+
+REGEX_KAT = [
+    ("[[:alpha:]]+[[:digit:]]", "ab1", 1), ("[[:^alpha:]]", "abc", 0), ("[[:space:]]", "a b", 1),
+    ("(?i)[a-c]+$", "xxABC", 1), ("(?i)[^a]", "A", 0), ("(?s).", "\n", 1), (".", "\n", 0), ("(?m)^b$", "a\nb\nc", 1), ("^b$", "a\nb\nc", 0),
+    ("a\\z", "ba", 1), ("\\Aab", "ab", 1), ("(?x) a b # comment\n c", "abc", 1), ("a{2}{2}", "aaaa", 1), ("a**", "", 1),
+    ("[a&&b]", "a", 0), ("[a-z&&[^b]]", "b", 0), ("[a-z--b]", "c", 1), ("\\x{41}", "A", 1), ("\\u0041", "A", 1), ("é", "cafe", 0),
+    ("[^é]", "e", 1), ("(?P<n>a)(?<m>b)", "ab", 1), ("a|", "zzz", 1), ("(|a)b", "b", 1), ("[]a]", "]", 1), ("[^]a]", "]", 0), ("[a-]", "-", 1),
+    ("\\$\\{jndi:(ldap|rmi|dns)://", "${jndi:ldap://x}", 1), ("}", "}", 1), ("]", "]", 1),
+]
+REGEX_BAD = [("(", -1), (")", -1), ("a{", -1), ("{", -1), ("*a", -1), ("a{,2}", -1), ("a{2,1}", -1), ("[a", -1), ("[]", -1), ("\\1", -1), ("\\Z", -1),
+             ("(?=a)", -1), ("(?<!a)b", -1), ("(?P=n)", -1), ("\\8", -1), ("\\q", -1), ("[z-a]", -1), ("(?y)a", -1), ("\\pL", -2), ("\\b{start}", -2),
+             ("(?R)a", -2), ("(a{1000}){1000}", -3)]
+
+
+@pytest.mark.parametrize("pat,hay,want", REGEX_KAT)
+def test_regex_known_answers(pat, hay, want):
+    L = oracle_lib()
+    pb, hb = pat.encode(), hay.encode()
+    assert L.orc_regex_is_match(pb, len(pb), hb, len(hb)) == want
+
+
+@pytest.mark.parametrize("pat,want", REGEX_BAD)
+def test_regex_rejections(pat, want):
+    L = oracle_lib()
+    pb = pat.encode()
+    assert L.orc_regex_is_match(pb, len(pb), b"x", 1) == want
+
+
+# ---- IpNetwork vs ipaddress --------------------------------------------------------------------------------
+def test_ipnetwork_against_python_ipaddress():
+    rng = random.Random(7)
+    L = oracle_lib()
+    for _ in range(3000):
+        if rng.random() < 0.6:
+            a = rng.getrandbits(32)
+            pl = rng.choice([0, 1, 8, 16, 20, 24, 30, 31, 32])
+            net_addr = ipaddress.IPv4Address(a)
+            text = f"{net_addr}/{pl}" if rng.random() < 0.8 else (f"{net_addr}/{ipaddress.IPv4Network((0, pl)).netmask}" if rng.random() < 0.5 else str(net_addr))
+            if "/" not in text:
+                pl = 32
+            net = ipaddress.IPv4Network((a >> (32 - pl) << (32 - pl) if pl else 0, pl))
+            probe = ipaddress.IPv4Address((int(net.network_address) + rng.getrandbits(32 - pl)) & 0xFFFFFFFF if rng.random() < 0.5 and pl < 32 else rng.getrandbits(32))
+            raw, v6 = probe.packed + b"\0" * 12, 0
+        else:
+            a = rng.getrandbits(128)
+            pl = rng.choice([0, 1, 16, 32, 48, 64, 96, 127, 128])
+            net_addr = ipaddress.IPv6Address(a)
+            text = f"{net_addr}/{pl}" if rng.random() < 0.8 else str(net_addr)
+            if "/" not in text:
+                pl = 128
+            net = ipaddress.IPv6Network((a >> (128 - pl) << (128 - pl) if pl else 0, pl))
+            probe = ipaddress.IPv6Address((int(net.network_address) + rng.getrandbits(128 - pl)) if rng.random() < 0.5 and pl < 128 else rng.getrandbits(128))
+            raw, v6 = probe.packed, 1
+        got = L.orc_ipnet_contains(text.encode(), raw, v6)
+        assert got == (1 if probe in net else 0), (text, str(probe))
+        # families never mix (A7)
+        other = b"\x01\x02\x03\x04" + b"\0" * 12 if v6 else b"\x20\x01" + b"\0" * 14
+        assert L.orc_ipnet_contains(text.encode(), other, 0 if v6 else 1) == 0
+
+
+@pytest.mark.parametrize("text", ["1.2.3", "1.2.3.4.5", "01.2.3.4", "256.1.1.1", "1.2.3.4/33", "::1/129", "1::2::3", ":1", "1:", "12345::", "g::1", "1.2.3.4/255.0.255.0",
+                                  "", " 1.2.3.4", "1.2.3.4/", "::ffff:1.2.3", "1:2:3:4:5:6:7:8:9"])
+def test_ipnetwork_rejections(text):
+    assert oracle_lib().orc_ipnet_contains(text.encode(), b"\0" * 16, 0) == -1
+
+
+@pytest.mark.parametrize("text,probe,v6,want", [
+    ("::ffff:1.2.3.4", ipaddress.IPv6Address("::ffff:102:304").packed, 1, 1), ("::", b"\0" * 16, 1, 1), ("1::", ipaddress.IPv6Address("1::").packed, 1, 1),
+    ("::1.2.3.4/96", ipaddress.IPv6Address("::5.6.7.8").packed, 1, 1), ("10.1.2.3/8", bytes([10, 9, 9, 9]) + b"\0" * 12, 0, 1),
+    ("1.2.3.4/255.255.255.0", bytes([1, 2, 3, 200]) + b"\0" * 12, 0, 1), ("0.0.0.0/0", bytes([9, 9, 9, 9]) + b"\0" * 12, 0, 1)])
+def test_ipnetwork_forms(text, probe, v6, want):
+    assert oracle_lib().orc_ipnet_contains(text.encode(), probe, v6) == want
+
+
+# ---- lists ----------------------------------------------------------------------------------------------------
+def test_list_csv_rules():
+    csv = b'127.0.0.1,"really bad person"\r\n\r\n 1.2.3.4 ,bad bot\n"10.0.0.0/8"\n'
+    rules = [Rule("r", 'lists["l"].contains(client.ip)', [Action.BLOCK])]
+    o = Oracle(rules, {"l": (ListType.Ip, csv)})
+    got = o.evaluate(pack_requests([req(ip="127.0.0.1"), req(ip="1.2.3.4"), req(ip="10.200.0.1"), req(ip="11.0.0.1"), req(ip="::1")]))
+    assert [fmt_verdict(v) for v in got] == ["block@0", "block@0", "block@0", "allow@-", "allow@-"]
+    with pytest.raises(ValueError, match="invalid number of columns"):
+        Oracle(rules, {"l": (ListType.Ip, b"1.1.1.1,a,b\n")})
+    with pytest.raises(ValueError, match="line 2: error parsing IP network"):
+        Oracle(rules, {"l": (ListType.Ip, b"1.1.1.1\nnot-an-ip\n")})
+    with pytest.raises(ValueError, match="error parsing int"):
+        Oracle(rules, {"l": (ListType.Int, b"12\n1x\n")})
+    ints = Oracle([Rule("r", 'lists["i"].contains(client.asn)', [Action.BLOCK])], {"i": (ListType.Int, b"+5\n-3\n 64500 \n")})
+    assert fmt_verdict(ints.evaluate(pack_requests([req()]))[0]) == "block@0"
+    strs = Oracle([Rule("r", 'lists["s"].contains(http_request.host)', [Action.BLOCK])], {"s": (ListType.String, b'"a,b"\n example.com \n')})
+    assert [fmt_verdict(v) for v in strs.evaluate(pack_requests([req(), req(host="a,b"), req(host="x")]))] == ["block@0", "block@0", "allow@-"]
+
+
+# ---- GeoIP -----------------------------------------------------------------------------------------------------
+def expected_geo(records, ip_obj):
+    """Plain reading of the record list with the reference's decoding rules (geoip.rs:73-142, serde_utils.rs:1-9)."""
+    if ip_obj.is_loopback or ip_obj.is_multicast:
+        return 0, "XX"
+    for net, rec in records:
+        if net.version == ip_obj.version and ip_obj in net:
+            asn, cc = rec.get("asn"), rec.get("country")
+            if not isinstance(asn, str) or not isinstance(cc, str):
+                return 0, "XX"
+            if len(cc) != 2 or not all("A" <= c <= "Z" for c in cc):
+                return 0, "XX"
+            s = asn
+            while s.startswith("AS"):
+                s = s[2:]
+            digits = s[1:] if s.startswith("+") else s
+            n = int(digits) if digits.isdigit() and digits.isascii() else 0
+            return (n if n <= 0xFFFFFFFF else 0), cc
+    return 0, "XX"
+
+
+@pytest.mark.parametrize("ip_version,record_size", [(6, 28), (6, 24), (6, 32), (4, 24)])
+def test_geoip_lookup_against_record_list(ip_version, record_size):
+    _, records = synth.make_geoip(400, config_id=40 + record_size, ip_version=ip_version)
+    mmdb = synth.write_mmdb(records, ip_version=ip_version, record_size=record_size)
+    o = Oracle([], geoip_mmdb=mmdb)
+    rng = random.Random(3)
+    probes = []
+    for net, _ in records:
+        probes.append(net.network_address)
+        probes.append(net.broadcast_address)
+        probes.append(net.network_address + rng.randrange(net.num_addresses))
+    probes += [ipaddress.ip_address(s) for s in ["127.0.0.1", "224.0.0.9", "8.8.8.8", "::1", "ff02::1", "2001:db8::1", "::ffff:8.8.8.8", "::8.8.8.8"]]
+    for _ in range(500):
+        probes.append(ipaddress.IPv4Address(rng.getrandbits(32)))
+    for p in probes:
+        raw = p.packed + b"\0" * (16 - len(p.packed))
+        want = expected_geo(records, p)
+        if ip_version == 4 and p.version == 6:
+            want = (0, "XX")
+        if ip_version == 6 and p.version == 6 and int(p) < (1 << 32) and not (p.is_loopback or p.is_multicast):
+            # ::a.b.c.d walks into the IPv4 subtree of an IPv6 database
+            want = expected_geo(records, ipaddress.IPv4Address(int(p)))
+            if ipaddress.IPv4Address(int(p)).is_loopback or ipaddress.IPv4Address(int(p)).is_multicast:
+                want = expected_geo([(n, r) for n, r in records], ipaddress.IPv4Address(int(p))) if False else _geo_no_skip(records, ipaddress.IPv4Address(int(p)))
+        assert o.geoip_lookup(raw, 1 if p.version == 6 else 0) == want, str(p)
+
+
+def _geo_no_skip(records, ip_obj):
+    class _P:
+        pass
+    for net, rec in records:
+        if net.version == ip_obj.version and ip_obj in net:
+            fake = ipaddress.IPv4Address("8.8.8.8")
+            return expected_geo([(ipaddress.ip_network("8.8.8.8/32"), rec)], fake)
+    return 0, "XX"
+
+
+def test_geoip_rejects_garbage():
+    with pytest.raises(ValueError, match="mmdb file is not valid"):
+        Oracle([], geoip_mmdb=b"not a database")
