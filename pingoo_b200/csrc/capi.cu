@@ -80,9 +80,9 @@ struct pgw_ruleset {
     size_t max_smem = 0;
     DevMem mem;
     KParams base;  // program pointers filled in, batch fields zero
-    bool smem_tables = false;
-    uint32_t tile_log2 = 10;
     size_t smem_bytes = 0;
+    uint32_t hot_states_total = 0;
+    uint32_t* counters = nullptr;  // ring of work counters: one per in-flight launch
     std::atomic<uint64_t> launches{0};
     // host-pointer path
     Staging stage_cols[5], stage_offs[5], stage_ip, stage_v6, stage_port, stage_asn, stage_country, stage_flags, stage_verdict;
@@ -165,15 +165,24 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     DevMem& M = rs->mem;
     bool ok = true;
     auto chk = [&](const void* p) { if (!p) ok = false; return p; };
-    P.units = (const UnitDesc*)chk(M.upload(H.units));
-    P.n_units = (uint32_t)H.units.size();
+    // shared-memory image: class maps + as many hot DFA rows as fit beside the per-lane bitmap rows
+    size_t fixed = waf_smem_fixed_bytes((uint32_t)H.units.size(), H.atom_words);
+    if (fixed + H.units.size() * 256 + 1024 > rs->max_smem)
+        return fail("ruleset does not fit the shared-memory plan (too many atoms or scan units)", err, err_cap);
+    std::vector<uint8_t> image;
+    std::vector<UnitDesc> units;
+    build_smem_image(H, rs->max_smem - fixed - 64, &image, &units);
+    rs->smem_bytes = waf_smem_bytes((uint32_t)image.size(), (uint32_t)units.size(), H.atom_words);
+    for (auto& u : units) rs->hot_states_total += u.hot_states;
+    P.units = (const UnitDesc*)chk(M.upload(units));
+    P.n_units = (uint32_t)units.size();
     P.arena = (const uint8_t*)chk(M.upload(H.arena));
-    P.arena_bytes = (uint32_t)H.arena.size();
-    P.cls_bytes = (uint32_t)H.units.size() * 256u;
+    P.image = (const uint8_t*)chk(M.upload(image));
+    P.image_bytes = (uint32_t)image.size();
     P.acc_idx = (const uint32_t*)chk(M.upload(H.acc_idx));
-    P.acc_atoms = (const uint16_t*)chk(M.upload(H.acc_atoms));
+    P.acc_events = (const uint32_t*)chk(M.upload(H.acc_events));
     P.end_idx = (const uint32_t*)chk(M.upload(H.end_idx));
-    P.end_atoms = (const uint16_t*)chk(M.upload(H.end_atoms));
+    P.end_events = (const uint32_t*)chk(M.upload(H.end_events));
     P.n_atoms = H.n_atoms;
     P.atom_words = H.atom_words;
     P.expect = (const uint32_t*)chk(M.upload(H.expect));
@@ -194,8 +203,6 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     P.iset_vals = (const int64_t*)chk(M.upload(H.iset_vals));
     P.iset_off = (const uint32_t*)chk(M.upload(H.iset_off));
     P.cset = (const uint32_t*)chk(M.upload(H.cset_words));
-    for (int f = 0; f < 5; ++f) P.slot[f] = H.field_slot[f];
-    P.n_slots = H.n_slots;
     P.gate_atom = H.gate_bypass_atom;
     P.eval_gates = H.eval_gates ? 1u : 0u;
     P.lpm_present = H.lpm.present ? 1u : 0u;
@@ -209,29 +216,11 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
         P.v6_leaf = (const uint32_t*)chk(M.upload(H.lpm.v6_leaf));
         P.n_v6 = (uint32_t)H.lpm.v6_leaf.size();
     }
+    std::vector<uint32_t> zeros(64, 0);
+    rs->counters = (uint32_t*)chk(M.upload(zeros));
     if (!ok) {
         M.release();
         return fail(std::string("CUDA: device allocation/upload failed: ") + cudaGetErrorString(cudaGetLastError()), err, err_cap);
-    }
-
-    // launch plan: prefer DFA tables in shared memory; shrink the tile before giving that up
-    bool planned = false;
-    for (int st = 1; st >= 0 && !planned; --st) {
-        int lo = st ? 8 : 6;
-        for (int tl = 10; tl >= lo; --tl) {
-            size_t need = waf_smem_bytes(P, st != 0, (uint32_t)tl);
-            if (need <= rs->max_smem) {
-                rs->smem_tables = st != 0;
-                rs->tile_log2 = (uint32_t)tl;
-                rs->smem_bytes = need;
-                planned = true;
-                break;
-            }
-        }
-    }
-    if (!planned) {
-        M.release();
-        return fail("ruleset does not fit the shared-memory plan (too many atoms or scan units)", err, err_cap);
     }
     if (cudaStreamCreateWithFlags(&rs->stream, cudaStreamNonBlocking) != cudaSuccess) {
         M.release();
@@ -264,15 +253,15 @@ static int launch_on(const pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdic
     if (H.needs_port && !b->remote_port) { e = "batch is missing client.remote_port"; return 1; }
     P.verdict = verdict_out;
     P.n = b->n;
-    P.tile_log2 = rs->tile_log2;
-    P.n_tiles = (b->n + (1u << rs->tile_log2) - 1) >> rs->tile_log2;
+    if (b->n == 0) return 0;
+    // each in-flight launch gets its own work counter (ring of 64), so concurrent callers do not interfere
+    uint64_t seq = const_cast<pgw_ruleset*>(rs)->launches.fetch_add(1, std::memory_order_relaxed);
+    P.work_counter = rs->counters + (seq & 63);
     LaunchPlan plan;
-    plan.smem_tables = rs->smem_tables;
-    plan.tile_log2 = rs->tile_log2;
     plan.smem_bytes = rs->smem_bytes;
-    plan.grid = (int)(P.n_tiles < (uint32_t)rs->sm_count ? P.n_tiles : (uint32_t)rs->sm_count);
+    uint32_t want = (b->n + kThreads - 1) / kThreads;
+    plan.grid = (int)(want < (uint32_t)rs->sm_count ? want : (uint32_t)rs->sm_count);
     if (const char* m = waf_launch(P, plan, stream)) { e = std::string("CUDA launch failed: ") + m; return 1; }
-    if (b->n) const_cast<pgw_ruleset*>(rs)->launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
 
@@ -394,11 +383,11 @@ int pgw_ruleset_info(const pgw_ruleset* rs, pgw_info* out) {
     out->reads_geo_columns = H.needs_geo_cols;
     out->table_arena_bytes = H.arena.size();
     out->smem_bytes = rs->smem_bytes;
-    out->tables_in_smem = rs->smem_tables;
-    out->tile_requests = 1u << rs->tile_log2;
+    for (auto& u : H.units) out->total_dfa_states += u.n_states;
+    out->tables_in_smem = rs->hot_states_total == out->total_dfa_states;
+    out->tile_requests = rs->hot_states_total;  /* states whose rows live in shared memory */
     out->grid = (uint32_t)rs->sm_count;
     out->threads = kThreads;
-    for (auto& u : H.units) out->total_dfa_states += u.n_states;
     out->lpm_present = H.lpm.present;
     out->geoip_loaded = H.lpm.geo_loaded;
     out->kernel_launches = rs->launches.load();

@@ -90,7 +90,9 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
             a.field = F_PATH;
             a.key = key;
             int id = (int)M.atoms.size();
-            a.nfa_start = nfa_literal(M.nfa[F_PATH], "/__pingoo/captcha", true, false, id);
+            a.event_base = (int)M.events.size();
+            a.nfa_starts.push_back(nfa_literal(M.nfa[F_PATH], "/__pingoo/captcha", true, false, a.event_base));
+            M.events.push_back(PatternEvent{EV_FIRE, id});
             M.atom_index[key] = id;
             M.atoms.push_back(a);
             H.gate_bypass_atom = id;
@@ -161,29 +163,44 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
     bool len_feat_used[N_FIELDS] = {false, false, false, false, false};
     static const int kFieldOrder[N_FIELDS] = {F_URL, F_USER_AGENT, F_PATH, F_HOST, F_METHOD};  // longest first
     // arena: all class maps first, then the tables
-    struct Pending { Dfa dfa; int field; };
+    struct Pending { Dfa dfa; int field; std::vector<int> latch_of_event; };
     std::vector<Pending> pend;
     for (int fo = 0; fo < N_FIELDS; ++fo) {
         int f = kFieldOrder[fo];
-        std::vector<int> starts;
+        std::vector<PatternBundle> bundles;
+        std::vector<uint32_t> bundle_atom;
         for (uint32_t a = 0; a < H.n_atoms; ++a)
-            if (M.atoms[a].kind == AtomDesc::STR_PATTERN && M.atoms[a].field == f) starts.push_back(M.atoms[a].nfa_start);
-        if (starts.empty()) continue;
+            if (M.atoms[a].kind == AtomDesc::STR_PATTERN && M.atoms[a].field == f) {
+                PatternBundle b;
+                b.starts = M.atoms[a].nfa_starts;
+                b.has_latch = M.atoms[a].has_latch;
+                bundles.push_back(std::move(b));
+                bundle_atom.push_back(a);
+            }
+        if (bundles.empty()) continue;
         DfaGroups groups;
         int failed = -1;
-        if (!build_dfa_groups(M.nfa[f], starts, opt.max_dfa_states, opt.max_unit_table_bytes, &groups, &failed)) {
-            std::string which = "?";
-            int k = 0;
-            for (uint32_t a = 0; a < H.n_atoms; ++a)
-                if (M.atoms[a].kind == AtomDesc::STR_PATTERN && M.atoms[a].field == f) {
-                    if (k == failed) which = M.atoms[a].key;
-                    ++k;
-                }
+        if (!build_dfa_groups(M.nfa[f], bundles, opt.max_dfa_states, opt.max_unit_table_bytes, (int)kMaxLatchesPerUnit, &groups, &failed)) {
+            std::string which = failed >= 0 ? M.atoms[bundle_atom[failed]].key : "?";
             err = "pattern on http_request." + std::string(kFieldNames[f]) + " needs a DFA larger than " +
                   std::to_string(opt.max_dfa_states) + " states: " + which;
             return false;
         }
-        for (auto& d : groups.dfas) pend.push_back(Pending{std::move(d), f});
+        for (size_t g = 0; g < groups.dfas.size(); ++g) {
+            Pending pd;
+            pd.dfa = std::move(groups.dfas[g]);
+            pd.field = f;
+            // latch numbering is local to the unit
+            pd.latch_of_event.assign(M.events.size(), 0);
+            int next_latch = 0;
+            for (int bi : groups.members[g]) {
+                const AtomDesc& ad = M.atoms[bundle_atom[bi]];
+                if (!ad.has_latch) continue;
+                for (size_t k = 0; k < ad.nfa_starts.size(); ++k) pd.latch_of_event[ad.event_base + k] = next_latch;
+                ++next_latch;
+            }
+            pend.push_back(std::move(pd));
+        }
         H.scanned_fields_mask |= 1u << f;
     }
     // class maps
@@ -194,6 +211,15 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
     }
     H.acc_idx.clear();
     H.end_idx.clear();
+    auto emit_events = [&](const Pending& pd, const std::vector<int>& pattern_ids, std::vector<uint32_t>& out_words) {
+        std::vector<uint32_t> w;
+        for (int pid : pattern_ids) {
+            const PatternEvent& ev = M.events[pid];
+            w.push_back(((uint32_t)ev.kind << kEvKindShift) | ((uint32_t)pd.latch_of_event[pid] << kEvLatchShift) | (uint32_t)ev.atom);
+        }
+        std::sort(w.begin(), w.end());  // kind is the most significant field: FIRE, TEST, CLEAR, SET
+        out_words.insert(out_words.end(), w.begin(), w.end());
+    };
     for (size_t u = 0; u < pend.size(); ++u) {
         const Dfa& d = pend[u].dfa;
         UnitDesc ud;
@@ -210,22 +236,24 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
         H.arena.insert(H.arena.end(), tb, tb + d.trans.size() * 2);
         ud.acc_base = (uint32_t)H.acc_idx.size();
         for (int s = d.acc_lo; s < d.n_states; ++s) {
-            H.acc_idx.push_back((uint32_t)H.acc_atoms.size());
-            for (int a : d.acc[s]) H.acc_atoms.push_back((uint16_t)a);
+            H.acc_idx.push_back((uint32_t)H.acc_events.size());
+            emit_events(pend[u], d.acc[s], H.acc_events);
         }
-        H.acc_idx.push_back((uint32_t)H.acc_atoms.size());
+        H.acc_idx.push_back((uint32_t)H.acc_events.size());
         ud.end_base = (uint32_t)H.end_idx.size();
         for (int s = 0; s < d.n_states; ++s) {
-            H.end_idx.push_back((uint32_t)H.end_atoms.size());
-            for (int a : d.endacc[s]) H.end_atoms.push_back((uint16_t)a);
+            H.end_idx.push_back((uint32_t)H.end_events.size());
+            emit_events(pend[u], d.endacc[s], H.end_events);
             if (!d.endacc[s].empty()) ud.end_any = 1;
         }
-        H.end_idx.push_back((uint32_t)H.end_atoms.size());
+        H.end_idx.push_back((uint32_t)H.end_events.size());
+        ud.hot_states = ud.n_states;
+        ud.hot_off = ud.tbl_off;
         H.units.push_back(ud);
     }
     pad16(H.arena);
-    if (H.acc_atoms.empty()) H.acc_atoms.push_back(0);
-    if (H.end_atoms.empty()) H.end_atoms.push_back(0);
+    if (H.acc_events.empty()) H.acc_events.push_back(0);
+    if (H.end_events.empty()) H.end_events.push_back(0);
 
     // ---- non-scan atoms ----------------------------------------------------------------
     H.iset_off.assign(1, 0);
@@ -280,6 +308,40 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
         if (!build_lpm(M.ip_sets, geo_mmdb, &H.lpm, err)) return false;
     }
     return true;
+}
+
+void build_smem_image(const HostProgram& H, size_t budget, std::vector<uint8_t>* image, std::vector<UnitDesc>* units) {
+    *units = H.units;
+    image->clear();
+    const size_t U = H.units.size();
+    image->insert(image->end(), H.arena.begin(), H.arena.begin() + U * 256);  // class maps keep their arena offsets
+    if (budget < image->size()) budget = image->size();
+    size_t left = budget - image->size();
+    left = left > 16 * U ? left - 16 * U : 0;  // padding slack
+    // expected bytes per request of each field decide who gets shared memory first
+    static const double kWeight[N_FIELDS] = {13, 240, 35, 3, 95};
+    std::vector<size_t> give(U, 0), order(U);
+    auto row_bytes = [&](size_t u) { return (size_t)H.units[u].n_classes * 2; };
+    // every unit first gets the neighbourhood of its start state, then the rest by expected traffic
+    for (size_t u = 0; u < U; ++u) {
+        order[u] = u;
+        size_t rows = std::min<size_t>(H.units[u].n_states, 32);
+        if (rows * row_bytes(u) <= left) { give[u] = rows; left -= rows * row_bytes(u); }
+    }
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return kWeight[H.units[a].field] > kWeight[H.units[b].field]; });
+    for (size_t u : order) {
+        size_t add = std::min<size_t>(H.units[u].n_states - give[u], left / row_bytes(u));
+        give[u] += add;
+        left -= add * row_bytes(u);
+    }
+    for (size_t u = 0; u < U; ++u) {
+        while (image->size() % 16) image->push_back(0);
+        (*units)[u].hot_states = (uint32_t)give[u];
+        (*units)[u].hot_off = (uint32_t)image->size();
+        const uint8_t* src = H.arena.data() + H.units[u].tbl_off;
+        image->insert(image->end(), src, src + give[u] * row_bytes(u));
+    }
+    while (image->size() % 16) image->push_back(0);
 }
 
 }  // namespace pgw

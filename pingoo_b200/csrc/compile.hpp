@@ -29,9 +29,9 @@ struct HostProgram {
     std::vector<UnitDesc> units;
     std::vector<uint8_t> arena;  // class maps then transition tables (16-byte aligned pieces)
     std::vector<uint32_t> acc_idx;
-    std::vector<uint16_t> acc_atoms;
+    std::vector<uint32_t> acc_events;  // event words (program.hpp), sorted by kind within each list
     std::vector<uint32_t> end_idx;
-    std::vector<uint16_t> end_atoms;
+    std::vector<uint32_t> end_events;
     uint32_t n_atoms = 0, atom_words = 0;
     std::vector<uint32_t> expect;  // expected atom values (perf heuristic only)
     std::vector<uint32_t> care;    // atoms referenced by at least one rule
@@ -60,6 +60,11 @@ struct HostProgram {
 // `geo_mmdb` may be empty (no database: every client is {0,"XX"}, http_listener.rs:156).
 bool compile_program(Model& model, const CompileOptions& opt, const std::vector<uint8_t>& geo_mmdb, HostProgram* out,
                      std::string& err);
+
+// Shared-memory image: every class map, then for each unit the rows of its first `hot_states` states
+// (BFS order from the start state, so these are the shallow, frequently visited ones).  Fills
+// units[u].hot_states / units[u].hot_off so that the image fits `budget_bytes`.
+void build_smem_image(const HostProgram& prog, size_t budget_bytes, std::vector<uint8_t>* image, std::vector<UnitDesc>* units);
 
 // lists (pingoo/lists.rs:62-113)
 bool parse_list_csv(const std::string& name, ListType type, const uint8_t* csv, size_t len, ListData* out, std::string& err);

@@ -286,15 +286,21 @@ namespace {
 
 struct Grouper {
     const Nfa& nfa;
-    const std::vector<int>& starts;
+    const std::vector<PatternBundle>& bundles;
     int max_states;
     size_t max_bytes;
+    int max_latches;
     DfaGroups* out;
     int failed = -1;
 
     bool try_build(const std::vector<int>& idx, Dfa* d) {
         std::vector<int> s;
-        for (int i : idx) s.push_back(starts[i]);
+        int latches = 0;
+        for (int i : idx) {
+            s.insert(s.end(), bundles[i].starts.begin(), bundles[i].starts.end());
+            latches += bundles[i].has_latch;
+        }
+        if (latches > max_latches) return false;
         // allow the raw construction some slack over the post-minimisation cap
         if (!build_dfa(nfa, s, max_states * 4, d)) return false;
         return d->n_states <= max_states && d->table_bytes() <= max_bytes;
@@ -316,13 +322,13 @@ struct Grouper {
 
 }  // namespace
 
-bool build_dfa_groups(const Nfa& nfa, const std::vector<int>& starts, int max_states, size_t max_table_bytes,
-                      DfaGroups* out, int* failed_index) {
+bool build_dfa_groups(const Nfa& nfa, const std::vector<PatternBundle>& bundles, int max_states, size_t max_table_bytes,
+                      int max_latches, DfaGroups* out, int* failed_index) {
     out->dfas.clear();
     out->members.clear();
-    if (starts.empty()) return true;
-    Grouper G{nfa, starts, max_states, max_table_bytes, out};
-    std::vector<int> all(starts.size());
+    if (bundles.empty()) return true;
+    Grouper G{nfa, bundles, max_states, max_table_bytes, max_latches, out};
+    std::vector<int> all(bundles.size());
     for (size_t i = 0; i < all.size(); ++i) all[i] = (int)i;
     if (!G.split(all)) {
         if (failed_index) *failed_index = G.failed;

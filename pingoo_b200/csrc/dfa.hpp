@@ -30,14 +30,21 @@ struct Dfa {
 // Returns false if the (unminimised) subset construction exceeds `max_raw_states`.
 bool build_dfa(const Nfa& nfa, const std::vector<int>& starts, int max_raw_states, Dfa* out);
 
-struct DfaGroups {
-    std::vector<Dfa> dfas;
-    std::vector<std::vector<int>> members;  // indices into `starts`
+// A bundle = the NFA patterns of one atom (1 normally, 2-3 for a gap-split pattern: they share a latch
+// and therefore must land in the same DFA).
+struct PatternBundle {
+    std::vector<int> starts;
+    bool has_latch = false;
 };
 
-// Partition patterns into as few DFAs as possible subject to the caps.
-// Returns false (with *failed_index set) if a single pattern alone exceeds the caps.
-bool build_dfa_groups(const Nfa& nfa, const std::vector<int>& starts, int max_states, size_t max_table_bytes,
-                      DfaGroups* out, int* failed_index);
+struct DfaGroups {
+    std::vector<Dfa> dfas;
+    std::vector<std::vector<int>> members;  // indices into `bundles`
+};
+
+// Partition bundles into as few DFAs as possible subject to the caps (and at most `max_latches` latch
+// bundles per DFA).  Returns false (with *failed_index set) if a single bundle alone exceeds the caps.
+bool build_dfa_groups(const Nfa& nfa, const std::vector<PatternBundle>& bundles, int max_states, size_t max_table_bytes,
+                      int max_latches, DfaGroups* out, int* failed_index);
 
 }  // namespace pgw

@@ -4,20 +4,23 @@
 //   ctx build (http_listener.rs:239-249) -> rule loop (http_listener.rs:251-264)
 //   -> bel::Program::execute (pingoo/rules.rs:36-52) -> regex / list / geoip work.
 //
-// Work decomposition
-//   tile  = 2^tile_log2 consecutive requests, owned by one CTA (static round robin)
-//   item  = (request in tile, scan unit); scan unit = one DFA over one string field
-//   lanes claim items dynamically (warp-aggregated shared-memory atomic); units are ordered
-//   longest field first so the tile tail consists of the shortest items.
+// Work decomposition (streaming, no tiles, no block-level barriers after set-up)
+//   Each lane owns one request at a time and walks its scan units (one DFA over one string field)
+//   in sequence; a warp claims kClaim requests at a time from a global counter and its lanes take
+//   them as they become free, so a long URL only delays its own lane.
 // Data movement
-//   request bytes: each lane streams its item with 128-bit ld.global.nc loads, one chunk
-//     prefetched a full iteration ahead (covers HBM latency with 32 resident warps);
-//   DFA tables + class maps: staged once per CTA into shared memory with TMA bulk copies
-//     (cp.async.bulk + mbarrier) when they fit, else read through L1 with ld.global.nc;
-//   atom hit bits: per-tile bitmap in shared memory (atomicOr on the rare accept events).
-// Epilogue (per request): list/int/country/GeoIP predicates, then verdict = first matching
-//   rule with a terminal action; requests whose atom vector equals the expected vector take
-//   the precomputed verdict, others evaluate only the rules that reference a changed atom.
+//   request bytes: each lane streams its field with 128-bit ld.global.nc loads; the chunk for the
+//     next iteration (same field, next field, or next request) is issued a full iteration ahead;
+//   DFA tables: class maps + the rows of the shallow ("hot") states of every DFA are staged once
+//     per CTA into shared memory by TMA bulk copies (cp.async.bulk + mbarrier); deeper states are
+//     read from the full tables in global memory (L1/L2);
+//   atom hit bits: two private bitmap rows per lane in shared memory (no atomics).
+// Events (rare): DFA accept states carry event lists: FIRE atom / SET, TEST, CLEAR of a per-unit
+//   latch register (gap-split patterns such as `<tag[^>]*>`, see regex.hpp).
+// Epilogue: finished requests wait in the lane's second row and are flushed a warp at a time:
+//   list/int/country/GeoIP predicates, gates, then verdict = first matching rule with a terminal
+//   action; a request whose atom vector equals the expected vector takes the precomputed verdict,
+//   otherwise only rules that reference a changed atom are evaluated.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -65,44 +68,50 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint8_t* p) {
 }
 
 struct SmemLayout {
-    uint32_t arena, units, offs, bits, misc, total;
+    uint32_t image, units, rows, misc, total;
 };
 
 __host__ __device__ inline uint32_t r16(uint32_t x) { return (x + 15u) & ~15u; }
 
-__host__ __device__ inline SmemLayout smem_layout(const KParams& p, bool smem_tables, uint32_t tile_log2) {
+__host__ __device__ inline SmemLayout smem_layout(uint32_t image_bytes, uint32_t n_units, uint32_t atom_words) {
     SmemLayout L;
-    uint32_t T = 1u << tile_log2;
     uint32_t o = 0;
-    L.arena = o;
-    o += r16(smem_tables ? p.arena_bytes : p.cls_bytes);
+    L.image = o;
+    o += r16(image_bytes);
     L.units = o;
-    o += r16(p.n_units * (uint32_t)sizeof(UnitDesc));
-    L.offs = o;
-    o += r16(p.n_slots * (T + 1) * 4u);
-    L.bits = o;
-    o += r16(T * p.atom_words * 4u);
+    o += r16(n_units * (uint32_t)sizeof(UnitDesc));
+    L.rows = o;
+    o += r16((uint32_t)kThreads * kRowsPerLane * atom_words * 4u);
     L.misc = o;
     o += 64;
     L.total = o;
     return L;
 }
 
-// OR the atoms of CSR row `row` into the request's bitmap (rare path)
-__device__ __noinline__ void fire_atoms(const uint32_t* __restrict__ idx, const uint16_t* __restrict__ atoms, uint32_t row,
-                                        uint32_t* bits) {
+// Apply the events of CSR row `row` (sorted FIRE, TEST, CLEAR, SET) to the lane's bitmap and latch register.
+// Returns true if every event was a plain FIRE (idempotent: the caller may skip an immediate repeat).
+__device__ __noinline__ bool run_events(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ events, uint32_t row,
+                                        uint32_t* bits, uint32_t stride, uint32_t* latch) {
     uint32_t a = __ldg(idx + row), b = __ldg(idx + row + 1);
+    bool pure = true;
+    uint32_t l = *latch;
     for (uint32_t i = a; i < b; ++i) {
-        uint32_t at = __ldg(atoms + i);
-        atomicOr(bits + (at >> 5), 1u << (at & 31));
+        const uint32_t e = __ldg(events + i);
+        const uint32_t kind = e >> kEvKindShift, lb = 1u << ((e >> kEvLatchShift) & 31u), at = e & kEvAtomMask;
+        if (kind == 0u || (kind == 1u && (l & lb))) bits[(at >> 5) * stride] |= 1u << (at & 31);
+        else if (kind == 2u) l &= ~lb;
+        else if (kind == 3u) l |= lb;
+        pure &= kind == 0u;
     }
+    *latch = l;
+    return pure;
 }
 
-__device__ __forceinline__ bool eval_rule(const uint16_t* __restrict__ code, uint32_t a, uint32_t b, const uint32_t* row) {
+__device__ __forceinline__ bool eval_rule(const uint16_t* __restrict__ code, uint32_t a, uint32_t b, const uint32_t* row, uint32_t stride) {
     uint32_t st = 0;
     for (uint32_t i = a; i < b; ++i) {
         uint32_t op = __ldg(code + i);
-        if (op < 0x4000u) st = (st << 1) | ((row[op >> 5] >> (op & 31)) & 1u);
+        if (op < 0x4000u) st = (st << 1) | ((row[(op >> 5) * stride] >> (op & 31)) & 1u);
         else if (op == OP_NOT) st ^= 1u;
         else if (op == OP_AND) st = ((st >> 1) & ~1u) | (st & (st >> 1) & 1u);
         else if (op == OP_OR) st = ((st >> 1) & ~1u) | ((st | (st >> 1)) & 1u);
@@ -135,142 +144,277 @@ __device__ __forceinline__ uint32_t lpm_lookup(const KParams& p, const uint8_t* 
     return __ldg(p.v6_leaf + l);
 }
 
-template <bool SMEM_TABLES>
+// Per-request predicates outside the byte scan + the verdict (http_listener.rs:196-264).
+// `row[w * stride]` is the request's atom bitmap (scan atoms already set).
+__device__ __noinline__ void request_epilogue(const KParams& p, uint32_t r, uint32_t* row, uint32_t stride) {
+    const uint32_t Aw = p.atom_words;
+    const uint32_t flags = p.flags ? p.flags[r] : 0u;
+    int64_t asn = 0;
+    uint32_t country = (uint32_t)'X' | ((uint32_t)'X' << 8);
+    uint32_t set_mask = 0;
+    if (p.need_lpm) {
+        const uint8_t* ip16 = p.ip + (size_t)r * 16;
+        const bool v6 = p.is_v6[r] != 0;
+        const LpmLeaf lf = p.leaves[lpm_lookup(p, ip16, v6)];
+        set_mask = lf.set_mask;
+        if (p.geo_loaded && p.asn == nullptr) {
+            // geoip.rs:74-76: loopback / multicast are never looked up
+            bool skip;
+            if (!v6) skip = ip16[0] == 127 || (ip16[0] >> 4) == 0xE;
+            else {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(ip16);
+                skip = ip16[0] == 0xFF || (w[0] == 0 && w[1] == 0 && w[2] == 0 && w[3] == 0x01000000u);
+            }
+            if (!skip) { asn = lf.asn; country = lf.country; }
+        }
+    }
+    if (p.asn) asn = p.asn[r];
+    if (p.country) country = p.country[r];
+
+    for (uint32_t i = 0; i < p.n_ns; ++i) {
+        const NsAtom a = p.ns[i];
+        bool v = false;
+        if (a.kind == 1 || a.kind == 2) {  // INT_CMP / INT_SET
+            int64_t x;
+            if (a.feat == 0) x = p.port ? (int64_t)p.port[r] : 0;
+            else if (a.feat == 1) x = asn;
+            else {
+                const uint32_t* o = p.off[a.feat - 2] + r;
+                x = (int64_t)(o[1] - o[0]);
+            }
+            if (a.kind == 1) {
+                switch (a.op) {
+                    case 0: v = x == a.cval; break;
+                    case 1: v = x != a.cval; break;
+                    case 2: v = x < a.cval; break;
+                    case 3: v = x <= a.cval; break;
+                    case 4: v = x > a.cval; break;
+                    default: v = x >= a.cval; break;
+                }
+            } else {
+                uint32_t l = p.iset_off[a.set_id], h = p.iset_off[a.set_id + 1];
+                while (l < h) {
+                    uint32_t m = (l + h) >> 1;
+                    int64_t mv = __ldg(p.iset_vals + m);
+                    if (mv == x) { v = true; break; }
+                    if (mv < x) l = m + 1;
+                    else h = m;
+                }
+            }
+        } else if (a.kind == 3) {  // IP_SET
+            v = (set_mask >> a.set_id) & 1u;
+        } else {  // COUNTRY_SET
+            uint32_t c0 = (country & 0xFFu) - 'A', c1 = ((country >> 8) & 0xFFu) - 'A';
+            if (c0 < 26u && c1 < 26u) {
+                uint32_t bit = c0 * 26u + c1;
+                v = (__ldg(p.cset + a.set_id * kCountryWords + (bit >> 5)) >> (bit & 31)) & 1u;
+            }
+        }
+        if (v) row[(a.atom >> 5) * stride] |= 1u << (a.atom & 31);
+    }
+
+    const uint32_t cv = flags & RF_CAPTCHA_VERIFIED;
+    uint32_t verdict = V_ALLOW | (kNoRule << 2);
+    bool decided = false;
+    if (flags & RF_PRE_BLOCK) { verdict = V_BLOCK | (kNoRule << 2); decided = true; }
+    if (!decided && p.eval_gates) {
+        // http_listener.rs:196-198: empty or over-long user agent is blocked before any rule
+        const uint32_t* o = p.off[4] + r;
+        uint32_t ual = o[1] - o[0];
+        if (ual == 0 || ual >= 256) { verdict = V_BLOCK | (kNoRule << 2); decided = true; }
+    }
+    if (!decided) {
+        bool bypass = flags & RF_BYPASS;
+        if (p.eval_gates && p.gate_atom >= 0) bypass |= (row[(p.gate_atom >> 5) * stride] >> (p.gate_atom & 31)) & 1u;
+        if (bypass) { verdict = V_BYPASS | (kNoRule << 2); decided = true; }
+    }
+    if (!decided && (flags & RF_PRE_CAPTCHA)) { verdict = V_CAPTCHA | (kNoRule << 2); decided = true; }
+    if (!decided) {
+        uint32_t diff = 0;
+        for (uint32_t w = 0; w < Aw; ++w) diff |= (row[w * stride] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
+        if (diff == 0) verdict = p.v0[cv];
+        else {
+            const uint32_t tshift = 2 * cv;
+            uint32_t best = kNoRule;
+            for (uint32_t w = 0; w < Aw; ++w) {
+                uint32_t x = (row[w * stride] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
+                while (x) {
+                    uint32_t b = __ffs(x) - 1;
+                    x &= x - 1;
+                    uint32_t atom = w * 32 + b;
+                    uint32_t i0 = __ldg(p.ar_idx + atom), i1 = __ldg(p.ar_idx + atom + 1);
+                    for (uint32_t i = i0; i < i1; ++i) {
+                        uint32_t rule = __ldg(p.ar_rules + i);
+                        if (rule >= best) break;  // lists are ascending
+                        if (((__ldg(p.term + rule) >> tshift) & 3u) == 0) continue;
+                        if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row, stride)) best = rule;
+                    }
+                }
+            }
+            for (uint32_t i = 0; i < p.n_dflt[cv]; ++i) {
+                uint32_t rule = __ldg(p.dflt[cv] + i);
+                if (rule >= best) break;
+                if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row, stride)) best = rule;
+            }
+            if (best == kNoRule) verdict = V_ALLOW | (kNoRule << 2);
+            else verdict = ((__ldg(p.term + best) >> tshift) & 3u) | (best << 2);
+        }
+    }
+    p.verdict[r] = verdict;
+}
+
 __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t T = 1u << p.tile_log2;
-    const SmemLayout L = smem_layout(p, SMEM_TABLES, p.tile_log2);
-    uint8_t* s_arena = smem + L.arena;
+    const SmemLayout L = smem_layout(p.image_bytes, p.n_units, p.atom_words);
+    uint8_t* s_img = smem + L.image;
     UnitDesc* s_units = reinterpret_cast<UnitDesc*>(smem + L.units);
-    uint32_t* s_offs = reinterpret_cast<uint32_t*>(smem + L.offs);
-    uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem + L.bits);
+    uint32_t* s_rows = reinterpret_cast<uint32_t*>(smem + L.rows);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L.misc);
-    int* s_next = reinterpret_cast<int*>(smem + L.misc + 16);
 
-    const int tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31;
     const uint32_t Aw = p.atom_words;
+    const uint32_t U = p.n_units;
 
-    // ---- one-time staging: tables via TMA bulk copies, unit descriptors by plain loads ----
+    // ---- one-time staging: table image via TMA bulk copies, unit descriptors by plain loads ----
     if (tid == 0) {
         mbar_init(s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const uint32_t stage_bytes = r16(SMEM_TABLES ? p.arena_bytes : p.cls_bytes);
+    const uint32_t stage_bytes = r16(p.image_bytes);
     if (tid == 0 && stage_bytes) {
         mbar_expect_tx(s_bar, stage_bytes);
         for (uint32_t o = 0; o < stage_bytes; o += 32768u) {
             uint32_t n = stage_bytes - o < 32768u ? stage_bytes - o : 32768u;
-            bulk_g2s(s_arena + o, p.arena + o, n, s_bar);
+            bulk_g2s(s_img + o, p.image + o, n, s_bar);
         }
     }
-    for (uint32_t i = tid; i < p.n_units * (sizeof(UnitDesc) / 4); i += kThreads)
+    for (uint32_t i = tid; i < U * (sizeof(UnitDesc) / 4); i += kThreads)
         reinterpret_cast<uint32_t*>(s_units)[i] = __ldg(reinterpret_cast<const uint32_t*>(p.units) + i);
     if (stage_bytes) mbar_wait(s_bar, 0);
     __syncthreads();
 
-    const uint32_t total_units = p.n_units;
+    // private bitmap rows: word w of row k of this lane lives at s_rows[(k * Aw + w) * kThreads + tid]
+    const uint32_t stride = kThreads;
+    uint32_t* my_rows = s_rows + tid;
 
-    for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const uint32_t tile0 = tile << p.tile_log2;
-        const uint32_t T_eff = min(T, p.n - tile0);
-
-        // ---- tile prologue: offsets of every needed field, cleared hit bitmap ----
-        for (uint32_t f = 0; f < 5; ++f) {
-            int sl = p.slot[f];
-            if (sl < 0) continue;
-            const uint32_t* src = p.off[f] + tile0;
-            uint32_t* dst = s_offs + sl * (T + 1);
-            for (uint32_t i = tid; i <= T_eff; i += kThreads) dst[i] = __ldg(src + i);
+    if (U == 0) {
+        // no string predicate at all: only the per-request epilogue runs
+        for (uint32_t r = blockIdx.x * kThreads + tid; r < p.n; r += gridDim.x * kThreads) {
+            for (uint32_t w = 0; w < Aw; ++w) my_rows[w * stride] = 0;
+            request_epilogue(p, r, my_rows, stride);
         }
-        for (uint32_t i = tid; i < T_eff * Aw; i += kThreads) s_bits[i] = 0;
-        if (tid == 0) *s_next = 0;
-        __syncthreads();
+        return;
+    }
 
-        // ---- scan: dynamic items, one 16-byte chunk per lane per iteration ----
-        const uint32_t total_items = total_units << p.tile_log2;
-        bool c_have = false, n_have = false, exhausted = (total_units == 0);
-        uint32_t c_base = 0, c_start = 0, c_end = 0, c_state = 0, c_C = 0, c_acclo = 0, c_tbl = 0, c_cls = 0, c_unit = 0, c_t = 0;
-        uint32_t c_last = 0xFFFFFFFFu;
-        const uint8_t* c_col = nullptr;
-        uint32_t n_item = 0, n_start = 0, n_end = 0;
-        const uint8_t* n_col = nullptr;
-        uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
+    // ---- per-lane state ----
+    bool c_have = false, n_have = false;
+    uint32_t c_req = 0, c_unit = 0, c_rowi = 0;
+    uint32_t c_base = 0, c_start = 0, c_end = 0, c_state = 0, c_C = 0, c_acclo = 0, c_hot = 0, c_hotoff = 0, c_tbl = 0, c_cls = 0;
+    uint32_t c_latch = 0, c_last = 0xFFFFFFFFu;
+    const uint8_t* c_col = nullptr;
+    uint32_t n_req = 0, n_unit = 0, n_rowi = 0, n_start = 0, n_end = 0;
+    const uint8_t* n_col = nullptr;
+    bool p_have = false;
+    uint32_t p_req = 0, p_rowi = 0;
+    uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
+    // warp-uniform pool of claimed requests
+    uint32_t pool_next = 0, pool_end = 0;
+    bool pool_dry = p.n == 0;
 
-        auto claim = [&](bool want) {
-            // warp-aggregated claim of the next item ids
-            uint32_t need = __ballot_sync(0xFFFFFFFFu, want && !exhausted);
-            if (need == 0) return;
-            uint32_t base = 0;
-            int leader = __ffs(need) - 1;
-            if ((int)lane == leader) base = (uint32_t)atomicAdd(s_next, __popc(need));
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (want && !exhausted) {
-                uint32_t id = base + __popc(need & ((1u << lane) - 1u));
-                if (id >= total_items) exhausted = true;
-                else {
-                    uint32_t u = id >> p.tile_log2, t = id & (T - 1);
-                    if (t < T_eff) {
-                        const UnitDesc& ud = s_units[u];
-                        const uint32_t* o = s_offs + ud.field_slot * (T + 1) + t;
-                        n_item = id;
-                        n_start = o[0];
-                        n_end = o[1];
-                        n_col = p.col[ud.field];
-                        n_have = true;
-                    }
-                }
+    auto flush = [&]() {
+        if (p_have) request_epilogue(p, p_req, my_rows + p_rowi * Aw * stride, stride);
+        p_have = false;
+    };
+
+    for (;;) {
+        // ---- (1) rotate: continue the current unit or adopt the prefetched one ----
+        if (c_have) {
+            c_base += kChunk;
+            cur = nxt;
+        } else if (n_have) {
+            const UnitDesc& ud = s_units[n_unit];
+            c_req = n_req;
+            c_unit = n_unit;
+            c_rowi = n_rowi;
+            c_start = n_start;
+            c_end = n_end;
+            c_base = n_start & ~15u;
+            c_col = n_col;
+            c_state = ud.start_state;
+            c_C = ud.n_classes;
+            c_acclo = ud.acc_lo;
+            c_hot = ud.hot_states;
+            c_hotoff = ud.hot_off;
+            c_tbl = ud.tbl_off;
+            c_cls = ud.cls_off;
+            c_latch = 0;
+            c_last = 0xFFFFFFFFu;
+            cur = nxt;
+            c_have = true;
+            n_have = false;
+        }
+        const bool any_have = __any_sync(0xFFFFFFFFu, c_have);
+        if (!any_have && pool_dry && pool_next == pool_end) {
+            flush();
+            break;
+        }
+
+        // ---- (2) plan the chunk each lane consumes in the NEXT iteration ----
+        const bool finishing = c_have && (c_end <= c_base + kChunk);
+        const bool last_unit = c_unit + 1 >= U;
+        const bool need_same = finishing && !last_unit;
+        bool need_new = (finishing && last_unit) || (!c_have && !n_have);
+        // a lane about to take a third request must first get its pending one evaluated
+        if (__any_sync(0xFFFFFFFFu, need_new && finishing && p_have)) flush();
+        const uint32_t need_mask = __ballot_sync(0xFFFFFFFFu, need_new);
+        bool got_new = false;
+        if (need_mask) {
+            if (pool_next == pool_end && !pool_dry) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(p.work_counter, kClaim);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (base >= p.n) pool_dry = true;
+                else { pool_next = base; pool_end = min(base + kClaim, p.n); }
             }
-        };
-
-        claim(true);
-        if (n_have) nxt = ld_nc_v4(n_col + (n_start & ~15u));
-
-        for (;;) {
-            // rotate: continue the current item or adopt the claimed one
-            if (c_have) {
-                c_base += kChunk;
-                cur = nxt;
-            } else if (n_have) {
-                uint32_t u = n_item >> p.tile_log2;
-                const UnitDesc& ud = s_units[u];
-                c_unit = u;
-                c_t = n_item & (T - 1);
-                c_start = n_start;
-                c_end = n_end;
-                c_base = n_start & ~15u;
-                c_col = n_col;
-                c_state = ud.start_state;
-                c_C = ud.n_classes;
-                c_acclo = ud.acc_lo;
-                c_tbl = ud.tbl_off;
-                c_cls = ud.cls_off;
-                c_last = 0xFFFFFFFFu;
-                cur = nxt;
-                c_have = true;
-                n_have = false;
+            const uint32_t rank = __popc(need_mask & ((1u << lane) - 1u));
+            if (need_new && pool_next + rank < pool_end) {
+                n_req = pool_next + rank;
+                n_unit = 0;
+                // free row: not the one still being scanned, not the pending one
+                n_rowi = finishing ? (c_rowi ^ 1u) : (p_have ? (p_rowi ^ 1u) : 0u);
+                uint32_t* row = my_rows + n_rowi * Aw * stride;
+                for (uint32_t w = 0; w < Aw; ++w) row[w * stride] = 0;
+                got_new = true;
             }
-            if (!__any_sync(0xFFFFFFFFu, c_have)) {
-                if (__all_sync(0xFFFFFFFFu, exhausted)) break;
-                claim(true);
-                if (n_have) nxt = ld_nc_v4(n_col + (n_start & ~15u));
-                continue;
-            }
-            const bool finishing = c_have && (c_end <= c_base + kChunk);
-            claim(!c_have || finishing);
-            // issue the load this lane consumes in the NEXT iteration
-            if (c_have && !finishing) nxt = ld_nc_v4(c_col + c_base + kChunk);
-            else if (n_have) nxt = ld_nc_v4(n_col + (n_start & ~15u));
+            pool_next = min(pool_end, pool_next + (uint32_t)__popc(need_mask));
+        }
+        if (need_same) {
+            n_req = c_req;
+            n_unit = c_unit + 1;
+            n_rowi = c_rowi;
+        }
+        if (need_same || got_new) {
+            const uint32_t f = s_units[n_unit].field;
+            const uint32_t* o = p.off[f] + n_req;
+            n_start = o[0];
+            n_end = o[1];
+            n_col = p.col[f];
+            nxt = ld_nc_v4(n_col + (n_start & ~15u));
+            n_have = true;
+        } else if (c_have && !finishing) {
+            nxt = ld_nc_v4(c_col + c_base + kChunk);
+        }
 
-            // process bytes [lo, hi) of the current chunk
+        // ---- (3) process bytes [lo, hi) of the current chunk ----
+        if (any_have) {
             uint32_t lo = 0, hi = 0;
             if (c_have) {
                 lo = c_start > c_base ? c_start - c_base : 0u;
                 hi = min(c_end - c_base, (uint32_t)kChunk);
-                if (c_end <= c_base) hi = 0;  // empty item
             }
-            uint32_t* row = s_bits + c_t * Aw;
+            uint32_t* row = my_rows + c_rowi * Aw * stride;
             const uint32_t words[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
             for (int wi = 0; wi < 4; ++wi) {
@@ -281,146 +425,30 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
                     const uint32_t k = 4 * wi + bi;
                     if (k >= lo && k < hi) {
                         const uint32_t byte = (w >> (8 * bi)) & 0xFFu;
-                        const uint32_t cls = s_arena[c_cls + byte];
+                        const uint32_t cls = s_img[c_cls + byte];
                         const uint32_t idx = c_state * c_C + cls;
                         uint32_t st;
-                        if (SMEM_TABLES) st = *reinterpret_cast<const uint16_t*>(s_arena + c_tbl + 2u * idx);
+                        if (c_state < c_hot) st = *reinterpret_cast<const uint16_t*>(s_img + c_hotoff + 2u * idx);
                         else st = __ldg(reinterpret_cast<const uint16_t*>(p.arena + c_tbl) + idx);
                         c_state = st;
                         if (st >= c_acclo && st != c_last) {
-                            c_last = st;
-                            fire_atoms(p.acc_idx, p.acc_atoms, s_units[c_unit].acc_base + st - c_acclo, row);
+                            const bool pure = run_events(p.acc_idx, p.acc_events, s_units[c_unit].acc_base + st - c_acclo, row, stride, &c_latch);
+                            c_last = pure ? st : 0xFFFFFFFFu;
                         }
                     }
                 }
             }
             if (finishing) {
                 const UnitDesc& ud = s_units[c_unit];
-                if (ud.end_any) fire_atoms(p.end_idx, p.end_atoms, ud.end_base + c_state, row);
+                if (ud.end_any) run_events(p.end_idx, p.end_events, ud.end_base + c_state, row, stride, &c_latch);
                 c_have = false;
+                if (last_unit) {
+                    p_have = true;
+                    p_req = c_req;
+                    p_rowi = c_rowi;
+                }
             }
         }
-        __syncthreads();
-
-        // ---- epilogue: per-request predicates and the verdict ----
-        for (uint32_t t = tid; t < T_eff; t += kThreads) {
-            const uint32_t r = tile0 + t;
-            uint32_t* row = s_bits + t * Aw;
-            const uint32_t flags = p.flags ? p.flags[r] : 0u;
-            int64_t asn = 0;
-            uint32_t country = (uint32_t)'X' | ((uint32_t)'X' << 8);
-            uint32_t set_mask = 0;
-            if (p.need_lpm) {
-                const uint8_t* ip16 = p.ip + (size_t)r * 16;
-                const bool v6 = p.is_v6[r] != 0;
-                const LpmLeaf lf = p.leaves[lpm_lookup(p, ip16, v6)];
-                set_mask = lf.set_mask;
-                if (p.geo_loaded && p.asn == nullptr) {
-                    // geoip.rs:74-76: loopback / multicast are never looked up
-                    bool skip;
-                    if (!v6) skip = ip16[0] == 127 || (ip16[0] >> 4) == 0xE;
-                    else {
-                        const uint32_t* w = reinterpret_cast<const uint32_t*>(ip16);
-                        skip = ip16[0] == 0xFF || (w[0] == 0 && w[1] == 0 && w[2] == 0 && w[3] == 0x01000000u);
-                    }
-                    if (!skip) { asn = lf.asn; country = lf.country; }
-                }
-            }
-            if (p.asn) asn = p.asn[r];
-            if (p.country) country = p.country[r];
-
-            for (uint32_t i = 0; i < p.n_ns; ++i) {
-                const NsAtom a = p.ns[i];
-                bool v = false;
-                if (a.kind == 1 || a.kind == 2) {  // INT_CMP / INT_SET
-                    int64_t x;
-                    if (a.feat == 0) x = p.port ? (int64_t)p.port[r] : 0;
-                    else if (a.feat == 1) x = asn;
-                    else {
-                        const uint32_t* o = s_offs + p.slot[a.feat - 2] * (T + 1) + t;
-                        x = (int64_t)(o[1] - o[0]);
-                    }
-                    if (a.kind == 1) {
-                        switch (a.op) {
-                            case 0: v = x == a.cval; break;
-                            case 1: v = x != a.cval; break;
-                            case 2: v = x < a.cval; break;
-                            case 3: v = x <= a.cval; break;
-                            case 4: v = x > a.cval; break;
-                            default: v = x >= a.cval; break;
-                        }
-                    } else {
-                        uint32_t l = p.iset_off[a.set_id], h = p.iset_off[a.set_id + 1];
-                        while (l < h) {
-                            uint32_t m = (l + h) >> 1;
-                            int64_t mv = __ldg(p.iset_vals + m);
-                            if (mv == x) { v = true; break; }
-                            if (mv < x) l = m + 1;
-                            else h = m;
-                        }
-                    }
-                } else if (a.kind == 3) {  // IP_SET
-                    v = (set_mask >> a.set_id) & 1u;
-                } else {  // COUNTRY_SET
-                    uint32_t c0 = (country & 0xFFu) - 'A', c1 = ((country >> 8) & 0xFFu) - 'A';
-                    if (c0 < 26u && c1 < 26u) {
-                        uint32_t bit = c0 * 26u + c1;
-                        v = (__ldg(p.cset + a.set_id * kCountryWords + (bit >> 5)) >> (bit & 31)) & 1u;
-                    }
-                }
-                if (v) row[a.atom >> 5] |= 1u << (a.atom & 31);
-            }
-
-            const uint32_t cv = flags & RF_CAPTCHA_VERIFIED;
-            uint32_t verdict;
-            bool decided = false;
-            if (flags & RF_PRE_BLOCK) { verdict = V_BLOCK | (kNoRule << 2); decided = true; }
-            if (!decided && p.eval_gates) {
-                // http_listener.rs:196-198: empty or over-long user agent is blocked before any rule
-                const uint32_t* o = s_offs + p.slot[4] * (T + 1) + t;
-                uint32_t ual = o[1] - o[0];
-                if (ual == 0 || ual >= 256) { verdict = V_BLOCK | (kNoRule << 2); decided = true; }
-            }
-            if (!decided) {
-                bool bypass = flags & RF_BYPASS;
-                if (p.eval_gates && p.gate_atom >= 0) bypass |= (row[p.gate_atom >> 5] >> (p.gate_atom & 31)) & 1u;
-                if (bypass) { verdict = V_BYPASS | (kNoRule << 2); decided = true; }
-            }
-            if (!decided && (flags & RF_PRE_CAPTCHA)) { verdict = V_CAPTCHA | (kNoRule << 2); decided = true; }
-            if (!decided) {
-                uint32_t diff = 0;
-                for (uint32_t w = 0; w < Aw; ++w) diff |= (row[w] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
-                if (diff == 0) verdict = p.v0[cv];
-                else {
-                    const uint32_t tshift = 2 * cv;
-                    uint32_t best = kNoRule;
-                    for (uint32_t w = 0; w < Aw; ++w) {
-                        uint32_t x = (row[w] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
-                        while (x) {
-                            uint32_t b = __ffs(x) - 1;
-                            x &= x - 1;
-                            uint32_t atom = w * 32 + b;
-                            uint32_t i0 = __ldg(p.ar_idx + atom), i1 = __ldg(p.ar_idx + atom + 1);
-                            for (uint32_t i = i0; i < i1; ++i) {
-                                uint32_t rule = __ldg(p.ar_rules + i);
-                                if (rule >= best) break;  // lists are ascending
-                                if (((__ldg(p.term + rule) >> tshift) & 3u) == 0) continue;
-                                if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row)) best = rule;
-                            }
-                        }
-                    }
-                    for (uint32_t i = 0; i < p.n_dflt[cv]; ++i) {
-                        uint32_t rule = __ldg(p.dflt[cv] + i);
-                        if (rule >= best) break;
-                        if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row)) best = rule;
-                    }
-                    if (best == kNoRule) verdict = V_ALLOW | (kNoRule << 2);
-                    else verdict = ((__ldg(p.term + best) >> tshift) & 3u) | (best << 2);
-                }
-            }
-            p.verdict[r] = verdict;
-        }
-        __syncthreads();
     }
 }
 
@@ -460,7 +488,8 @@ const char* geoip_launch(const KParams& p, const uint8_t* ip, const uint8_t* is_
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
-size_t waf_smem_bytes(const KParams& p, bool smem_tables, uint32_t tile_log2) { return smem_layout(p, smem_tables, tile_log2).total; }
+size_t waf_smem_bytes(uint32_t image_bytes, uint32_t n_units, uint32_t atom_words) { return smem_layout(image_bytes, n_units, atom_words).total; }
+size_t waf_smem_fixed_bytes(uint32_t n_units, uint32_t atom_words) { return smem_layout(0, n_units, atom_words).total; }
 
 const char* waf_configure(int device, size_t* max_smem_optin, int* sm_count) {
     cudaError_t e = cudaSetDevice(device);
@@ -472,9 +501,7 @@ const char* waf_configure(int device, size_t* max_smem_optin, int* sm_count) {
     e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return cudaGetErrorString(e);
     *sm_count = v;
-    e = cudaFuncSetAttribute(waf_verdict_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*max_smem_optin);
-    if (e != cudaSuccess) return cudaGetErrorString(e);
-    e = cudaFuncSetAttribute(waf_verdict_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*max_smem_optin);
+    e = cudaFuncSetAttribute(waf_verdict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*max_smem_optin);
     if (e != cudaSuccess) return cudaGetErrorString(e);
     return nullptr;
 }
@@ -482,9 +509,10 @@ const char* waf_configure(int device, size_t* max_smem_optin, int* sm_count) {
 const char* waf_launch(const KParams& p, const LaunchPlan& plan, void* stream) {
     if (p.n == 0) return nullptr;
     cudaStream_t s = (cudaStream_t)stream;
-    if (plan.smem_tables) waf_verdict_kernel<true><<<plan.grid, kThreads, plan.smem_bytes, s>>>(p);
-    else waf_verdict_kernel<false><<<plan.grid, kThreads, plan.smem_bytes, s>>>(p);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), s);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    waf_verdict_kernel<<<plan.grid, kThreads, plan.smem_bytes, s>>>(p);
+    e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 

@@ -8,6 +8,8 @@ namespace pgw {
 
 constexpr int kThreads = 1024;      // one persistent CTA per SM, 32 warps
 constexpr int kChunk = 16;          // bytes per lane per scan iteration (one 128-bit load)
+constexpr int kRowsPerLane = 2;     // atom bitmaps per lane: the request being scanned + one awaiting its epilogue
+constexpr uint32_t kClaim = 32;     // requests a warp claims from the global counter at a time
 
 struct KParams {
     // ---- batch (device pointers, SoA) ----
@@ -21,18 +23,17 @@ struct KParams {
     const uint8_t* flags;       // n or null
     uint32_t* verdict;          // n
     uint32_t n;
-    uint32_t tile_log2;
-    uint32_t n_tiles;
+    uint32_t* work_counter;     // zeroed before each launch: next unclaimed request index
     // ---- program ----
-    const UnitDesc* units;
+    const UnitDesc* units;      // with hot_states / hot_off filled for the shared-memory image
     uint32_t n_units;
-    const uint8_t* arena;
-    uint32_t arena_bytes;
-    uint32_t cls_bytes;         // leading part of the arena holding the class maps
+    const uint8_t* arena;       // full tables (global memory)
+    const uint8_t* image;       // shared-memory image: class maps + hot rows
+    uint32_t image_bytes;
     const uint32_t* acc_idx;
-    const uint16_t* acc_atoms;
+    const uint32_t* acc_events;
     const uint32_t* end_idx;
-    const uint16_t* end_atoms;
+    const uint32_t* end_events;
     uint32_t n_atoms, atom_words;
     const uint32_t* expect;
     const uint32_t* care;
@@ -50,8 +51,6 @@ struct KParams {
     const int64_t* iset_vals;
     const uint32_t* iset_off;
     const uint32_t* cset;
-    int32_t slot[5];
-    uint32_t n_slots;
     int32_t gate_atom;
     uint32_t eval_gates;
     // ---- longest-prefix tables ----
@@ -68,14 +67,13 @@ struct KParams {
 };
 
 struct LaunchPlan {
-    bool smem_tables;
-    uint32_t tile_log2;
     size_t smem_bytes;
     int grid;
 };
 
 // host-callable wrappers (kernels.cu)
-size_t waf_smem_bytes(const KParams& p, bool smem_tables, uint32_t tile_log2);
+size_t waf_smem_bytes(uint32_t image_bytes, uint32_t n_units, uint32_t atom_words);
+size_t waf_smem_fixed_bytes(uint32_t n_units, uint32_t atom_words);  // everything except the image
 const char* waf_launch(const KParams& p, const LaunchPlan& plan, void* stream);
 const char* geoip_launch(const KParams& p, const uint8_t* ip, const uint8_t* is_v6, uint32_t n, uint32_t* asn_out,
                          uint16_t* country_out, void* stream);

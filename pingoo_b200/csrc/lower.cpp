@@ -71,13 +71,13 @@ bool BoolPool::eval(int root, const std::vector<uint8_t>& av) const {
 
 bool host_regex_is_match(const std::string& pattern, const std::string& hay, RegexStatus* st, std::string& err) {
     Nfa nfa;
-    int start = -1;
+    RegexParts parts;
     RegexInfo info;
-    *st = regex_compile(pattern, 0, nfa, &start, &info, err);
+    *st = regex_compile(pattern, 0, nfa, &parts, &info, err, /*allow_split=*/false);
     if (*st != RX_OK) return false;
     if (info.always_true) return true;
     Dfa d;
-    if (!build_dfa(nfa, {start}, 1 << 20, &d)) {
+    if (!build_dfa(nfa, {parts.start[0]}, 1 << 20, &d)) {
         *st = RX_TOO_BIG;
         err = "pattern too complex for constant folding";
         return false;
@@ -176,7 +176,9 @@ struct Lowerer {
         a.field = field;
         a.key = key;
         int id = (int)M.atoms.size();
-        a.nfa_start = nfa_literal(M.nfa[field], lit, a_start, a_end, id);
+        a.event_base = (int)M.events.size();
+        a.nfa_starts.push_back(nfa_literal(M.nfa[field], lit, a_start, a_end, a.event_base));
+        M.events.push_back(PatternEvent{EV_FIRE, id});
         return boolean(P.atom(add_atom(std::move(a))));
     }
 
@@ -190,14 +192,21 @@ struct Lowerer {
         a.key = key;
         int id = (int)M.atoms.size();
         RegexInfo info;
+        RegexParts parts;
         std::string msg;
-        RegexStatus st = regex_compile(pattern, id, M.nfa[field], &a.nfa_start, &info, msg);
+        a.event_base = (int)M.events.size();
+        RegexStatus st = regex_compile(pattern, a.event_base, M.nfa[field], &parts, &info, msg);
         if (st == RX_UNSUPPORTED) unsupported(e, "regex feature: " + msg);
         if (st != RX_OK) {
             M.warnings.push_back("rule '" + rule + "': regex does not compile (" + msg + "); evaluation is a runtime error -> no match");
             return err();
         }
         if (info.always_true) return const_bool(true);
+        for (int k = 0; k < parts.n; ++k) {
+            a.nfa_starts.push_back(parts.start[k]);
+            M.events.push_back(PatternEvent{parts.kind[k], id});
+        }
+        a.has_latch = parts.n > 1;
         return boolean(P.atom(add_atom(std::move(a))));
     }
 
@@ -220,8 +229,10 @@ struct Lowerer {
         int id = (int)M.atoms.size();
         Nfa& nfa = M.nfa[field];
         auto add = [&](NfaKind k) { NfaNode n; n.kind = k; nfa.nodes.push_back(n); return (int)nfa.nodes.size() - 1; };
+        a.event_base = (int)M.events.size();
+        M.events.push_back(PatternEvent{EV_FIRE, id});
         int m = add(N_MATCH);
-        nfa.nodes[m].pattern = id;
+        nfa.nodes[m].pattern = a.event_base;
         int eol = add(N_ASSERT);
         nfa.nodes[eol].assert_kind = A_EOL_TEXT;
         nfa.nodes[eol].out = m;
@@ -267,7 +278,7 @@ struct Lowerer {
         int bol = add(N_ASSERT);
         nfa.nodes[bol].assert_kind = A_BOL_TEXT;
         nfa.nodes[bol].out = body;
-        a.nfa_start = bol;
+        a.nfa_starts.push_back(bol);
         return boolean(P.atom(add_atom(std::move(a))));
     }
 

@@ -81,13 +81,21 @@ struct AtomDesc {
         COUNTRY_SET    // client.country in a 26x26 bitmap
     } kind;
     int field = -1;        // STR_PATTERN
-    int nfa_start = -1;    // STR_PATTERN: start node in Model::nfa[field]
+    std::vector<int> nfa_starts;  // STR_PATTERN: start node(s) in Model::nfa[field]; pattern id of part k = event_base + k
+    int event_base = -1;          // STR_PATTERN: first index into Model::events
+    bool has_latch = false;       // STR_PATTERN: gap-split pattern (RegexParts) needing one latch bit in its scan unit
     int feat = -1;         // INT_*
     int op = 0;            // INT_CMP
     int64_t cval = 0;      // INT_CMP
     int set_id = -1;       // INT_SET / IP_SET / COUNTRY_SET
     int pos_refs = 0, neg_refs = 0;  // polarity statistics -> expected value heuristic
     std::string key;       // dedupe key / debug description
+};
+
+// What the DFA reports for NFA pattern id i (= index into Model::events)
+struct PatternEvent {
+    uint8_t kind;  // EventKind
+    int atom;
 };
 
 struct RuleModel {
@@ -105,6 +113,7 @@ struct GeoRecord {
 struct Model {
     BoolPool pool;
     std::vector<AtomDesc> atoms;
+    std::vector<PatternEvent> events;
     std::unordered_map<std::string, int> atom_index;
     Nfa nfa[N_FIELDS];
     std::vector<std::vector<int64_t>> int_sets;

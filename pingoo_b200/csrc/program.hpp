@@ -20,6 +20,13 @@ enum ReqFlags : uint8_t {
     RF_BYPASS = 8             // request is for the captcha API itself (http_listener.rs:200-204)
 };
 
+// DFA accept-event word (uint32): kind << 30 | latch << 24 | atom.  Kinds follow regex.hpp EventKind:
+//   0 FIRE  atom := 1                     1 TEST  if latch set: atom := 1
+//   2 CLEAR latch := 0                    3 SET   latch := 1
+// Lists are sorted by kind, which is also the order events of one position must be applied in.
+constexpr uint32_t kEvKindShift = 30, kEvLatchShift = 24, kEvAtomMask = 0x3FFF;
+constexpr uint32_t kMaxLatchesPerUnit = 32;
+
 // rule bytecode (uint16): 0x0000..0x3FFF push atom, else opcode
 enum RuleOp : uint16_t { OP_NOT = 0x4000, OP_AND = 0x4001, OP_OR = 0x4002, OP_PUSH0 = 0x4003, OP_PUSH1 = 0x4004 };
 
@@ -32,11 +39,13 @@ struct UnitDesc {
     uint32_t acc_lo;       // states >= acc_lo fire accept events
     uint32_t tbl_off;      // byte offset of uint16 trans[n_states][n_classes] in the table arena
     uint32_t cls_off;      // byte offset of the 256-byte class map in the table arena
-    uint32_t acc_base;     // acc_idx[acc_base + (s - acc_lo)] .. [+1] -> range in acc_atoms
-    uint32_t end_base;     // end_idx[end_base + s] .. [+1] -> range in end_atoms
+    uint32_t acc_base;     // acc_idx[acc_base + (s - acc_lo)] .. [+1] -> range in acc_events
+    uint32_t end_base;     // end_idx[end_base + s] .. [+1] -> range in end_events
     uint32_t end_any;      // 0 if no state of this DFA has end-of-input accepts (skip finalisation)
     uint32_t field_slot;   // index among the fields that are actually scanned
-    uint32_t pad;
+    uint32_t hot_states;   // states < hot_states have their rows in the shared-memory image
+    uint32_t hot_off;      // byte offset of those rows in the shared-memory image
+    uint32_t pad[3];
 };
 
 // predicates evaluated once per request outside the byte scan

@@ -697,8 +697,12 @@ struct Emitter {
 
 }  // namespace
 
-RegexStatus regex_compile(const std::string& pattern, int pattern_id, Nfa& nfa, int* start, RegexInfo* info,
-                          std::string& err) {
+static int popcount_set(const ByteSet& s) {
+    return __builtin_popcountll(s.w[0]) + __builtin_popcountll(s.w[1]) + __builtin_popcountll(s.w[2]) + __builtin_popcountll(s.w[3]);
+}
+
+RegexStatus regex_compile(const std::string& pattern, int first_pattern_id, Nfa& nfa, RegexParts* parts, RegexInfo* info,
+                          std::string& err, bool allow_split) {
     std::vector<Ast> pool;
     RegexInfo local;
     size_t nodes0 = nfa.nodes.size(), sets0 = nfa.sets.size();
@@ -707,9 +711,63 @@ RegexStatus regex_compile(const std::string& pattern, int pattern_id, Nfa& nfa, 
         int root = p.parse();
         local.always_true = nullable_no_assert(pool, root);
         Emitter em{nfa, pool, nodes0};
-        int m = em.node(N_MATCH);
-        nfa.nodes[m].pattern = pattern_id;
-        *start = em.emit(root, m);
+        *parts = RegexParts();
+
+        // ---- gap split:  X G* S  ------------------------------------------------------------
+        bool split = false;
+        if (allow_split && !local.always_true && pool[root].kind == Ast::CONCAT && pool[root].kids.size() >= 3) {
+            const std::vector<int>& it = pool[root].kids;
+            const Ast& last = pool[it[it.size() - 1]];
+            const Ast& rep = pool[it[it.size() - 2]];
+            if (last.kind == Ast::SET && !last.set.empty() && rep.kind == Ast::REPEAT && rep.max < 0 && pool[rep.kids[0]].kind == Ast::SET &&
+                rep.min <= 4) {
+                ByteSet G = pool[rep.kids[0]].set;
+                ByteSet notG = G;
+                notG.negate();
+                if (popcount_set(notG) <= 4) {
+                    // prefix = items[0 .. n-2) followed by `min` mandatory copies of G
+                    int pre = (int)pool.size();
+                    pool.emplace_back();
+                    pool[pre].kind = Ast::CONCAT;
+                    for (size_t k = 0; k + 2 < pool[root].kids.size(); ++k) pool[pre].kids.push_back(pool[root].kids[k]);
+                    int gchild = pool[pool[root].kids[pool[root].kids.size() - 2]].kids[0];
+                    int gmin = pool[pool[root].kids[pool[root].kids.size() - 2]].min;
+                    for (int k = 0; k < gmin; ++k) pool[pre].kids.push_back(gchild);
+                    if (!nullable_no_assert(pool, pre)) {
+                        int m0 = em.node(N_MATCH);
+                        nfa.nodes[m0].pattern = first_pattern_id;
+                        parts->start[0] = em.emit(pre, m0);
+                        parts->kind[0] = EV_SET;
+                        int m1 = em.node(N_MATCH);
+                        nfa.nodes[m1].pattern = first_pattern_id + 1;
+                        int c1 = em.node(N_CHAR);
+                        nfa.nodes[c1].set = nfa.add_set(pool[pool[root].kids.back()].set);
+                        nfa.nodes[c1].out = m1;
+                        parts->start[1] = c1;
+                        parts->kind[1] = EV_TEST;
+                        parts->n = 2;
+                        if (!notG.empty()) {
+                            int m2 = em.node(N_MATCH);
+                            nfa.nodes[m2].pattern = first_pattern_id + 2;
+                            int c2 = em.node(N_CHAR);
+                            nfa.nodes[c2].set = nfa.add_set(notG);
+                            nfa.nodes[c2].out = m2;
+                            parts->start[2] = c2;
+                            parts->kind[2] = EV_CLEAR;
+                            parts->n = 3;
+                        }
+                        split = true;
+                    }
+                }
+            }
+        }
+        if (!split) {
+            int m = em.node(N_MATCH);
+            nfa.nodes[m].pattern = first_pattern_id;
+            parts->start[0] = em.emit(root, m);
+            parts->kind[0] = EV_FIRE;
+            parts->n = 1;
+        }
     } catch (const ParseFail& f) {
         nfa.nodes.resize(nodes0);
         nfa.sets.resize(sets0);

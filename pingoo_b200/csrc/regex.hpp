@@ -59,6 +59,23 @@ enum RegexStatus {
     RX_TOO_BIG = 3       // exceeds the compiled-size cap -> treated like RX_INVALID (regex size_limit)
 };
 
+// What a DFA accept event does (see RegexParts).
+enum EventKind : uint8_t { EV_FIRE = 0, EV_TEST = 1, EV_CLEAR = 2, EV_SET = 3 };
+
+// A compiled pattern is one NFA pattern (EV_FIRE: the atom is true when it matches), or -- for patterns of
+// the shape  X G* S  where G is a byte class whose complement has at most 4 bytes and S is a single byte
+// class (e.g. `<script[^>]*>`) -- three cooperating patterns that avoid the 2^k state blow-up such "sticky"
+// gap loops cause in a multi-pattern DFA:
+//   part 0  X          EV_SET    latch := 1 when X has matched ending here
+//   part 1  S          EV_TEST   atom := true if latch is set when a byte of S is seen
+//   part 2  not-G      EV_CLEAR  latch := 0 when a byte outside G is seen      (absent if G is every byte)
+// Events of one position are applied in the order TEST, CLEAR, SET.
+struct RegexParts {
+    int n = 0;
+    int start[3] = {-1, -1, -1};
+    uint8_t kind[3] = {EV_FIRE, EV_FIRE, EV_FIRE};
+};
+
 struct RegexInfo {
     bool always_true = false;      // nullable without crossing an assertion: is_match is true on every haystack
     bool uses_word_boundary = false;
@@ -66,10 +83,10 @@ struct RegexInfo {
     bool uses_bol = false;
 };
 
-// Compile `pattern` into `nfa`, ending in a MATCH node carrying `pattern_id`.
-// Returns the start node index in *start.  On failure `err` holds a message.
-RegexStatus regex_compile(const std::string& pattern, int pattern_id, Nfa& nfa, int* start, RegexInfo* info,
-                          std::string& err);
+// Compile `pattern` into `nfa`; part k ends in a MATCH node carrying pattern id `first_pattern_id + k`.
+// On failure `err` holds a message.
+RegexStatus regex_compile(const std::string& pattern, int first_pattern_id, Nfa& nfa, RegexParts* parts, RegexInfo* info,
+                          std::string& err, bool allow_split = true);
 
 // Literal helpers used for ==, starts_with, ends_with, contains: build the
 // equivalent anchored/unanchored literal pattern straight into the NFA.

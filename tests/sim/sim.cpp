@@ -164,17 +164,20 @@ int pgwsim_evaluate(void* h, const pgw_batch* b, uint32_t* out) {
             const uint8_t* cls = H.arena.data() + u.cls_off;
             const uint16_t* tbl = (const uint16_t*)(H.arena.data() + u.tbl_off);
             uint32_t st = u.start_state;
+            uint32_t latch = 0;
+            auto run_events = [&](const std::vector<uint32_t>& idx, const std::vector<uint32_t>& ev, uint32_t ci) {
+                for (uint32_t k = idx[ci]; k < idx[ci + 1]; ++k) {
+                    uint32_t w = ev[k], kind = w >> kEvKindShift, lb = 1u << ((w >> kEvLatchShift) & 31u), at = w & kEvAtomMask;
+                    if (kind == 0 || (kind == 1 && (latch & lb))) row[at >> 5] |= 1u << (at & 31);
+                    else if (kind == 2) latch &= ~lb;
+                    else if (kind == 3) latch |= lb;
+                }
+            };
             for (uint32_t i = a; i < e; ++i) {
                 st = tbl[st * u.n_classes + cls[bytes[i]]];
-                if (st >= u.acc_lo) {
-                    uint32_t ci = u.acc_base + st - u.acc_lo;
-                    for (uint32_t k = H.acc_idx[ci]; k < H.acc_idx[ci + 1]; ++k) row[H.acc_atoms[k] >> 5] |= 1u << (H.acc_atoms[k] & 31);
-                }
+                if (st >= u.acc_lo) run_events(H.acc_idx, H.acc_events, u.acc_base + st - u.acc_lo);
             }
-            if (u.end_any) {
-                uint32_t ci = u.end_base + st;
-                for (uint32_t k = H.end_idx[ci]; k < H.end_idx[ci + 1]; ++k) row[H.end_atoms[k] >> 5] |= 1u << (H.end_atoms[k] & 31);
-            }
+            if (u.end_any) run_events(H.end_idx, H.end_events, u.end_base + st);
         }
         // per-request predicates
         uint32_t flags = b->flags ? b->flags[r] : 0;
