@@ -322,11 +322,12 @@ void build_smem_image(const HostProgram& H, size_t budget, std::vector<uint8_t>*
     static const double kWeight[N_FIELDS] = {13, 240, 35, 3, 95};
     std::vector<size_t> give(U, 0), order(U);
     auto row_bytes = [&](size_t u) { return (size_t)H.units[u].n_classes * 2; };
-    // every unit first gets the neighbourhood of its start state, then the rest by expected traffic
+    // every unit first gets the neighbourhood of its start state, then the rest by expected traffic;
+    // each unit also needs one extra "trap" row
     for (size_t u = 0; u < U; ++u) {
         order[u] = u;
         size_t rows = std::min<size_t>(H.units[u].n_states, 32);
-        if (rows * row_bytes(u) <= left) { give[u] = rows; left -= rows * row_bytes(u); }
+        if ((rows + 1) * row_bytes(u) <= left) { give[u] = rows; left -= (rows + 1) * row_bytes(u); }
     }
     std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return kWeight[H.units[a].field] > kWeight[H.units[b].field]; });
     for (size_t u : order) {
@@ -336,10 +337,24 @@ void build_smem_image(const HostProgram& H, size_t budget, std::vector<uint8_t>*
     }
     for (size_t u = 0; u < U; ++u) {
         while (image->size() % 16) image->push_back(0);
-        (*units)[u].hot_states = (uint32_t)give[u];
-        (*units)[u].hot_off = (uint32_t)image->size();
-        const uint8_t* src = H.arena.data() + H.units[u].tbl_off;
-        image->insert(image->end(), src, src + give[u] * row_bytes(u));
+        UnitDesc& ud = (*units)[u];
+        ud.hot_states = (uint32_t)give[u];
+        ud.hot_off = (uint32_t)image->size();
+        ud.lim = std::min(ud.hot_states, ud.acc_lo);
+        const uint16_t* src = reinterpret_cast<const uint16_t*>(H.arena.data() + H.units[u].tbl_off);
+        const uint16_t trap = (uint16_t)ud.hot_states;
+        const size_t C = ud.n_classes;
+        for (size_t s = 0; s < give[u]; ++s)
+            for (size_t c = 0; c < C; ++c) {
+                uint16_t t = src[s * C + c];
+                if (t >= ud.lim) t = trap;
+                image->push_back((uint8_t)(t & 0xFF));
+                image->push_back((uint8_t)(t >> 8));
+            }
+        for (size_t c = 0; c < C; ++c) {  // trap row: absorbing
+            image->push_back((uint8_t)(trap & 0xFF));
+            image->push_back((uint8_t)(trap >> 8));
+        }
     }
     while (image->size() % 16) image->push_back(0);
 }

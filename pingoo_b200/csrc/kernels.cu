@@ -23,6 +23,7 @@
 //   otherwise only rules that reference a changed atom are evaluated.
 #include <cuda_runtime.h>
 
+#include <cstddef>
 #include <cstdint>
 #include <cstdio>
 
@@ -263,6 +264,43 @@ __device__ __noinline__ void request_epilogue(const KParams& p, uint32_t r, uint
     p.verdict[r] = verdict;
 }
 
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint16_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+
+// Careful re-walk of one 32-bit word of a field (rare): true transitions from the full table in global memory,
+// accept events with latches.  `m4` selects which of the 4 bytes belong to the field.
+__device__ __noinline__ void slow_word(const KParams& p, const UnitDesc* ud, uint32_t clsaddr, uint32_t w, uint32_t m4, uint32_t* state,
+                                       uint32_t* last, uint32_t* latch, uint32_t* row, uint32_t stride) {
+    const uint16_t* tbl = reinterpret_cast<const uint16_t*>(p.arena + ud->tbl_off);
+    uint32_t st = *state, la = *last;
+    const uint32_t C = ud->n_classes, acclo = ud->acc_lo;
+    for (uint32_t b = 0; b < 4; ++b) {
+        if (!((m4 >> b) & 1u)) continue;
+        const uint32_t byte = (w >> (8 * b)) & 0xFFu;
+        st = __ldg(tbl + st * C + lds_u8(clsaddr + byte));
+        if (st >= acclo && st != la) {
+            const bool pure = run_events(p.acc_idx, p.acc_events, ud->acc_base + st - acclo, row, stride, latch);
+            la = pure ? st : 0xFFFFFFFFu;
+        }
+    }
+    *state = st;
+    *last = la;
+}
+
 __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const SmemLayout L = smem_layout(p.image_bytes, p.n_units, p.atom_words);
@@ -308,10 +346,15 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
         return;
     }
 
+    // 32-bit shared-window addresses (computed once: no per-access generic->shared conversion)
+    const uint32_t a_img = smem_u32(s_img);
+    const uint32_t a_units = smem_u32(s_units);
+    const uint32_t a_rows = smem_u32(my_rows);
+
     // ---- per-lane state ----
     bool c_have = false, n_have = false;
     uint32_t c_req = 0, c_unit = 0, c_rowi = 0;
-    uint32_t c_base = 0, c_start = 0, c_end = 0, c_state = 0, c_C = 0, c_acclo = 0, c_hot = 0, c_hotoff = 0, c_tbl = 0, c_cls = 0;
+    uint32_t c_base = 0, c_start = 0, c_end = 0, c_state = 0, c_C2 = 0, c_lim = 0, c_trap = 0, c_clsaddr = 0, c_hotaddr = 0;
     uint32_t c_latch = 0, c_last = 0xFFFFFFFFu;
     const uint8_t* c_col = nullptr;
     uint32_t n_req = 0, n_unit = 0, n_rowi = 0, n_start = 0, n_end = 0;
@@ -334,7 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
             c_base += kChunk;
             cur = nxt;
         } else if (n_have) {
-            const UnitDesc& ud = s_units[n_unit];
+            const uint32_t ua = a_units + n_unit * (uint32_t)sizeof(UnitDesc);
             c_req = n_req;
             c_unit = n_unit;
             c_rowi = n_rowi;
@@ -342,13 +385,12 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
             c_end = n_end;
             c_base = n_start & ~15u;
             c_col = n_col;
-            c_state = ud.start_state;
-            c_C = ud.n_classes;
-            c_acclo = ud.acc_lo;
-            c_hot = ud.hot_states;
-            c_hotoff = ud.hot_off;
-            c_tbl = ud.tbl_off;
-            c_cls = ud.cls_off;
+            c_C2 = 2u * lds_u32(ua + offsetof(UnitDesc, n_classes));
+            c_state = lds_u32(ua + offsetof(UnitDesc, start_state));
+            c_trap = lds_u32(ua + offsetof(UnitDesc, hot_states));
+            c_lim = lds_u32(ua + offsetof(UnitDesc, lim));
+            c_clsaddr = a_img + lds_u32(ua + offsetof(UnitDesc, cls_off));
+            c_hotaddr = a_img + lds_u32(ua + offsetof(UnitDesc, hot_off));
             c_latch = 0;
             c_last = 0xFFFFFFFFu;
             cur = nxt;
@@ -365,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
         const bool finishing = c_have && (c_end <= c_base + kChunk);
         const bool last_unit = c_unit + 1 >= U;
         const bool need_same = finishing && !last_unit;
-        bool need_new = (finishing && last_unit) || (!c_have && !n_have);
+        const bool need_new = (finishing && last_unit) || (!c_have && !n_have);
         // a lane about to take a third request must first get its pending one evaluated
         if (__any_sync(0xFFFFFFFFu, need_new && finishing && p_have)) flush();
         const uint32_t need_mask = __ballot_sync(0xFFFFFFFFu, need_new);
@@ -384,8 +426,8 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
                 n_unit = 0;
                 // free row: not the one still being scanned, not the pending one
                 n_rowi = finishing ? (c_rowi ^ 1u) : (p_have ? (p_rowi ^ 1u) : 0u);
-                uint32_t* row = my_rows + n_rowi * Aw * stride;
-                for (uint32_t w = 0; w < Aw; ++w) row[w * stride] = 0;
+                const uint32_t ra = a_rows + n_rowi * Aw * stride * 4u;
+                for (uint32_t w = 0; w < Aw; ++w) sts_u32(ra + w * stride * 4u, 0u);
                 got_new = true;
             }
             pool_next = min(pool_end, pool_next + (uint32_t)__popc(need_mask));
@@ -396,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
             n_rowi = c_rowi;
         }
         if (need_same || got_new) {
-            const uint32_t f = s_units[n_unit].field;
+            const uint32_t f = lds_u32(a_units + n_unit * (uint32_t)sizeof(UnitDesc) + offsetof(UnitDesc, field));
             const uint32_t* o = p.off[f] + n_req;
             n_start = o[0];
             n_end = o[1];
@@ -409,38 +451,46 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
 
         // ---- (3) process bytes [lo, hi) of the current chunk ----
         if (any_have) {
-            uint32_t lo = 0, hi = 0;
+            uint32_t m16 = 0;  // bit k set: byte k of the chunk belongs to this lane's field
             if (c_have) {
-                lo = c_start > c_base ? c_start - c_base : 0u;
-                hi = min(c_end - c_base, (uint32_t)kChunk);
+                const uint32_t lo = c_start > c_base ? c_start - c_base : 0u;
+                const uint32_t hi = min(c_end - c_base, (uint32_t)kChunk);
+                m16 = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
             }
-            uint32_t* row = my_rows + c_rowi * Aw * stride;
             const uint32_t words[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
             for (int wi = 0; wi < 4; ++wi) {
-                if (!__any_sync(0xFFFFFFFFu, lo < (uint32_t)(4 * wi + 4) && hi > (uint32_t)(4 * wi))) continue;
+                const uint32_t m4 = (m16 >> (4 * wi)) & 0xFu;
+                if (!__any_sync(0xFFFFFFFFu, m4)) continue;
                 const uint32_t w = words[wi];
+                // speculative walk on the shared-memory rows: transitions to states >= lim lead to the absorbing trap row
+                uint32_t spec = min(c_state, c_trap);
+                uint32_t mx = c_state;
 #pragma unroll
                 for (int bi = 0; bi < 4; ++bi) {
-                    const uint32_t k = 4 * wi + bi;
-                    if (k >= lo && k < hi) {
-                        const uint32_t byte = (w >> (8 * bi)) & 0xFFu;
-                        const uint32_t cls = s_img[c_cls + byte];
-                        const uint32_t idx = c_state * c_C + cls;
-                        uint32_t st;
-                        if (c_state < c_hot) st = *reinterpret_cast<const uint16_t*>(s_img + c_hotoff + 2u * idx);
-                        else st = __ldg(reinterpret_cast<const uint16_t*>(p.arena + c_tbl) + idx);
-                        c_state = st;
-                        if (st >= c_acclo && st != c_last) {
-                            const bool pure = run_events(p.acc_idx, p.acc_events, s_units[c_unit].acc_base + st - c_acclo, row, stride, &c_latch);
-                            c_last = pure ? st : 0xFFFFFFFFu;
-                        }
-                    }
+                    const uint32_t byte = __byte_perm(w, 0, 0x4440 + bi);
+                    const uint32_t cls = lds_u8(c_clsaddr + byte);
+                    const uint32_t st = lds_u16(c_hotaddr + spec * c_C2 + 2u * cls);
+                    spec = (m4 & (1u << bi)) ? st : spec;
+                    mx = max(mx, spec);
+                }
+                if (mx >= c_lim) {
+                    // copies keep c_state / c_last / c_latch in registers on the fast path
+                    uint32_t t_state = c_state, t_last = c_last, t_latch = c_latch;
+                    slow_word(p, &s_units[c_unit], c_clsaddr, w, m4, &t_state, &t_last, &t_latch, my_rows + c_rowi * Aw * stride, stride);
+                    c_state = t_state;
+                    c_last = t_last;
+                    c_latch = t_latch;
+                } else {
+                    c_state = spec;
                 }
             }
             if (finishing) {
                 const UnitDesc& ud = s_units[c_unit];
-                if (ud.end_any) run_events(p.end_idx, p.end_events, ud.end_base + c_state, row, stride, &c_latch);
+                if (ud.end_any) {
+                    uint32_t t_latch = c_latch;
+                    run_events(p.end_idx, p.end_events, ud.end_base + c_state, my_rows + c_rowi * Aw * stride, stride, &t_latch);
+                }
                 c_have = false;
                 if (last_unit) {
                     p_have = true;

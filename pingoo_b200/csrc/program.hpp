@@ -43,9 +43,11 @@ struct UnitDesc {
     uint32_t end_base;     // end_idx[end_base + s] .. [+1] -> range in end_events
     uint32_t end_any;      // 0 if no state of this DFA has end-of-input accepts (skip finalisation)
     uint32_t field_slot;   // index among the fields that are actually scanned
-    uint32_t hot_states;   // states < hot_states have their rows in the shared-memory image
+    uint32_t hot_states;   // states < hot_states have their rows in the shared-memory image; row `hot_states` is the trap row
     uint32_t hot_off;      // byte offset of those rows in the shared-memory image
-    uint32_t pad[3];
+    uint32_t lim;          // min(hot_states, acc_lo): states >= lim need the careful path (events and/or global table);
+                           // in the image every transition to a state >= lim is replaced by the trap row index
+    uint32_t pad[2];
 };
 
 // predicates evaluated once per request outside the byte scan
