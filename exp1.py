@@ -21,10 +21,6 @@ def run(rules, batch, label, steps=10):
 rules, payloads, _ = synth.make_ruleset(128)
 batch = synth.RequestStream(config_id=2, payloads=payloads).generate(0, 1_000_000)
 run(rules, batch, "128 rules")
-notag = [r for r in rules if not r.name.startswith('tag_')]
-run(notag, batch, "128-notag")
-small = [r for r in notag if not r.name.startswith(('sql_pair','func','event','sqli'))]
-run(small, batch, "128-notag-small")
 rules16, p16, _ = synth.make_ruleset(16, config_id=1)
 run(rules16, batch, "16 rules")
 one=[r for r in rules16 if r.name.startswith('sql_pair')][:1]

@@ -52,14 +52,14 @@ typedef struct pgw_rule_desc {
 } pgw_rule_desc;
 
 typedef struct pgw_options {
-    int32_t max_dfa_states;        /* per scan unit; 0 = default (4096) */
-    uint64_t max_unit_table_bytes; /* per scan unit; 0 = default (96 KiB) */
+    int32_t max_dfa_states;        /* per scan unit; 0 = default (16384) */
+    uint64_t max_unit_table_bytes; /* per scan unit; 0 = default (8 MiB) */
     int32_t eval_gates;            /* 1 (default): evaluate the user-agent and captcha-path gates of
                                       http_listener.rs:196-204 inside the engine; 0: rules only */
 } pgw_options;
 
-/* One string column: concatenated bytes + n+1 offsets.  `bytes` must be 16-byte
- * aligned and readable up to round_up(offsets[n], 16). */
+/* One string column: concatenated bytes + n+1 offsets.  `bytes` must be 32-byte
+ * aligned and readable up to round_up(offsets[n], 32) (the kernel loads whole 32-byte chunks). */
 typedef struct pgw_strcol {
     const uint8_t* bytes;
     const uint32_t* offsets;

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpingoo_waf.so")
+LIB_PATH = os.environ.get("PGW_LIB", os.path.join(_HERE, "libpingoo_waf.so"))  # PGW_LIB: tuning experiments only
 
 
 class RuleDesc(C.Structure):

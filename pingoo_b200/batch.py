@@ -17,9 +17,10 @@ FIELDS = _ffi.FIELDS
 
 
 def _pad16(a: np.ndarray) -> np.ndarray:
-    n = (len(a) + 15) // 16 * 16
+    # the kernel reads whole 32-byte chunks: keep the column readable to round_up(len, 32)
+    n = (len(a) + 31) // 32 * 32
     if n == 0:
-        n = 16
+        n = 32
     out = np.zeros(n, dtype=np.uint8)
     out[: len(a)] = a
     return out
@@ -38,7 +39,7 @@ class RequestBatch:
             assert len(o) == self.n + 1, f"{f}: need n+1 offsets"
             self.total = getattr(self, "total", {})
             self.total[f] = int(o[-1]) if len(o) else 0
-            if len(b) % 16 or len(b) < self.total[f] or len(b) == 0:
+            if len(b) % 32 or len(b) < self.total[f] or len(b) == 0:
                 b = _pad16(b[: self.total[f]])
             self.cols[f] = (b, o)
         self.ip = np.ascontiguousarray(ip, dtype=np.uint8).reshape(self.n, 16)

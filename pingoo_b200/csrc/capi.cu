@@ -239,7 +239,7 @@ static int launch_on(const pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdic
         P.off[f] = cols[f]->offsets;
         if (H.field_slot[f] >= 0 && !cols[f]->offsets) { e = std::string("batch is missing offsets for http_request.") + kFieldNames[f]; return 1; }
         if (((H.scanned_fields_mask >> f) & 1) && !cols[f]->bytes) { e = std::string("batch is missing bytes for http_request.") + kFieldNames[f]; return 1; }
-        if (((H.scanned_fields_mask >> f) & 1) && ((uintptr_t)cols[f]->bytes & 15)) { e = std::string("bytes of http_request.") + kFieldNames[f] + " are not 16-byte aligned"; return 1; }
+        if (((H.scanned_fields_mask >> f) & 1) && ((uintptr_t)cols[f]->bytes & 31)) { e = std::string("bytes of http_request.") + kFieldNames[f] + " are not 32-byte aligned"; return 1; }
     }
     P.ip = b->ip;
     P.is_v6 = b->ip_is_v6;
@@ -308,7 +308,7 @@ int pgw_evaluate_batch_host(pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdi
         if ((H.scanned_fields_mask >> f) & 1) {
             if (!hc[f]->bytes) return fail(std::string("batch is missing bytes for http_request.") + kFieldNames[f], nullptr, 0);
             size_t total = hc[f]->offsets[n];
-            dc[f]->bytes = (const uint8_t*)up(rs->stage_cols[f], hc[f]->bytes, total, 16);
+            dc[f]->bytes = (const uint8_t*)up(rs->stage_cols[f], hc[f]->bytes, total, 64);
             if (!dc[f]->bytes) return fail("CUDA: staging copy failed", nullptr, 0);
         }
     }

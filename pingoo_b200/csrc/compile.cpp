@@ -347,7 +347,7 @@ void build_smem_image(const HostProgram& H, size_t budget, std::vector<uint8_t>*
         for (size_t s = 0; s < give[u]; ++s)
             for (size_t c = 0; c < C; ++c) {
                 uint16_t t = src[s * C + c];
-                if (t >= ud.lim) t = trap;
+                if (t >= ud.hot_states) t = trap;  // only cold states trap; accepting states stay on the fast path
                 image->push_back((uint8_t)(t & 0xFF));
                 image->push_back((uint8_t)(t >> 8));
             }

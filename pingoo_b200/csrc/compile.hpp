@@ -9,8 +9,8 @@
 namespace pgw {
 
 struct CompileOptions {
-    int max_dfa_states = 4096;                 // per scan unit, after minimisation
-    size_t max_unit_table_bytes = 96u << 10;   // per scan unit transition table
+    int max_dfa_states = 16384;                // per scan unit, after minimisation
+    size_t max_unit_table_bytes = 8u << 20;    // per scan unit transition table (hot rows go to shared memory, the rest stays in L2)
     bool eval_gates = true;                    // evaluate http_listener.rs:196-204 gates inside the engine
 };
 

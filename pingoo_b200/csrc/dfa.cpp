@@ -302,7 +302,7 @@ struct Grouper {
         }
         if (latches > max_latches) return false;
         // allow the raw construction some slack over the post-minimisation cap
-        if (!build_dfa(nfa, s, max_states * 4, d)) return false;
+        if (!build_dfa(nfa, s, max_states * 3, d)) return false;
         return d->n_states <= max_states && d->table_bytes() <= max_bytes;
     }
 

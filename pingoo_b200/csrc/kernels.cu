@@ -281,6 +281,22 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     return v;
 }
 
+// Accept events of one walked word (all four states were hot, at least one is accepting): `s01`/`s23` hold the four
+// 16-bit states the speculative walk produced, `m4` the bytes that belong to the field.
+__device__ __noinline__ uint32_t events_word(const KParams& p, const UnitDesc* ud, uint32_t s01, uint32_t s23, uint32_t m4, uint32_t last,
+                                             uint32_t* latch, uint32_t* row, uint32_t stride) {
+    const uint32_t acclo = ud->acc_lo;
+    for (uint32_t b = 0; b < 4; ++b) {
+        if (!((m4 >> b) & 1u)) continue;
+        const uint32_t st = ((b < 2 ? s01 : s23) >> (16 * (b & 1))) & 0xFFFFu;
+        if (st >= acclo && st != last) {
+            const bool pure = run_events(p.acc_idx, p.acc_events, ud->acc_base + st - acclo, row, stride, latch);
+            last = pure ? st : 0xFFFFFFFFu;
+        }
+    }
+    return last;
+}
+
 // Careful re-walk of one 32-bit word of a field (rare): true transitions from the full table in global memory,
 // accept events with latches.  `m4` selects which of the 4 bytes belong to the field.
 __device__ __noinline__ void slow_word(const KParams& p, const UnitDesc* ud, uint32_t clsaddr, uint32_t w, uint32_t m4, uint32_t* state,
@@ -354,14 +370,18 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
     // ---- per-lane state ----
     bool c_have = false, n_have = false;
     uint32_t c_req = 0, c_unit = 0, c_rowi = 0;
-    uint32_t c_base = 0, c_start = 0, c_end = 0, c_state = 0, c_C2 = 0, c_lim = 0, c_trap = 0, c_clsaddr = 0, c_hotaddr = 0;
+    uint32_t c_base = 0, c_start = 0, c_end = 0, c_state = 0, c_C2 = 0, c_lim = 0, c_trap = 0, c_acclo = 0, c_clsaddr = 0, c_hotaddr = 0;
     uint32_t c_latch = 0, c_last = 0xFFFFFFFFu;
     const uint8_t* c_col = nullptr;
     uint32_t n_req = 0, n_unit = 0, n_rowi = 0, n_start = 0, n_end = 0;
     const uint8_t* n_col = nullptr;
     bool p_have = false;
     uint32_t p_req = 0, p_rowi = 0;
-    uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
+    constexpr int kVec = kChunk / 16;
+    constexpr uint32_t kAlign = ~(uint32_t)(kChunk - 1);
+    uint4 cur[kVec], nxt[kVec];
+#pragma unroll
+    for (int v = 0; v < kVec; ++v) cur[v] = nxt[v] = make_uint4(0, 0, 0, 0);
     // warp-uniform pool of claimed requests
     uint32_t pool_next = 0, pool_end = 0;
     bool pool_dry = p.n == 0;
@@ -375,7 +395,8 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
         // ---- (1) rotate: continue the current unit or adopt the prefetched one ----
         if (c_have) {
             c_base += kChunk;
-            cur = nxt;
+#pragma unroll
+            for (int v = 0; v < kVec; ++v) cur[v] = nxt[v];
         } else if (n_have) {
             const uint32_t ua = a_units + n_unit * (uint32_t)sizeof(UnitDesc);
             c_req = n_req;
@@ -383,17 +404,19 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
             c_rowi = n_rowi;
             c_start = n_start;
             c_end = n_end;
-            c_base = n_start & ~15u;
+            c_base = n_start & kAlign;
             c_col = n_col;
             c_C2 = 2u * lds_u32(ua + offsetof(UnitDesc, n_classes));
             c_state = lds_u32(ua + offsetof(UnitDesc, start_state));
             c_trap = lds_u32(ua + offsetof(UnitDesc, hot_states));
             c_lim = lds_u32(ua + offsetof(UnitDesc, lim));
+            c_acclo = lds_u32(ua + offsetof(UnitDesc, acc_lo));
             c_clsaddr = a_img + lds_u32(ua + offsetof(UnitDesc, cls_off));
             c_hotaddr = a_img + lds_u32(ua + offsetof(UnitDesc, hot_off));
             c_latch = 0;
             c_last = 0xFFFFFFFFu;
-            cur = nxt;
+#pragma unroll
+            for (int v = 0; v < kVec; ++v) cur[v] = nxt[v];
             c_have = true;
             n_have = false;
         }
@@ -443,44 +466,59 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
             n_start = o[0];
             n_end = o[1];
             n_col = p.col[f];
-            nxt = ld_nc_v4(n_col + (n_start & ~15u));
+            const uint8_t* src = n_col + (n_start & kAlign);
+#pragma unroll
+            for (int v = 0; v < kVec; ++v) nxt[v] = ld_nc_v4(src + 16 * v);
             n_have = true;
         } else if (c_have && !finishing) {
-            nxt = ld_nc_v4(c_col + c_base + kChunk);
+            const uint8_t* src = c_col + c_base + kChunk;
+#pragma unroll
+            for (int v = 0; v < kVec; ++v) nxt[v] = ld_nc_v4(src + 16 * v);
         }
 
         // ---- (3) process bytes [lo, hi) of the current chunk ----
         if (any_have) {
-            uint32_t m16 = 0;  // bit k set: byte k of the chunk belongs to this lane's field
+            uint32_t mk = 0;  // bit k set: byte k of the chunk belongs to this lane's field
             if (c_have) {
                 const uint32_t lo = c_start > c_base ? c_start - c_base : 0u;
                 const uint32_t hi = min(c_end - c_base, (uint32_t)kChunk);
-                m16 = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+                mk = (hi >= 32u ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
             }
-            const uint32_t words[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
-            for (int wi = 0; wi < 4; ++wi) {
-                const uint32_t m4 = (m16 >> (4 * wi)) & 0xFu;
+            for (int wi = 0; wi < kChunk / 4; ++wi) {
+                const uint32_t m4 = (mk >> (4 * wi)) & 0xFu;
                 if (!__any_sync(0xFFFFFFFFu, m4)) continue;
-                const uint32_t w = words[wi];
-                // speculative walk on the shared-memory rows: transitions to states >= lim lead to the absorbing trap row
+                const uint4 q = cur[wi / 4];
+                const uint32_t w = (wi % 4) == 0 ? q.x : (wi % 4) == 1 ? q.y : (wi % 4) == 2 ? q.z : q.w;
+                // speculative walk on the shared-memory rows: transitions to cold states lead to the absorbing trap row
                 uint32_t spec = min(c_state, c_trap);
-                uint32_t mx = c_state;
+                uint32_t sv[4];
 #pragma unroll
                 for (int bi = 0; bi < 4; ++bi) {
                     const uint32_t byte = __byte_perm(w, 0, 0x4440 + bi);
                     const uint32_t cls = lds_u8(c_clsaddr + byte);
                     const uint32_t st = lds_u16(c_hotaddr + spec * c_C2 + 2u * cls);
                     spec = (m4 & (1u << bi)) ? st : spec;
-                    mx = max(mx, spec);
+                    sv[bi] = spec;
                 }
-                if (mx >= c_lim) {
-                    // copies keep c_state / c_last / c_latch in registers on the fast path
-                    uint32_t t_state = c_state, t_last = c_last, t_latch = c_latch;
-                    slow_word(p, &s_units[c_unit], c_clsaddr, w, m4, &t_state, &t_last, &t_latch, my_rows + c_rowi * Aw * stride, stride);
-                    c_state = t_state;
-                    c_last = t_last;
-                    c_latch = t_latch;
+                const uint32_t mx = max(max(sv[0], sv[1]), max(sv[2], sv[3]));
+                if (max(mx, c_state) >= c_lim) {
+                    uint32_t* row = my_rows + c_rowi * Aw * stride;
+                    if (max(mx, c_state) >= c_trap) {
+                        // a cold state is involved: re-walk the word on the full table (copies keep the fast-path state in registers)
+                        uint32_t t_state = c_state, t_last = c_last, t_latch = c_latch;
+                        slow_word(p, &s_units[c_unit], c_clsaddr, w, m4, &t_state, &t_last, &t_latch, row, stride);
+                        c_state = t_state;
+                        c_last = t_last;
+                        c_latch = t_latch;
+                    } else {
+                        if (mx >= c_acclo) {
+                            uint32_t t_latch = c_latch;
+                            c_last = events_word(p, &s_units[c_unit], sv[0] | (sv[1] << 16), sv[2] | (sv[3] << 16), m4, c_last, &t_latch, row, stride);
+                            c_latch = t_latch;
+                        }
+                        c_state = spec;
+                    }
                 } else {
                     c_state = spec;
                 }

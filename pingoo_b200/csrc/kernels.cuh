@@ -6,8 +6,14 @@
 
 namespace pgw {
 
-constexpr int kThreads = 1024;      // one persistent CTA per SM, 32 warps
-constexpr int kChunk = 16;          // bytes per lane per scan iteration (one 128-bit load)
+#ifndef PGW_THREADS
+#define PGW_THREADS 768
+#endif
+constexpr int kThreads = PGW_THREADS;  // one persistent CTA per SM
+#ifndef PGW_CHUNK
+#define PGW_CHUNK 16
+#endif
+constexpr int kChunk = PGW_CHUNK;   // bytes per lane per scan iteration (PGW_CHUNK/16 128-bit loads)
 constexpr int kRowsPerLane = 2;     // atom bitmaps per lane: the request being scanned + one awaiting its epilogue
 constexpr uint32_t kClaim = 32;     // requests a warp claims from the global counter at a time
 

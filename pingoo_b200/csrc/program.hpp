@@ -45,8 +45,8 @@ struct UnitDesc {
     uint32_t field_slot;   // index among the fields that are actually scanned
     uint32_t hot_states;   // states < hot_states have their rows in the shared-memory image; row `hot_states` is the trap row
     uint32_t hot_off;      // byte offset of those rows in the shared-memory image
-    uint32_t lim;          // min(hot_states, acc_lo): states >= lim need the careful path (events and/or global table);
-                           // in the image every transition to a state >= lim is replaced by the trap row index
+    uint32_t lim;          // min(hot_states, acc_lo): a walked word whose maximum state is < lim needs no attention at all.
+                           // In the image every transition to a cold state (>= hot_states) is replaced by the trap row index.
     uint32_t pad[2];
 };
 

@@ -74,8 +74,8 @@ class RequestStream:
         cols = {}
         for i, f in enumerate(FIELDS):
             ln = self.L.synth_col_len(self.h, i)
-            padded = (ln + 15) // 16 * 16
-            by = np.ctypeslib.as_array(C.cast(self.L.synth_col_bytes(self.h, i), C.POINTER(C.c_uint8)), shape=(max(padded, 16),)).copy()
+            padded = (ln + 31) // 32 * 32
+            by = np.ctypeslib.as_array(C.cast(self.L.synth_col_bytes(self.h, i), C.POINTER(C.c_uint8)), shape=(max(padded, 32),)).copy()
             of = np.ctypeslib.as_array(C.cast(self.L.synth_col_offsets(self.h, i), C.POINTER(C.c_uint32)), shape=(n + 1,)).copy()
             cols[f] = (by, of)
         ip = np.ctypeslib.as_array(C.cast(self.L.synth_ip(self.h), C.POINTER(C.c_uint8)), shape=(n, 16)).copy()

@@ -343,8 +343,9 @@ int synth_generate(gen_t* g, uint64_t first, uint32_t n) {
     }
     for (int f = 0; f < 5; ++f) {
         g->off[f][n] = (uint32_t)g->col[f].len;
-        buf_put(&g->col[f], "\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0", 16); /* readable padding */
-        g->col[f].len -= 16;
+        static const char zeros[64] = {0};
+        buf_put(&g->col[f], zeros, 64); /* readable padding */
+        g->col[f].len -= 64;
     }
     return 0;
 }

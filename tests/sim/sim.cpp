@@ -277,6 +277,27 @@ int pgwsim_evaluate(void* h, const pgw_batch* b, uint32_t* out) {
     return 0;
 }
 
+// debug: per-state visit counts of unit `unit` over a batch (counts must hold n_states entries); returns n_states
+uint32_t pgwsim_state_histogram(void* h, const pgw_batch* b, uint32_t unit, uint64_t* counts, uint32_t* acc_lo) {
+    Sim* s = (Sim*)h;
+    const HostProgram& H = s->H;
+    if (unit >= H.units.size()) return 0;
+    const UnitDesc& u = H.units[unit];
+    const pgw_strcol* cols[5] = {&b->host, &b->url, &b->path, &b->method, &b->user_agent};
+    if (acc_lo) *acc_lo = u.acc_lo;
+    if (!counts) return u.n_states;
+    const uint8_t* cls = H.arena.data() + u.cls_off;
+    const uint16_t* tbl = (const uint16_t*)(H.arena.data() + u.tbl_off);
+    for (uint32_t r = 0; r < b->n; ++r) {
+        uint32_t st = u.start_state;
+        for (uint32_t i = cols[u.field]->offsets[r]; i < cols[u.field]->offsets[r + 1]; ++i) {
+            st = tbl[st * u.n_classes + cls[cols[u.field]->bytes[i]]];
+            counts[st]++;
+        }
+    }
+    return u.n_states;
+}
+
 void pgwsim_destroy(void* h) { delete (Sim*)h; }
 
 }  // extern "C"
