@@ -166,13 +166,19 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     bool ok = true;
     auto chk = [&](const void* p) { if (!p) ok = false; return p; };
     // shared-memory image: class maps + as many hot DFA rows as fit beside the per-lane bitmap rows
-    size_t fixed = waf_smem_fixed_bytes((uint32_t)H.units.size(), H.atom_words);
+    uint32_t n_scan_slots = 0;
+    uint32_t slot_of_field[5] = {0, 0, 0, 0, 0};
+    for (int f = 0; f < 5; ++f)
+        if ((H.scanned_fields_mask >> f) & 1) { P.slot_field[n_scan_slots] = (uint32_t)f; slot_of_field[f] = n_scan_slots++; }
+    P.n_slots = n_scan_slots;
+    size_t fixed = waf_smem_fixed_bytes((uint32_t)H.units.size(), H.atom_words, n_scan_slots);
     if (fixed + H.units.size() * 256 + 1024 > rs->max_smem)
         return fail("ruleset does not fit the shared-memory plan (too many atoms or scan units)", err, err_cap);
     std::vector<uint8_t> image;
     std::vector<UnitDesc> units;
     build_smem_image(H, rs->max_smem - fixed - 64, &image, &units);
-    rs->smem_bytes = waf_smem_bytes((uint32_t)image.size(), (uint32_t)units.size(), H.atom_words);
+    for (auto& u : units) u.field_slot = slot_of_field[u.field];  // slot among the scanned fields
+    rs->smem_bytes = waf_smem_bytes((uint32_t)image.size(), (uint32_t)units.size(), H.atom_words, n_scan_slots);
     for (auto& u : units) rs->hot_states_total += u.hot_states;
     P.units = (const UnitDesc*)chk(M.upload(units));
     P.n_units = (uint32_t)units.size();

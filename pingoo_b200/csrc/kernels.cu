@@ -69,12 +69,12 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint8_t* p) {
 }
 
 struct SmemLayout {
-    uint32_t image, units, rows, misc, total;
+    uint32_t image, units, rows, ext, misc, total;
 };
 
 __host__ __device__ inline uint32_t r16(uint32_t x) { return (x + 15u) & ~15u; }
 
-__host__ __device__ inline SmemLayout smem_layout(uint32_t image_bytes, uint32_t n_units, uint32_t atom_words) {
+__host__ __device__ inline SmemLayout smem_layout(uint32_t image_bytes, uint32_t n_units, uint32_t atom_words, uint32_t n_slots) {
     SmemLayout L;
     uint32_t o = 0;
     L.image = o;
@@ -83,6 +83,8 @@ __host__ __device__ inline SmemLayout smem_layout(uint32_t image_bytes, uint32_t
     o += r16(n_units * (uint32_t)sizeof(UnitDesc));
     L.rows = o;
     o += r16((uint32_t)kThreads * kRowsPerLane * atom_words * 4u);
+    L.ext = o;  // per lane: (start, end) offsets of every scanned field of its next request
+    o += r16((uint32_t)kThreads * 2u * n_slots * 4u);
     L.misc = o;
     o += 64;
     L.total = o;
@@ -282,16 +284,23 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
 }
 
 // Accept events of one walked word (all four states were hot, at least one is accepting): `s01`/`s23` hold the four
-// 16-bit states the speculative walk produced, `m4` the bytes that belong to the field.
-__device__ __noinline__ uint32_t events_word(const KParams& p, const UnitDesc* ud, uint32_t s01, uint32_t s23, uint32_t m4, uint32_t last,
-                                             uint32_t* latch, uint32_t* row, uint32_t stride) {
+// 16-bit states the speculative walk produced, `m4` the bytes that belong to the field.  One-atom FIRE lists are
+// resolved from the shared-memory acc1 table; anything else takes the general event list in global memory.
+__device__ __noinline__ uint32_t events_word(const KParams& p, const UnitDesc* ud, uint32_t acc1addr, uint32_t s01, uint32_t s23, uint32_t m4,
+                                             uint32_t last, uint32_t* latch, uint32_t* row, uint32_t stride) {
     const uint32_t acclo = ud->acc_lo;
     for (uint32_t b = 0; b < 4; ++b) {
         if (!((m4 >> b) & 1u)) continue;
         const uint32_t st = ((b < 2 ? s01 : s23) >> (16 * (b & 1))) & 0xFFFFu;
         if (st >= acclo && st != last) {
-            const bool pure = run_events(p.acc_idx, p.acc_events, ud->acc_base + st - acclo, row, stride, latch);
-            last = pure ? st : 0xFFFFFFFFu;
+            const uint32_t a1 = lds_u16(acc1addr + 2u * (st - acclo));
+            if (a1 != 0xFFFFu) {
+                row[(a1 >> 5) * stride] |= 1u << (a1 & 31);
+                last = st;
+            } else {
+                const bool pure = run_events(p.acc_idx, p.acc_events, ud->acc_base + st - acclo, row, stride, latch);
+                last = pure ? st : 0xFFFFFFFFu;
+            }
         }
     }
     return last;
@@ -317,9 +326,16 @@ __device__ __noinline__ void slow_word(const KParams& p, const UnitDesc* ud, uin
     *last = la;
 }
 
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const SmemLayout L = smem_layout(p.image_bytes, p.n_units, p.atom_words);
+    const SmemLayout L = smem_layout(p.image_bytes, p.n_units, p.atom_words, p.n_slots);
     uint8_t* s_img = smem + L.image;
     UnitDesc* s_units = reinterpret_cast<UnitDesc*>(smem + L.units);
     uint32_t* s_rows = reinterpret_cast<uint32_t*>(smem + L.rows);
@@ -366,16 +382,24 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
     const uint32_t a_img = smem_u32(s_img);
     const uint32_t a_units = smem_u32(s_units);
     const uint32_t a_rows = smem_u32(my_rows);
+    const uint32_t a_ext = smem_u32(smem + L.ext) + tid * 4u;  // word k of this lane: a_ext + k * kThreads * 4
+    constexpr uint32_t kExtStride = kThreads * 4u;
 
     // ---- per-lane state ----
-    bool c_have = false, n_have = false;
+    bool c_have = false;   // a unit is being scanned (its chunk for this iteration is in `cur`)
+    bool n_have = false;   // the next unit is prepared: extents known, first chunk load issued into `nxt`
+    bool n_new = false;    //   ... and it is unit 0 of the queued request
+    bool q_have = false;   // a request is queued: claimed, bitmap row cleared, field offsets landing in `ext`
+    bool q_fresh = false;  //   ... claimed in this very iteration (offsets not yet usable)
+    bool own = false;      // a request is in progress (between its first adoption and the end of its last unit)
+    bool p_have = false;   // a finished request waits for its epilogue
     uint32_t c_req = 0, c_unit = 0, c_rowi = 0;
-    uint32_t c_base = 0, c_start = 0, c_end = 0, c_state = 0, c_C2 = 0, c_lim = 0, c_trap = 0, c_acclo = 0, c_clsaddr = 0, c_hotaddr = 0;
+    uint32_t c_base = 0, c_start = 0, c_end = 0, c_state = 0, c_C2 = 0, c_lim = 0, c_trap = 0, c_acclo = 0, c_clsaddr = 0, c_hotaddr = 0, c_acc1 = 0;
     uint32_t c_latch = 0, c_last = 0xFFFFFFFFu;
     const uint8_t* c_col = nullptr;
-    uint32_t n_req = 0, n_unit = 0, n_rowi = 0, n_start = 0, n_end = 0;
+    uint32_t n_unit = 0, n_start = 0, n_end = 0;
     const uint8_t* n_col = nullptr;
-    bool p_have = false;
+    uint32_t q_req = 0, q_rowi = 0;
     uint32_t p_req = 0, p_rowi = 0;
     constexpr int kVec = kChunk / 16;
     constexpr uint32_t kAlign = ~(uint32_t)(kChunk - 1);
@@ -392,16 +416,20 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
     };
 
     for (;;) {
-        // ---- (1) rotate: continue the current unit or adopt the prefetched one ----
+        // ---- (1) rotate: continue the current unit or adopt the prepared one ----
         if (c_have) {
             c_base += kChunk;
 #pragma unroll
             for (int v = 0; v < kVec; ++v) cur[v] = nxt[v];
         } else if (n_have) {
             const uint32_t ua = a_units + n_unit * (uint32_t)sizeof(UnitDesc);
-            c_req = n_req;
+            if (n_new) {
+                c_req = q_req;
+                c_rowi = q_rowi;
+                q_have = false;
+                own = true;
+            }
             c_unit = n_unit;
-            c_rowi = n_rowi;
             c_start = n_start;
             c_end = n_end;
             c_base = n_start & kAlign;
@@ -413,6 +441,7 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
             c_acclo = lds_u32(ua + offsetof(UnitDesc, acc_lo));
             c_clsaddr = a_img + lds_u32(ua + offsetof(UnitDesc, cls_off));
             c_hotaddr = a_img + lds_u32(ua + offsetof(UnitDesc, hot_off));
+            c_acc1 = a_img + lds_u32(ua + offsetof(UnitDesc, acc1_off));
             c_latch = 0;
             c_last = 0xFFFFFFFFu;
 #pragma unroll
@@ -421,20 +450,18 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
             n_have = false;
         }
         const bool any_have = __any_sync(0xFFFFFFFFu, c_have);
-        if (!any_have && pool_dry && pool_next == pool_end) {
+        if (!any_have && pool_dry && pool_next == pool_end && !__any_sync(0xFFFFFFFFu, q_have)) {
             flush();
             break;
         }
 
-        // ---- (2) plan the chunk each lane consumes in the NEXT iteration ----
-        const bool finishing = c_have && (c_end <= c_base + kChunk);
+        // ---- (2) queue the next request early: while scanning the last unit, or when idle ----
         const bool last_unit = c_unit + 1 >= U;
-        const bool need_same = finishing && !last_unit;
-        const bool need_new = (finishing && last_unit) || (!c_have && !n_have);
-        // a lane about to take a third request must first get its pending one evaluated
-        if (__any_sync(0xFFFFFFFFu, need_new && finishing && p_have)) flush();
-        const uint32_t need_mask = __ballot_sync(0xFFFFFFFFu, need_new);
-        bool got_new = false;
+        const bool want_claim = !q_have && (own ? (c_have && last_unit) : !n_have);
+        // rows: current + pending + queued would be three; the pending one goes first
+        if (__any_sync(0xFFFFFFFFu, want_claim && own && p_have)) flush();
+        const uint32_t need_mask = __ballot_sync(0xFFFFFFFFu, want_claim);
+        q_fresh = false;
         if (need_mask) {
             if (pool_next == pool_end && !pool_dry) {
                 uint32_t base = 0;
@@ -444,28 +471,36 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
                 else { pool_next = base; pool_end = min(base + kClaim, p.n); }
             }
             const uint32_t rank = __popc(need_mask & ((1u << lane) - 1u));
-            if (need_new && pool_next + rank < pool_end) {
-                n_req = pool_next + rank;
-                n_unit = 0;
-                // free row: not the one still being scanned, not the pending one
-                n_rowi = finishing ? (c_rowi ^ 1u) : (p_have ? (p_rowi ^ 1u) : 0u);
-                const uint32_t ra = a_rows + n_rowi * Aw * stride * 4u;
+            if (want_claim && pool_next + rank < pool_end) {
+                q_req = pool_next + rank;
+                q_rowi = own ? (c_rowi ^ 1u) : (p_have ? (p_rowi ^ 1u) : 0u);
+                const uint32_t ra = a_rows + q_rowi * Aw * stride * 4u;
                 for (uint32_t w = 0; w < Aw; ++w) sts_u32(ra + w * stride * 4u, 0u);
-                got_new = true;
+                // field offsets of the queued request land in this lane's `ext` words (the current request no longer needs them)
+                for (uint32_t sl = 0; sl < p.n_slots; ++sl) {
+                    const uint32_t* o = p.off[p.slot_field[sl]] + q_req;
+                    cp_async4(a_ext + (2u * sl) * kExtStride, o);
+                    cp_async4(a_ext + (2u * sl + 1u) * kExtStride, o + 1);
+                }
+                q_have = true;
+                q_fresh = true;
             }
             pool_next = min(pool_end, pool_next + (uint32_t)__popc(need_mask));
         }
-        if (need_same) {
-            n_req = c_req;
-            n_unit = c_unit + 1;
-            n_rowi = c_rowi;
-        }
-        if (need_same || got_new) {
-            const uint32_t f = lds_u32(a_units + n_unit * (uint32_t)sizeof(UnitDesc) + offsetof(UnitDesc, field));
-            const uint32_t* o = p.off[f] + n_req;
-            n_start = o[0];
-            n_end = o[1];
-            n_col = p.col[f];
+
+        // ---- (3) issue the loads each lane consumes in the NEXT iteration ----
+        const bool finishing = c_have && (c_end <= c_base + kChunk);
+        const bool to_new = q_have && !q_fresh && !n_have && (own ? (finishing && last_unit) : true);
+        const bool to_same = finishing && !last_unit;
+        if (to_same || to_new) {
+            if (to_new) cp_async_commit_wait();
+            n_unit = to_new ? 0u : c_unit + 1u;
+            n_new = to_new;
+            const uint32_t ua = a_units + n_unit * (uint32_t)sizeof(UnitDesc);
+            const uint32_t sl = lds_u32(ua + offsetof(UnitDesc, field_slot));
+            n_start = lds_u32(a_ext + (2u * sl) * kExtStride);
+            n_end = lds_u32(a_ext + (2u * sl + 1u) * kExtStride);
+            n_col = p.col[lds_u32(ua + offsetof(UnitDesc, field))];
             const uint8_t* src = n_col + (n_start & kAlign);
 #pragma unroll
             for (int v = 0; v < kVec; ++v) nxt[v] = ld_nc_v4(src + 16 * v);
@@ -476,7 +511,7 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
             for (int v = 0; v < kVec; ++v) nxt[v] = ld_nc_v4(src + 16 * v);
         }
 
-        // ---- (3) process bytes [lo, hi) of the current chunk ----
+        // ---- (4) walk the bytes of the current chunk that belong to the field ----
         if (any_have) {
             uint32_t mk = 0;  // bit k set: byte k of the chunk belongs to this lane's field
             if (c_have) {
@@ -501,10 +536,10 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
                     spec = (m4 & (1u << bi)) ? st : spec;
                     sv[bi] = spec;
                 }
-                const uint32_t mx = max(max(sv[0], sv[1]), max(sv[2], sv[3]));
-                if (max(mx, c_state) >= c_lim) {
+                const uint32_t mx = max(max(max(sv[0], sv[1]), max(sv[2], sv[3])), c_state);
+                if (mx >= c_lim) {
                     uint32_t* row = my_rows + c_rowi * Aw * stride;
-                    if (max(mx, c_state) >= c_trap) {
+                    if (mx >= c_trap) {
                         // a cold state is involved: re-walk the word on the full table (copies keep the fast-path state in registers)
                         uint32_t t_state = c_state, t_last = c_last, t_latch = c_latch;
                         slow_word(p, &s_units[c_unit], c_clsaddr, w, m4, &t_state, &t_last, &t_latch, row, stride);
@@ -512,9 +547,9 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
                         c_last = t_last;
                         c_latch = t_latch;
                     } else {
-                        if (mx >= c_acclo) {
+                        if (max(max(sv[0], sv[1]), max(sv[2], sv[3])) >= c_acclo) {
                             uint32_t t_latch = c_latch;
-                            c_last = events_word(p, &s_units[c_unit], sv[0] | (sv[1] << 16), sv[2] | (sv[3] << 16), m4, c_last, &t_latch, row, stride);
+                            c_last = events_word(p, &s_units[c_unit], c_acc1, sv[0] | (sv[1] << 16), sv[2] | (sv[3] << 16), m4, c_last, &t_latch, row, stride);
                             c_latch = t_latch;
                         }
                         c_state = spec;
@@ -534,6 +569,7 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
                     p_have = true;
                     p_req = c_req;
                     p_rowi = c_rowi;
+                    own = false;
                 }
             }
         }
@@ -576,8 +612,8 @@ const char* geoip_launch(const KParams& p, const uint8_t* ip, const uint8_t* is_
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
-size_t waf_smem_bytes(uint32_t image_bytes, uint32_t n_units, uint32_t atom_words) { return smem_layout(image_bytes, n_units, atom_words).total; }
-size_t waf_smem_fixed_bytes(uint32_t n_units, uint32_t atom_words) { return smem_layout(0, n_units, atom_words).total; }
+size_t waf_smem_bytes(uint32_t image_bytes, uint32_t n_units, uint32_t atom_words, uint32_t n_slots) { return smem_layout(image_bytes, n_units, atom_words, n_slots).total; }
+size_t waf_smem_fixed_bytes(uint32_t n_units, uint32_t atom_words, uint32_t n_slots) { return smem_layout(0, n_units, atom_words, n_slots).total; }
 
 const char* waf_configure(int device, size_t* max_smem_optin, int* sm_count) {
     cudaError_t e = cudaSetDevice(device);

@@ -59,6 +59,8 @@ struct KParams {
     const uint32_t* cset;
     int32_t gate_atom;
     uint32_t eval_gates;
+    uint32_t n_slots;           // scanned fields
+    uint32_t slot_field[5];     // slot -> Field
     // ---- longest-prefix tables ----
     const uint32_t* dir24;
     const uint32_t* tbl8;
@@ -78,8 +80,8 @@ struct LaunchPlan {
 };
 
 // host-callable wrappers (kernels.cu)
-size_t waf_smem_bytes(uint32_t image_bytes, uint32_t n_units, uint32_t atom_words);
-size_t waf_smem_fixed_bytes(uint32_t n_units, uint32_t atom_words);  // everything except the image
+size_t waf_smem_bytes(uint32_t image_bytes, uint32_t n_units, uint32_t atom_words, uint32_t n_slots);
+size_t waf_smem_fixed_bytes(uint32_t n_units, uint32_t atom_words, uint32_t n_slots);  // everything except the image
 const char* waf_launch(const KParams& p, const LaunchPlan& plan, void* stream);
 const char* geoip_launch(const KParams& p, const uint8_t* ip, const uint8_t* is_v6, uint32_t n, uint32_t* asn_out,
                          uint16_t* country_out, void* stream);

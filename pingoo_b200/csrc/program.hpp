@@ -47,7 +47,9 @@ struct UnitDesc {
     uint32_t hot_off;      // byte offset of those rows in the shared-memory image
     uint32_t lim;          // min(hot_states, acc_lo): a walked word whose maximum state is < lim needs no attention at all.
                            // In the image every transition to a cold state (>= hot_states) is replaced by the trap row index.
-    uint32_t pad[2];
+    uint32_t acc1_off;     // image offset of uint16 acc1[s - acc_lo] for acc_lo <= s < hot_states: the atom of a single-FIRE
+                           // event list, or 0xFFFF when the list needs the general path
+    uint32_t pad;
 };
 
 // predicates evaluated once per request outside the byte scan
