@@ -720,7 +720,16 @@ static int addthread(const rx_prog* p, sset* list, int* stack, int pc0, const ui
 
 int rx_is_match(const rx_prog* p, const uint8_t* s, size_t n) {
     int N = p->n;
-    int* mem = (int*)malloc(((size_t)N * 7 + 8) * sizeof(int));
+    /* per-thread scratch: the baseline should time matching, not malloc */
+    static __thread int* scratch = NULL;
+    static __thread size_t scratch_cap = 0;
+    size_t need = (size_t)N * 7 + 8;
+    if (need > scratch_cap) {
+        free(scratch);
+        scratch = (int*)malloc(need * sizeof(int));
+        scratch_cap = need;
+    }
+    int* mem = scratch;
     sset a = {mem, mem + N, 0}, b = {mem + 2 * N, mem + 3 * N, 0};
     int* stack = mem + 4 * N; /* every visited pc pushes at most two successors: 2N+1 entries suffice */
     sset *cur = &a, *nxt = &b;
@@ -740,6 +749,5 @@ int rx_is_match(const rx_prog* p, const uint8_t* s, size_t n) {
         if (found) break;
         sset* t = cur; cur = nxt; nxt = t;
     }
-    free(mem);
     return found;
 }

@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -176,7 +177,14 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
         return fail("ruleset does not fit the shared-memory plan (too many atoms or scan units)", err, err_cap);
     std::vector<uint8_t> image;
     std::vector<UnitDesc> units;
-    build_smem_image(H, rs->max_smem - fixed - 64, &image, &units);
+    // Only a few hundred shallow states are ever visited by real traffic: cap the image so most of the 228 KB stays L1
+    // (request bytes, offsets, spills).  PGW_SMEM_IMAGE_KB overrides the cap for tuning.
+    size_t image_cap = 96u << 10;
+    if (const char* ev = getenv("PGW_SMEM_IMAGE_KB")) image_cap = (size_t)atoi(ev) << 10;
+    size_t image_budget = rs->max_smem - fixed - 64;
+    if (image_budget > image_cap) image_budget = image_cap;
+    if (image_budget < H.units.size() * 256 + 4096) image_budget = H.units.size() * 256 + 4096;
+    build_smem_image(H, image_budget, &image, &units);
     for (auto& u : units) u.field_slot = slot_of_field[u.field];  // slot among the scanned fields
     rs->smem_bytes = waf_smem_bytes((uint32_t)image.size(), (uint32_t)units.size(), H.atom_words, n_scan_slots);
     for (auto& u : units) rs->hot_states_total += u.hot_states;

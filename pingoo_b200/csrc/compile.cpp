@@ -319,7 +319,7 @@ void build_smem_image(const HostProgram& H, size_t budget, std::vector<uint8_t>*
     size_t left = budget - image->size();
     left = left > 16 * U ? left - 16 * U : 0;  // padding slack
     for (size_t u = 0; u < U; ++u) {  // acc1 tables (upper bound: every accepting state hot)
-        size_t a1 = 2 * (size_t)(H.units[u].n_states - H.units[u].acc_lo) + 4;
+        size_t a1 = 2 * (size_t)(H.units[u].n_states - H.units[u].acc_lo) + 2 * (size_t)H.units[u].n_states + 8;
         left = left > a1 ? left - a1 : 0;
     }
     // expected bytes per request of each field decide who gets shared memory first
@@ -372,6 +372,18 @@ void build_smem_image(const HostProgram& H, size_t budget, std::vector<uint8_t>*
             uint32_t a = H.acc_idx[ci], b = H.acc_idx[ci + 1];
             uint16_t v = 0xFFFF;
             if (b - a == 1 && (H.acc_events[a] >> kEvKindShift) == 0) v = (uint16_t)(H.acc_events[a] & kEvAtomMask);
+            image->push_back((uint8_t)(v & 0xFF));
+            image->push_back((uint8_t)(v >> 8));
+        }
+        // end1: end-of-field events of hot states
+        while (image->size() % 4) image->push_back(0);
+        ud.end1_off = (uint32_t)image->size();
+        for (uint32_t st = 0; st < ud.hot_states; ++st) {
+            uint32_t ci = ud.end_base + st;
+            uint32_t a = H.end_idx[ci], b = H.end_idx[ci + 1];
+            uint16_t v = 0xFFFF;
+            if (a == b) v = 0xFFFE;
+            else if (b - a == 1 && (H.end_events[a] >> kEvKindShift) == 0) v = (uint16_t)(H.end_events[a] & kEvAtomMask);
             image->push_back((uint8_t)(v & 0xFF));
             image->push_back((uint8_t)(v >> 8));
         }

@@ -29,6 +29,10 @@
 
 #include "kernels.cuh"
 
+#ifndef PGW_L2_PREFETCH
+#define PGW_L2_PREFETCH 0
+#endif
+
 namespace pgw {
 
 namespace {
@@ -276,6 +280,11 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u32_v(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     uint16_t v;
@@ -394,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
     bool own = false;      // a request is in progress (between its first adoption and the end of its last unit)
     bool p_have = false;   // a finished request waits for its epilogue
     uint32_t c_req = 0, c_unit = 0, c_rowi = 0;
-    uint32_t c_base = 0, c_start = 0, c_end = 0, c_state = 0, c_C2 = 0, c_lim = 0, c_trap = 0, c_acclo = 0, c_clsaddr = 0, c_hotaddr = 0, c_acc1 = 0;
+    uint32_t c_base = 0, c_start = 0, c_end = 0, c_state = 0, c_C2 = 0, c_lim = 0, c_trap = 0, c_acclo = 0, c_clsaddr = 0, c_hotaddr = 0, c_acc1 = 0, c_end1 = 0;
     uint32_t c_latch = 0, c_last = 0xFFFFFFFFu;
     const uint8_t* c_col = nullptr;
     uint32_t n_unit = 0, n_start = 0, n_end = 0;
@@ -442,6 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
             c_clsaddr = a_img + lds_u32(ua + offsetof(UnitDesc, cls_off));
             c_hotaddr = a_img + lds_u32(ua + offsetof(UnitDesc, hot_off));
             c_acc1 = a_img + lds_u32(ua + offsetof(UnitDesc, acc1_off));
+            c_end1 = a_img + lds_u32(ua + offsetof(UnitDesc, end1_off));
             c_latch = 0;
             c_last = 0xFFFFFFFFu;
 #pragma unroll
@@ -509,6 +519,10 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
             const uint8_t* src = c_col + c_base + kChunk;
 #pragma unroll
             for (int v = 0; v < kVec; ++v) nxt[v] = ld_nc_v4(src + 16 * v);
+#if PGW_L2_PREFETCH
+            // pull the line a few chunks ahead into L2 so the next loads see L2 rather than HBM latency
+            if (c_end > c_base + PGW_L2_PREFETCH) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + PGW_L2_PREFETCH));
+#endif
         }
 
         // ---- (4) walk the bytes of the current chunk that belong to the field ----
@@ -559,10 +573,18 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
                 }
             }
             if (finishing) {
-                const UnitDesc& ud = s_units[c_unit];
-                if (ud.end_any) {
-                    uint32_t t_latch = c_latch;
-                    run_events(p.end_idx, p.end_events, ud.end_base + c_state, my_rows + c_rowi * Aw * stride, stride, &t_latch);
+                // end-of-field events of the final state: resolved from the shared-memory end1 table when the state is hot
+                uint32_t e1 = 0xFFFFu;
+                if (c_state < c_trap) e1 = lds_u16(c_end1 + 2u * c_state);
+                if (e1 != 0xFFFEu) {
+                    if (e1 != 0xFFFFu) {
+                        const uint32_t wa = a_rows + (c_rowi * Aw + (e1 >> 5)) * stride * 4u;
+                        sts_u32(wa, lds_u32_v(wa) | (1u << (e1 & 31)));
+                    } else {
+                        const UnitDesc& ud = s_units[c_unit];
+                        uint32_t t_latch = c_latch;
+                        if (ud.end_any) run_events(p.end_idx, p.end_events, ud.end_base + c_state, my_rows + c_rowi * Aw * stride, stride, &t_latch);
+                    }
                 }
                 c_have = false;
                 if (last_unit) {

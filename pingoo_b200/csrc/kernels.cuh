@@ -7,7 +7,7 @@
 namespace pgw {
 
 #ifndef PGW_THREADS
-#define PGW_THREADS 768
+#define PGW_THREADS 640
 #endif
 constexpr int kThreads = PGW_THREADS;  // one persistent CTA per SM
 #ifndef PGW_CHUNK

@@ -49,7 +49,8 @@ struct UnitDesc {
                            // In the image every transition to a cold state (>= hot_states) is replaced by the trap row index.
     uint32_t acc1_off;     // image offset of uint16 acc1[s - acc_lo] for acc_lo <= s < hot_states: the atom of a single-FIRE
                            // event list, or 0xFFFF when the list needs the general path
-    uint32_t pad;
+    uint32_t end1_off;     // image offset of uint16 end1[s] for s < hot_states: end-of-field events of state s:
+                           // 0xFFFE none, an atom id for a single FIRE, 0xFFFF general list
 };
 
 // predicates evaluated once per request outside the byte scan
@@ -60,7 +61,8 @@ struct NsAtom {
     uint32_t op;       // CmpOp
     int64_t cval;
     uint32_t set_id;   // int set / ip set bit / country set
-    uint32_t pad;
+    uint32_t end1_off;     // image offset of uint16 end1[s] for s < hot_states: end-of-field events of state s:
+                           // 0xFFFE none, an atom id for a single FIRE, 0xFFFF general list
 };
 
 struct LpmLeaf {

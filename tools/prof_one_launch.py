@@ -1,5 +1,5 @@
 import sys, os
-sys.path.insert(0,'.'); sys.path.insert(0,'tests')
+import os; R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0,R); sys.path.insert(0,os.path.join(R,'tests'))
 import numpy as np, torch
 import synth
 from pingoo_b200 import WafEngine
