@@ -29,6 +29,9 @@
 
 #include "kernels.cuh"
 
+#ifndef PGW_LD_MODE
+#define PGW_LD_MODE 0
+#endif
 #ifndef PGW_L2_PREFETCH
 #define PGW_L2_PREFETCH 0
 #endif
@@ -68,7 +71,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 __device__ __forceinline__ uint4 ld_nc_v4(const uint8_t* p) {
     uint4 r;
+#if PGW_LD_MODE == 1
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+#elif PGW_LD_MODE == 2
+    asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+#endif
     return r;
 }
 

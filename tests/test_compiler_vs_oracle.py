@@ -56,3 +56,38 @@ def test_geoip_tables_vs_oracle_walk():
     for i in range(len(v6_np)):
         a, c = orc.geoip_lookup(bytes(ip_np[i]), int(v6_np[i]))
         assert (int(asn[i]), bytes([cc[i] & 0xFF, cc[i] >> 8]).decode()) == (a, c), f"address {i}: {bytes(ip_np[i]).hex()}"
+
+
+def test_gap_split_patterns_and_latches():
+    """Patterns of the shape X G* S are compiled into SET/TEST/CLEAR latch events instead of sticky DFA loops;
+    the verdicts must stay those of the plain regex semantics (oracle = Pike VM on the unsplit pattern)."""
+    import random
+
+    from pingoo_b200 import Action, Rule
+
+    rng = random.Random(99)
+    tags = ["script", "iframe", "svg", "img", "a", "ab"]
+    rules = []
+    for i, t in enumerate(tags):
+        rules.append(Rule(f"tag{i}", 'http_request.url.matches("(?i)<%s[^>]*>")' % t, [Action.BLOCK]))
+    rules += [
+        Rule("quote", 'http_request.url.matches("x=\\"[^\\"]*\\"")', [Action.BLOCK]),
+        Rule("dotstar", 'http_request.url.matches("select.*;")', [Action.CAPTCHA]),
+        Rule("plus", 'http_request.url.matches("a[^b]+b")', [Action.BLOCK]),
+        Rule("two", 'http_request.url.matches("k[^/]{2,}/")', [Action.BLOCK]),
+        Rule("dots", 'http_request.url.matches("(?s)q.*z")', [Action.BLOCK]),
+        Rule("anch", 'http_request.url.matches("^/p[^?]*\\\\?")', [Action.CAPTCHA, Action.BLOCK]),
+        Rule("ua", 'http_request.user_agent.matches("\\\\([^)]*\\\\)")', [Action.CAPTCHA]),
+    ]
+    alphabet = ['<', '>', 'script', 'SVG', 'img', 'a', 'b', 'ab', ' ', '/', 'x=', '"', 'select', ';', '\n', 'k', 'q', 'z', '?', '/p', 'iframe', '<a', '<ab>', 'aab']
+    reqs = []
+    for i in range(6000):
+        url = "".join(rng.choice(alphabet) for _ in range(rng.randint(0, 14)))
+        ua = "Mozilla/5.0 " + "".join(rng.choice(["(", ")", "x", " "]) for _ in range(rng.randint(0, 6)))
+        reqs.append(dict(host="h", url=url, path="/p", method="GET", user_agent=ua, ip="1.2.3.4", remote_port=1, flags=i % 2))
+    batch = pack_requests(reqs)
+    want = _check(rules, batch)
+    assert len(set(want.tolist())) > 8
+    # the split really happened: one URL automaton despite six sticky gap patterns
+    desc = Sim(rules).describe()
+    assert desc.count("[url:") == 1, desc
