@@ -164,7 +164,7 @@ def cpu_baseline_run(rules, lists, mmdb, batch, sample, threads, repeats=1):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
@@ -289,6 +289,13 @@ def main():
     hist = np.bincount(gpu_out & 3, minlength=4).tolist()
 
     peak, peak_src = peaks()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "latest_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get("workload") == f"config {args.config}":
+            traffic = tj["dram_bytes_per_launch"]
     kernel_ms = ms / (args.steps * len(batches))
     achieved = (alg_total / len(batches)) / (kernel_ms / 1e3) / 1e9
     out = {
@@ -299,7 +306,7 @@ def main():
                    "avg_algorithmic_bytes_per_request": round(alg_per_req, 1), "l2": "inputs larger than L2 (no flush needed)",
                    "tables_in_smem": bool(info.tables_in_smem), "scan_units": info.n_scan_units, "dfa_states": info.total_dfa_states,
                    "verdict_hist_allow_block_captcha_bypass": hist, "verdict_mismatches_vs_oracle": mismatches, "parallelism": f"dp{world}"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "kernel": "waf_verdict_kernel", "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_launch": alg_total / len(batches)},
         "cpu_baseline": {"value": cpu_v / 1e6, "unit": unit, "cores": ncores, "kind": "port",
