@@ -99,6 +99,87 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
         } else H.gate_bypass_atom = it->second;
     }
 
+    // ---- complement events for atoms that are expected to be true -------------------------------------------
+    // `!ua.starts_with("Mozilla/")` (docs/configuration.md:67-70) makes the atom true for most requests, which would
+    // fire one accept event per request.  For literals anchored at the start the complement language is regular and
+    // cheap ("some byte of the prefix differs, or the field ends early"): scan for THAT, and negate in the formula,
+    // so the common case fires nothing.
+    {
+        std::vector<int> pos(M.atoms.size(), 0), neg(M.atoms.size(), 0);
+        for (auto& r : M.rules) {
+            std::vector<std::pair<int, bool>> refs;
+            collect_atoms(M.pool, r.formula, false, refs);
+            for (auto& pr : refs) (pr.second ? neg : pos)[pr.first]++;
+        }
+        std::vector<int> repl(M.atoms.size(), -1);
+        const size_t n0 = M.atoms.size();
+        for (size_t a = 0; a < n0; ++a) {
+            if (M.atoms[a].kind != AtomDesc::STR_PATTERN || M.atoms[a].lit_kind == 0 || neg[a] <= pos[a]) continue;
+            if ((int)a == H.gate_bypass_atom) continue;
+            const int f = M.atoms[a].field;
+            const std::string lit = M.atoms[a].lit;
+            AtomDesc c;
+            c.kind = AtomDesc::STR_PATTERN;
+            c.field = f;
+            c.key = "S|" + std::to_string(f) + "|not" + (M.atoms[a].lit_kind == 2 ? "eq" : "sw") + "|" + lit;
+            c.event_base = (int)M.events.size();
+            const int id = (int)M.atoms.size();
+            Nfa& nfa = M.nfa[f];
+            auto add = [&](NfaKind k) { NfaNode n; n.kind = k; nfa.nodes.push_back(n); return (int)nfa.nodes.size() - 1; };
+            int m = add(N_MATCH);
+            nfa.nodes[m].pattern = c.event_base;
+            int next = -1;  // continuation after the whole literal matched: dead for starts_with, "any further byte" for ==
+            if (M.atoms[a].lit_kind == 2) {
+                ByteSet any;
+                any.negate();
+                next = add(N_CHAR);
+                nfa.nodes[next].set = nfa.add_set(any);
+                nfa.nodes[next].out = m;
+            }
+            for (size_t k = lit.size(); k-- > 0;) {
+                ByteSet is, isnot;
+                is.set((unsigned char)lit[k]);
+                isnot = is;
+                isnot.negate();
+                int diff = add(N_CHAR);  // a different byte here
+                nfa.nodes[diff].set = nfa.add_set(isnot);
+                nfa.nodes[diff].out = m;
+                int eol = add(N_ASSERT);  // or the field ends here
+                nfa.nodes[eol].assert_kind = A_EOL_TEXT;
+                nfa.nodes[eol].out = m;
+                int alt = add(N_SPLIT);
+                nfa.nodes[alt].out = diff;
+                nfa.nodes[alt].out1 = eol;
+                int node = alt;
+                if (next >= 0) {
+                    int same = add(N_CHAR);
+                    nfa.nodes[same].set = nfa.add_set(is);
+                    nfa.nodes[same].out = next;
+                    int sp = add(N_SPLIT);
+                    nfa.nodes[sp].out = alt;
+                    nfa.nodes[sp].out1 = same;
+                    node = sp;
+                }
+                next = node;
+            }
+            if (next < 0) continue;  // empty starts_with literal cannot get here
+            int bol = add(N_ASSERT);
+            nfa.nodes[bol].assert_kind = A_BOL_TEXT;
+            nfa.nodes[bol].out = next;
+            c.nfa_starts.push_back(bol);
+            M.events.push_back(PatternEvent{EV_FIRE, id});
+            M.atom_index[c.key] = id;
+            M.atoms.push_back(c);
+            repl[a] = M.pool.mk_not(M.pool.atom(id));
+        }
+        bool any = false;
+        for (int r : repl) any |= r >= 0;
+        if (any) {
+            repl.resize(M.atoms.size(), -1);
+            for (auto& r : M.rules) r.formula = M.pool.substitute(r.formula, repl);
+        }
+    }
+
     if (M.atoms.size() > 0x3FFF) {
         err = "too many distinct predicates (" + std::to_string(M.atoms.size()) + " > 16383)";
         return false;
@@ -171,6 +252,8 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
         std::vector<uint32_t> bundle_atom;
         for (uint32_t a = 0; a < H.n_atoms; ++a)
             if (M.atoms[a].kind == AtomDesc::STR_PATTERN && M.atoms[a].field == f) {
+                // atoms no rule refers to any more (replaced by their complement) are not scanned
+                if (M.atoms[a].pos_refs + M.atoms[a].neg_refs == 0 && (int)a != H.gate_bypass_atom) continue;
                 PatternBundle b;
                 b.starts = M.atoms[a].nfa_starts;
                 b.has_latch = M.atoms[a].has_latch;

@@ -571,9 +571,28 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
                         c_latch = t_latch;
                     } else {
                         if (max(max(sv[0], sv[1]), max(sv[2], sv[3])) >= c_acclo) {
-                            uint32_t t_latch = c_latch;
-                            c_last = events_word(p, &s_units[c_unit], c_acc1, sv[0] | (sv[1] << 16), sv[2] | (sv[3] << 16), m4, c_last, &t_latch, row, stride);
-                            c_latch = t_latch;
+                            // accept events straight from the four states in registers; one-atom FIRE lists are resolved from the
+                            // shared-memory acc1 table inline, anything else (latches, multi-atom lists) goes out of line
+                            bool general = false;
+#pragma unroll
+                            for (int bi = 0; bi < 4; ++bi) {
+                                const uint32_t st = sv[bi];
+                                if ((m4 & (1u << bi)) && st >= c_acclo && st != c_last) {
+                                    const uint32_t a1 = lds_u16(c_acc1 + 2u * (st - c_acclo));
+                                    if (a1 != 0xFFFFu) {
+                                        const uint32_t wa = a_rows + (c_rowi * Aw + (a1 >> 5)) * stride * 4u;
+                                        sts_u32(wa, lds_u32_v(wa) | (1u << (a1 & 31)));
+                                        c_last = st;
+                                    } else {
+                                        general = true;
+                                    }
+                                }
+                            }
+                            if (general) {
+                                uint32_t t_latch = c_latch;
+                                c_last = events_word(p, &s_units[c_unit], c_acc1, sv[0] | (sv[1] << 16), sv[2] | (sv[3] << 16), m4, 0xFFFFFFFFu, &t_latch, row, stride);
+                                c_latch = t_latch;
+                            }
                         }
                         c_state = spec;
                     }

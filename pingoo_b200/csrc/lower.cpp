@@ -57,6 +57,17 @@ int BoolPool::mk_or(int x, int y) {
     if (x > y) std::swap(x, y);
     return intern(BoolNode::OR, x, y);
 }
+int BoolPool::substitute(int root, const std::vector<int>& repl) {
+    const BoolNode n = nodes_[root];
+    switch (n.kind) {
+        case BoolNode::CONST: return root;
+        case BoolNode::ATOM: return (n.a < (int)repl.size() && repl[n.a] >= 0) ? repl[n.a] : root;
+        case BoolNode::NOT: return mk_not(substitute(n.a, repl));
+        case BoolNode::AND: return mk_and(substitute(n.a, repl), substitute(n.b, repl));
+        case BoolNode::OR: return mk_or(substitute(n.a, repl), substitute(n.b, repl));
+    }
+    return root;
+}
 bool BoolPool::eval(int root, const std::vector<uint8_t>& av) const {
     const BoolNode& n = nodes_[root];
     switch (n.kind) {
@@ -179,6 +190,7 @@ struct Lowerer {
         a.event_base = (int)M.events.size();
         a.nfa_starts.push_back(nfa_literal(M.nfa[field], lit, a_start, a_end, a.event_base));
         M.events.push_back(PatternEvent{EV_FIRE, id});
+        if (a_start) { a.lit_kind = a_end ? 2 : 1; a.lit = lit; }
         return boolean(P.atom(add_atom(std::move(a))));
     }
 

