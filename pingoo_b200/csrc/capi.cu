@@ -84,6 +84,8 @@ struct pgw_ruleset {
     size_t smem_bytes = 0;
     uint32_t hot_states_total = 0;
     uint32_t* counters = nullptr;  // ring of work counters: one per in-flight launch
+    bool stream_kernel = false;    // kernel path: stream scan (v5) instead of lane-owned requests (v3)
+    size_t stream_smem = 0;
     std::atomic<uint64_t> launches{0};
     // host-pointer path
     Staging stage_cols[5], stage_offs[5], stage_ip, stage_v6, stage_port, stage_asn, stage_country, stage_flags, stage_verdict;
@@ -232,6 +234,11 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     }
     std::vector<uint32_t> zeros(64, 0);
     rs->counters = (uint32_t*)chk(M.upload(zeros));
+    rs->stream_smem = waf_stream_smem_bytes((uint32_t)image.size(), (uint32_t)units.size());
+    {
+        const char* km = getenv("PGW_KERNEL");
+        rs->stream_kernel = km ? (strcmp(km, "stream") == 0) : false;
+    }
     if (!ok) {
         M.release();
         return fail(std::string("CUDA: device allocation/upload failed: ") + cudaGetErrorString(cudaGetLastError()), err, err_cap);
@@ -271,6 +278,17 @@ static int launch_on(const pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdic
     // each in-flight launch gets its own work counter (ring of 64), so concurrent callers do not interfere
     uint64_t seq = const_cast<pgw_ruleset*>(rs)->launches.fetch_add(1, std::memory_order_relaxed);
     P.work_counter = rs->counters + (seq & 63);
+    if (rs->stream_kernel) {
+        // scratch (atom bitmaps + task counter) comes from the stream-ordered allocator: no state shared between callers
+        const size_t row_words = (size_t)b->n * P.atom_words;
+        uint32_t* scratch = nullptr;
+        if (cudaMallocAsync((void**)&scratch, (row_words + 64) * 4, (cudaStream_t)stream) != cudaSuccess) { e = "CUDA: scratch allocation failed"; return 1; }
+        const char* m = waf_stream_launch(P, scratch, scratch + row_words + 16, rs->sm_count, rs->stream_smem, stream);
+        cudaFreeAsync(scratch, (cudaStream_t)stream);
+        if (m) { e = std::string("CUDA launch failed: ") + m; return 1; }
+        const_cast<pgw_ruleset*>(rs)->launches.fetch_add(1, std::memory_order_relaxed);  // two kernels per batch on this path
+        return 0;
+    }
     LaunchPlan plan;
     plan.smem_bytes = rs->smem_bytes;
     uint32_t want = (b->n + kThreads - 1) / kThreads;

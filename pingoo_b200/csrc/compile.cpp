@@ -332,6 +332,24 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
         H.end_idx.push_back((uint32_t)H.end_events.size());
         ud.hot_states = ud.n_states;
         ud.hot_off = ud.tbl_off;
+        // idle state: the mode of the state distribution on pseudo-random printable text (speculation hint only)
+        {
+            std::vector<uint32_t> hist(d.n_states, 0);
+            uint32_t st = (uint32_t)d.start;
+            uint64_t x = 0x9E3779B97F4A7C15ull;
+            static const char kText[] = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789/=&?-_.%+ ";
+            for (int i = 0; i < 20000; ++i) {
+                x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+                unsigned char c = (unsigned char)kText[x % (sizeof(kText) - 1)];
+                st = d.trans[(size_t)st * d.n_classes + d.classmap[c]];
+                hist[st]++;
+            }
+            ud.idle_state = (uint32_t)(std::max_element(hist.begin(), hist.end()) - hist.begin());
+        }
+        ud.has_latch = 0;
+        for (int lv : pend[u].latch_of_event) if (lv) ud.has_latch = 1;
+        for (size_t a = 0; a < M.atoms.size(); ++a)
+            if (M.atoms[a].kind == AtomDesc::STR_PATTERN && M.atoms[a].has_latch && M.atoms[a].field == pend[u].field) ud.has_latch = 1;
         H.units.push_back(ud);
     }
     pad16(H.arena);

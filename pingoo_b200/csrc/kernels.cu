@@ -626,6 +626,350 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
     }
 }
 
+// =====================================================================================================================
+// Stream scan (kernel path "v5"): each scan unit's field column is one contiguous byte stream.  A warp owns a block of
+// kStreamNB consecutive requests of one unit and walks the block's bytes in windows of 512 B: lane j takes the 16 bytes
+// [W+16j, W+16j+16) with one coalesced 128-bit load.  Lane 0 starts from the exact carried state; the other lanes start
+// from a speculated state (the unit's idle state warmed up on the 4 preceding bytes, or the DFA start state if their
+// segment begins a request).  Validation: lane j's assumed start must equal lane j-1's end state (shuffle + vote);
+// mismatching lanes re-walk from the correct state until the chain is consistent, which makes every state exact by
+// induction.  Request boundaries inside a segment reset the DFA to its start state.  Side effects (accept events,
+// end-of-field events) are applied after validation, to atom bitmaps in global memory (atomicOr, rare).
+// The verdict is produced by waf_epilogue_kernel once every unit has been scanned.
+// =====================================================================================================================
+constexpr int kStreamThreads = 512;
+constexpr int kStreamNB = 64;  // requests per task
+
+struct StreamCtx {
+    const UnitDesc* ud;     // shared memory
+    uint32_t clsaddr;       // shared-window address of the class map
+    const uint16_t* gtbl;   // full transition table (global)
+    uint32_t C;
+    uint32_t D0;
+    uint32_t acclo;
+    uint32_t end1addr;      // shared-window address of end1 (valid for states < hot)
+    uint32_t hot;
+    uint32_t Aw;
+    uint32_t* rows;         // global atom bitmaps [n][Aw]
+    const uint32_t* s_off;  // this task's offsets (shared memory), s_off[i] = off[r0 + i]
+    uint32_t r0, nreq;
+};
+
+__device__ __forceinline__ void st_fire_list(const KParams& p, const uint32_t* idx, const uint32_t* events, uint32_t ci, uint32_t* row, uint32_t* latch) {
+    uint32_t a = __ldg(idx + ci), b = __ldg(idx + ci + 1);
+    uint32_t l = *latch;
+    for (uint32_t i = a; i < b; ++i) {
+        const uint32_t e = __ldg(events + i);
+        const uint32_t kind = e >> kEvKindShift, lb = 1u << ((e >> kEvLatchShift) & 31u), at = e & kEvAtomMask;
+        if (kind == 0u || (kind == 1u && (l & lb))) atomicOr(row + (at >> 5), 1u << (at & 31));
+        else if (kind == 2u) l &= ~lb;
+        else if (kind == 3u) l |= lb;
+    }
+    *latch = l;
+}
+
+// end-of-field events of `state` for request `req`
+__device__ __forceinline__ void st_apply_end(const KParams& p, const StreamCtx& c, uint32_t state, uint32_t req, uint32_t* latch) {
+    uint32_t e1 = 0xFFFFu;
+    if (state < c.hot) e1 = lds_u16(c.end1addr + 2u * state);
+    if (e1 == 0xFFFEu) return;
+    uint32_t* row = c.rows + (size_t)req * c.Aw;
+    if (e1 != 0xFFFFu) atomicOr(row + (e1 >> 5), 1u << (e1 & 31));
+    else st_fire_list(p, p.end_idx, p.end_events, c.ud->end_base + state, row, latch);
+}
+
+// Exact walk of one 16-byte segment on the full table.  `vm`: bytes that belong to the block; `bm`: positions where a
+// new request starts.  `req` = request (absolute index) owning the first valid byte.  With `apply`, accept and
+// end-of-field events are applied to the global bitmaps.  Returns the end state.
+__device__ __noinline__ uint32_t st_careful_segment(const KParams& p, const StreamCtx& c, uint4 data, uint32_t seg, uint32_t vm, uint32_t bm, uint32_t state,
+                                                    uint32_t req, bool apply, uint32_t* latch_io) {
+    const uint32_t words[4] = {data.x, data.y, data.z, data.w};
+    uint32_t latch = *latch_io;
+    uint32_t last = 0xFFFFFFFFu;
+    for (uint32_t k = 0; k < 16; ++k) {
+        if (!((vm >> k) & 1u)) continue;
+        if ((bm >> k) & 1u) {
+            if (apply) st_apply_end(p, c, state, req, &latch);
+            state = c.D0;
+            latch = 0;
+            last = 0xFFFFFFFFu;
+            // the request that owns this byte: the last one starting at or before it (empty requests share offsets)
+            const uint32_t pos = seg + k;
+            uint32_t i = req - c.r0 + 1;
+            while (i + 1 <= c.nreq && c.s_off[i + 1] <= pos) ++i;
+            req = c.r0 + i;
+        }
+        const uint32_t byte = (words[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+        state = __ldg(c.gtbl + state * c.C + lds_u8(c.clsaddr + byte));
+        if (apply && state >= c.acclo && state != last) {
+            st_fire_list(p, p.acc_idx, p.acc_events, c.ud->acc_base + state - c.acclo, c.rows + (size_t)req * c.Aw, &latch);
+            last = state;
+        }
+    }
+    *latch_io = latch;
+    return state;
+}
+
+__global__ void __launch_bounds__(kStreamThreads, 2) waf_stream_scan_kernel(const __grid_constant__ KParams p, uint32_t* __restrict__ rows,
+                                                                            uint32_t* __restrict__ task_counter, uint32_t n_blocks, uint32_t n_tasks) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    // layout: image | units | per-warp offsets
+    const uint32_t img_bytes = r16(p.image_bytes);
+    uint8_t* s_img = smem;
+    UnitDesc* s_units = reinterpret_cast<UnitDesc*>(smem + img_bytes);
+    uint32_t* s_offs_all = reinterpret_cast<uint32_t*>(smem + img_bytes + r16(p.n_units * (uint32_t)sizeof(UnitDesc)));
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + img_bytes + r16(p.n_units * (uint32_t)sizeof(UnitDesc)) + (kStreamThreads / 32) * (kStreamNB + 4) * 4);
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0 && img_bytes) {
+        mbar_expect_tx(s_bar, img_bytes);
+        for (uint32_t o = 0; o < img_bytes; o += 32768u) {
+            uint32_t n = img_bytes - o < 32768u ? img_bytes - o : 32768u;
+            bulk_g2s(s_img + o, p.image + o, n, s_bar);
+        }
+    }
+    for (uint32_t i = tid; i < p.n_units * (sizeof(UnitDesc) / 4); i += kStreamThreads)
+        reinterpret_cast<uint32_t*>(s_units)[i] = __ldg(reinterpret_cast<const uint32_t*>(p.units) + i);
+    if (img_bytes) mbar_wait(s_bar, 0);
+    __syncthreads();
+
+    const uint32_t a_img = smem_u32(s_img);
+    uint32_t* s_off = s_offs_all + warp * (kStreamNB + 4);
+    const uint32_t a_off = smem_u32(s_off);
+    const uint32_t FULL = 0xFFFFFFFFu;
+
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(task_counter, 1u);
+        t = __shfl_sync(FULL, t, 0);
+        if (t >= n_tasks) break;
+        const uint32_t u = t / n_blocks, b = t - u * n_blocks;
+        const UnitDesc& ud = s_units[u];
+        StreamCtx c;
+        c.ud = &ud;
+        c.clsaddr = a_img + ud.cls_off;
+        c.gtbl = reinterpret_cast<const uint16_t*>(p.arena + ud.tbl_off);
+        c.C = ud.n_classes;
+        c.D0 = ud.start_state;
+        c.acclo = ud.acc_lo;
+        c.end1addr = a_img + ud.end1_off;
+        c.hot = ud.hot_states;
+        c.Aw = p.atom_words;
+        c.rows = rows;
+        c.s_off = s_off;
+        c.r0 = b * kStreamNB;
+        c.nreq = min((uint32_t)kStreamNB, p.n - c.r0);
+        const uint32_t C2 = 2u * ud.n_classes, trap = ud.hot_states, lim = ud.lim, idle = ud.idle_state;
+        const uint32_t hotaddr = a_img + ud.hot_off, acc1addr = a_img + ud.acc1_off;
+        const bool has_latch = ud.has_latch != 0;
+        const uint8_t* col = p.col[ud.field];
+        const uint32_t* goff = p.off[ud.field] + c.r0;
+        __syncwarp();
+        for (uint32_t i = lane; i <= c.nreq; i += 32) s_off[i] = __ldg(goff + i);
+        __syncwarp();
+        const uint32_t B0 = s_off[0], B1 = s_off[c.nreq];
+        uint32_t carry = c.D0;
+        uint32_t latch = 0;  // warp-uniform
+        uint32_t prev_w3 = 0;  // last word of lane 31 of the previous window (warm-up bytes for lane 0 are never needed: lane 0 is exact)
+
+        for (uint32_t Wb = B0 & ~15u; Wb < B1; Wb += 512u) {
+            const uint32_t seg = Wb + 16u * lane;
+            uint4 d = make_uint4(0, 0, 0, 0);
+            if (seg < B1 && seg + 16u > B0) d = ld_nc_v4(col + seg);
+            // valid bytes of this segment
+            uint32_t vm = 0;
+            {
+                const uint32_t lo = B0 > seg ? min(B0 - seg, 16u) : 0u;
+                const uint32_t hi = B1 > seg ? min(B1 - seg, 16u) : 0u;
+                if (hi > lo) vm = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+            }
+            // request owning the first valid byte, and the request starts inside the segment
+            uint32_t ri = 0, bm = 0;
+            bool starts_exact = false;
+            if (vm) {
+                const uint32_t p0 = seg + (__ffs(vm) - 1);
+                // upper_bound over s_off[0..nreq]: first index with s_off[i] > p0
+                uint32_t lo = 0, hi = c.nreq + 1;
+                while (lo < hi) {
+                    uint32_t mid = (lo + hi) >> 1;
+                    if (lds_u32_v(a_off + 4u * mid) <= p0) lo = mid + 1;
+                    else hi = mid;
+                }
+                ri = lo - 1;  // last request starting at or before p0: it is non-empty and owns p0
+                starts_exact = lds_u32_v(a_off + 4u * ri) == p0;
+                for (uint32_t i = ri + 1; i < c.nreq; ++i) {
+                    const uint32_t o = lds_u32_v(a_off + 4u * i);
+                    if (o >= seg + 16u) break;
+                    if (o > p0 && lds_u32_v(a_off + 4u * (i + 1)) > o) bm |= 1u << (o - seg);  // non-empty request starting at o
+                }
+            }
+            const uint32_t req0 = c.r0 + ri;
+
+            // ---- P1: speculative walk on the shared-memory rows (no side effects) ----
+            const uint32_t words[4] = {d.x, d.y, d.z, d.w};
+            uint32_t assumed;
+            {
+                const uint32_t up = __shfl_up_sync(FULL, d.w, 1);
+                const uint32_t wprev = lane == 0 ? prev_w3 : up;
+                if (lane == 0 || starts_exact) assumed = starts_exact ? c.D0 : carry;
+                else {
+                    uint32_t s = idle;
+#pragma unroll
+                    for (int bi = 0; bi < 4; ++bi) {
+                        const uint32_t byte = __byte_perm(wprev, 0, 0x4440 + bi);
+                        s = lds_u16(hotaddr + min(s, trap) * C2 + 2u * lds_u8(c.clsaddr + byte));
+                    }
+                    assumed = s;
+                }
+            }
+            uint32_t s_end = assumed, mx = 0, nb = 0, s_pre0 = 0, s_pre1 = 0;
+            {
+                uint32_t s = min(assumed, trap);
+                mx = assumed >= trap ? assumed : 0;
+#pragma unroll
+                for (int wi = 0; wi < 4; ++wi) {
+                    const uint32_t w = words[wi];
+                    const uint32_t v4 = (vm >> (4 * wi)) & 0xFu, b4 = (bm >> (4 * wi)) & 0xFu;
+                    if (!__any_sync(FULL, v4)) continue;
+                    if (b4 == 0) {
+#pragma unroll
+                        for (int bi = 0; bi < 4; ++bi) {
+                            const uint32_t byte = __byte_perm(w, 0, 0x4440 + bi);
+                            const uint32_t st = lds_u16(hotaddr + s * C2 + 2u * lds_u8(c.clsaddr + byte));
+                            s = (v4 & (1u << bi)) ? st : s;
+                            mx = max(mx, s);
+                        }
+                    } else {
+#pragma unroll
+                        for (int bi = 0; bi < 4; ++bi) {
+                            if (!(v4 & (1u << bi))) continue;
+                            if (b4 & (1u << bi)) {
+                                if (nb == 0) s_pre0 = s;
+                                else if (nb == 1) s_pre1 = s;
+                                ++nb;
+                                s = min(c.D0, trap);
+                            }
+                            const uint32_t byte = __byte_perm(w, 0, 0x4440 + bi);
+                            s = lds_u16(hotaddr + s * C2 + 2u * lds_u8(c.clsaddr + byte));
+                            mx = max(mx, s);
+                        }
+                    }
+                }
+                s_end = s;
+            }
+            bool need_full = vm && (mx >= lim || nb > 2);  // accept events, a cold state, or more boundaries than recorded
+            bool trapped = vm && mx >= trap;
+
+            // ---- P2: make the chain of states exact ----
+            for (;;) {
+                const uint32_t prev_end = __shfl_up_sync(FULL, s_end, 1);
+                const uint32_t true_start = starts_exact ? c.D0 : (lane == 0 ? carry : prev_end);
+                const bool bad = vm && (trapped || assumed != true_start);
+                if (!__any_sync(FULL, bad)) break;
+                if (bad) {
+                    uint32_t l2 = 0;
+                    s_end = st_careful_segment(p, c, d, seg, vm, bm, true_start, req0, false, &l2);
+                    assumed = true_start;
+                    trapped = false;
+                    need_full = true;
+                }
+            }
+
+            // ---- P3: side effects, from validated states ----
+            if (has_latch && vm && !need_full && nb) {
+                // end-of-field lists that involve latches (or are not in the shared-memory table) must be applied in string order
+                if (s_pre0 >= c.hot || lds_u16(c.end1addr + 2u * s_pre0) == 0xFFFFu) need_full = true;
+                if (nb > 1 && (s_pre1 >= c.hot || lds_u16(c.end1addr + 2u * s_pre1) == 0xFFFFu)) need_full = true;
+            }
+            const uint32_t full_mask = __ballot_sync(FULL, need_full);
+            const uint32_t bnd_mask = __ballot_sync(FULL, vm && nb > 0);
+            if (!has_latch) {
+                if (need_full) {
+                    uint32_t l2 = 0;
+                    st_careful_segment(p, c, d, seg, vm, bm, assumed, req0, true, &l2);
+                } else if (nb) {
+                    uint32_t l2 = 0;
+                    st_apply_end(p, c, s_pre0, req0, &l2);
+                    if (nb > 1) {
+                        // request owning the byte at the first boundary
+                        const uint32_t pos = seg + (__ffs(bm) - 1);
+                        uint32_t i = ri + 1;
+                        while (i + 1 <= c.nreq && s_off[i + 1] <= pos) ++i;
+                        st_apply_end(p, c, s_pre1, c.r0 + i, &l2);
+                    }
+                }
+            } else {
+                // latch events are order dependent: lanes that need the general path run one after the other, the latch
+                // register travelling with them; a request boundary anywhere resets it
+                if (!need_full && nb) {
+                    uint32_t l2 = 0;
+                    st_apply_end(p, c, s_pre0, req0, &l2);  // no latch kinds can fire here: one-atom / empty lists only take the cheap path
+                    if (nb > 1) {
+                        const uint32_t pos = seg + (__ffs(bm) - 1);
+                        uint32_t i = ri + 1;
+                        while (i + 1 <= c.nreq && s_off[i + 1] <= pos) ++i;
+                        st_apply_end(p, c, s_pre1, c.r0 + i, &l2);
+                    }
+                }
+                uint32_t m = full_mask;
+                int prev_lane = -1;
+                while (m) {
+                    const int l = __ffs(m) - 1;
+                    m &= m - 1;
+                    // boundaries in lanes strictly between the previous general lane and this one reset the latch
+                    const uint32_t between = bnd_mask & ((1u << l) - 1u) & ~((prev_lane < 0) ? 0u : ((2u << prev_lane) - 1u));
+                    if (between) latch = 0;
+                    uint32_t lt = latch;
+                    if ((int)lane == l) st_careful_segment(p, c, d, seg, vm, bm, assumed, req0, true, &lt);
+                    latch = __shfl_sync(FULL, lt, l);
+                    prev_lane = l;
+                }
+                {
+                    const uint32_t after = bnd_mask & ~((prev_lane < 0) ? 0u : ((2u << prev_lane) - 1u));
+                    if (after) latch = 0;
+                }
+            }
+
+            // carry for the next window: end state of the last valid lane
+            const uint32_t vlanes = __ballot_sync(FULL, vm != 0);
+            const int last_lane = 31 - __clz(vlanes);
+            carry = __shfl_sync(FULL, s_end, last_lane);
+            prev_w3 = __shfl_sync(FULL, d.w, 31);
+        }
+        // end of the block: the last non-empty request ends at B1
+        if (lane == 0 && B1 > B0) {
+            uint32_t i = c.nreq - 1;
+            while (i > 0 && s_off[i] == B1) --i;  // trailing empty requests
+            uint32_t lt = latch;
+            st_apply_end(p, c, carry, c.r0 + i, &lt);
+        }
+    }
+}
+
+// Verdicts once every unit has been scanned: one thread per request.  Empty fields never reach the stream scan;
+// their end-of-field events (the DFA's start state at end of input) are applied here.
+__global__ void __launch_bounds__(256) waf_epilogue_kernel(const __grid_constant__ KParams p, uint32_t* __restrict__ rows) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < p.n; r += gridDim.x * blockDim.x) {
+        uint32_t* row = rows + (size_t)r * p.atom_words;
+        for (uint32_t u = 0; u < p.n_units; ++u) {
+            const UnitDesc ud = p.units[u];
+            const uint32_t* o = p.off[ud.field] + r;
+            if (o[0] != o[1] || !ud.end_any) continue;
+            uint32_t a = __ldg(p.end_idx + ud.end_base + ud.start_state), b = __ldg(p.end_idx + ud.end_base + ud.start_state + 1);
+            for (uint32_t i = a; i < b; ++i) {
+                const uint32_t e = __ldg(p.end_events + i);
+                if ((e >> kEvKindShift) == 0u) row[(e & kEvAtomMask) >> 5] |= 1u << (e & 31);  // latch kinds cannot fire on an empty field
+            }
+        }
+        request_epilogue(p, r, row, 1);
+    }
+}
+
 // GeoipDB::lookup for a batch of addresses (pingoo/geoip.rs:73-91)
 __global__ void geoip_lookup_kernel(const __grid_constant__ KParams p, const uint8_t* __restrict__ ip,
                                     const uint8_t* __restrict__ is_v6, uint32_t n, uint32_t* __restrict__ asn_out,
@@ -677,7 +1021,35 @@ const char* waf_configure(int device, size_t* max_smem_optin, int* sm_count) {
     *sm_count = v;
     e = cudaFuncSetAttribute(waf_verdict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*max_smem_optin);
     if (e != cudaSuccess) return cudaGetErrorString(e);
+    e = cudaFuncSetAttribute(waf_stream_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*max_smem_optin);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
     return nullptr;
+}
+
+size_t waf_stream_smem_bytes(uint32_t image_bytes, uint32_t n_units) {
+    return r16(image_bytes) + r16(n_units * (uint32_t)sizeof(UnitDesc)) + (kStreamThreads / 32) * (kStreamNB + 4) * 4 + 64;
+}
+
+const char* waf_stream_launch(const KParams& p, uint32_t* rows, uint32_t* task_counter, int sm_count, size_t smem_bytes, void* stream) {
+    if (p.n == 0) return nullptr;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(task_counter, 0, sizeof(uint32_t), s);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    e = cudaMemsetAsync(rows, 0, (size_t)p.n * p.atom_words * 4, s);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    const uint32_t n_blocks = (p.n + kStreamNB - 1) / kStreamNB;
+    const uint32_t n_tasks = n_blocks * p.n_units;
+    if (n_tasks) {
+        int ctas_per_sm = smem_bytes * 2 + 2048 <= 227 * 1024 ? 2 : 1;
+        waf_stream_scan_kernel<<<sm_count * ctas_per_sm, kStreamThreads, smem_bytes, s>>>(p, rows, task_counter, n_blocks, n_tasks);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cudaGetErrorString(e);
+    }
+    int blocks = (int)((p.n + 255) / 256);
+    if (blocks > sm_count * 8) blocks = sm_count * 8;
+    waf_epilogue_kernel<<<blocks, 256, 0, s>>>(p, rows);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
 const char* waf_launch(const KParams& p, const LaunchPlan& plan, void* stream) {
