@@ -50,6 +50,8 @@ struct DevMem {
     }
 };
 
+constexpr uint32_t kHostSlices = 16;  // host-pointer path: copy/compute pipeline depth
+
 struct Staging {
     void* d = nullptr;
     size_t cap = 0;
@@ -89,7 +91,8 @@ struct pgw_ruleset {
     std::atomic<uint64_t> launches{0};
     // host-pointer path
     Staging stage_cols[5], stage_offs[5], stage_ip, stage_v6, stage_port, stage_asn, stage_country, stage_flags, stage_verdict;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t slice_ready[kHostSlices] = {};
     uint64_t last_h2d = 0, last_d2h = 0;
 };
 
@@ -243,7 +246,10 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
         M.release();
         return fail(std::string("CUDA: device allocation/upload failed: ") + cudaGetErrorString(cudaGetLastError()), err, err_cap);
     }
-    if (cudaStreamCreateWithFlags(&rs->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    bool sok = cudaStreamCreateWithFlags(&rs->stream, cudaStreamNonBlocking) == cudaSuccess &&
+               cudaStreamCreateWithFlags(&rs->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (uint32_t i = 0; i < kHostSlices && sok; ++i) sok = cudaEventCreateWithFlags(&rs->slice_ready[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!sok) {
         M.release();
         return fail("CUDA: stream creation failed", err, err_cap);
     }
@@ -319,59 +325,99 @@ int pgw_evaluate_batch_host(pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdi
     cudaSetDevice(rs->device);
     const HostProgram& H = rs->prog;
     const uint32_t n = b->n;
-    cudaStream_t s = rs->stream;
+    cudaStream_t s = rs->stream, cs = rs->copy_stream;
+    const pgw_strcol* hc[5] = {&b->host, &b->url, &b->path, &b->method, &b->user_agent};
+    const bool geo_on_device = H.lpm.geo_loaded && H.needs_geo_cols && !(b->asn && b->country);
+    const bool need_ip = H.needs_ip || geo_on_device;
+    const bool geo_cols = H.needs_geo_cols && b->asn && b->country;
+
+    // device staging for the whole batch (grown on demand, reused by later calls)
     pgw_batch d;
     memset(&d, 0, sizeof d);
-    d.n = n;
-    uint64_t h2d = 0;
-    auto up = [&](Staging& st, const void* src, size_t bytes, size_t pad) -> const void* {
-        if (!st.ensure(bytes + pad)) return nullptr;
-        if (bytes && cudaMemcpyAsync(st.d, src, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return nullptr;
-        h2d += bytes;
-        return st.d;
-    };
-    const pgw_strcol* hc[5] = {&b->host, &b->url, &b->path, &b->method, &b->user_agent};
     pgw_strcol* dc[5] = {&d.host, &d.url, &d.path, &d.method, &d.user_agent};
-    for (int f = 0; f < 5; ++f) {
+    bool ok = true;
+    for (int f = 0; f < 5 && ok; ++f) {
         if (H.field_slot[f] < 0) continue;
         if (!hc[f]->offsets) return fail(std::string("batch is missing offsets for http_request.") + kFieldNames[f], nullptr, 0);
-        dc[f]->offsets = (const uint32_t*)up(rs->stage_offs[f], hc[f]->offsets, (size_t)(n + 1) * 4, 0);
-        if (!dc[f]->offsets) return fail("CUDA: staging copy failed", nullptr, 0);
-        if ((H.scanned_fields_mask >> f) & 1) {
+        ok = rs->stage_offs[f].ensure((size_t)(n + 1) * 4);
+        dc[f]->offsets = (const uint32_t*)rs->stage_offs[f].d;
+        if (ok && ((H.scanned_fields_mask >> f) & 1)) {
             if (!hc[f]->bytes) return fail(std::string("batch is missing bytes for http_request.") + kFieldNames[f], nullptr, 0);
-            size_t total = hc[f]->offsets[n];
-            dc[f]->bytes = (const uint8_t*)up(rs->stage_cols[f], hc[f]->bytes, total, 64);
-            if (!dc[f]->bytes) return fail("CUDA: staging copy failed", nullptr, 0);
+            ok = rs->stage_cols[f].ensure((size_t)hc[f]->offsets[n] + 64);
+            dc[f]->bytes = (const uint8_t*)rs->stage_cols[f].d;
         }
     }
-    bool geo_on_device = H.lpm.geo_loaded && H.needs_geo_cols && !(b->asn && b->country);
-    bool need_ip = H.needs_ip || geo_on_device;
     if (need_ip) {
         if (!b->ip || !b->ip_is_v6) return fail("batch is missing client.ip columns", nullptr, 0);
-        d.ip = (const uint8_t*)up(rs->stage_ip, b->ip, (size_t)n * 16, 0);
-        d.ip_is_v6 = (const uint8_t*)up(rs->stage_v6, b->ip_is_v6, n, 0);
-        if (!d.ip || !d.ip_is_v6) return fail("CUDA: staging copy failed", nullptr, 0);
+        ok = ok && rs->stage_ip.ensure((size_t)n * 16) && rs->stage_v6.ensure(n);
+        d.ip = (const uint8_t*)rs->stage_ip.d;
+        d.ip_is_v6 = (const uint8_t*)rs->stage_v6.d;
     }
     if (H.needs_port) {
         if (!b->remote_port) return fail("batch is missing client.remote_port", nullptr, 0);
-        d.remote_port = (const int32_t*)up(rs->stage_port, b->remote_port, (size_t)n * 4, 0);
-        if (!d.remote_port) return fail("CUDA: staging copy failed", nullptr, 0);
+        ok = ok && rs->stage_port.ensure((size_t)n * 4);
+        d.remote_port = (const int32_t*)rs->stage_port.d;
     }
-    if (H.needs_geo_cols && b->asn && b->country) {
-        d.asn = (const int64_t*)up(rs->stage_asn, b->asn, (size_t)n * 8, 0);
-        d.country = (const uint16_t*)up(rs->stage_country, b->country, (size_t)n * 2, 0);
-        if (!d.asn || !d.country) return fail("CUDA: staging copy failed", nullptr, 0);
+    if (geo_cols) {
+        ok = ok && rs->stage_asn.ensure((size_t)n * 8) && rs->stage_country.ensure((size_t)n * 2);
+        d.asn = (const int64_t*)rs->stage_asn.d;
+        d.country = (const uint16_t*)rs->stage_country.d;
     }
     if (b->flags) {
-        d.flags = (const uint8_t*)up(rs->stage_flags, b->flags, n, 0);
-        if (!d.flags) return fail("CUDA: staging copy failed", nullptr, 0);
+        ok = ok && rs->stage_flags.ensure(n);
+        d.flags = (const uint8_t*)rs->stage_flags.d;
     }
-    if (!rs->stage_verdict.ensure((size_t)n * 4)) return fail("CUDA: staging allocation failed", nullptr, 0);
+    ok = ok && rs->stage_verdict.ensure((size_t)n * 4);
+    if (!ok) return fail("CUDA: staging allocation failed", nullptr, 0);
+
+    // The batch is cut into slices of whole requests: slice k is copied on the copy stream while slice k-1 is evaluated
+    // on the compute stream, so that only the first copy and the last kernel are exposed.  Offsets stay absolute (the
+    // column base does not move), a slice is just a window of the offset arrays.
+    uint32_t slice = 262144;
+    if (const char* e = getenv("PGW_HOST_SLICE")) { long v = atol(e); if (v >= 1024) slice = (uint32_t)v; }
+    uint32_t n_slices = (n + slice / 2) / slice;
+    if (n_slices < 1) n_slices = 1;
+    if (n_slices > kHostSlices) n_slices = kHostSlices;
+    const uint32_t per = ((n + n_slices - 1) / n_slices + 31u) & ~31u;
+    uint64_t h2d = 0;
+    cudaError_t ce = cudaSuccess;
+    auto up = [&](const void* dst, const void* src, size_t off, size_t bytes) {
+        if (!bytes || ce != cudaSuccess) return;
+        ce = cudaMemcpyAsync((uint8_t*)dst + off, (const uint8_t*)src + off, bytes, cudaMemcpyHostToDevice, cs);
+        h2d += bytes;
+    };
     std::string e;
-    if (launch_on(rs, &d, (uint32_t*)rs->stage_verdict.d, s, e)) return fail(e, nullptr, 0);
-    if (cudaMemcpyAsync(verdict_out, rs->stage_verdict.d, (size_t)n * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess)
-        return fail("CUDA: verdict copy failed", nullptr, 0);
-    cudaError_t ce = cudaStreamSynchronize(s);
+    uint32_t k = 0;
+    for (uint32_t a = 0; a < n; a += per, ++k) {
+        const uint32_t z = a + per < n ? a + per : n, m = z - a;
+        for (int f = 0; f < 5; ++f) {
+            if (H.field_slot[f] < 0) continue;
+            // the slice's offsets (its first entry is the previous slice's last one: copied once)
+            up(dc[f]->offsets, hc[f]->offsets, a ? ((size_t)a + 1) * 4 : 0, a ? (size_t)m * 4 : ((size_t)m + 1) * 4);
+            if ((H.scanned_fields_mask >> f) & 1) up(dc[f]->bytes, hc[f]->bytes, hc[f]->offsets[a], (size_t)hc[f]->offsets[z] - hc[f]->offsets[a]);
+        }
+        if (need_ip) { up(d.ip, b->ip, (size_t)a * 16, (size_t)m * 16); up(d.ip_is_v6, b->ip_is_v6, a, m); }
+        if (H.needs_port) up(d.remote_port, b->remote_port, (size_t)a * 4, (size_t)m * 4);
+        if (geo_cols) { up(d.asn, b->asn, (size_t)a * 8, (size_t)m * 8); up(d.country, b->country, (size_t)a * 2, (size_t)m * 2); }
+        if (b->flags) up(d.flags, b->flags, a, m);
+        if (ce != cudaSuccess) break;
+        if ((ce = cudaEventRecord(rs->slice_ready[k], cs)) != cudaSuccess) break;
+        if ((ce = cudaStreamWaitEvent(s, rs->slice_ready[k], 0)) != cudaSuccess) break;
+        pgw_batch v = d;
+        v.n = m;
+        pgw_strcol* vc[5] = {&v.host, &v.url, &v.path, &v.method, &v.user_agent};
+        for (int f = 0; f < 5; ++f)
+            if (vc[f]->offsets) vc[f]->offsets += a;
+        if (v.ip) { v.ip += (size_t)a * 16; v.ip_is_v6 += a; }
+        if (v.remote_port) v.remote_port += a;
+        if (v.asn) { v.asn += a; v.country += a; }
+        if (v.flags) v.flags += a;
+        uint32_t* vd = (uint32_t*)rs->stage_verdict.d + a;
+        if (launch_on(rs, &v, vd, s, e)) { cudaStreamSynchronize(cs); cudaStreamSynchronize(s); return fail(e, nullptr, 0); }
+        if ((ce = cudaMemcpyAsync(verdict_out + a, vd, (size_t)m * 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
+    }
+    cudaError_t c1 = cudaStreamSynchronize(cs), c2 = cudaStreamSynchronize(s);
+    if (ce == cudaSuccess) ce = c1 != cudaSuccess ? c1 : c2;
     if (ce != cudaSuccess) return fail(std::string("CUDA: ") + cudaGetErrorString(ce), nullptr, 0);
     rs->last_h2d = h2d;
     rs->last_d2h = (uint64_t)n * 4;
@@ -448,6 +494,9 @@ void pgw_ruleset_destroy(pgw_ruleset* rs) {
     rs->stage_ip.release(); rs->stage_v6.release(); rs->stage_port.release(); rs->stage_asn.release();
     rs->stage_country.release(); rs->stage_flags.release(); rs->stage_verdict.release();
     if (rs->stream) cudaStreamDestroy(rs->stream);
+    if (rs->copy_stream) cudaStreamDestroy(rs->copy_stream);
+    for (auto& ev : rs->slice_ready)
+        if (ev) cudaEventDestroy(ev);
     delete rs;
 }
 

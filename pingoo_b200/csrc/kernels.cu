@@ -702,12 +702,75 @@ __device__ __noinline__ uint32_t st_careful_segment(const KParams& p, const Stre
         const uint32_t byte = (words[k >> 2] >> (8 * (k & 3))) & 0xFFu;
         state = __ldg(c.gtbl + state * c.C + lds_u8(c.clsaddr + byte));
         if (apply && state >= c.acclo && state != last) {
+            const uint32_t l0 = latch;
             st_fire_list(p, p.acc_idx, p.acc_events, c.ud->acc_base + state - c.acclo, c.rows + (size_t)req * c.Aw, &latch);
-            last = state;
+            last = (c.ud->has_latch || l0 != latch) ? 0xFFFFFFFFu : state;  // only plain FIRE lists are idempotent
         }
     }
     *latch_io = latch;
     return state;
+}
+
+struct StreamWalk {
+    uint32_t end, mx, nb, pre0, pre1;
+};
+
+// Re-walk of one segment on the shared-memory rows from an exact start state (rare path of the stream scan, cheaper than
+// st_careful_segment: no global table reads).  Without `apply` it recomputes what P1 computes (end state, max state,
+// states before the first two request boundaries); with `apply` it applies accept / end-of-field events.  Falls back to
+// the full table when a cold state is met.
+__device__ __noinline__ void st_rewalk(const KParams& p, const StreamCtx& c, uint32_t hotaddr, uint32_t C2, uint32_t acc1addr, uint4 data, uint32_t seg,
+                                       uint32_t vm, uint32_t bm, uint32_t start, uint32_t req, bool apply, uint32_t* latch_io, StreamWalk* out) {
+    const uint32_t words[4] = {data.x, data.y, data.z, data.w};
+    const uint32_t trap = c.hot;
+    uint32_t latch = *latch_io, last = 0xFFFFFFFFu;
+    uint32_t s = start, mx = start >= trap ? start : 0, nb = 0, pre0 = 0, pre1 = 0;
+    const uint32_t req_in = req;
+    bool cold = start >= trap;
+    for (uint32_t k = 0; k < 16 && !cold; ++k) {
+        if (!((vm >> k) & 1u)) continue;
+        if ((bm >> k) & 1u) {
+            if (nb == 0) pre0 = s;
+            else if (nb == 1) pre1 = s;
+            ++nb;
+            if (apply) st_apply_end(p, c, s, req, &latch);
+            s = c.D0;
+            latch = 0;
+            last = 0xFFFFFFFFu;
+            const uint32_t pos = seg + k;
+            uint32_t i = req - c.r0 + 1;
+            while (i + 1 <= c.nreq && c.s_off[i + 1] <= pos) ++i;
+            req = c.r0 + i;
+        }
+        const uint32_t byte = (words[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+        s = lds_u16(hotaddr + s * C2 + 2u * lds_u8(c.clsaddr + byte));
+        mx = max(mx, s);
+        if (s >= trap) { cold = true; break; }
+        if (apply && s >= c.acclo && s != last) {
+            const uint32_t a1 = lds_u16(acc1addr + 2u * (s - c.acclo));
+            uint32_t* row = c.rows + (size_t)req * c.Aw;
+            if (a1 != 0xFFFFu) {
+                atomicOr(row + (a1 >> 5), 1u << (a1 & 31));
+                last = s;
+            } else {
+                st_fire_list(p, p.acc_idx, p.acc_events, c.ud->acc_base + s - c.acclo, row, &latch);
+            }
+        }
+    }
+    if (cold) {
+        // a cold state: redo the whole segment exactly on the full table (events are idempotent / replayed from the same latch)
+        uint32_t l2 = *latch_io;
+        s = st_careful_segment(p, c, data, seg, vm, bm, start, req_in, apply, &l2);
+        latch = l2;
+        mx = trap;  // forces the apply pass for this lane
+        nb = 3;
+    }
+    *latch_io = latch;
+    out->end = s;
+    out->mx = mx;
+    out->nb = nb;
+    out->pre0 = pre0;
+    out->pre1 = pre1;
 }
 
 __global__ void __launch_bounds__(kStreamThreads, 2) waf_stream_scan_kernel(const __grid_constant__ KParams p, uint32_t* __restrict__ rows,
@@ -814,14 +877,15 @@ __global__ void __launch_bounds__(kStreamThreads, 2) waf_stream_scan_kernel(cons
             const uint32_t words[4] = {d.x, d.y, d.z, d.w};
             uint32_t assumed;
             {
-                const uint32_t up = __shfl_up_sync(FULL, d.w, 1);
-                const uint32_t wprev = lane == 0 ? prev_w3 : up;
+                const uint32_t up2 = __shfl_up_sync(FULL, d.z, 1);
+                const uint32_t up3 = __shfl_up_sync(FULL, d.w, 1);
                 if (lane == 0 || starts_exact) assumed = starts_exact ? c.D0 : carry;
                 else {
+                    // warm up on the 8 bytes before the segment (the previous lane's last two words)
                     uint32_t s = idle;
 #pragma unroll
-                    for (int bi = 0; bi < 4; ++bi) {
-                        const uint32_t byte = __byte_perm(wprev, 0, 0x4440 + bi);
+                    for (int bi = 0; bi < 8; ++bi) {
+                        const uint32_t byte = __byte_perm(bi < 4 ? up2 : up3, 0, 0x4440 + (bi & 3));
                         s = lds_u16(hotaddr + min(s, trap) * C2 + 2u * lds_u8(c.clsaddr + byte));
                     }
                     assumed = s;
@@ -866,34 +930,55 @@ __global__ void __launch_bounds__(kStreamThreads, 2) waf_stream_scan_kernel(cons
             bool trapped = vm && mx >= trap;
 
             // ---- P2: make the chain of states exact ----
+            const uint32_t p0pos = vm ? seg + (__ffs(vm) - 1) : 0u;
+            const bool pre_b = vm && starts_exact && p0pos > B0;  // a request ends exactly where this segment starts
+            uint32_t prev_end;
             for (;;) {
-                const uint32_t prev_end = __shfl_up_sync(FULL, s_end, 1);
-                const uint32_t true_start = starts_exact ? c.D0 : (lane == 0 ? carry : prev_end);
+                prev_end = __shfl_up_sync(FULL, s_end, 1);
+                if (lane == 0) prev_end = carry;
+                const uint32_t true_start = starts_exact ? c.D0 : prev_end;
                 const bool bad = vm && (trapped || assumed != true_start);
                 if (!__any_sync(FULL, bad)) break;
                 if (bad) {
                     uint32_t l2 = 0;
-                    s_end = st_careful_segment(p, c, d, seg, vm, bm, true_start, req0, false, &l2);
+                    StreamWalk wk;
+                    st_rewalk(p, c, hotaddr, C2, acc1addr, d, seg, vm, bm, true_start, req0, false, &l2, &wk);
+                    s_end = wk.end;
+                    mx = wk.mx;
+                    nb = wk.nb;
+                    s_pre0 = wk.pre0;
+                    s_pre1 = wk.pre1;
                     assumed = true_start;
                     trapped = false;
-                    need_full = true;
+                    need_full = mx >= lim || nb > 2;
                 }
             }
 
             // ---- P3: side effects, from validated states ----
-            if (has_latch && vm && !need_full && nb) {
-                // end-of-field lists that involve latches (or are not in the shared-memory table) must be applied in string order
-                if (s_pre0 >= c.hot || lds_u16(c.end1addr + 2u * s_pre0) == 0xFFFFu) need_full = true;
-                if (nb > 1 && (s_pre1 >= c.hot || lds_u16(c.end1addr + 2u * s_pre1) == 0xFFFFu)) need_full = true;
+            // request whose field ends right before this segment (pre_b): its final state is the previous lane's end state
+            uint32_t preq = 0;
+            if (pre_b) {
+                uint32_t i = ri - 1;
+                while (i > 0 && s_off[i] == s_off[i + 1]) --i;
+                preq = c.r0 + i;
             }
-            const uint32_t full_mask = __ballot_sync(FULL, need_full);
-            const uint32_t bnd_mask = __ballot_sync(FULL, vm && nb > 0);
+            bool pre_general = false;
+            if (has_latch && vm) {
+                // end-of-field lists that involve latches (or are not in the shared-memory table) must be applied in string order
+                if (!need_full && nb) {
+                    if (s_pre0 >= c.hot || lds_u16(c.end1addr + 2u * s_pre0) == 0xFFFFu) need_full = true;
+                    if (nb > 1 && (s_pre1 >= c.hot || lds_u16(c.end1addr + 2u * s_pre1) == 0xFFFFu)) need_full = true;
+                }
+                if (pre_b && (prev_end >= c.hot || lds_u16(c.end1addr + 2u * prev_end) == 0xFFFFu)) pre_general = true;
+            }
+            const uint32_t bnd_mask = __ballot_sync(FULL, vm && (nb > 0 || pre_b));
             if (!has_latch) {
+                uint32_t l2 = 0;
+                if (pre_b) st_apply_end(p, c, prev_end, preq, &l2);
                 if (need_full) {
-                    uint32_t l2 = 0;
-                    st_careful_segment(p, c, d, seg, vm, bm, assumed, req0, true, &l2);
+                    StreamWalk wk;
+                    st_rewalk(p, c, hotaddr, C2, acc1addr, d, seg, vm, bm, assumed, req0, true, &l2, &wk);
                 } else if (nb) {
-                    uint32_t l2 = 0;
                     st_apply_end(p, c, s_pre0, req0, &l2);
                     if (nb > 1) {
                         // request owning the byte at the first boundary
@@ -905,33 +990,45 @@ __global__ void __launch_bounds__(kStreamThreads, 2) waf_stream_scan_kernel(cons
                 }
             } else {
                 // latch events are order dependent: lanes that need the general path run one after the other, the latch
-                // register travelling with them; a request boundary anywhere resets it
-                if (!need_full && nb) {
+                // register travelling with them; a request boundary anywhere resets it.  Lists without latch kinds are
+                // applied in parallel first (they commute with everything).
+                {
                     uint32_t l2 = 0;
-                    st_apply_end(p, c, s_pre0, req0, &l2);  // no latch kinds can fire here: one-atom / empty lists only take the cheap path
-                    if (nb > 1) {
-                        const uint32_t pos = seg + (__ffs(bm) - 1);
-                        uint32_t i = ri + 1;
-                        while (i + 1 <= c.nreq && s_off[i + 1] <= pos) ++i;
-                        st_apply_end(p, c, s_pre1, c.r0 + i, &l2);
+                    if (pre_b && !pre_general) st_apply_end(p, c, prev_end, preq, &l2);
+                    if (!need_full && nb) {
+                        st_apply_end(p, c, s_pre0, req0, &l2);
+                        if (nb > 1) {
+                            const uint32_t pos = seg + (__ffs(bm) - 1);
+                            uint32_t i = ri + 1;
+                            while (i + 1 <= c.nreq && s_off[i + 1] <= pos) ++i;
+                            st_apply_end(p, c, s_pre1, c.r0 + i, &l2);
+                        }
                     }
                 }
-                uint32_t m = full_mask;
+                uint32_t m = __ballot_sync(FULL, need_full || pre_general);
                 int prev_lane = -1;
                 while (m) {
                     const int l = __ffs(m) - 1;
                     m &= m - 1;
-                    // boundaries in lanes strictly between the previous general lane and this one reset the latch
-                    const uint32_t between = bnd_mask & ((1u << l) - 1u) & ~((prev_lane < 0) ? 0u : ((2u << prev_lane) - 1u));
-                    if (between) latch = 0;
+                    // boundaries in lanes strictly between the previous ordered lane and this one reset the latch
+                    const uint32_t below_l = (1u << l) - 1u;
+                    const uint32_t upto_prev = prev_lane < 0 ? 0u : ((2u << prev_lane) - 1u);
+                    if (bnd_mask & below_l & ~upto_prev) latch = 0;
                     uint32_t lt = latch;
-                    if ((int)lane == l) st_careful_segment(p, c, d, seg, vm, bm, assumed, req0, true, &lt);
+                    if ((int)lane == l) {
+                        if (pre_general) st_apply_end(p, c, prev_end, preq, &lt);
+                        if (pre_b) lt = 0;
+                        if (need_full) {
+                            StreamWalk wk;
+                            st_rewalk(p, c, hotaddr, C2, acc1addr, d, seg, vm, bm, assumed, req0, true, &lt, &wk);
+                        } else if (nb) lt = 0;
+                    }
                     latch = __shfl_sync(FULL, lt, l);
                     prev_lane = l;
                 }
                 {
-                    const uint32_t after = bnd_mask & ~((prev_lane < 0) ? 0u : ((2u << prev_lane) - 1u));
-                    if (after) latch = 0;
+                    const uint32_t upto_prev = prev_lane < 0 ? 0u : ((2u << prev_lane) - 1u);
+                    if (bnd_mask & ~upto_prev) latch = 0;
                 }
             }
 
