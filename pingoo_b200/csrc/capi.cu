@@ -87,7 +87,8 @@ struct pgw_ruleset {
     uint32_t hot_states_total = 0;
     uint32_t* counters = nullptr;  // ring of work counters: one per in-flight launch
     bool stream_kernel = false;    // kernel path: stream scan (v5) instead of lane-owned requests (v3)
-    size_t stream_smem = 0;
+    bool field_kernel = false;     // kernel path: unit-major field scan (v6)
+    size_t stream_smem = 0, field_smem = 0;
     std::atomic<uint64_t> launches{0};
     // host-pointer path
     Staging stage_cols[5], stage_offs[5], stage_ip, stage_v6, stage_port, stage_asn, stage_country, stage_flags, stage_verdict;
@@ -238,9 +239,13 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     std::vector<uint32_t> zeros(64, 0);
     rs->counters = (uint32_t*)chk(M.upload(zeros));
     rs->stream_smem = waf_stream_smem_bytes((uint32_t)image.size(), (uint32_t)units.size());
+    rs->field_smem = waf_field_smem_bytes((uint32_t)image.size(), (uint32_t)units.size());
     {
         const char* km = getenv("PGW_KERNEL");
-        rs->stream_kernel = km ? (strcmp(km, "stream") == 0) : false;
+        // default path: unit-major field scan; "lane" (request-major persistent kernel) and "stream" (speculative
+        // column scan) remain selectable for comparison
+        rs->stream_kernel = km && strcmp(km, "stream") == 0;
+        rs->field_kernel = !km || (strcmp(km, "lane") != 0 && strcmp(km, "stream") != 0);
     }
     if (!ok) {
         M.release();
@@ -252,6 +257,15 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     if (!sok) {
         M.release();
         return fail("CUDA: stream creation failed", err, err_cap);
+    }
+    {
+        // scratch of the field/stream paths comes from the stream-ordered allocator: keep freed blocks cached in the
+        // pool instead of returning them to the driver at every synchronisation
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, rs->device) == cudaSuccess && pool) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
     }
     rs->finalized = true;
     return 0;
@@ -284,6 +298,16 @@ static int launch_on(const pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdic
     // each in-flight launch gets its own work counter (ring of 64), so concurrent callers do not interfere
     uint64_t seq = const_cast<pgw_ruleset*>(rs)->launches.fetch_add(1, std::memory_order_relaxed);
     P.work_counter = rs->counters + (seq & 63);
+    if (rs->field_kernel) {
+        const size_t row_words = (size_t)b->n * P.atom_words;
+        uint32_t* scratch = nullptr;
+        if (cudaMallocAsync((void**)&scratch, (row_words + kFieldCounters) * 4, (cudaStream_t)stream) != cudaSuccess) { e = "CUDA: scratch allocation failed"; return 1; }
+        const char* m = waf_field_launch(P, scratch, scratch + row_words, rs->sm_count, rs->field_smem, stream);
+        cudaFreeAsync(scratch, (cudaStream_t)stream);
+        if (m) { e = std::string("CUDA launch failed: ") + m; return 1; }
+        const_cast<pgw_ruleset*>(rs)->launches.fetch_add(1, std::memory_order_relaxed);  // two kernels per batch on this path
+        return 0;
+    }
     if (rs->stream_kernel) {
         // scratch (atom bitmaps + task counter) comes from the stream-ordered allocator: no state shared between callers
         const size_t row_words = (size_t)b->n * P.atom_words;

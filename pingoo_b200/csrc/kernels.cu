@@ -402,6 +402,10 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
     const uint32_t a_rows = smem_u32(my_rows);
     const uint32_t a_ext = smem_u32(smem + L.ext) + tid * 4u;  // word k of this lane: a_ext + k * kThreads * 4
     constexpr uint32_t kExtStride = kThreads * 4u;
+    const uint32_t a_ext_w = a_ext - lane * 4u;    // the same for lane 0 of this warp
+    const uint32_t a_rows_w = a_rows - lane * 4u;
+    // lane k of a warp fetches word k of a claimed request's offsets: (field slot k/2, entry r + k%2)
+    const uint32_t* my_off = lane < 2u * p.n_slots ? p.off[p.slot_field[lane >> 1]] + (lane & 1u) : nullptr;
 
     // ---- per-lane state ----
     bool c_have = false;   // a unit is being scanned (its chunk for this iteration is in `cur`)
@@ -490,20 +494,27 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
                 else { pool_next = base; pool_end = min(base + kClaim, p.n); }
             }
             const uint32_t rank = __popc(need_mask & ((1u << lane) - 1u));
-            if (want_claim && pool_next + rank < pool_end) {
+            const bool got = want_claim && pool_next + rank < pool_end;
+            if (got) {
                 q_req = pool_next + rank;
                 q_rowi = own ? (c_rowi ^ 1u) : (p_have ? (p_rowi ^ 1u) : 0u);
-                const uint32_t ra = a_rows + q_rowi * Aw * stride * 4u;
-                for (uint32_t w = 0; w < Aw; ++w) sts_u32(ra + w * stride * 4u, 0u);
-                // field offsets of the queued request land in this lane's `ext` words (the current request no longer needs them)
-                for (uint32_t sl = 0; sl < p.n_slots; ++sl) {
-                    const uint32_t* o = p.off[p.slot_field[sl]] + q_req;
-                    cp_async4(a_ext + (2u * sl) * kExtStride, o);
-                    cp_async4(a_ext + (2u * sl + 1u) * kExtStride, o + 1);
-                }
                 q_have = true;
                 q_fresh = true;
             }
+            // The per-request setup is done by the whole warp for each claiming lane `t` (claims trickle in one or two
+            // lanes at a time, so doing it in the claiming lane alone would run at 1/32 efficiency): lane k fetches word k
+            // of the field offsets of t's request into t's `ext` slots (cp.async, lands before the next iteration's use)
+            // and lanes < Aw clear t's bitmap row.
+            uint32_t gm = __ballot_sync(0xFFFFFFFFu, got);
+            while (gm) {
+                const uint32_t t = __ffs(gm) - 1u;
+                gm &= gm - 1u;
+                const uint32_t req_t = pool_next + __popc(need_mask & ((1u << t) - 1u));
+                const uint32_t rowi_t = __shfl_sync(0xFFFFFFFFu, q_rowi, t);
+                if (lane < 2u * p.n_slots) cp_async4(a_ext_w + t * 4u + lane * kExtStride, my_off + req_t);
+                for (uint32_t w = lane; w < Aw; w += 32u) sts_u32(a_rows_w + t * 4u + (rowi_t * Aw + w) * stride * 4u, 0u);
+            }
+            __syncwarp();
             pool_next = min(pool_end, pool_next + (uint32_t)__popc(need_mask));
         }
 
@@ -511,8 +522,12 @@ __global__ void __launch_bounds__(kThreads, 1) waf_verdict_kernel(const __grid_c
         const bool finishing = c_have && (c_end <= c_base + kChunk);
         const bool to_new = q_have && !q_fresh && !n_have && (own ? (finishing && last_unit) : true);
         const bool to_same = finishing && !last_unit;
+        if (__any_sync(0xFFFFFFFFu, to_new)) {
+            // offsets of queued requests were fetched by other lanes of the warp in an earlier iteration
+            cp_async_commit_wait();
+            __syncwarp();
+        }
         if (to_same || to_new) {
-            if (to_new) cp_async_commit_wait();
             n_unit = to_new ? 0u : c_unit + 1u;
             n_new = to_new;
             const uint32_t ua = a_units + n_unit * (uint32_t)sizeof(UnitDesc);
@@ -1048,6 +1063,244 @@ __global__ void __launch_bounds__(kStreamThreads, 2) waf_stream_scan_kernel(cons
     }
 }
 
+// =====================================================================================================================
+// Field scan (kernel path "field"): unit-major, lane-owned strings.  A warp works on ONE scan unit at a time, so all the
+// per-unit parameters are warp-uniform; each lane owns one request's field of that unit and walks it 16 bytes per
+// iteration exactly like the lane path (speculative 4-byte word walk on the shared-memory rows).  A lane that finishes
+// takes the next request of the unit from a warp pool of 32 claimed requests whose field offsets were fetched coalesced
+// one pool ahead, so the per-request setup is a shuffle.  Atom bits go to bitmaps in global memory (red.or, rare) and
+// waf_epilogue_kernel turns them into verdicts.  Warps move to the next unit on their own when a unit runs dry.
+// =====================================================================================================================
+#ifndef PGW_FS_THREADS
+#define PGW_FS_THREADS 1024
+#endif
+constexpr int kFsThreads = PGW_FS_THREADS;
+
+__device__ __forceinline__ void red_or(uint32_t* addr, uint32_t v) { asm volatile("red.global.or.b32 [%0], %1;" ::"l"(addr), "r"(v) : "memory"); }
+
+// events of CSR row `ci` applied to a bitmap in global memory; true if all of them were plain FIREs
+__device__ __forceinline__ bool fs_fire_list(const uint32_t* idx, const uint32_t* events, uint32_t ci, uint32_t* row, uint32_t* latch) {
+    uint32_t a = __ldg(idx + ci), b = __ldg(idx + ci + 1);
+    uint32_t l = *latch;
+    bool pure = true;
+    for (uint32_t i = a; i < b; ++i) {
+        const uint32_t e = __ldg(events + i);
+        const uint32_t kind = e >> kEvKindShift, lb = 1u << ((e >> kEvLatchShift) & 31u), at = e & kEvAtomMask;
+        if (kind == 0u || (kind == 1u && (l & lb))) red_or(row + (at >> 5), 1u << (at & 31));
+        else if (kind == 2u) l &= ~lb;
+        else if (kind == 3u) l |= lb;
+        pure &= kind == 0u;
+    }
+    *latch = l;
+    return pure;
+}
+
+// accept events of four hot states of one word (at least one accepting); returns the new `last`
+__device__ __noinline__ uint32_t fs_events_word(const KParams& p, const UnitDesc* ud, uint32_t acc1addr, uint32_t s01, uint32_t s23, uint32_t m4,
+                                                uint32_t last, uint32_t* latch, uint32_t* row) {
+    const uint32_t acclo = ud->acc_lo;
+#pragma unroll 1
+    for (int bi = 0; bi < 4; ++bi) {
+        const uint32_t st = ((bi < 2 ? s01 : s23) >> (16 * (bi & 1))) & 0xFFFFu;
+        if (!((m4 >> bi) & 1u) || st < acclo || st == last) continue;
+        const uint32_t a1 = lds_u16(acc1addr + 2u * (st - acclo));
+        if (a1 != 0xFFFFu) {
+            red_or(row + (a1 >> 5), 1u << (a1 & 31));
+            last = st;
+        } else {
+            last = fs_fire_list(p.acc_idx, p.acc_events, ud->acc_base + st - acclo, row, latch) ? st : 0xFFFFFFFFu;
+        }
+    }
+    return last;
+}
+
+// one word walked on the full table in global memory (a cold state is involved)
+__device__ __noinline__ void fs_slow_word(const KParams& p, const UnitDesc* ud, uint32_t clsaddr, uint32_t w, uint32_t m4, uint32_t* state,
+                                          uint32_t* last, uint32_t* latch, uint32_t* row) {
+    const uint16_t* tbl = reinterpret_cast<const uint16_t*>(p.arena + ud->tbl_off);
+    const uint32_t C = ud->n_classes, acclo = ud->acc_lo;
+    uint32_t st = *state, la = *last;
+#pragma unroll 1
+    for (int bi = 0; bi < 4; ++bi) {
+        if (!((m4 >> bi) & 1u)) continue;
+        const uint32_t byte = (w >> (8 * bi)) & 0xFFu;
+        st = __ldg(tbl + st * C + lds_u8(clsaddr + byte));
+        if (st >= acclo && st != la) la = fs_fire_list(p.acc_idx, p.acc_events, ud->acc_base + st - acclo, row, latch) ? st : 0xFFFFFFFFu;
+    }
+    *state = st;
+    *last = la;
+}
+
+__global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __grid_constant__ KParams p, uint32_t* __restrict__ rows,
+                                                                       uint32_t* __restrict__ counters) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t img_bytes = r16(p.image_bytes);
+    uint8_t* s_img = smem;
+    UnitDesc* s_units = reinterpret_cast<UnitDesc*>(smem + img_bytes);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + img_bytes + r16(p.n_units * (uint32_t)sizeof(UnitDesc)));
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0 && img_bytes) {
+        mbar_expect_tx(s_bar, img_bytes);
+        for (uint32_t o = 0; o < img_bytes; o += 32768u) {
+            uint32_t n = img_bytes - o < 32768u ? img_bytes - o : 32768u;
+            bulk_g2s(s_img + o, p.image + o, n, s_bar);
+        }
+    }
+    for (uint32_t i = tid; i < p.n_units * (sizeof(UnitDesc) / 4); i += kFsThreads)
+        reinterpret_cast<uint32_t*>(s_units)[i] = __ldg(reinterpret_cast<const uint32_t*>(p.units) + i);
+    if (img_bytes) mbar_wait(s_bar, 0);
+    __syncthreads();
+
+    const uint32_t a_img = smem_u32(s_img);
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t Aw = p.atom_words, N = p.n;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    for (uint32_t u = 0; u < p.n_units; ++u) {
+        const UnitDesc* ud = &s_units[u];
+        const uint32_t C2 = 2u * ud->n_classes, D0 = ud->start_state, trap = ud->hot_states, lim = ud->lim, acclo = ud->acc_lo;
+        const uint32_t clsaddr = a_img + ud->cls_off, hotaddr = a_img + ud->hot_off, acc1addr = a_img + ud->acc1_off, end1addr = a_img + ud->end1_off;
+        const uint8_t* col = p.col[ud->field];
+        const uint32_t* off = p.off[ud->field];
+        uint32_t* ctr = counters + u;
+
+        // warp pools: `pool` is being handed out, `ahead` is claimed and its offsets are in flight
+        uint32_t pool_base = 0, pool_next = 0, pool_end = 0, my_lo = 0, my_hi = 0;
+        uint32_t ah_base = 0, ah_end = 0, ah_lo = 0, ah_hi = 0;
+        bool ah_valid = false, dry = N == 0;
+        auto claim_ahead = [&]() {
+            ah_valid = false;
+            if (dry) return;
+            uint32_t b = 0;
+            if (lane == 0) b = atomicAdd(ctr, 32u);
+            b = __shfl_sync(FULL, b, 0);
+            if (b >= N) { dry = true; return; }
+            ah_base = b;
+            ah_end = min(b + 32u, N);
+            ah_lo = __ldg(off + min(b + lane, N));
+            ah_hi = __ldg(off + min(b + lane + 1u, N));
+            ah_valid = true;
+        };
+        claim_ahead();
+
+        bool have = false, pend = false;
+        uint32_t req = 0, base = 0, start = 0, end = 0, state = 0, latch = 0, last = 0xFFFFFFFFu;
+        uint32_t q_req = 0, q_start = 0, q_end = 0;
+        uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
+
+        for (;;) {
+            // ---- rotate: next chunk of the current string, or adopt the pending one ----
+            if (have) {
+                base += 16u;
+                cur = nxt;
+            } else if (pend) {
+                req = q_req;
+                start = q_start;
+                end = q_end;
+                base = start & ~15u;
+                state = D0;
+                latch = 0;
+                last = 0xFFFFFFFFu;
+                cur = nxt;
+                have = true;
+                pend = false;
+            }
+            // ---- lanes that run out of bytes in this iteration (or are idle) take the next request of the pool ----
+            const bool finishing = have && end <= base + 16u;
+            const bool want = !pend && (!have || finishing);
+            const uint32_t need = __ballot_sync(FULL, want);
+            if (need) {
+                if (pool_next == pool_end && ah_valid) {
+                    pool_base = pool_next = ah_base;
+                    pool_end = ah_end;
+                    my_lo = ah_lo;
+                    my_hi = ah_hi;
+                    claim_ahead();
+                }
+                const uint32_t idx = pool_next + __popc(need & lt_mask);
+                const uint32_t k = (idx - pool_base) & 31u;
+                const uint32_t s0 = __shfl_sync(FULL, my_lo, k), e0 = __shfl_sync(FULL, my_hi, k);
+                if (want && idx < pool_end && e0 > s0) {  // empty fields are left to the epilogue kernel
+                    q_req = idx;
+                    q_start = s0;
+                    q_end = e0;
+                    pend = true;
+                    nxt = ld_nc_v4(col + (s0 & ~15u));
+                }
+                pool_next = min(pool_end, pool_next + (uint32_t)__popc(need));
+            }
+            if (!__any_sync(FULL, have)) {
+                if (!__any_sync(FULL, pend) && pool_next == pool_end && !ah_valid) break;
+                continue;
+            }
+            if (have && !finishing) nxt = ld_nc_v4(col + base + 16u);
+
+            // ---- walk the bytes of this chunk that belong to the field ----
+            uint32_t mk = 0;
+            if (have) {
+                const uint32_t lo = start > base ? start - base : 0u;
+                const uint32_t hi = min(end - base, 16u);
+                mk = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+            }
+#pragma unroll
+            for (int wi = 0; wi < 4; ++wi) {
+                const uint32_t m4 = (mk >> (4 * wi)) & 0xFu;
+                if (!__any_sync(FULL, m4)) continue;
+                const uint32_t w = wi == 0 ? cur.x : wi == 1 ? cur.y : wi == 2 ? cur.z : cur.w;
+                uint32_t spec = min(state, trap);
+                uint32_t sv[4];
+#pragma unroll
+                for (int bi = 0; bi < 4; ++bi) {
+                    const uint32_t byte = __byte_perm(w, 0, 0x4440 + bi);
+                    const uint32_t cls = lds_u8(clsaddr + byte);
+                    const uint32_t st = lds_u16(hotaddr + spec * C2 + 2u * cls);
+                    spec = (m4 & (1u << bi)) ? st : spec;
+                    sv[bi] = spec;
+                }
+                const uint32_t mx4 = max(max(sv[0], sv[1]), max(sv[2], sv[3]));
+                if (max(mx4, state) >= lim) {
+                    uint32_t* row = rows + (size_t)req * Aw;
+                    if (max(mx4, state) >= trap) {
+                        uint32_t t_state = state, t_last = last, t_latch = latch;
+                        fs_slow_word(p, ud, clsaddr, w, m4, &t_state, &t_last, &t_latch, row);
+                        state = t_state;
+                        last = t_last;
+                        latch = t_latch;
+                    } else {
+                        if (mx4 >= acclo) {
+                            uint32_t t_latch = latch;
+                            last = fs_events_word(p, ud, acc1addr, sv[0] | (sv[1] << 16), sv[2] | (sv[3] << 16), m4, last, &t_latch, row);
+                            latch = t_latch;
+                        }
+                        state = spec;
+                    }
+                } else {
+                    state = spec;
+                }
+            }
+            if (finishing) {
+                uint32_t e1 = 0xFFFFu;
+                if (state < trap) e1 = lds_u16(end1addr + 2u * state);
+                if (e1 != 0xFFFEu) {
+                    uint32_t* row = rows + (size_t)req * Aw;
+                    if (e1 != 0xFFFFu) red_or(row + (e1 >> 5), 1u << (e1 & 31));
+                    else if (ud->end_any) {
+                        uint32_t t_latch = latch;
+                        fs_fire_list(p.end_idx, p.end_events, ud->end_base + state, row, &t_latch);
+                    }
+                }
+                have = false;
+            }
+        }
+    }
+}
+
 // Verdicts once every unit has been scanned: one thread per request.  Empty fields never reach the stream scan;
 // their end-of-field events (the DFA's start state at end of input) are applied here.
 __global__ void __launch_bounds__(256) waf_epilogue_kernel(const __grid_constant__ KParams p, uint32_t* __restrict__ rows) {
@@ -1120,7 +1373,32 @@ const char* waf_configure(int device, size_t* max_smem_optin, int* sm_count) {
     if (e != cudaSuccess) return cudaGetErrorString(e);
     e = cudaFuncSetAttribute(waf_stream_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*max_smem_optin);
     if (e != cudaSuccess) return cudaGetErrorString(e);
+    e = cudaFuncSetAttribute(waf_field_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*max_smem_optin);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
     return nullptr;
+}
+
+size_t waf_field_smem_bytes(uint32_t image_bytes, uint32_t n_units) { return r16(image_bytes) + r16(n_units * (uint32_t)sizeof(UnitDesc)) + 64; }
+
+const char* waf_field_launch(const KParams& p, uint32_t* rows, uint32_t* counters, int sm_count, size_t smem_bytes, void* stream) {
+    if (p.n == 0) return nullptr;
+    if (p.n_units > kFieldCounters) return "too many scan units for the field-scan path";
+    cudaStream_t s = (cudaStream_t)stream;
+    // bitmaps and the per-unit claim counters are one allocation: one memset
+    cudaError_t e = cudaMemsetAsync(rows, 0, ((size_t)p.n * p.atom_words + kFieldCounters) * 4, s);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    if (p.n_units) {
+        const uint32_t want = (p.n + kFsThreads - 1) / kFsThreads;
+        const int grid = (int)(want < (uint32_t)sm_count ? want : (uint32_t)sm_count);
+        waf_field_scan_kernel<<<grid, kFsThreads, smem_bytes, s>>>(p, rows, counters);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cudaGetErrorString(e);
+    }
+    int blocks = (int)((p.n + 255) / 256);
+    if (blocks > sm_count * 8) blocks = sm_count * 8;
+    waf_epilogue_kernel<<<blocks, 256, 0, s>>>(p, rows);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
 size_t waf_stream_smem_bytes(uint32_t image_bytes, uint32_t n_units) {

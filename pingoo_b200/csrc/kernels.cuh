@@ -86,6 +86,11 @@ const char* waf_launch(const KParams& p, const LaunchPlan& plan, void* stream);
 // stream-scan path: scan kernel + epilogue kernel; `rows` = n * atom_words words of scratch, `task_counter` one word
 size_t waf_stream_smem_bytes(uint32_t image_bytes, uint32_t n_units);
 const char* waf_stream_launch(const KParams& p, uint32_t* rows, uint32_t* task_counter, int sm_count, size_t smem_bytes, void* stream);
+// field-scan path: scan kernel + epilogue kernel; `rows` = n * atom_words words immediately followed by
+// kFieldCounters claim counters (`counters` points at them)
+constexpr uint32_t kFieldCounters = 64;
+size_t waf_field_smem_bytes(uint32_t image_bytes, uint32_t n_units);
+const char* waf_field_launch(const KParams& p, uint32_t* rows, uint32_t* counters, int sm_count, size_t smem_bytes, void* stream);
 const char* geoip_launch(const KParams& p, const uint8_t* ip, const uint8_t* is_v6, uint32_t n, uint32_t* asn_out,
                          uint16_t* country_out, void* stream);
 const char* waf_configure(int device, size_t* max_smem_optin, int* sm_count);

@@ -11,11 +11,15 @@ def run(rules, batch, label, steps=10):
     st = torch.cuda.current_stream().cuda_stream
     for _ in range(3): eng.evaluate_device(cb, out, st)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps): eng.evaluate_device(cb, out, st)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)/steps
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record()
+    for i in range(steps):
+        eng.evaluate_device(cb, out, st)
+        evs[i + 1].record()
+    torch.cuda.synchronize()
+    per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
+    ms = evs[0].elapsed_time(evs[steps])/steps
+    label = f"{label} [min {per[0]:.3f} med {per[len(per)//2]:.3f} max {per[-1]:.3f}]"
     scanned = sum(batch.total[f] for i,f in enumerate(synth.FIELDS) if (info.scanned_fields_mask>>i)&1)
     print(f"{label}: {ms:.3f} ms  {batch.n/ms/1e3:.1f} M req/s  alg {scanned/ms/1e6:.0f} GB/s  units={info.n_scan_units} hot={info.tile_requests}/{info.total_dfa_states} arena={info.table_arena_bytes} smem={info.smem_bytes}", flush=True)
 rules, payloads, _ = synth.make_ruleset(128)
