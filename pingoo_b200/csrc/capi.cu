@@ -195,6 +195,8 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     rs->smem_bytes = waf_smem_bytes((uint32_t)image.size(), (uint32_t)units.size(), H.atom_words, n_scan_slots);
     for (auto& u : units) rs->hot_states_total += u.hot_states;
     P.units = (const UnitDesc*)chk(M.upload(units));
+    memset(P.udesc, 0, sizeof P.udesc);
+    for (size_t i = 0; i < units.size() && i < kMaxConstUnits; ++i) P.udesc[i] = units[i];
     P.n_units = (uint32_t)units.size();
     P.arena = (const uint8_t*)chk(M.upload(H.arena));
     P.image = (const uint8_t*)chk(M.upload(image));
@@ -245,7 +247,7 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
         // default path: unit-major field scan; "lane" (request-major persistent kernel) and "stream" (speculative
         // column scan) remain selectable for comparison
         rs->stream_kernel = km && strcmp(km, "stream") == 0;
-        rs->field_kernel = !km || (strcmp(km, "lane") != 0 && strcmp(km, "stream") != 0);
+        rs->field_kernel = (!km || (strcmp(km, "lane") != 0 && strcmp(km, "stream") != 0)) && units.size() <= kMaxConstUnits;
     }
     if (!ok) {
         M.release();

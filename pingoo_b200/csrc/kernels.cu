@@ -1075,6 +1075,8 @@ __global__ void __launch_bounds__(kStreamThreads, 2) waf_stream_scan_kernel(cons
 #define PGW_FS_THREADS 1024
 #endif
 constexpr int kFsThreads = PGW_FS_THREADS;
+constexpr uint32_t kFsSlotStride = kFsThreads * 4u;  // per-lane slots: request index, latch register, last fired state
+constexpr uint32_t kFsPoolBytes = 144;  // 33 offsets of a claimed pool (+pad), two buffers per warp
 
 __device__ __forceinline__ void red_or(uint32_t* addr, uint32_t v) { asm volatile("red.global.or.b32 [%0], %1;" ::"l"(addr), "r"(v) : "memory"); }
 
@@ -1158,21 +1160,24 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
     __syncthreads();
 
     const uint32_t a_img = smem_u32(s_img);
+    const uint32_t a_pool = smem_u32(s_bar) + 64u + (tid >> 5) * 2u * kFsPoolBytes;
+    const uint32_t a_slot = smem_u32(s_bar) + 64u + (kFsThreads / 32) * 2u * kFsPoolBytes + tid * 4u;  // word k at a_slot + k * kFsSlotStride
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t Aw = p.atom_words, N = p.n;
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     for (uint32_t u = 0; u < p.n_units; ++u) {
-        const UnitDesc* ud = &s_units[u];
-        const uint32_t C2 = 2u * ud->n_classes, D0 = ud->start_state, trap = ud->hot_states, lim = ud->lim, acclo = ud->acc_lo;
-        const uint32_t clsaddr = a_img + ud->cls_off, hotaddr = a_img + ud->hot_off, acc1addr = a_img + ud->acc1_off, end1addr = a_img + ud->end1_off;
-        const uint8_t* col = p.col[ud->field];
-        const uint32_t* off = p.off[ud->field];
+        const UnitDesc* ud = &s_units[u];  // for the out-of-line event paths
+        const UnitDesc& cu = p.udesc[u];   // constant bank, uniform index
+        const uint32_t C2 = 2u * cu.n_classes, D0 = cu.start_state, trap = cu.hot_states, lim = cu.lim, acclo = cu.acc_lo;
+        const uint32_t clsaddr = a_img + cu.cls_off, hotaddr = a_img + cu.hot_off, acc1addr = a_img + cu.acc1_off, end1addr = a_img + cu.end1_off;
+        const uint8_t* col = p.col[cu.field];
+        const uint32_t* off = p.off[cu.field];
         uint32_t* ctr = counters + u;
 
-        // warp pools: `pool` is being handed out, `ahead` is claimed and its offsets are in flight
-        uint32_t pool_base = 0, pool_next = 0, pool_end = 0, my_lo = 0, my_hi = 0;
-        uint32_t ah_base = 0, ah_end = 0, ah_lo = 0, ah_hi = 0;
+        // warp pools of 32 claimed requests, double buffered in shared memory: buffer `pb` is being handed out, the other
+        // one holds the next claim whose 33 field offsets are landing through cp.async (no registers, no stall)
+        uint32_t pool_next = 0, pool_end = 0, pb = 0, ah_base = 0;
         bool ah_valid = false, dry = N == 0;
         auto claim_ahead = [&]() {
             ah_valid = false;
@@ -1182,31 +1187,38 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
             b = __shfl_sync(FULL, b, 0);
             if (b >= N) { dry = true; return; }
             ah_base = b;
-            ah_end = min(b + 32u, N);
-            ah_lo = __ldg(off + min(b + lane, N));
-            ah_hi = __ldg(off + min(b + lane + 1u, N));
+            const uint32_t dst = a_pool + (pb ^ 1u) * kFsPoolBytes;
+            cp_async4(dst + lane * 4u, off + min(b + lane, N));
+            if (lane == 0) cp_async4(dst + 128u, off + min(b + 32u, N));
+            asm volatile("cp.async.commit_group;" ::: "memory");
             ah_valid = true;
         };
+        __syncwarp();
         claim_ahead();
 
         bool have = false, pend = false;
-        uint32_t req = 0, base = 0, start = 0, end = 0, state = 0, latch = 0, last = 0xFFFFFFFFu;
-        uint32_t q_req = 0, q_start = 0, q_end = 0;
+        // hot per-lane state lives in registers; what only the (rare) event paths need -- request index, latch register,
+        // last fired state -- lives in this lane's shared-memory slots
+        uint32_t base = 0, skip = 0, end = 0, state = 0;
+        uint32_t q_req = 0;
         uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
 
         for (;;) {
             // ---- rotate: next chunk of the current string, or adopt the pending one ----
             if (have) {
                 base += 16u;
+                skip = 0;
                 cur = nxt;
             } else if (pend) {
-                req = q_req;
-                start = q_start;
-                end = q_end;
+                const uint32_t sa = a_pool + pb * kFsPoolBytes + (q_req & 31u) * 4u;
+                const uint32_t start = lds_u32_v(sa);
+                end = lds_u32_v(sa + 4u);
                 base = start & ~15u;
+                skip = start & 15u;
                 state = D0;
-                latch = 0;
-                last = 0xFFFFFFFFu;
+                sts_u32(a_slot, q_req);
+                sts_u32(a_slot + kFsSlotStride, 0u);
+                sts_u32(a_slot + 2u * kFsSlotStride, 0xFFFFFFFFu);
                 cur = nxt;
                 have = true;
                 pend = false;
@@ -1217,21 +1229,22 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
             const uint32_t need = __ballot_sync(FULL, want);
             if (need) {
                 if (pool_next == pool_end && ah_valid) {
-                    pool_base = pool_next = ah_base;
-                    pool_end = ah_end;
-                    my_lo = ah_lo;
-                    my_hi = ah_hi;
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
+                    pb ^= 1u;
+                    pool_next = ah_base;
+                    pool_end = min(ah_base + 32u, N);
                     claim_ahead();
                 }
                 const uint32_t idx = pool_next + __popc(need & lt_mask);
-                const uint32_t k = (idx - pool_base) & 31u;
-                const uint32_t s0 = __shfl_sync(FULL, my_lo, k), e0 = __shfl_sync(FULL, my_hi, k);
-                if (want && idx < pool_end && e0 > s0) {  // empty fields are left to the epilogue kernel
-                    q_req = idx;
-                    q_start = s0;
-                    q_end = e0;
-                    pend = true;
-                    nxt = ld_nc_v4(col + (s0 & ~15u));
+                if (want && idx < pool_end) {
+                    const uint32_t sa = a_pool + pb * kFsPoolBytes + (idx & 31u) * 4u;
+                    const uint32_t s0 = lds_u32_v(sa), e0 = lds_u32_v(sa + 4u);
+                    if (e0 > s0) {  // empty fields are left to the epilogue kernel
+                        q_req = idx;
+                        pend = true;
+                        nxt = ld_nc_v4(col + (s0 & ~15u));
+                    }
                 }
                 pool_next = min(pool_end, pool_next + (uint32_t)__popc(need));
             }
@@ -1244,9 +1257,8 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
             // ---- walk the bytes of this chunk that belong to the field ----
             uint32_t mk = 0;
             if (have) {
-                const uint32_t lo = start > base ? start - base : 0u;
                 const uint32_t hi = min(end - base, 16u);
-                mk = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+                mk = ((1u << hi) - 1u) & ~((1u << skip) - 1u);
             }
 #pragma unroll
             for (int wi = 0; wi < 4; ++wi) {
@@ -1265,34 +1277,31 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                 }
                 const uint32_t mx4 = max(max(sv[0], sv[1]), max(sv[2], sv[3]));
                 if (max(mx4, state) >= lim) {
-                    uint32_t* row = rows + (size_t)req * Aw;
-                    if (max(mx4, state) >= trap) {
-                        uint32_t t_state = state, t_last = last, t_latch = latch;
-                        fs_slow_word(p, ud, clsaddr, w, m4, &t_state, &t_last, &t_latch, row);
-                        state = t_state;
-                        last = t_last;
-                        latch = t_latch;
-                    } else {
-                        if (mx4 >= acclo) {
-                            uint32_t t_latch = latch;
-                            last = fs_events_word(p, ud, acc1addr, sv[0] | (sv[1] << 16), sv[2] | (sv[3] << 16), m4, last, &t_latch, row);
-                            latch = t_latch;
+                    if (max(mx4, state) >= trap || mx4 >= acclo) {
+                        uint32_t* row = rows + (size_t)lds_u32_v(a_slot) * Aw;
+                        uint32_t t_latch = lds_u32_v(a_slot + kFsSlotStride), t_last = lds_u32_v(a_slot + 2u * kFsSlotStride);
+                        if (max(mx4, state) >= trap) {
+                            uint32_t t_state = state;
+                            fs_slow_word(p, ud, clsaddr, w, m4, &t_state, &t_last, &t_latch, row);
+                            spec = t_state;
+                        } else {
+                            t_last = fs_events_word(p, ud, acc1addr, sv[0] | (sv[1] << 16), sv[2] | (sv[3] << 16), m4, t_last, &t_latch, row);
                         }
-                        state = spec;
+                        sts_u32(a_slot + kFsSlotStride, t_latch);
+                        sts_u32(a_slot + 2u * kFsSlotStride, t_last);
                     }
-                } else {
-                    state = spec;
                 }
+                state = spec;
             }
             if (finishing) {
                 uint32_t e1 = 0xFFFFu;
                 if (state < trap) e1 = lds_u16(end1addr + 2u * state);
                 if (e1 != 0xFFFEu) {
-                    uint32_t* row = rows + (size_t)req * Aw;
+                    uint32_t* row = rows + (size_t)lds_u32_v(a_slot) * Aw;
                     if (e1 != 0xFFFFu) red_or(row + (e1 >> 5), 1u << (e1 & 31));
-                    else if (ud->end_any) {
-                        uint32_t t_latch = latch;
-                        fs_fire_list(p.end_idx, p.end_events, ud->end_base + state, row, &t_latch);
+                    else if (cu.end_any) {
+                        uint32_t t_latch = lds_u32_v(a_slot + kFsSlotStride);
+                        fs_fire_list(p.end_idx, p.end_events, cu.end_base + state, row, &t_latch);
                     }
                 }
                 have = false;
@@ -1378,11 +1387,13 @@ const char* waf_configure(int device, size_t* max_smem_optin, int* sm_count) {
     return nullptr;
 }
 
-size_t waf_field_smem_bytes(uint32_t image_bytes, uint32_t n_units) { return r16(image_bytes) + r16(n_units * (uint32_t)sizeof(UnitDesc)) + 64; }
+size_t waf_field_smem_bytes(uint32_t image_bytes, uint32_t n_units) {
+    return r16(image_bytes) + r16(n_units * (uint32_t)sizeof(UnitDesc)) + 64 + (kFsThreads / 32) * 2 * kFsPoolBytes + 3 * kFsSlotStride;
+}
 
 const char* waf_field_launch(const KParams& p, uint32_t* rows, uint32_t* counters, int sm_count, size_t smem_bytes, void* stream) {
     if (p.n == 0) return nullptr;
-    if (p.n_units > kFieldCounters) return "too many scan units for the field-scan path";
+    if (p.n_units > kFieldCounters || p.n_units > kMaxConstUnits) return "too many scan units for the field-scan path";
     cudaStream_t s = (cudaStream_t)stream;
     // bitmaps and the per-unit claim counters are one allocation: one memset
     cudaError_t e = cudaMemsetAsync(rows, 0, ((size_t)p.n * p.atom_words + kFieldCounters) * 4, s);

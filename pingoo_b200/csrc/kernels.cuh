@@ -17,6 +17,8 @@ constexpr int kChunk = PGW_CHUNK;   // bytes per lane per scan iteration (PGW_CH
 constexpr int kRowsPerLane = 2;     // atom bitmaps per lane: the request being scanned + one awaiting its epilogue
 constexpr uint32_t kClaim = 32;     // requests a warp claims from the global counter at a time
 
+constexpr uint32_t kMaxConstUnits = 24;  // rule sets with more scan units run on the lane path
+
 struct KParams {
     // ---- batch (device pointers, SoA) ----
     const uint8_t* col[5];      // field bytes, Field order; 16-byte aligned, readable to round_up(len,16)
@@ -72,6 +74,9 @@ struct KParams {
     uint32_t lpm_present;
     uint32_t geo_loaded;
     uint32_t need_lpm;          // any ip-set atom, or geo columns needed and resolved on device
+    // ---- copy of the first unit descriptors in the parameter (constant) bank: the field-scan kernel reads them with a
+    //      warp-uniform index, which keeps the per-unit parameters out of the vector register file ----
+    UnitDesc udesc[kMaxConstUnits];
 };
 
 struct LaunchPlan {
