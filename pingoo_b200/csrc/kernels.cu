@@ -1178,22 +1178,29 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
         // warp pools of 32 claimed requests, double buffered in shared memory: buffer `pb` is being handed out, the other
         // one holds the next claim whose 33 field offsets are landing through cp.async (no registers, no stall)
         uint32_t pool_next = 0, pool_end = 0, pb = 0, ah_base = 0;
-        bool ah_valid = false, dry = N == 0;
+        // claims are pipelined three deep so that no global latency is ever waited for: `ticket` (atomicAdd issued, result
+        // not looked at yet) -> `ahead` (offsets landing in the spare buffer) -> the pool being handed out
+        uint32_t ticket = 0;
+        bool tk_valid = false, ah_valid = false;
+        auto issue_ticket = [&]() {
+            if (lane == 0) ticket = atomicAdd(ctr, 32u);
+            tk_valid = true;
+        };
         auto claim_ahead = [&]() {
             ah_valid = false;
-            if (dry) return;
-            uint32_t b = 0;
-            if (lane == 0) b = atomicAdd(ctr, 32u);
-            b = __shfl_sync(FULL, b, 0);
-            if (b >= N) { dry = true; return; }
+            if (!tk_valid) return;
+            const uint32_t b = __shfl_sync(FULL, ticket, 0);
+            if (b >= N) { tk_valid = false; return; }
             ah_base = b;
             const uint32_t dst = a_pool + (pb ^ 1u) * kFsPoolBytes;
             cp_async4(dst + lane * 4u, off + min(b + lane, N));
             if (lane == 0) cp_async4(dst + 128u, off + min(b + 32u, N));
             asm volatile("cp.async.commit_group;" ::: "memory");
             ah_valid = true;
+            issue_ticket();
         };
         __syncwarp();
+        if (N) issue_ticket();
         claim_ahead();
 
         bool have = false, pend = false;
@@ -1226,6 +1233,8 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
             // ---- lanes that run out of bytes in this iteration (or are idle) take the next request of the pool ----
             const bool finishing = have && end <= base + 16u;
             const bool want = !pend && (!have || finishing);
+            bool do_ld = have && !finishing;
+            uint32_t ld_off = base + 16u;
             const uint32_t need = __ballot_sync(FULL, want);
             if (need) {
                 if (pool_next == pool_end && ah_valid) {
@@ -1243,16 +1252,19 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                     if (e0 > s0) {  // empty fields are left to the epilogue kernel
                         q_req = idx;
                         pend = true;
-                        nxt = ld_nc_v4(col + (s0 & ~15u));
+                        ld_off = s0 & ~15u;
+                        do_ld = true;
                     }
                 }
                 pool_next = min(pool_end, pool_next + (uint32_t)__popc(need));
             }
+            // one load per lane and iteration, consumed in the next one: the next chunk of the current string or the first
+            // chunk of the string just claimed (a single instruction: two loads into the same registers would serialise)
+            if (do_ld) nxt = ld_nc_v4(col + ld_off);
             if (!__any_sync(FULL, have)) {
                 if (!__any_sync(FULL, pend) && pool_next == pool_end && !ah_valid) break;
                 continue;
             }
-            if (have && !finishing) nxt = ld_nc_v4(col + base + 16u);
 
             // ---- walk the bytes of this chunk that belong to the field ----
             uint32_t mk = 0;
