@@ -211,6 +211,8 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     P.care = (const uint32_t*)chk(M.upload(H.care));
     P.ns = (const NsAtom*)chk(M.upload(H.ns_atoms));
     P.n_ns = (uint32_t)H.ns_atoms.size();
+    memset(P.nsd, 0, sizeof P.nsd);
+    for (size_t i = 0; i < H.ns_atoms.size() && i < kMaxConstNs; ++i) P.nsd[i] = H.ns_atoms[i];
     P.code = (const uint16_t*)chk(M.upload(H.code));
     P.rule_off = (const uint32_t*)chk(M.upload(H.rule_off));
     P.term = (const uint8_t*)chk(M.upload(H.term));
@@ -246,7 +248,7 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
         const char* km = getenv("PGW_KERNEL");
         // default path: unit-major field scan; "lane" (request-major persistent kernel) and "stream" (speculative
         // column scan) remain selectable for comparison
-        rs->stream_kernel = km && strcmp(km, "stream") == 0;
+        rs->stream_kernel = km && strcmp(km, "stream") == 0 && units.size() <= kMaxConstUnits;
         rs->field_kernel = (!km || (strcmp(km, "lane") != 0 && strcmp(km, "stream") != 0)) && units.size() <= kMaxConstUnits;
     }
     if (!ok) {

@@ -188,7 +188,7 @@ __device__ __noinline__ void request_epilogue(const KParams& p, uint32_t r, uint
     if (p.country) country = p.country[r];
 
     for (uint32_t i = 0; i < p.n_ns; ++i) {
-        const NsAtom a = p.ns[i];
+        const NsAtom a = p.n_ns <= kMaxConstNs ? p.nsd[i] : p.ns[i];
         bool v = false;
         if (a.kind == 1 || a.kind == 2) {  // INT_CMP / INT_SET
             int64_t x;
@@ -1101,10 +1101,18 @@ __device__ __forceinline__ bool fs_fire_list(const uint32_t* idx, const uint32_t
 __device__ __noinline__ uint32_t fs_events_word(const KParams& p, const UnitDesc* ud, uint32_t acc1addr, uint32_t s01, uint32_t s23, uint32_t m4,
                                                 uint32_t last, uint32_t* latch, uint32_t* row) {
     const uint32_t acclo = ud->acc_lo;
+    // positions whose state is accepting
+    uint32_t am = m4;
+    if ((s01 & 0xFFFFu) < acclo) am &= ~1u;
+    if ((s01 >> 16) < acclo) am &= ~2u;
+    if ((s23 & 0xFFFFu) < acclo) am &= ~4u;
+    if ((s23 >> 16) < acclo) am &= ~8u;
 #pragma unroll 1
-    for (int bi = 0; bi < 4; ++bi) {
+    while (am) {
+        const int bi = __ffs(am) - 1;
+        am &= am - 1u;
         const uint32_t st = ((bi < 2 ? s01 : s23) >> (16 * (bi & 1))) & 0xFFFFu;
-        if (!((m4 >> bi) & 1u) || st < acclo || st == last) continue;
+        if (st == last) continue;
         const uint32_t a1 = lds_u16(acc1addr + 2u * (st - acclo));
         if (a1 != 0xFFFFu) {
             red_or(row + (a1 >> 5), 1u << (a1 & 31));
@@ -1297,7 +1305,10 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                             fs_slow_word(p, ud, clsaddr, w, m4, &t_state, &t_last, &t_latch, row);
                             spec = t_state;
                         } else {
-                            t_last = fs_events_word(p, ud, acc1addr, sv[0] | (sv[1] << 16), sv[2] | (sv[3] << 16), m4, t_last, &t_latch, row);
+                            // a string sitting in a sticky accepting state whose events were already applied: nothing to do
+                            const uint32_t s01 = sv[0] | (sv[1] << 16), s23 = sv[2] | (sv[3] << 16), ll = t_last | (t_last << 16);
+                            if (t_last > 0xFFFFu || s01 != ll || s23 != ll)
+                                t_last = fs_events_word(p, ud, acc1addr, s01, s23, m4, t_last, &t_latch, row);
                         }
                         sts_u32(a_slot + kFsSlotStride, t_latch);
                         sts_u32(a_slot + 2u * kFsSlotStride, t_last);
@@ -1328,9 +1339,10 @@ __global__ void __launch_bounds__(256) waf_epilogue_kernel(const __grid_constant
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < p.n; r += gridDim.x * blockDim.x) {
         uint32_t* row = rows + (size_t)r * p.atom_words;
         for (uint32_t u = 0; u < p.n_units; ++u) {
-            const UnitDesc ud = p.units[u];
+            const UnitDesc& ud = p.udesc[u];  // parameter bank (both callers keep n_units <= kMaxConstUnits)
+            if (!ud.end_any) continue;
             const uint32_t* o = p.off[ud.field] + r;
-            if (o[0] != o[1] || !ud.end_any) continue;
+            if (o[0] != o[1]) continue;
             uint32_t a = __ldg(p.end_idx + ud.end_base + ud.start_state), b = __ldg(p.end_idx + ud.end_base + ud.start_state + 1);
             for (uint32_t i = a; i < b; ++i) {
                 const uint32_t e = __ldg(p.end_events + i);

@@ -17,6 +17,7 @@ constexpr int kChunk = PGW_CHUNK;   // bytes per lane per scan iteration (PGW_CH
 constexpr int kRowsPerLane = 2;     // atom bitmaps per lane: the request being scanned + one awaiting its epilogue
 constexpr uint32_t kClaim = 32;     // requests a warp claims from the global counter at a time
 
+constexpr uint32_t kMaxConstNs = 16;
 constexpr uint32_t kMaxConstUnits = 24;  // rule sets with more scan units run on the lane path
 
 struct KParams {
@@ -77,6 +78,7 @@ struct KParams {
     // ---- copy of the first unit descriptors in the parameter (constant) bank: the field-scan kernel reads them with a
     //      warp-uniform index, which keeps the per-unit parameters out of the vector register file ----
     UnitDesc udesc[kMaxConstUnits];
+    NsAtom nsd[kMaxConstNs];    // likewise for the first non-scan atoms (read by every request's epilogue)
 };
 
 struct LaunchPlan {

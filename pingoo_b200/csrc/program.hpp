@@ -64,11 +64,7 @@ struct NsAtom {
     uint32_t op;       // CmpOp
     int64_t cval;
     uint32_t set_id;   // int set / ip set bit / country set
-    uint32_t end1_off;     // image offset of uint16 end1[s] for s < hot_states: end-of-field events of state s:
-                           // 0xFFFE none, an atom id for a single FIRE, 0xFFFF general list
-    uint32_t idle_state;   // most frequent state on neutral text: speculative start state of the stream scan
-    uint32_t has_latch;    // the unit has gap-split patterns (latch events must be applied in string order)
-    uint32_t pad2[2];
+    uint32_t pad;
 };
 
 struct LpmLeaf {
