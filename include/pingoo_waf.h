@@ -123,6 +123,12 @@ void* pgw_host_alloc(size_t bytes);
 void pgw_host_free(void* p);
 
 int pgw_ruleset_info(const pgw_ruleset* rs, pgw_info* out);
+/* Measurement hook (no reference counterpart): while enabled, every batch evaluated on the default kernel path is
+ * bracketed by CUDA events around its scan kernel, on the stream the kernel is launched on (a ring of 256 pairs).
+ * pgw_ruleset_profile synchronises those events and returns the summed scan-kernel time and the number of launches
+ * it covers (at most the 256 most recent), then clears the ring. */
+int pgw_ruleset_set_profiling(pgw_ruleset* rs, int enable);
+int pgw_ruleset_profile(pgw_ruleset* rs, double* scan_ms_sum, uint32_t* launches);
 /* Human-readable compile summary / warnings (e.g. a regex that does not compile => that rule never matches). */
 size_t pgw_ruleset_describe(const pgw_ruleset* rs, char* buf, size_t cap);
 void pgw_ruleset_destroy(pgw_ruleset* rs);

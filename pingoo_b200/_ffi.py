@@ -53,7 +53,8 @@ FLAG_CAPTCHA_VERIFIED, FLAG_PRE_BLOCK, FLAG_PRE_CAPTCHA, FLAG_BYPASS = 1, 2, 4, 
 EXPORTS = (
     "pgw_compile_expression", "pgw_validate_expression", "pgw_ruleset_create", "pgw_lists_add", "pgw_geoip_load",
     "pgw_ruleset_finalize", "pgw_evaluate_batch", "pgw_evaluate_batch_host", "pgw_geoip_lookup_batch",
-    "pgw_host_alloc", "pgw_host_free", "pgw_ruleset_info", "pgw_ruleset_describe", "pgw_ruleset_destroy", "pgw_last_error",
+    "pgw_host_alloc", "pgw_host_free", "pgw_ruleset_info", "pgw_ruleset_set_profiling", "pgw_ruleset_profile",
+    "pgw_ruleset_describe", "pgw_ruleset_destroy", "pgw_last_error",
 )
 
 _lib = None
@@ -75,6 +76,8 @@ def declare(lib, prefix="pgw_"):
         "host_alloc": (p, [C.c_size_t]),
         "host_free": (None, [p]),
         "ruleset_info": (C.c_int, [p, C.POINTER(Info)]),
+        "ruleset_set_profiling": (C.c_int, [p, C.c_int]),
+        "ruleset_profile": (C.c_int, [p, C.POINTER(C.c_double), C.POINTER(C.c_uint32)]),
         "ruleset_describe": (C.c_size_t, [p, C.c_char_p, C.c_size_t]),
         "ruleset_destroy": (None, [p]),
         "last_error": (C.c_char_p, []),

@@ -50,6 +50,7 @@ struct DevMem {
     }
 };
 
+constexpr uint32_t kProfRing = 256;
 constexpr uint32_t kHostSlices = 16;  // host-pointer path: copy/compute pipeline depth
 
 struct Staging {
@@ -95,6 +96,10 @@ struct pgw_ruleset {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t slice_ready[kHostSlices] = {};
     uint64_t last_h2d = 0, last_d2h = 0;
+    // measurement hook: event pairs around the scan kernel
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_ev;  // 2 * kProfRing events, created on first enable
+    std::atomic<uint64_t> prof_n{0};
 };
 
 extern "C" {
@@ -306,7 +311,13 @@ static int launch_on(const pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdic
         const size_t row_words = (size_t)b->n * P.atom_words;
         uint32_t* scratch = nullptr;
         if (cudaMallocAsync((void**)&scratch, (row_words + kFieldCounters) * 4, (cudaStream_t)stream) != cudaSuccess) { e = "CUDA: scratch allocation failed"; return 1; }
-        const char* m = waf_field_launch(P, scratch, scratch + row_words, rs->sm_count, rs->field_smem, stream);
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        if (rs->profiling) {
+            const uint64_t k = const_cast<pgw_ruleset*>(rs)->prof_n.fetch_add(1, std::memory_order_relaxed) % kProfRing;
+            ev0 = rs->prof_ev[2 * k];
+            ev1 = rs->prof_ev[2 * k + 1];
+        }
+        const char* m = waf_field_launch(P, scratch, scratch + row_words, rs->sm_count, rs->field_smem, stream, ev0, ev1);
         cudaFreeAsync(scratch, (cudaStream_t)stream);
         if (m) { e = std::string("CUDA launch failed: ") + m; return 1; }
         const_cast<pgw_ruleset*>(rs)->launches.fetch_add(1, std::memory_order_relaxed);  // two kernels per batch on this path
@@ -472,6 +483,38 @@ void pgw_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
+int pgw_ruleset_set_profiling(pgw_ruleset* rs, int enable) {
+    if (!rs || !rs->finalized) return fail("ruleset is not finalized", nullptr, 0);
+    cudaSetDevice(rs->device);
+    if (enable && rs->prof_ev.empty()) {
+        rs->prof_ev.resize(2 * kProfRing, nullptr);
+        for (auto& ev : rs->prof_ev)
+            if (cudaEventCreate(&ev) != cudaSuccess) return fail("CUDA: event creation failed", nullptr, 0);
+    }
+    rs->prof_n.store(0);
+    rs->profiling = enable != 0;
+    return 0;
+}
+
+int pgw_ruleset_profile(pgw_ruleset* rs, double* scan_ms_sum, uint32_t* launches) {
+    if (!rs || !scan_ms_sum || !launches) return fail("null argument", nullptr, 0);
+    *scan_ms_sum = 0.0;
+    *launches = 0;
+    if (rs->prof_ev.empty()) return 0;
+    cudaSetDevice(rs->device);
+    const uint64_t n = rs->prof_n.load();
+    const uint32_t have = (uint32_t)(n < kProfRing ? n : kProfRing);
+    for (uint32_t k = 0; k < have; ++k) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(rs->prof_ev[2 * k + 1]) != cudaSuccess || cudaEventElapsedTime(&ms, rs->prof_ev[2 * k], rs->prof_ev[2 * k + 1]) != cudaSuccess)
+            return fail("CUDA: profiling events are not complete", nullptr, 0);
+        *scan_ms_sum += ms;
+    }
+    *launches = have;
+    rs->prof_n.store(0);
+    return 0;
+}
+
 int pgw_ruleset_info(const pgw_ruleset* rs, pgw_info* out) {
     if (!rs || !out) return fail("null argument", nullptr, 0);
     memset(out, 0, sizeof *out);
@@ -523,6 +566,8 @@ void pgw_ruleset_destroy(pgw_ruleset* rs) {
     rs->stage_country.release(); rs->stage_flags.release(); rs->stage_verdict.release();
     if (rs->stream) cudaStreamDestroy(rs->stream);
     if (rs->copy_stream) cudaStreamDestroy(rs->copy_stream);
+    for (auto& ev : rs->prof_ev)
+        if (ev) cudaEventDestroy(ev);
     for (auto& ev : rs->slice_ready)
         if (ev) cudaEventDestroy(ev);
     delete rs;

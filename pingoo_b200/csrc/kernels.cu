@@ -1415,7 +1415,8 @@ size_t waf_field_smem_bytes(uint32_t image_bytes, uint32_t n_units) {
     return r16(image_bytes) + r16(n_units * (uint32_t)sizeof(UnitDesc)) + 64 + (kFsThreads / 32) * 2 * kFsPoolBytes + 3 * kFsSlotStride;
 }
 
-const char* waf_field_launch(const KParams& p, uint32_t* rows, uint32_t* counters, int sm_count, size_t smem_bytes, void* stream) {
+const char* waf_field_launch(const KParams& p, uint32_t* rows, uint32_t* counters, int sm_count, size_t smem_bytes, void* stream, cudaEvent_t ev0,
+                             cudaEvent_t ev1) {
     if (p.n == 0) return nullptr;
     if (p.n_units > kFieldCounters || p.n_units > kMaxConstUnits) return "too many scan units for the field-scan path";
     cudaStream_t s = (cudaStream_t)stream;
@@ -1425,7 +1426,9 @@ const char* waf_field_launch(const KParams& p, uint32_t* rows, uint32_t* counter
     if (p.n_units) {
         const uint32_t want = (p.n + kFsThreads - 1) / kFsThreads;
         const int grid = (int)(want < (uint32_t)sm_count ? want : (uint32_t)sm_count);
+        if (ev0) cudaEventRecord(ev0, s);
         waf_field_scan_kernel<<<grid, kFsThreads, smem_bytes, s>>>(p, rows, counters);
+        if (ev1) cudaEventRecord(ev1, s);
         e = cudaGetLastError();
         if (e != cudaSuccess) return cudaGetErrorString(e);
     }

@@ -70,6 +70,18 @@ class WafEngine:
         self._lib.pgw_ruleset_info(self._h, C.byref(i))
         return i
 
+    def set_profiling(self, enable: bool) -> None:
+        """Measurement hook: bracket every scan-kernel launch with CUDA events (see include/pingoo_waf.h)."""
+        if self._lib.pgw_ruleset_set_profiling(self._h, 1 if enable else 0) != 0:
+            raise Error(self._lib.pgw_last_error().decode(errors="replace"))
+
+    def profile(self) -> tuple[float, int]:
+        """(summed scan-kernel milliseconds, launches covered) since profiling was enabled / last read."""
+        ms, n = C.c_double(0.0), C.c_uint32(0)
+        if self._lib.pgw_ruleset_profile(self._h, C.byref(ms), C.byref(n)) != 0:
+            raise Error(self._lib.pgw_last_error().decode(errors="replace"))
+        return ms.value, n.value
+
     def describe(self) -> str:
         n = self._lib.pgw_ruleset_describe(self._h, None, 0)
         buf = C.create_string_buffer(n + 1)
