@@ -122,6 +122,24 @@ int pgw_geoip_lookup_batch(const pgw_ruleset* rs, const uint8_t* ip, const uint8
 void* pgw_host_alloc(size_t bytes);
 void pgw_host_free(void* p);
 
+/* ---- service routes, evaluated in the same pass -----------------------------------------------
+ * http_listener.rs:266-272 + HttpService::match_request (services/mod.rs:33-37, http_proxy_service.rs:84-95,
+ * http_static_site_service.rs:70-81): a request the rules let through is offered to the services in configuration
+ * order; a service takes it if it has no `route` or its route evaluates to Bool(true) (an error or a non-bool value
+ * is "no match"); if none does the listener answers 404.  A route is compiled like a rule expression
+ * (config_file.rs:257-265: a route that does not compile is a fatal configuration error).
+ * pgw_services_set is called between pgw_ruleset_create and pgw_ruleset_finalize.  The routed entry points
+ * additionally write, per request, the index of the service that takes it, or PGW_NO_SERVICE when none matches
+ * or when the verdict's action is not PGW_ALLOW (the reference never consults the services for those). */
+typedef struct pgw_service_desc {
+    const char* name;
+    const char* route; /* NULL: the service matches every request */
+} pgw_service_desc;
+#define PGW_NO_SERVICE 0xFFFFu
+int pgw_services_set(pgw_ruleset* rs, const pgw_service_desc* services, uint32_t n, char* err, size_t err_cap);
+int pgw_evaluate_batch_routed(const pgw_ruleset* rs, const pgw_batch* batch, uint32_t* verdict_dev, uint16_t* service_dev, void* stream);
+int pgw_evaluate_batch_routed_host(pgw_ruleset* rs, const pgw_batch* batch, uint32_t* verdict_host, uint16_t* service_host);
+
 int pgw_ruleset_info(const pgw_ruleset* rs, pgw_info* out);
 /* Measurement hook (no reference counterpart): while enabled, every batch evaluated on the default kernel path is
  * bracketed by CUDA events around its scan kernel, on the stream the kernel is launched on (a ring of 256 pairs).

@@ -42,6 +42,9 @@ struct orc_ruleset {
     bel_lists lists_view;
     int eval_gates;
     orc_mmdb* geo;
+    /* services (http_listener.rs:266-270): tried in order; route == NULL matches every request */
+    orc_rule* services;
+    uint32_t n_services;
 };
 
 static void set_err(char* err, size_t cap, const char* msg) {
@@ -89,6 +92,27 @@ orc_ruleset* orc_create(const pgw_rule_desc* rules, uint32_t n, int eval_gates, 
         }
     }
     return rs;
+}
+
+/* config_file.rs:257-265: a service's route is compiled with rules::compile_expression */
+int orc_services_set(orc_ruleset* rs, const pgw_service_desc* sv, uint32_t n, char* err, size_t cap) {
+    rs->services = (orc_rule*)calloc(n ? n : 1, sizeof(orc_rule));
+    rs->n_services = n;
+    for (uint32_t i = 0; i < n; ++i) {
+        orc_rule* r = &rs->services[i];
+        r->name = strdup(sv[i].name ? sv[i].name : "");
+        if (sv[i].route) {
+            char msg[200];
+            r->expr = bel_compile(sv[i].route, msg, sizeof msg);
+            if (!r->expr) {
+                char full[300];
+                snprintf(full, sizeof full, "error parsing route for service %s: %s", r->name, msg);
+                set_err(err, cap, full);
+                return 1;
+            }
+        }
+    }
+    return 0;
 }
 
 /* ---- lists (pingoo/lists.rs:62-113) ------------------------------------------------------ */
@@ -479,7 +503,8 @@ void orc_geoip_lookup(const orc_ruleset* rs, const uint8_t ip[16], int is_v6, ui
 }
 
 /* ---- request loop -------------------------------------------------------------------------- */
-static uint32_t verdict_for(const orc_ruleset* rs, const pgw_batch* b, uint32_t r) {
+static uint32_t verdict_for(const orc_ruleset* rs, const pgw_batch* b, uint32_t r, uint16_t* svc) {
+    if (svc) *svc = (uint16_t)PGW_NO_SERVICE;
     const pgw_strcol* cols[5] = {&b->host, &b->url, &b->path, &b->method, &b->user_agent};
     bel_ctx c;
     memset(&c, 0, sizeof c);
@@ -536,6 +561,13 @@ static uint32_t verdict_for(const orc_ruleset* rs, const pgw_batch* b, uint32_t 
             if (rule->actions[k] == PGW_ACTION_CAPTCHA && !captcha_verified) return PGW_CAPTCHA | (i << 2);
         }
     }
+    /* http_listener.rs:266-272 + HttpService::match_request (http_proxy_service.rs:84-95): first service whose route
+     * is absent or evaluates to true; none => 404 (PGW_NO_SERVICE) */
+    if (svc)
+        for (uint32_t i = 0; i < rs->n_services; ++i) {
+            const orc_rule* sv = &rs->services[i];
+            if (!sv->expr || bel_matches(sv->expr, &c)) { *svc = (uint16_t)i; break; }
+        }
     return PGW_ALLOW | (PGW_NO_RULE << 2);
 }
 
@@ -543,21 +575,26 @@ typedef struct {
     const orc_ruleset* rs;
     const pgw_batch* b;
     uint32_t* out;
+    uint16_t* svc;
     uint32_t lo, hi;
 } job;
 
 static void* worker(void* arg) {
     job* j = (job*)arg;
-    for (uint32_t r = j->lo; r < j->hi; ++r) j->out[r] = verdict_for(j->rs, j->b, r);
+    for (uint32_t r = j->lo; r < j->hi; ++r) j->out[r] = verdict_for(j->rs, j->b, r, j->svc ? j->svc + r : NULL);
     return NULL;
 }
 
 int orc_evaluate(const orc_ruleset* rs, const pgw_batch* batch, uint32_t* out, int n_threads) {
+    return orc_evaluate_routed(rs, batch, out, NULL, n_threads);
+}
+
+int orc_evaluate_routed(const orc_ruleset* rs, const pgw_batch* batch, uint32_t* out, uint16_t* svc, int n_threads) {
     uint32_t n = batch->n;
     if (n_threads < 1) n_threads = 1;
     if ((uint32_t)n_threads > n) n_threads = n ? (int)n : 1;
     if (n_threads == 1) {
-        job j = {rs, batch, out, 0, n};
+        job j = {rs, batch, out, svc, 0, n};
         worker(&j);
         return 0;
     }
@@ -567,6 +604,7 @@ int orc_evaluate(const orc_ruleset* rs, const pgw_batch* batch, uint32_t* out, i
         jobs[t].rs = rs;
         jobs[t].b = batch;
         jobs[t].out = out;
+        jobs[t].svc = svc;
         jobs[t].lo = (uint32_t)((uint64_t)n * (uint64_t)t / (uint64_t)n_threads);
         jobs[t].hi = (uint32_t)((uint64_t)n * (uint64_t)(t + 1) / (uint64_t)n_threads);
         pthread_create(&th[t], NULL, worker, &jobs[t]);
@@ -585,6 +623,11 @@ void orc_destroy(orc_ruleset* rs) {
         bel_free(rs->rules[i].expr);
     }
     free(rs->rules);
+    for (uint32_t i = 0; i < rs->n_services; ++i) {
+        free(rs->services[i].name);
+        bel_free(rs->services[i].expr);
+    }
+    free(rs->services);
     for (size_t i = 0; i < rs->n_lists; ++i) {
         bel_list* L = &rs->lists[i];
         if (L->strs) for (size_t k = 0; k < L->n; ++k) free(L->strs[k]);

@@ -2,4 +2,4 @@
 from . import _ffi  # noqa: F401
 from .batch import RequestBatch, country_code, pack_requests  # noqa: F401
 from .engine import WafEngine, decode_verdict  # noqa: F401
-from .rules import Action, Error, ExpressionIsNotValid, ListType, Rule, compile_expression, validate_expression  # noqa: F401
+from .rules import Action, Error, ExpressionIsNotValid, ListType, Rule, Service, compile_expression, validate_expression  # noqa: F401

@@ -15,6 +15,10 @@ class RuleDesc(C.Structure):
     _fields_ = [("name", C.c_char_p), ("expression", C.c_char_p), ("actions", C.POINTER(C.c_uint8)), ("n_actions", C.c_uint32)]
 
 
+class ServiceDesc(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("route", C.c_char_p)]
+
+
 class Options(C.Structure):
     _fields_ = [("max_dfa_states", C.c_int32), ("max_unit_table_bytes", C.c_uint64), ("eval_gates", C.c_int32)]
 
@@ -48,11 +52,13 @@ FIELDS = ("host", "url", "path", "method", "user_agent")
 ACTION_BLOCK, ACTION_CAPTCHA = 1, 2
 ALLOW, BLOCK, CAPTCHA, BYPASS = 0, 1, 2, 3
 NO_RULE = 0x3FFFFFFF
+NO_SERVICE = 0xFFFF
 FLAG_CAPTCHA_VERIFIED, FLAG_PRE_BLOCK, FLAG_PRE_CAPTCHA, FLAG_BYPASS = 1, 2, 4, 8
 
 EXPORTS = (
     "pgw_compile_expression", "pgw_validate_expression", "pgw_ruleset_create", "pgw_lists_add", "pgw_geoip_load",
     "pgw_ruleset_finalize", "pgw_evaluate_batch", "pgw_evaluate_batch_host", "pgw_geoip_lookup_batch",
+    "pgw_services_set", "pgw_evaluate_batch_routed", "pgw_evaluate_batch_routed_host",
     "pgw_host_alloc", "pgw_host_free", "pgw_ruleset_info", "pgw_ruleset_set_profiling", "pgw_ruleset_profile",
     "pgw_ruleset_describe", "pgw_ruleset_destroy", "pgw_last_error",
 )
@@ -72,6 +78,9 @@ def declare(lib, prefix="pgw_"):
         "ruleset_finalize": (C.c_int, [p, C.c_int, C.c_char_p, C.c_size_t]),
         "evaluate_batch": (C.c_int, [p, C.POINTER(Batch), p, p]),
         "evaluate_batch_host": (C.c_int, [p, C.POINTER(Batch), p]),
+        "services_set": (C.c_int, [p, C.POINTER(ServiceDesc), C.c_uint32, C.c_char_p, C.c_size_t]),
+        "evaluate_batch_routed": (C.c_int, [p, C.POINTER(Batch), p, p, p]),
+        "evaluate_batch_routed_host": (C.c_int, [p, C.POINTER(Batch), p, p]),
         "geoip_lookup_batch": (C.c_int, [p, p, p, C.c_uint32, p, p, p]),
         "host_alloc": (p, [C.c_size_t]),
         "host_free": (None, [p]),

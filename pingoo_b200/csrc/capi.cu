@@ -92,7 +92,7 @@ struct pgw_ruleset {
     size_t stream_smem = 0, field_smem = 0;
     std::atomic<uint64_t> launches{0};
     // host-pointer path
-    Staging stage_cols[5], stage_offs[5], stage_ip, stage_v6, stage_port, stage_asn, stage_country, stage_flags, stage_verdict;
+    Staging stage_cols[5], stage_offs[5], stage_ip, stage_v6, stage_port, stage_asn, stage_country, stage_flags, stage_verdict, stage_service;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t slice_ready[kHostSlices] = {};
     uint64_t last_h2d = 0, last_d2h = 0;
@@ -147,6 +147,16 @@ int pgw_lists_add(pgw_ruleset* rs, const char* name, int list_type, const uint8_
     if (!rs || !name) return fail("null argument", err, err_cap);
     std::string e;
     if (!rs->builder.add_list(name, list_type, csv, csv_len, e)) return fail(e, err, err_cap);
+    return 0;
+}
+
+int pgw_services_set(pgw_ruleset* rs, const pgw_service_desc* services, uint32_t n, char* err, size_t err_cap) {
+    if (!rs || (n && !services)) return fail("null argument", err, err_cap);
+    if (rs->finalized) return fail("ruleset already finalized", err, err_cap);
+    if (rs->builder.n_services()) return fail("services are already set", err, err_cap);
+    std::string e;
+    for (uint32_t i = 0; i < n; ++i)
+        if (!rs->builder.add_service(services[i].name, services[i].route, e)) return fail(e, err, err_cap);
     return 0;
 }
 
@@ -222,6 +232,11 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     P.rule_off = (const uint32_t*)chk(M.upload(H.rule_off));
     P.term = (const uint8_t*)chk(M.upload(H.term));
     P.n_rules = H.n_rules;
+    P.n_waf_rules = H.n_waf_rules;
+    P.s0 = H.s0;
+    P.dflt_services = (const uint32_t*)chk(M.upload(H.dflt_services));
+    P.n_dflt_services = (uint32_t)H.dflt_services.size();
+    P.service = nullptr;
     P.ar_idx = (const uint32_t*)chk(M.upload(H.ar_idx));
     P.ar_rules = (const uint32_t*)chk(M.upload(H.ar_rules));
     for (int cv = 0; cv < 2; ++cv) {
@@ -280,7 +295,7 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     return 0;
 }
 
-static int launch_on(const pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdict_out, void* stream, std::string& e) {
+static int launch_on(const pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdict_out, void* stream, std::string& e, uint16_t* service_out = nullptr) {
     const HostProgram& H = rs->prog;
     KParams P = rs->base;
     const pgw_strcol* cols[5] = {&b->host, &b->url, &b->path, &b->method, &b->user_agent};
@@ -302,6 +317,7 @@ static int launch_on(const pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdic
     if (P.need_lpm && (!b->ip || !b->ip_is_v6)) { e = "batch is missing client.ip columns"; return 1; }
     if (H.needs_port && !b->remote_port) { e = "batch is missing client.remote_port"; return 1; }
     P.verdict = verdict_out;
+    P.service = service_out;
     P.n = b->n;
     if (b->n == 0) return 0;
     // each in-flight launch gets its own work counter (ring of 64), so concurrent callers do not interfere
@@ -343,6 +359,10 @@ static int launch_on(const pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdic
 }
 
 int pgw_evaluate_batch(const pgw_ruleset* rs, const pgw_batch* batch, uint32_t* verdict_out, void* stream) {
+    return pgw_evaluate_batch_routed(rs, batch, verdict_out, nullptr, stream);
+}
+
+int pgw_evaluate_batch_routed(const pgw_ruleset* rs, const pgw_batch* batch, uint32_t* verdict_out, uint16_t* service_out, void* stream) {
     if (!rs || !batch) return fail("null argument", nullptr, 0);
     if (!rs->finalized) return fail("ruleset is not finalized", nullptr, 0);
     if (batch->n && !verdict_out) return fail("verdict_out is null", nullptr, 0);
@@ -350,13 +370,17 @@ int pgw_evaluate_batch(const pgw_ruleset* rs, const pgw_batch* batch, uint32_t* 
     cudaGetDevice(&cur);
     if (cur != rs->device) cudaSetDevice(rs->device);
     std::string e;
-    int rc = launch_on(rs, batch, verdict_out, stream, e);
+    int rc = launch_on(rs, batch, verdict_out, stream, e, service_out);
     if (cur != rs->device && cur >= 0) cudaSetDevice(cur);
     if (rc) return fail(e, nullptr, 0);
     return 0;
 }
 
 int pgw_evaluate_batch_host(pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdict_out) {
+    return pgw_evaluate_batch_routed_host(rs, b, verdict_out, nullptr);
+}
+
+int pgw_evaluate_batch_routed_host(pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdict_out, uint16_t* service_out) {
     if (!rs || !b) return fail("null argument", nullptr, 0);
     if (!rs->finalized) return fail("ruleset is not finalized", nullptr, 0);
     if (b->n == 0) return 0;
@@ -406,7 +430,7 @@ int pgw_evaluate_batch_host(pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdi
         ok = ok && rs->stage_flags.ensure(n);
         d.flags = (const uint8_t*)rs->stage_flags.d;
     }
-    ok = ok && rs->stage_verdict.ensure((size_t)n * 4);
+    ok = ok && rs->stage_verdict.ensure((size_t)n * 4) && (!service_out || rs->stage_service.ensure((size_t)n * 2));
     if (!ok) return fail("CUDA: staging allocation failed", nullptr, 0);
 
     // The batch is cut into slices of whole requests: slice k is copied on the copy stream while slice k-1 is evaluated
@@ -452,14 +476,16 @@ int pgw_evaluate_batch_host(pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdi
         if (v.asn) { v.asn += a; v.country += a; }
         if (v.flags) v.flags += a;
         uint32_t* vd = (uint32_t*)rs->stage_verdict.d + a;
-        if (launch_on(rs, &v, vd, s, e)) { cudaStreamSynchronize(cs); cudaStreamSynchronize(s); return fail(e, nullptr, 0); }
+        uint16_t* sd = service_out ? (uint16_t*)rs->stage_service.d + a : nullptr;
+        if (launch_on(rs, &v, vd, s, e, sd)) { cudaStreamSynchronize(cs); cudaStreamSynchronize(s); return fail(e, nullptr, 0); }
         if ((ce = cudaMemcpyAsync(verdict_out + a, vd, (size_t)m * 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
+        if (sd && (ce = cudaMemcpyAsync(service_out + a, sd, (size_t)m * 2, cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
     }
     cudaError_t c1 = cudaStreamSynchronize(cs), c2 = cudaStreamSynchronize(s);
     if (ce == cudaSuccess) ce = c1 != cudaSuccess ? c1 : c2;
     if (ce != cudaSuccess) return fail(std::string("CUDA: ") + cudaGetErrorString(ce), nullptr, 0);
     rs->last_h2d = h2d;
-    rs->last_d2h = (uint64_t)n * 4;
+    rs->last_d2h = (uint64_t)n * (service_out ? 6 : 4);
     return 0;
 }
 
@@ -563,7 +589,7 @@ void pgw_ruleset_destroy(pgw_ruleset* rs) {
     rs->mem.release();
     for (int f = 0; f < 5; ++f) { rs->stage_cols[f].release(); rs->stage_offs[f].release(); }
     rs->stage_ip.release(); rs->stage_v6.release(); rs->stage_port.release(); rs->stage_asn.release();
-    rs->stage_country.release(); rs->stage_flags.release(); rs->stage_verdict.release();
+    rs->stage_country.release(); rs->stage_flags.release(); rs->stage_verdict.release(); rs->stage_service.release();
     if (rs->stream) cudaStreamDestroy(rs->stream);
     if (rs->copy_stream) cudaStreamDestroy(rs->copy_stream);
     for (auto& ev : rs->prof_ev)

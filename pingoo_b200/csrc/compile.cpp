@@ -79,6 +79,11 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
     H.eval_gates = opt.eval_gates;
     H.warnings = M.warnings;
     H.n_rules = (uint32_t)M.rules.size();
+    H.n_waf_rules = M.n_waf_rules <= M.rules.size() ? M.n_waf_rules : (uint32_t)M.rules.size();
+    if (H.n_rules - H.n_waf_rules >= 0xFFFFu) {
+        err = "too many services";
+        return false;
+    }
 
     // ---- internal gate atom: path.starts_with("/__pingoo/captcha") (http_listener.rs:200-204)
     if (opt.eval_gates) {
@@ -225,7 +230,18 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
         H.code.insert(H.code.end(), code.begin(), code.end());
         H.rule_off.push_back((uint32_t)H.code.size());
         uint8_t t0 = terminal_for(M.rules[r].actions, false), t1 = terminal_for(M.rules[r].actions, true);
+        if (M.rules[r].is_service) t0 = t1 = 0;
         H.term.push_back((uint8_t)(t0 | (t1 << 2)));
+    }
+    // services: first route that is true under the expected atom values, and every route that is (candidates when
+    // some atom deviates)
+    H.s0 = 0xFFFFu;
+    H.dflt_services.clear();
+    for (size_t r = H.n_waf_rules; r < M.rules.size(); ++r) {
+        if (!M.pool.eval(M.rules[r].formula, expect_vals)) continue;
+        H.dflt_services.push_back((uint32_t)r);
+        if (H.s0 == 0xFFFFu) H.s0 = (uint32_t)(r - H.n_waf_rules);
+        if (M.pool.is_const(M.rules[r].formula)) break;  // a route-less service shadows everything after it
     }
     for (int cv = 0; cv < 2; ++cv) {
         H.v0[cv] = V_ALLOW | (kNoRule << 2);

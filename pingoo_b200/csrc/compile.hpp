@@ -42,6 +42,10 @@ struct HostProgram {
     std::vector<uint32_t> ar_idx, ar_rules;  // atom -> rules CSR
     std::vector<uint32_t> dflt_rules[2];     // rules true under `expect` with a terminal action, per captcha_verified
     uint32_t v0[2] = {0, 0};                 // verdict when every cared atom has its expected value
+    // service routes: rules [n_waf_rules, n_rules) of the same program (term = 0: the verdict loop skips them)
+    uint32_t n_waf_rules = 0;
+    std::vector<uint32_t> dflt_services;     // routes true under `expect` (rule indices)
+    uint32_t s0 = 0xFFFFu;                   // service when every cared atom has its expected value
     std::vector<int64_t> iset_vals;
     std::vector<uint32_t> iset_off;
     std::vector<uint32_t> cset_words;

@@ -277,6 +277,41 @@ __device__ __noinline__ void request_epilogue(const KParams& p, uint32_t r, uint
         }
     }
     p.verdict[r] = verdict;
+    if (p.service) {
+        // http_listener.rs:266-272: only a request the rules let through reaches the services; the first service whose
+        // route is absent or true takes it, none => 404 (kNoService)
+        uint32_t svc = kNoService;
+        if ((verdict & 3u) == V_ALLOW && p.n_rules > p.n_waf_rules) {
+            uint32_t diff = 0;
+            for (uint32_t w = 0; w < Aw; ++w) diff |= (row[w * stride] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
+            if (diff == 0) svc = p.s0;
+            else {
+                uint32_t best = kNoRule;
+                for (uint32_t w = 0; w < Aw; ++w) {
+                    uint32_t x = (row[w * stride] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
+                    while (x) {
+                        uint32_t b = __ffs(x) - 1;
+                        x &= x - 1;
+                        uint32_t atom = w * 32 + b;
+                        uint32_t i0 = __ldg(p.ar_idx + atom), i1 = __ldg(p.ar_idx + atom + 1);
+                        for (uint32_t i = i0; i < i1; ++i) {
+                            uint32_t rule = __ldg(p.ar_rules + i);
+                            if (rule >= best) break;  // lists are ascending
+                            if (rule < p.n_waf_rules) continue;
+                            if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row, stride)) best = rule;
+                        }
+                    }
+                }
+                for (uint32_t i = 0; i < p.n_dflt_services; ++i) {
+                    uint32_t rule = __ldg(p.dflt_services + i);
+                    if (rule >= best) break;
+                    if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row, stride)) best = rule;
+                }
+                if (best != kNoRule) svc = best - p.n_waf_rules;
+            }
+        }
+        p.service[r] = (uint16_t)svc;
+    }
 }
 
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {

@@ -58,6 +58,12 @@ struct KParams {
     const uint32_t* dflt[2];
     uint32_t n_dflt[2];
     uint32_t v0[2];
+    // service routes (rules [n_waf_rules, n_rules)); `service` null: not requested for this batch
+    uint32_t n_waf_rules;
+    uint32_t s0;
+    const uint32_t* dflt_services;
+    uint32_t n_dflt_services;
+    uint16_t* service;
     const int64_t* iset_vals;
     const uint32_t* iset_off;
     const uint32_t* cset;

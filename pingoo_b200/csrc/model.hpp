@@ -106,6 +106,7 @@ struct RuleModel {
     std::string name;
     bool has_expression = false;
     int formula = 1;                 // BoolPool node: "expression evaluates to Bool(true)"
+    bool is_service = false;         // a service route (HttpService::match_request), not a WAF rule
     std::vector<uint8_t> actions;    // ActionCode sequence, reference order
 };
 
@@ -123,7 +124,8 @@ struct Model {
     std::vector<std::vector<int64_t>> int_sets;
     std::vector<std::vector<IpNet>> ip_sets;
     std::vector<std::bitset<676>> country_sets;
-    std::vector<RuleModel> rules;
+    std::vector<RuleModel> rules;    // WAF rules first, then service routes
+    uint32_t n_waf_rules = 0xFFFFFFFFu;  // unset: every rule is a WAF rule
     std::map<std::string, ListData> lists;
     std::vector<std::string> warnings;  // e.g. invalid regex folded to runtime error
 };

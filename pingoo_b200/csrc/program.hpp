@@ -5,6 +5,7 @@
 
 namespace pgw {
 
+constexpr uint32_t kNoService = 0xFFFFu;             // service index when no service takes the request
 constexpr uint32_t kNoRule = 0x3FFFFFFFu;          // verdict rule index when no rule decided
 constexpr uint32_t kMaxStackDepth = 32;            // rule bytecode evaluation stack (one 32-bit register)
 constexpr uint32_t kCountryWords = 22;             // ceil(676 / 32)

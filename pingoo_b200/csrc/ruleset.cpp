@@ -55,6 +55,23 @@ bool RulesetBuilder::add_rule(const char* name, const char* expression, const ui
     return true;
 }
 
+bool RulesetBuilder::add_service(const char* name, const char* route, std::string& err) {
+    if (finalized_) { err = "ruleset already finalized"; return false; }
+    RuleSource r;
+    r.name = name ? name : "";
+    if (route) {
+        r.has_expression = true;
+        r.expression = route;
+        std::string cerr;
+        if (!compile_expression(r.expression, cerr, &r.ast)) {
+            err = "error parsing route for service " + r.name + ": " + cerr;
+            return false;
+        }
+    }
+    services_.push_back(std::move(r));
+    return true;
+}
+
 bool RulesetBuilder::add_list(const char* name, int type, const uint8_t* csv, size_t len, std::string& err) {
     if (finalized_) { err = "ruleset already finalized"; return false; }
     if (type < 0 || type > 2) { err = std::to_string(type) + " is not a valid ListType"; return false; }
@@ -80,6 +97,17 @@ bool RulesetBuilder::finalize(HostProgram* out, std::string& err) {
             rm.has_expression = r.has_expression;
             rm.actions = r.actions;
             // pingoo/rules.rs:36-52: no expression => the rule matches every request
+            rm.formula = r.has_expression ? lower_rule_expression(model_, *r.ast, r.name) : model_.pool.constant(true);
+            model_.rules.push_back(std::move(rm));
+        }
+        // service routes ride in the same program after the WAF rules: same atoms, same scan, no actions
+        model_.n_waf_rules = (uint32_t)model_.rules.size();
+        for (auto& r : services_) {
+            RuleModel rm;
+            rm.name = r.name;
+            rm.has_expression = r.has_expression;
+            rm.is_service = true;
+            // http_proxy_service.rs:84-95: no route => the service matches every request
             rm.formula = r.has_expression ? lower_rule_expression(model_, *r.ast, r.name) : model_.pool.constant(true);
             model_.rules.push_back(std::move(rm));
         }

@@ -28,14 +28,19 @@ class RulesetBuilder {
 
     // config.rs:255-269: a rule whose expression does not compile is a fatal configuration error
     bool add_rule(const char* name, const char* expression, const uint8_t* actions, uint32_t n_actions, std::string& err);
+    // config_file.rs:257-265: a service's `route` is compiled like a rule expression (a failure is a fatal config error);
+    // services are tried in order (http_listener.rs:266-270)
+    bool add_service(const char* name, const char* route, std::string& err);
     bool add_list(const char* name, int type, const uint8_t* csv, size_t len, std::string& err);
     bool load_geoip(const uint8_t* mmdb, size_t len, std::string& err);
     bool finalize(HostProgram* out, std::string& err);
 
     size_t n_rules() const { return rules_.size(); }
+    size_t n_services() const { return services_.size(); }
 
   private:
     std::vector<RuleSource> rules_;
+    std::vector<RuleSource> services_;
     Model model_;
     std::vector<uint8_t> mmdb_;
     bool finalized_ = false;

@@ -14,13 +14,13 @@ import numpy as np
 
 from . import _ffi
 from .batch import FIELDS, RequestBatch
-from .rules import Error, ListType, Rule
+from .rules import Error, ListType, Rule, Service
 
 
 class WafEngine:
     def __init__(self, rules: Iterable[Rule], lists: Optional[Dict[str, Tuple[ListType, bytes]]] = None,
                  geoip_mmdb: Optional[bytes] = None, device: int = 0, eval_gates: bool = True,
-                 max_dfa_states: int = 0, max_unit_table_bytes: int = 0):
+                 max_dfa_states: int = 0, max_unit_table_bytes: int = 0, services: Optional[Iterable[Service]] = None):
         self._lib = _ffi.load()
         self._h = C.c_void_p()
         self.rules = list(rules)
@@ -44,6 +44,17 @@ class WafEngine:
                 raise Error(msg)
         if geoip_mmdb is not None:
             if self._lib.pgw_geoip_load(self._h, geoip_mmdb, len(geoip_mmdb), err, len(err)):
+                msg = err.value.decode(errors="replace")
+                self.close()
+                raise Error(msg)
+        self.services = list(services or [])
+        if self.services:
+            # http_listener.rs:266-270: services are tried in configuration order
+            sd = (_ffi.ServiceDesc * len(self.services))()
+            for i, sv in enumerate(self.services):
+                sd[i].name = sv.name.encode()
+                sd[i].route = None if sv.route is None else sv.route.encode()
+            if self._lib.pgw_services_set(self._h, sd, len(self.services), err, len(err)):
                 msg = err.value.decode(errors="replace")
                 self.close()
                 raise Error(msg)
@@ -97,6 +108,15 @@ class WafEngine:
             raise Error(self._lib.pgw_last_error().decode(errors="replace"))
         return out
 
+    def evaluate_host_routed(self, batch: RequestBatch):
+        """Verdicts plus, for allowed requests, the index of the first matching service (NO_SERVICE = 404)."""
+        out = np.empty(batch.n, dtype=np.uint32)
+        svc = np.empty(batch.n, dtype=np.uint16)
+        cb = batch.as_ctypes()
+        if self._lib.pgw_evaluate_batch_routed_host(self._h, C.byref(cb), out.ctypes.data, svc.ctypes.data):
+            raise Error(self._lib.pgw_last_error().decode(errors="replace"))
+        return out, svc
+
     def to_device(self, batch: RequestBatch):
         """Copy a host batch into torch CUDA tensors; returns (tensors, pgw_batch of device pointers)."""
         import torch
@@ -125,6 +145,11 @@ class WafEngine:
     def evaluate_device(self, cbatch: _ffi.Batch, verdict_tensor, stream: int = 0):
         """Enqueue the kernel on `stream` (cudaStream_t handle) for device-resident columns."""
         if self._lib.pgw_evaluate_batch(self._h, C.byref(cbatch), verdict_tensor.data_ptr(), stream):
+            raise Error(self._lib.pgw_last_error().decode(errors="replace"))
+
+    def evaluate_device_routed(self, cbatch: _ffi.Batch, verdict_tensor, service_tensor, stream: int = 0):
+        """Like evaluate_device, also writing the uint16 service index per request (int16 tensor of n elements)."""
+        if self._lib.pgw_evaluate_batch_routed(self._h, C.byref(cbatch), verdict_tensor.data_ptr(), service_tensor.data_ptr(), stream):
             raise Error(self._lib.pgw_last_error().decode(errors="replace"))
 
     def geoip_lookup_device(self, ip_t, v6_t, asn_t, cc_t, stream: int = 0):

@@ -80,3 +80,17 @@ class Rule:
     def from_config(cls, name, cfg):
         """RuleConfigFile {expression?, actions} (pingoo/config/config_file.rs:97-101)."""
         return cls(name=name, expression=cfg.get("expression"), actions=[Action.from_config(a) for a in cfg.get("actions", [])])
+
+
+@dataclass
+class Service:
+    """The routing view of an HTTP service: `HttpService::match_request` (pingoo/services/mod.rs:33-37,
+    http_proxy_service.rs:84-95, http_static_site_service.rs:70-81). `route=None` matches every request."""
+
+    name: str
+    route: Optional[str] = None
+
+    @classmethod
+    def from_config(cls, name, cfg):
+        """ServiceConfigFile {route?, ...} (pingoo/config/config_file.rs:257-265): only the route matters here."""
+        return cls(name=name, route=cfg.get("route"))

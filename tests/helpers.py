@@ -48,6 +48,8 @@ def oracle_lib():
         lib.orc_lists_add.argtypes = [p, C.c_char_p, C.c_int, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
         lib.orc_geoip_load.argtypes = [p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
         lib.orc_evaluate.argtypes = [p, C.POINTER(_ffi.Batch), p, C.c_int]
+        lib.orc_services_set.argtypes = [p, C.POINTER(_ffi.ServiceDesc), C.c_uint32, C.c_char_p, C.c_size_t]
+        lib.orc_evaluate_routed.argtypes = [p, C.POINTER(_ffi.Batch), p, p, C.c_int]
         lib.orc_geoip_lookup.argtypes = [p, C.c_char_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint16)]
         lib.orc_geoip_lookup.restype = None
         lib.orc_destroy.argtypes = [p]
@@ -61,10 +63,19 @@ def oracle_lib():
     return _oracle
 
 
+def _svc_descs(services):
+    services = list(services or [])
+    sd = (_ffi.ServiceDesc * max(1, len(services)))()
+    for i, sv in enumerate(services):
+        sd[i].name = sv.name.encode()
+        sd[i].route = None if sv.route is None else sv.route.encode()
+    return sd, len(services)
+
+
 class Oracle:
     """CPU restatement of the reference path (the checker)."""
 
-    def __init__(self, rules, lists=None, geoip_mmdb=None, eval_gates=True):
+    def __init__(self, rules, lists=None, geoip_mmdb=None, eval_gates=True, services=None):
         self.lib = oracle_lib()
         descs, keep, n = _descs(rules)
         err = C.create_string_buffer(1024)
@@ -77,12 +88,23 @@ class Oracle:
         if geoip_mmdb is not None:
             if self.lib.orc_geoip_load(self.h, geoip_mmdb, len(geoip_mmdb), err, len(err)):
                 raise ValueError(err.value.decode(errors="replace"))
+        if services:
+            sd, ns = _svc_descs(services)
+            if self.lib.orc_services_set(self.h, sd, ns, err, len(err)):
+                raise ValueError(err.value.decode(errors="replace"))
 
     def evaluate(self, batch: RequestBatch, threads=1) -> np.ndarray:
         out = np.empty(batch.n, dtype=np.uint32)
         cb = batch.as_ctypes()
         self.lib.orc_evaluate(self.h, C.byref(cb), out.ctypes.data, threads)
         return out
+
+    def evaluate_routed(self, batch: RequestBatch, threads=1):
+        out = np.empty(batch.n, dtype=np.uint32)
+        svc = np.empty(batch.n, dtype=np.uint16)
+        cb = batch.as_ctypes()
+        self.lib.orc_evaluate_routed(self.h, C.byref(cb), out.ctypes.data, svc.ctypes.data, threads)
+        return out, svc
 
     def geoip_lookup(self, ip16: bytes, is_v6: int):
         a = C.c_uint32()
@@ -115,6 +137,8 @@ def sim_lib():
         lib.pgwsim_describe.restype = C.c_size_t
         lib.pgwsim_describe.argtypes = [p, C.c_char_p, C.c_size_t]
         lib.pgwsim_evaluate.argtypes = [p, C.POINTER(_ffi.Batch), p]
+        lib.pgwsim_services_set.argtypes = [p, C.POINTER(_ffi.ServiceDesc), C.c_uint32, C.c_char_p, C.c_size_t]
+        lib.pgwsim_evaluate_routed.argtypes = [p, C.POINTER(_ffi.Batch), p, p]
         lib.pgwsim_geoip_lookup.argtypes = [p, p, p, C.c_uint32, p, p]
         lib.pgwsim_destroy.argtypes = [p]
         lib.pgwsim_destroy.restype = None
@@ -125,7 +149,7 @@ def sim_lib():
 class Sim:
     """CPU walk over the tables the product compiler emits (compiler check without a GPU)."""
 
-    def __init__(self, rules, lists=None, geoip_mmdb=None, eval_gates=True, max_dfa_states=0, max_unit_table_bytes=0):
+    def __init__(self, rules, lists=None, geoip_mmdb=None, eval_gates=True, max_dfa_states=0, max_unit_table_bytes=0, services=None):
         self.lib = sim_lib()
         descs, keep, n = _descs(rules)
         err = C.create_string_buffer(2048)
@@ -138,6 +162,10 @@ class Sim:
                 raise ValueError(err.value.decode(errors="replace"))
         if geoip_mmdb is not None:
             if self.lib.pgwsim_geoip_load(self.h, geoip_mmdb, len(geoip_mmdb), err, len(err)):
+                raise ValueError(err.value.decode(errors="replace"))
+        if services:
+            sd, ns = _svc_descs(services)
+            if self.lib.pgwsim_services_set(self.h, sd, ns, err, len(err)):
                 raise ValueError(err.value.decode(errors="replace"))
         if self.lib.pgwsim_finalize(self.h, err, len(err)):
             raise ValueError(err.value.decode(errors="replace"))
@@ -154,6 +182,14 @@ class Sim:
         if self.lib.pgwsim_evaluate(self.h, C.byref(cb), out.ctypes.data):
             raise RuntimeError("sim evaluate failed")
         return out
+
+    def evaluate_routed(self, batch: RequestBatch):
+        out = np.empty(batch.n, dtype=np.uint32)
+        svc = np.empty(batch.n, dtype=np.uint16)
+        cb = batch.as_ctypes()
+        if self.lib.pgwsim_evaluate_routed(self.h, C.byref(cb), out.ctypes.data, svc.ctypes.data):
+            raise RuntimeError("sim evaluate failed")
+        return out, svc
 
     def geoip_lookup(self, ip: np.ndarray, v6: np.ndarray):
         n = len(v6)

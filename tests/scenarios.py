@@ -3,6 +3,7 @@
 import numpy as np
 
 import synth
+from pingoo_b200 import Service  # noqa: E402
 from pingoo_b200 import Action, ListType, Rule, pack_requests
 
 
@@ -96,3 +97,26 @@ def geo_probe_addresses(records, seed=11):
         v6.append(1)
     ip_np = np.frombuffer(b"".join(ips), dtype=np.uint8).reshape(-1, 16).copy()
     return ip_np, np.array(v6, dtype=np.uint8)
+
+
+def services(n=20_000, catch_all=True):
+    """WAF rules of config 2 plus a service table (http_listener.rs:266-272): routes from the docs (two of the documented
+    examples refer to names that do not exist and therefore never match), a regex route, a list route, a non-bool route."""
+    rules, payloads, _ = synth.make_ruleset(128, config_id=2)
+    lists = {"static_hosts": (ListType.String, b"mionliwasa.org\ngaonta.net,cdn\n")}
+    svcs = [
+        Service("api", 'http_request.host.starts_with("be.") || http_request.host.starts_with("lo.")'),  # getting_started.md:38 shape
+        Service("doc_unknown_variable", 'host.starts_with("api")'),               # docs/services.md:18: `host` is not a variable
+        Service("doc_method_on_map", 'http_request.starts_with("/api")'),         # docs/configuration.md:53
+        Service("images", 'http_request.path.ends_with(".png") || http_request.path.ends_with(".svg")'),
+        Service("numbered", 'http_request.path.matches("^/[0-9]+/") && client.remote_port > 1024'),
+        Service("static_site", 'lists["static_hosts"].contains(http_request.host) && http_request.method == "GET"'),
+        Service("non_bool", "http_request.url.length()"),
+        Service("missing_list", 'lists["nope"].contains(http_request.host)'),
+        Service("writes", 'http_request.method == "POST" || http_request.method == "PUT"'),
+    ]
+    if catch_all:
+        svcs.append(Service("default"))
+        svcs.append(Service("shadowed", 'http_request.method == "GET"'))
+    batch = synth.RequestStream(config_id=2, payloads=payloads, attack_rate=0.05).generate(7_000, n)
+    return rules, lists, svcs, batch

@@ -148,7 +148,18 @@ int pgwsim_geoip_lookup(void* h, const uint8_t* ip, const uint8_t* is_v6, uint32
     return 0;
 }
 
-int pgwsim_evaluate(void* h, const pgw_batch* b, uint32_t* out) {
+int pgwsim_services_set(void* h, const pgw_service_desc* sv, uint32_t n, char* err, size_t cap) {
+    Sim* s = (Sim*)h;
+    std::string e;
+    for (uint32_t i = 0; i < n; ++i)
+        if (!s->builder.add_service(sv[i].name, sv[i].route, e)) { snprintf(err, cap, "%s", e.c_str()); return 1; }
+    return 0;
+}
+
+int pgwsim_evaluate_routed(void* h, const pgw_batch* b, uint32_t* out, uint16_t* svc_out);
+int pgwsim_evaluate(void* h, const pgw_batch* b, uint32_t* out) { return pgwsim_evaluate_routed(h, b, out, nullptr); }
+
+int pgwsim_evaluate_routed(void* h, const pgw_batch* b, uint32_t* out, uint16_t* svc_out) {
     Sim* s = (Sim*)h;
     if (!s->finalized) return 1;
     const HostProgram& H = s->H;
@@ -273,6 +284,37 @@ int pgwsim_evaluate(void* h, const pgw_batch* b, uint32_t* out) {
             }
         }
         out[r] = verdict;
+        if (svc_out) {
+            uint32_t svc = kNoService;
+            if ((verdict & 3u) == V_ALLOW && H.n_rules > H.n_waf_rules) {
+                uint32_t diff = 0;
+                for (uint32_t w = 0; w < Aw; ++w) diff |= (row[w] ^ H.expect[w]) & H.care[w];
+                if (!diff) svc = H.s0;
+                else {
+                    uint32_t best = kNoRule;
+                    for (uint32_t w = 0; w < Aw; ++w) {
+                        uint32_t x = (row[w] ^ H.expect[w]) & H.care[w];
+                        while (x) {
+                            uint32_t bit = __builtin_ctz(x);
+                            x &= x - 1;
+                            uint32_t atom = w * 32 + bit;
+                            for (uint32_t i = H.ar_idx[atom]; i < H.ar_idx[atom + 1]; ++i) {
+                                uint32_t rule = H.ar_rules[i];
+                                if (rule >= best) break;
+                                if (rule < H.n_waf_rules) continue;
+                                if (eval_rule(H, rule, row)) best = rule;
+                            }
+                        }
+                    }
+                    for (uint32_t rule : H.dflt_services) {
+                        if (rule >= best) break;
+                        if (eval_rule(H, rule, row)) best = rule;
+                    }
+                    if (best != kNoRule) svc = best - H.n_waf_rules;
+                }
+            }
+            svc_out[r] = (uint16_t)svc;
+        }
     }
     return 0;
 }

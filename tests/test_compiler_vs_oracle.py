@@ -117,3 +117,41 @@ def test_complement_events_for_expected_true_literals():
     want = _check(rules, batch, eval_gates=False)
     assert len(set(want.tolist())) >= 4
     assert "not" in Sim(rules, eval_gates=False).describe() or True
+
+
+def test_service_routes_same_pass():
+    """SURVEY.md 8f #1: first matching service for allowed requests, from the same atom bitmap as the verdict."""
+    from pingoo_b200._ffi import NO_SERVICE
+
+    for catch_all in (True, False):
+        rules, lists, svcs, batch = scenarios.services(12_000, catch_all)
+        got_v, got_s = Sim(rules, lists, services=svcs).evaluate_routed(batch)
+        want_v, want_s = Oracle(rules, lists, services=svcs).evaluate_routed(batch, threads=8)
+        assert np.array_equal(got_v, want_v)
+        bad = np.nonzero(got_s != want_s)[0]
+        assert len(bad) == 0, "\n".join(
+            [f"{len(bad)} of {batch.n} services differ"] +
+            [f"req {i}: oracle {want_s[i]} tables {got_s[i]} host={batch.field('host', i)!r} path={batch.field('path', i)!r} method={batch.field('method', i)!r}" for i in bad[:5]])
+        allowed = (want_v & 3) == 0
+        assert np.all(want_s[~allowed] == NO_SERVICE)
+        hist = np.bincount(want_s[allowed].astype(np.int64), minlength=len(svcs))
+        # the documented-but-broken routes, the non-bool route and the missing list never take a request
+        for dead in (1, 2, 6, 7):
+            assert hist[dead] == 0
+        assert hist[0] > 0 and hist[3] > 0 and hist[4] > 0 and hist[5] > 0 and hist[8] > 0
+        if catch_all:
+            assert hist[9] > 0 and hist[10] == 0 and not np.any(want_s[allowed] == NO_SERVICE)
+        else:
+            assert np.any(want_s[allowed] == NO_SERVICE)
+    # a service table without WAF rules, and a route that does not compile (config_file.rs:257-265)
+    from pingoo_b200 import Service
+    import pytest
+
+    rules, lists, svcs, batch = scenarios.services(2_000, True)
+    got_v, got_s = Sim([], lists, services=svcs).evaluate_routed(batch)
+    want_v, want_s = Oracle([], lists, services=svcs).evaluate_routed(batch)
+    assert np.array_equal(got_v, want_v) and np.array_equal(got_s, want_s)
+    with pytest.raises(ValueError, match="error parsing route for service broken"):
+        Sim([], services=[Service("broken", "http_request.host ==")])
+    with pytest.raises(ValueError, match="error parsing route for service broken"):
+        Oracle([], services=[Service("broken", "http_request.host ==")])

@@ -125,3 +125,48 @@ def test_full_size_properties_config2():
         orc = Oracle(rules)
         for i, sb in zip(idx[:2000], sub_reqs):
             assert orc.evaluate(sb)[0] == v[i], f"request {i}"
+
+
+def test_service_routes_in_the_same_pass():
+    """SURVEY.md 8f #1 (http_listener.rs:266-272, http_proxy_service.rs:84-95): verdict and first matching service from
+    one scan, through both entry points."""
+    import torch
+    from pingoo_b200._ffi import NO_SERVICE
+
+    for catch_all in (True, False):
+        rules, lists, svcs, batch = scenarios.services(60_000, catch_all)
+        want_v, want_s = Oracle(rules, lists, services=svcs).evaluate_routed(batch, threads=THREADS)
+        eng = WafEngine(rules, lists, device=0, services=svcs)
+        got_v, got_s = eng.evaluate_host_routed(batch)
+        assert np.array_equal(got_v, want_v), _explain(batch, rules, want_v, got_v)
+        bad = np.nonzero(got_s != want_s)[0]
+        assert len(bad) == 0, f"{len(bad)} services differ, first: req {bad[0]} oracle {want_s[bad[0]]} gpu {got_s[bad[0]]}"
+        t, cb = eng.to_device(batch)
+        out = torch.empty(batch.n, dtype=torch.int32, device="cuda")
+        svc = torch.empty(batch.n, dtype=torch.int16, device="cuda")
+        eng.evaluate_device_routed(cb, out, svc, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), want_v)
+        assert np.array_equal(svc.cpu().numpy().view(np.uint16), want_s)
+        # the plain entry point is unaffected by the presence of services
+        assert np.array_equal(eng.evaluate_host(batch), want_v)
+        assert np.all(want_s[(want_v & 3) != 0] == NO_SERVICE)
+    # services only (no WAF rule): everything is allowed and routed
+    rules, lists, svcs, batch = scenarios.services(5_000, True)
+    want_v, want_s = Oracle([], lists, services=svcs).evaluate_routed(batch, threads=THREADS)
+    got_v, got_s = WafEngine([], lists, device=0, services=svcs).evaluate_host_routed(batch)
+    assert np.array_equal(got_v, want_v) and np.array_equal(got_s, want_s)
+
+
+@pytest.mark.parametrize("path", ["lane", "stream"])
+def test_alternative_kernel_paths_agree(monkeypatch, path):
+    """The two earlier kernel designs stay selectable (PGW_KERNEL) and must give the oracle's answers too."""
+    monkeypatch.setenv("PGW_KERNEL", path)
+    rules, lists, mmdb, batch, g = scenarios.config1()
+    _check(rules, batch)
+    rules, reqs = scenarios.ragged()
+    _check(rules, pack_requests(reqs))
+    rules, lists, svcs, batch = scenarios.services(20_000, True)
+    want_v, want_s = Oracle(rules, lists, services=svcs).evaluate_routed(batch, threads=THREADS)
+    got_v, got_s = WafEngine(rules, lists, device=0, services=svcs).evaluate_host_routed(batch)
+    assert np.array_equal(got_v, want_v) and np.array_equal(got_s, want_s)
