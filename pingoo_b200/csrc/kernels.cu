@@ -1326,7 +1326,10 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                 for (int bi = 0; bi < 4; ++bi) {
                     const uint32_t byte = __byte_perm(w, 0, 0x4440 + bi);
                     const uint32_t cls = lds_u8(clsaddr + byte);
-                    const uint32_t st = lds_u16(hotaddr + spec * C2 + 2u * cls);
+                    // column address first (independent of the state): the state chain is IMAD -> LDS -> SEL only
+                    uint32_t colad = hotaddr + 2u * cls, ad;
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ad) : "r"(spec), "r"(C2), "r"(colad));
+                    const uint32_t st = lds_u16(ad);
                     spec = (m4 & (1u << bi)) ? st : spec;
                     sv[bi] = spec;
                 }
@@ -1342,8 +1345,24 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                         } else {
                             // a string sitting in a sticky accepting state whose events were already applied: nothing to do
                             const uint32_t s01 = sv[0] | (sv[1] << 16), s23 = sv[2] | (sv[3] << 16), ll = t_last | (t_last << 16);
-                            if (t_last > 0xFFFFu || s01 != ll || s23 != ll)
-                                t_last = fs_events_word(p, ud, acc1addr, s01, s23, m4, t_last, &t_latch, row);
+                            if (t_last > 0xFFFFu || s01 != ll || s23 != ll) {
+                                // the common event -- one accepting position whose list is a single FIRE -- is applied inline
+                                uint32_t am = m4;
+                                if (sv[0] < acclo) am &= ~1u;
+                                if (sv[1] < acclo) am &= ~2u;
+                                if (sv[2] < acclo) am &= ~4u;
+                                if (sv[3] < acclo) am &= ~8u;
+                                const uint32_t pos = __ffs(am) - 1u;
+                                const uint32_t st1 = ((pos < 2u ? s01 : s23) >> (16u * (pos & 1u))) & 0xFFFFu;
+                                uint32_t a1 = 0xFFFFu;
+                                if ((am & (am - 1u)) == 0u) a1 = lds_u16(acc1addr + 2u * (st1 - acclo));
+                                if (a1 != 0xFFFFu) {
+                                    if (st1 != t_last) red_or(row + (a1 >> 5), 1u << (a1 & 31));
+                                    t_last = st1;
+                                } else {
+                                    t_last = fs_events_word(p, ud, acc1addr, s01, s23, m4, t_last, &t_latch, row);
+                                }
+                            }
                         }
                         sts_u32(a_slot + kFsSlotStride, t_latch);
                         sts_u32(a_slot + 2u * kFsSlotStride, t_last);
