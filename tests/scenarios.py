@@ -34,7 +34,9 @@ def ragged():
         Rule("word", 'http_request.url.matches("\\\\bcat\\\\b")', [Action.CAPTCHA, Action.BLOCK]),
     ]
     reqs = []
-    urls = ["", "/", "/x=", "aab", "aaba", "a cat", "concat", "cat", "x" * 15, "y" * 16, "z" * 17, "b" * 31 + "=", "q" * 4097 + "aab"]
+    urls = ["", "/", "/x=", "aab", "aaba", "a cat", "concat", "cat", "x" * 15, "y" * 16, "z" * 17, "b" * 31 + "=", "q" * 4097 + "aab",
+            # bytes outside printable ASCII (control characters, DEL, UTF-8): the scan leaves its byte-indexed fast path
+            "a\tcat", "caf\u00e9 cat", "\x01aab", "aab\x7f", "\x7fa cat\x1f", "x" * 30 + "\u00e9" * 3 + " cat", "aa\x00b"]
     for i, u in enumerate(urls * 7):
         reqs.append(dict(host="" if i % 5 == 0 else "h.example", url=u, path="" if i % 3 == 0 else u[:40], method="GET",
                          user_agent="Mozilla/5.0 t", ip="10.0.0.%d" % (i % 250), remote_port=1000 + i, flags=i % 2))
