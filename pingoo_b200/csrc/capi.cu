@@ -193,32 +193,19 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     for (int f = 0; f < 5; ++f)
         if ((H.scanned_fields_mask >> f) & 1) { P.slot_field[n_scan_slots] = (uint32_t)f; slot_of_field[f] = n_scan_slots++; }
     P.n_slots = n_scan_slots;
-    // kernel path: unit-major field scan by default; "lane" (request-major persistent kernel) and "stream" (speculative
-    // column scan) remain selectable for comparison
-    {
-        const char* km = getenv("PGW_KERNEL");
-        rs->stream_kernel = km && strcmp(km, "stream") == 0 && H.units.size() <= kMaxConstUnits;
-        rs->field_kernel = (!km || (strcmp(km, "lane") != 0 && strcmp(km, "stream") != 0)) && H.units.size() <= kMaxConstUnits;
-    }
-    // PGW_DIRECT_ROWS=1 (field path only): hot rows indexed by the request byte instead of its class.  Measured: it saves
-    // the class lookup but costs as many instructions for the range check, and the rows are 2-4x wider -- no gain, so
-    // class rows stay the default (profiles/README.md).
-    bool direct = false;
-    if (const char* ev = getenv("PGW_DIRECT_ROWS")) direct = rs->field_kernel && atoi(ev) != 0;
-    size_t fixed = rs->field_kernel ? waf_field_smem_bytes(0, (uint32_t)H.units.size())
-                                    : waf_smem_fixed_bytes((uint32_t)H.units.size(), H.atom_words, n_scan_slots);
+    size_t fixed = waf_smem_fixed_bytes((uint32_t)H.units.size(), H.atom_words, n_scan_slots);
     if (fixed + H.units.size() * 256 + 1024 > rs->max_smem)
         return fail("ruleset does not fit the shared-memory plan (too many atoms or scan units)", err, err_cap);
     std::vector<uint8_t> image;
     std::vector<UnitDesc> units;
-    // Only a few hundred shallow states are ever visited by real traffic: cap the image so that part of the 228 KB stays
-    // L1 (spills, offsets).  Direct rows are 2-4x wider than class rows and get a larger cap.  PGW_SMEM_IMAGE_KB overrides.
-    size_t image_cap = direct ? (176u << 10) : (96u << 10);
+    // Only a few hundred shallow states are ever visited by real traffic: cap the image so most of the 228 KB stays L1
+    // (request bytes, offsets, spills).  PGW_SMEM_IMAGE_KB overrides the cap for tuning.
+    size_t image_cap = 96u << 10;
     if (const char* ev = getenv("PGW_SMEM_IMAGE_KB")) image_cap = (size_t)atoi(ev) << 10;
     size_t image_budget = rs->max_smem - fixed - 64;
     if (image_budget > image_cap) image_budget = image_cap;
     if (image_budget < H.units.size() * 256 + 4096) image_budget = H.units.size() * 256 + 4096;
-    build_smem_image(H, image_budget, &image, &units, direct);
+    build_smem_image(H, image_budget, &image, &units);
     for (auto& u : units) u.field_slot = slot_of_field[u.field];  // slot among the scanned fields
     rs->smem_bytes = waf_smem_bytes((uint32_t)image.size(), (uint32_t)units.size(), H.atom_words, n_scan_slots);
     for (auto& u : units) rs->hot_states_total += u.hot_states;
@@ -277,6 +264,13 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     rs->counters = (uint32_t*)chk(M.upload(zeros));
     rs->stream_smem = waf_stream_smem_bytes((uint32_t)image.size(), (uint32_t)units.size());
     rs->field_smem = waf_field_smem_bytes((uint32_t)image.size(), (uint32_t)units.size());
+    {
+        const char* km = getenv("PGW_KERNEL");
+        // default path: unit-major field scan; "lane" (request-major persistent kernel) and "stream" (speculative
+        // column scan) remain selectable for comparison
+        rs->stream_kernel = km && strcmp(km, "stream") == 0 && units.size() <= kMaxConstUnits;
+        rs->field_kernel = (!km || (strcmp(km, "lane") != 0 && strcmp(km, "stream") != 0)) && units.size() <= kMaxConstUnits;
+    }
     if (!ok) {
         M.release();
         return fail(std::string("CUDA: device allocation/upload failed: ") + cudaGetErrorString(cudaGetLastError()), err, err_cap);
@@ -563,7 +557,7 @@ int pgw_ruleset_info(const pgw_ruleset* rs, pgw_info* out) {
     out->reads_port = H.needs_port;
     out->reads_geo_columns = H.needs_geo_cols;
     out->table_arena_bytes = H.arena.size();
-    out->smem_bytes = rs->field_kernel ? rs->field_smem : (rs->stream_kernel ? rs->stream_smem : rs->smem_bytes);
+    out->smem_bytes = rs->smem_bytes;
     for (auto& u : H.units) out->total_dfa_states += u.n_states;
     out->tables_in_smem = rs->hot_states_total == out->total_dfa_states;
     out->tile_requests = rs->hot_states_total;  /* states whose rows live in shared memory */

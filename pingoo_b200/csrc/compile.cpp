@@ -427,14 +427,14 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
     return true;
 }
 
-void build_smem_image(const HostProgram& H, size_t budget, std::vector<uint8_t>* image, std::vector<UnitDesc>* units, bool direct) {
+void build_smem_image(const HostProgram& H, size_t budget, std::vector<uint8_t>* image, std::vector<UnitDesc>* units) {
     *units = H.units;
     image->clear();
     const size_t U = H.units.size();
     image->insert(image->end(), H.arena.begin(), H.arena.begin() + U * 256);  // class maps keep their arena offsets
     if (budget < image->size()) budget = image->size();
     size_t left = budget - image->size();
-    left = left > 96 * U ? left - 96 * U : 0;  // padding slack
+    left = left > 16 * U ? left - 16 * U : 0;  // padding slack
     for (size_t u = 0; u < U; ++u) {  // acc1 tables (upper bound: every accepting state hot)
         size_t a1 = 2 * (size_t)(H.units[u].n_states - H.units[u].acc_lo) + 2 * (size_t)H.units[u].n_states + 8;
         left = left > a1 ? left - a1 : 0;
@@ -442,7 +442,7 @@ void build_smem_image(const HostProgram& H, size_t budget, std::vector<uint8_t>*
     // expected bytes per request of each field decide who gets shared memory first
     static const double kWeight[N_FIELDS] = {13, 240, 35, 3, 95};
     std::vector<size_t> give(U, 0), order(U);
-    auto row_bytes = [&](size_t u) { return direct ? (size_t)kDirectRowBytes : (size_t)H.units[u].n_classes * 2; };
+    auto row_bytes = [&](size_t u) { return (size_t)H.units[u].n_classes * 2; };
     // Rows are handed out in passes of growing depth (32, 256, 1024, all states), each pass in order of expected
     // traffic, so no DFA is starved: visit frequency falls off steeply with BFS depth (measured on the synthetic
     // stream: the first 256 states of a 2300-state URL automaton receive 99.97 % of the transitions).
@@ -465,26 +465,19 @@ void build_smem_image(const HostProgram& H, size_t budget, std::vector<uint8_t>*
         while (image->size() % 16) image->push_back(0);
         UnitDesc& ud = (*units)[u];
         ud.hot_states = (uint32_t)give[u];
-        // direct rows: a byte below 32 indexes up to 64 bytes before its row; in front of row 0 that must read as a
-        // valid state (the word is re-walked on the full table anyway, but the speculative chain must stay in bounds)
-        if (direct) image->insert(image->end(), 64, 0);
         ud.hot_off = (uint32_t)image->size();
         ud.lim = std::min(ud.hot_states, ud.acc_lo);
         const uint16_t* src = reinterpret_cast<const uint16_t*>(H.arena.data() + H.units[u].tbl_off);
         const uint16_t trap = (uint16_t)ud.hot_states;
         const size_t C = ud.n_classes;
-        ud.direct = direct ? 1u : 0u;
-        ud.row_bytes = (uint32_t)row_bytes(u);
-        const uint8_t* cmap = H.arena.data() + H.units[u].cls_off;
-        const size_t cols = direct ? kDirectRowBytes / 2 : C;  // direct: one column per byte 32..127
         for (size_t s = 0; s < give[u]; ++s)
-            for (size_t c = 0; c < cols; ++c) {
-                uint16_t t = src[s * C + (direct ? cmap[c + 32] : c)];
+            for (size_t c = 0; c < C; ++c) {
+                uint16_t t = src[s * C + c];
                 if (t >= ud.hot_states) t = trap;  // only cold states trap; accepting states stay on the fast path
                 image->push_back((uint8_t)(t & 0xFF));
                 image->push_back((uint8_t)(t >> 8));
             }
-        for (size_t c = 0; c < cols; ++c) {  // trap row: absorbing
+        for (size_t c = 0; c < C; ++c) {  // trap row: absorbing
             image->push_back((uint8_t)(trap & 0xFF));
             image->push_back((uint8_t)(trap >> 8));
         }

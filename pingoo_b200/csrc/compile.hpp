@@ -68,10 +68,7 @@ bool compile_program(Model& model, const CompileOptions& opt, const std::vector<
 // Shared-memory image: every class map, then for each unit the rows of its first `hot_states` states
 // (BFS order from the start state, so these are the shallow, frequently visited ones).  Fills
 // units[u].hot_states / units[u].hot_off so that the image fits `budget_bytes`.
-// `direct`: hot rows are indexed by the request byte itself (printable ASCII 32..127, 192 bytes per row) instead of by
-// its class, which removes the class lookup from the scan's fast path; any other byte takes the full-table path.
-void build_smem_image(const HostProgram& prog, size_t budget_bytes, std::vector<uint8_t>* image, std::vector<UnitDesc>* units,
-                      bool direct = false);
+void build_smem_image(const HostProgram& prog, size_t budget_bytes, std::vector<uint8_t>* image, std::vector<UnitDesc>* units);
 
 // lists (pingoo/lists.rs:62-113)
 bool parse_list_csv(const std::string& name, ListType type, const uint8_t* csv, size_t len, ListData* out, std::string& err);

@@ -1176,205 +1176,6 @@ __device__ __noinline__ void fs_slow_word(const KParams& p, const UnitDesc* ud, 
     *last = la;
 }
 
-// One scan unit for one warp.  DIRECT: hot rows are indexed by the byte itself (32..127), otherwise by its class.
-template <bool DIRECT>
-__device__ __forceinline__ void fs_scan_unit(const KParams& p, const uint32_t u, const UnitDesc* s_units, const uint32_t a_img, const uint32_t a_pool,
-                                             const uint32_t a_slot, uint32_t* __restrict__ rows, uint32_t* __restrict__ counters, const uint32_t lane) {
-    const uint32_t FULL = 0xFFFFFFFFu;
-    const uint32_t Aw = p.atom_words, N = p.n;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const UnitDesc* ud = &s_units[u];  // for the out-of-line event paths
-    const UnitDesc& cu = p.udesc[u];   // constant bank, uniform index
-    const uint32_t C2 = 2u * cu.n_classes, D0 = cu.start_state, trap = cu.hot_states, lim = cu.lim, acclo = cu.acc_lo;
-    const uint32_t clsaddr = a_img + cu.cls_off, hotaddr = a_img + cu.hot_off, acc1addr = a_img + cu.acc1_off, end1addr = a_img + cu.end1_off;
-    const uint8_t* col = p.col[cu.field];
-    const uint32_t* off = p.off[cu.field];
-    uint32_t* ctr = counters + u;
-
-    // warp pools of 32 claimed requests, double buffered in shared memory: buffer `pb` is being handed out, the other
-    // one holds the next claim whose 33 field offsets are landing through cp.async (no registers, no stall)
-    uint32_t pool_next = 0, pool_end = 0, pb = 0, ah_base = 0;
-    // claims are pipelined three deep so that no global latency is ever waited for: `ticket` (atomicAdd issued, result
-    // not looked at yet) -> `ahead` (offsets landing in the spare buffer) -> the pool being handed out
-    uint32_t ticket = 0;
-    bool tk_valid = false, ah_valid = false;
-    auto issue_ticket = [&]() {
-        if (lane == 0) ticket = atomicAdd(ctr, 32u);
-        tk_valid = true;
-    };
-    auto claim_ahead = [&]() {
-        ah_valid = false;
-        if (!tk_valid) return;
-        const uint32_t b = __shfl_sync(FULL, ticket, 0);
-        if (b >= N) { tk_valid = false; return; }
-        ah_base = b;
-        const uint32_t dst = a_pool + (pb ^ 1u) * kFsPoolBytes;
-        cp_async4(dst + lane * 4u, off + min(b + lane, N));
-        if (lane == 0) cp_async4(dst + 128u, off + min(b + 32u, N));
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        ah_valid = true;
-        issue_ticket();
-    };
-    __syncwarp();
-    if (N) issue_ticket();
-    claim_ahead();
-
-    bool have = false, pend = false;
-    // hot per-lane state lives in registers; what only the (rare) event paths need -- request index, latch register,
-    // last fired state -- lives in this lane's shared-memory slots
-    uint32_t base = 0, skip = 0, end = 0, state = 0;
-    uint32_t q_req = 0;
-    uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
-
-    for (;;) {
-        // ---- rotate: next chunk of the current string, or adopt the pending one ----
-        if (have) {
-            base += 16u;
-            skip = 0;
-            cur = nxt;
-        } else if (pend) {
-            const uint32_t sa = a_pool + pb * kFsPoolBytes + (q_req & 31u) * 4u;
-            const uint32_t start = lds_u32_v(sa);
-            end = lds_u32_v(sa + 4u);
-            base = start & ~15u;
-            skip = start & 15u;
-            state = D0;
-            sts_u32(a_slot, q_req);
-            sts_u32(a_slot + kFsSlotStride, 0u);
-            sts_u32(a_slot + 2u * kFsSlotStride, 0xFFFFFFFFu);
-            cur = nxt;
-            have = true;
-            pend = false;
-        }
-        // ---- lanes that run out of bytes in this iteration (or are idle) take the next request of the pool ----
-        const bool finishing = have && end <= base + 16u;
-        const bool want = !pend && (!have || finishing);
-        bool do_ld = have && !finishing;
-        uint32_t ld_off = base + 16u;
-        const uint32_t need = __ballot_sync(FULL, want);
-        if (need) {
-            if (pool_next == pool_end && ah_valid) {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                __syncwarp();
-                pb ^= 1u;
-                pool_next = ah_base;
-                pool_end = min(ah_base + 32u, N);
-                claim_ahead();
-            }
-            const uint32_t idx = pool_next + __popc(need & lt_mask);
-            if (want && idx < pool_end) {
-                const uint32_t sa = a_pool + pb * kFsPoolBytes + (idx & 31u) * 4u;
-                const uint32_t s0 = lds_u32_v(sa), e0 = lds_u32_v(sa + 4u);
-                if (e0 > s0) {  // empty fields are left to the epilogue kernel
-                    q_req = idx;
-                    pend = true;
-                    ld_off = s0 & ~15u;
-                    do_ld = true;
-                }
-            }
-            pool_next = min(pool_end, pool_next + (uint32_t)__popc(need));
-        }
-        // one load per lane and iteration, consumed in the next one: the next chunk of the current string or the first
-        // chunk of the string just claimed (a single instruction: two loads into the same registers would serialise)
-        if (do_ld) nxt = ld_nc_v4(col + ld_off);
-        if (!__any_sync(FULL, have)) {
-            if (!__any_sync(FULL, pend) && pool_next == pool_end && !ah_valid) break;
-            continue;
-        }
-
-        // ---- walk the bytes of this chunk that belong to the field ----
-        uint32_t mk = 0;
-        if (have) {
-            const uint32_t hi = min(end - base, 16u);
-            mk = ((1u << hi) - 1u) & ~((1u << skip) - 1u);
-        }
-#pragma unroll
-        for (int wi = 0; wi < 4; ++wi) {
-            const uint32_t m4 = (mk >> (4 * wi)) & 0xFu;
-            if (!__any_sync(FULL, m4)) continue;
-            const uint32_t w = wi == 0 ? cur.x : wi == 1 ? cur.y : wi == 2 ? cur.z : cur.w;
-            uint32_t spec = min(state, trap);
-            uint32_t sv[4];
-            bool odd = false;  // DIRECT: a byte outside 32..127 in the word (taken care of on the full table)
-            if (DIRECT) {
-                // doubled bytes index the row directly; the row base is shifted by the 32 missing columns
-                const uint32_t w2 = (w << 1) & 0xFEFEFEFEu;
-                odd = m4 != 0u && ((~((w & 0x7F7F7F7Fu) + 0x60606060u) | w) & 0x80808080u) != 0u;
-#pragma unroll
-                for (int bi = 0; bi < 4; ++bi) {
-                    const uint32_t colad = hotaddr - 64u + __byte_perm(w2, 0, 0x4440 + bi);
-                    uint32_t ad;
-                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ad) : "r"(spec), "r"(kDirectRowBytes), "r"(colad));
-                    const uint32_t st = lds_u16(ad);
-                    spec = (m4 & (1u << bi)) ? st : spec;
-                    sv[bi] = spec;
-                }
-            } else {
-#pragma unroll
-                for (int bi = 0; bi < 4; ++bi) {
-                    const uint32_t byte = __byte_perm(w, 0, 0x4440 + bi);
-                    const uint32_t cls = lds_u8(clsaddr + byte);
-                    // column address first (independent of the state): the state chain is IMAD -> LDS -> SEL only
-                    uint32_t colad = hotaddr + 2u * cls, ad;
-                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ad) : "r"(spec), "r"(C2), "r"(colad));
-                    const uint32_t st = lds_u16(ad);
-                    spec = (m4 & (1u << bi)) ? st : spec;
-                    sv[bi] = spec;
-                }
-            }
-            const uint32_t mx4 = odd ? trap : max(max(sv[0], sv[1]), max(sv[2], sv[3]));
-            if (max(mx4, state) >= lim) {
-                if (max(mx4, state) >= trap || mx4 >= acclo) {
-                    uint32_t* row = rows + (size_t)lds_u32_v(a_slot) * Aw;
-                    uint32_t t_latch = lds_u32_v(a_slot + kFsSlotStride), t_last = lds_u32_v(a_slot + 2u * kFsSlotStride);
-                    if (max(mx4, state) >= trap) {
-                        uint32_t t_state = state;
-                        fs_slow_word(p, ud, clsaddr, w, m4, &t_state, &t_last, &t_latch, row);
-                        spec = t_state;
-                    } else {
-                        // a string sitting in a sticky accepting state whose events were already applied: nothing to do
-                        const uint32_t s01 = sv[0] | (sv[1] << 16), s23 = sv[2] | (sv[3] << 16), ll = t_last | (t_last << 16);
-                        if (t_last > 0xFFFFu || s01 != ll || s23 != ll) {
-                            // the common event -- one accepting position whose list is a single FIRE -- is applied inline
-                            uint32_t am = m4;
-                            if (sv[0] < acclo) am &= ~1u;
-                            if (sv[1] < acclo) am &= ~2u;
-                            if (sv[2] < acclo) am &= ~4u;
-                            if (sv[3] < acclo) am &= ~8u;
-                            const uint32_t pos = __ffs(am) - 1u;
-                            const uint32_t st1 = ((pos < 2u ? s01 : s23) >> (16u * (pos & 1u))) & 0xFFFFu;
-                            uint32_t a1 = 0xFFFFu;
-                            if ((am & (am - 1u)) == 0u) a1 = lds_u16(acc1addr + 2u * (st1 - acclo));
-                            if (a1 != 0xFFFFu) {
-                                if (st1 != t_last) red_or(row + (a1 >> 5), 1u << (a1 & 31));
-                                t_last = st1;
-                            } else {
-                                t_last = fs_events_word(p, ud, acc1addr, s01, s23, m4, t_last, &t_latch, row);
-                            }
-                        }
-                    }
-                    sts_u32(a_slot + kFsSlotStride, t_latch);
-                    sts_u32(a_slot + 2u * kFsSlotStride, t_last);
-                }
-            }
-            state = spec;
-        }
-        if (finishing) {
-            uint32_t e1 = 0xFFFFu;
-            if (state < trap) e1 = lds_u16(end1addr + 2u * state);
-            if (e1 != 0xFFFEu) {
-                uint32_t* row = rows + (size_t)lds_u32_v(a_slot) * Aw;
-                if (e1 != 0xFFFFu) red_or(row + (e1 >> 5), 1u << (e1 & 31));
-                else if (cu.end_any) {
-                    uint32_t t_latch = lds_u32_v(a_slot + kFsSlotStride);
-                    fs_fire_list(p.end_idx, p.end_events, cu.end_base + state, row, &t_latch);
-                }
-            }
-            have = false;
-        }
-    }
-}
-
 __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __grid_constant__ KParams p, uint32_t* __restrict__ rows,
                                                                        uint32_t* __restrict__ counters) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -1404,10 +1205,185 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
     const uint32_t a_img = smem_u32(s_img);
     const uint32_t a_pool = smem_u32(s_bar) + 64u + (tid >> 5) * 2u * kFsPoolBytes;
     const uint32_t a_slot = smem_u32(s_bar) + 64u + (kFsThreads / 32) * 2u * kFsPoolBytes + tid * 4u;  // word k at a_slot + k * kFsSlotStride
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t Aw = p.atom_words, N = p.n;
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
     for (uint32_t u = 0; u < p.n_units; ++u) {
-        if (p.udesc[u].direct) fs_scan_unit<true>(p, u, s_units, a_img, a_pool, a_slot, rows, counters, lane);
-        else fs_scan_unit<false>(p, u, s_units, a_img, a_pool, a_slot, rows, counters, lane);
+        const UnitDesc* ud = &s_units[u];  // for the out-of-line event paths
+        const UnitDesc& cu = p.udesc[u];   // constant bank, uniform index
+        const uint32_t C2 = 2u * cu.n_classes, D0 = cu.start_state, trap = cu.hot_states, lim = cu.lim, acclo = cu.acc_lo;
+        const uint32_t clsaddr = a_img + cu.cls_off, hotaddr = a_img + cu.hot_off, acc1addr = a_img + cu.acc1_off, end1addr = a_img + cu.end1_off;
+        const uint8_t* col = p.col[cu.field];
+        const uint32_t* off = p.off[cu.field];
+        uint32_t* ctr = counters + u;
+
+        // warp pools of 32 claimed requests, double buffered in shared memory: buffer `pb` is being handed out, the other
+        // one holds the next claim whose 33 field offsets are landing through cp.async (no registers, no stall)
+        uint32_t pool_next = 0, pool_end = 0, pb = 0, ah_base = 0;
+        // claims are pipelined three deep so that no global latency is ever waited for: `ticket` (atomicAdd issued, result
+        // not looked at yet) -> `ahead` (offsets landing in the spare buffer) -> the pool being handed out
+        uint32_t ticket = 0;
+        bool tk_valid = false, ah_valid = false;
+        auto issue_ticket = [&]() {
+            if (lane == 0) ticket = atomicAdd(ctr, 32u);
+            tk_valid = true;
+        };
+        auto claim_ahead = [&]() {
+            ah_valid = false;
+            if (!tk_valid) return;
+            const uint32_t b = __shfl_sync(FULL, ticket, 0);
+            if (b >= N) { tk_valid = false; return; }
+            ah_base = b;
+            const uint32_t dst = a_pool + (pb ^ 1u) * kFsPoolBytes;
+            cp_async4(dst + lane * 4u, off + min(b + lane, N));
+            if (lane == 0) cp_async4(dst + 128u, off + min(b + 32u, N));
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            ah_valid = true;
+            issue_ticket();
+        };
+        __syncwarp();
+        if (N) issue_ticket();
+        claim_ahead();
+
+        bool have = false, pend = false;
+        // hot per-lane state lives in registers; what only the (rare) event paths need -- request index, latch register,
+        // last fired state -- lives in this lane's shared-memory slots
+        uint32_t base = 0, skip = 0, end = 0, state = 0;
+        uint32_t q_req = 0;
+        uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
+
+        for (;;) {
+            // ---- rotate: next chunk of the current string, or adopt the pending one ----
+            if (have) {
+                base += 16u;
+                skip = 0;
+                cur = nxt;
+            } else if (pend) {
+                const uint32_t sa = a_pool + pb * kFsPoolBytes + (q_req & 31u) * 4u;
+                const uint32_t start = lds_u32_v(sa);
+                end = lds_u32_v(sa + 4u);
+                base = start & ~15u;
+                skip = start & 15u;
+                state = D0;
+                sts_u32(a_slot, q_req);
+                sts_u32(a_slot + kFsSlotStride, 0u);
+                sts_u32(a_slot + 2u * kFsSlotStride, 0xFFFFFFFFu);
+                cur = nxt;
+                have = true;
+                pend = false;
+            }
+            // ---- lanes that run out of bytes in this iteration (or are idle) take the next request of the pool ----
+            const bool finishing = have && end <= base + 16u;
+            const bool want = !pend && (!have || finishing);
+            bool do_ld = have && !finishing;
+            uint32_t ld_off = base + 16u;
+            const uint32_t need = __ballot_sync(FULL, want);
+            if (need) {
+                if (pool_next == pool_end && ah_valid) {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
+                    pb ^= 1u;
+                    pool_next = ah_base;
+                    pool_end = min(ah_base + 32u, N);
+                    claim_ahead();
+                }
+                const uint32_t idx = pool_next + __popc(need & lt_mask);
+                if (want && idx < pool_end) {
+                    const uint32_t sa = a_pool + pb * kFsPoolBytes + (idx & 31u) * 4u;
+                    const uint32_t s0 = lds_u32_v(sa), e0 = lds_u32_v(sa + 4u);
+                    if (e0 > s0) {  // empty fields are left to the epilogue kernel
+                        q_req = idx;
+                        pend = true;
+                        ld_off = s0 & ~15u;
+                        do_ld = true;
+                    }
+                }
+                pool_next = min(pool_end, pool_next + (uint32_t)__popc(need));
+            }
+            // one load per lane and iteration, consumed in the next one: the next chunk of the current string or the first
+            // chunk of the string just claimed (a single instruction: two loads into the same registers would serialise)
+            if (do_ld) nxt = ld_nc_v4(col + ld_off);
+            if (!__any_sync(FULL, have)) {
+                if (!__any_sync(FULL, pend) && pool_next == pool_end && !ah_valid) break;
+                continue;
+            }
+
+            // ---- walk the bytes of this chunk that belong to the field ----
+            uint32_t mk = 0;
+            if (have) {
+                const uint32_t hi = min(end - base, 16u);
+                mk = ((1u << hi) - 1u) & ~((1u << skip) - 1u);
+            }
+#pragma unroll
+            for (int wi = 0; wi < 4; ++wi) {
+                const uint32_t m4 = (mk >> (4 * wi)) & 0xFu;
+                if (!__any_sync(FULL, m4)) continue;
+                const uint32_t w = wi == 0 ? cur.x : wi == 1 ? cur.y : wi == 2 ? cur.z : cur.w;
+                uint32_t spec = min(state, trap);
+                uint32_t sv[4];
+#pragma unroll
+                for (int bi = 0; bi < 4; ++bi) {
+                    const uint32_t byte = __byte_perm(w, 0, 0x4440 + bi);
+                    const uint32_t cls = lds_u8(clsaddr + byte);
+                    // column address first (independent of the state): the state chain is IMAD -> LDS -> SEL only
+                    uint32_t colad = hotaddr + 2u * cls, ad;
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ad) : "r"(spec), "r"(C2), "r"(colad));
+                    const uint32_t st = lds_u16(ad);
+                    spec = (m4 & (1u << bi)) ? st : spec;
+                    sv[bi] = spec;
+                }
+                const uint32_t mx4 = max(max(sv[0], sv[1]), max(sv[2], sv[3]));
+                if (max(mx4, state) >= lim) {
+                    if (max(mx4, state) >= trap || mx4 >= acclo) {
+                        uint32_t* row = rows + (size_t)lds_u32_v(a_slot) * Aw;
+                        uint32_t t_latch = lds_u32_v(a_slot + kFsSlotStride), t_last = lds_u32_v(a_slot + 2u * kFsSlotStride);
+                        if (max(mx4, state) >= trap) {
+                            uint32_t t_state = state;
+                            fs_slow_word(p, ud, clsaddr, w, m4, &t_state, &t_last, &t_latch, row);
+                            spec = t_state;
+                        } else {
+                            // a string sitting in a sticky accepting state whose events were already applied: nothing to do
+                            const uint32_t s01 = sv[0] | (sv[1] << 16), s23 = sv[2] | (sv[3] << 16), ll = t_last | (t_last << 16);
+                            if (t_last > 0xFFFFu || s01 != ll || s23 != ll) {
+                                // the common event -- one accepting position whose list is a single FIRE -- is applied inline
+                                uint32_t am = m4;
+                                if (sv[0] < acclo) am &= ~1u;
+                                if (sv[1] < acclo) am &= ~2u;
+                                if (sv[2] < acclo) am &= ~4u;
+                                if (sv[3] < acclo) am &= ~8u;
+                                const uint32_t pos = __ffs(am) - 1u;
+                                const uint32_t st1 = ((pos < 2u ? s01 : s23) >> (16u * (pos & 1u))) & 0xFFFFu;
+                                uint32_t a1 = 0xFFFFu;
+                                if ((am & (am - 1u)) == 0u) a1 = lds_u16(acc1addr + 2u * (st1 - acclo));
+                                if (a1 != 0xFFFFu) {
+                                    if (st1 != t_last) red_or(row + (a1 >> 5), 1u << (a1 & 31));
+                                    t_last = st1;
+                                } else {
+                                    t_last = fs_events_word(p, ud, acc1addr, s01, s23, m4, t_last, &t_latch, row);
+                                }
+                            }
+                        }
+                        sts_u32(a_slot + kFsSlotStride, t_latch);
+                        sts_u32(a_slot + 2u * kFsSlotStride, t_last);
+                    }
+                }
+                state = spec;
+            }
+            if (finishing) {
+                uint32_t e1 = 0xFFFFu;
+                if (state < trap) e1 = lds_u16(end1addr + 2u * state);
+                if (e1 != 0xFFFEu) {
+                    uint32_t* row = rows + (size_t)lds_u32_v(a_slot) * Aw;
+                    if (e1 != 0xFFFFu) red_or(row + (e1 >> 5), 1u << (e1 & 31));
+                    else if (cu.end_any) {
+                        uint32_t t_latch = lds_u32_v(a_slot + kFsSlotStride);
+                        fs_fire_list(p.end_idx, p.end_events, cu.end_base + state, row, &t_latch);
+                    }
+                }
+                have = false;
+            }
+        }
     }
 }
 

@@ -5,7 +5,6 @@
 
 namespace pgw {
 
-constexpr uint32_t kDirectRowBytes = 192;           // direct hot rows: uint16 per byte value 32..127
 constexpr uint32_t kNoService = 0xFFFFu;             // service index when no service takes the request
 constexpr uint32_t kNoRule = 0x3FFFFFFFu;          // verdict rule index when no rule decided
 constexpr uint32_t kMaxStackDepth = 32;            // rule bytecode evaluation stack (one 32-bit register)
@@ -55,8 +54,7 @@ struct UnitDesc {
                            // 0xFFFE none, an atom id for a single FIRE, 0xFFFF general list
     uint32_t idle_state;   // most frequent state on neutral text: speculative start state of the stream scan
     uint32_t has_latch;    // the unit has gap-split patterns (latch events must be applied in string order)
-    uint32_t row_bytes;    // bytes per hot row in the image: 2 * n_classes (class rows) or 192 (direct ASCII rows)
-    uint32_t direct;       // 1: hot rows are indexed by the byte itself (32..127), no class lookup on the fast path
+    uint32_t pad2[2];
 };
 
 // predicates evaluated once per request outside the byte scan
