@@ -1180,9 +1180,9 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                                                                        uint32_t* __restrict__ counters) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t img_bytes = r16(p.image_bytes);
-    uint8_t* s_img = smem;
-    UnitDesc* s_units = reinterpret_cast<UnitDesc*>(smem + img_bytes);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + img_bytes + r16(p.n_units * (uint32_t)sizeof(UnitDesc)));
+    uint8_t* s_img = smem + ((0u - smem_u32(smem)) & 255u);  // class maps (image offsets u * 256) on 256-byte boundaries
+    UnitDesc* s_units = reinterpret_cast<UnitDesc*>(s_img + img_bytes);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_img + img_bytes + r16(p.n_units * (uint32_t)sizeof(UnitDesc)));
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) {
@@ -1249,33 +1249,36 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
         bool have = false, pend = false;
         // hot per-lane state lives in registers; what only the (rare) event paths need -- request index, latch register,
         // last fired state -- lives in this lane's shared-memory slots
-        uint32_t base = 0, skip = 0, end = 0, state = 0;
+        uint32_t base = 0, skip = 0, nskip = 0, end = 0, state = 0;
         uint32_t q_req = 0;
         uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
 
         for (;;) {
-            // ---- rotate: next chunk of the current string, or adopt the pending one ----
-            if (have) {
-                base += 16u;
-                skip = 0;
+            // ---- rotate: next chunk of the current string, or the first chunk of the string claimed last iteration ----
+            if (have || pend) {
+                base += 16u;  // a claim leaves `base` one chunk before the string's first one
                 cur = nxt;
-            } else if (pend) {
-                const uint32_t sa = a_pool + pb * kFsPoolBytes + (q_req & 31u) * 4u;
-                const uint32_t start = lds_u32_v(sa);
-                end = lds_u32_v(sa + 4u);
-                base = start & ~15u;
-                skip = start & 15u;
+            }
+            skip = 0;
+            if (pend) {
+                skip = nskip;
                 state = D0;
                 sts_u32(a_slot, q_req);
                 sts_u32(a_slot + kFsSlotStride, 0u);
                 sts_u32(a_slot + 2u * kFsSlotStride, 0xFFFFFFFFu);
-                cur = nxt;
                 have = true;
                 pend = false;
             }
-            // ---- lanes that run out of bytes in this iteration (or are idle) take the next request of the pool ----
+            // everything this iteration's walk needs from (base, end, skip) is derived here, so that a lane on its last
+            // chunk can overwrite them with its next string right away
             const bool finishing = have && end <= base + 16u;
-            const bool want = !pend && (!have || finishing);
+            uint32_t mk = 0;
+            if (have) {
+                const uint32_t hi = min(end - base, 16u);
+                mk = ((1u << hi) - 1u) & ~((1u << skip) - 1u);
+            }
+            // ---- lanes that run out of bytes in this iteration (or are idle) take the next request of the pool ----
+            const bool want = !have || finishing;
             bool do_ld = have && !finishing;
             uint32_t ld_off = base + 16u;
             const uint32_t need = __ballot_sync(FULL, want);
@@ -1295,7 +1298,10 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                     if (e0 > s0) {  // empty fields are left to the epilogue kernel
                         q_req = idx;
                         pend = true;
+                        end = e0;
                         ld_off = s0 & ~15u;
+                        base = ld_off - 16u;
+                        nskip = s0 & 15u;
                         do_ld = true;
                     }
                 }
@@ -1310,11 +1316,6 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
             }
 
             // ---- walk the bytes of this chunk that belong to the field ----
-            uint32_t mk = 0;
-            if (have) {
-                const uint32_t hi = min(end - base, 16u);
-                mk = ((1u << hi) - 1u) & ~((1u << skip) - 1u);
-            }
 #pragma unroll
             for (int wi = 0; wi < 4; ++wi) {
                 const uint32_t m4 = (mk >> (4 * wi)) & 0xFu;
@@ -1324,8 +1325,8 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                 uint32_t sv[4];
 #pragma unroll
                 for (int bi = 0; bi < 4; ++bi) {
-                    const uint32_t byte = __byte_perm(w, 0, 0x4440 + bi);
-                    const uint32_t cls = lds_u8(clsaddr + byte);
+                    // class maps sit on 256-byte boundaries of the shared window: one PRMT extracts the byte AND adds the base
+                    const uint32_t cls = lds_u8(__byte_perm(w, clsaddr, 0x7650 + bi));
                     // column address first (independent of the state): the state chain is IMAD -> LDS -> SEL only
                     uint32_t colad = hotaddr + 2u * cls, ad;
                     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ad) : "r"(spec), "r"(C2), "r"(colad));
@@ -1466,7 +1467,7 @@ const char* waf_configure(int device, size_t* max_smem_optin, int* sm_count) {
 }
 
 size_t waf_field_smem_bytes(uint32_t image_bytes, uint32_t n_units) {
-    return r16(image_bytes) + r16(n_units * (uint32_t)sizeof(UnitDesc)) + 64 + (kFsThreads / 32) * 2 * kFsPoolBytes + 3 * kFsSlotStride;
+    return 256 + r16(image_bytes) + r16(n_units * (uint32_t)sizeof(UnitDesc)) + 64 + (kFsThreads / 32) * 2 * kFsPoolBytes + 3 * kFsSlotStride;
 }
 
 const char* waf_field_launch(const KParams& p, uint32_t* rows, uint32_t* counters, int sm_count, size_t smem_bytes, void* stream, cudaEvent_t ev0,
