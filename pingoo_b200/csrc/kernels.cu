@@ -1315,11 +1315,11 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                 continue;
             }
 
-            // ---- walk the bytes of this chunk that belong to the field ----
+            // ---- walk the bytes of this chunk that belong to the field (no per-word vote: some lane almost always has
+            //      bytes in every word, the vote cost more than the words it skipped) ----
 #pragma unroll
             for (int wi = 0; wi < 4; ++wi) {
                 const uint32_t m4 = (mk >> (4 * wi)) & 0xFu;
-                if (!__any_sync(FULL, m4)) continue;
                 const uint32_t w = wi == 0 ? cur.x : wi == 1 ? cur.y : wi == 2 ? cur.z : cur.w;
                 uint32_t spec = min(state, trap);
                 uint32_t sv[4];
@@ -1334,12 +1334,13 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                     spec = (m4 & (1u << bi)) ? st : spec;
                     sv[bi] = spec;
                 }
+                // a cold start state walks the trap row, so the four new states alone tell whether the word needs attention
                 const uint32_t mx4 = max(max(sv[0], sv[1]), max(sv[2], sv[3]));
-                if (max(mx4, state) >= lim) {
-                    if (max(mx4, state) >= trap || mx4 >= acclo) {
+                if (mx4 >= lim) {
+                    if (mx4 >= trap || mx4 >= acclo) {
                         uint32_t* row = rows + (size_t)lds_u32_v(a_slot) * Aw;
                         uint32_t t_latch = lds_u32_v(a_slot + kFsSlotStride), t_last = lds_u32_v(a_slot + 2u * kFsSlotStride);
-                        if (max(mx4, state) >= trap) {
+                        if (mx4 >= trap) {
                             uint32_t t_state = state;
                             fs_slow_word(p, ud, clsaddr, w, m4, &t_state, &t_last, &t_latch, row);
                             spec = t_state;
@@ -1383,6 +1384,7 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                     }
                 }
                 have = false;
+                state = 0;  // an idle lane must not look like it sits in a cold or accepting state
             }
         }
     }
