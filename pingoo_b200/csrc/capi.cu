@@ -232,6 +232,8 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     P.rule_off = (const uint32_t*)chk(M.upload(H.rule_off));
     P.term = (const uint8_t*)chk(M.upload(H.term));
     P.n_rules = H.n_rules;
+    P.v1 = (const uint32_t*)chk(M.upload(H.v1));
+    P.s1 = (const uint16_t*)chk(M.upload(H.s1));
     P.n_waf_rules = H.n_waf_rules;
     P.s0 = H.s0;
     P.dflt_services = (const uint32_t*)chk(M.upload(H.dflt_services));

@@ -233,6 +233,30 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
         if (M.rules[r].is_service) t0 = t1 = 0;
         H.term.push_back((uint8_t)(t0 | (t1 << 2)));
     }
+    // The most common deviation from the expected vector is a single atom (a non-GET method, one matched pattern):
+    // its verdict and service are tabulated here so that the epilogue needs no rule evaluation for it either.
+    {
+        H.v1.assign(2 * (size_t)H.n_atoms, 0);
+        H.s1.assign(H.n_atoms, (uint16_t)kNoService);
+        std::vector<uint8_t> vals = expect_vals;
+        for (uint32_t a = 0; a < H.n_atoms; ++a) {
+            if (!((H.care[a >> 5] >> (a & 31)) & 1u)) continue;
+            vals[a] ^= 1;
+            for (int cv = 0; cv < 2; ++cv) {
+                uint32_t v = V_ALLOW | (kNoRule << 2);
+                for (size_t r = 0; r < H.n_waf_rules; ++r) {
+                    uint8_t t = (H.term[r] >> (2 * cv)) & 3;
+                    if (!t || !M.pool.eval(M.rules[r].formula, vals)) continue;
+                    v = t | ((uint32_t)r << 2);
+                    break;
+                }
+                H.v1[(size_t)cv * H.n_atoms + a] = v;
+            }
+            for (size_t r = H.n_waf_rules; r < M.rules.size(); ++r)
+                if (M.pool.eval(M.rules[r].formula, vals)) { H.s1[a] = (uint16_t)(r - H.n_waf_rules); break; }
+            vals[a] ^= 1;
+        }
+    }
     // services: first route that is true under the expected atom values, and every route that is (candidates when
     // some atom deviates)
     H.s0 = 0xFFFFu;

@@ -42,6 +42,8 @@ struct HostProgram {
     std::vector<uint32_t> ar_idx, ar_rules;  // atom -> rules CSR
     std::vector<uint32_t> dflt_rules[2];     // rules true under `expect` with a terminal action, per captcha_verified
     uint32_t v0[2] = {0, 0};                 // verdict when every cared atom has its expected value
+    std::vector<uint32_t> v1;                // [cv][atom]: verdict when exactly that one cared atom deviates
+    std::vector<uint16_t> s1;                // [atom]: service in that case
     // service routes: rules [n_waf_rules, n_rules) of the same program (term = 0: the verdict loop skips them)
     uint32_t n_waf_rules = 0;
     std::vector<uint32_t> dflt_services;     // routes true under `expect` (rule indices)

@@ -162,8 +162,14 @@ __device__ __forceinline__ uint32_t lpm_lookup(const KParams& p, const uint8_t* 
 
 // Per-request predicates outside the byte scan + the verdict (http_listener.rs:196-264).
 // `row[w * stride]` is the request's atom bitmap (scan atoms already set).
-__device__ __noinline__ void request_epilogue(const KParams& p, uint32_t r, uint32_t* row, uint32_t stride) {
+// WARP: called by all 32 lanes of a converged warp (`valid` false for lanes past the end of the batch, which shadow the
+// last request without storing anything): requests of the warp that deviate from the expected atom vector in the same
+// way are evaluated once -- verdict and service are functions of the deviation and of `captcha_verified` alone -- and
+// the result is shared by shuffle.
+template <bool WARP>
+__device__ __forceinline__ void request_epilogue_t(const KParams& p, uint32_t r, uint32_t* row, uint32_t stride, bool valid) {
     const uint32_t Aw = p.atom_words;
+    const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t flags = p.flags ? p.flags[r] : 0u;
     int64_t asn = 0;
     uint32_t country = (uint32_t)'X' | ((uint32_t)'X' << 8);
@@ -226,7 +232,7 @@ __device__ __noinline__ void request_epilogue(const KParams& p, uint32_t r, uint
                 v = (__ldg(p.cset + a.set_id * kCountryWords + (bit >> 5)) >> (bit & 31)) & 1u;
             }
         }
-        if (v) row[(a.atom >> 5) * stride] |= 1u << (a.atom & 31);
+        if (v && valid) row[(a.atom >> 5) * stride] |= 1u << (a.atom & 31);
     }
 
     const uint32_t cv = flags & RF_CAPTCHA_VERIFIED;
@@ -245,13 +251,41 @@ __device__ __noinline__ void request_epilogue(const KParams& p, uint32_t r, uint
         if (bypass) { verdict = V_BYPASS | (kNoRule << 2); decided = true; }
     }
     if (!decided && (flags & RF_PRE_CAPTCHA)) { verdict = V_CAPTCHA | (kNoRule << 2); decided = true; }
+
+    // deviations from the expected atom vector: none -> v0 / s0, exactly one -> v1[atom] / s1[atom], otherwise the
+    // candidate rules (those that mention a deviating atom, plus the ones true by default) are evaluated
+    const bool routes = p.service != nullptr && p.n_rules > p.n_waf_rules;
+    uint32_t ndev = 0, dev_atom = 0, sig = cv;
+    for (uint32_t w = 0; w < Aw; ++w) {
+        const uint32_t x = (row[w * stride] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
+        if (x) dev_atom = w * 32u + (uint32_t)__ffs(x) - 1u;
+        ndev += (uint32_t)__popc(x);
+        sig = sig * 0x9E3779B1u + x;
+    }
+    uint32_t svc = kNoService;
     if (!decided) {
-        uint32_t diff = 0;
-        for (uint32_t w = 0; w < Aw; ++w) diff |= (row[w * stride] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
-        if (diff == 0) verdict = p.v0[cv];
-        else {
+        if (ndev == 0u) { verdict = p.v0[cv]; svc = p.s0; }
+        else if (ndev == 1u) { verdict = __ldg(p.v1 + cv * p.n_atoms + dev_atom); svc = routes ? (uint32_t)__ldg(p.s1 + dev_atom) : kNoService; }
+    }
+    const bool need_eval = !decided && ndev >= 2u;
+    if (WARP ? __any_sync(FULL, need_eval) : need_eval) {
+        bool do_eval = need_eval, same = false;
+        uint32_t leader = 0;
+        if (WARP) {
+            const uint32_t lane = threadIdx.x & 31u;
+            const uint32_t peers = __match_any_sync(FULL, need_eval ? (sig & 0x7FFFFFFFu) : (0x80000000u | lane));
+            leader = (uint32_t)__ffs(peers) - 1u;
+            same = true;  // equal signature: confirm that the deviation really is the leader's
+            for (uint32_t w = 0; w < Aw; ++w) {
+                const uint32_t x = (row[w * stride] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
+                same &= __shfl_sync(FULL, x, leader) == x;
+            }
+            same &= __shfl_sync(FULL, cv, leader) == cv;
+            do_eval = need_eval && (leader == lane || !same);
+        }
+        if (do_eval) {
             const uint32_t tshift = 2 * cv;
-            uint32_t best = kNoRule;
+            uint32_t best = kNoRule, best_svc = kNoRule;
             for (uint32_t w = 0; w < Aw; ++w) {
                 uint32_t x = (row[w * stride] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
                 while (x) {
@@ -260,10 +294,14 @@ __device__ __noinline__ void request_epilogue(const KParams& p, uint32_t r, uint
                     uint32_t atom = w * 32 + b;
                     uint32_t i0 = __ldg(p.ar_idx + atom), i1 = __ldg(p.ar_idx + atom + 1);
                     for (uint32_t i = i0; i < i1; ++i) {
-                        uint32_t rule = __ldg(p.ar_rules + i);
-                        if (rule >= best) break;  // lists are ascending
-                        if (((__ldg(p.term + rule) >> tshift) & 3u) == 0) continue;
-                        if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row, stride)) best = rule;
+                        uint32_t rule = __ldg(p.ar_rules + i);  // ascending; WAF rules first, then service routes
+                        if (rule < p.n_waf_rules) {
+                            if (rule >= best || ((__ldg(p.term + rule) >> tshift) & 3u) == 0) continue;
+                            if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row, stride)) best = rule;
+                        } else {
+                            if (!routes || rule >= best_svc) break;
+                            if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row, stride)) best_svc = rule;
+                        }
                     }
                 }
             }
@@ -272,46 +310,29 @@ __device__ __noinline__ void request_epilogue(const KParams& p, uint32_t r, uint
                 if (rule >= best) break;
                 if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row, stride)) best = rule;
             }
-            if (best == kNoRule) verdict = V_ALLOW | (kNoRule << 2);
-            else verdict = ((__ldg(p.term + best) >> tshift) & 3u) | (best << 2);
-        }
-    }
-    p.verdict[r] = verdict;
-    if (p.service) {
-        // http_listener.rs:266-272: only a request the rules let through reaches the services; the first service whose
-        // route is absent or true takes it, none => 404 (kNoService)
-        uint32_t svc = kNoService;
-        if ((verdict & 3u) == V_ALLOW && p.n_rules > p.n_waf_rules) {
-            uint32_t diff = 0;
-            for (uint32_t w = 0; w < Aw; ++w) diff |= (row[w * stride] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
-            if (diff == 0) svc = p.s0;
-            else {
-                uint32_t best = kNoRule;
-                for (uint32_t w = 0; w < Aw; ++w) {
-                    uint32_t x = (row[w * stride] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
-                    while (x) {
-                        uint32_t b = __ffs(x) - 1;
-                        x &= x - 1;
-                        uint32_t atom = w * 32 + b;
-                        uint32_t i0 = __ldg(p.ar_idx + atom), i1 = __ldg(p.ar_idx + atom + 1);
-                        for (uint32_t i = i0; i < i1; ++i) {
-                            uint32_t rule = __ldg(p.ar_rules + i);
-                            if (rule >= best) break;  // lists are ascending
-                            if (rule < p.n_waf_rules) continue;
-                            if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row, stride)) best = rule;
-                        }
-                    }
-                }
+            if (routes)
                 for (uint32_t i = 0; i < p.n_dflt_services; ++i) {
                     uint32_t rule = __ldg(p.dflt_services + i);
-                    if (rule >= best) break;
-                    if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row, stride)) best = rule;
+                    if (rule >= best_svc) break;
+                    if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row, stride)) best_svc = rule;
                 }
-                if (best != kNoRule) svc = best - p.n_waf_rules;
-            }
+            verdict = best == kNoRule ? (V_ALLOW | (kNoRule << 2)) : (((__ldg(p.term + best) >> tshift) & 3u) | (best << 2));
+            svc = best_svc == kNoRule ? kNoService : best_svc - p.n_waf_rules;
         }
-        p.service[r] = (uint16_t)svc;
+        if (WARP) {
+            const uint32_t lv = __shfl_sync(FULL, verdict, leader), ls = __shfl_sync(FULL, svc, leader);
+            if (need_eval && same) { verdict = lv; svc = ls; }
+        }
     }
+    if (!valid) return;
+    p.verdict[r] = verdict;
+    // http_listener.rs:266-272: only a request the rules let through reaches the services; the first service whose
+    // route is absent or true takes it, none => 404 (kNoService)
+    if (p.service) p.service[r] = (uint16_t)(((verdict & 3u) == V_ALLOW && routes) ? svc : kNoService);
+}
+
+__device__ __noinline__ void request_epilogue(const KParams& p, uint32_t r, uint32_t* row, uint32_t stride) {
+    request_epilogue_t<false>(p, r, row, stride, true);
 }
 
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
@@ -1393,20 +1414,26 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
 // Verdicts once every unit has been scanned: one thread per request.  Empty fields never reach the stream scan;
 // their end-of-field events (the DFA's start state at end of input) are applied here.
 __global__ void __launch_bounds__(256) waf_epilogue_kernel(const __grid_constant__ KParams p, uint32_t* __restrict__ rows) {
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < p.n; r += gridDim.x * blockDim.x) {
+    // warp-uniform trip count: every lane of a warp goes through request_epilogue_t<true> together
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < p.n; base += gridDim.x * blockDim.x) {
+        const uint32_t rr = base + (threadIdx.x & 31u);
+        const bool valid = rr < p.n;
+        const uint32_t r = valid ? rr : p.n - 1u;
         uint32_t* row = rows + (size_t)r * p.atom_words;
-        for (uint32_t u = 0; u < p.n_units; ++u) {
-            const UnitDesc& ud = p.udesc[u];  // parameter bank (both callers keep n_units <= kMaxConstUnits)
-            if (!ud.end_any) continue;
-            const uint32_t* o = p.off[ud.field] + r;
-            if (o[0] != o[1]) continue;
-            uint32_t a = __ldg(p.end_idx + ud.end_base + ud.start_state), b = __ldg(p.end_idx + ud.end_base + ud.start_state + 1);
-            for (uint32_t i = a; i < b; ++i) {
-                const uint32_t e = __ldg(p.end_events + i);
-                if ((e >> kEvKindShift) == 0u) row[(e & kEvAtomMask) >> 5] |= 1u << (e & 31);  // latch kinds cannot fire on an empty field
+        if (valid)
+            for (uint32_t u = 0; u < p.n_units; ++u) {
+                const UnitDesc& ud = p.udesc[u];  // parameter bank (both callers keep n_units <= kMaxConstUnits)
+                if (!ud.end_any) continue;
+                const uint32_t* o = p.off[ud.field] + r;
+                if (o[0] != o[1]) continue;
+                uint32_t a = __ldg(p.end_idx + ud.end_base + ud.start_state), b = __ldg(p.end_idx + ud.end_base + ud.start_state + 1);
+                for (uint32_t i = a; i < b; ++i) {
+                    const uint32_t e = __ldg(p.end_events + i);
+                    if ((e >> kEvKindShift) == 0u) row[(e & kEvAtomMask) >> 5] |= 1u << (e & 31);  // latch kinds cannot fire on an empty field
+                }
             }
-        }
-        request_epilogue(p, r, row, 1);
+        __syncwarp();
+        request_epilogue_t<true>(p, r, row, 1, valid);
     }
 }
 

@@ -58,6 +58,8 @@ struct KParams {
     const uint32_t* dflt[2];
     uint32_t n_dflt[2];
     uint32_t v0[2];
+    const uint32_t* v1;         // [cv][atom] verdict when exactly one cared atom deviates from `expect`
+    const uint16_t* s1;         // [atom] service in that case
     // service routes (rules [n_waf_rules, n_rules)); `service` null: not requested for this batch
     uint32_t n_waf_rules;
     uint32_t s0;

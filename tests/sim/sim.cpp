@@ -243,6 +243,7 @@ int pgwsim_evaluate_routed(void* h, const pgw_batch* b, uint32_t* out, uint16_t*
         }
         uint32_t cv = flags & RF_CAPTCHA_VERIFIED;
         uint32_t verdict = 0;
+        uint32_t single_dev = 0xFFFFFFFFu;
         bool decided = false;
         if (flags & RF_PRE_BLOCK) { verdict = V_BLOCK | (kNoRule << 2); decided = true; }
         if (!decided && H.eval_gates) {
@@ -256,9 +257,16 @@ int pgwsim_evaluate_routed(void* h, const pgw_batch* b, uint32_t* out, uint16_t*
         }
         if (!decided && (flags & RF_PRE_CAPTCHA)) { verdict = V_CAPTCHA | (kNoRule << 2); decided = true; }
         if (!decided) {
-            uint32_t diff = 0;
-            for (uint32_t w = 0; w < Aw; ++w) diff |= (row[w] ^ H.expect[w]) & H.care[w];
+            uint32_t diff = 0, ndev = 0, dev_atom = 0;
+            for (uint32_t w = 0; w < Aw; ++w) {
+                uint32_t x = (row[w] ^ H.expect[w]) & H.care[w];
+                if (x) dev_atom = w * 32 + (uint32_t)__builtin_ctz(x);
+                ndev += (uint32_t)__builtin_popcount(x);
+                diff |= x;
+            }
+            if (ndev == 1) single_dev = dev_atom;
             if (!diff) verdict = H.v0[cv];
+            else if (ndev == 1) verdict = H.v1[(size_t)cv * H.n_atoms + dev_atom];
             else {
                 uint32_t best = kNoRule;
                 uint32_t tshift = 2 * cv;
@@ -289,7 +297,8 @@ int pgwsim_evaluate_routed(void* h, const pgw_batch* b, uint32_t* out, uint16_t*
             if ((verdict & 3u) == V_ALLOW && H.n_rules > H.n_waf_rules) {
                 uint32_t diff = 0;
                 for (uint32_t w = 0; w < Aw; ++w) diff |= (row[w] ^ H.expect[w]) & H.care[w];
-                if (!diff) svc = H.s0;
+                if (single_dev != 0xFFFFFFFFu) svc = H.s1[single_dev];
+                else if (!diff) svc = H.s0;
                 else {
                     uint32_t best = kNoRule;
                     for (uint32_t w = 0; w < Aw; ++w) {
