@@ -16,6 +16,7 @@ import statistics
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -84,16 +85,66 @@ def algorithmic_bytes(info, batches):
 
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML from a thread every ~2 ms (a timed region can
+    be a few tens of milliseconds), nvidia-smi -lms as the fallback."""
+
+    _REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
+
     def __init__(self, device):
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.p = None
+        self.t = None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = None
+            try:
+                import torch
+
+                uuid = str(torch.cuda.get_device_properties(device).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.nv, self.h = pynvml, h
+            self.max_clock = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.t = None
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
+    def _run(self):
+        nv, h = self.nv, self.h
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(self.max_clock)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in self._REASONS:
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def stop(self):
+        if self.t is not None:
+            self._stop.set()
+            self.t.join(timeout=2)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -118,7 +169,8 @@ class ClockSampler:
                 if parts[3 + k].lower().startswith("active"):
                     reasons.add(nm)
         os.unlink(self.f.name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi"}
 
 
 def pinned_copy(batch):
@@ -277,7 +329,7 @@ def main():
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = world * n_local * e2e_steps / float(t_e.item()) / 1e6
     i2 = eng.info()
-    h2d, d2h = int(i2.last_h2d_bytes) * len(batches), int(i2.last_d2h_bytes) * len(batches)
+    h2d, d2h = int(i2.last_h2d_bytes) * len(batches) * world, int(i2.last_d2h_bytes) * len(batches) * world  # whole job
 
     if rank != 0:
         if world > 1:
