@@ -140,6 +140,45 @@ int pgw_services_set(pgw_ruleset* rs, const pgw_service_desc* services, uint32_t
 int pgw_evaluate_batch_routed(const pgw_ruleset* rs, const pgw_batch* batch, uint32_t* verdict_dev, uint16_t* service_dev, void* stream);
 int pgw_evaluate_batch_routed_host(pgw_ruleset* rs, const pgw_batch* batch, uint32_t* verdict_host, uint16_t* service_host);
 
+/* ---- request packer + micro-batching queue ------------------------------------------------------
+ * The reference evaluates each request inline on the worker that serves the connection (http_listener.rs:139-272);
+ * nothing like this queue exists there.  Worker threads hand single requests -- the strings the listener has in hand --
+ * to pgw_queue_evaluate, which blocks until the verdict is known.  The queue applies the listener's shaping (host:
+ * header to_str + trim + at most 256 bytes, http_listener.rs:284-296; path: trailing '/' trimmed, http_utils.rs:114-116;
+ * user agent: to_str + trim + at most 256 bytes, http_listener.rs:159-165), packs the requests into the columnar
+ * pgw_batch in pinned memory and evaluates a batch (pgw_evaluate_batch_routed_host) when `max_batch` requests are
+ * waiting or the oldest has waited `max_delay_us`.  Two batches are in flight at most: one being filled, one being
+ * evaluated.  While a queue exists it must be the only caller of the host-pointer entry points of its ruleset.
+ * asn / country columns are not part of a queued request: GeoIP is resolved on the device (pgw_geoip_load). */
+typedef struct pgw_request {
+    const char* host; size_t host_len;             /* uri.host() or the Host header, raw */
+    const char* url; size_t url_len;               /* uri.to_string() */
+    const char* path; size_t path_len;             /* uri.path() */
+    const char* method; size_t method_len;
+    const char* user_agent; size_t user_agent_len; /* raw header value */
+    uint8_t ip[16];                                /* network order, IPv4 in bytes 0-3 */
+    uint8_t ip_is_v6;
+    uint8_t flags;                                 /* PGW_FLAG_* */
+    int32_t remote_port;
+} pgw_request;
+typedef struct pgw_queue_stats {
+    uint64_t batches, requests, full_flushes, deadline_flushes;
+    uint32_t largest_batch, reserved;
+} pgw_queue_stats;
+typedef struct pgw_queue pgw_queue;
+int pgw_queue_create(pgw_ruleset* rs, uint32_t max_batch, uint32_t max_delay_us, pgw_queue** out, char* err, size_t err_cap);
+/* Thread-safe, blocking.  0 on success; `service` may be NULL. */
+int pgw_queue_evaluate(pgw_queue* q, const pgw_request* req, uint32_t* verdict, uint16_t* service);
+/* Thread-safe, returns as soon as the request is packed (its strings are copied); `done` is called exactly once from the
+ * queue's dispatcher thread when the batch has been evaluated -- the shape an async runtime (tokio) wants: wake a task. */
+typedef void (*pgw_done_fn)(void* user, uint32_t verdict, uint16_t service, int rc);
+int pgw_queue_submit(pgw_queue* q, const pgw_request* req, pgw_done_fn done, void* user);
+int pgw_queue_get_stats(pgw_queue* q, pgw_queue_stats* out);
+/* Flushes what is pending; no thread may be inside pgw_queue_evaluate any more. */
+void pgw_queue_destroy(pgw_queue* q);
+/* The shaping alone (no device needed): pointers into the request's own strings, Field order host,url,path,method,user_agent. */
+int pgw_shape_request(const pgw_request* req, const char* out_ptr[5], size_t out_len[5]);
+
 int pgw_ruleset_info(const pgw_ruleset* rs, pgw_info* out);
 /* Measurement hook (no reference counterpart): while enabled, every batch evaluated on the default kernel path is
  * bracketed by CUDA events around its scan kernel, on the stream the kernel is launched on (a ring of 256 pairs).

@@ -19,6 +19,23 @@ class ServiceDesc(C.Structure):
     _fields_ = [("name", C.c_char_p), ("route", C.c_char_p)]
 
 
+class Request(C.Structure):
+    _fields_ = [
+        ("host", C.c_char_p), ("host_len", C.c_size_t), ("url", C.c_char_p), ("url_len", C.c_size_t),
+        ("path", C.c_char_p), ("path_len", C.c_size_t), ("method", C.c_char_p), ("method_len", C.c_size_t),
+        ("user_agent", C.c_char_p), ("user_agent_len", C.c_size_t),
+        ("ip", C.c_uint8 * 16), ("ip_is_v6", C.c_uint8), ("flags", C.c_uint8), ("remote_port", C.c_int32),
+    ]
+
+
+class QueueStats(C.Structure):
+    _fields_ = [("batches", C.c_uint64), ("requests", C.c_uint64), ("full_flushes", C.c_uint64), ("deadline_flushes", C.c_uint64),
+                ("largest_batch", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+DONE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_uint16, C.c_int)
+
+
 class Options(C.Structure):
     _fields_ = [("max_dfa_states", C.c_int32), ("max_unit_table_bytes", C.c_uint64), ("eval_gates", C.c_int32)]
 
@@ -59,6 +76,7 @@ EXPORTS = (
     "pgw_compile_expression", "pgw_validate_expression", "pgw_ruleset_create", "pgw_lists_add", "pgw_geoip_load",
     "pgw_ruleset_finalize", "pgw_evaluate_batch", "pgw_evaluate_batch_host", "pgw_geoip_lookup_batch",
     "pgw_services_set", "pgw_evaluate_batch_routed", "pgw_evaluate_batch_routed_host",
+    "pgw_queue_create", "pgw_queue_evaluate", "pgw_queue_submit", "pgw_queue_get_stats", "pgw_queue_destroy", "pgw_shape_request",
     "pgw_host_alloc", "pgw_host_free", "pgw_ruleset_info", "pgw_ruleset_set_profiling", "pgw_ruleset_profile",
     "pgw_ruleset_describe", "pgw_ruleset_destroy", "pgw_last_error",
 )
@@ -81,6 +99,12 @@ def declare(lib, prefix="pgw_"):
         "services_set": (C.c_int, [p, C.POINTER(ServiceDesc), C.c_uint32, C.c_char_p, C.c_size_t]),
         "evaluate_batch_routed": (C.c_int, [p, C.POINTER(Batch), p, p, p]),
         "evaluate_batch_routed_host": (C.c_int, [p, C.POINTER(Batch), p, p]),
+        "queue_create": (C.c_int, [p, C.c_uint32, C.c_uint32, C.POINTER(p), C.c_char_p, C.c_size_t]),
+        "queue_evaluate": (C.c_int, [p, C.POINTER(Request), C.POINTER(C.c_uint32), C.POINTER(C.c_uint16)]),
+        "queue_submit": (C.c_int, [p, C.POINTER(Request), DONE_FN, p]),
+        "queue_get_stats": (C.c_int, [p, C.POINTER(QueueStats)]),
+        "queue_destroy": (None, [p]),
+        "shape_request": (C.c_int, [C.POINTER(Request), C.POINTER(C.c_char_p), C.POINTER(C.c_size_t)]),
         "geoip_lookup_batch": (C.c_int, [p, p, p, C.c_uint32, p, p, p]),
         "host_alloc": (p, [C.c_size_t]),
         "host_free": (None, [p]),

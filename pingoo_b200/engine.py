@@ -162,3 +162,71 @@ def decode_verdict(v: int):
     """(action, rule_index or None) from a verdict word."""
     rule = int(v) >> 2
     return int(v) & 3, (None if rule == _ffi.NO_RULE else rule)
+
+
+def make_request(host=b"", url=b"", path=b"", method=b"GET", user_agent=b"", ip="0.0.0.0", remote_port=0, flags=0) -> _ffi.Request:
+    """A pgw_request from raw byte strings (what the listener has in hand before any shaping)."""
+    import ipaddress
+
+    def b(x):
+        return x if isinstance(x, bytes) else str(x).encode("utf-8", "surrogateescape")
+
+    r = _ffi.Request()
+    for name, val in (("host", host), ("url", url), ("path", path), ("method", method), ("user_agent", user_agent)):
+        raw = b(val)
+        setattr(r, name, raw)
+        setattr(r, name + "_len", len(raw))
+    a = ipaddress.ip_address(ip)
+    packed = a.packed + (b"\0" * 12 if a.version == 4 else b"")
+    r.ip = (C.c_uint8 * 16)(*packed)
+    r.ip_is_v6 = 0 if a.version == 4 else 1
+    r.remote_port = int(remote_port)
+    r.flags = int(flags)
+    return r
+
+
+def shape_request(req: _ffi.Request):
+    """The listener's shaping of one request (no device needed): dict of the five rule-visible strings."""
+    lib = _ffi.load()
+    ptr = (C.c_char_p * 5)()
+    ln = (C.c_size_t * 5)()
+    raw = (C.c_void_p * 5)()
+    if lib.pgw_shape_request(C.byref(req), C.cast(raw, C.POINTER(C.c_char_p)), ln):
+        raise Error("pgw_shape_request failed")
+    return {f: C.string_at(raw[i], ln[i]) if ln[i] else b"" for i, f in enumerate(FIELDS)}
+
+
+class RequestQueue:
+    """Micro-batching front of a WafEngine (include/pingoo_waf.h: pgw_queue_*): `evaluate` is thread-safe and blocks until
+    the batch that contains the request has been evaluated (ctypes releases the GIL while it waits)."""
+
+    def __init__(self, engine: WafEngine, max_batch: int = 4096, max_delay_us: int = 200):
+        self._engine = engine  # keeps the ruleset alive
+        self._lib = engine._lib
+        self._q = C.c_void_p()
+        err = C.create_string_buffer(256)
+        if self._lib.pgw_queue_create(engine._h, max_batch, max_delay_us, C.byref(self._q), err, len(err)):
+            raise Error(err.value.decode(errors="replace"))
+
+    def evaluate(self, req: _ffi.Request):
+        v, s = C.c_uint32(0), C.c_uint16(0)
+        rc = self._lib.pgw_queue_evaluate(self._q, C.byref(req), C.byref(v), C.byref(s))
+        if rc:
+            raise Error(f"pgw_queue_evaluate failed ({rc}): " + self._lib.pgw_last_error().decode(errors="replace"))
+        return v.value, s.value
+
+    def stats(self) -> _ffi.QueueStats:
+        st = _ffi.QueueStats()
+        self._lib.pgw_queue_get_stats(self._q, C.byref(st))
+        return st
+
+    def close(self):
+        if getattr(self, "_q", None) and self._q.value:
+            self._lib.pgw_queue_destroy(self._q)
+            self._q = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
