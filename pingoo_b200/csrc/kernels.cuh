@@ -19,7 +19,7 @@ constexpr int kRowsPerLane = 2;     // atom bitmaps per lane: the request being 
 constexpr uint32_t kClaim = 32;     // requests a warp claims from the global counter at a time
 
 constexpr uint32_t kMaxConstNs = 16;
-constexpr uint32_t kMaxConstUnits = 24;  // rule sets with more scan units run on the lane path
+constexpr uint32_t kMaxConstUnits = 64;  // rule sets with more scan units run on the lane path (parameter block stays under 8 KB)
 
 struct KParams {
     // ---- batch (device pointers, SoA) ----
