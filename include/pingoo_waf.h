@@ -179,6 +179,13 @@ void pgw_queue_destroy(pgw_queue* q);
 /* The shaping alone (no device needed): pointers into the request's own strings, Field order host,url,path,method,user_agent. */
 int pgw_shape_request(const pgw_request* req, const char* out_ptr[5], size_t out_len[5]);
 
+/* ---- captcha client id for a batch -------------------------------------------------------------
+ * generate_captcha_client_id (pingoo/captcha.rs:409-421), called per request at http_listener.rs:167:
+ * base64url-no-pad(SHA-256(ip octets (4 or 16) || user_agent || host)) = 43 characters.  `batch` holds DEVICE pointers
+ * on the current device (ip, ip_is_v6, user_agent, host are read); out44_dev receives n x 44 bytes (43 characters and
+ * a terminating 0).  No ruleset is involved. */
+int pgw_captcha_client_id_batch(const pgw_batch* batch, uint8_t* out44_dev, void* stream);
+
 int pgw_ruleset_info(const pgw_ruleset* rs, pgw_info* out);
 /* Measurement hook (no reference counterpart): while enabled, every batch evaluated on the default kernel path is
  * bracketed by CUDA events around its scan kernel, on the stream the kernel is launched on (a ring of 256 pairs).

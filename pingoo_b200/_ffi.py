@@ -76,7 +76,7 @@ EXPORTS = (
     "pgw_compile_expression", "pgw_validate_expression", "pgw_ruleset_create", "pgw_lists_add", "pgw_geoip_load",
     "pgw_ruleset_finalize", "pgw_evaluate_batch", "pgw_evaluate_batch_host", "pgw_geoip_lookup_batch",
     "pgw_services_set", "pgw_evaluate_batch_routed", "pgw_evaluate_batch_routed_host",
-    "pgw_queue_create", "pgw_queue_evaluate", "pgw_queue_submit", "pgw_queue_get_stats", "pgw_queue_destroy", "pgw_shape_request",
+    "pgw_captcha_client_id_batch", "pgw_queue_create", "pgw_queue_evaluate", "pgw_queue_submit", "pgw_queue_get_stats", "pgw_queue_destroy", "pgw_shape_request",
     "pgw_host_alloc", "pgw_host_free", "pgw_ruleset_info", "pgw_ruleset_set_profiling", "pgw_ruleset_profile",
     "pgw_ruleset_describe", "pgw_ruleset_destroy", "pgw_last_error",
 )
@@ -99,6 +99,7 @@ def declare(lib, prefix="pgw_"):
         "services_set": (C.c_int, [p, C.POINTER(ServiceDesc), C.c_uint32, C.c_char_p, C.c_size_t]),
         "evaluate_batch_routed": (C.c_int, [p, C.POINTER(Batch), p, p, p]),
         "evaluate_batch_routed_host": (C.c_int, [p, C.POINTER(Batch), p, p]),
+        "captcha_client_id_batch": (C.c_int, [C.POINTER(Batch), p, p]),
         "queue_create": (C.c_int, [p, C.c_uint32, C.c_uint32, C.POINTER(p), C.c_char_p, C.c_size_t]),
         "queue_evaluate": (C.c_int, [p, C.POINTER(Request), C.POINTER(C.c_uint32), C.POINTER(C.c_uint16)]),
         "queue_submit": (C.c_int, [p, C.POINTER(Request), DONE_FN, p]),

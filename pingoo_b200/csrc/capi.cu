@@ -501,6 +501,17 @@ int pgw_geoip_lookup_batch(const pgw_ruleset* rs, const uint8_t* ip, const uint8
     return 0;
 }
 
+int pgw_captcha_client_id_batch(const pgw_batch* batch, uint8_t* out44_dev, void* stream) {
+    if (!batch) return fail("null argument", nullptr, 0);
+    if (batch->n == 0) return 0;
+    if (!out44_dev || !batch->ip || !batch->ip_is_v6 || !batch->user_agent.offsets || !batch->host.offsets)
+        return fail("client id needs ip, ip_is_v6, user_agent and host columns", nullptr, 0);
+    if (const char* m = client_id_launch(batch->ip, batch->ip_is_v6, batch->user_agent.bytes, batch->user_agent.offsets, batch->host.bytes,
+                                        batch->host.offsets, batch->n, out44_dev, stream))
+        return fail(std::string("CUDA launch failed: ") + m, nullptr, 0);
+    return 0;
+}
+
 void* pgw_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;

@@ -108,6 +108,8 @@ constexpr uint32_t kFieldCounters = 64;
 size_t waf_field_smem_bytes(uint32_t image_bytes, uint32_t n_units);
 const char* waf_field_launch(const KParams& p, uint32_t* rows, uint32_t* counters, int sm_count, size_t smem_bytes, void* stream,
                              cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);  // optional events around the scan kernel
+const char* client_id_launch(const uint8_t* ip, const uint8_t* is_v6, const uint8_t* ua_bytes, const uint32_t* ua_off, const uint8_t* host_bytes,
+                             const uint32_t* host_off, uint32_t n, uint8_t* out44, void* stream);
 const char* geoip_launch(const KParams& p, const uint8_t* ip, const uint8_t* is_v6, uint32_t n, uint32_t* asn_out,
                          uint16_t* country_out, void* stream);
 const char* waf_configure(int device, size_t* max_smem_optin, int* sm_count);

@@ -152,6 +152,11 @@ class WafEngine:
         if self._lib.pgw_evaluate_batch_routed(self._h, C.byref(cbatch), verdict_tensor.data_ptr(), service_tensor.data_ptr(), stream):
             raise Error(self._lib.pgw_last_error().decode(errors="replace"))
 
+    def client_ids_device(self, cbatch: _ffi.Batch, out_tensor, stream: int = 0):
+        """generate_captcha_client_id for every request of a device-resident batch: out_tensor is uint8 [n, 44]."""
+        if self._lib.pgw_captcha_client_id_batch(C.byref(cbatch), out_tensor.data_ptr(), stream):
+            raise Error(self._lib.pgw_last_error().decode(errors="replace"))
+
     def geoip_lookup_device(self, ip_t, v6_t, asn_t, cc_t, stream: int = 0):
         n = ip_t.shape[0]
         if self._lib.pgw_geoip_lookup_batch(self._h, ip_t.data_ptr(), v6_t.data_ptr(), n, asn_t.data_ptr(), cc_t.data_ptr(), stream):
