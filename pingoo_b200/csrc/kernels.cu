@@ -1131,7 +1131,8 @@ __global__ void __launch_bounds__(kStreamThreads, 2) waf_stream_scan_kernel(cons
 #define PGW_FS_THREADS 1024
 #endif
 constexpr int kFsThreads = PGW_FS_THREADS;
-constexpr uint32_t kFsSlotStride = kFsThreads * 4u;  // per-lane slots: request index, latch register, last fired state
+constexpr uint32_t kFsSlotStride = kFsThreads * 4u;  // per-lane slots: request index, latch register, last fired state, next request
+constexpr uint32_t kFsTicket = 128;    // requests per atomic claim (four pools)
 constexpr uint32_t kFsPoolBytes = 144;  // 33 offsets of a claimed pool (+pad), two buffers per warp
 
 __device__ __forceinline__ void red_or(uint32_t* addr, uint32_t v) { asm volatile("red.global.or.b32 [%0], %1;" ::"l"(addr), "r"(v) : "memory"); }
@@ -1247,21 +1248,26 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
         uint32_t ticket = 0;
         bool tk_valid = false, ah_valid = false;
         auto issue_ticket = [&]() {
-            if (lane == 0) ticket = atomicAdd(ctr, 32u);
+            if (lane == 0) ticket = atomicAdd(ctr, kFsTicket);  // a ticket covers kFsTicket / 32 consecutive pools
             tk_valid = true;
         };
+        uint32_t more = 0;  // end of the current ticket's range (pools still to take from it start at ah_base + 32)
         auto claim_ahead = [&]() {
             ah_valid = false;
-            if (!tk_valid) return;
-            const uint32_t b = __shfl_sync(FULL, ticket, 0);
-            if (b >= N) { tk_valid = false; return; }
+            uint32_t b = ah_base + 32u;
+            if (b >= more) {
+                if (!tk_valid) return;
+                b = __shfl_sync(FULL, ticket, 0);
+                if (b >= N) { tk_valid = false; return; }
+                more = min(b + kFsTicket, N);
+                issue_ticket();
+            }
             ah_base = b;
             const uint32_t dst = a_pool + (pb ^ 1u) * kFsPoolBytes;
             cp_async4(dst + lane * 4u, off + min(b + lane, N));
             if (lane == 0) cp_async4(dst + 128u, off + min(b + 32u, N));
             asm volatile("cp.async.commit_group;" ::: "memory");
             ah_valid = true;
-            issue_ticket();
         };
         __syncwarp();
         if (N) issue_ticket();
@@ -1270,25 +1276,28 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
         bool have = false, pend = false;
         // hot per-lane state lives in registers; what only the (rare) event paths need -- request index, latch register,
         // last fired state -- lives in this lane's shared-memory slots
-        uint32_t base = 0, skip = 0, nskip = 0, end = 0, state = 0;
-        uint32_t q_req = 0;
+        uint32_t base = 0, skip = 0, end = 0, state = 0;
         uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
 
         for (;;) {
             // ---- rotate: next chunk of the current string, or the first chunk of the string claimed last iteration ----
-            if (have || pend) {
-                base += 16u;  // a claim leaves `base` one chunk before the string's first one
-                cur = nxt;
-            }
             skip = 0;
             if (pend) {
-                skip = nskip;
+                // a claim leaves `base` one chunk before the string's first one, its low four bits carry the offset of the
+                // first byte in that chunk; the request index waits in the lane's fourth slot word
+                skip = base & 15u;
+                base &= ~15u;
                 state = D0;
-                sts_u32(a_slot, q_req);
+                sts_u32(a_slot, lds_u32_v(a_slot + 3u * kFsSlotStride));
                 sts_u32(a_slot + kFsSlotStride, 0u);
                 sts_u32(a_slot + 2u * kFsSlotStride, 0xFFFFFFFFu);
                 have = true;
                 pend = false;
+                base += 16u;
+                cur = nxt;
+            } else if (have) {
+                base += 16u;
+                cur = nxt;
             }
             // everything this iteration's walk needs from (base, end, skip) is derived here, so that a lane on its last
             // chunk can overwrite them with its next string right away
@@ -1317,12 +1326,11 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                     const uint32_t sa = a_pool + pb * kFsPoolBytes + (idx & 31u) * 4u;
                     const uint32_t s0 = lds_u32_v(sa), e0 = lds_u32_v(sa + 4u);
                     if (e0 > s0) {  // empty fields are left to the epilogue kernel
-                        q_req = idx;
+                        sts_u32(a_slot + 3u * kFsSlotStride, idx);
                         pend = true;
                         end = e0;
                         ld_off = s0 & ~15u;
-                        base = ld_off - 16u;
-                        nskip = s0 & 15u;
+                        base = (ld_off - 16u) | (s0 & 15u);
                         do_ld = true;
                     }
                 }
@@ -1587,7 +1595,7 @@ const char* waf_configure(int device, size_t* max_smem_optin, int* sm_count) {
 }
 
 size_t waf_field_smem_bytes(uint32_t image_bytes, uint32_t n_units) {
-    return 256 + r16(image_bytes) + r16(n_units * (uint32_t)sizeof(UnitDesc)) + 64 + (kFsThreads / 32) * 2 * kFsPoolBytes + 3 * kFsSlotStride;
+    return 256 + r16(image_bytes) + r16(n_units * (uint32_t)sizeof(UnitDesc)) + 64 + (kFsThreads / 32) * 2 * kFsPoolBytes + 4 * kFsSlotStride;
 }
 
 const char* waf_field_launch(const KParams& p, uint32_t* rows, uint32_t* counters, int sm_count, size_t smem_bytes, void* stream, cudaEvent_t ev0,
