@@ -1132,7 +1132,10 @@ __global__ void __launch_bounds__(kStreamThreads, 2) waf_stream_scan_kernel(cons
 #endif
 constexpr int kFsThreads = PGW_FS_THREADS;
 constexpr uint32_t kFsSlotStride = kFsThreads * 4u;  // per-lane slots: request index, latch register, last fired state, next request
-constexpr uint32_t kFsTicket = 128;    // requests per atomic claim (four pools)
+#ifndef PGW_FS_TICKET
+#define PGW_FS_TICKET 64
+#endif
+constexpr uint32_t kFsTicket = PGW_FS_TICKET;  // requests per atomic claim (two 32-request pools: 128 and 256 measured worse, tail imbalance)
 constexpr uint32_t kFsPoolBytes = 144;  // 33 offsets of a claimed pool (+pad), two buffers per warp
 
 __device__ __forceinline__ void red_or(uint32_t* addr, uint32_t v) { asm volatile("red.global.or.b32 [%0], %1;" ::"l"(addr), "r"(v) : "memory"); }
