@@ -170,3 +170,42 @@ def test_alternative_kernel_paths_agree(monkeypatch, path):
     want_v, want_s = Oracle(rules, lists, services=svcs).evaluate_routed(batch, threads=THREADS)
     got_v, got_s = WafEngine(rules, lists, device=0, services=svcs).evaluate_host_routed(batch)
     assert np.array_equal(got_v, want_v) and np.array_equal(got_s, want_s)
+
+
+def test_tiny_batches_and_concurrent_streams():
+    """Edge sizes (0, 1, 31, 32, 33 requests) and several host threads evaluating on their own streams against one shared
+    ruleset (many connection tasks evaluate concurrently against the same Arc'd rules)."""
+    import threading
+
+    import torch
+
+    rules, lists, mmdb, batch, g = scenarios.config2_sample(4_000)
+    eng = WafEngine(rules, device=0)
+    want = Oracle(rules).evaluate(batch, threads=THREADS)
+    for n in (0, 1, 31, 32, 33, 1000):
+        sub = batch.slice(0, n)
+        assert np.array_equal(eng.evaluate_host(sub), want[:n]), n
+    parts = [batch.slice(i * 1000, (i + 1) * 1000) for i in range(4)]
+    outs = [None] * 4
+    errs = []
+
+    def work(i):
+        try:
+            torch.cuda.set_device(0)
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                t, cb = eng.to_device(parts[i])
+                o = torch.empty(parts[i].n, dtype=torch.int32, device="cuda")
+                for _ in range(20):
+                    eng.evaluate_device(cb, o, st.cuda_stream)
+                st.synchronize()
+                outs[i] = o.cpu().numpy().view(np.uint32)
+        except Exception as e:  # surfaced below
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for i in range(4):
+        assert np.array_equal(outs[i], want[i * 1000:(i + 1) * 1000]), i
