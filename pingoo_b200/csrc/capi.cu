@@ -453,18 +453,19 @@ int pgw_evaluate_batch_routed_host(pgw_ruleset* rs, const pgw_batch* b, uint32_t
     };
     std::string e;
     uint32_t k = 0;
+    // the small fixed-width columns go first, whole (a dozen tiny copies per slice would cost more in call overhead than
+    // they move); only the byte columns -- 90 % of the traffic -- are sliced
+    for (int f = 0; f < 5; ++f)
+        if (H.field_slot[f] >= 0) up(dc[f]->offsets, hc[f]->offsets, 0, ((size_t)n + 1) * 4);
+    if (need_ip) { up(d.ip, b->ip, 0, (size_t)n * 16); up(d.ip_is_v6, b->ip_is_v6, 0, n); }
+    if (H.needs_port) up(d.remote_port, b->remote_port, 0, (size_t)n * 4);
+    if (geo_cols) { up(d.asn, b->asn, 0, (size_t)n * 8); up(d.country, b->country, 0, (size_t)n * 2); }
+    if (b->flags) up(d.flags, b->flags, 0, n);
     for (uint32_t a = 0; a < n; a += per, ++k) {
         const uint32_t z = a + per < n ? a + per : n, m = z - a;
-        for (int f = 0; f < 5; ++f) {
-            if (H.field_slot[f] < 0) continue;
-            // the slice's offsets (its first entry is the previous slice's last one: copied once)
-            up(dc[f]->offsets, hc[f]->offsets, a ? ((size_t)a + 1) * 4 : 0, a ? (size_t)m * 4 : ((size_t)m + 1) * 4);
-            if ((H.scanned_fields_mask >> f) & 1) up(dc[f]->bytes, hc[f]->bytes, hc[f]->offsets[a], (size_t)hc[f]->offsets[z] - hc[f]->offsets[a]);
-        }
-        if (need_ip) { up(d.ip, b->ip, (size_t)a * 16, (size_t)m * 16); up(d.ip_is_v6, b->ip_is_v6, a, m); }
-        if (H.needs_port) up(d.remote_port, b->remote_port, (size_t)a * 4, (size_t)m * 4);
-        if (geo_cols) { up(d.asn, b->asn, (size_t)a * 8, (size_t)m * 8); up(d.country, b->country, (size_t)a * 2, (size_t)m * 2); }
-        if (b->flags) up(d.flags, b->flags, a, m);
+        for (int f = 0; f < 5; ++f)
+            if (H.field_slot[f] >= 0 && ((H.scanned_fields_mask >> f) & 1))
+                up(dc[f]->bytes, hc[f]->bytes, hc[f]->offsets[a], (size_t)hc[f]->offsets[z] - hc[f]->offsets[a]);
         if (ce != cudaSuccess) break;
         if ((ce = cudaEventRecord(rs->slice_ready[k], cs)) != cudaSuccess) break;
         if ((ce = cudaStreamWaitEvent(s, rs->slice_ready[k], 0)) != cudaSuccess) break;

@@ -88,10 +88,14 @@ def test_threads_through_the_queue_match_the_oracle():
         res_s[i] = service
         left.release()
 
+    q.close()
+    # a long deadline and a small batch: the (slow) Python submitter fills batches before the deadline fires
+    q = RequestQueue(eng, max_batch=64, max_delay_us=200_000)
     for i in range(n):
         assert eng._lib.pgw_queue_submit(q._q, C.byref(reqs[i]), done, C.c_void_p(i)) == 0
     for _ in range(n):
         assert left.acquire(timeout=30)
     assert np.array_equal(res_v, want_v) and np.array_equal(res_s, want_s)
-    assert q.stats().full_flushes >= 1
+    st = q.stats()
+    assert st.requests == n and st.full_flushes >= n // 64 - 1 and st.largest_batch == 64
     q.close()
