@@ -1,26 +1,31 @@
 // sm_100a kernels for the batched WAF verdict path.
 //
-// One fused persistent kernel replaces, per batch, the reference's per-request
+// Per batch they replace the reference's per-request
 //   ctx build (http_listener.rs:239-249) -> rule loop (http_listener.rs:251-264)
-//   -> bel::Program::execute (pingoo/rules.rs:36-52) -> regex / list / geoip work.
+//   -> bel::Program::execute (pingoo/rules.rs:36-52) -> regex / list / geoip work -> service routing (:266-272).
 //
-// Work decomposition (streaming, no tiles, no block-level barriers after set-up)
-//   Each lane owns one request at a time and walks its scan units (one DFA over one string field)
-//   in sequence; a warp claims kClaim requests at a time from a global counter and its lanes take
-//   them as they become free, so a long URL only delays its own lane.
-// Data movement
-//   request bytes: each lane streams its field with 128-bit ld.global.nc loads; the chunk for the
-//     next iteration (same field, next field, or next request) is issued a full iteration ahead;
-//   DFA tables: class maps + the rows of the shallow ("hot") states of every DFA are staged once
-//     per CTA into shared memory by TMA bulk copies (cp.async.bulk + mbarrier); deeper states are
-//     read from the full tables in global memory (L1/L2);
-//   atom hit bits: two private bitmap rows per lane in shared memory (no atomics).
-// Events (rare): DFA accept states carry event lists: FIRE atom / SET, TEST, CLEAR of a per-unit
-//   latch register (gap-split patterns such as `<tag[^>]*>`, see regex.hpp).
-// Epilogue: finished requests wait in the lane's second row and are flushed a warp at a time:
-//   list/int/country/GeoIP predicates, gates, then verdict = first matching rule with a terminal
-//   action; a request whose atom vector equals the expected vector takes the precomputed verdict,
-//   otherwise only rules that reference a changed atom are evaluated.
+// File map
+//   helpers                    shared-window loads/stores (explicit ld.shared: no generic-address conversion per access),
+//                              mbarrier + TMA bulk copy, event lists, rule bytecode, longest-prefix lookup
+//   request_epilogue_t         per-request predicates outside the byte scan, gates, verdict and service
+//   waf_verdict_kernel         "lane" path (PGW_KERNEL=lane; also the fall-back beyond kMaxConstUnits scan units):
+//                              request-major persistent kernel, bitmaps in shared memory, epilogue fused
+//   waf_stream_scan_kernel     "stream" path (PGW_KERNEL=stream): coalesced 16-byte segments, speculated start states
+//   waf_field_scan_kernel      DEFAULT path: unit-major, lane-owned strings, pooled claims, bitmaps in global memory
+//   waf_epilogue_kernel        verdicts for the field / stream paths (one thread per request, warp-shared evaluation)
+//   geoip_lookup_kernel        GeoipDB::lookup for a batch (geoip.rs:73-91)
+//   captcha_client_id_kernel   generate_captcha_client_id for a batch (captcha.rs:409-421)
+//   launch wrappers            host-callable, no CUDA types in their signatures beyond the stream handle
+//
+// Common to all scan paths
+//   DFA tables: class maps + the rows of the shallow ("hot") states of every DFA are staged once per CTA into shared
+//     memory by TMA bulk copies (cp.async.bulk + mbarrier); transitions into deeper states lead to a trap row and the
+//     word is re-walked on the full table in global memory (L1/L2);
+//   request bytes: 128-bit ld.global.nc loads issued one iteration ahead of their use;
+//   events (rare): accepting states carry event lists -- FIRE atom / SET, TEST, CLEAR of a per-scan latch register
+//     (gap-split patterns such as `<tag[^>]*>`, see regex.hpp);
+//   verdict = first matching rule with a terminal action; a request whose atom vector equals the expected vector takes a
+//     precomputed verdict, one deviating atom a tabulated one, otherwise only rules that mention a deviating atom run.
 #include <cuda_runtime.h>
 
 #include <cstddef>
