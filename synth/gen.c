@@ -146,8 +146,8 @@ gen_t* synth_create(uint64_t seed) {
     char tmp[512];
     for (int i = 0; i < 1024; ++i) {
         size_t n = 0;
-        if (rng_below(&r, 3) == 0) { n += word(&r, tmp + n, 1, 2); tmp[n++] = '.'; }
-        n += word(&r, tmp + n, 2, 6);
+        if (rng_below(&r, 2) == 0) { n += word(&r, tmp + n, 1, 3); tmp[n++] = '.'; }
+        n += word(&r, tmp + n, 3, 9);
         const char* t = TLD[rng_below(&r, 8)];
         memcpy(tmp + n, t, strlen(t));
         n += strlen(t);
@@ -156,11 +156,11 @@ gen_t* synth_create(uint64_t seed) {
     g->paths = (str_t*)malloc(sizeof(str_t) * 65536);
     for (int i = 0; i < 65536; ++i) {
         size_t n = 0;
-        int segs = 1 + (int)rng_below(&r, 6);
-        for (int s = 0; s < segs; ++s) {
+        int segs = 2 + (int)rng_below(&r, 8);
+        for (int s = 0; s < segs && n < 140; ++s) {
             tmp[n++] = '/';
             if (rng_below(&r, 5) == 0) n += (size_t)sprintf(tmp + n, "%u", rng_below(&r, 100000));
-            else n += word(&r, tmp + n, 1, 7);
+            else n += word(&r, tmp + n, 1, 8);
         }
         const char* e = EXT[rng_below(&r, 10)];
         memcpy(tmp + n, e, strlen(e));
@@ -251,10 +251,10 @@ static void gen_one(gen_t* g, uint64_t index, buf_t* host, buf_t* url, buf_t* pa
         first = 0;
         buf_put(url, key->s, key->len);
         buf_put(url, "=", 1);
-        /* log-normal(mu=3.55, sigma=0.7): mean ~ 44 */
+        /* log-normal(mu=3.72, sigma=0.7): mean ~ 52 */
         double u1 = rng_unit(&r), u2 = rng_unit(&r);
         double z = sqrt(-2.0 * log(u1 + 1e-300)) * cos(6.283185307179586 * u2);
-        int vl = (int)exp(3.55 + 0.7 * z);
+        int vl = (int)exp(3.72 + 0.7 * z);
         if (vl < 1) vl = 1;
         if (vl > 600) vl = 600;
         for (int i = 0; i < vl; ++i) {
@@ -290,6 +290,7 @@ static void gen_one(gen_t* g, uint64_t index, buf_t* host, buf_t* url, buf_t* pa
         uint32_t t = fam < 70 ? rng_below(&r, 6) : 6 + rng_below(&r, (uint32_t)N_UA_T - 6);
         uint32_t band = rng_below(&r, 4);
         int n = snprintf(tmp, sizeof tmp, UA_T[t], 90 + band * 10 + rng_below(&r, 10), rng_below(&r, 7000), rng_below(&r, 200));
+        if (n > 0 && n < 230) n += snprintf(tmp + n, sizeof tmp - (size_t)n, " Build/%06u.%05u", rng_below(&r, 1000000), rng_below(&r, 100000));
         if (n > 250) n = 250;
         buf_put(ua, tmp, (size_t)n);
     }

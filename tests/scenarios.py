@@ -105,9 +105,16 @@ def services(n=20_000, catch_all=True):
     """WAF rules of config 2 plus a service table (http_listener.rs:266-272): routes from the docs (two of the documented
     examples refer to names that do not exist and therefore never match), a regex route, a list route, a non-bool route."""
     rules, payloads, _ = synth.make_ruleset(128, config_id=2)
-    lists = {"static_hosts": (ListType.String, b"mionliwasa.org\ngaonta.net,cdn\n")}
+    # host names come from the generator's vocabulary: take frequent ones so that every live route sees traffic
+    from collections import Counter
+
+    probe = synth.RequestStream(config_id=2, payloads=payloads).generate(7_000, 3_000)
+    common = [h for h, _ in Counter(probe.field("host", i) for i in range(probe.n)).most_common(40)]
+    plain = [h for h in common if h.count(b".") == 1][:2]
+    sub = [h.split(b".")[0] + b"." for h in common if h.count(b".") >= 2][:2]
+    lists = {"static_hosts": (ListType.String, plain[0] + b"\n" + plain[1] + b",cdn\n")}
     svcs = [
-        Service("api", 'http_request.host.starts_with("be.") || http_request.host.starts_with("lo.")'),  # getting_started.md:38 shape
+        Service("api", 'http_request.host.starts_with("%s") || http_request.host.starts_with("%s")' % (sub[0].decode(), sub[1].decode())),  # getting_started.md:38 shape
         Service("doc_unknown_variable", 'host.starts_with("api")'),               # docs/services.md:18: `host` is not a variable
         Service("doc_method_on_map", 'http_request.starts_with("/api")'),         # docs/configuration.md:53
         Service("images", 'http_request.path.ends_with(".png") || http_request.path.ends_with(".svg")'),
