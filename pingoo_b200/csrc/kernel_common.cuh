@@ -1,0 +1,306 @@
+// Part of kernels.cu (included inside namespace pgw { namespace { ... } }, one translation unit: device functions are
+// not linked across files).  Helpers shared by every kernel path: shared-window accessors, mbarrier / TMA bulk copy, event lists,
+// rule bytecode, longest-prefix lookup and the per-request epilogue.
+
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ uint4 ld_nc_v4(const uint8_t* p) {
+    uint4 r;
+#if PGW_LD_MODE == 1
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+#elif PGW_LD_MODE == 2
+    asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+#else
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+#endif
+    return r;
+}
+
+// Apply the events of CSR row `row` (sorted FIRE, TEST, CLEAR, SET) to the lane's bitmap and latch register.
+// Returns true if every event was a plain FIRE (idempotent: the caller may skip an immediate repeat).
+__device__ __noinline__ bool run_events(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ events, uint32_t row,
+                                        uint32_t* bits, uint32_t stride, uint32_t* latch) {
+    uint32_t a = __ldg(idx + row), b = __ldg(idx + row + 1);
+    bool pure = true;
+    uint32_t l = *latch;
+    for (uint32_t i = a; i < b; ++i) {
+        const uint32_t e = __ldg(events + i);
+        const uint32_t kind = e >> kEvKindShift, lb = 1u << ((e >> kEvLatchShift) & 31u), at = e & kEvAtomMask;
+        if (kind == 0u || (kind == 1u && (l & lb))) bits[(at >> 5) * stride] |= 1u << (at & 31);
+        else if (kind == 2u) l &= ~lb;
+        else if (kind == 3u) l |= lb;
+        pure &= kind == 0u;
+    }
+    *latch = l;
+    return pure;
+}
+
+__device__ __forceinline__ bool eval_rule(const uint16_t* __restrict__ code, uint32_t a, uint32_t b, const uint32_t* row, uint32_t stride) {
+    uint32_t st = 0;
+    for (uint32_t i = a; i < b; ++i) {
+        uint32_t op = __ldg(code + i);
+        if (op < 0x4000u) st = (st << 1) | ((row[(op >> 5) * stride] >> (op & 31)) & 1u);
+        else if (op == OP_NOT) st ^= 1u;
+        else if (op == OP_AND) st = ((st >> 1) & ~1u) | (st & (st >> 1) & 1u);
+        else if (op == OP_OR) st = ((st >> 1) & ~1u) | ((st | (st >> 1)) & 1u);
+        else if (op == OP_PUSH0) st <<= 1;
+        else st = (st << 1) | 1u;
+    }
+    return st & 1u;
+}
+
+__device__ __forceinline__ uint32_t lpm_lookup(const KParams& p, const uint8_t* ip16, bool v6) {
+    if (!v6) {
+        uint32_t w = *reinterpret_cast<const uint32_t*>(ip16);
+        uint32_t a = __byte_perm(w, 0, 0x0123);  // network order -> host integer
+        uint32_t e = __ldg(p.dir24 + (a >> 8));
+        if (e & 0x80000000u) e = __ldg(p.tbl8 + ((e & 0x7FFFFFFFu) << 8) + (a & 0xFFu));
+        return e;
+    }
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(ip16);
+    uint64_t hi = ((uint64_t)__byte_perm(w[0], 0, 0x0123) << 32) | __byte_perm(w[1], 0, 0x0123);
+    uint64_t lo = ((uint64_t)__byte_perm(w[2], 0, 0x0123) << 32) | __byte_perm(w[3], 0, 0x0123);
+    // last range whose start <= (hi,lo); range 0 starts at 0
+    uint32_t l = 0, r = p.n_v6;
+    while (r - l > 1) {
+        uint32_t m = (l + r) >> 1;
+        uint64_t mh = __ldg(p.v6_hi + m), ml = __ldg(p.v6_lo + m);
+        bool le = mh < hi || (mh == hi && ml <= lo);
+        if (le) l = m;
+        else r = m;
+    }
+    return __ldg(p.v6_leaf + l);
+}
+
+// Per-request predicates outside the byte scan + the verdict (http_listener.rs:196-264).
+// `row[w * stride]` is the request's atom bitmap (scan atoms already set).
+// WARP: called by all 32 lanes of a converged warp (`valid` false for lanes past the end of the batch, which shadow the
+// last request without storing anything): requests of the warp that deviate from the expected atom vector in the same
+// way are evaluated once -- verdict and service are functions of the deviation and of `captcha_verified` alone -- and
+// the result is shared by shuffle.
+template <bool WARP>
+__device__ __forceinline__ void request_epilogue_t(const KParams& p, uint32_t r, uint32_t* row, uint32_t stride, bool valid) {
+    const uint32_t Aw = p.atom_words;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t flags = p.flags ? p.flags[r] : 0u;
+    int64_t asn = 0;
+    uint32_t country = (uint32_t)'X' | ((uint32_t)'X' << 8);
+    uint32_t set_mask = 0;
+    if (p.need_lpm) {
+        const uint8_t* ip16 = p.ip + (size_t)r * 16;
+        const bool v6 = p.is_v6[r] != 0;
+        const LpmLeaf lf = p.leaves[lpm_lookup(p, ip16, v6)];
+        set_mask = lf.set_mask;
+        if (p.geo_loaded && p.asn == nullptr) {
+            // geoip.rs:74-76: loopback / multicast are never looked up
+            bool skip;
+            if (!v6) skip = ip16[0] == 127 || (ip16[0] >> 4) == 0xE;
+            else {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(ip16);
+                skip = ip16[0] == 0xFF || (w[0] == 0 && w[1] == 0 && w[2] == 0 && w[3] == 0x01000000u);
+            }
+            if (!skip) { asn = lf.asn; country = lf.country; }
+        }
+    }
+    if (p.asn) asn = p.asn[r];
+    if (p.country) country = p.country[r];
+
+    for (uint32_t i = 0; i < p.n_ns; ++i) {
+        const NsAtom a = p.n_ns <= kMaxConstNs ? p.nsd[i] : p.ns[i];
+        bool v = false;
+        if (a.kind == 1 || a.kind == 2) {  // INT_CMP / INT_SET
+            int64_t x;
+            if (a.feat == 0) x = p.port ? (int64_t)p.port[r] : 0;
+            else if (a.feat == 1) x = asn;
+            else {
+                const uint32_t* o = p.off[a.feat - 2] + r;
+                x = (int64_t)(o[1] - o[0]);
+            }
+            if (a.kind == 1) {
+                switch (a.op) {
+                    case 0: v = x == a.cval; break;
+                    case 1: v = x != a.cval; break;
+                    case 2: v = x < a.cval; break;
+                    case 3: v = x <= a.cval; break;
+                    case 4: v = x > a.cval; break;
+                    default: v = x >= a.cval; break;
+                }
+            } else {
+                uint32_t l = p.iset_off[a.set_id], h = p.iset_off[a.set_id + 1];
+                while (l < h) {
+                    uint32_t m = (l + h) >> 1;
+                    int64_t mv = __ldg(p.iset_vals + m);
+                    if (mv == x) { v = true; break; }
+                    if (mv < x) l = m + 1;
+                    else h = m;
+                }
+            }
+        } else if (a.kind == 3) {  // IP_SET
+            v = (set_mask >> a.set_id) & 1u;
+        } else {  // COUNTRY_SET
+            uint32_t c0 = (country & 0xFFu) - 'A', c1 = ((country >> 8) & 0xFFu) - 'A';
+            if (c0 < 26u && c1 < 26u) {
+                uint32_t bit = c0 * 26u + c1;
+                v = (__ldg(p.cset + a.set_id * kCountryWords + (bit >> 5)) >> (bit & 31)) & 1u;
+            }
+        }
+        if (v && valid) row[(a.atom >> 5) * stride] |= 1u << (a.atom & 31);
+    }
+
+    const uint32_t cv = flags & RF_CAPTCHA_VERIFIED;
+    uint32_t verdict = V_ALLOW | (kNoRule << 2);
+    bool decided = false;
+    if (flags & RF_PRE_BLOCK) { verdict = V_BLOCK | (kNoRule << 2); decided = true; }
+    if (!decided && p.eval_gates) {
+        // http_listener.rs:196-198: empty or over-long user agent is blocked before any rule
+        const uint32_t* o = p.off[4] + r;
+        uint32_t ual = o[1] - o[0];
+        if (ual == 0 || ual >= 256) { verdict = V_BLOCK | (kNoRule << 2); decided = true; }
+    }
+    if (!decided) {
+        bool bypass = flags & RF_BYPASS;
+        if (p.eval_gates && p.gate_atom >= 0) bypass |= (row[(p.gate_atom >> 5) * stride] >> (p.gate_atom & 31)) & 1u;
+        if (bypass) { verdict = V_BYPASS | (kNoRule << 2); decided = true; }
+    }
+    if (!decided && (flags & RF_PRE_CAPTCHA)) { verdict = V_CAPTCHA | (kNoRule << 2); decided = true; }
+
+    // deviations from the expected atom vector: none -> v0 / s0, exactly one -> v1[atom] / s1[atom], otherwise the
+    // candidate rules (those that mention a deviating atom, plus the ones true by default) are evaluated
+    const bool routes = p.service != nullptr && p.n_rules > p.n_waf_rules;
+    uint32_t ndev = 0, dev_atom = 0, sig = cv;
+    for (uint32_t w = 0; w < Aw; ++w) {
+        const uint32_t x = (row[w * stride] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
+        if (x) dev_atom = w * 32u + (uint32_t)__ffs(x) - 1u;
+        ndev += (uint32_t)__popc(x);
+        sig = sig * 0x9E3779B1u + x;
+    }
+    uint32_t svc = kNoService;
+    if (!decided) {
+        if (ndev == 0u) { verdict = p.v0[cv]; svc = p.s0; }
+        else if (ndev == 1u) { verdict = __ldg(p.v1 + cv * p.n_atoms + dev_atom); svc = routes ? (uint32_t)__ldg(p.s1 + dev_atom) : kNoService; }
+    }
+    const bool need_eval = !decided && ndev >= 2u;
+    if (WARP ? __any_sync(FULL, need_eval) : need_eval) {
+        bool do_eval = need_eval, same = false;
+        uint32_t leader = 0;
+        if (WARP) {
+            const uint32_t lane = threadIdx.x & 31u;
+            const uint32_t peers = __match_any_sync(FULL, need_eval ? (sig & 0x7FFFFFFFu) : (0x80000000u | lane));
+            leader = (uint32_t)__ffs(peers) - 1u;
+            same = true;  // equal signature: confirm that the deviation really is the leader's
+            for (uint32_t w = 0; w < Aw; ++w) {
+                const uint32_t x = (row[w * stride] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
+                same &= __shfl_sync(FULL, x, leader) == x;
+            }
+            same &= __shfl_sync(FULL, cv, leader) == cv;
+            do_eval = need_eval && (leader == lane || !same);
+        }
+        if (do_eval) {
+            const uint32_t tshift = 2 * cv;
+            uint32_t best = kNoRule, best_svc = kNoRule;
+            for (uint32_t w = 0; w < Aw; ++w) {
+                uint32_t x = (row[w * stride] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
+                while (x) {
+                    uint32_t b = __ffs(x) - 1;
+                    x &= x - 1;
+                    uint32_t atom = w * 32 + b;
+                    uint32_t i0 = __ldg(p.ar_idx + atom), i1 = __ldg(p.ar_idx + atom + 1);
+                    for (uint32_t i = i0; i < i1; ++i) {
+                        uint32_t rule = __ldg(p.ar_rules + i);  // ascending; WAF rules first, then service routes
+                        if (rule < p.n_waf_rules) {
+                            if (rule >= best || ((__ldg(p.term + rule) >> tshift) & 3u) == 0) continue;
+                            if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row, stride)) best = rule;
+                        } else {
+                            if (!routes || rule >= best_svc) break;
+                            if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row, stride)) best_svc = rule;
+                        }
+                    }
+                }
+            }
+            for (uint32_t i = 0; i < p.n_dflt[cv]; ++i) {
+                uint32_t rule = __ldg(p.dflt[cv] + i);
+                if (rule >= best) break;
+                if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row, stride)) best = rule;
+            }
+            if (routes)
+                for (uint32_t i = 0; i < p.n_dflt_services; ++i) {
+                    uint32_t rule = __ldg(p.dflt_services + i);
+                    if (rule >= best_svc) break;
+                    if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row, stride)) best_svc = rule;
+                }
+            verdict = best == kNoRule ? (V_ALLOW | (kNoRule << 2)) : (((__ldg(p.term + best) >> tshift) & 3u) | (best << 2));
+            svc = best_svc == kNoRule ? kNoService : best_svc - p.n_waf_rules;
+        }
+        if (WARP) {
+            const uint32_t lv = __shfl_sync(FULL, verdict, leader), ls = __shfl_sync(FULL, svc, leader);
+            if (need_eval && same) { verdict = lv; svc = ls; }
+        }
+    }
+    if (!valid) return;
+    p.verdict[r] = verdict;
+    // http_listener.rs:266-272: only a request the rules let through reaches the services; the first service whose
+    // route is absent or true takes it, none => 404 (kNoService)
+    if (p.service) p.service[r] = (uint16_t)(((verdict & 3u) == V_ALLOW && routes) ? svc : kNoService);
+}
+
+__device__ __noinline__ void request_epilogue(const KParams& p, uint32_t r, uint32_t* row, uint32_t stride) {
+    request_epilogue_t<false>(p, r, row, stride, true);
+}
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32_v(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint16_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+

@@ -1,0 +1,332 @@
+// Part of kernels.cu (included inside namespace pgw { namespace { ... } }, one translation unit: device functions are
+// not linked across files).  The default "field" path and the epilogue kernel shared with the stream path.
+
+// =====================================================================================================================
+// Field scan (kernel path "field"): unit-major, lane-owned strings.  A warp works on ONE scan unit at a time, so all the
+// per-unit parameters are warp-uniform; each lane owns one request's field of that unit and walks it 16 bytes per
+// iteration exactly like the lane path (speculative 4-byte word walk on the shared-memory rows).  A lane that finishes
+// takes the next request of the unit from a warp pool of 32 claimed requests whose field offsets were fetched coalesced
+// one pool ahead, so the per-request setup is a shuffle.  Atom bits go to bitmaps in global memory (red.or, rare) and
+// waf_epilogue_kernel turns them into verdicts.  Warps move to the next unit on their own when a unit runs dry.
+// =====================================================================================================================
+#ifndef PGW_FS_THREADS
+#define PGW_FS_THREADS 1024
+#endif
+constexpr int kFsThreads = PGW_FS_THREADS;
+constexpr uint32_t kFsSlotStride = kFsThreads * 4u;  // per-lane slots: request index, latch register, last fired state, next request
+#ifndef PGW_FS_TICKET
+#define PGW_FS_TICKET 64
+#endif
+constexpr uint32_t kFsTicket = PGW_FS_TICKET;  // requests per atomic claim (two 32-request pools: 128 and 256 measured worse, tail imbalance)
+constexpr uint32_t kFsPoolBytes = 144;  // 33 offsets of a claimed pool (+pad), two buffers per warp
+
+__device__ __forceinline__ void red_or(uint32_t* addr, uint32_t v) { asm volatile("red.global.or.b32 [%0], %1;" ::"l"(addr), "r"(v) : "memory"); }
+
+// events of CSR row `ci` applied to a bitmap in global memory; true if all of them were plain FIREs
+__device__ __forceinline__ bool fs_fire_list(const uint32_t* idx, const uint32_t* events, uint32_t ci, uint32_t* row, uint32_t* latch) {
+    uint32_t a = __ldg(idx + ci), b = __ldg(idx + ci + 1);
+    uint32_t l = *latch;
+    bool pure = true;
+    for (uint32_t i = a; i < b; ++i) {
+        const uint32_t e = __ldg(events + i);
+        const uint32_t kind = e >> kEvKindShift, lb = 1u << ((e >> kEvLatchShift) & 31u), at = e & kEvAtomMask;
+        if (kind == 0u || (kind == 1u && (l & lb))) red_or(row + (at >> 5), 1u << (at & 31));
+        else if (kind == 2u) l &= ~lb;
+        else if (kind == 3u) l |= lb;
+        pure &= kind == 0u;
+    }
+    *latch = l;
+    return pure;
+}
+
+// accept events of four hot states of one word (at least one accepting); returns the new `last`
+__device__ __noinline__ uint32_t fs_events_word(const KParams& p, const UnitDesc* ud, uint32_t acc1addr, uint32_t s01, uint32_t s23, uint32_t m4,
+                                                uint32_t last, uint32_t* latch, uint32_t* row) {
+    const uint32_t acclo = ud->acc_lo;
+    // positions whose state is accepting
+    uint32_t am = m4;
+    if ((s01 & 0xFFFFu) < acclo) am &= ~1u;
+    if ((s01 >> 16) < acclo) am &= ~2u;
+    if ((s23 & 0xFFFFu) < acclo) am &= ~4u;
+    if ((s23 >> 16) < acclo) am &= ~8u;
+#pragma unroll 1
+    while (am) {
+        const int bi = __ffs(am) - 1;
+        am &= am - 1u;
+        const uint32_t st = ((bi < 2 ? s01 : s23) >> (16 * (bi & 1))) & 0xFFFFu;
+        if (st == last) continue;
+        const uint32_t a1 = lds_u16(acc1addr + 2u * (st - acclo));
+        if (a1 != 0xFFFFu) {
+            red_or(row + (a1 >> 5), 1u << (a1 & 31));
+            last = st;
+        } else {
+            last = fs_fire_list(p.acc_idx, p.acc_events, ud->acc_base + st - acclo, row, latch) ? st : 0xFFFFFFFFu;
+        }
+    }
+    return last;
+}
+
+// one word walked on the full table in global memory (a cold state is involved)
+__device__ __noinline__ void fs_slow_word(const KParams& p, const UnitDesc* ud, uint32_t clsaddr, uint32_t w, uint32_t m4, uint32_t* state,
+                                          uint32_t* last, uint32_t* latch, uint32_t* row) {
+    const uint16_t* tbl = reinterpret_cast<const uint16_t*>(p.arena + ud->tbl_off);
+    const uint32_t C = ud->n_classes, acclo = ud->acc_lo;
+    uint32_t st = *state, la = *last;
+#pragma unroll 1
+    for (int bi = 0; bi < 4; ++bi) {
+        if (!((m4 >> bi) & 1u)) continue;
+        const uint32_t byte = (w >> (8 * bi)) & 0xFFu;
+        st = __ldg(tbl + st * C + lds_u8(clsaddr + byte));
+        if (st >= acclo && st != la) la = fs_fire_list(p.acc_idx, p.acc_events, ud->acc_base + st - acclo, row, latch) ? st : 0xFFFFFFFFu;
+    }
+    *state = st;
+    *last = la;
+}
+
+__global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __grid_constant__ KParams p, uint32_t* __restrict__ rows,
+                                                                       uint32_t* __restrict__ counters) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t img_bytes = r16(p.image_bytes);
+    uint8_t* s_img = smem + ((0u - smem_u32(smem)) & 255u);  // class maps (image offsets u * 256) on 256-byte boundaries
+    UnitDesc* s_units = reinterpret_cast<UnitDesc*>(s_img + img_bytes);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_img + img_bytes + r16(p.n_units * (uint32_t)sizeof(UnitDesc)));
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0 && img_bytes) {
+        mbar_expect_tx(s_bar, img_bytes);
+        for (uint32_t o = 0; o < img_bytes; o += 32768u) {
+            uint32_t n = img_bytes - o < 32768u ? img_bytes - o : 32768u;
+            bulk_g2s(s_img + o, p.image + o, n, s_bar);
+        }
+    }
+    for (uint32_t i = tid; i < p.n_units * (sizeof(UnitDesc) / 4); i += kFsThreads)
+        reinterpret_cast<uint32_t*>(s_units)[i] = __ldg(reinterpret_cast<const uint32_t*>(p.units) + i);
+    if (img_bytes) mbar_wait(s_bar, 0);
+    __syncthreads();
+
+    const uint32_t a_img = smem_u32(s_img);
+    const uint32_t a_pool = smem_u32(s_bar) + 64u + (tid >> 5) * 2u * kFsPoolBytes;
+    const uint32_t a_slot = smem_u32(s_bar) + 64u + (kFsThreads / 32) * 2u * kFsPoolBytes + tid * 4u;  // word k at a_slot + k * kFsSlotStride
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t Aw = p.atom_words, N = p.n;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    for (uint32_t u = 0; u < p.n_units; ++u) {
+        const UnitDesc* ud = &s_units[u];  // for the out-of-line event paths
+        const UnitDesc& cu = p.udesc[u];   // constant bank, uniform index
+        const uint32_t C2 = 2u * cu.n_classes, D0 = cu.start_state, trap = cu.hot_states, lim = cu.lim, acclo = cu.acc_lo;
+        const uint32_t clsaddr = a_img + cu.cls_off, hotaddr = a_img + cu.hot_off, acc1addr = a_img + cu.acc1_off, end1addr = a_img + cu.end1_off;
+        const uint8_t* col = p.col[cu.field];
+        const uint32_t* off = p.off[cu.field];
+        uint32_t* ctr = counters + u;
+
+        // warp pools of 32 claimed requests, double buffered in shared memory: buffer `pb` is being handed out, the other
+        // one holds the next claim whose 33 field offsets are landing through cp.async (no registers, no stall)
+        uint32_t pool_next = 0, pool_end = 0, pb = 0, ah_base = 0;
+        // claims are pipelined three deep so that no global latency is ever waited for: `ticket` (atomicAdd issued, result
+        // not looked at yet) -> `ahead` (offsets landing in the spare buffer) -> the pool being handed out
+        uint32_t ticket = 0;
+        bool tk_valid = false, ah_valid = false;
+        auto issue_ticket = [&]() {
+            if (lane == 0) ticket = atomicAdd(ctr, kFsTicket);  // a ticket covers kFsTicket / 32 consecutive pools
+            tk_valid = true;
+        };
+        uint32_t more = 0;  // end of the current ticket's range (pools still to take from it start at ah_base + 32)
+        auto claim_ahead = [&]() {
+            ah_valid = false;
+            uint32_t b = ah_base + 32u;
+            if (b >= more) {
+                if (!tk_valid) return;
+                b = __shfl_sync(FULL, ticket, 0);
+                if (b >= N) { tk_valid = false; return; }
+                more = min(b + kFsTicket, N);
+                issue_ticket();
+            }
+            ah_base = b;
+            const uint32_t dst = a_pool + (pb ^ 1u) * kFsPoolBytes;
+            cp_async4(dst + lane * 4u, off + min(b + lane, N));
+            if (lane == 0) cp_async4(dst + 128u, off + min(b + 32u, N));
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            ah_valid = true;
+        };
+        __syncwarp();
+        if (N) issue_ticket();
+        claim_ahead();
+
+        bool have = false, pend = false;
+        // hot per-lane state lives in registers; what only the (rare) event paths need -- request index, latch register,
+        // last fired state -- lives in this lane's shared-memory slots
+        uint32_t base = 0, skip = 0, end = 0, state = 0;
+        uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
+
+        for (;;) {
+            // ---- rotate: next chunk of the current string, or the first chunk of the string claimed last iteration ----
+            skip = 0;
+            if (pend) {
+                // a claim leaves `base` one chunk before the string's first one, its low four bits carry the offset of the
+                // first byte in that chunk; the request index waits in the lane's fourth slot word
+                skip = base & 15u;
+                base &= ~15u;
+                state = D0;
+                sts_u32(a_slot, lds_u32_v(a_slot + 3u * kFsSlotStride));
+                sts_u32(a_slot + kFsSlotStride, 0u);
+                sts_u32(a_slot + 2u * kFsSlotStride, 0xFFFFFFFFu);
+                have = true;
+                pend = false;
+                base += 16u;
+                cur = nxt;
+            } else if (have) {
+                base += 16u;
+                cur = nxt;
+            }
+            // everything this iteration's walk needs from (base, end, skip) is derived here, so that a lane on its last
+            // chunk can overwrite them with its next string right away
+            const bool finishing = have && end <= base + 16u;
+            uint32_t mk = 0;
+            if (have) {
+                const uint32_t hi = min(end - base, 16u);
+                mk = ((1u << hi) - 1u) & ~((1u << skip) - 1u);
+            }
+            // ---- lanes that run out of bytes in this iteration (or are idle) take the next request of the pool ----
+            const bool want = !have || finishing;
+            bool do_ld = have && !finishing;
+            uint32_t ld_off = base + 16u;
+            const uint32_t need = __ballot_sync(FULL, want);
+            if (need) {
+                if (pool_next == pool_end && ah_valid) {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
+                    pb ^= 1u;
+                    pool_next = ah_base;
+                    pool_end = min(ah_base + 32u, N);
+                    claim_ahead();
+                }
+                const uint32_t idx = pool_next + __popc(need & lt_mask);
+                if (want && idx < pool_end) {
+                    const uint32_t sa = a_pool + pb * kFsPoolBytes + (idx & 31u) * 4u;
+                    const uint32_t s0 = lds_u32_v(sa), e0 = lds_u32_v(sa + 4u);
+                    if (e0 > s0) {  // empty fields are left to the epilogue kernel
+                        sts_u32(a_slot + 3u * kFsSlotStride, idx);
+                        pend = true;
+                        end = e0;
+                        ld_off = s0 & ~15u;
+                        base = (ld_off - 16u) | (s0 & 15u);
+                        do_ld = true;
+                    }
+                }
+                pool_next = min(pool_end, pool_next + (uint32_t)__popc(need));
+            }
+            // one load per lane and iteration, consumed in the next one: the next chunk of the current string or the first
+            // chunk of the string just claimed (a single instruction: two loads into the same registers would serialise)
+            if (do_ld) nxt = ld_nc_v4(col + ld_off);
+            if (!__any_sync(FULL, have)) {
+                if (!__any_sync(FULL, pend) && pool_next == pool_end && !ah_valid) break;
+                continue;
+            }
+
+            // ---- walk the bytes of this chunk that belong to the field (no per-word vote: some lane almost always has
+            //      bytes in every word, the vote cost more than the words it skipped) ----
+#pragma unroll
+            for (int wi = 0; wi < 4; ++wi) {
+                const uint32_t m4 = (mk >> (4 * wi)) & 0xFu;
+                const uint32_t w = wi == 0 ? cur.x : wi == 1 ? cur.y : wi == 2 ? cur.z : cur.w;
+                uint32_t spec = min(state, trap);
+                uint32_t sv[4];
+#pragma unroll
+                for (int bi = 0; bi < 4; ++bi) {
+                    // class maps sit on 256-byte boundaries of the shared window: one PRMT extracts the byte AND adds the base
+                    const uint32_t cls = lds_u8(__byte_perm(w, clsaddr, 0x7650 + bi));
+                    // column address first (independent of the state): the state chain is IMAD -> LDS -> SEL only
+                    uint32_t colad = hotaddr + 2u * cls, ad;
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ad) : "r"(spec), "r"(C2), "r"(colad));
+                    const uint32_t st = lds_u16(ad);
+                    spec = (m4 & (1u << bi)) ? st : spec;
+                    sv[bi] = spec;
+                }
+                // a cold start state walks the trap row, so the four new states alone tell whether the word needs attention
+                const uint32_t mx4 = max(max(sv[0], sv[1]), max(sv[2], sv[3]));
+                if (mx4 >= lim) {
+                    if (mx4 >= trap || mx4 >= acclo) {
+                        uint32_t* row = rows + (size_t)lds_u32_v(a_slot) * Aw;
+                        uint32_t t_latch = lds_u32_v(a_slot + kFsSlotStride), t_last = lds_u32_v(a_slot + 2u * kFsSlotStride);
+                        if (mx4 >= trap) {
+                            uint32_t t_state = state;
+                            fs_slow_word(p, ud, clsaddr, w, m4, &t_state, &t_last, &t_latch, row);
+                            spec = t_state;
+                        } else {
+                            // a string sitting in a sticky accepting state whose events were already applied: nothing to do
+                            const uint32_t s01 = sv[0] | (sv[1] << 16), s23 = sv[2] | (sv[3] << 16), ll = t_last | (t_last << 16);
+                            if (t_last > 0xFFFFu || s01 != ll || s23 != ll) {
+                                // the common event -- one accepting position whose list is a single FIRE -- is applied inline
+                                uint32_t am = m4;
+                                if (sv[0] < acclo) am &= ~1u;
+                                if (sv[1] < acclo) am &= ~2u;
+                                if (sv[2] < acclo) am &= ~4u;
+                                if (sv[3] < acclo) am &= ~8u;
+                                const uint32_t pos = __ffs(am) - 1u;
+                                const uint32_t st1 = ((pos < 2u ? s01 : s23) >> (16u * (pos & 1u))) & 0xFFFFu;
+                                uint32_t a1 = 0xFFFFu;
+                                if ((am & (am - 1u)) == 0u) a1 = lds_u16(acc1addr + 2u * (st1 - acclo));
+                                if (a1 != 0xFFFFu) {
+                                    if (st1 != t_last) red_or(row + (a1 >> 5), 1u << (a1 & 31));
+                                    t_last = st1;
+                                } else {
+                                    t_last = fs_events_word(p, ud, acc1addr, s01, s23, m4, t_last, &t_latch, row);
+                                }
+                            }
+                        }
+                        sts_u32(a_slot + kFsSlotStride, t_latch);
+                        sts_u32(a_slot + 2u * kFsSlotStride, t_last);
+                    }
+                }
+                state = spec;
+            }
+            if (finishing) {
+                uint32_t e1 = 0xFFFFu;
+                if (state < trap) e1 = lds_u16(end1addr + 2u * state);
+                if (e1 != 0xFFFEu) {
+                    uint32_t* row = rows + (size_t)lds_u32_v(a_slot) * Aw;
+                    if (e1 != 0xFFFFu) red_or(row + (e1 >> 5), 1u << (e1 & 31));
+                    else if (cu.end_any) {
+                        uint32_t t_latch = lds_u32_v(a_slot + kFsSlotStride);
+                        fs_fire_list(p.end_idx, p.end_events, cu.end_base + state, row, &t_latch);
+                    }
+                }
+                have = false;
+                state = 0;  // an idle lane must not look like it sits in a cold or accepting state
+            }
+        }
+    }
+}
+
+// Verdicts once every unit has been scanned: one thread per request.  Empty fields never reach the stream scan;
+// their end-of-field events (the DFA's start state at end of input) are applied here.
+__global__ void __launch_bounds__(256) waf_epilogue_kernel(const __grid_constant__ KParams p, uint32_t* __restrict__ rows) {
+    // warp-uniform trip count: every lane of a warp goes through request_epilogue_t<true> together
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < p.n; base += gridDim.x * blockDim.x) {
+        const uint32_t rr = base + (threadIdx.x & 31u);
+        const bool valid = rr < p.n;
+        const uint32_t r = valid ? rr : p.n - 1u;
+        uint32_t* row = rows + (size_t)r * p.atom_words;
+        if (valid)
+            for (uint32_t u = 0; u < p.n_units; ++u) {
+                const UnitDesc& ud = p.udesc[u];  // parameter bank (both callers keep n_units <= kMaxConstUnits)
+                if (!ud.end_any) continue;
+                const uint32_t* o = p.off[ud.field] + r;
+                if (o[0] != o[1]) continue;
+                uint32_t a = __ldg(p.end_idx + ud.end_base + ud.start_state), b = __ldg(p.end_idx + ud.end_base + ud.start_state + 1);
+                for (uint32_t i = a; i < b; ++i) {
+                    const uint32_t e = __ldg(p.end_events + i);
+                    if ((e >> kEvKindShift) == 0u) row[(e & kEvAtomMask) >> 5] |= 1u << (e & 31);  // latch kinds cannot fire on an empty field
+                }
+            }
+        __syncwarp();
+        request_epilogue_t<true>(p, r, row, 1, valid);
+    }
+}
+
