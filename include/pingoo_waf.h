@@ -83,7 +83,9 @@ typedef struct pgw_info {
     uint32_t offset_fields_mask;  /* bit f set: offsets of field f are read */
     uint32_t reads_ip, reads_port, reads_geo_columns;
     uint64_t table_arena_bytes, smem_bytes;
-    uint32_t tables_in_smem, tile_requests, grid, threads;
+    uint32_t tables_in_smem;      /* every DFA row is resident in shared memory */
+    uint32_t hot_dfa_states;      /* DFA states whose rows are in the shared-memory image (the rest is read from L2) */
+    uint32_t grid, threads;       /* launch shape of the scan kernel of the active path */
     uint32_t total_dfa_states, lpm_present, geoip_loaded;
     uint64_t kernel_launches;     /* launches issued through this ruleset so far */
     uint64_t last_h2d_bytes, last_d2h_bytes; /* bytes moved by the last pgw_evaluate_batch_host call */

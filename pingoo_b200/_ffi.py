@@ -59,7 +59,7 @@ class Info(C.Structure):
         ("scanned_fields_mask", C.c_uint32), ("offset_fields_mask", C.c_uint32),
         ("reads_ip", C.c_uint32), ("reads_port", C.c_uint32), ("reads_geo_columns", C.c_uint32),
         ("table_arena_bytes", C.c_uint64), ("smem_bytes", C.c_uint64),
-        ("tables_in_smem", C.c_uint32), ("tile_requests", C.c_uint32), ("grid", C.c_uint32), ("threads", C.c_uint32),
+        ("tables_in_smem", C.c_uint32), ("hot_dfa_states", C.c_uint32), ("grid", C.c_uint32), ("threads", C.c_uint32),
         ("total_dfa_states", C.c_uint32), ("lpm_present", C.c_uint32), ("geoip_loaded", C.c_uint32),
         ("kernel_launches", C.c_uint64), ("last_h2d_bytes", C.c_uint64), ("last_d2h_bytes", C.c_uint64),
     ]

@@ -574,9 +574,9 @@ int pgw_ruleset_info(const pgw_ruleset* rs, pgw_info* out) {
     out->smem_bytes = rs->smem_bytes;
     for (auto& u : H.units) out->total_dfa_states += u.n_states;
     out->tables_in_smem = rs->hot_states_total == out->total_dfa_states;
-    out->tile_requests = rs->hot_states_total;  /* states whose rows live in shared memory */
+    out->hot_dfa_states = rs->hot_states_total;  /* states whose rows live in shared memory */
     out->grid = (uint32_t)rs->sm_count;
-    out->threads = kThreads;
+    out->threads = rs->field_kernel ? (uint32_t)waf_field_threads() : (uint32_t)kThreads;
     out->lpm_present = H.lpm.present;
     out->geoip_loaded = H.lpm.geo_loaded;
     out->kernel_launches = rs->launches.load();

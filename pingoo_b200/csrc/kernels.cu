@@ -91,6 +91,8 @@ const char* waf_configure(int device, size_t* max_smem_optin, int* sm_count) {
     return nullptr;
 }
 
+int waf_field_threads() { return kFsThreads; }
+
 size_t waf_field_smem_bytes(uint32_t image_bytes, uint32_t n_units) {
     return 256 + r16(image_bytes) + r16(n_units * (uint32_t)sizeof(UnitDesc)) + 64 + (kFsThreads / 32) * 2 * kFsPoolBytes + 4 * kFsSlotStride;
 }

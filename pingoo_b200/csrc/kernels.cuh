@@ -106,6 +106,7 @@ const char* waf_stream_launch(const KParams& p, uint32_t* rows, uint32_t* task_c
 // kFieldCounters claim counters (`counters` points at them)
 constexpr uint32_t kFieldCounters = 64;
 size_t waf_field_smem_bytes(uint32_t image_bytes, uint32_t n_units);
+int waf_field_threads();  // threads per CTA of the field-scan kernel
 const char* waf_field_launch(const KParams& p, uint32_t* rows, uint32_t* counters, int sm_count, size_t smem_bytes, void* stream,
                              cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);  // optional events around the scan kernel
 const char* client_id_launch(const uint8_t* ip, const uint8_t* is_v6, const uint8_t* ua_bytes, const uint32_t* ua_off, const uint8_t* host_bytes,

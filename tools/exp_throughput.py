@@ -21,7 +21,7 @@ def run(rules, batch, label, steps=10):
     ms = evs[0].elapsed_time(evs[steps])/steps
     label = f"{label} [min {per[0]:.3f} med {per[len(per)//2]:.3f} max {per[-1]:.3f}]"
     scanned = sum(batch.total[f] for i,f in enumerate(synth.FIELDS) if (info.scanned_fields_mask>>i)&1)
-    print(f"{label}: {ms:.3f} ms  {batch.n/ms/1e3:.1f} M req/s  alg {scanned/ms/1e6:.0f} GB/s  units={info.n_scan_units} hot={info.tile_requests}/{info.total_dfa_states} arena={info.table_arena_bytes} smem={info.smem_bytes}", flush=True)
+    print(f"{label}: {ms:.3f} ms  {batch.n/ms/1e3:.1f} M req/s  alg {scanned/ms/1e6:.0f} GB/s  units={info.n_scan_units} hot={info.hot_dfa_states}/{info.total_dfa_states} arena={info.table_arena_bytes} smem={info.smem_bytes}", flush=True)
 rules, payloads, _ = synth.make_ruleset(128)
 batch = synth.RequestStream(config_id=2, payloads=payloads).generate(0, 1_000_000)
 run(rules, batch, "128 rules")
