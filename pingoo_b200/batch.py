@@ -5,9 +5,8 @@ describes; `pack_requests` mirrors what http_listener.rs:139-219 extracts from o
 hyper request (host/path trimming rules, user-agent shaping) so tests can start
 from "raw" requests.
 """
-import ctypes as C
 import ipaddress
-from typing import Iterable, Optional
+from typing import Iterable
 
 import numpy as np
 

@@ -8,7 +8,6 @@ import numpy as np
 
 from pingoo_b200 import _ffi
 from pingoo_b200.batch import RequestBatch
-from pingoo_b200.rules import Rule
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")

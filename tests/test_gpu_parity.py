@@ -7,7 +7,7 @@ import pytest
 import scenarios
 import synth
 from helpers import Oracle, Sim, fmt_verdict
-from pingoo_b200 import Action, ListType, Rule, WafEngine, pack_requests
+from pingoo_b200 import Action, Rule, WafEngine, pack_requests
 
 pytestmark = pytest.mark.gpu
 THREADS = os.cpu_count() or 1

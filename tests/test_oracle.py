@@ -23,7 +23,7 @@ import pytest
 
 import synth
 from helpers import Oracle, Sim, fmt_verdict, oracle_lib
-from pingoo_b200 import Action, ListType, Rule, _ffi, pack_requests
+from pingoo_b200 import Action, ListType, Rule, pack_requests
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 

@@ -1,4 +1,4 @@
-import sys, time, os
+import sys, os
 import os; R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0,R); sys.path.insert(0,os.path.join(R,'tests'))
 import numpy as np, torch
 import synth
