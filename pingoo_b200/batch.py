@@ -103,7 +103,7 @@ def pack_requests(requests: Iterable[dict], with_geo: bool = True) -> RequestBat
 
     Applies the shaping the listener applies before rules see a request:
       path: trailing '/' trimmed (services/http_utils.rs:114-116, "/" -> "")
-      host: trimmed, longer than 256 bytes -> ""   (http_listener.rs:284-296)
+      host: header `to_str` (visible ASCII or tab, else ""), trimmed, longer than 256 bytes -> ""   (http_listener.rs:284-296)
       user_agent: trimmed; non-visible-ASCII or longer than 256 bytes -> "" (http_listener.rs:159-165)
     """
     reqs = list(requests)
@@ -111,7 +111,11 @@ def pack_requests(requests: Iterable[dict], with_geo: bool = True) -> RequestBat
     cols = {}
     shaped = []
     for r in reqs:
-        host = r.get("host", "").strip()
+        host = r.get("host", "")
+        hb = host.encode("utf-8", "surrogateescape")
+        if any(not (32 <= c < 127 or c == 9) for c in hb):  # HeaderValue::to_str fails -> unwrap_or_default()
+            host = ""
+        host = host.strip()
         if len(host.encode()) > 256:
             host = ""
         ua = r.get("user_agent", "")

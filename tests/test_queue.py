@@ -18,6 +18,7 @@ RAW = [
     dict(host=" " + "h" * 256 + " ", url="/x", path="//", method="GET", user_agent="\t" + "u" * 256 + " "),  # trimmed first
     dict(host="tab\there", url="/", path="", method="HEAD", user_agent="tab\tinside"),      # tab is allowed by to_str
     dict(host="", url="", path="", method="", user_agent=""),
+    dict(host="caf\u00e9.example", url="/", path="/", method="GET", user_agent="Mozilla/5.0 \u2713"),  # non-ASCII header values
 ]
 RAW_BYTES = [
     dict(host=b"caf\xc3\xa9.example", url=b"/caf\xc3\xa9", path=b"/caf\xc3\xa9/", method=b"GET", user_agent=b"Mozilla/5.0 (\xe2\x9c\x93)"),
