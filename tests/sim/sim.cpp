@@ -352,3 +352,70 @@ uint32_t pgwsim_state_histogram(void* h, const pgw_batch* b, uint32_t unit, uint
 void pgwsim_destroy(void* h) { delete (Sim*)h; }
 
 }  // extern "C"
+
+// Analysis tool (no product counterpart): shared-memory wavefronts of the scan's row look-ups for one unit, emulating
+// one warp of 32 lanes that each walk one request's field and take the next request when done (the field path's
+// schedule).  For every lock-step byte the active lanes read 2 bytes at row(state) * row_stride + 2 * column(class); a
+// wavefront serves all lanes whose addresses fall in distinct banks or in the same 4-byte word.  `perm` (class -> column)
+// and `state_rows` (state -> row) may be null (identity).
+// out[0] = lock-steps with at least one active lane, out[1] = wavefronts, out[2] = active lane-steps,
+// out[3] = distinct states summed over steps.
+extern "C" int pgwsim_bank_stats(void* h, const pgw_batch* b, uint32_t unit, uint32_t row_stride, const uint16_t* perm, const uint32_t* state_rows,
+                                 uint64_t* out) {
+    Sim* s = (Sim*)h;
+    const HostProgram& H = s->H;
+    if (unit >= H.units.size()) return 1;
+    const UnitDesc& u = H.units[unit];
+    const pgw_strcol* cols[5] = {&b->host, &b->url, &b->path, &b->method, &b->user_agent};
+    const uint8_t* cls = H.arena.data() + u.cls_off;
+    const uint16_t* tbl = (const uint16_t*)(H.arena.data() + u.tbl_off);
+    const pgw_strcol* col = cols[u.field];
+    uint64_t steps = 0, waves = 0, lane_steps = 0, distinct = 0;
+    uint32_t next = 0;
+    struct Lane { uint32_t pos, end, st; bool on; } L[32];
+    for (auto& l : L) l.on = false;
+    for (;;) {
+        bool any = false;
+        for (auto& l : L) {
+            while (!l.on && next < b->n) {
+                l.pos = col->offsets[next];
+                l.end = col->offsets[next + 1];
+                l.st = u.start_state;
+                l.on = l.end > l.pos;
+                ++next;
+            }
+            any |= l.on;
+        }
+        if (!any) break;
+        uint32_t words[32], nw = 0, sts[32], ns = 0;
+        for (auto& l : L) {
+            if (!l.on) continue;
+            const uint32_t c = cls[col->bytes[l.pos]];
+            const uint32_t row = state_rows ? state_rows[l.st] : l.st;
+            const uint32_t addr = row * row_stride + 2u * (perm ? perm[c] : c);
+            const uint32_t w = addr >> 2;
+            bool seen = false;
+            for (uint32_t k = 0; k < nw; ++k) seen |= words[k] == w;
+            if (!seen) words[nw++] = w;
+            bool ss = false;
+            for (uint32_t k = 0; k < ns; ++k) ss |= sts[k] == l.st;
+            if (!ss) sts[ns++] = l.st;
+            l.st = tbl[l.st * u.n_classes + c];
+            if (++l.pos >= l.end) l.on = false;
+            ++lane_steps;
+        }
+        uint32_t load[32] = {0}, mx = 0;
+        for (uint32_t k = 0; k < nw; ++k) {
+            const uint32_t v = ++load[words[k] & 31];
+            if (v > mx) mx = v;
+        }
+        waves += mx;
+        distinct += ns;
+        ++steps;
+    }
+    out[0] = steps;
+    out[1] = waves;
+    out[2] = lane_steps;
+    out[3] = distinct;
+    return 0;
+}
