@@ -253,7 +253,8 @@ def main():
             "impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
             "ms_per_step": 1e3 * min(args.cpu_sample, batches[0].n) / (v * 1e6), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"config {args.config}: {CONFIGS[args.config][0]}", "rules": len(rules), "sample": sample},
+            "config": {"workload": f"config {args.config}: {CONFIGS[args.config][0]}", "requests_per_gpu": args.requests or CONFIGS[args.config][1],
+                       "rules": len(rules), "parallelism": f"dp{args.gpus}", "sample": sample},
             "cpu_baseline": {"value": v, "unit": unit, "cores": ncores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
