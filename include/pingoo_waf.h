@@ -56,10 +56,13 @@ typedef struct pgw_options {
     uint64_t max_unit_table_bytes; /* per scan unit; 0 = default (8 MiB) */
     int32_t eval_gates;            /* 1 (default): evaluate the user-agent and captcha-path gates of
                                       http_listener.rs:196-204 inside the engine; 0: rules only */
+    int32_t disable_candidate_gate; /* 0 (default): url / user_agent / path patterns are prefiltered by the gram gate and
+                                      only candidate requests are walked by their DFAs; 1: every request is walked
+                                      (same verdicts; kept for measurements and tests) */
 } pgw_options;
 
 /* One string column: concatenated bytes + n+1 offsets.  `bytes` must be 32-byte
- * aligned and readable up to round_up(offsets[n], 32) (the kernel loads whole 32-byte chunks). */
+ * aligned and readable up to round_up(offsets[n], 32) (the kernels load aligned 16-byte chunks). */
 typedef struct pgw_strcol {
     const uint8_t* bytes;
     const uint32_t* offsets;
@@ -89,6 +92,9 @@ typedef struct pgw_info {
     uint32_t total_dfa_states, lpm_present, geoip_loaded;
     uint64_t kernel_launches;     /* launches issued through this ruleset so far */
     uint64_t last_h2d_bytes, last_d2h_bytes; /* bytes moved by the last pgw_evaluate_batch_host call */
+    uint32_t gated_fields_mask;   /* fields in front of whose DFAs the candidate gate runs */
+    uint32_t gate_grams;          /* 4-byte grams in the gate bitmaps, all fields */
+    uint64_t gate_smem_bytes;     /* shared memory of the gate kernel (largest field's two bitmaps) */
 } pgw_info;
 
 /* rules::compile_expression(&str) -> Result<CompiledExpression, Error>   (rules/rules.rs:45-53) */
@@ -113,7 +119,8 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
  * Thread-safe on a finalized ruleset. */
 int pgw_evaluate_batch(const pgw_ruleset* rs, const pgw_batch* batch, uint32_t* verdict_out, void* stream);
 /* Same with HOST pointers: copies the columns to the device, evaluates, copies verdicts back, synchronises.
- * Uses staging buffers owned by the ruleset (not thread-safe on one ruleset). */
+ * Thread-safe on a finalized ruleset: every call takes its own staging buffers and streams from a pool
+ * (the reference evaluates concurrently on shared Arcs, http_listener.rs:91-103,134-138). */
 int pgw_evaluate_batch_host(pgw_ruleset* rs, const pgw_batch* batch, uint32_t* verdict_out);
 
 /* GeoipDB::lookup for a batch of addresses (pingoo/geoip.rs:73-91); device pointers, not-found => {0,"XX"}. */

@@ -37,7 +37,8 @@ DONE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_uint16, C.c_int)
 
 
 class Options(C.Structure):
-    _fields_ = [("max_dfa_states", C.c_int32), ("max_unit_table_bytes", C.c_uint64), ("eval_gates", C.c_int32)]
+    _fields_ = [("max_dfa_states", C.c_int32), ("max_unit_table_bytes", C.c_uint64), ("eval_gates", C.c_int32),
+                ("disable_candidate_gate", C.c_int32)]
 
 
 class StrCol(C.Structure):
@@ -62,6 +63,7 @@ class Info(C.Structure):
         ("tables_in_smem", C.c_uint32), ("hot_dfa_states", C.c_uint32), ("grid", C.c_uint32), ("threads", C.c_uint32),
         ("total_dfa_states", C.c_uint32), ("lpm_present", C.c_uint32), ("geoip_loaded", C.c_uint32),
         ("kernel_launches", C.c_uint64), ("last_h2d_bytes", C.c_uint64), ("last_d2h_bytes", C.c_uint64),
+        ("gated_fields_mask", C.c_uint32), ("gate_grams", C.c_uint32), ("gate_smem_bytes", C.c_uint64),
     ]
 
 

@@ -73,6 +73,46 @@ struct Staging {
     }
 };
 
+// Per-batch device scratch.  rows / dirty obey the invariant "all zero between batches" (the epilogue re-zeroes what
+// the scan touched), so a batch costs no memset of the n x atom_words bitmap; `small` (claim counters + candidate
+// counters) is zeroed at every launch.  Blocks are reused in stream order: a block released on stream S can be taken
+// again on S at once, on another stream only after its event has completed.
+struct Scratch {
+    uint8_t* base = nullptr;
+    size_t cap_requests = 0;
+    cudaEvent_t done = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool busy = false;
+    // carved out of `base`
+    uint32_t* rows = nullptr;
+    uint32_t* dirty = nullptr;
+    uint32_t* small = nullptr;       // [0, kSmallCounters): per-unit claim counters; [kSmallCounters, +5): candidate counters
+    uint32_t* cand[5][3] = {};       // per gated field: idx, start, end
+};
+constexpr uint32_t kSmallCounters = 1024;   // scan units a program may have
+constexpr uint32_t kSmallWords = kSmallCounters + 8;
+
+struct HostStage {   // device staging of one host-pointer call (pgw_evaluate_batch_host), pooled so that calls may overlap
+    Staging cols[5], offs[5], ip, v6, port, asn, country, flags, verdict, service;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t slice_ready[kHostSlices] = {};
+    bool busy = false;
+    bool init() {
+        bool ok = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+        for (uint32_t i = 0; i < kHostSlices && ok; ++i) ok = cudaEventCreateWithFlags(&slice_ready[i], cudaEventDisableTiming) == cudaSuccess;
+        return ok;
+    }
+    void release() {
+        for (int f = 0; f < 5; ++f) { cols[f].release(); offs[f].release(); }
+        ip.release(); v6.release(); port.release(); asn.release(); country.release(); flags.release(); verdict.release(); service.release();
+        if (stream) cudaStreamDestroy(stream);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        for (auto& ev : slice_ready)
+            if (ev) cudaEventDestroy(ev);
+    }
+};
+
 }  // namespace
 
 struct pgw_ruleset {
@@ -84,23 +124,72 @@ struct pgw_ruleset {
     size_t max_smem = 0;
     DevMem mem;
     KParams base;  // program pointers filled in, batch fields zero
-    size_t smem_bytes = 0;
+    GateParams gate_base;  // bitmaps and shifts filled in
+    int gate_field[kMaxGateFields] = {0, 0, 0};
+    std::vector<UnitDesc> units;   // with the image fields filled in
+    size_t scan_smem = 0, gate_smem = 0;
     uint32_t hot_states_total = 0;
-    uint32_t* counters = nullptr;  // ring of work counters: one per in-flight launch
-    bool stream_kernel = false;    // kernel path: stream scan (v5) instead of lane-owned requests (v3)
-    bool field_kernel = false;     // kernel path: unit-major field scan (v6)
-    size_t stream_smem = 0, field_smem = 0;
     std::atomic<uint64_t> launches{0};
-    // host-pointer path
-    Staging stage_cols[5], stage_offs[5], stage_ip, stage_v6, stage_port, stage_asn, stage_country, stage_flags, stage_verdict, stage_service;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t slice_ready[kHostSlices] = {};
-    uint64_t last_h2d = 0, last_d2h = 0;
-    // measurement hook: event pairs around the scan kernel
+    // scratch pool (device-pointer and host-pointer paths)
+    std::mutex pool_mu;
+    std::vector<Scratch*> pool;
+    // host-pointer path: staging pool
+    std::vector<HostStage*> stages;
+    std::atomic<uint64_t> last_h2d{0}, last_d2h{0};
+    // measurement hook: event pairs around the gate + scan kernels
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev;  // 2 * kProfRing events, created on first enable
     std::atomic<uint64_t> prof_n{0};
 };
+
+namespace {
+
+Scratch* scratch_acquire(pgw_ruleset* rs, uint32_t n, cudaStream_t stream, std::string& e) {
+    const HostProgram& H = rs->prog;
+    std::lock_guard<std::mutex> lk(rs->pool_mu);
+    for (Scratch* sc : rs->pool) {
+        if (sc->busy || sc->cap_requests < n) continue;
+        if (sc->last_stream != stream && cudaEventQuery(sc->done) != cudaSuccess) continue;
+        sc->busy = true;
+        return sc;
+    }
+    // a new block, sized with head-room so that slightly larger batches reuse it
+    Scratch* sc = new Scratch();
+    size_t cap = (size_t)n + n / 8 + 1024;
+    cap = (cap + 31) & ~(size_t)31;
+    size_t n_gated = 0;
+    for (int f = 0; f < 5; ++f) n_gated += H.gate[f].present ? 1 : 0;
+    const size_t rows_b = cap * H.atom_words * 4, dirty_b = cap / 32 * 4 + 64, small_b = kSmallWords * 4, cand_b = n_gated * 3 * cap * 4;
+    const size_t total = rows_b + dirty_b + small_b + cand_b + 1024;
+    if (cudaMalloc((void**)&sc->base, total) != cudaSuccess || cudaEventCreateWithFlags(&sc->done, cudaEventDisableTiming) != cudaSuccess) {
+        e = std::string("CUDA: scratch allocation failed (") + std::to_string(total >> 20) + " MiB): " + cudaGetErrorString(cudaGetLastError());
+        if (sc->base) cudaFree(sc->base);
+        delete sc;
+        return nullptr;
+    }
+    // the zero invariant starts here; ordered before the first kernel that uses the block
+    if (cudaMemsetAsync(sc->base, 0, rows_b + dirty_b + small_b, stream) != cudaSuccess) { e = "CUDA: scratch memset failed"; cudaFree(sc->base); delete sc; return nullptr; }
+    uint8_t* q = sc->base;
+    sc->rows = (uint32_t*)q; q += rows_b;
+    sc->dirty = (uint32_t*)q; q += dirty_b;
+    sc->small = (uint32_t*)q; q += small_b;
+    for (int f = 0; f < 5; ++f)
+        if (H.gate[f].present)
+            for (int k = 0; k < 3; ++k) { sc->cand[f][k] = (uint32_t*)q; q += cap * 4; }
+    sc->cap_requests = cap;
+    sc->busy = true;
+    rs->pool.push_back(sc);
+    return sc;
+}
+
+void scratch_release(pgw_ruleset* rs, Scratch* sc, cudaStream_t stream) {
+    cudaEventRecord(sc->done, stream);
+    std::lock_guard<std::mutex> lk(rs->pool_mu);
+    sc->last_stream = stream;
+    sc->busy = false;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -130,6 +219,7 @@ int pgw_ruleset_create(const pgw_rule_desc* rules, uint32_t n_rules, const pgw_o
         if (options->max_dfa_states > 0) rs->builder.options.max_dfa_states = options->max_dfa_states;
         if (options->max_unit_table_bytes > 0) rs->builder.options.max_unit_table_bytes = (size_t)options->max_unit_table_bytes;
         rs->builder.options.eval_gates = options->eval_gates != 0;
+        rs->builder.options.candidate_gate = options->disable_candidate_gate == 0;
     }
     for (uint32_t i = 0; i < n_rules; ++i) {
         std::string e;
@@ -187,35 +277,51 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     DevMem& M = rs->mem;
     bool ok = true;
     auto chk = [&](const void* p) { if (!p) ok = false; return p; };
-    // shared-memory image: class maps + as many hot DFA rows as fit beside the per-lane bitmap rows
-    uint32_t n_scan_slots = 0;
-    uint32_t slot_of_field[5] = {0, 0, 0, 0, 0};
-    for (int f = 0; f < 5; ++f)
-        if ((H.scanned_fields_mask >> f) & 1) { P.slot_field[n_scan_slots] = (uint32_t)f; slot_of_field[f] = n_scan_slots++; }
-    P.n_slots = n_scan_slots;
-    size_t fixed = waf_smem_fixed_bytes((uint32_t)H.units.size(), H.atom_words, n_scan_slots);
-    if (fixed + H.units.size() * 256 + 1024 > rs->max_smem)
-        return fail("ruleset does not fit the shared-memory plan (too many atoms or scan units)", err, err_cap);
+    // per-unit shared-memory images: each unit gets the whole budget while it is being walked
+    if (H.units.size() > kSmallCounters) return fail("ruleset has too many scan units", err, err_cap);
     std::vector<uint8_t> image;
-    std::vector<UnitDesc> units;
-    // Only a few hundred shallow states are ever visited by real traffic: cap the image so most of the 228 KB stays L1
-    // (request bytes, offsets, spills).  PGW_SMEM_IMAGE_KB overrides the cap for tuning.
-    size_t image_cap = 96u << 10;
-    if (const char* ev = getenv("PGW_SMEM_IMAGE_KB")) image_cap = (size_t)atoi(ev) << 10;
-    size_t image_budget = rs->max_smem - fixed - 64;
-    if (image_budget > image_cap) image_budget = image_cap;
-    if (image_budget < H.units.size() * 256 + 4096) image_budget = H.units.size() * 256 + 4096;
-    build_smem_image(H, image_budget, &image, &units);
-    for (auto& u : units) u.field_slot = slot_of_field[u.field];  // slot among the scanned fields
-    rs->smem_bytes = waf_smem_bytes((uint32_t)image.size(), (uint32_t)units.size(), H.atom_words, n_scan_slots);
-    for (auto& u : units) rs->hot_states_total += u.hot_states;
+    std::vector<UnitDesc>& units = rs->units;
+    size_t image_budget = waf_scan_image_budget(rs->max_smem);
+    if (const char* ev = getenv("PGW_SMEM_IMAGE_KB")) {  // tuning knob
+        size_t v = (size_t)atoi(ev) << 10;
+        if (v >= 4096 && v < image_budget) image_budget = v;
+    }
+    build_unit_images(H, image_budget, &image, &units);
+    uint32_t max_img = 0;
+    for (auto& u : units) {
+        rs->hot_states_total += u.hot_states;
+        if (u.img_bytes > max_img) max_img = u.img_bytes;
+    }
+    rs->scan_smem = waf_scan_smem_bytes(max_img);
+    if (rs->scan_smem > rs->max_smem) return fail("ruleset does not fit the shared-memory plan", err, err_cap);
     P.units = (const UnitDesc*)chk(M.upload(units));
     memset(P.udesc, 0, sizeof P.udesc);
-    for (size_t i = 0; i < units.size() && i < kMaxConstUnits; ++i) P.udesc[i] = units[i];
-    P.n_units = (uint32_t)units.size();
+    P.n_units_total = (uint32_t)units.size();
+    P.n_units = 0;
+    P.unit_base = 0;
     P.arena = (const uint8_t*)chk(M.upload(H.arena));
-    P.image = (const uint8_t*)chk(M.upload(image));
-    P.image_bytes = (uint32_t)image.size();
+    P.images = (const uint8_t*)chk(M.upload(image, 256));
+    P.n_start_end = 0;
+    for (size_t u = 0; u < units.size(); ++u)
+        if (units[u].start_end) {
+            if (P.n_start_end >= 8) return fail("too many scan units with patterns that match an empty field", err, err_cap);
+            P.start_end_unit[P.n_start_end++] = (uint32_t)u;
+        }
+    // candidate gate tables
+    GateParams& G = rs->gate_base;
+    memset(&G, 0, sizeof G);
+    for (int f = 0; f < 5; ++f) {
+        if (!H.gate[f].present) continue;
+        if (G.n_fields >= kMaxGateFields) return fail("too many gated fields", err, err_cap);
+        GateField& gf = G.f[G.n_fields];
+        gf.b1 = (const uint32_t*)chk(M.upload(H.gate[f].b1));
+        gf.b2 = (const uint32_t*)chk(M.upload(H.gate[f].b2));
+        gf.k1 = H.gate[f].k1;
+        gf.k2 = H.gate[f].k2;
+        rs->gate_field[G.n_fields++] = f;
+    }
+    rs->gate_smem = waf_gate_smem_bytes(G);
+    if (rs->gate_smem > rs->max_smem) return fail("candidate-gate bitmaps do not fit shared memory", err, err_cap);
     P.acc_idx = (const uint32_t*)chk(M.upload(H.acc_idx));
     P.acc_events = (const uint32_t*)chk(M.upload(H.acc_events));
     P.end_idx = (const uint32_t*)chk(M.upload(H.end_idx));
@@ -236,6 +342,9 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     P.s1 = (const uint16_t*)chk(M.upload(H.s1));
     P.n_waf_rules = H.n_waf_rules;
     P.s0 = H.s0;
+    P.vclean[0] = H.vclean[0];
+    P.vclean[1] = H.vclean[1];
+    P.sclean = H.sclean;
     P.dflt_services = (const uint32_t*)chk(M.upload(H.dflt_services));
     P.n_dflt_services = (uint32_t)H.dflt_services.size();
     P.service = nullptr;
@@ -262,42 +371,15 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
         P.v6_leaf = (const uint32_t*)chk(M.upload(H.lpm.v6_leaf));
         P.n_v6 = (uint32_t)H.lpm.v6_leaf.size();
     }
-    std::vector<uint32_t> zeros(64, 0);
-    rs->counters = (uint32_t*)chk(M.upload(zeros));
-    rs->stream_smem = waf_stream_smem_bytes((uint32_t)image.size(), (uint32_t)units.size());
-    rs->field_smem = waf_field_smem_bytes((uint32_t)image.size(), (uint32_t)units.size());
-    {
-        const char* km = getenv("PGW_KERNEL");
-        // default path: unit-major field scan; "lane" (request-major persistent kernel) and "stream" (speculative
-        // column scan) remain selectable for comparison
-        rs->stream_kernel = km && strcmp(km, "stream") == 0 && units.size() <= kMaxConstUnits;
-        rs->field_kernel = (!km || (strcmp(km, "lane") != 0 && strcmp(km, "stream") != 0)) && units.size() <= kMaxConstUnits;
-    }
     if (!ok) {
         M.release();
         return fail(std::string("CUDA: device allocation/upload failed: ") + cudaGetErrorString(cudaGetLastError()), err, err_cap);
-    }
-    bool sok = cudaStreamCreateWithFlags(&rs->stream, cudaStreamNonBlocking) == cudaSuccess &&
-               cudaStreamCreateWithFlags(&rs->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
-    for (uint32_t i = 0; i < kHostSlices && sok; ++i) sok = cudaEventCreateWithFlags(&rs->slice_ready[i], cudaEventDisableTiming) == cudaSuccess;
-    if (!sok) {
-        M.release();
-        return fail("CUDA: stream creation failed", err, err_cap);
-    }
-    {
-        // scratch of the field/stream paths comes from the stream-ordered allocator: keep freed blocks cached in the
-        // pool instead of returning them to the driver at every synchronisation
-        cudaMemPool_t pool = nullptr;
-        if (cudaDeviceGetDefaultMemPool(&pool, rs->device) == cudaSuccess && pool) {
-            uint64_t keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
     }
     rs->finalized = true;
     return 0;
 }
 
-static int launch_on(const pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdict_out, void* stream, std::string& e, uint16_t* service_out = nullptr) {
+static int launch_on(pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdict_out, void* stream, std::string& e, uint16_t* service_out = nullptr) {
     const HostProgram& H = rs->prog;
     KParams P = rs->base;
     const pgw_strcol* cols[5] = {&b->host, &b->url, &b->path, &b->method, &b->user_agent};
@@ -311,10 +393,13 @@ static int launch_on(const pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdic
     P.ip = b->ip;
     P.is_v6 = b->ip_is_v6;
     P.port = b->remote_port;
-    P.asn = b->asn;
-    P.country = b->country;
+    // the geo columns count only when BOTH are supplied (the reference resolves asn and country together, before the
+    // context is built: http_listener.rs:143-157); otherwise both come from the loaded database, or are {0, "XX"}
+    const bool geo_cols = b->asn && b->country;
+    P.asn = geo_cols ? b->asn : nullptr;
+    P.country = geo_cols ? b->country : nullptr;
     P.flags = b->flags;
-    bool geo_on_device = H.lpm.geo_loaded && H.needs_geo_cols && !(b->asn && b->country);
+    bool geo_on_device = H.lpm.geo_loaded && H.needs_geo_cols && !geo_cols;
     P.need_lpm = (H.needs_ip || geo_on_device) ? 1u : 0u;
     if (P.need_lpm && (!b->ip || !b->ip_is_v6)) { e = "batch is missing client.ip columns"; return 1; }
     if (H.needs_port && !b->remote_port) { e = "batch is missing client.remote_port"; return 1; }
@@ -322,41 +407,38 @@ static int launch_on(const pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdic
     P.service = service_out;
     P.n = b->n;
     if (b->n == 0) return 0;
-    // each in-flight launch gets its own work counter (ring of 64), so concurrent callers do not interfere
-    uint64_t seq = const_cast<pgw_ruleset*>(rs)->launches.fetch_add(1, std::memory_order_relaxed);
-    P.work_counter = rs->counters + (seq & 63);
-    if (rs->field_kernel) {
-        const size_t row_words = (size_t)b->n * P.atom_words;
-        uint32_t* scratch = nullptr;
-        if (cudaMallocAsync((void**)&scratch, (row_words + kFieldCounters) * 4, (cudaStream_t)stream) != cudaSuccess) { e = "CUDA: scratch allocation failed"; return 1; }
-        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-        if (rs->profiling) {
-            const uint64_t k = const_cast<pgw_ruleset*>(rs)->prof_n.fetch_add(1, std::memory_order_relaxed) % kProfRing;
-            ev0 = rs->prof_ev[2 * k];
-            ev1 = rs->prof_ev[2 * k + 1];
-        }
-        const char* m = waf_field_launch(P, scratch, scratch + row_words, rs->sm_count, rs->field_smem, stream, ev0, ev1);
-        cudaFreeAsync(scratch, (cudaStream_t)stream);
-        if (m) { e = std::string("CUDA launch failed: ") + m; return 1; }
-        const_cast<pgw_ruleset*>(rs)->launches.fetch_add(1, std::memory_order_relaxed);  // two kernels per batch on this path
-        return 0;
+    cudaStream_t cs = (cudaStream_t)stream;
+    Scratch* sc = scratch_acquire(rs, b->n, cs, e);
+    if (!sc) return 1;
+    P.rows = sc->rows;
+    P.dirty = sc->dirty;
+    P.counters = sc->small;
+    GateParams G = rs->gate_base;
+    G.n = b->n;
+    for (uint32_t i = 0; i < G.n_fields; ++i) {
+        const int f = rs->gate_field[i];
+        G.f[i].col = cols[f]->bytes;
+        G.f[i].off = cols[f]->offsets;
+        G.f[i].cand_count = sc->small + kSmallCounters + f;
+        G.f[i].cand_idx = sc->cand[f][0];
+        G.f[i].cand_start = sc->cand[f][1];
+        G.f[i].cand_end = sc->cand[f][2];
+        P.cand_count[f] = G.f[i].cand_count;
+        P.cand_idx[f] = G.f[i].cand_idx;
+        P.cand_start[f] = G.f[i].cand_start;
+        P.cand_end[f] = G.f[i].cand_end;
     }
-    if (rs->stream_kernel) {
-        // scratch (atom bitmaps + task counter) comes from the stream-ordered allocator: no state shared between callers
-        const size_t row_words = (size_t)b->n * P.atom_words;
-        uint32_t* scratch = nullptr;
-        if (cudaMallocAsync((void**)&scratch, (row_words + 64) * 4, (cudaStream_t)stream) != cudaSuccess) { e = "CUDA: scratch allocation failed"; return 1; }
-        const char* m = waf_stream_launch(P, scratch, scratch + row_words + 16, rs->sm_count, rs->stream_smem, stream);
-        cudaFreeAsync(scratch, (cudaStream_t)stream);
-        if (m) { e = std::string("CUDA launch failed: ") + m; return 1; }
-        const_cast<pgw_ruleset*>(rs)->launches.fetch_add(1, std::memory_order_relaxed);  // two kernels per batch on this path
-        return 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (rs->profiling) {
+        const uint64_t k = rs->prof_n.fetch_add(1, std::memory_order_relaxed) % kProfRing;
+        ev0 = rs->prof_ev[2 * k];
+        ev1 = rs->prof_ev[2 * k + 1];
     }
-    LaunchPlan plan;
-    plan.smem_bytes = rs->smem_bytes;
-    uint32_t want = (b->n + kThreads - 1) / kThreads;
-    plan.grid = (int)(want < (uint32_t)rs->sm_count ? want : (uint32_t)rs->sm_count);
-    if (const char* m = waf_launch(P, plan, stream)) { e = std::string("CUDA launch failed: ") + m; return 1; }
+    uint32_t nl = 0;
+    const char* m = waf_batch_launch(P, G, rs->units.data(), sc->small, kSmallWords, rs->sm_count, rs->scan_smem, rs->gate_smem, stream, ev0, ev1, &nl);
+    scratch_release(rs, sc, cs);
+    rs->launches.fetch_add(nl, std::memory_order_relaxed);
+    if (m) { e = std::string("CUDA launch failed: ") + m; return 1; }
     return 0;
 }
 
@@ -372,7 +454,7 @@ int pgw_evaluate_batch_routed(const pgw_ruleset* rs, const pgw_batch* batch, uin
     cudaGetDevice(&cur);
     if (cur != rs->device) cudaSetDevice(rs->device);
     std::string e;
-    int rc = launch_on(rs, batch, verdict_out, stream, e, service_out);
+    int rc = launch_on(const_cast<pgw_ruleset*>(rs), batch, verdict_out, stream, e, service_out);
     if (cur != rs->device && cur >= 0) cudaSetDevice(cur);
     if (rc) return fail(e, nullptr, 0);
     return 0;
@@ -390,7 +472,24 @@ int pgw_evaluate_batch_routed_host(pgw_ruleset* rs, const pgw_batch* b, uint32_t
     cudaSetDevice(rs->device);
     const HostProgram& H = rs->prog;
     const uint32_t n = b->n;
-    cudaStream_t s = rs->stream, cs = rs->copy_stream;
+    // staging (device buffers, two streams, slice events) comes from a pool: concurrent callers each get their own
+    HostStage* hs = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(rs->pool_mu);
+        for (HostStage* h : rs->stages)
+            if (!h->busy) { hs = h; break; }
+        if (!hs) {
+            hs = new HostStage();
+            if (!hs->init()) { hs->release(); delete hs; return fail("CUDA: stream creation failed", nullptr, 0); }
+            rs->stages.push_back(hs);
+        }
+        hs->busy = true;
+    }
+    struct Unbusy {
+        pgw_ruleset* rs; HostStage* hs;
+        ~Unbusy() { std::lock_guard<std::mutex> lk(rs->pool_mu); hs->busy = false; }
+    } unbusy{rs, hs};
+    cudaStream_t s = hs->stream, cs = hs->copy_stream;
     const pgw_strcol* hc[5] = {&b->host, &b->url, &b->path, &b->method, &b->user_agent};
     const bool geo_on_device = H.lpm.geo_loaded && H.needs_geo_cols && !(b->asn && b->country);
     const bool need_ip = H.needs_ip || geo_on_device;
@@ -404,35 +503,35 @@ int pgw_evaluate_batch_routed_host(pgw_ruleset* rs, const pgw_batch* b, uint32_t
     for (int f = 0; f < 5 && ok; ++f) {
         if (H.field_slot[f] < 0) continue;
         if (!hc[f]->offsets) return fail(std::string("batch is missing offsets for http_request.") + kFieldNames[f], nullptr, 0);
-        ok = rs->stage_offs[f].ensure((size_t)(n + 1) * 4);
-        dc[f]->offsets = (const uint32_t*)rs->stage_offs[f].d;
+        ok = hs->offs[f].ensure((size_t)(n + 1) * 4);
+        dc[f]->offsets = (const uint32_t*)hs->offs[f].d;
         if (ok && ((H.scanned_fields_mask >> f) & 1)) {
             if (!hc[f]->bytes) return fail(std::string("batch is missing bytes for http_request.") + kFieldNames[f], nullptr, 0);
-            ok = rs->stage_cols[f].ensure((size_t)hc[f]->offsets[n] + 64);
-            dc[f]->bytes = (const uint8_t*)rs->stage_cols[f].d;
+            ok = hs->cols[f].ensure((size_t)hc[f]->offsets[n] + 64);
+            dc[f]->bytes = (const uint8_t*)hs->cols[f].d;
         }
     }
     if (need_ip) {
         if (!b->ip || !b->ip_is_v6) return fail("batch is missing client.ip columns", nullptr, 0);
-        ok = ok && rs->stage_ip.ensure((size_t)n * 16) && rs->stage_v6.ensure(n);
-        d.ip = (const uint8_t*)rs->stage_ip.d;
-        d.ip_is_v6 = (const uint8_t*)rs->stage_v6.d;
+        ok = ok && hs->ip.ensure((size_t)n * 16) && hs->v6.ensure(n);
+        d.ip = (const uint8_t*)hs->ip.d;
+        d.ip_is_v6 = (const uint8_t*)hs->v6.d;
     }
     if (H.needs_port) {
         if (!b->remote_port) return fail("batch is missing client.remote_port", nullptr, 0);
-        ok = ok && rs->stage_port.ensure((size_t)n * 4);
-        d.remote_port = (const int32_t*)rs->stage_port.d;
+        ok = ok && hs->port.ensure((size_t)n * 4);
+        d.remote_port = (const int32_t*)hs->port.d;
     }
     if (geo_cols) {
-        ok = ok && rs->stage_asn.ensure((size_t)n * 8) && rs->stage_country.ensure((size_t)n * 2);
-        d.asn = (const int64_t*)rs->stage_asn.d;
-        d.country = (const uint16_t*)rs->stage_country.d;
+        ok = ok && hs->asn.ensure((size_t)n * 8) && hs->country.ensure((size_t)n * 2);
+        d.asn = (const int64_t*)hs->asn.d;
+        d.country = (const uint16_t*)hs->country.d;
     }
     if (b->flags) {
-        ok = ok && rs->stage_flags.ensure(n);
-        d.flags = (const uint8_t*)rs->stage_flags.d;
+        ok = ok && hs->flags.ensure(n);
+        d.flags = (const uint8_t*)hs->flags.d;
     }
-    ok = ok && rs->stage_verdict.ensure((size_t)n * 4) && (!service_out || rs->stage_service.ensure((size_t)n * 2));
+    ok = ok && hs->verdict.ensure((size_t)n * 4) && (!service_out || hs->service.ensure((size_t)n * 2));
     if (!ok) return fail("CUDA: staging allocation failed", nullptr, 0);
 
     // The batch is cut into slices of whole requests: slice k is copied on the copy stream while slice k-1 is evaluated
@@ -467,8 +566,8 @@ int pgw_evaluate_batch_routed_host(pgw_ruleset* rs, const pgw_batch* b, uint32_t
             if (H.field_slot[f] >= 0 && ((H.scanned_fields_mask >> f) & 1))
                 up(dc[f]->bytes, hc[f]->bytes, hc[f]->offsets[a], (size_t)hc[f]->offsets[z] - hc[f]->offsets[a]);
         if (ce != cudaSuccess) break;
-        if ((ce = cudaEventRecord(rs->slice_ready[k], cs)) != cudaSuccess) break;
-        if ((ce = cudaStreamWaitEvent(s, rs->slice_ready[k], 0)) != cudaSuccess) break;
+        if ((ce = cudaEventRecord(hs->slice_ready[k], cs)) != cudaSuccess) break;
+        if ((ce = cudaStreamWaitEvent(s, hs->slice_ready[k], 0)) != cudaSuccess) break;
         pgw_batch v = d;
         v.n = m;
         pgw_strcol* vc[5] = {&v.host, &v.url, &v.path, &v.method, &v.user_agent};
@@ -478,8 +577,8 @@ int pgw_evaluate_batch_routed_host(pgw_ruleset* rs, const pgw_batch* b, uint32_t
         if (v.remote_port) v.remote_port += a;
         if (v.asn) { v.asn += a; v.country += a; }
         if (v.flags) v.flags += a;
-        uint32_t* vd = (uint32_t*)rs->stage_verdict.d + a;
-        uint16_t* sd = service_out ? (uint16_t*)rs->stage_service.d + a : nullptr;
+        uint32_t* vd = (uint32_t*)hs->verdict.d + a;
+        uint16_t* sd = service_out ? (uint16_t*)hs->service.d + a : nullptr;
         if (launch_on(rs, &v, vd, s, e, sd)) { cudaStreamSynchronize(cs); cudaStreamSynchronize(s); return fail(e, nullptr, 0); }
         if ((ce = cudaMemcpyAsync(verdict_out + a, vd, (size_t)m * 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
         if (sd && (ce = cudaMemcpyAsync(service_out + a, sd, (size_t)m * 2, cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
@@ -487,8 +586,8 @@ int pgw_evaluate_batch_routed_host(pgw_ruleset* rs, const pgw_batch* b, uint32_t
     cudaError_t c1 = cudaStreamSynchronize(cs), c2 = cudaStreamSynchronize(s);
     if (ce == cudaSuccess) ce = c1 != cudaSuccess ? c1 : c2;
     if (ce != cudaSuccess) return fail(std::string("CUDA: ") + cudaGetErrorString(ce), nullptr, 0);
-    rs->last_h2d = h2d;
-    rs->last_d2h = (uint64_t)n * (service_out ? 6 : 4);
+    rs->last_h2d.store(h2d);
+    rs->last_d2h.store((uint64_t)n * (service_out ? 6 : 4));
     return 0;
 }
 
@@ -496,8 +595,13 @@ int pgw_geoip_lookup_batch(const pgw_ruleset* rs, const uint8_t* ip, const uint8
                            uint16_t* country_out, void* stream) {
     if (!rs || !rs->finalized) return fail("ruleset is not finalized", nullptr, 0);
     if (n && (!ip || !ip_is_v6 || !asn_out || !country_out)) return fail("null argument", nullptr, 0);
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != rs->device) cudaSetDevice(rs->device);
     KParams P = rs->base;
-    if (const char* m = geoip_launch(P, ip, ip_is_v6, n, asn_out, country_out, stream)) return fail(std::string("CUDA launch failed: ") + m, nullptr, 0);
+    const char* m = geoip_launch(P, ip, ip_is_v6, n, asn_out, country_out, stream);
+    if (cur != rs->device && cur >= 0) cudaSetDevice(cur);
+    if (m) return fail(std::string("CUDA launch failed: ") + m, nullptr, 0);
     if (n) const_cast<pgw_ruleset*>(rs)->launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
@@ -571,17 +675,20 @@ int pgw_ruleset_info(const pgw_ruleset* rs, pgw_info* out) {
     out->reads_port = H.needs_port;
     out->reads_geo_columns = H.needs_geo_cols;
     out->table_arena_bytes = H.arena.size();
-    out->smem_bytes = rs->smem_bytes;
+    out->smem_bytes = rs->scan_smem;
     for (auto& u : H.units) out->total_dfa_states += u.n_states;
     out->tables_in_smem = rs->hot_states_total == out->total_dfa_states;
     out->hot_dfa_states = rs->hot_states_total;  /* states whose rows live in shared memory */
     out->grid = (uint32_t)rs->sm_count;
-    out->threads = rs->field_kernel ? (uint32_t)waf_field_threads() : (uint32_t)kThreads;
+    out->threads = (uint32_t)waf_scan_threads();
+    for (int f = 0; f < 5; ++f)
+        if (H.gate[f].present) { out->gated_fields_mask |= 1u << f; out->gate_grams += H.gate[f].n_grams; }
+    out->gate_smem_bytes = rs->gate_smem;
     out->lpm_present = H.lpm.present;
     out->geoip_loaded = H.lpm.geo_loaded;
     out->kernel_launches = rs->launches.load();
-    out->last_h2d_bytes = rs->last_h2d;
-    out->last_d2h_bytes = rs->last_d2h;
+    out->last_h2d_bytes = rs->last_h2d.load();
+    out->last_d2h_bytes = rs->last_d2h.load();
     return 0;
 }
 
@@ -601,14 +708,13 @@ void pgw_ruleset_destroy(pgw_ruleset* rs) {
     if (!rs) return;
     if (rs->device >= 0) cudaSetDevice(rs->device);
     rs->mem.release();
-    for (int f = 0; f < 5; ++f) { rs->stage_cols[f].release(); rs->stage_offs[f].release(); }
-    rs->stage_ip.release(); rs->stage_v6.release(); rs->stage_port.release(); rs->stage_asn.release();
-    rs->stage_country.release(); rs->stage_flags.release(); rs->stage_verdict.release(); rs->stage_service.release();
-    if (rs->stream) cudaStreamDestroy(rs->stream);
-    if (rs->copy_stream) cudaStreamDestroy(rs->copy_stream);
+    for (HostStage* h : rs->stages) { h->release(); delete h; }
+    for (Scratch* sc : rs->pool) {
+        if (sc->done) { cudaEventSynchronize(sc->done); cudaEventDestroy(sc->done); }
+        if (sc->base) cudaFree(sc->base);
+        delete sc;
+    }
     for (auto& ev : rs->prof_ev)
-        if (ev) cudaEventDestroy(ev);
-    for (auto& ev : rs->slice_ready)
         if (ev) cudaEventDestroy(ev);
     delete rs;
 }

@@ -2,11 +2,15 @@
 #include "compile.hpp"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <iterator>
 #include <sstream>
 
 #include "dfa.hpp"
+#include "gate.hpp"
 
 namespace pgw {
 namespace {
@@ -67,7 +71,10 @@ std::string HostProgram::summary() const {
     std::ostringstream o;
     o << "rules=" << n_rules << " atoms=" << n_atoms << " units=" << units.size() << " arena_bytes=" << arena.size();
     for (size_t u = 0; u < units.size(); ++u)
-        o << " [" << kFieldNames[units[u].field] << ": states=" << units[u].n_states << " classes=" << units[u].n_classes << "]";
+        o << " [" << kFieldNames[units[u].field] << (units[u].mode == UM_CANDIDATES ? "/gated" : units[u].abs0 != 0xFFFFFFFFu ? "/early-exit" : "")
+          << ": states=" << units[u].n_states << " classes=" << units[u].n_classes << "]";
+    for (int f = 0; f < N_FIELDS; ++f)
+        if (gate[f].present) o << " gate(" << kFieldNames[f] << ": grams=" << gate[f].n_grams << " bits=2^" << gate[f].k1 << ")";
     o << " ns_atoms=" << ns_atoms.size() << " lpm=" << (lpm.present ? 1 : 0);
     return o.str();
 }
@@ -280,16 +287,43 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
         }
     }
 
+    // a request none of whose atoms is true (the overwhelmingly common case once complements are in place): its
+    // verdict and service are constants, the epilogue writes them without touching the atom bitmap
+    {
+        std::vector<uint8_t> zeros(H.n_atoms, 0);
+        for (int cv = 0; cv < 2; ++cv) {
+            H.vclean[cv] = V_ALLOW | (kNoRule << 2);
+            for (size_t r = 0; r < H.n_waf_rules; ++r) {
+                uint8_t t = (H.term[r] >> (2 * cv)) & 3;
+                if (!t || !M.pool.eval(M.rules[r].formula, zeros)) continue;
+                H.vclean[cv] = t | ((uint32_t)r << 2);
+                break;
+            }
+        }
+        H.sclean = kNoService;
+        for (size_t r = H.n_waf_rules; r < M.rules.size(); ++r)
+            if (M.pool.eval(M.rules[r].formula, zeros)) { H.sclean = (uint32_t)(r - H.n_waf_rules); break; }
+    }
+
     // ---- scan units: DFA groups per field ------------------------------------------
+    // The string atoms of a field fall into three classes:
+    //   anchored  every triggering pattern is tied to the start of the field (starts_with, ==, ^...): decided by a prefix,
+    //             walked for every request but only until the DFA reaches an absorbing state (UnitDesc::abs0/abs1);
+    //   gated     url / user_agent / path patterns the candidate gate covers (gate.hpp): walked for gate candidates only;
+    //   full      everything else: walked for every request, whole field.
     bool len_feat_used[N_FIELDS] = {false, false, false, false, false};
     static const int kFieldOrder[N_FIELDS] = {F_URL, F_USER_AGENT, F_PATH, F_HOST, F_METHOD};  // longest first
+    enum { UC_FULL = 0, UC_ANCH = 1, UC_GATED = 2, N_UC = 3 };
     // arena: all class maps first, then the tables
-    struct Pending { Dfa dfa; int field; std::vector<int> latch_of_event; };
+    struct Pending { Dfa dfa; int field; uint32_t mode; std::vector<int> latch_of_event; };
     std::vector<Pending> pend;
     for (int fo = 0; fo < N_FIELDS; ++fo) {
         int f = kFieldOrder[fo];
-        std::vector<PatternBundle> bundles;
-        std::vector<uint32_t> bundle_atom;
+        const bool gate_field = opt.candidate_gate && (f == F_URL || f == F_USER_AGENT || f == F_PATH);
+        std::vector<PatternBundle> bundles[N_UC];
+        std::vector<uint32_t> bundle_atom[N_UC];
+        struct GatedGrams { std::vector<uint32_t> grams; };
+        std::vector<GatedGrams> gated_grams;
         for (uint32_t a = 0; a < H.n_atoms; ++a)
             if (M.atoms[a].kind == AtomDesc::STR_PATTERN && M.atoms[a].field == f) {
                 // atoms no rule refers to any more (replaced by their complement) are not scanned
@@ -297,34 +331,82 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
                 PatternBundle b;
                 b.starts = M.atoms[a].nfa_starts;
                 b.has_latch = M.atoms[a].has_latch;
-                bundles.push_back(std::move(b));
-                bundle_atom.push_back(a);
+                int cls = UC_FULL;
+                if (gate_field) {
+                    // the parts whose match can make the atom true: FIRE, and SET of a gap-split pattern (TEST needs an
+                    // earlier SET, CLEAR never fires)
+                    bool all_anch = true, all_gate = true;
+                    GatedGrams gg;
+                    for (size_t k = 0; k < b.starts.size(); ++k) {
+                        const uint8_t kind = M.events[M.atoms[a].event_base + k].kind;
+                        if (kind != EV_FIRE && kind != EV_SET) continue;
+                        if (!pattern_is_start_anchored(M.nfa[f], b.starts[k])) all_anch = false;
+                        if (all_gate && !gate_grams_for_pattern(M.nfa[f], b.starts[k], opt.gate_pattern_cap, &gg.grams)) all_gate = false;
+                    }
+                    if (all_anch) cls = UC_ANCH;
+                    else if (all_gate) { cls = UC_GATED; gated_grams.push_back(std::move(gg)); }
+                }
+                if (getenv("PGW_DEBUG_CLASSES") && cls == UC_GATED && gated_grams.back().grams.size() > 300) fprintf(stderr, "gated field %s grams %zu: %s\n", kFieldNames[f], gated_grams.back().grams.size(), M.atoms[a].key.c_str());
+                bundles[cls].push_back(std::move(b));
+                bundle_atom[cls].push_back(a);
             }
-        if (bundles.empty()) continue;
-        DfaGroups groups;
-        int failed = -1;
-        if (!build_dfa_groups(M.nfa[f], bundles, opt.max_dfa_states, opt.max_unit_table_bytes, (int)kMaxLatchesPerUnit, &groups, &failed)) {
-            std::string which = failed >= 0 ? M.atoms[bundle_atom[failed]].key : "?";
-            err = "pattern on http_request." + std::string(kFieldNames[f]) + " needs a DFA larger than " +
-                  std::to_string(opt.max_dfa_states) + " states: " + which;
-            return false;
-        }
-        for (size_t g = 0; g < groups.dfas.size(); ++g) {
-            Pending pd;
-            pd.dfa = std::move(groups.dfas[g]);
-            pd.field = f;
-            // latch numbering is local to the unit
-            pd.latch_of_event.assign(M.events.size(), 0);
-            int next_latch = 0;
-            for (int bi : groups.members[g]) {
-                const AtomDesc& ad = M.atoms[bundle_atom[bi]];
-                if (!ad.has_latch) continue;
-                for (size_t k = 0; k < ad.nfa_starts.size(); ++k) pd.latch_of_event[ad.event_base + k] = next_latch;
-                ++next_latch;
+        // the field's gram budget (distinct grams: patterns built from one template share most of theirs): patterns are
+        // admitted smallest set first, the ones that no longer fit fall back to the full class
+        if (!bundles[UC_GATED].empty()) {
+            std::vector<size_t> order(gated_grams.size());
+            for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return gated_grams[x].grams.size() < gated_grams[y].grams.size(); });
+            std::vector<uint32_t> all;
+            std::vector<char> keep(gated_grams.size(), 0);
+            for (size_t i : order) {
+                std::vector<uint32_t> g = gated_grams[i].grams, merged;
+                std::sort(g.begin(), g.end());
+                g.erase(std::unique(g.begin(), g.end()), g.end());
+                std::set_union(all.begin(), all.end(), g.begin(), g.end(), std::back_inserter(merged));
+                if (merged.size() > opt.gate_field_cap) continue;
+                all.swap(merged);
+                keep[i] = 1;
             }
-            pend.push_back(std::move(pd));
+            std::vector<PatternBundle> kept_b;
+            std::vector<uint32_t> kept_a;
+            for (size_t i = 0; i < gated_grams.size(); ++i) {
+                if (keep[i]) { kept_b.push_back(std::move(bundles[UC_GATED][i])); kept_a.push_back(bundle_atom[UC_GATED][i]); }
+                else { bundles[UC_FULL].push_back(std::move(bundles[UC_GATED][i])); bundle_atom[UC_FULL].push_back(bundle_atom[UC_GATED][i]); }
+            }
+            bundles[UC_GATED].swap(kept_b);
+            bundle_atom[UC_GATED].swap(kept_a);
+            if (!bundles[UC_GATED].empty()) gate_build_tables(std::move(all), &H.gate[f]);
         }
-        H.scanned_fields_mask |= 1u << f;
+        bool any = false;
+        for (int cls = 0; cls < N_UC; ++cls) {
+            if (bundles[cls].empty()) continue;
+            any = true;
+            DfaGroups groups;
+            int failed = -1;
+            if (!build_dfa_groups(M.nfa[f], bundles[cls], opt.max_dfa_states, opt.max_unit_table_bytes, (int)kMaxLatchesPerUnit, &groups, &failed)) {
+                std::string which = failed >= 0 ? M.atoms[bundle_atom[cls][failed]].key : "?";
+                err = "pattern on http_request." + std::string(kFieldNames[f]) + " needs a DFA larger than " +
+                      std::to_string(opt.max_dfa_states) + " states: " + which;
+                return false;
+            }
+            for (size_t g = 0; g < groups.dfas.size(); ++g) {
+                Pending pd;
+                pd.dfa = std::move(groups.dfas[g]);
+                pd.field = f;
+                pd.mode = cls == UC_GATED ? UM_CANDIDATES : UM_ALL;
+                // latch numbering is local to the unit
+                pd.latch_of_event.assign(M.events.size(), 0);
+                int next_latch = 0;
+                for (int bi : groups.members[g]) {
+                    const AtomDesc& ad = M.atoms[bundle_atom[cls][bi]];
+                    if (!ad.has_latch) continue;
+                    for (size_t k = 0; k < ad.nfa_starts.size(); ++k) pd.latch_of_event[ad.event_base + k] = next_latch;
+                    ++next_latch;
+                }
+                pend.push_back(std::move(pd));
+            }
+        }
+        if (any) H.scanned_fields_mask |= 1u << f;
     }
     // class maps
     std::vector<uint32_t> cls_offs;
@@ -372,20 +454,17 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
         H.end_idx.push_back((uint32_t)H.end_events.size());
         ud.hot_states = ud.n_states;
         ud.hot_off = ud.tbl_off;
-        // idle state: the mode of the state distribution on pseudo-random printable text (speculation hint only)
-        {
-            std::vector<uint32_t> hist(d.n_states, 0);
-            uint32_t st = (uint32_t)d.start;
-            uint64_t x = 0x9E3779B97F4A7C15ull;
-            static const char kText[] = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789/=&?-_.%+ ";
-            for (int i = 0; i < 20000; ++i) {
-                x ^= x << 13; x ^= x >> 7; x ^= x << 17;
-                unsigned char c = (unsigned char)kText[x % (sizeof(kText) - 1)];
-                st = d.trans[(size_t)st * d.n_classes + d.classmap[c]];
-                hist[st]++;
-            }
-            ud.idle_state = (uint32_t)(std::max_element(hist.begin(), hist.end()) - hist.begin());
+        ud.mode = pend[u].mode;
+        // absorbing states: once reached nothing can change any more, the field is finished as if it ended there
+        ud.abs0 = ud.abs1 = 0xFFFFFFFFu;
+        for (int st = 0; st < d.n_states; ++st) {
+            bool absorbing = true;
+            for (int c = 0; c < d.n_classes && absorbing; ++c) absorbing = d.trans[(size_t)st * d.n_classes + c] == (uint16_t)st;
+            if (!absorbing || (st >= d.acc_lo && !d.acc[st].empty())) continue;  // a sticky accepting state keeps firing: not handled early
+            if (ud.abs0 == 0xFFFFFFFFu) ud.abs0 = (uint32_t)st;
+            else if (ud.abs1 == 0xFFFFFFFFu) ud.abs1 = (uint32_t)st;
         }
+        ud.start_end = d.endacc[d.start].empty() ? 0u : 1u;
         ud.has_latch = 0;
         for (int lv : pend[u].latch_of_event) if (lv) ud.has_latch = 1;
         for (size_t a = 0; a < M.atoms.size(); ++a)
@@ -451,50 +530,45 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
     return true;
 }
 
-void build_smem_image(const HostProgram& H, size_t budget, std::vector<uint8_t>* image, std::vector<UnitDesc>* units) {
+void build_unit_images(const HostProgram& H, size_t budget, std::vector<uint8_t>* image, std::vector<UnitDesc>* units) {
     *units = H.units;
     image->clear();
-    const size_t U = H.units.size();
-    image->insert(image->end(), H.arena.begin(), H.arena.begin() + U * 256);  // class maps keep their arena offsets
-    if (budget < image->size()) budget = image->size();
-    size_t left = budget - image->size();
-    left = left > 16 * U ? left - 16 * U : 0;  // padding slack
-    for (size_t u = 0; u < U; ++u) {  // acc1 tables (upper bound: every accepting state hot)
-        size_t a1 = 2 * (size_t)(H.units[u].n_states - H.units[u].acc_lo) + 2 * (size_t)H.units[u].n_states + 8;
-        left = left > a1 ? left - a1 : 0;
-    }
-    // expected bytes per request of each field decide who gets shared memory first
-    static const double kWeight[N_FIELDS] = {13, 240, 35, 3, 95};
-    std::vector<size_t> give(U, 0), order(U);
-    auto row_bytes = [&](size_t u) { return (size_t)H.units[u].n_classes * 2; };
-    // Rows are handed out in passes of growing depth (32, 256, 1024, all states), each pass in order of expected
-    // traffic, so no DFA is starved: visit frequency falls off steeply with BFS depth (measured on the synthetic
-    // stream: the first 256 states of a 2300-state URL automaton receive 99.97 % of the transitions).
-    // Every unit also needs one extra "trap" row.
-    for (size_t u = 0; u < U; ++u) {
-        order[u] = u;
-        if (row_bytes(u) <= left) left -= row_bytes(u);  // trap row
-    }
-    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return kWeight[H.units[a].field] > kWeight[H.units[b].field]; });
-    static const size_t kPass[4] = {32, 256, 1024, (size_t)1 << 30};
-    for (size_t pass = 0; pass < 4; ++pass)
-        for (size_t u : order) {
-            size_t target = std::min<size_t>(H.units[u].n_states, kPass[pass]);
-            if (target <= give[u]) continue;
-            size_t add = std::min(target - give[u], left / row_bytes(u));
-            give[u] += add;
-            left -= add * row_bytes(u);
-        }
-    for (size_t u = 0; u < U; ++u) {
-        while (image->size() % 16) image->push_back(0);
+    for (size_t u = 0; u < H.units.size(); ++u) {
+        while (image->size() % 256) image->push_back(0);
         UnitDesc& ud = (*units)[u];
-        ud.hot_states = (uint32_t)give[u];
-        ud.hot_off = (uint32_t)image->size();
+        const size_t base = image->size();
+        ud.img_off = (uint32_t)base;
+        image->insert(image->end(), H.arena.begin() + H.units[u].cls_off, H.arena.begin() + H.units[u].cls_off + 256);
+        const size_t C = ud.n_classes, row = C * 2;
+        // fixed parts: class map, trap row, acc1 (upper bound: every accepting state hot), end1, alignment slack
+        size_t fixed = 256 + row + 2 * (size_t)(ud.n_states - ud.acc_lo) + 2 * (size_t)ud.n_states + 64;
+        size_t give = ud.n_states;
+        if (fixed + give * row > budget) {
+            give = budget > fixed ? (budget - fixed) / row : 0;
+            // acc1 / end1 only cover hot states: recompute with the real sizes (they shrink with `give`)
+            for (;;) {
+                size_t acc_hot = give > ud.acc_lo ? give - ud.acc_lo : 0;
+                size_t need = 256 + row + 2 * acc_hot + 2 * give + 64 + give * row;
+                if (need <= budget || give == 0) break;
+                --give;
+            }
+            size_t more = give;
+            for (;;) {  // grow back while it fits
+                size_t g2 = more + 1;
+                if (g2 > ud.n_states) break;
+                size_t acc_hot = g2 > ud.acc_lo ? g2 - ud.acc_lo : 0;
+                if (256 + row + 2 * acc_hot + 2 * g2 + 64 + g2 * row > budget) break;
+                more = g2;
+            }
+            give = more;
+        }
+        ud.hot_states = (uint32_t)give;
         ud.lim = std::min(ud.hot_states, ud.acc_lo);
+        while (image->size() % 16) image->push_back(0);
+        ud.hot_off = (uint32_t)(image->size() - base);
         const uint16_t* src = reinterpret_cast<const uint16_t*>(H.arena.data() + H.units[u].tbl_off);
         const uint16_t trap = (uint16_t)ud.hot_states;
-        const size_t C = ud.n_classes;
-        for (size_t s = 0; s < give[u]; ++s)
+        for (size_t s = 0; s < give; ++s)
             for (size_t c = 0; c < C; ++c) {
                 uint16_t t = src[s * C + c];
                 if (t >= ud.hot_states) t = trap;  // only cold states trap; accepting states stay on the fast path
@@ -507,7 +581,7 @@ void build_smem_image(const HostProgram& H, size_t budget, std::vector<uint8_t>*
         }
         // acc1: one-atom FIRE lists resolved without leaving shared memory
         while (image->size() % 4) image->push_back(0);
-        ud.acc1_off = (uint32_t)image->size();
+        ud.acc1_off = (uint32_t)(image->size() - base);
         for (uint32_t st = ud.acc_lo; st < ud.hot_states; ++st) {
             uint32_t ci = ud.acc_base + st - ud.acc_lo;
             uint32_t a = H.acc_idx[ci], b = H.acc_idx[ci + 1];
@@ -518,7 +592,7 @@ void build_smem_image(const HostProgram& H, size_t budget, std::vector<uint8_t>*
         }
         // end1: end-of-field events of hot states
         while (image->size() % 4) image->push_back(0);
-        ud.end1_off = (uint32_t)image->size();
+        ud.end1_off = (uint32_t)(image->size() - base);
         for (uint32_t st = 0; st < ud.hot_states; ++st) {
             uint32_t ci = ud.end_base + st;
             uint32_t a = H.end_idx[ci], b = H.end_idx[ci + 1];
@@ -528,8 +602,10 @@ void build_smem_image(const HostProgram& H, size_t budget, std::vector<uint8_t>*
             image->push_back((uint8_t)(v & 0xFF));
             image->push_back((uint8_t)(v >> 8));
         }
+        while (image->size() % 16) image->push_back(0);
+        ud.img_bytes = (uint32_t)(image->size() - base);
     }
-    while (image->size() % 16) image->push_back(0);
+    while (image->size() % 256) image->push_back(0);
 }
 
 }  // namespace pgw

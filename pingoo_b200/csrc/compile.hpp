@@ -3,6 +3,7 @@
 #include <string>
 #include <vector>
 
+#include "gate.hpp"
 #include "model.hpp"
 #include "program.hpp"
 
@@ -12,6 +13,9 @@ struct CompileOptions {
     int max_dfa_states = 16384;                // per scan unit, after minimisation
     size_t max_unit_table_bytes = 8u << 20;    // per scan unit transition table (hot rows go to shared memory, the rest stays in L2)
     bool eval_gates = true;                    // evaluate http_listener.rs:196-204 gates inside the engine
+    bool candidate_gate = true;                // gram prefilter in front of the DFA scan of url / user_agent / path (gate.hpp)
+    size_t gate_pattern_cap = 4096;            // grams one pattern may contribute before it is left to an ungated unit
+    size_t gate_field_cap = 12288;             // grams per field (bitmaps of at most 2^19 bits each)
 };
 
 struct LpmTables {
@@ -51,6 +55,9 @@ struct HostProgram {
     std::vector<int64_t> iset_vals;
     std::vector<uint32_t> iset_off;
     std::vector<uint32_t> cset_words;
+    GateTables gate[N_FIELDS];               // candidate gate of a field (present only if it has UM_CANDIDATES units)
+    uint32_t vclean[2] = {0, 0};             // verdict of a request none of whose atoms is true, per captcha_verified
+    uint32_t sclean = 0xFFFFu;               // its service
     int field_slot[N_FIELDS] = {-1, -1, -1, -1, -1};  // fields whose offsets the kernel stages
     uint32_t n_slots = 0;
     uint32_t scanned_fields_mask = 0;  // fields whose bytes are read (algorithmic-bytes accounting)
@@ -67,10 +74,12 @@ struct HostProgram {
 bool compile_program(Model& model, const CompileOptions& opt, const std::vector<uint8_t>& geo_mmdb, HostProgram* out,
                      std::string& err);
 
-// Shared-memory image: every class map, then for each unit the rows of its first `hot_states` states
-// (BFS order from the start state, so these are the shallow, frequently visited ones).  Fills
-// units[u].hot_states / units[u].hot_off so that the image fits `budget_bytes`.
-void build_smem_image(const HostProgram& prog, size_t budget_bytes, std::vector<uint8_t>* image, std::vector<UnitDesc>* units);
+// Shared-memory images, one per unit (the scan kernel re-stages shared memory for every unit, so each DFA gets the
+// whole budget while it is being walked): class map, the rows of the first `hot_states` states (BFS order from the
+// start state, so these are the shallow, frequently visited ones) with transitions to deeper states redirected to a
+// trap row, and the acc1 / end1 event tables.  Fills units[u].{hot_states, hot_off, lim, acc1_off, end1_off, img_off,
+// img_bytes}; `image` is the concatenation (each piece 256-byte aligned, at most `budget_bytes` long).
+void build_unit_images(const HostProgram& prog, size_t budget_bytes, std::vector<uint8_t>* image, std::vector<UnitDesc>* units);
 
 // lists (pingoo/lists.rs:62-113)
 bool parse_list_csv(const std::string& name, ListType type, const uint8_t* csv, size_t len, ListData* out, std::string& err);

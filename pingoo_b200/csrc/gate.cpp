@@ -1,0 +1,311 @@
+// Gram extraction for the candidate gate (see gate.hpp).
+#include "gate.hpp"
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+
+namespace pgw {
+namespace {
+
+constexpr int kWild = 256;     // "any byte" symbol in a padded prefix
+constexpr int kPrefix = 5;     // padded prefixes are 5 symbols long: windows m[0..4) and m[1..5)
+constexpr size_t kMaxPrefixes = 4096;
+
+inline bool is_folded(int v) { return !((v & 0x40) && !(v & 0x20)); }
+
+// Enumerates the padded 5-byte prefixes (forward) or suffixes (backward) of a pattern's matches over folded bytes.
+struct Walker {
+    const Nfa& nfa;
+    const bool backward;
+    int start_node = -1;
+    std::vector<int> stamp;
+    int gen = 0;
+    std::vector<int> stack;
+    std::vector<std::vector<int>> radj;   // backward: predecessors within the pattern's sub-graph
+    std::vector<int> char_nodes;          // backward: byte-consuming nodes of the sub-graph
+    std::vector<std::array<int, kPrefix>> out;
+    bool overflow = false;
+
+    Walker(const Nfa& n, int start, bool back) : nfa(n), backward(back), start_node(start), stamp(n.nodes.size(), 0) {
+        if (!backward) return;
+        radj.resize(n.nodes.size());
+        std::vector<char> seen(n.nodes.size(), 0);
+        std::vector<int> st(1, start);
+        while (!st.empty()) {
+            int x = st.back();
+            st.pop_back();
+            if (x < 0 || seen[x]) continue;
+            seen[x] = 1;
+            const NfaNode& nd = nfa.nodes[x];
+            if (nd.kind == N_MATCH) continue;
+            if (nd.kind == N_CHAR) char_nodes.push_back(x);
+            if (nd.out >= 0) { radj[nd.out].push_back(x); st.push_back(nd.out); }
+            if (nd.kind == N_SPLIT && nd.out1 >= 0) { radj[nd.out1].push_back(x); st.push_back(nd.out1); }
+        }
+    }
+
+    // forward: epsilon closure with every assertion treated as satisfied (a superset of the real language);
+    //   `chars` = byte-consuming nodes reached, `edge` = a MATCH node is reachable (the match may end here)
+    // backward: reverse closure; `chars` = the closed node set itself, `edge` = the pattern's start node is in it
+    void closure(const std::vector<int>& from, std::vector<int>& chars, bool& edge) {
+        ++gen;
+        chars.clear();
+        edge = false;
+        stack.assign(from.begin(), from.end());
+        while (!stack.empty()) {
+            int n = stack.back();
+            stack.pop_back();
+            if (n < 0 || stamp[n] == gen) continue;
+            stamp[n] = gen;
+            const NfaNode& nd = nfa.nodes[n];
+            if (backward) {
+                chars.push_back(n);
+                if (n == start_node) edge = true;
+                for (int p : radj[n])
+                    if (nfa.nodes[p].kind != N_CHAR) stack.push_back(p);  // epsilon predecessors only
+                continue;
+            }
+            switch (nd.kind) {
+                case N_CHAR: chars.push_back(n); break;
+                case N_MATCH: edge = true; break;
+                case N_JUMP:
+                case N_ASSERT: stack.push_back(nd.out); break;
+                case N_SPLIT:
+                    stack.push_back(nd.out);
+                    stack.push_back(nd.out1);
+                    break;
+            }
+        }
+        std::sort(chars.begin(), chars.end());
+    }
+
+    // forward: pads the tail; backward: sequences are built last byte first and emitted in text order, padded in front
+    void emit(const std::array<int, kPrefix>& seq, int len) {
+        std::array<int, kPrefix> o;
+        o.fill(kWild);
+        if (!backward) for (int k = 0; k < len; ++k) o[k] = seq[k];
+        else for (int k = 0; k < len; ++k) o[kPrefix - 1 - k] = seq[k];
+        out.push_back(o);
+        if (out.size() > kMaxPrefixes) overflow = true;
+    }
+
+    void dfs(int depth, const std::vector<int>& cur, std::array<int, kPrefix>& seq) {
+        std::vector<int> next, nset;
+        std::vector<char> in_cur;
+        if (backward) {
+            in_cur.assign(nfa.nodes.size(), 0);
+            for (int n : cur) in_cur[n] = 1;
+        }
+        for (int v = 0; v < 256 && !overflow; ++v) {
+            if (!is_folded(v)) continue;
+            const int alt = ((v & 0x60) == 0x60) ? v - 0x20 : -1;  // the other byte folding to v
+            next.clear();
+            if (!backward) {
+                for (int c : cur) {
+                    const ByteSet& bs = nfa.sets[nfa.nodes[c].set];
+                    if (bs.test((unsigned)v) || (alt >= 0 && bs.test((unsigned)alt))) next.push_back(nfa.nodes[c].out);
+                }
+            } else {
+                for (int c : char_nodes) {
+                    if (!in_cur[nfa.nodes[c].out]) continue;
+                    const ByteSet& bs = nfa.sets[nfa.nodes[c].set];
+                    if (bs.test((unsigned)v) || (alt >= 0 && bs.test((unsigned)alt))) next.push_back(c);
+                }
+            }
+            if (next.empty()) continue;
+            bool edge = false;
+            closure(next, nset, edge);
+            seq[depth] = v;
+            const int d1 = depth + 1;
+            if (d1 == kPrefix) {
+                emit(seq, d1);
+                continue;
+            }
+            if (edge) emit(seq, d1);  // the match may end (begin) here: what follows (precedes) is arbitrary
+            bool more = !nset.empty();
+            if (backward && more) {
+                // anything byte-consuming before this point?
+                more = false;
+                std::vector<char> in(nfa.nodes.size(), 0);
+                for (int n : nset) in[n] = 1;
+                for (int c : char_nodes)
+                    if (in[nfa.nodes[c].out]) { more = true; break; }
+            }
+            if (more) {
+                std::vector<int> copy = nset;  // `nset` is reused by the recursion's siblings
+                dfs(d1, copy, seq);
+            }
+        }
+    }
+};
+
+// number of concrete grams a 4-symbol sequence expands to (192 folded values per wildcard)
+size_t expansion(const std::array<int, 4>& s) {
+    size_t n = 1;
+    for (int x : s)
+        if (x == kWild) n *= 192;
+    return n;
+}
+
+void expand(const std::array<int, 4>& s, std::vector<uint32_t>* out) {
+    std::vector<uint32_t> acc(1, 0u);
+    for (int k = 0; k < 4; ++k) {
+        std::vector<uint32_t> nx;
+        if (s[k] != kWild) {
+            for (uint32_t a : acc) nx.push_back(a | ((uint32_t)s[k] << (8 * k)));
+        } else {
+            for (uint32_t a : acc)
+                for (int v = 0; v < 256; ++v)
+                    if (is_folded(v)) nx.push_back(a | ((uint32_t)v << (8 * k)));
+        }
+        acc.swap(nx);
+    }
+    out->insert(out->end(), acc.begin(), acc.end());
+}
+
+}  // namespace
+
+bool pattern_is_start_anchored(const Nfa& nfa, int start) {
+    // closure that refuses to cross start-of-text assertions: anchored iff nothing byte-consuming (or a match) is left
+    std::vector<int> stack(1, start);
+    std::vector<char> seen(nfa.nodes.size(), 0);
+    while (!stack.empty()) {
+        int n = stack.back();
+        stack.pop_back();
+        if (n < 0 || seen[n]) continue;
+        seen[n] = 1;
+        const NfaNode& nd = nfa.nodes[n];
+        switch (nd.kind) {
+            case N_CHAR:
+            case N_MATCH: return false;
+            case N_JUMP: stack.push_back(nd.out); break;
+            case N_SPLIT:
+                stack.push_back(nd.out);
+                stack.push_back(nd.out1);
+                break;
+            case N_ASSERT:
+                if (nd.assert_kind != A_BOL_TEXT) stack.push_back(nd.out);
+                break;
+        }
+    }
+    return true;
+}
+
+bool gate_grams_for_pattern(const Nfa& nfa, int start, size_t cap, std::vector<uint32_t>* out) {
+    typedef std::vector<std::array<int, 4>> Seqs;
+    auto uniq = [](Seqs& v) {
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+    };
+    auto total = [&](const Seqs& v) {
+        size_t n = 0;
+        for (auto& s : v) {
+            n += expansion(s);
+            if (n > (cap << 4)) break;
+        }
+        return n;
+    };
+    // windows tied to the START of a match (gate.hpp): A = m[0..4), B = (any, m[0..3)) or m[1..5)
+    Seqs best_a, best_b;
+    size_t best = (size_t)-1;
+    {
+        Walker W(nfa, start, false);
+        std::vector<int> chars;
+        bool match = false;
+        W.closure(std::vector<int>(1, start), chars, match);
+        if (match) return false;         // matches the empty string: nothing to look for
+        if (chars.empty()) return true;  // matches nothing: no grams needed
+        std::array<int, kPrefix> seq;
+        seq.fill(kWild);
+        W.dfs(0, chars, seq);
+        if (!W.overflow) {
+            Seqs A, B1, B2;
+            for (auto& s : W.out) {
+                A.push_back({s[0], s[1], s[2], s[3]});
+                B1.push_back({kWild, s[0], s[1], s[2]});
+                B2.push_back({s[1], s[2], s[3], s[4]});
+            }
+            uniq(A);
+            uniq(B1);
+            uniq(B2);
+            const size_t na = total(A), nb1 = total(B1), nb2 = total(B2);
+            best = na + std::min(nb1, nb2);
+            best_a = A;
+            best_b = nb2 <= nb1 ? B2 : B1;
+        }
+    }
+    // windows tied to the END of a match (patterns that begin with a gap but end in a literal): with t = the last five
+    // bytes and q the end position, q even -> window [q-4, q) = t[1..5); q odd -> [q-3, q+1) = (t[2..5), any) or
+    // [q-5, q-1) = t[0..4)
+    {
+        Walker W(nfa, start, true);
+        int match_node = -1;
+        {
+            // the pattern's MATCH node: forward search
+            std::vector<char> seen(nfa.nodes.size(), 0);
+            std::vector<int> st(1, start);
+            while (!st.empty() && match_node < 0) {
+                int x = st.back();
+                st.pop_back();
+                if (x < 0 || seen[x]) continue;
+                seen[x] = 1;
+                const NfaNode& nd = nfa.nodes[x];
+                if (nd.kind == N_MATCH) { match_node = x; break; }
+                st.push_back(nd.out);
+                if (nd.kind == N_SPLIT) st.push_back(nd.out1);
+            }
+        }
+        if (match_node >= 0) {
+            std::vector<int> set0;
+            bool at_start = false;
+            W.closure(std::vector<int>(1, match_node), set0, at_start);
+            std::array<int, kPrefix> seq;
+            seq.fill(kWild);
+            W.dfs(0, set0, seq);
+            if (!W.overflow && !W.out.empty()) {
+                Seqs A, B1, B2;
+                for (auto& t : W.out) {
+                    A.push_back({t[1], t[2], t[3], t[4]});
+                    B1.push_back({t[2], t[3], t[4], kWild});
+                    B2.push_back({t[0], t[1], t[2], t[3]});
+                }
+                uniq(A);
+                uniq(B1);
+                uniq(B2);
+                const size_t na = total(A), nb1 = total(B1), nb2 = total(B2);
+                if (na + std::min(nb1, nb2) < best) {
+                    best = na + std::min(nb1, nb2);
+                    best_a = A;
+                    best_b = nb2 <= nb1 ? B2 : B1;
+                }
+            }
+        }
+    }
+    if (best > cap) return false;
+    for (auto& s : best_a) expand(s, out);
+    for (auto& s : best_b) expand(s, out);
+    return true;
+}
+
+void gate_build_tables(std::vector<uint32_t> grams, GateTables* out) {
+    std::sort(grams.begin(), grams.end());
+    grams.erase(std::unique(grams.begin(), grams.end()), grams.end());
+    GateTables& T = *out;
+    T = GateTables();
+    T.present = true;
+    T.n_grams = (uint32_t)grams.size();
+    // first bitmap: at most ~1.5 % of windows pass by collision; second (independent hash) the same again
+    uint32_t k = 12;
+    while (k < kGateMaxLog2 - 1 && ((size_t)1 << k) < grams.size() * 64) ++k;
+    T.k1 = T.k2 = k;
+    T.b1.assign(((size_t)1 << T.k1) / 32, 0u);
+    T.b2.assign(((size_t)1 << T.k2) / 32, 0u);
+    for (uint32_t g : grams) {
+        const uint32_t h1 = (g * kGateHash1) >> (32 - T.k1), h2 = (g * kGateHash2) >> (32 - T.k2);
+        T.b1[h1 >> 5] |= 1u << (h1 & 31);
+        T.b2[h2 >> 5] |= 1u << (h2 & 31);
+    }
+}
+
+}  // namespace pgw

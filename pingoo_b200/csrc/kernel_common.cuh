@@ -2,6 +2,8 @@
 // not linked across files).  Helpers shared by every kernel path: shared-window accessors, mbarrier / TMA bulk copy, event lists,
 // rule bytecode, longest-prefix lookup and the per-request epilogue.
 
+__host__ __device__ inline uint32_t r16(uint32_t x) { return (x + 15u) & ~15u; }
+
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -44,30 +46,11 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint8_t* p) {
     return r;
 }
 
-// Apply the events of CSR row `row` (sorted FIRE, TEST, CLEAR, SET) to the lane's bitmap and latch register.
-// Returns true if every event was a plain FIRE (idempotent: the caller may skip an immediate repeat).
-__device__ __noinline__ bool run_events(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ events, uint32_t row,
-                                        uint32_t* bits, uint32_t stride, uint32_t* latch) {
-    uint32_t a = __ldg(idx + row), b = __ldg(idx + row + 1);
-    bool pure = true;
-    uint32_t l = *latch;
-    for (uint32_t i = a; i < b; ++i) {
-        const uint32_t e = __ldg(events + i);
-        const uint32_t kind = e >> kEvKindShift, lb = 1u << ((e >> kEvLatchShift) & 31u), at = e & kEvAtomMask;
-        if (kind == 0u || (kind == 1u && (l & lb))) bits[(at >> 5) * stride] |= 1u << (at & 31);
-        else if (kind == 2u) l &= ~lb;
-        else if (kind == 3u) l |= lb;
-        pure &= kind == 0u;
-    }
-    *latch = l;
-    return pure;
-}
-
-__device__ __forceinline__ bool eval_rule(const uint16_t* __restrict__ code, uint32_t a, uint32_t b, const uint32_t* row, uint32_t stride) {
+__device__ __forceinline__ bool eval_rule(const uint16_t* __restrict__ code, uint32_t a, uint32_t b, const uint32_t* row) {
     uint32_t st = 0;
     for (uint32_t i = a; i < b; ++i) {
         uint32_t op = __ldg(code + i);
-        if (op < 0x4000u) st = (st << 1) | ((row[(op >> 5) * stride] >> (op & 31)) & 1u);
+        if (op < 0x4000u) st = (st << 1) | ((row[op >> 5] >> (op & 31)) & 1u);
         else if (op == OP_NOT) st ^= 1u;
         else if (op == OP_AND) st = ((st >> 1) & ~1u) | (st & (st >> 1) & 1u);
         else if (op == OP_OR) st = ((st >> 1) & ~1u) | ((st | (st >> 1)) & 1u);
@@ -101,13 +84,13 @@ __device__ __forceinline__ uint32_t lpm_lookup(const KParams& p, const uint8_t* 
 }
 
 // Per-request predicates outside the byte scan + the verdict (http_listener.rs:196-264).
-// `row[w * stride]` is the request's atom bitmap (scan atoms already set).
-// WARP: called by all 32 lanes of a converged warp (`valid` false for lanes past the end of the batch, which shadow the
-// last request without storing anything): requests of the warp that deviate from the expected atom vector in the same
-// way are evaluated once -- verdict and service are functions of the deviation and of `captcha_verified` alone -- and
-// the result is shared by shuffle.
-template <bool WARP>
-__device__ __forceinline__ void request_epilogue_t(const KParams& p, uint32_t r, uint32_t* row, uint32_t stride, bool valid) {
+// `row` is the request's atom bitmap in global memory (scan atoms already set; all zero unless `row_dirty`).
+// Called by all 32 lanes of a converged warp (`valid` false for lanes past the end of the batch, which shadow the last
+// request without storing anything).  A request whose bitmap stays all zero takes the precomputed verdict `vclean`
+// without reading the row; for the others, requests of the warp that deviate from the expected atom vector in the same
+// way are evaluated once -- verdict and service are functions of the deviation and of `captcha_verified` alone -- and the
+// result is shared by shuffle.  Rows that were touched are written back to zero (the scratch invariant).
+__device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, uint32_t* row, bool valid, bool row_dirty) {
     const uint32_t Aw = p.atom_words;
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t flags = p.flags ? p.flags[r] : 0u;
@@ -119,7 +102,7 @@ __device__ __forceinline__ void request_epilogue_t(const KParams& p, uint32_t r,
         const bool v6 = p.is_v6[r] != 0;
         const LpmLeaf lf = p.leaves[lpm_lookup(p, ip16, v6)];
         set_mask = lf.set_mask;
-        if (p.geo_loaded && p.asn == nullptr) {
+        if (p.geo_loaded) {
             // geoip.rs:74-76: loopback / multicast are never looked up
             bool skip;
             if (!v6) skip = ip16[0] == 127 || (ip16[0] >> 4) == 0xE;
@@ -127,6 +110,7 @@ __device__ __forceinline__ void request_epilogue_t(const KParams& p, uint32_t r,
                 const uint32_t* w = reinterpret_cast<const uint32_t*>(ip16);
                 skip = ip16[0] == 0xFF || (w[0] == 0 && w[1] == 0 && w[2] == 0 && w[3] == 0x01000000u);
             }
+            // each column the caller did not supply comes from the database
             if (!skip) { asn = lf.asn; country = lf.country; }
         }
     }
@@ -172,7 +156,10 @@ __device__ __forceinline__ void request_epilogue_t(const KParams& p, uint32_t r,
                 v = (__ldg(p.cset + a.set_id * kCountryWords + (bit >> 5)) >> (bit & 31)) & 1u;
             }
         }
-        if (v && valid) row[(a.atom >> 5) * stride] |= 1u << (a.atom & 31);
+        if (v && valid) {
+            row[a.atom >> 5] |= 1u << (a.atom & 31);
+            row_dirty = true;
+        }
     }
 
     const uint32_t cv = flags & RF_CAPTCHA_VERIFIED;
@@ -187,92 +174,92 @@ __device__ __forceinline__ void request_epilogue_t(const KParams& p, uint32_t r,
     }
     if (!decided) {
         bool bypass = flags & RF_BYPASS;
-        if (p.eval_gates && p.gate_atom >= 0) bypass |= (row[(p.gate_atom >> 5) * stride] >> (p.gate_atom & 31)) & 1u;
+        if (p.eval_gates && p.gate_atom >= 0 && row_dirty) bypass |= (row[p.gate_atom >> 5] >> (p.gate_atom & 31)) & 1u;
         if (bypass) { verdict = V_BYPASS | (kNoRule << 2); decided = true; }
     }
     if (!decided && (flags & RF_PRE_CAPTCHA)) { verdict = V_CAPTCHA | (kNoRule << 2); decided = true; }
 
+    const bool routes = p.service != nullptr && p.n_rules > p.n_waf_rules;
+    uint32_t svc = kNoService;
+    // no atom of this request is true: constants
+    if (!decided && !row_dirty) { verdict = p.vclean[cv]; svc = p.sclean; decided = true; }
+
     // deviations from the expected atom vector: none -> v0 / s0, exactly one -> v1[atom] / s1[atom], otherwise the
     // candidate rules (those that mention a deviating atom, plus the ones true by default) are evaluated
-    const bool routes = p.service != nullptr && p.n_rules > p.n_waf_rules;
-    uint32_t ndev = 0, dev_atom = 0, sig = cv;
-    for (uint32_t w = 0; w < Aw; ++w) {
-        const uint32_t x = (row[w * stride] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
-        if (x) dev_atom = w * 32u + (uint32_t)__ffs(x) - 1u;
-        ndev += (uint32_t)__popc(x);
-        sig = sig * 0x9E3779B1u + x;
-    }
-    uint32_t svc = kNoService;
-    if (!decided) {
-        if (ndev == 0u) { verdict = p.v0[cv]; svc = p.s0; }
-        else if (ndev == 1u) { verdict = __ldg(p.v1 + cv * p.n_atoms + dev_atom); svc = routes ? (uint32_t)__ldg(p.s1 + dev_atom) : kNoService; }
-    }
-    const bool need_eval = !decided && ndev >= 2u;
-    if (WARP ? __any_sync(FULL, need_eval) : need_eval) {
-        bool do_eval = need_eval, same = false;
-        uint32_t leader = 0;
-        if (WARP) {
+    const bool look = row_dirty && !decided;
+    if (__any_sync(FULL, look)) {
+        uint32_t ndev = 0, dev_atom = 0, sig = cv;
+        if (look)
+            for (uint32_t w = 0; w < Aw; ++w) {
+                const uint32_t x = (row[w] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
+                if (x) dev_atom = w * 32u + (uint32_t)__ffs(x) - 1u;
+                ndev += (uint32_t)__popc(x);
+                sig = sig * 0x9E3779B1u + x;
+            }
+        if (look) {
+            if (ndev == 0u) { verdict = p.v0[cv]; svc = p.s0; }
+            else if (ndev == 1u) { verdict = __ldg(p.v1 + cv * p.n_atoms + dev_atom); svc = routes ? (uint32_t)__ldg(p.s1 + dev_atom) : kNoService; }
+        }
+        const bool need_eval = look && ndev >= 2u;
+        if (__any_sync(FULL, need_eval)) {
             const uint32_t lane = threadIdx.x & 31u;
             const uint32_t peers = __match_any_sync(FULL, need_eval ? (sig & 0x7FFFFFFFu) : (0x80000000u | lane));
-            leader = (uint32_t)__ffs(peers) - 1u;
-            same = true;  // equal signature: confirm that the deviation really is the leader's
+            const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+            bool same = true;  // equal signature: confirm that the deviation really is the leader's
             for (uint32_t w = 0; w < Aw; ++w) {
-                const uint32_t x = (row[w * stride] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
+                const uint32_t x = need_eval ? (row[w] ^ __ldg(p.expect + w)) & __ldg(p.care + w) : 0u;
                 same &= __shfl_sync(FULL, x, leader) == x;
             }
             same &= __shfl_sync(FULL, cv, leader) == cv;
-            do_eval = need_eval && (leader == lane || !same);
-        }
-        if (do_eval) {
-            const uint32_t tshift = 2 * cv;
-            uint32_t best = kNoRule, best_svc = kNoRule;
-            for (uint32_t w = 0; w < Aw; ++w) {
-                uint32_t x = (row[w * stride] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
-                while (x) {
-                    uint32_t b = __ffs(x) - 1;
-                    x &= x - 1;
-                    uint32_t atom = w * 32 + b;
-                    uint32_t i0 = __ldg(p.ar_idx + atom), i1 = __ldg(p.ar_idx + atom + 1);
-                    for (uint32_t i = i0; i < i1; ++i) {
-                        uint32_t rule = __ldg(p.ar_rules + i);  // ascending; WAF rules first, then service routes
-                        if (rule < p.n_waf_rules) {
-                            if (rule >= best || ((__ldg(p.term + rule) >> tshift) & 3u) == 0) continue;
-                            if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row, stride)) best = rule;
-                        } else {
-                            if (!routes || rule >= best_svc) break;
-                            if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row, stride)) best_svc = rule;
+            const bool do_eval = need_eval && (leader == lane || !same);
+            if (do_eval) {
+                const uint32_t tshift = 2 * cv;
+                uint32_t best = kNoRule, best_svc = kNoRule;
+                for (uint32_t w = 0; w < Aw; ++w) {
+                    uint32_t x = (row[w] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
+                    while (x) {
+                        uint32_t b = __ffs(x) - 1;
+                        x &= x - 1;
+                        uint32_t atom = w * 32 + b;
+                        uint32_t i0 = __ldg(p.ar_idx + atom), i1 = __ldg(p.ar_idx + atom + 1);
+                        for (uint32_t i = i0; i < i1; ++i) {
+                            uint32_t rule = __ldg(p.ar_rules + i);  // ascending; WAF rules first, then service routes
+                            if (rule < p.n_waf_rules) {
+                                if (rule >= best || ((__ldg(p.term + rule) >> tshift) & 3u) == 0) continue;
+                                if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row)) best = rule;
+                            } else {
+                                if (!routes || rule >= best_svc) break;
+                                if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row)) best_svc = rule;
+                            }
                         }
                     }
                 }
-            }
-            for (uint32_t i = 0; i < p.n_dflt[cv]; ++i) {
-                uint32_t rule = __ldg(p.dflt[cv] + i);
-                if (rule >= best) break;
-                if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row, stride)) best = rule;
-            }
-            if (routes)
-                for (uint32_t i = 0; i < p.n_dflt_services; ++i) {
-                    uint32_t rule = __ldg(p.dflt_services + i);
-                    if (rule >= best_svc) break;
-                    if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row, stride)) best_svc = rule;
+                for (uint32_t i = 0; i < p.n_dflt[cv]; ++i) {
+                    uint32_t rule = __ldg(p.dflt[cv] + i);
+                    if (rule >= best) break;
+                    if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row)) best = rule;
                 }
-            verdict = best == kNoRule ? (V_ALLOW | (kNoRule << 2)) : (((__ldg(p.term + best) >> tshift) & 3u) | (best << 2));
-            svc = best_svc == kNoRule ? kNoService : best_svc - p.n_waf_rules;
-        }
-        if (WARP) {
+                if (routes)
+                    for (uint32_t i = 0; i < p.n_dflt_services; ++i) {
+                        uint32_t rule = __ldg(p.dflt_services + i);
+                        if (rule >= best_svc) break;
+                        if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row)) best_svc = rule;
+                    }
+                verdict = best == kNoRule ? (V_ALLOW | (kNoRule << 2)) : (((__ldg(p.term + best) >> tshift) & 3u) | (best << 2));
+                svc = best_svc == kNoRule ? kNoService : best_svc - p.n_waf_rules;
+            }
             const uint32_t lv = __shfl_sync(FULL, verdict, leader), ls = __shfl_sync(FULL, svc, leader);
             if (need_eval && same) { verdict = lv; svc = ls; }
         }
     }
+    __syncwarp();  // every lane is done reading rows (the shadow lanes of the last warp read the last request's)
     if (!valid) return;
+    if (row_dirty)
+        for (uint32_t w = 0; w < Aw; ++w) row[w] = 0u;  // scratch goes back all-zero
     p.verdict[r] = verdict;
     // http_listener.rs:266-272: only a request the rules let through reaches the services; the first service whose
     // route is absent or true takes it, none => 404 (kNoService)
     if (p.service) p.service[r] = (uint16_t)(((verdict & 3u) == V_ALLOW && routes) ? svc : kNoService);
-}
-
-__device__ __noinline__ void request_epilogue(const KParams& p, uint32_t r, uint32_t* row, uint32_t stride) {
-    request_epilogue_t<false>(p, r, row, stride, true);
 }
 
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {

@@ -1,13 +1,16 @@
 // Part of kernels.cu (included inside namespace pgw { namespace { ... } }, one translation unit: device functions are
-// not linked across files).  The default "field" path and the epilogue kernel shared with the stream path.
+// not linked across files).  The DFA scan and the epilogue kernel.
 
 // =====================================================================================================================
-// Field scan (kernel path "field"): unit-major, lane-owned strings.  A warp works on ONE scan unit at a time, so all the
-// per-unit parameters are warp-uniform; each lane owns one request's field of that unit and walks it 16 bytes per
-// iteration exactly like the lane path (speculative 4-byte word walk on the shared-memory rows).  A lane that finishes
-// takes the next request of the unit from a warp pool of 32 claimed requests whose field offsets were fetched coalesced
-// one pool ahead, so the per-request setup is a shuffle.  Atom bits go to bitmaps in global memory (red.or, rare) and
-// waf_epilogue_kernel turns them into verdicts.  Warps move to the next unit on their own when a unit runs dry.
+// Field scan: unit-major, lane-owned strings.  All warps of a CTA work on ONE scan unit at a time: its shared-memory
+// image (class map, hot rows, event tables -- up to the whole shared-memory budget) is staged by TMA bulk copies at the
+// start of the unit, so every per-unit parameter is warp-uniform.  Each lane owns one request's field of that unit and
+// walks it 16 bytes per iteration (speculative 4-byte word walk on the shared-memory rows).  A unit walks either every
+// request (UM_ALL) or the candidates the gate kernel listed for its field (UM_CANDIDATES).  A lane that finishes --
+// end of the field, or an absorbing DFA state (UnitDesc::abs0/abs1: nothing can change any more) -- takes the next
+// request from a warp pool of 32 claimed entries whose (start, end, request) triples were fetched one pool ahead.
+// Atom bits go to bitmaps in global memory (red.or, rare) together with the request's dirty bit;
+// waf_epilogue_kernel turns them into verdicts.
 // =====================================================================================================================
 #ifndef PGW_FS_THREADS
 #define PGW_FS_THREADS 1024
@@ -17,8 +20,10 @@ constexpr uint32_t kFsSlotStride = kFsThreads * 4u;  // per-lane slots: request 
 #ifndef PGW_FS_TICKET
 #define PGW_FS_TICKET 64
 #endif
-constexpr uint32_t kFsTicket = PGW_FS_TICKET;  // requests per atomic claim (two 32-request pools: 128 and 256 measured worse, tail imbalance)
-constexpr uint32_t kFsPoolBytes = 144;  // 33 offsets of a claimed pool (+pad), two buffers per warp
+constexpr uint32_t kFsTicket = PGW_FS_TICKET;  // entries per atomic claim (two 32-entry pools: 128 and 256 measured worse, tail imbalance)
+constexpr uint32_t kFsPoolBytes = 384;  // a claimed pool: 32 field starts, 32 field ends, 32 request indices; two buffers per warp
+// front of the shared window (mbarrier, claim pools, per-lane slots), rounded so that the unit image behind it starts on a 256-byte boundary
+constexpr uint32_t kFsFront = (64u + (kFsThreads / 32) * 2u * kFsPoolBytes + 4u * kFsSlotStride + 255u) & ~255u;
 
 __device__ __forceinline__ void red_or(uint32_t* addr, uint32_t v) { asm volatile("red.global.or.b32 [%0], %1;" ::"l"(addr), "r"(v) : "memory"); }
 
@@ -40,9 +45,8 @@ __device__ __forceinline__ bool fs_fire_list(const uint32_t* idx, const uint32_t
 }
 
 // accept events of four hot states of one word (at least one accepting); returns the new `last`
-__device__ __noinline__ uint32_t fs_events_word(const KParams& p, const UnitDesc* ud, uint32_t acc1addr, uint32_t s01, uint32_t s23, uint32_t m4,
-                                                uint32_t last, uint32_t* latch, uint32_t* row) {
-    const uint32_t acclo = ud->acc_lo;
+__device__ __noinline__ uint32_t fs_events_word(const KParams& p, uint32_t acclo, uint32_t acc_base, uint32_t acc1addr, uint32_t s01, uint32_t s23,
+                                                uint32_t m4, uint32_t last, uint32_t* latch, uint32_t* row) {
     // positions whose state is accepting
     uint32_t am = m4;
     if ((s01 & 0xFFFFu) < acclo) am &= ~1u;
@@ -60,76 +64,81 @@ __device__ __noinline__ uint32_t fs_events_word(const KParams& p, const UnitDesc
             red_or(row + (a1 >> 5), 1u << (a1 & 31));
             last = st;
         } else {
-            last = fs_fire_list(p.acc_idx, p.acc_events, ud->acc_base + st - acclo, row, latch) ? st : 0xFFFFFFFFu;
+            last = fs_fire_list(p.acc_idx, p.acc_events, acc_base + st - acclo, row, latch) ? st : 0xFFFFFFFFu;
         }
     }
     return last;
 }
 
 // one word walked on the full table in global memory (a cold state is involved)
-__device__ __noinline__ void fs_slow_word(const KParams& p, const UnitDesc* ud, uint32_t clsaddr, uint32_t w, uint32_t m4, uint32_t* state,
-                                          uint32_t* last, uint32_t* latch, uint32_t* row) {
-    const uint16_t* tbl = reinterpret_cast<const uint16_t*>(p.arena + ud->tbl_off);
-    const uint32_t C = ud->n_classes, acclo = ud->acc_lo;
+__device__ __noinline__ void fs_slow_word(const KParams& p, uint32_t tbl_off, uint32_t C, uint32_t acclo, uint32_t acc_base, uint32_t clsaddr,
+                                          uint32_t w, uint32_t m4, uint32_t* state, uint32_t* last, uint32_t* latch, uint32_t* row) {
+    const uint16_t* tbl = reinterpret_cast<const uint16_t*>(p.arena + tbl_off);
     uint32_t st = *state, la = *last;
 #pragma unroll 1
     for (int bi = 0; bi < 4; ++bi) {
         if (!((m4 >> bi) & 1u)) continue;
         const uint32_t byte = (w >> (8 * bi)) & 0xFFu;
         st = __ldg(tbl + st * C + lds_u8(clsaddr + byte));
-        if (st >= acclo && st != la) la = fs_fire_list(p.acc_idx, p.acc_events, ud->acc_base + st - acclo, row, latch) ? st : 0xFFFFFFFFu;
+        if (st >= acclo && st != la) la = fs_fire_list(p.acc_idx, p.acc_events, acc_base + st - acclo, row, latch) ? st : 0xFFFFFFFFu;
     }
     *state = st;
     *last = la;
 }
 
-__global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __grid_constant__ KParams p, uint32_t* __restrict__ rows,
-                                                                       uint32_t* __restrict__ counters) {
+__global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t img_bytes = r16(p.image_bytes);
-    uint8_t* s_img = smem + ((0u - smem_u32(smem)) & 255u);  // class maps (image offsets u * 256) on 256-byte boundaries
-    UnitDesc* s_units = reinterpret_cast<UnitDesc*>(s_img + img_bytes);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_img + img_bytes + r16(p.n_units * (uint32_t)sizeof(UnitDesc)));
-
+    uint8_t* s_img = smem + ((0u - smem_u32(smem)) & 255u);  // the class map (image offset 0) sits on a 256-byte boundary
     const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t Aw = p.atom_words;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t* const rows = p.rows;
+    uint32_t* const dirty = p.dirty;
+
+    // fixed part of the shared window sits in FRONT of the image: mbarrier, pools, slots
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_img);
+    const uint32_t a_pool = smem_u32(s_img) + 64u + (tid >> 5) * 2u * kFsPoolBytes;
+    const uint32_t a_slot = smem_u32(s_img) + 64u + (kFsThreads / 32) * 2u * kFsPoolBytes + tid * 4u;  // word k at a_slot + k * kFsSlotStride
+    uint8_t* const s_image = s_img + kFsFront;
+    const uint32_t a_img = smem_u32(s_image);
+
     if (tid == 0) {
         mbar_init(s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
-    if (tid == 0 && img_bytes) {
-        mbar_expect_tx(s_bar, img_bytes);
-        for (uint32_t o = 0; o < img_bytes; o += 32768u) {
-            uint32_t n = img_bytes - o < 32768u ? img_bytes - o : 32768u;
-            bulk_g2s(s_img + o, p.image + o, n, s_bar);
-        }
-    }
-    for (uint32_t i = tid; i < p.n_units * (sizeof(UnitDesc) / 4); i += kFsThreads)
-        reinterpret_cast<uint32_t*>(s_units)[i] = __ldg(reinterpret_cast<const uint32_t*>(p.units) + i);
-    if (img_bytes) mbar_wait(s_bar, 0);
-    __syncthreads();
-
-    const uint32_t a_img = smem_u32(s_img);
-    const uint32_t a_pool = smem_u32(s_bar) + 64u + (tid >> 5) * 2u * kFsPoolBytes;
-    const uint32_t a_slot = smem_u32(s_bar) + 64u + (kFsThreads / 32) * 2u * kFsPoolBytes + tid * 4u;  // word k at a_slot + k * kFsSlotStride
-    const uint32_t FULL = 0xFFFFFFFFu;
-    const uint32_t Aw = p.atom_words, N = p.n;
-    const uint32_t lt_mask = (1u << lane) - 1u;
 
     for (uint32_t u = 0; u < p.n_units; ++u) {
-        const UnitDesc* ud = &s_units[u];  // for the out-of-line event paths
         const UnitDesc& cu = p.udesc[u];   // constant bank, uniform index
+        // ---- stage this unit's image: everybody has left the previous unit's tables ----
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bytes = cu.img_bytes;
+            mbar_expect_tx(s_bar, bytes);
+            for (uint32_t o = 0; o < bytes; o += 32768u) {
+                const uint32_t nb = bytes - o < 32768u ? bytes - o : 32768u;
+                bulk_g2s(s_image + o, p.images + cu.img_off + o, nb, s_bar);
+            }
+        }
+        mbar_wait(s_bar, u & 1u);
+
         const uint32_t C2 = 2u * cu.n_classes, D0 = cu.start_state, trap = cu.hot_states, lim = cu.lim, acclo = cu.acc_lo;
-        const uint32_t clsaddr = a_img + cu.cls_off, hotaddr = a_img + cu.hot_off, acc1addr = a_img + cu.acc1_off, end1addr = a_img + cu.end1_off;
+        const uint32_t abs0 = cu.abs0, abs1 = cu.abs1;
+        const uint32_t clsaddr = a_img, hotaddr = a_img + cu.hot_off, acc1addr = a_img + cu.acc1_off, end1addr = a_img + cu.end1_off;
         const uint8_t* col = p.col[cu.field];
         const uint32_t* off = p.off[cu.field];
-        uint32_t* ctr = counters + u;
+        const bool cand = cu.mode == UM_CANDIDATES;
+        const uint32_t* c_idx = p.cand_idx[cu.field];
+        const uint32_t* c_start = p.cand_start[cu.field];
+        const uint32_t* c_end = p.cand_end[cu.field];
+        const uint32_t N = cand ? __ldg(p.cand_count[cu.field]) : p.n;
+        uint32_t* ctr = p.counters + p.unit_base + u;
 
-        // warp pools of 32 claimed requests, double buffered in shared memory: buffer `pb` is being handed out, the other
-        // one holds the next claim whose 33 field offsets are landing through cp.async (no registers, no stall)
+        // warp pools of 32 claimed entries, double buffered in shared memory: buffer `pb` is being handed out, the other
+        // one holds the next claim whose triples are landing through cp.async (no registers, no stall)
         uint32_t pool_next = 0, pool_end = 0, pb = 0, ah_base = 0;
         // claims are pipelined three deep so that no global latency is ever waited for: `ticket` (atomicAdd issued, result
-        // not looked at yet) -> `ahead` (offsets landing in the spare buffer) -> the pool being handed out
+        // not looked at yet) -> `ahead` (triples landing in the spare buffer) -> the pool being handed out
         uint32_t ticket = 0;
         bool tk_valid = false, ah_valid = false;
         auto issue_ticket = [&]() {
@@ -148,9 +157,17 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                 issue_ticket();
             }
             ah_base = b;
-            const uint32_t dst = a_pool + (pb ^ 1u) * kFsPoolBytes;
-            cp_async4(dst + lane * 4u, off + min(b + lane, N));
-            if (lane == 0) cp_async4(dst + 128u, off + min(b + 32u, N));
+            const uint32_t dst = a_pool + (pb ^ 1u) * kFsPoolBytes + lane * 4u;
+            const uint32_t e = min(b + lane, N - 1u);  // entries past N are never handed out
+            if (cand) {
+                cp_async4(dst, c_start + e);
+                cp_async4(dst + 128u, c_end + e);
+                cp_async4(dst + 256u, c_idx + e);
+            } else {
+                cp_async4(dst, off + e);
+                cp_async4(dst + 128u, off + e + 1u);
+                sts_u32(dst + 256u, e);
+            }
             asm volatile("cp.async.commit_group;" ::: "memory");
             ah_valid = true;
         };
@@ -192,7 +209,7 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                 const uint32_t hi = min(end - base, 16u);
                 mk = ((1u << hi) - 1u) & ~((1u << skip) - 1u);
             }
-            // ---- lanes that run out of bytes in this iteration (or are idle) take the next request of the pool ----
+            // ---- lanes that run out of bytes in this iteration (or are idle) take the next entry of the pool ----
             const bool want = !have || finishing;
             bool do_ld = have && !finishing;
             uint32_t ld_off = base + 16u;
@@ -209,9 +226,9 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                 const uint32_t idx = pool_next + __popc(need & lt_mask);
                 if (want && idx < pool_end) {
                     const uint32_t sa = a_pool + pb * kFsPoolBytes + (idx & 31u) * 4u;
-                    const uint32_t s0 = lds_u32_v(sa), e0 = lds_u32_v(sa + 4u);
+                    const uint32_t s0 = lds_u32_v(sa), e0 = lds_u32_v(sa + 128u);
                     if (e0 > s0) {  // empty fields are left to the epilogue kernel
-                        sts_u32(a_slot + 3u * kFsSlotStride, idx);
+                        sts_u32(a_slot + 3u * kFsSlotStride, lds_u32_v(sa + 256u));
                         pend = true;
                         end = e0;
                         ld_off = s0 & ~15u;
@@ -239,7 +256,7 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                 uint32_t sv[4];
 #pragma unroll
                 for (int bi = 0; bi < 4; ++bi) {
-                    // class maps sit on 256-byte boundaries of the shared window: one PRMT extracts the byte AND adds the base
+                    // the class map sits on a 256-byte boundary of the shared window: one PRMT extracts the byte AND adds the base
                     const uint32_t cls = lds_u8(__byte_perm(w, clsaddr, 0x7650 + bi));
                     // column address first (independent of the state): the state chain is IMAD -> LDS -> SEL only
                     uint32_t colad = hotaddr + 2u * cls, ad;
@@ -252,11 +269,13 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                 const uint32_t mx4 = max(max(sv[0], sv[1]), max(sv[2], sv[3]));
                 if (mx4 >= lim) {
                     if (mx4 >= trap || mx4 >= acclo) {
-                        uint32_t* row = rows + (size_t)lds_u32_v(a_slot) * Aw;
+                        const uint32_t ridx = lds_u32_v(a_slot);
+                        uint32_t* row = rows + (size_t)ridx * Aw;
+                        red_or(dirty + (ridx >> 5), 1u << (ridx & 31u));  // the epilogue must look at (and re-zero) this row
                         uint32_t t_latch = lds_u32_v(a_slot + kFsSlotStride), t_last = lds_u32_v(a_slot + 2u * kFsSlotStride);
                         if (mx4 >= trap) {
                             uint32_t t_state = state;
-                            fs_slow_word(p, ud, clsaddr, w, m4, &t_state, &t_last, &t_latch, row);
+                            fs_slow_word(p, cu.tbl_off, cu.n_classes, acclo, cu.acc_base, clsaddr, w, m4, &t_state, &t_last, &t_latch, row);
                             spec = t_state;
                         } else {
                             // a string sitting in a sticky accepting state whose events were already applied: nothing to do
@@ -276,7 +295,7 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                                     if (st1 != t_last) red_or(row + (a1 >> 5), 1u << (a1 & 31));
                                     t_last = st1;
                                 } else {
-                                    t_last = fs_events_word(p, ud, acc1addr, s01, s23, m4, t_last, &t_latch, row);
+                                    t_last = fs_events_word(p, acclo, cu.acc_base, acc1addr, s01, s23, m4, t_last, &t_latch, row);
                                 }
                             }
                         }
@@ -286,15 +305,20 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                 }
                 state = spec;
             }
-            if (finishing) {
+            // the field ends in this chunk, or the DFA reached an absorbing state: finish as at the end of the field
+            if (finishing || (have && (state == abs0 || state == abs1))) {
                 uint32_t e1 = 0xFFFFu;
                 if (state < trap) e1 = lds_u16(end1addr + 2u * state);
                 if (e1 != 0xFFFEu) {
-                    uint32_t* row = rows + (size_t)lds_u32_v(a_slot) * Aw;
-                    if (e1 != 0xFFFFu) red_or(row + (e1 >> 5), 1u << (e1 & 31));
-                    else if (cu.end_any) {
+                    const uint32_t ridx = lds_u32_v(a_slot);
+                    uint32_t* row = rows + (size_t)ridx * Aw;
+                    if (e1 != 0xFFFFu) {
+                        red_or(row + (e1 >> 5), 1u << (e1 & 31));
+                        red_or(dirty + (ridx >> 5), 1u << (ridx & 31u));
+                    } else if (cu.end_any) {
                         uint32_t t_latch = lds_u32_v(a_slot + kFsSlotStride);
                         fs_fire_list(p.end_idx, p.end_events, cu.end_base + state, row, &t_latch);
+                        red_or(dirty + (ridx >> 5), 1u << (ridx & 31u));
                     }
                 }
                 have = false;
@@ -304,29 +328,35 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
     }
 }
 
-// Verdicts once every unit has been scanned: one thread per request.  Empty fields never reach the stream scan;
-// their end-of-field events (the DFA's start state at end of input) are applied here.
-__global__ void __launch_bounds__(256) waf_epilogue_kernel(const __grid_constant__ KParams p, uint32_t* __restrict__ rows) {
-    // warp-uniform trip count: every lane of a warp goes through request_epilogue_t<true> together
+// Verdicts once every unit has been scanned: one thread per request, one warp per word of the dirty bitmap.
+// Empty fields never reach the scan; their end-of-field events (the DFA's start state at end of input) are applied here.
+__global__ void __launch_bounds__(256) waf_epilogue_kernel(const __grid_constant__ KParams p) {
+    // warp-uniform trip count: every lane of a warp goes through request_epilogue together
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < p.n; base += gridDim.x * blockDim.x) {
-        const uint32_t rr = base + (threadIdx.x & 31u);
+        const uint32_t lane = threadIdx.x & 31u;
+        const uint32_t rr = base + lane;
         const bool valid = rr < p.n;
         const uint32_t r = valid ? rr : p.n - 1u;
-        uint32_t* row = rows + (size_t)r * p.atom_words;
+        const uint32_t dword = p.dirty[base >> 5];
+        __syncwarp();
+        if (lane == 0 && dword) p.dirty[base >> 5] = 0u;  // scratch goes back all-zero
+        bool row_dirty = valid && ((dword >> lane) & 1u);
+        uint32_t* row = p.rows + (size_t)r * p.atom_words;
         if (valid)
-            for (uint32_t u = 0; u < p.n_units; ++u) {
-                const UnitDesc& ud = p.udesc[u];  // parameter bank (both callers keep n_units <= kMaxConstUnits)
-                if (!ud.end_any) continue;
+            for (uint32_t k = 0; k < p.n_start_end; ++k) {
+                const UnitDesc& ud = p.units[p.start_end_unit[k]];
                 const uint32_t* o = p.off[ud.field] + r;
                 if (o[0] != o[1]) continue;
                 uint32_t a = __ldg(p.end_idx + ud.end_base + ud.start_state), b = __ldg(p.end_idx + ud.end_base + ud.start_state + 1);
                 for (uint32_t i = a; i < b; ++i) {
                     const uint32_t e = __ldg(p.end_events + i);
-                    if ((e >> kEvKindShift) == 0u) row[(e & kEvAtomMask) >> 5] |= 1u << (e & 31);  // latch kinds cannot fire on an empty field
+                    if ((e >> kEvKindShift) == 0u) {  // latch kinds cannot fire on an empty field
+                        row[(e & kEvAtomMask) >> 5] |= 1u << (e & 31);
+                        row_dirty = true;
+                    }
                 }
             }
         __syncwarp();
-        request_epilogue_t<true>(p, r, row, 1, valid);
+        request_epilogue(p, r, row, valid, row_dirty);
     }
 }
-

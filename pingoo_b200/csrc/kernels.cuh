@@ -7,23 +7,14 @@
 
 namespace pgw {
 
-#ifndef PGW_THREADS
-#define PGW_THREADS 640
-#endif
-constexpr int kThreads = PGW_THREADS;  // one persistent CTA per SM
-#ifndef PGW_CHUNK
-#define PGW_CHUNK 16
-#endif
-constexpr int kChunk = PGW_CHUNK;   // bytes per lane per scan iteration (PGW_CHUNK/16 128-bit loads)
-constexpr int kRowsPerLane = 2;     // atom bitmaps per lane: the request being scanned + one awaiting its epilogue
-constexpr uint32_t kClaim = 32;     // requests a warp claims from the global counter at a time
-
 constexpr uint32_t kMaxConstNs = 16;
-constexpr uint32_t kMaxConstUnits = 64;  // rule sets with more scan units run on the lane path (parameter block stays under 8 KB)
+constexpr uint32_t kMaxConstUnits = 64;  // scan units per scan-kernel launch (their descriptors ride in the parameter bank);
+                                         // rule sets with more units are scanned by several launches
+constexpr uint32_t kMaxGateFields = 3;   // url, user_agent, path
 
 struct KParams {
     // ---- batch (device pointers, SoA) ----
-    const uint8_t* col[5];      // field bytes, Field order; 16-byte aligned, readable to round_up(len,16)
+    const uint8_t* col[5];      // field bytes, Field order; 32-byte aligned, readable to round_up(len, 32)
     const uint32_t* off[5];     // n+1 offsets per field
     const uint8_t* ip;          // n x 16, network order; IPv4 in bytes [0,4)
     const uint8_t* is_v6;       // n
@@ -33,13 +24,21 @@ struct KParams {
     const uint8_t* flags;       // n or null
     uint32_t* verdict;          // n
     uint32_t n;
-    uint32_t* work_counter;     // zeroed before each launch: next unclaimed request index
+    // ---- per-launch scratch ----
+    uint32_t* rows;             // n x atom_words atom bitmaps; all zero between batches (the epilogue re-zeroes what was touched)
+    uint32_t* dirty;            // ceil(n / 32) words: bit r set <=> row r may be non-zero; all zero between batches
+    uint32_t* counters;         // per scan unit: next unclaimed request / candidate (zeroed before each batch)
+    const uint32_t* cand_count[5];  // gate candidates of a field (null: the field has no gate)
+    const uint32_t* cand_idx[5];
+    const uint32_t* cand_start[5];
+    const uint32_t* cand_end[5];
     // ---- program ----
-    const UnitDesc* units;      // with hot_states / hot_off filled for the shared-memory image
-    uint32_t n_units;
+    uint32_t n_units;           // units of THIS launch: udesc[0 .. n_units)
+    uint32_t unit_base;         // index of udesc[0] in the program (claim counter = counters[unit_base + u])
+    uint32_t n_units_total;
+    const UnitDesc* units;      // all units (global memory copy, read by the epilogue beyond the parameter bank)
     const uint8_t* arena;       // full tables (global memory)
-    const uint8_t* image;       // shared-memory image: class maps + hot rows
-    uint32_t image_bytes;
+    const uint8_t* images;      // per-unit shared-memory images (UnitDesc::img_off / img_bytes)
     const uint32_t* acc_idx;
     const uint32_t* acc_events;
     const uint32_t* end_idx;
@@ -60,6 +59,8 @@ struct KParams {
     uint32_t v0[2];
     const uint32_t* v1;         // [cv][atom] verdict when exactly one cared atom deviates from `expect`
     const uint16_t* s1;         // [atom] service in that case
+    uint32_t vclean[2];         // verdict of a request whose atom bitmap is all zero
+    uint32_t sclean;            // its service
     // service routes (rules [n_waf_rules, n_rules)); `service` null: not requested for this batch
     uint32_t n_waf_rules;
     uint32_t s0;
@@ -71,8 +72,9 @@ struct KParams {
     const uint32_t* cset;
     int32_t gate_atom;
     uint32_t eval_gates;
-    uint32_t n_slots;           // scanned fields
-    uint32_t slot_field[5];     // slot -> Field
+    // units whose start state has end-of-field events: the epilogue finishes their EMPTY fields (they never reach the scan)
+    uint32_t n_start_end;
+    uint32_t start_end_unit[8];
     // ---- longest-prefix tables ----
     const uint32_t* dir24;
     const uint32_t* tbl8;
@@ -84,31 +86,42 @@ struct KParams {
     uint32_t lpm_present;
     uint32_t geo_loaded;
     uint32_t need_lpm;          // any ip-set atom, or geo columns needed and resolved on device
-    // ---- copy of the first unit descriptors in the parameter (constant) bank: the field-scan kernel reads them with a
+    // ---- unit descriptors of this launch in the parameter (constant) bank: the scan kernel reads them with a
     //      warp-uniform index, which keeps the per-unit parameters out of the vector register file ----
     UnitDesc udesc[kMaxConstUnits];
     NsAtom nsd[kMaxConstNs];    // likewise for the first non-scan atoms (read by every request's epilogue)
 };
 
-struct LaunchPlan {
-    size_t smem_bytes;
-    int grid;
+// candidate gate (kernel_gate.cuh)
+struct GateField {
+    const uint8_t* col;      // field bytes
+    const uint32_t* off;     // n + 1 offsets
+    const uint32_t* b1;      // first bitmap (2^k1 bits), global memory
+    const uint32_t* b2;      // second bitmap (2^k2 bits)
+    uint32_t k1, k2;
+    uint32_t* cand_count;    // candidate list of the field: one counter ...
+    uint32_t* cand_idx;      // ... and request index / field start / field end per candidate
+    uint32_t* cand_start;
+    uint32_t* cand_end;
+};
+
+struct GateParams {
+    GateField f[kMaxGateFields];
+    uint32_t n_fields;
+    uint32_t n;              // requests
 };
 
 // host-callable wrappers (kernels.cu)
-size_t waf_smem_bytes(uint32_t image_bytes, uint32_t n_units, uint32_t atom_words, uint32_t n_slots);
-size_t waf_smem_fixed_bytes(uint32_t n_units, uint32_t atom_words, uint32_t n_slots);  // everything except the image
-const char* waf_launch(const KParams& p, const LaunchPlan& plan, void* stream);
-// stream-scan path: scan kernel + epilogue kernel; `rows` = n * atom_words words of scratch, `task_counter` one word
-size_t waf_stream_smem_bytes(uint32_t image_bytes, uint32_t n_units);
-const char* waf_stream_launch(const KParams& p, uint32_t* rows, uint32_t* task_counter, int sm_count, size_t smem_bytes, void* stream);
-// field-scan path: scan kernel + epilogue kernel; `rows` = n * atom_words words immediately followed by
-// kFieldCounters claim counters (`counters` points at them)
-constexpr uint32_t kFieldCounters = 64;
-size_t waf_field_smem_bytes(uint32_t image_bytes, uint32_t n_units);
-int waf_field_threads();  // threads per CTA of the field-scan kernel
-const char* waf_field_launch(const KParams& p, uint32_t* rows, uint32_t* counters, int sm_count, size_t smem_bytes, void* stream,
-                             cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);  // optional events around the scan kernel
+size_t waf_scan_smem_bytes(uint32_t max_image_bytes);
+size_t waf_scan_image_budget(size_t max_smem_optin);  // bytes a unit image may take
+int waf_scan_threads();
+size_t waf_gate_smem_bytes(const GateParams& g);
+// One batch: [gate] -> scan (one launch per kMaxConstUnits units) -> epilogue, all on `stream`.
+// `all_units` = the program's unit descriptors (host copy); `small` = the block of claim counters and candidate counters
+// to zero first (`small_words` words).  ev0 / ev1 (optional) bracket the gate + scan kernels.
+const char* waf_batch_launch(KParams& p, const GateParams& g, const UnitDesc* all_units, uint32_t* small, uint32_t small_words, int sm_count,
+                             size_t scan_smem, size_t gate_smem, void* stream, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,
+                             uint32_t* launches = nullptr);
 const char* client_id_launch(const uint8_t* ip, const uint8_t* is_v6, const uint8_t* ua_bytes, const uint32_t* ua_off, const uint8_t* host_bytes,
                              const uint32_t* host_off, uint32_t n, uint8_t* out44, void* stream);
 const char* geoip_launch(const KParams& p, const uint8_t* ip, const uint8_t* is_v6, uint32_t n, uint32_t* asn_out,

@@ -45,16 +45,27 @@ struct UnitDesc {
     uint32_t end_any;      // 0 if no state of this DFA has end-of-input accepts (skip finalisation)
     uint32_t field_slot;   // index among the fields that are actually scanned
     uint32_t hot_states;   // states < hot_states have their rows in the shared-memory image; row `hot_states` is the trap row
-    uint32_t hot_off;      // byte offset of those rows in the shared-memory image
+    uint32_t hot_off;      // byte offset of those rows in the unit's shared-memory image
     uint32_t lim;          // min(hot_states, acc_lo): a walked word whose maximum state is < lim needs no attention at all.
                            // In the image every transition to a cold state (>= hot_states) is replaced by the trap row index.
-    uint32_t acc1_off;     // image offset of uint16 acc1[s - acc_lo] for acc_lo <= s < hot_states: the atom of a single-FIRE
+    uint32_t acc1_off;     // unit-image offset of uint16 acc1[s - acc_lo] for acc_lo <= s < hot_states: the atom of a single-FIRE
                            // event list, or 0xFFFF when the list needs the general path
-    uint32_t end1_off;     // image offset of uint16 end1[s] for s < hot_states: end-of-field events of state s:
+    uint32_t end1_off;     // unit-image offset of uint16 end1[s] for s < hot_states: end-of-field events of state s:
                            // 0xFFFE none, an atom id for a single FIRE, 0xFFFF general list
-    uint32_t idle_state;   // most frequent state on neutral text: speculative start state of the stream scan
+    uint32_t mode;         // UnitMode: which requests the unit walks
     uint32_t has_latch;    // the unit has gap-split patterns (latch events must be applied in string order)
-    uint32_t pad2[2];
+    uint32_t abs0, abs1;   // absorbing states (every transition leads back to the state itself): a string that reaches one
+                           // is finished early, as if the field ended there; 0xFFFFFFFF when absent
+    uint32_t img_off;      // byte offset of this unit's shared-memory image in the image buffer (256-byte aligned)
+    uint32_t img_bytes;    // size of that image: class map (offset 0), hot rows + trap row (hot_off), acc1, end1
+    uint32_t start_end;    // 1 if the start state has end-of-field events (empty fields are finished by the epilogue)
+    uint32_t pad3;
+};
+
+// which requests a scan unit walks
+enum UnitMode : uint32_t {
+    UM_ALL = 0,        // every request (patterns the gate cannot cover; start-anchored patterns, which finish early)
+    UM_CANDIDATES = 1  // only the requests the candidate gate flagged for the unit's field
 };
 
 // predicates evaluated once per request outside the byte scan

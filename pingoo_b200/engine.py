@@ -20,7 +20,8 @@ from .rules import Error, ListType, Rule, Service
 class WafEngine:
     def __init__(self, rules: Iterable[Rule], lists: Optional[Dict[str, Tuple[ListType, bytes]]] = None,
                  geoip_mmdb: Optional[bytes] = None, device: int = 0, eval_gates: bool = True,
-                 max_dfa_states: int = 0, max_unit_table_bytes: int = 0, services: Optional[Iterable[Service]] = None):
+                 max_dfa_states: int = 0, max_unit_table_bytes: int = 0, services: Optional[Iterable[Service]] = None,
+                 candidate_gate: bool = True):
         self._lib = _ffi.load()
         self._h = C.c_void_p()
         self.rules = list(rules)
@@ -33,7 +34,7 @@ class WafEngine:
             descs[i].expression = None if r.expression is None else r.expression.encode()
             descs[i].actions = C.cast(acts, C.POINTER(C.c_uint8))
             descs[i].n_actions = len(r.actions)
-        opt = _ffi.Options(max_dfa_states, max_unit_table_bytes, 1 if eval_gates else 0)
+        opt = _ffi.Options(max_dfa_states, max_unit_table_bytes, 1 if eval_gates else 0, 0 if candidate_gate else 1)
         err = C.create_string_buffer(1024)
         if self._lib.pgw_ruleset_create(descs, len(self.rules), C.byref(opt), C.byref(self._h), err, len(err)):
             raise Error(err.value.decode(errors="replace"))

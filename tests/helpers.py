@@ -141,6 +141,8 @@ def sim_lib():
         lib.pgwsim_geoip_lookup.argtypes = [p, p, p, C.c_uint32, p, p]
         lib.pgwsim_destroy.argtypes = [p]
         lib.pgwsim_destroy.restype = None
+        lib.pgwsim_set_gate_stats.argtypes = [p, p]
+        lib.pgwsim_set_gate_stats.restype = None
         _sim = lib
     return _sim
 
@@ -148,11 +150,12 @@ def sim_lib():
 class Sim:
     """CPU walk over the tables the product compiler emits (compiler check without a GPU)."""
 
-    def __init__(self, rules, lists=None, geoip_mmdb=None, eval_gates=True, max_dfa_states=0, max_unit_table_bytes=0, services=None):
+    def __init__(self, rules, lists=None, geoip_mmdb=None, eval_gates=True, max_dfa_states=0, max_unit_table_bytes=0, services=None,
+                 candidate_gate=True):
         self.lib = sim_lib()
         descs, keep, n = _descs(rules)
         err = C.create_string_buffer(2048)
-        opt = _ffi.Options(max_dfa_states, max_unit_table_bytes, 1 if eval_gates else 0)
+        opt = _ffi.Options(max_dfa_states, max_unit_table_bytes, 1 if eval_gates else 0, 0 if candidate_gate else 1)
         self.h = self.lib.pgwsim_create(descs, n, C.byref(opt), err, len(err))
         if not self.h:
             raise ValueError(err.value.decode(errors="replace"))
@@ -168,6 +171,12 @@ class Sim:
                 raise ValueError(err.value.decode(errors="replace"))
         if self.lib.pgwsim_finalize(self.h, err, len(err)):
             raise ValueError(err.value.decode(errors="replace"))
+
+    def gate_stats(self):
+        """Start counting, per field, how many requests the gate saw and how many it made candidates."""
+        self._stats = np.zeros(10, dtype=np.uint64)
+        self.lib.pgwsim_set_gate_stats(self.h, self._stats.ctypes.data)
+        return self._stats
 
     def describe(self):
         n = self.lib.pgwsim_describe(self.h, None, 0)

@@ -22,6 +22,7 @@ struct Sim {
     HostProgram H;
     bool finalized = false;
     std::string last_error;
+    uint64_t* stats = nullptr;  // optional: per field {requests gated, candidates}
 };
 
 int fail(Sim* s, const std::string& m, char* err, size_t cap) {
@@ -85,6 +86,7 @@ void* pgwsim_create(const pgw_rule_desc* rules, uint32_t n, const pgw_options* o
         if (opt->max_dfa_states > 0) s->builder.options.max_dfa_states = opt->max_dfa_states;
         if (opt->max_unit_table_bytes > 0) s->builder.options.max_unit_table_bytes = (size_t)opt->max_unit_table_bytes;
         s->builder.options.eval_gates = opt->eval_gates != 0;
+        s->builder.options.candidate_gate = opt->disable_candidate_gate == 0;
     }
     for (uint32_t i = 0; i < n; ++i) {
         std::string e;
@@ -168,8 +170,26 @@ int pgwsim_evaluate_routed(void* h, const pgw_batch* b, uint32_t* out, uint16_t*
     std::vector<uint32_t> row(Aw);
     for (uint32_t r = 0; r < b->n; ++r) {
         std::fill(row.begin(), row.end(), 0);
+        // candidate gate (gate.hpp): every even-aligned 4-byte window of the column that overlaps the field
+        bool cand[N_FIELDS] = {false, false, false, false, false};
+        for (int f = 0; f < N_FIELDS; ++f) {
+            const GateTables& G = H.gate[f];
+            if (!G.present) continue;
+            const uint8_t* bytes = cols[f]->bytes;
+            const uint32_t a = cols[f]->offsets[r], e = cols[f]->offsets[r + 1], total = cols[f]->offsets[b->n];
+            uint32_t j = a >= 3 ? a - 3 : 0;
+            j += j & 1u;
+            for (; j < e && !cand[f]; j += 2) {
+                uint32_t w = 0;
+                for (uint32_t k = 0; k < 4; ++k)
+                    if (j + k < total) w |= (uint32_t)bytes[j + k] << (8 * k);  // past the column: zeros
+                cand[f] = G.test(w);
+            }
+            if (s->stats) { s->stats[2 * f] += 1; s->stats[2 * f + 1] += cand[f] ? 1 : 0; }
+        }
         // scan units
         for (const UnitDesc& u : H.units) {
+            if (u.mode == UM_CANDIDATES && !cand[u.field]) continue;
             const uint8_t* bytes = cols[u.field]->bytes;
             uint32_t a = cols[u.field]->offsets[r], e = cols[u.field]->offsets[r + 1];
             const uint8_t* cls = H.arena.data() + u.cls_off;
@@ -187,6 +207,7 @@ int pgwsim_evaluate_routed(void* h, const pgw_batch* b, uint32_t* out, uint16_t*
             for (uint32_t i = a; i < e; ++i) {
                 st = tbl[st * u.n_classes + cls[bytes[i]]];
                 if (st >= u.acc_lo) run_events(H.acc_idx, H.acc_events, u.acc_base + st - u.acc_lo);
+                if (st == u.abs0 || st == u.abs1) break;  // absorbing: the kernel finishes the field here
             }
             if (u.end_any) run_events(H.end_idx, H.end_events, u.end_base + st);
         }
@@ -201,10 +222,10 @@ int pgwsim_evaluate_routed(void* h, const pgw_batch* b, uint32_t* out, uint16_t*
             bool v6 = b->ip_is_v6[r] != 0;
             const LpmLeaf& lf = H.lpm.leaves[lpm_lookup(H.lpm, ip16, v6)];
             set_mask = lf.set_mask;
-            if (H.lpm.geo_loaded && !b->asn && !geo_skip(ip16, v6)) { asn = lf.asn; country = lf.country; }
+            if (H.lpm.geo_loaded && !(b->asn && b->country) && !geo_skip(ip16, v6)) { asn = lf.asn; country = lf.country; }
         }
-        if (b->asn) asn = b->asn[r];
-        if (b->country) country = b->country[r];
+        // the geo columns count only when BOTH are supplied (capi.cu launch_on nulls them otherwise; the oracle likewise)
+        if (b->asn && b->country) { asn = b->asn[r]; country = b->country[r]; }
         for (const NsAtom& a : H.ns_atoms) {
             bool v = false;
             if (a.kind == AtomDesc::INT_CMP || a.kind == AtomDesc::INT_SET) {
@@ -256,6 +277,9 @@ int pgwsim_evaluate_routed(void* h, const pgw_batch* b, uint32_t* out, uint16_t*
             if (bypass) { verdict = V_BYPASS | (kNoRule << 2); decided = true; }
         }
         if (!decided && (flags & RF_PRE_CAPTCHA)) { verdict = V_CAPTCHA | (kNoRule << 2); decided = true; }
+        bool dirty = false;
+        for (uint32_t w = 0; w < Aw; ++w) dirty |= row[w] != 0;
+        if (!decided && !dirty) { verdict = H.vclean[cv]; decided = true; }  // the epilogue's clean path
         if (!decided) {
             uint32_t diff = 0, ndev = 0, dev_atom = 0;
             for (uint32_t w = 0; w < Aw; ++w) {
@@ -294,7 +318,8 @@ int pgwsim_evaluate_routed(void* h, const pgw_batch* b, uint32_t* out, uint16_t*
         out[r] = verdict;
         if (svc_out) {
             uint32_t svc = kNoService;
-            if ((verdict & 3u) == V_ALLOW && H.n_rules > H.n_waf_rules) {
+            if ((verdict & 3u) == V_ALLOW && H.n_rules > H.n_waf_rules && !dirty) svc = H.sclean;
+            else if ((verdict & 3u) == V_ALLOW && H.n_rules > H.n_waf_rules) {
                 uint32_t diff = 0;
                 for (uint32_t w = 0; w < Aw; ++w) diff |= (row[w] ^ H.expect[w]) & H.care[w];
                 if (single_dev != 0xFFFFFFFFu) svc = H.s1[single_dev];
@@ -348,6 +373,9 @@ uint32_t pgwsim_state_histogram(void* h, const pgw_batch* b, uint32_t unit, uint
     }
     return u.n_states;
 }
+
+// debug: per field {requests seen by the gate, candidates} accumulated over later evaluate calls (10 counters)
+void pgwsim_set_gate_stats(void* h, uint64_t* stats10) { ((Sim*)h)->stats = stats10; }
 
 void pgwsim_destroy(void* h) { delete (Sim*)h; }
 

@@ -35,9 +35,9 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_ffi.RuleDesc) == 32
     assert C.sizeof(_ffi.StrCol) == 16
     assert C.sizeof(_ffi.Batch) == 8 + 5 * 16 + 6 * 8
-    assert C.sizeof(_ffi.Options) == 24
+    assert C.sizeof(_ffi.Options) == 24  # 4 (+4 pad) + 8 + 4 + 4
     assert C.sizeof(_ffi.ServiceDesc) == 16
-    assert C.sizeof(_ffi.Info) == 9 * 4 + 4 + 2 * 8 + 4 * 4 + 3 * 4 + 4 + 3 * 8
+    assert C.sizeof(_ffi.Info) == 9 * 4 + 4 + 2 * 8 + 4 * 4 + 3 * 4 + 4 + 3 * 8 + 2 * 4 + 8
 
 
 def test_compile_and_validate_expression_need_no_gpu():
