@@ -87,7 +87,7 @@ struct Scratch {
     uint32_t* rows = nullptr;
     uint32_t* dirty = nullptr;
     uint32_t* small = nullptr;       // [0, kSmallCounters): per-unit claim counters; [kSmallCounters, +5): candidate counters
-    uint32_t* cand[5][3] = {};       // per gated field: idx, start, end
+    uint32_t* cand[5][4] = {};       // per gated field: idx, start, end, unit mask
 };
 constexpr uint32_t kSmallCounters = 1024;   // scan units a program may have
 constexpr uint32_t kSmallWords = kSmallCounters + 8;
@@ -159,7 +159,7 @@ Scratch* scratch_acquire(pgw_ruleset* rs, uint32_t n, cudaStream_t stream, std::
     cap = (cap + 31) & ~(size_t)31;
     size_t n_gated = 0;
     for (int f = 0; f < 5; ++f) n_gated += H.gate[f].present ? 1 : 0;
-    const size_t rows_b = cap * H.atom_words * 4, dirty_b = cap / 32 * 4 + 64, small_b = kSmallWords * 4, cand_b = n_gated * 3 * cap * 4;
+    const size_t rows_b = cap * H.atom_words * 4, dirty_b = cap / 32 * 4 + 64, small_b = kSmallWords * 4, cand_b = n_gated * 4 * cap * 4;
     const size_t total = rows_b + dirty_b + small_b + cand_b + 1024;
     if (cudaMalloc((void**)&sc->base, total) != cudaSuccess || cudaEventCreateWithFlags(&sc->done, cudaEventDisableTiming) != cudaSuccess) {
         e = std::string("CUDA: scratch allocation failed (") + std::to_string(total >> 20) + " MiB): " + cudaGetErrorString(cudaGetLastError());
@@ -175,7 +175,7 @@ Scratch* scratch_acquire(pgw_ruleset* rs, uint32_t n, cudaStream_t stream, std::
     sc->small = (uint32_t*)q; q += small_b;
     for (int f = 0; f < 5; ++f)
         if (H.gate[f].present)
-            for (int k = 0; k < 3; ++k) { sc->cand[f][k] = (uint32_t*)q; q += cap * 4; }
+            for (int k = 0; k < 4; ++k) { sc->cand[f][k] = (uint32_t*)q; q += cap * 4; }
     sc->cap_requests = cap;
     sc->busy = true;
     rs->pool.push_back(sc);
@@ -315,9 +315,9 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
         if (G.n_fields >= kMaxGateFields) return fail("too many gated fields", err, err_cap);
         GateField& gf = G.f[G.n_fields];
         gf.b1 = (const uint32_t*)chk(M.upload(H.gate[f].b1));
-        gf.b2 = (const uint32_t*)chk(M.upload(H.gate[f].b2));
+        gf.slots = (const uint32_t*)chk(M.upload(H.gate[f].slots));
         gf.k1 = H.gate[f].k1;
-        gf.k2 = H.gate[f].k2;
+        gf.kt = H.gate[f].kt;
         rs->gate_field[G.n_fields++] = f;
     }
     rs->gate_smem = waf_gate_smem_bytes(G);
@@ -332,6 +332,8 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     P.care = (const uint32_t*)chk(M.upload(H.care));
     P.ns = (const NsAtom*)chk(M.upload(H.ns_atoms));
     P.n_ns = (uint32_t)H.ns_atoms.size();
+    for (int g = 0; g < 9; ++g) P.ns_begin[g] = H.ns_begin[g];
+    for (int f = 0; f < 7; ++f) { P.ns_lo[f] = H.ns_lo[f]; P.ns_hi[f] = H.ns_hi[f]; P.ns_vmin[f] = H.ns_vmin[f]; P.ns_vmax[f] = H.ns_vmax[f]; }
     memset(P.nsd, 0, sizeof P.nsd);
     for (size_t i = 0; i < H.ns_atoms.size() && i < kMaxConstNs; ++i) P.nsd[i] = H.ns_atoms[i];
     P.code = (const uint16_t*)chk(M.upload(H.code));
@@ -423,6 +425,8 @@ static int launch_on(pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdict_out,
         G.f[i].cand_idx = sc->cand[f][0];
         G.f[i].cand_start = sc->cand[f][1];
         G.f[i].cand_end = sc->cand[f][2];
+        G.f[i].cand_mask = sc->cand[f][3];
+        P.cand_mask[f] = G.f[i].cand_mask;
         P.cand_count[f] = G.f[i].cand_count;
         P.cand_idx[f] = G.f[i].cand_idx;
         P.cand_start[f] = G.f[i].cand_start;

@@ -2,6 +2,8 @@
 #include "compile.hpp"
 
 #include <algorithm>
+#include <climits>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -74,7 +76,7 @@ std::string HostProgram::summary() const {
         o << " [" << kFieldNames[units[u].field] << (units[u].mode == UM_CANDIDATES ? "/gated" : units[u].abs0 != 0xFFFFFFFFu ? "/early-exit" : "")
           << ": states=" << units[u].n_states << " classes=" << units[u].n_classes << "]";
     for (int f = 0; f < N_FIELDS; ++f)
-        if (gate[f].present) o << " gate(" << kFieldNames[f] << ": grams=" << gate[f].n_grams << " bits=2^" << gate[f].k1 << ")";
+        if (gate[f].present) o << " gate(" << kFieldNames[f] << ": grams=" << gate[f].n_grams << " bloom=2^" << gate[f].k1 << " table=2^" << gate[f].kt << ")";
     o << " ns_atoms=" << ns_atoms.size() << " lpm=" << (lpm.present ? 1 : 0);
     return o.str();
 }
@@ -315,7 +317,7 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
     static const int kFieldOrder[N_FIELDS] = {F_URL, F_USER_AGENT, F_PATH, F_HOST, F_METHOD};  // longest first
     enum { UC_FULL = 0, UC_ANCH = 1, UC_GATED = 2, N_UC = 3 };
     // arena: all class maps first, then the tables
-    struct Pending { Dfa dfa; int field; uint32_t mode; std::vector<int> latch_of_event; };
+    struct Pending { Dfa dfa; int field; uint32_t mode; uint32_t gate_bit = 0; std::vector<int> latch_of_event; };
     std::vector<Pending> pend;
     for (int fo = 0; fo < N_FIELDS; ++fo) {
         int f = kFieldOrder[fo];
@@ -373,9 +375,12 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
                 if (keep[i]) { kept_b.push_back(std::move(bundles[UC_GATED][i])); kept_a.push_back(bundle_atom[UC_GATED][i]); }
                 else { bundles[UC_FULL].push_back(std::move(bundles[UC_GATED][i])); bundle_atom[UC_FULL].push_back(bundle_atom[UC_GATED][i]); }
             }
+            std::vector<GatedGrams> kept_g;
+            for (size_t i = 0; i < gated_grams.size(); ++i)
+                if (keep[i]) kept_g.push_back(std::move(gated_grams[i]));
+            gated_grams.swap(kept_g);
             bundles[UC_GATED].swap(kept_b);
             bundle_atom[UC_GATED].swap(kept_a);
-            if (!bundles[UC_GATED].empty()) gate_build_tables(std::move(all), &H.gate[f]);
         }
         bool any = false;
         for (int cls = 0; cls < N_UC; ++cls) {
@@ -389,11 +394,20 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
                       std::to_string(opt.max_dfa_states) + " states: " + which;
                 return false;
             }
+            if (cls == UC_GATED) {
+                // a gram leads to the units whose patterns it came from (bit = unit index among the field's gated units, mod 32)
+                std::vector<uint32_t> grams, masks;
+                for (size_t g = 0; g < groups.dfas.size(); ++g)
+                    for (int bi : groups.members[g])
+                        for (uint32_t x : gated_grams[bi].grams) { grams.push_back(x); masks.push_back(1u << (g & 31)); }
+                gate_build_tables(grams, masks, &H.gate[f]);
+            }
             for (size_t g = 0; g < groups.dfas.size(); ++g) {
                 Pending pd;
                 pd.dfa = std::move(groups.dfas[g]);
                 pd.field = f;
                 pd.mode = cls == UC_GATED ? UM_CANDIDATES : UM_ALL;
+                pd.gate_bit = (uint32_t)(g & 31);
                 // latch numbering is local to the unit
                 pd.latch_of_event.assign(M.events.size(), 0);
                 int next_latch = 0;
@@ -455,6 +469,7 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
         ud.hot_states = ud.n_states;
         ud.hot_off = ud.tbl_off;
         ud.mode = pend[u].mode;
+        ud.gate_bit = pend[u].gate_bit;
         // absorbing states: once reached nothing can change any more, the field is finished as if it ended there
         ud.abs0 = ud.abs1 = 0xFFFFFFFFu;
         for (int st = 0; st < d.n_states; ++st) {
@@ -509,6 +524,33 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
         }
         if (d.kind == AtomDesc::IP_SET) H.needs_ip = true;
         if (d.kind == AtomDesc::COUNTRY_SET) H.needs_geo_cols = true;
+    }
+    // group the predicates by feature and derive the per-feature quick reject (most requests satisfy none of them)
+    {
+        auto group = [](const NsAtom& a) { return (a.kind == AtomDesc::INT_CMP || a.kind == AtomDesc::INT_SET) ? (int)a.feat : (int)N_INT_FEATS; };
+        std::stable_sort(H.ns_atoms.begin(), H.ns_atoms.end(), [&](const NsAtom& x, const NsAtom& y) { return group(x) < group(y); });
+        for (int g = 0; g <= N_INT_FEATS + 1; ++g) H.ns_begin[g] = 0;
+        for (auto& a : H.ns_atoms) H.ns_begin[group(a) + 1]++;
+        for (int g = 0; g <= N_INT_FEATS; ++g) H.ns_begin[g + 1] += H.ns_begin[g];
+        for (int f = 0; f < N_INT_FEATS; ++f) {
+            int64_t lo = INT64_MIN, hi = INT64_MAX, vmin = INT64_MAX, vmax = INT64_MIN;
+            for (uint32_t i = H.ns_begin[f]; i < H.ns_begin[f + 1]; ++i) {
+                const NsAtom& a = H.ns_atoms[i];
+                if (a.kind == AtomDesc::INT_SET) {
+                    for (uint32_t k = H.iset_off[a.set_id]; k < H.iset_off[a.set_id + 1]; ++k) { vmin = std::min(vmin, H.iset_vals[k]); vmax = std::max(vmax, H.iset_vals[k]); }
+                    continue;
+                }
+                switch (a.op) {
+                    case CMP_LT: lo = std::max(lo, a.cval); break;
+                    case CMP_LE: lo = std::max(lo, a.cval == INT64_MAX ? a.cval : a.cval + 1); if (a.cval == INT64_MAX) hi = INT64_MIN; break;
+                    case CMP_GT: hi = std::min(hi, a.cval); break;
+                    case CMP_GE: hi = std::min(hi, a.cval == INT64_MIN ? a.cval : a.cval - 1); if (a.cval == INT64_MIN) lo = INT64_MAX; break;
+                    case CMP_EQ: vmin = std::min(vmin, a.cval); vmax = std::max(vmax, a.cval); break;
+                    default: lo = INT64_MAX; hi = INT64_MIN; break;  // (CMP_NE is lowered to NOT EQ; be safe: no quick reject)
+                }
+            }
+            H.ns_lo[f] = lo; H.ns_hi[f] = hi; H.ns_vmin[f] = vmin; H.ns_vmax[f] = vmax;
+        }
     }
     if (M.ip_sets.size() > 32) {
         err = "more than 32 distinct Ip lists referenced by rules";

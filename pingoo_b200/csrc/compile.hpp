@@ -39,7 +39,10 @@ struct HostProgram {
     uint32_t n_atoms = 0, atom_words = 0;
     std::vector<uint32_t> expect;  // expected atom values (perf heuristic only)
     std::vector<uint32_t> care;    // atoms referenced by at least one rule
-    std::vector<NsAtom> ns_atoms;
+    std::vector<NsAtom> ns_atoms;            // grouped: integer predicates by feature (IntFeat order), then ip / country sets
+    uint32_t ns_begin[N_INT_FEATS + 2] = {0};  // group g = ns_atoms[ns_begin[g], ns_begin[g + 1]); group N_INT_FEATS = the sets
+    // quick reject per integer feature: lo <= x <= hi and (x < vmin or x > vmax) => every predicate on the feature is false
+    int64_t ns_lo[N_INT_FEATS], ns_hi[N_INT_FEATS], ns_vmin[N_INT_FEATS], ns_vmax[N_INT_FEATS];
     std::vector<uint16_t> code;
     std::vector<uint32_t> rule_off;  // n_rules + 1
     std::vector<uint8_t> term;       // per rule: terminal action for cv=0 (bits 0-1) and cv=1 (bits 2-3)

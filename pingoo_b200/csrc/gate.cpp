@@ -288,23 +288,38 @@ bool gate_grams_for_pattern(const Nfa& nfa, int start, size_t cap, std::vector<u
     return true;
 }
 
-void gate_build_tables(std::vector<uint32_t> grams, GateTables* out) {
-    std::sort(grams.begin(), grams.end());
-    grams.erase(std::unique(grams.begin(), grams.end()), grams.end());
+void gate_build_tables(const std::vector<uint32_t>& grams, const std::vector<uint32_t>& masks, GateTables* out) {
+    std::vector<std::pair<uint32_t, uint32_t>> gm;
+    gm.reserve(grams.size());
+    for (size_t i = 0; i < grams.size(); ++i) gm.emplace_back(grams[i], masks[i]);
+    std::sort(gm.begin(), gm.end());
+    std::vector<std::pair<uint32_t, uint32_t>> u;
+    for (auto& x : gm) {
+        if (!u.empty() && u.back().first == x.first) u.back().second |= x.second;
+        else u.push_back(x);
+    }
     GateTables& T = *out;
     T = GateTables();
     T.present = true;
-    T.n_grams = (uint32_t)grams.size();
-    // first bitmap: at most ~1.5 % of windows pass by collision; second (independent hash) the same again
+    T.n_grams = (uint32_t)u.size();
+    // level 1: two bits per gram in one word; density <= 1/64 -> false-positive rate <= 2.5e-4 per window
     uint32_t k = 12;
-    while (k < kGateMaxLog2 - 1 && ((size_t)1 << k) < grams.size() * 64) ++k;
-    T.k1 = T.k2 = k;
+    while (k < kGateMaxLog2 && ((size_t)1 << k) < u.size() * 128) ++k;
+    T.k1 = k;
     T.b1.assign(((size_t)1 << T.k1) / 32, 0u);
-    T.b2.assign(((size_t)1 << T.k2) / 32, 0u);
-    for (uint32_t g : grams) {
-        const uint32_t h1 = (g * kGateHash1) >> (32 - T.k1), h2 = (g * kGateHash2) >> (32 - T.k2);
-        T.b1[h1 >> 5] |= 1u << (h1 & 31);
-        T.b2[h2 >> 5] |= 1u << (h2 & 31);
+    const uint32_t sh = 32 - T.k1;
+    // level 2: load factor <= 1/2
+    T.kt = 4;
+    while (((size_t)1 << T.kt) < u.size() * 2) ++T.kt;
+    T.slots.assign(((size_t)2 << T.kt), 0u);
+    const uint32_t tm = (1u << T.kt) - 1u;
+    for (auto& x : u) {
+        const uint32_t g = x.first, h = g * kGateHash1;
+        T.b1[h >> (sh + 5)] |= (1u << ((h >> sh) & 31)) | (1u << ((h >> (sh - 5)) & 31));
+        uint32_t s = (g * kGateHash2) >> (32 - T.kt);
+        while (T.slots[2 * s + 1] != 0) s = (s + 1) & tm;
+        T.slots[2 * s] = g;
+        T.slots[2 * s + 1] = x.second;
     }
 }
 

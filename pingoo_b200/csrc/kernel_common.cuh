@@ -117,17 +117,22 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, u
     if (p.asn) asn = p.asn[r];
     if (p.country) country = p.country[r];
 
-    for (uint32_t i = 0; i < p.n_ns; ++i) {
-        const NsAtom a = p.n_ns <= kMaxConstNs ? p.nsd[i] : p.ns[i];
-        bool v = false;
-        if (a.kind == 1 || a.kind == 2) {  // INT_CMP / INT_SET
-            int64_t x;
-            if (a.feat == 0) x = p.port ? (int64_t)p.port[r] : 0;
-            else if (a.feat == 1) x = asn;
-            else {
-                const uint32_t* o = p.off[a.feat - 2] + r;
-                x = (int64_t)(o[1] - o[0]);
-            }
+    // integer predicates, one feature at a time: the feature's quick reject (compile.hpp) settles almost every request
+#pragma unroll 1
+    for (uint32_t fe = 0; fe < 7u; ++fe) {
+        const uint32_t b0 = p.ns_begin[fe], b1 = p.ns_begin[fe + 1u];
+        if (b0 == b1) continue;
+        int64_t x;
+        if (fe == 0u) x = p.port ? (int64_t)p.port[r] : 0;
+        else if (fe == 1u) x = asn;
+        else {
+            const uint32_t* o = p.off[fe - 2u] + r;
+            x = (int64_t)(o[1] - o[0]);
+        }
+        if (x >= p.ns_lo[fe] && x <= p.ns_hi[fe] && (x < p.ns_vmin[fe] || x > p.ns_vmax[fe])) continue;
+        for (uint32_t i = b0; i < b1; ++i) {
+            const NsAtom a = p.n_ns <= kMaxConstNs ? p.nsd[i] : p.ns[i];
+            bool v = false;
             if (a.kind == 1) {
                 switch (a.op) {
                     case 0: v = x == a.cval; break;
@@ -147,7 +152,16 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, u
                     else h = m;
                 }
             }
-        } else if (a.kind == 3) {  // IP_SET
+            if (v && valid) {
+                row[a.atom >> 5] |= 1u << (a.atom & 31);
+                row_dirty = true;
+            }
+        }
+    }
+    for (uint32_t i = p.ns_begin[7]; i < p.n_ns; ++i) {
+        const NsAtom a = p.n_ns <= kMaxConstNs ? p.nsd[i] : p.ns[i];
+        bool v = false;
+        if (a.kind == 3) {  // IP_SET
             v = (set_mask >> a.set_id) & 1u;
         } else {  // COUNTRY_SET
             uint32_t c0 = (country & 0xFFu) - 'A', c1 = ((country >> 8) & 0xFFu) - 'A';

@@ -21,8 +21,8 @@ constexpr uint32_t kFsSlotStride = kFsThreads * 4u;  // per-lane slots: request 
 #define PGW_FS_TICKET 64
 #endif
 constexpr uint32_t kFsTicket = PGW_FS_TICKET;  // entries per atomic claim (two 32-entry pools: 128 and 256 measured worse, tail imbalance)
-constexpr uint32_t kFsPoolBytes = 384;  // a claimed pool: 32 field starts, 32 field ends, 32 request indices; two buffers per warp
-// front of the shared window (mbarrier, claim pools, per-lane slots), rounded so that the unit image behind it starts on a 256-byte boundary
+constexpr uint32_t kFsPoolBytes = 512;  // a claimed pool: 32 field starts, 32 field ends, 32 request indices, 32 unit masks; two buffers per warp
+// front of the shared window (mbarrier + skip flag, claim pools, per-lane slots), rounded so that the unit image behind it starts on a 256-byte boundary
 constexpr uint32_t kFsFront = (64u + (kFsThreads / 32) * 2u * kFsPoolBytes + 4u * kFsSlotStride + 255u) & ~255u;
 
 __device__ __forceinline__ void red_or(uint32_t* addr, uint32_t v) { asm volatile("red.global.or.b32 [%0], %1;" ::"l"(addr), "r"(v) : "memory"); }
@@ -108,31 +108,46 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
-    for (uint32_t u = 0; u < p.n_units; ++u) {
+    // CTAs start on different units (and wrap around), so that the latency tails of the units -- a long field is walked
+    // by one lane, byte after byte -- overlap instead of adding up; a unit whose work has all been claimed is skipped
+    uint32_t staged = 0;
+    volatile uint32_t* s_skip = reinterpret_cast<volatile uint32_t*>(s_img + 16);
+    for (uint32_t uk = 0; uk < p.n_units; ++uk) {
+        const uint32_t u = (uk + blockIdx.x) % p.n_units;
         const UnitDesc& cu = p.udesc[u];   // constant bank, uniform index
+        const bool cand = cu.mode == UM_CANDIDATES;
+        const uint32_t N = cand ? __ldg(p.cand_count[cu.field]) : p.n;
+        uint32_t* ctr = p.counters + p.unit_base + u;
         // ---- stage this unit's image: everybody has left the previous unit's tables ----
         __syncthreads();
         if (tid == 0) {
-            const uint32_t bytes = cu.img_bytes;
-            mbar_expect_tx(s_bar, bytes);
-            for (uint32_t o = 0; o < bytes; o += 32768u) {
-                const uint32_t nb = bytes - o < 32768u ? bytes - o : 32768u;
-                bulk_g2s(s_image + o, p.images + cu.img_off + o, nb, s_bar);
+            const uint32_t taken = *reinterpret_cast<volatile uint32_t*>(ctr);
+            const uint32_t skip_unit = taken >= N ? 1u : 0u;
+            *s_skip = skip_unit;
+            if (!skip_unit) {
+                const uint32_t bytes = cu.img_bytes;
+                mbar_expect_tx(s_bar, bytes);
+                for (uint32_t o = 0; o < bytes; o += 32768u) {
+                    const uint32_t nb = bytes - o < 32768u ? bytes - o : 32768u;
+                    bulk_g2s(s_image + o, p.images + cu.img_off + o, nb, s_bar);
+                }
             }
         }
-        mbar_wait(s_bar, u & 1u);
+        __syncthreads();
+        if (*s_skip) continue;
+        mbar_wait(s_bar, staged & 1u);
+        ++staged;
 
         const uint32_t C2 = 2u * cu.n_classes, D0 = cu.start_state, trap = cu.hot_states, lim = cu.lim, acclo = cu.acc_lo;
         const uint32_t abs0 = cu.abs0, abs1 = cu.abs1;
         const uint32_t clsaddr = a_img, hotaddr = a_img + cu.hot_off, acc1addr = a_img + cu.acc1_off, end1addr = a_img + cu.end1_off;
         const uint8_t* col = p.col[cu.field];
         const uint32_t* off = p.off[cu.field];
-        const bool cand = cu.mode == UM_CANDIDATES;
         const uint32_t* c_idx = p.cand_idx[cu.field];
         const uint32_t* c_start = p.cand_start[cu.field];
         const uint32_t* c_end = p.cand_end[cu.field];
-        const uint32_t N = cand ? __ldg(p.cand_count[cu.field]) : p.n;
-        uint32_t* ctr = p.counters + p.unit_base + u;
+        const uint32_t* c_mask = p.cand_mask[cu.field];
+        const uint32_t gate_bit = cu.gate_bit;
 
         // warp pools of 32 claimed entries, double buffered in shared memory: buffer `pb` is being handed out, the other
         // one holds the next claim whose triples are landing through cp.async (no registers, no stall)
@@ -163,10 +178,12 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                 cp_async4(dst, c_start + e);
                 cp_async4(dst + 128u, c_end + e);
                 cp_async4(dst + 256u, c_idx + e);
+                cp_async4(dst + 384u, c_mask + e);
             } else {
                 cp_async4(dst, off + e);
                 cp_async4(dst + 128u, off + e + 1u);
                 sts_u32(dst + 256u, e);
+                sts_u32(dst + 384u, 0xFFFFFFFFu);
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
             ah_valid = true;
@@ -227,7 +244,8 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                 if (want && idx < pool_end) {
                     const uint32_t sa = a_pool + pb * kFsPoolBytes + (idx & 31u) * 4u;
                     const uint32_t s0 = lds_u32_v(sa), e0 = lds_u32_v(sa + 128u);
-                    if (e0 > s0) {  // empty fields are left to the epilogue kernel
+                    // empty fields are left to the epilogue kernel; a candidate of other units of the field is not ours
+                    if (e0 > s0 && ((lds_u32_v(sa + 384u) >> gate_bit) & 1u)) {
                         sts_u32(a_slot + 3u * kFsSlotStride, lds_u32_v(sa + 256u));
                         pend = true;
                         end = e0;

@@ -94,10 +94,10 @@ size_t waf_scan_smem_bytes(uint32_t max_image_bytes) { return 256 + kFsFront + r
 size_t waf_gate_smem_bytes(const GateParams& g) {
     size_t m = 0;
     for (uint32_t i = 0; i < g.n_fields; ++i) {
-        size_t b = ((size_t)1 << g.f[i].k1) / 8 + ((size_t)1 << g.f[i].k2) / 8;
+        size_t b = ((size_t)1 << g.f[i].k1) / 8;
         if (b > m) m = b;
     }
-    return m;
+    return m + (kGateThreads / 32) * kGateWarpSmem;
 }
 
 const char* waf_batch_launch(KParams& p, const GateParams& g, const UnitDesc* all_units, uint32_t* small, uint32_t small_words, int sm_count,

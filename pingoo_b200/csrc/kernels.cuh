@@ -32,6 +32,7 @@ struct KParams {
     const uint32_t* cand_idx[5];
     const uint32_t* cand_start[5];
     const uint32_t* cand_end[5];
+    const uint32_t* cand_mask[5];   // per candidate: the gated units of the field it is a candidate for (UnitDesc::gate_bit)
     // ---- program ----
     uint32_t n_units;           // units of THIS launch: udesc[0 .. n_units)
     uint32_t unit_base;         // index of udesc[0] in the program (claim counter = counters[unit_base + u])
@@ -46,8 +47,10 @@ struct KParams {
     uint32_t n_atoms, atom_words;
     const uint32_t* expect;
     const uint32_t* care;
-    const NsAtom* ns;
+    const NsAtom* ns;           // grouped by integer feature, then the ip / country sets
     uint32_t n_ns;
+    uint32_t ns_begin[9];       // group g = ns[ns_begin[g], ns_begin[g + 1]); groups 0..6 = IntFeat, 7 = sets
+    int64_t ns_lo[7], ns_hi[7], ns_vmin[7], ns_vmax[7];  // quick reject of a whole integer group (compile.hpp)
     const uint16_t* code;
     const uint32_t* rule_off;
     const uint8_t* term;
@@ -96,13 +99,14 @@ struct KParams {
 struct GateField {
     const uint8_t* col;      // field bytes
     const uint32_t* off;     // n + 1 offsets
-    const uint32_t* b1;      // first bitmap (2^k1 bits), global memory
-    const uint32_t* b2;      // second bitmap (2^k2 bits)
-    uint32_t k1, k2;
+    const uint32_t* b1;      // level 1: blocked Bloom filter (2^k1 bits), global memory copy (staged into shared memory)
+    const uint32_t* slots;   // level 2: exact table, 2^kt slots of {gram, unit mask}
+    uint32_t k1, kt;
     uint32_t* cand_count;    // candidate list of the field: one counter ...
-    uint32_t* cand_idx;      // ... and request index / field start / field end per candidate
+    uint32_t* cand_idx;      // ... and request index / field start / field end / unit mask per candidate
     uint32_t* cand_start;
     uint32_t* cand_end;
+    uint32_t* cand_mask;
 };
 
 struct GateParams {

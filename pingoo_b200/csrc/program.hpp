@@ -59,7 +59,7 @@ struct UnitDesc {
     uint32_t img_off;      // byte offset of this unit's shared-memory image in the image buffer (256-byte aligned)
     uint32_t img_bytes;    // size of that image: class map (offset 0), hot rows + trap row (hot_off), acc1, end1
     uint32_t start_end;    // 1 if the start state has end-of-field events (empty fields are finished by the epilogue)
-    uint32_t pad3;
+    uint32_t gate_bit;     // UM_CANDIDATES: this unit's bit in a candidate's unit mask
 };
 
 // which requests a scan unit walks

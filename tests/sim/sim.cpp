@@ -171,7 +171,7 @@ int pgwsim_evaluate_routed(void* h, const pgw_batch* b, uint32_t* out, uint16_t*
     for (uint32_t r = 0; r < b->n; ++r) {
         std::fill(row.begin(), row.end(), 0);
         // candidate gate (gate.hpp): every even-aligned 4-byte window of the column that overlaps the field
-        bool cand[N_FIELDS] = {false, false, false, false, false};
+        uint32_t cand[N_FIELDS] = {0, 0, 0, 0, 0};  // per field: mask of the gated units the request is a candidate for
         for (int f = 0; f < N_FIELDS; ++f) {
             const GateTables& G = H.gate[f];
             if (!G.present) continue;
@@ -179,17 +179,17 @@ int pgwsim_evaluate_routed(void* h, const pgw_batch* b, uint32_t* out, uint16_t*
             const uint32_t a = cols[f]->offsets[r], e = cols[f]->offsets[r + 1], total = cols[f]->offsets[b->n];
             uint32_t j = a >= 3 ? a - 3 : 0;
             j += j & 1u;
-            for (; j < e && !cand[f]; j += 2) {
+            for (; j < e; j += 2) {
                 uint32_t w = 0;
                 for (uint32_t k = 0; k < 4; ++k)
                     if (j + k < total) w |= (uint32_t)bytes[j + k] << (8 * k);  // past the column: zeros
-                cand[f] = G.test(w);
+                cand[f] |= G.probe(w);
             }
             if (s->stats) { s->stats[2 * f] += 1; s->stats[2 * f + 1] += cand[f] ? 1 : 0; }
         }
         // scan units
         for (const UnitDesc& u : H.units) {
-            if (u.mode == UM_CANDIDATES && !cand[u.field]) continue;
+            if (u.mode == UM_CANDIDATES && !((cand[u.field] >> u.gate_bit) & 1u)) continue;
             const uint8_t* bytes = cols[u.field]->bytes;
             uint32_t a = cols[u.field]->offsets[r], e = cols[u.field]->offsets[r + 1];
             const uint8_t* cls = H.arena.data() + u.cls_off;
