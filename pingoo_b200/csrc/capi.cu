@@ -85,7 +85,7 @@ struct Scratch {
     bool busy = false;
     // carved out of `base`
     uint32_t* rows = nullptr;
-    uint32_t* dirty = nullptr;
+    uint32_t* info = nullptr;
     uint32_t* small = nullptr;       // [0, kSmallCounters): per-unit claim counters; [kSmallCounters, +5): candidate counters
     uint32_t* cand[5][4] = {};       // per gated field: idx, start, end, unit mask
 };
@@ -125,7 +125,7 @@ struct pgw_ruleset {
     DevMem mem;
     KParams base;  // program pointers filled in, batch fields zero
     GateParams gate_base;  // bitmaps and shifts filled in
-    int gate_field[kMaxGateFields] = {0, 0, 0};
+    int gate_field[kMaxGateFields] = {0, 0, 0, 0, 0};
     std::vector<UnitDesc> units;   // with the image fields filled in
     size_t scan_smem = 0, gate_smem = 0;
     uint32_t hot_states_total = 0;
@@ -159,7 +159,7 @@ Scratch* scratch_acquire(pgw_ruleset* rs, uint32_t n, cudaStream_t stream, std::
     cap = (cap + 31) & ~(size_t)31;
     size_t n_gated = 0;
     for (int f = 0; f < 5; ++f) n_gated += H.gate[f].present ? 1 : 0;
-    const size_t rows_b = cap * H.atom_words * 4, dirty_b = cap / 32 * 4 + 64, small_b = kSmallWords * 4, cand_b = n_gated * 4 * cap * 4;
+    const size_t rows_b = cap * H.atom_words * 4, dirty_b = cap * 8 + 64, small_b = kSmallWords * 4, cand_b = n_gated * 4 * cap * 4;
     const size_t total = rows_b + dirty_b + small_b + cand_b + 1024;
     if (cudaMalloc((void**)&sc->base, total) != cudaSuccess || cudaEventCreateWithFlags(&sc->done, cudaEventDisableTiming) != cudaSuccess) {
         e = std::string("CUDA: scratch allocation failed (") + std::to_string(total >> 20) + " MiB): " + cudaGetErrorString(cudaGetLastError());
@@ -171,7 +171,7 @@ Scratch* scratch_acquire(pgw_ruleset* rs, uint32_t n, cudaStream_t stream, std::
     if (cudaMemsetAsync(sc->base, 0, rows_b + dirty_b + small_b, stream) != cudaSuccess) { e = "CUDA: scratch memset failed"; cudaFree(sc->base); delete sc; return nullptr; }
     uint8_t* q = sc->base;
     sc->rows = (uint32_t*)q; q += rows_b;
-    sc->dirty = (uint32_t*)q; q += dirty_b;
+    sc->info = (uint32_t*)q; q += dirty_b;
     sc->small = (uint32_t*)q; q += small_b;
     for (int f = 0; f < 5; ++f)
         if (H.gate[f].present)
@@ -294,7 +294,6 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     }
     rs->scan_smem = waf_scan_smem_bytes(max_img);
     if (rs->scan_smem > rs->max_smem) return fail("ruleset does not fit the shared-memory plan", err, err_cap);
-    P.units = (const UnitDesc*)chk(M.upload(units));
     memset(P.udesc, 0, sizeof P.udesc);
     P.n_units_total = (uint32_t)units.size();
     P.n_units = 0;
@@ -307,19 +306,42 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
             if (P.n_start_end >= 8) return fail("too many scan units with patterns that match an empty field", err, err_cap);
             P.start_end_unit[P.n_start_end++] = (uint32_t)u;
         }
-    // candidate gate tables
+    // pre-pass kernel: candidate gate tables, and the small early-exit units (start-anchored patterns) of each field --
+    // those are walked there, one lane per request, instead of costing a pass of the scan kernel each
     GateParams& G = rs->gate_base;
     memset(&G, 0, sizeof G);
-    for (int f = 0; f < 5; ++f) {
-        if (!H.gate[f].present) continue;
-        if (G.n_fields >= kMaxGateFields) return fail("too many gated fields", err, err_cap);
-        GateField& gf = G.f[G.n_fields];
-        gf.b1 = (const uint32_t*)chk(M.upload(H.gate[f].b1));
-        gf.slots = (const uint32_t*)chk(M.upload(H.gate[f].slots));
-        gf.k1 = H.gate[f].k1;
-        gf.kt = H.gate[f].kt;
-        rs->gate_field[G.n_fields++] = f;
+    static const int kPrepassOrder[5] = {F_URL, F_USER_AGENT, F_PATH, F_HOST, F_METHOD};
+    size_t image_area = 0;
+    for (int fo = 0; fo < 5; ++fo) {
+        const int f = kPrepassOrder[fo];
+        GateField gf;
+        memset(&gf, 0, sizeof gf);
+        size_t used = 0;
+        for (size_t u = 0; u < units.size(); ++u) {
+            UnitDesc& ud = units[u];
+            if ((int)ud.field != f || ud.mode != UM_ALL || ud.abs0 == 0xFFFFFFFFu || ud.hot_states != ud.n_states) continue;
+            const size_t need = ((size_t)ud.img_bytes + 255) & ~(size_t)255;
+            if (gf.n_prefix >= kMaxPrefixUnits || used + need > waf_gate_prefix_budget()) continue;
+            ud.mode = UM_PREPASS;
+            gf.prefix_img[gf.n_prefix] = (uint32_t)used;
+            gf.prefix[gf.n_prefix++] = ud;
+            used += need;
+        }
+        if (used > image_area) image_area = used;
+        if (H.gate[f].present) {
+            gf.b1 = (const uint32_t*)chk(M.upload(H.gate[f].b1));
+            gf.slots = (const uint32_t*)chk(M.upload(H.gate[f].slots));
+            gf.k1 = H.gate[f].k1;
+            gf.kt = H.gate[f].kt;
+        }
+        if (!gf.b1 && !gf.n_prefix) continue;
+        rs->gate_field[G.n_fields] = f;
+        G.f[G.n_fields++] = gf;
     }
+    G.image_area = (uint32_t)image_area;
+    // the scan kernel reads the unit descriptors from the host copy (parameter bank) and the epilogue from P.units: both
+    // must see the UM_PREPASS marks
+    P.units = (const UnitDesc*)chk(M.upload(units));
     rs->gate_smem = waf_gate_smem_bytes(G);
     if (rs->gate_smem > rs->max_smem) return fail("candidate-gate bitmaps do not fit shared memory", err, err_cap);
     P.acc_idx = (const uint32_t*)chk(M.upload(H.acc_idx));
@@ -347,6 +369,8 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     P.vclean[0] = H.vclean[0];
     P.vclean[1] = H.vclean[1];
     P.sclean = H.sclean;
+    P.v1z = (const uint32_t*)chk(M.upload(H.v1z));
+    P.s1z = (const uint16_t*)chk(M.upload(H.s1z));
     P.dflt_services = (const uint32_t*)chk(M.upload(H.dflt_services));
     P.n_dflt_services = (uint32_t)H.dflt_services.size();
     P.service = nullptr;
@@ -413,7 +437,7 @@ static int launch_on(pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdict_out,
     Scratch* sc = scratch_acquire(rs, b->n, cs, e);
     if (!sc) return 1;
     P.rows = sc->rows;
-    P.dirty = sc->dirty;
+    P.info = sc->info;
     P.counters = sc->small;
     GateParams G = rs->gate_base;
     G.n = b->n;
@@ -421,6 +445,7 @@ static int launch_on(pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdict_out,
         const int f = rs->gate_field[i];
         G.f[i].col = cols[f]->bytes;
         G.f[i].off = cols[f]->offsets;
+        if (!G.f[i].b1) continue;
         G.f[i].cand_count = sc->small + kSmallCounters + f;
         G.f[i].cand_idx = sc->cand[f][0];
         G.f[i].cand_start = sc->cand[f][1];

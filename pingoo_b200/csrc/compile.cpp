@@ -305,6 +305,37 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
         H.sclean = kNoService;
         for (size_t r = H.n_waf_rules; r < M.rules.size(); ++r)
             if (M.pool.eval(M.rules[r].formula, zeros)) { H.sclean = (uint32_t)(r - H.n_waf_rules); break; }
+        // ... and one with exactly one true atom (one matched pattern, a non-GET method, ...): tabulated as well.
+        // Only rules that mention the atom, or that are true on the all-false vector, can be true there.
+        H.v1z.assign(2 * (size_t)H.n_atoms, 0);
+        H.s1z.assign(H.n_atoms, (uint16_t)kNoService);
+        std::vector<uint32_t> zero_true;  // rules true when every atom is false
+        for (size_t r = 0; r < M.rules.size(); ++r)
+            if (M.pool.eval(M.rules[r].formula, zeros)) zero_true.push_back((uint32_t)r);
+        for (uint32_t a = 0; a < H.n_atoms; ++a) {
+            zeros[a] = 1;
+            std::vector<uint32_t> cands(atom_rules[a].begin(), atom_rules[a].end());
+            cands.insert(cands.end(), zero_true.begin(), zero_true.end());
+            std::sort(cands.begin(), cands.end());
+            cands.erase(std::unique(cands.begin(), cands.end()), cands.end());
+            std::vector<uint32_t> true_rules;
+            for (uint32_t r : cands)
+                if (M.pool.eval(M.rules[r].formula, zeros)) true_rules.push_back(r);
+            for (int cv = 0; cv < 2; ++cv) {
+                uint32_t v = V_ALLOW | (kNoRule << 2);
+                for (uint32_t r : true_rules) {
+                    if (r >= H.n_waf_rules) break;
+                    uint8_t t = (H.term[r] >> (2 * cv)) & 3;
+                    if (!t) continue;
+                    v = t | (r << 2);
+                    break;
+                }
+                H.v1z[(size_t)cv * H.n_atoms + a] = v;
+            }
+            for (uint32_t r : true_rules)
+                if (r >= H.n_waf_rules) { H.s1z[a] = (uint16_t)(r - H.n_waf_rules); break; }
+            zeros[a] = 0;
+        }
     }
 
     // ---- scan units: DFA groups per field ------------------------------------------

@@ -61,6 +61,8 @@ struct HostProgram {
     GateTables gate[N_FIELDS];               // candidate gate of a field (present only if it has UM_CANDIDATES units)
     uint32_t vclean[2] = {0, 0};             // verdict of a request none of whose atoms is true, per captcha_verified
     uint32_t sclean = 0xFFFFu;               // its service
+    std::vector<uint32_t> v1z;               // [cv][atom]: verdict when exactly that atom is true, every other one false
+    std::vector<uint16_t> s1z;               // [atom]: service in that case
     int field_slot[N_FIELDS] = {-1, -1, -1, -1, -1};  // fields whose offsets the kernel stages
     uint32_t n_slots = 0;
     uint32_t scanned_fields_mask = 0;  // fields whose bytes are read (algorithmic-bytes accounting)

@@ -46,6 +46,40 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint8_t* p) {
     return r;
 }
 
+// ---- what a scan reports ----
+__device__ __forceinline__ void red_or(uint32_t* addr, uint32_t v) { asm volatile("red.global.or.b32 [%0], %1;" ::"l"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_max(uint32_t* addr, uint32_t v) { asm volatile("red.global.max.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory"); }
+
+// Where a scan writes what it found about one request: the request's atom bitmap row and its two info words
+// (KParams::info: largest fired atom + 1, 0x4000 - smallest fired atom).  All three are fire-and-forget reductions.
+struct Sink {
+    uint32_t* row;
+    uint32_t* inf;
+};
+__device__ __forceinline__ Sink sink_of(const KParams& p, uint32_t ridx) { return Sink{p.rows + (size_t)ridx * p.atom_words, p.info + 2u * (size_t)ridx}; }
+__device__ __forceinline__ void fire_atom(const Sink& k, uint32_t at) {
+    red_or(k.row + (at >> 5), 1u << (at & 31));
+    red_max(k.inf, at + 1u);
+    red_max(k.inf + 1, 0x4000u - at);
+}
+
+// events of CSR row `ci` applied to a request's sink; true if all of them were plain FIREs
+__device__ __forceinline__ bool fs_fire_list(const uint32_t* idx, const uint32_t* events, uint32_t ci, const Sink& row, uint32_t* latch) {
+    uint32_t a = __ldg(idx + ci), b = __ldg(idx + ci + 1);
+    uint32_t l = *latch;
+    bool pure = true;
+    for (uint32_t i = a; i < b; ++i) {
+        const uint32_t e = __ldg(events + i);
+        const uint32_t kind = e >> kEvKindShift, lb = 1u << ((e >> kEvLatchShift) & 31u), at = e & kEvAtomMask;
+        if (kind == 0u || (kind == 1u && (l & lb))) fire_atom(row, at);
+        else if (kind == 2u) l &= ~lb;
+        else if (kind == 3u) l |= lb;
+        pure &= kind == 0u;
+    }
+    *latch = l;
+    return pure;
+}
+
 __device__ __forceinline__ bool eval_rule(const uint16_t* __restrict__ code, uint32_t a, uint32_t b, const uint32_t* row) {
     uint32_t st = 0;
     for (uint32_t i = a; i < b; ++i) {
@@ -84,16 +118,20 @@ __device__ __forceinline__ uint32_t lpm_lookup(const KParams& p, const uint8_t* 
 }
 
 // Per-request predicates outside the byte scan + the verdict (http_listener.rs:196-264).
-// `row` is the request's atom bitmap in global memory (scan atoms already set; all zero unless `row_dirty`).
-// Called by all 32 lanes of a converged warp (`valid` false for lanes past the end of the batch, which shadow the last
-// request without storing anything).  A request whose bitmap stays all zero takes the precomputed verdict `vclean`
-// without reading the row; for the others, requests of the warp that deviate from the expected atom vector in the same
-// way are evaluated once -- verdict and service are functions of the deviation and of `captcha_verified` alone -- and the
-// result is shared by shuffle.  Rows that were touched are written back to zero (the scratch invariant).
-__device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, uint32_t* row, bool valid, bool row_dirty) {
+// The scan left, per request, two info words (KParams::info) and the bits of the fired atoms in the request's bitmap
+// row.  Called by all 32 lanes of a converged warp (`valid` false for lanes past the end of the batch, which shadow the
+// last request without storing anything).
+//   no atom true            -> the precomputed verdict `vclean` (the row is never read)
+//   one distinct atom true  -> the tabulated verdict `v1z[atom]`
+//   otherwise               -> the row is completed and the candidate rules are evaluated; requests of the warp that
+//                              deviate from the expected atom vector in the same way are evaluated once (verdict and
+//                              service are functions of the deviation and of `captcha_verified` alone), shared by shuffle.
+// Whatever the scan or this function wrote to the row / info words is written back to zero (the scratch invariant).
+__device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, bool valid) {
     const uint32_t Aw = p.atom_words;
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t flags = p.flags ? p.flags[r] : 0u;
+    uint32_t* const row = p.rows + (size_t)r * Aw;
     int64_t asn = 0;
     uint32_t country = (uint32_t)'X' | ((uint32_t)'X' << 8);
     uint32_t set_mask = 0;
@@ -110,71 +148,93 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, u
                 const uint32_t* w = reinterpret_cast<const uint32_t*>(ip16);
                 skip = ip16[0] == 0xFF || (w[0] == 0 && w[1] == 0 && w[2] == 0 && w[3] == 0x01000000u);
             }
-            // each column the caller did not supply comes from the database
             if (!skip) { asn = lf.asn; country = lf.country; }
         }
     }
     if (p.asn) asn = p.asn[r];
     if (p.country) country = p.country[r];
 
-    // integer predicates, one feature at a time: the feature's quick reject (compile.hpp) settles almost every request
-#pragma unroll 1
-    for (uint32_t fe = 0; fe < 7u; ++fe) {
-        const uint32_t b0 = p.ns_begin[fe], b1 = p.ns_begin[fe + 1u];
-        if (b0 == b1) continue;
-        int64_t x;
-        if (fe == 0u) x = p.port ? (int64_t)p.port[r] : 0;
-        else if (fe == 1u) x = asn;
-        else {
-            const uint32_t* o = p.off[fe - 2u] + r;
-            x = (int64_t)(o[1] - o[0]);
+    // atoms that are true outside the byte scan: end-of-field events of EMPTY fields (they never reach the scan) and
+    // the integer / set predicates.  Walked twice at most: once to count, once more to complete the row.
+    auto extras = [&](auto&& fn) {
+        for (uint32_t k = 0; k < p.n_start_end; ++k) {
+            const UnitDesc& ud = p.units[p.start_end_unit[k]];
+            const uint32_t* o = p.off[ud.field] + r;
+            if (o[0] != o[1]) continue;
+            const uint32_t a = __ldg(p.end_idx + ud.end_base + ud.start_state), b = __ldg(p.end_idx + ud.end_base + ud.start_state + 1);
+            for (uint32_t i = a; i < b; ++i) {
+                const uint32_t e = __ldg(p.end_events + i);
+                if ((e >> kEvKindShift) == 0u) fn(e & kEvAtomMask);  // latch kinds cannot fire on an empty field
+            }
         }
-        if (x >= p.ns_lo[fe] && x <= p.ns_hi[fe] && (x < p.ns_vmin[fe] || x > p.ns_vmax[fe])) continue;
-        for (uint32_t i = b0; i < b1; ++i) {
+        // integer predicates, one feature at a time: the feature's quick reject (compile.hpp) settles almost every request
+#pragma unroll 1
+        for (uint32_t fe = 0; fe < 7u; ++fe) {
+            const uint32_t b0 = p.ns_begin[fe], b1 = p.ns_begin[fe + 1u];
+            if (b0 == b1) continue;
+            int64_t x;
+            if (fe == 0u) x = p.port ? (int64_t)p.port[r] : 0;
+            else if (fe == 1u) x = asn;
+            else {
+                const uint32_t* o = p.off[fe - 2u] + r;
+                x = (int64_t)(o[1] - o[0]);
+            }
+            if (x >= p.ns_lo[fe] && x <= p.ns_hi[fe] && (x < p.ns_vmin[fe] || x > p.ns_vmax[fe])) continue;
+            for (uint32_t i = b0; i < b1; ++i) {
+                const NsAtom a = p.n_ns <= kMaxConstNs ? p.nsd[i] : p.ns[i];
+                bool v = false;
+                if (a.kind == 1) {
+                    switch (a.op) {
+                        case 0: v = x == a.cval; break;
+                        case 1: v = x != a.cval; break;
+                        case 2: v = x < a.cval; break;
+                        case 3: v = x <= a.cval; break;
+                        case 4: v = x > a.cval; break;
+                        default: v = x >= a.cval; break;
+                    }
+                } else {
+                    uint32_t l = p.iset_off[a.set_id], h = p.iset_off[a.set_id + 1];
+                    while (l < h) {
+                        uint32_t m = (l + h) >> 1;
+                        int64_t mv = __ldg(p.iset_vals + m);
+                        if (mv == x) { v = true; break; }
+                        if (mv < x) l = m + 1;
+                        else h = m;
+                    }
+                }
+                if (v) fn(a.atom);
+            }
+        }
+        for (uint32_t i = p.ns_begin[7]; i < p.n_ns; ++i) {
             const NsAtom a = p.n_ns <= kMaxConstNs ? p.nsd[i] : p.ns[i];
             bool v = false;
-            if (a.kind == 1) {
-                switch (a.op) {
-                    case 0: v = x == a.cval; break;
-                    case 1: v = x != a.cval; break;
-                    case 2: v = x < a.cval; break;
-                    case 3: v = x <= a.cval; break;
-                    case 4: v = x > a.cval; break;
-                    default: v = x >= a.cval; break;
-                }
-            } else {
-                uint32_t l = p.iset_off[a.set_id], h = p.iset_off[a.set_id + 1];
-                while (l < h) {
-                    uint32_t m = (l + h) >> 1;
-                    int64_t mv = __ldg(p.iset_vals + m);
-                    if (mv == x) { v = true; break; }
-                    if (mv < x) l = m + 1;
-                    else h = m;
+            if (a.kind == 3) {  // IP_SET
+                v = (set_mask >> a.set_id) & 1u;
+            } else {  // COUNTRY_SET
+                uint32_t c0 = (country & 0xFFu) - 'A', c1 = ((country >> 8) & 0xFFu) - 'A';
+                if (c0 < 26u && c1 < 26u) {
+                    uint32_t bit = c0 * 26u + c1;
+                    v = (__ldg(p.cset + a.set_id * kCountryWords + (bit >> 5)) >> (bit & 31)) & 1u;
                 }
             }
-            if (v && valid) {
-                row[a.atom >> 5] |= 1u << (a.atom & 31);
-                row_dirty = true;
-            }
+            if (v) fn(a.atom);
         }
-    }
-    for (uint32_t i = p.ns_begin[7]; i < p.n_ns; ++i) {
-        const NsAtom a = p.n_ns <= kMaxConstNs ? p.nsd[i] : p.ns[i];
-        bool v = false;
-        if (a.kind == 3) {  // IP_SET
-            v = (set_mask >> a.set_id) & 1u;
-        } else {  // COUNTRY_SET
-            uint32_t c0 = (country & 0xFFu) - 'A', c1 = ((country >> 8) & 0xFFu) - 'A';
-            if (c0 < 26u && c1 < 26u) {
-                uint32_t bit = c0 * 26u + c1;
-                v = (__ldg(p.cset + a.set_id * kCountryWords + (bit >> 5)) >> (bit & 31)) & 1u;
-            }
-        }
-        if (v && valid) {
-            row[a.atom >> 5] |= 1u << (a.atom & 31);
-            row_dirty = true;
-        }
-    }
+    };
+
+    const uint2 inf = *reinterpret_cast<const uint2*>(p.info + 2u * (size_t)r);
+    uint32_t amax = inf.x, binv = inf.y;  // largest true atom + 1 (0: none), 0x4000 - smallest true atom
+    bool had_extra = false;
+    extras([&](uint32_t a) {
+        amax = max(amax, a + 1u);
+        binv = max(binv, 0x4000u - a);
+        had_extra = true;
+    });
+    const bool any_atom = amax != 0u;
+    const bool single = any_atom && (amax - 1u == 0x4000u - binv);
+    const bool multi = any_atom && !single;
+    if (multi && valid && had_extra)  // complete the row (the scan's bits are in it already)
+        extras([&](uint32_t a) { row[a >> 5] |= 1u << (a & 31); });
+    __syncwarp();
 
     const uint32_t cv = flags & RF_CAPTCHA_VERIFIED;
     uint32_t verdict = V_ALLOW | (kNoRule << 2);
@@ -188,19 +248,26 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, u
     }
     if (!decided) {
         bool bypass = flags & RF_BYPASS;
-        if (p.eval_gates && p.gate_atom >= 0 && row_dirty) bypass |= (row[p.gate_atom >> 5] >> (p.gate_atom & 31)) & 1u;
+        if (p.eval_gates && p.gate_atom >= 0) {
+            if (single) bypass |= amax - 1u == (uint32_t)p.gate_atom;
+            else if (multi) bypass |= (row[p.gate_atom >> 5] >> (p.gate_atom & 31)) & 1u;
+        }
         if (bypass) { verdict = V_BYPASS | (kNoRule << 2); decided = true; }
     }
     if (!decided && (flags & RF_PRE_CAPTCHA)) { verdict = V_CAPTCHA | (kNoRule << 2); decided = true; }
 
     const bool routes = p.service != nullptr && p.n_rules > p.n_waf_rules;
     uint32_t svc = kNoService;
-    // no atom of this request is true: constants
-    if (!decided && !row_dirty) { verdict = p.vclean[cv]; svc = p.sclean; decided = true; }
+    if (!decided && !any_atom) { verdict = p.vclean[cv]; svc = p.sclean; decided = true; }
+    if (!decided && single) {
+        verdict = __ldg(p.v1z + cv * p.n_atoms + (amax - 1u));
+        svc = routes ? (uint32_t)__ldg(p.s1z + (amax - 1u)) : kNoService;
+        decided = true;
+    }
 
-    // deviations from the expected atom vector: none -> v0 / s0, exactly one -> v1[atom] / s1[atom], otherwise the
-    // candidate rules (those that mention a deviating atom, plus the ones true by default) are evaluated
-    const bool look = row_dirty && !decided;
+    // several atoms: deviations from the expected atom vector: none -> v0 / s0, exactly one -> v1[atom] / s1[atom],
+    // otherwise the candidate rules (those that mention a deviating atom, plus the ones true by default) are evaluated
+    const bool look = multi && !decided;
     if (__any_sync(FULL, look)) {
         uint32_t ndev = 0, dev_atom = 0, sig = cv;
         if (look)
@@ -268,8 +335,13 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, u
     }
     __syncwarp();  // every lane is done reading rows (the shadow lanes of the last warp read the last request's)
     if (!valid) return;
-    if (row_dirty)
-        for (uint32_t w = 0; w < Aw; ++w) row[w] = 0u;  // scratch goes back all-zero
+    // scratch goes back all-zero: the scan's bits (one word if a single atom fired), the completed row, the info words
+    if (inf.x != 0u) {
+        *reinterpret_cast<uint2*>(p.info + 2u * (size_t)r) = make_uint2(0u, 0u);
+        if (inf.x - 1u == 0x4000u - inf.y) row[(inf.x - 1u) >> 5] = 0u;
+    }
+    if (multi)
+        for (uint32_t w = 0; w < Aw; ++w) row[w] = 0u;
     p.verdict[r] = verdict;
     // http_listener.rs:266-272: only a request the rules let through reaches the services; the first service whose
     // route is absent or true takes it, none => 404 (kNoService)

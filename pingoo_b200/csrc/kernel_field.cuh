@@ -9,7 +9,7 @@
 // request (UM_ALL) or the candidates the gate kernel listed for its field (UM_CANDIDATES).  A lane that finishes --
 // end of the field, or an absorbing DFA state (UnitDesc::abs0/abs1: nothing can change any more) -- takes the next
 // request from a warp pool of 32 claimed entries whose (start, end, request) triples were fetched one pool ahead.
-// Atom bits go to bitmaps in global memory (red.or, rare) together with the request's dirty bit;
+// Atom bits go to bitmaps in global memory (red.or, rare) together with the request's info words;
 // waf_epilogue_kernel turns them into verdicts.
 // =====================================================================================================================
 #ifndef PGW_FS_THREADS
@@ -25,28 +25,9 @@ constexpr uint32_t kFsPoolBytes = 512;  // a claimed pool: 32 field starts, 32 f
 // front of the shared window (mbarrier + skip flag, claim pools, per-lane slots), rounded so that the unit image behind it starts on a 256-byte boundary
 constexpr uint32_t kFsFront = (64u + (kFsThreads / 32) * 2u * kFsPoolBytes + 4u * kFsSlotStride + 255u) & ~255u;
 
-__device__ __forceinline__ void red_or(uint32_t* addr, uint32_t v) { asm volatile("red.global.or.b32 [%0], %1;" ::"l"(addr), "r"(v) : "memory"); }
-
-// events of CSR row `ci` applied to a bitmap in global memory; true if all of them were plain FIREs
-__device__ __forceinline__ bool fs_fire_list(const uint32_t* idx, const uint32_t* events, uint32_t ci, uint32_t* row, uint32_t* latch) {
-    uint32_t a = __ldg(idx + ci), b = __ldg(idx + ci + 1);
-    uint32_t l = *latch;
-    bool pure = true;
-    for (uint32_t i = a; i < b; ++i) {
-        const uint32_t e = __ldg(events + i);
-        const uint32_t kind = e >> kEvKindShift, lb = 1u << ((e >> kEvLatchShift) & 31u), at = e & kEvAtomMask;
-        if (kind == 0u || (kind == 1u && (l & lb))) red_or(row + (at >> 5), 1u << (at & 31));
-        else if (kind == 2u) l &= ~lb;
-        else if (kind == 3u) l |= lb;
-        pure &= kind == 0u;
-    }
-    *latch = l;
-    return pure;
-}
-
 // accept events of four hot states of one word (at least one accepting); returns the new `last`
 __device__ __noinline__ uint32_t fs_events_word(const KParams& p, uint32_t acclo, uint32_t acc_base, uint32_t acc1addr, uint32_t s01, uint32_t s23,
-                                                uint32_t m4, uint32_t last, uint32_t* latch, uint32_t* row) {
+                                                uint32_t m4, uint32_t last, uint32_t* latch, const Sink& row) {
     // positions whose state is accepting
     uint32_t am = m4;
     if ((s01 & 0xFFFFu) < acclo) am &= ~1u;
@@ -61,7 +42,7 @@ __device__ __noinline__ uint32_t fs_events_word(const KParams& p, uint32_t acclo
         if (st == last) continue;
         const uint32_t a1 = lds_u16(acc1addr + 2u * (st - acclo));
         if (a1 != 0xFFFFu) {
-            red_or(row + (a1 >> 5), 1u << (a1 & 31));
+            fire_atom(row, a1);
             last = st;
         } else {
             last = fs_fire_list(p.acc_idx, p.acc_events, acc_base + st - acclo, row, latch) ? st : 0xFFFFFFFFu;
@@ -72,7 +53,7 @@ __device__ __noinline__ uint32_t fs_events_word(const KParams& p, uint32_t acclo
 
 // one word walked on the full table in global memory (a cold state is involved)
 __device__ __noinline__ void fs_slow_word(const KParams& p, uint32_t tbl_off, uint32_t C, uint32_t acclo, uint32_t acc_base, uint32_t clsaddr,
-                                          uint32_t w, uint32_t m4, uint32_t* state, uint32_t* last, uint32_t* latch, uint32_t* row) {
+                                          uint32_t w, uint32_t m4, uint32_t* state, uint32_t* last, uint32_t* latch, const Sink& row) {
     const uint16_t* tbl = reinterpret_cast<const uint16_t*>(p.arena + tbl_off);
     uint32_t st = *state, la = *last;
 #pragma unroll 1
@@ -91,10 +72,7 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
     uint8_t* s_img = smem + ((0u - smem_u32(smem)) & 255u);  // the class map (image offset 0) sits on a 256-byte boundary
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t FULL = 0xFFFFFFFFu;
-    const uint32_t Aw = p.atom_words;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t* const rows = p.rows;
-    uint32_t* const dirty = p.dirty;
 
     // fixed part of the shared window sits in FRONT of the image: mbarrier, pools, slots
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_img);
@@ -115,6 +93,7 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
     for (uint32_t uk = 0; uk < p.n_units; ++uk) {
         const uint32_t u = (uk + blockIdx.x) % p.n_units;
         const UnitDesc& cu = p.udesc[u];   // constant bank, uniform index
+        if (cu.mode == UM_PREPASS) continue;  // walked by the pre-pass kernel
         const bool cand = cu.mode == UM_CANDIDATES;
         const uint32_t N = cand ? __ldg(p.cand_count[cu.field]) : p.n;
         uint32_t* ctr = p.counters + p.unit_base + u;
@@ -287,9 +266,7 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                 const uint32_t mx4 = max(max(sv[0], sv[1]), max(sv[2], sv[3]));
                 if (mx4 >= lim) {
                     if (mx4 >= trap || mx4 >= acclo) {
-                        const uint32_t ridx = lds_u32_v(a_slot);
-                        uint32_t* row = rows + (size_t)ridx * Aw;
-                        red_or(dirty + (ridx >> 5), 1u << (ridx & 31u));  // the epilogue must look at (and re-zero) this row
+                        const Sink row = sink_of(p, lds_u32_v(a_slot));
                         uint32_t t_latch = lds_u32_v(a_slot + kFsSlotStride), t_last = lds_u32_v(a_slot + 2u * kFsSlotStride);
                         if (mx4 >= trap) {
                             uint32_t t_state = state;
@@ -310,7 +287,7 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                                 uint32_t a1 = 0xFFFFu;
                                 if ((am & (am - 1u)) == 0u) a1 = lds_u16(acc1addr + 2u * (st1 - acclo));
                                 if (a1 != 0xFFFFu) {
-                                    if (st1 != t_last) red_or(row + (a1 >> 5), 1u << (a1 & 31));
+                                    if (st1 != t_last) fire_atom(row, a1);
                                     t_last = st1;
                                 } else {
                                     t_last = fs_events_word(p, acclo, cu.acc_base, acc1addr, s01, s23, m4, t_last, &t_latch, row);
@@ -328,15 +305,12 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                 uint32_t e1 = 0xFFFFu;
                 if (state < trap) e1 = lds_u16(end1addr + 2u * state);
                 if (e1 != 0xFFFEu) {
-                    const uint32_t ridx = lds_u32_v(a_slot);
-                    uint32_t* row = rows + (size_t)ridx * Aw;
+                    const Sink row = sink_of(p, lds_u32_v(a_slot));
                     if (e1 != 0xFFFFu) {
-                        red_or(row + (e1 >> 5), 1u << (e1 & 31));
-                        red_or(dirty + (ridx >> 5), 1u << (ridx & 31u));
+                        fire_atom(row, e1);
                     } else if (cu.end_any) {
                         uint32_t t_latch = lds_u32_v(a_slot + kFsSlotStride);
                         fs_fire_list(p.end_idx, p.end_events, cu.end_base + state, row, &t_latch);
-                        red_or(dirty + (ridx >> 5), 1u << (ridx & 31u));
                     }
                 }
                 have = false;
@@ -346,35 +320,12 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
     }
 }
 
-// Verdicts once every unit has been scanned: one thread per request, one warp per word of the dirty bitmap.
-// Empty fields never reach the scan; their end-of-field events (the DFA's start state at end of input) are applied here.
+// Verdicts once every unit has been scanned: one thread per request.
 __global__ void __launch_bounds__(256) waf_epilogue_kernel(const __grid_constant__ KParams p) {
     // warp-uniform trip count: every lane of a warp goes through request_epilogue together
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < p.n; base += gridDim.x * blockDim.x) {
-        const uint32_t lane = threadIdx.x & 31u;
-        const uint32_t rr = base + lane;
+        const uint32_t rr = base + (threadIdx.x & 31u);
         const bool valid = rr < p.n;
-        const uint32_t r = valid ? rr : p.n - 1u;
-        const uint32_t dword = p.dirty[base >> 5];
-        __syncwarp();
-        if (lane == 0 && dword) p.dirty[base >> 5] = 0u;  // scratch goes back all-zero
-        bool row_dirty = valid && ((dword >> lane) & 1u);
-        uint32_t* row = p.rows + (size_t)r * p.atom_words;
-        if (valid)
-            for (uint32_t k = 0; k < p.n_start_end; ++k) {
-                const UnitDesc& ud = p.units[p.start_end_unit[k]];
-                const uint32_t* o = p.off[ud.field] + r;
-                if (o[0] != o[1]) continue;
-                uint32_t a = __ldg(p.end_idx + ud.end_base + ud.start_state), b = __ldg(p.end_idx + ud.end_base + ud.start_state + 1);
-                for (uint32_t i = a; i < b; ++i) {
-                    const uint32_t e = __ldg(p.end_events + i);
-                    if ((e >> kEvKindShift) == 0u) {  // latch kinds cannot fire on an empty field
-                        row[(e & kEvAtomMask) >> 5] |= 1u << (e & 31);
-                        row_dirty = true;
-                    }
-                }
-            }
-        __syncwarp();
-        request_epilogue(p, r, row, valid, row_dirty);
+        request_epilogue(p, valid ? rr : p.n - 1u, valid);
     }
 }

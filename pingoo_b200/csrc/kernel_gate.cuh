@@ -53,7 +53,43 @@ __device__ __noinline__ void gate_mark(uint32_t a_offs, uint32_t a_mask, uint32_
     }
 }
 
-__global__ void __launch_bounds__(kGateThreads, 1) waf_gate_kernel(const __grid_constant__ GateParams gp) {
+// One request's field walked on a small early-exit DFA whose whole table is in shared memory at `img` (class map,
+// rows, acc1, end1: the unit image of compile.hpp): start-anchored patterns are decided within the first few bytes.
+__device__ __noinline__ void prefix_walk(const KParams& p, const UnitDesc& ud, uint32_t img, const uint8_t* __restrict__ col, uint32_t s, uint32_t e,
+                                         uint32_t ridx) {
+    const uint32_t C2 = 2u * ud.n_classes, acclo = ud.acc_lo, abs0 = ud.abs0, abs1 = ud.abs1;
+    const uint32_t hot = img + ud.hot_off;
+    uint32_t st = ud.start_state, latch = 0u;
+    const Sink sink = sink_of(p, ridx);
+    bool done = false;
+    for (uint32_t base = s & ~15u; base < e && !done; base += 16u) {
+        const uint4 c = *reinterpret_cast<const uint4*>(col + base);
+#pragma unroll
+        for (int wi = 0; wi < 4; ++wi) {
+            const uint32_t w = wi == 0 ? c.x : wi == 1 ? c.y : wi == 2 ? c.z : c.w;
+#pragma unroll
+            for (int bi = 0; bi < 4; ++bi) {
+                const uint32_t pos = base + 4u * wi + bi;
+                if (done || pos < s || pos >= e) continue;
+                const uint32_t cls = lds_u8(img + ((w >> (8 * bi)) & 0xFFu));
+                st = lds_u16(hot + st * C2 + 2u * cls);
+                if (st >= acclo) {
+                    const uint32_t a1 = lds_u16(img + ud.acc1_off + 2u * (st - acclo));
+                    if (a1 != 0xFFFFu) fire_atom(sink, a1);
+                    else fs_fire_list(p.acc_idx, p.acc_events, ud.acc_base + st - acclo, sink, &latch);
+                }
+                done = st == abs0 || st == abs1;  // absorbing: nothing can change any more
+            }
+        }
+    }
+    const uint32_t e1 = lds_u16(img + ud.end1_off + 2u * st);
+    if (e1 != 0xFFFEu) {
+        if (e1 != 0xFFFFu) fire_atom(sink, e1);
+        else if (ud.end_any) fs_fire_list(p.end_idx, p.end_events, ud.end_base + st, sink, &latch);
+    }
+}
+
+__global__ void __launch_bounds__(kGateThreads, 1) waf_gate_kernel(const __grid_constant__ GateParams gp, const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) uint8_t gsm[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const uint32_t FULL = 0xFFFFFFFFu;
@@ -61,16 +97,23 @@ __global__ void __launch_bounds__(kGateThreads, 1) waf_gate_kernel(const __grid_
     const uint32_t n = gp.n;
     const uint32_t n_tiles = (n + 31u) / 32u;
     const uint32_t a_offs = smem_u32(gsm) + (tid >> 5) * kGateWarpSmem, a_mask = a_offs + 33u * 4u;
-    uint8_t* const bloom = gsm + (kGateThreads / 32) * kGateWarpSmem;
+    uint8_t* const images = gsm + (kGateThreads / 32) * kGateWarpSmem;  // prefix-unit images (256-byte aligned pieces), then the Bloom bitmap
+    uint8_t* const bloom = images + gp.image_area;
 
     for (uint32_t fi = 0; fi < gp.n_fields; ++fi) {
         const GateField& F = gp.f[fi];
-        const uint32_t words1 = 1u << (F.k1 - 5u);
-        __syncthreads();  // everybody is done with the previous field's bitmap
+        const bool gated = F.b1 != nullptr;
+        const uint32_t words1 = gated ? 1u << (F.k1 - 5u) : 0u;
+        __syncthreads();  // everybody is done with the previous field's tables
         {
             uint4* d1 = reinterpret_cast<uint4*>(bloom);
             const uint4* s1 = reinterpret_cast<const uint4*>(F.b1);
             for (uint32_t i = tid; i < words1 / 4u; i += kGateThreads) d1[i] = __ldg(s1 + i);
+            for (uint32_t k = 0; k < F.n_prefix; ++k) {
+                uint4* di = reinterpret_cast<uint4*>(images + F.prefix_img[k]);
+                const uint4* si = reinterpret_cast<const uint4*>(p.images + F.prefix[k].img_off);
+                for (uint32_t i = tid; i < F.prefix[k].img_bytes / 16u; i += kGateThreads) di[i] = __ldg(si + i);
+            }
         }
         __syncthreads();
         const uint32_t t1 = smem_u32(bloom);
@@ -84,6 +127,7 @@ __global__ void __launch_bounds__(kGateThreads, 1) waf_gate_kernel(const __grid_
             const uint32_t s_l = __ldg(F.off + min(r, n)), e_l = __ldg(F.off + min(r + 1u, n));
             const uint32_t A = __shfl_sync(FULL, s_l, 0), B = __shfl_sync(FULL, e_l, 31);
             if (A == B) continue;  // 32 empty fields
+            if (gated) {
             __syncwarp();
             sts_u32(a_offs + 4u * lane, s_l);
             sts_u32(a_mask + 4u * lane, 0u);
@@ -148,6 +192,10 @@ __global__ void __launch_bounds__(kGateThreads, 1) waf_gate_kernel(const __grid_
                     F.cand_mask[k] = mine;
                 }
             }
+            }
+            // the field's small early-exit units: one lane per request, the bytes are in the cache
+            if (r < n && e_l > s_l)
+                for (uint32_t k = 0; k < F.n_prefix; ++k) prefix_walk(p, F.prefix[k], smem_u32(images) + F.prefix_img[k], col, s_l, e_l, r);
         }
     }
 }

@@ -94,13 +94,15 @@ size_t waf_scan_smem_bytes(uint32_t max_image_bytes) { return 256 + kFsFront + r
 size_t waf_gate_smem_bytes(const GateParams& g) {
     size_t m = 0;
     for (uint32_t i = 0; i < g.n_fields; ++i) {
-        size_t b = ((size_t)1 << g.f[i].k1) / 8;
+        size_t b = g.f[i].b1 ? ((size_t)1 << g.f[i].k1) / 8 : 0;
         if (b > m) m = b;
     }
-    return m + (kGateThreads / 32) * kGateWarpSmem;
+    return m + g.image_area + (kGateThreads / 32) * kGateWarpSmem + 256;
 }
 
-const char* waf_batch_launch(KParams& p, const GateParams& g, const UnitDesc* all_units, uint32_t* small, uint32_t small_words, int sm_count,
+size_t waf_gate_prefix_budget() { return 48u << 10; }
+
+const char* waf_batch_launch(KParams& p, GateParams& g, const UnitDesc* all_units, uint32_t* small, uint32_t small_words, int sm_count,
                              size_t scan_smem, size_t gate_smem, void* stream, cudaEvent_t ev0, cudaEvent_t ev1, uint32_t* launches) {
     if (p.n == 0) return nullptr;
     cudaStream_t s = (cudaStream_t)stream;
@@ -112,7 +114,7 @@ const char* waf_batch_launch(KParams& p, const GateParams& g, const UnitDesc* al
         // tiles of 32 requests, one per warp at a time
         const uint32_t tiles = (p.n + 31u) / 32u, want = (tiles + kGateThreads / 32 - 1) / (kGateThreads / 32);
         const int grid = (int)(want < (uint32_t)sm_count ? want : (uint32_t)sm_count);
-        waf_gate_kernel<<<grid, kGateThreads, gate_smem, s>>>(g);
+        waf_gate_kernel<<<grid, kGateThreads, gate_smem, s>>>(g, p);
         e = cudaGetLastError();
         if (e != cudaSuccess) return cudaGetErrorString(e);
         ++nl;

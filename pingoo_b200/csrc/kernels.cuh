@@ -10,7 +10,8 @@ namespace pgw {
 constexpr uint32_t kMaxConstNs = 16;
 constexpr uint32_t kMaxConstUnits = 64;  // scan units per scan-kernel launch (their descriptors ride in the parameter bank);
                                          // rule sets with more units are scanned by several launches
-constexpr uint32_t kMaxGateFields = 3;   // url, user_agent, path
+constexpr uint32_t kMaxGateFields = 5;   // fields the pre-pass kernel visits (gate bitmaps and / or small early-exit units)
+constexpr uint32_t kMaxPrefixUnits = 2;  // early-exit units of one field walked inside the pre-pass kernel
 
 struct KParams {
     // ---- batch (device pointers, SoA) ----
@@ -26,7 +27,8 @@ struct KParams {
     uint32_t n;
     // ---- per-launch scratch ----
     uint32_t* rows;             // n x atom_words atom bitmaps; all zero between batches (the epilogue re-zeroes what was touched)
-    uint32_t* dirty;            // ceil(n / 32) words: bit r set <=> row r may be non-zero; all zero between batches
+    uint32_t* info;             // 2 words per request, zero between batches: [0] = largest fired atom + 1 (0: none fired),
+                                // [1] = 0x4000 - smallest fired atom; one distinct atom fired <=> [0] - 1 == 0x4000 - [1]
     uint32_t* counters;         // per scan unit: next unclaimed request / candidate (zeroed before each batch)
     const uint32_t* cand_count[5];  // gate candidates of a field (null: the field has no gate)
     const uint32_t* cand_idx[5];
@@ -64,6 +66,8 @@ struct KParams {
     const uint16_t* s1;         // [atom] service in that case
     uint32_t vclean[2];         // verdict of a request whose atom bitmap is all zero
     uint32_t sclean;            // its service
+    const uint32_t* v1z;        // [cv][atom] verdict when exactly that atom is true and every other one false
+    const uint16_t* s1z;        // [atom] service in that case
     // service routes (rules [n_waf_rules, n_rules)); `service` null: not requested for this batch
     uint32_t n_waf_rules;
     uint32_t s0;
@@ -99,7 +103,8 @@ struct KParams {
 struct GateField {
     const uint8_t* col;      // field bytes
     const uint32_t* off;     // n + 1 offsets
-    const uint32_t* b1;      // level 1: blocked Bloom filter (2^k1 bits), global memory copy (staged into shared memory)
+    const uint32_t* b1;      // level 1: blocked Bloom filter (2^k1 bits), global memory copy (staged into shared memory);
+                             // null: the field has no gate (it is visited for its prefix units only)
     const uint32_t* slots;   // level 2: exact table, 2^kt slots of {gram, unit mask}
     uint32_t k1, kt;
     uint32_t* cand_count;    // candidate list of the field: one counter ...
@@ -107,12 +112,18 @@ struct GateField {
     uint32_t* cand_start;
     uint32_t* cand_end;
     uint32_t* cand_mask;
+    // small early-exit units of the field (start-anchored patterns): walked here, one lane per request, right after the
+    // tile's bytes went through the cache, instead of costing a pass of the scan kernel each
+    uint32_t n_prefix;
+    uint32_t prefix_img[kMaxPrefixUnits];   // offset of the unit's image inside the kernel's image area (shared memory)
+    UnitDesc prefix[kMaxPrefixUnits];
 };
 
 struct GateParams {
     GateField f[kMaxGateFields];
     uint32_t n_fields;
     uint32_t n;              // requests
+    uint32_t image_area;     // bytes of shared memory reserved for prefix-unit images (multiple of 256)
 };
 
 // host-callable wrappers (kernels.cu)
@@ -120,10 +131,11 @@ size_t waf_scan_smem_bytes(uint32_t max_image_bytes);
 size_t waf_scan_image_budget(size_t max_smem_optin);  // bytes a unit image may take
 int waf_scan_threads();
 size_t waf_gate_smem_bytes(const GateParams& g);
+size_t waf_gate_prefix_budget();  // shared memory the prefix-unit images of one field may take
 // One batch: [gate] -> scan (one launch per kMaxConstUnits units) -> epilogue, all on `stream`.
 // `all_units` = the program's unit descriptors (host copy); `small` = the block of claim counters and candidate counters
 // to zero first (`small_words` words).  ev0 / ev1 (optional) bracket the gate + scan kernels.
-const char* waf_batch_launch(KParams& p, const GateParams& g, const UnitDesc* all_units, uint32_t* small, uint32_t small_words, int sm_count,
+const char* waf_batch_launch(KParams& p, GateParams& g, const UnitDesc* all_units, uint32_t* small, uint32_t small_words, int sm_count,
                              size_t scan_smem, size_t gate_smem, void* stream, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,
                              uint32_t* launches = nullptr);
 const char* client_id_launch(const uint8_t* ip, const uint8_t* is_v6, const uint8_t* ua_bytes, const uint32_t* ua_off, const uint8_t* host_bytes,

@@ -65,7 +65,8 @@ struct UnitDesc {
 // which requests a scan unit walks
 enum UnitMode : uint32_t {
     UM_ALL = 0,        // every request (patterns the gate cannot cover; start-anchored patterns, which finish early)
-    UM_CANDIDATES = 1  // only the requests the candidate gate flagged for the unit's field
+    UM_CANDIDATES = 1, // only the requests the candidate gate flagged for the unit's field
+    UM_PREPASS = 2     // every request, but inside the pre-pass kernel (small early-exit units; set at finalize, not by the compiler)
 };
 
 // predicates evaluated once per request outside the byte scan

@@ -280,6 +280,13 @@ int pgwsim_evaluate_routed(void* h, const pgw_batch* b, uint32_t* out, uint16_t*
         bool dirty = false;
         for (uint32_t w = 0; w < Aw; ++w) dirty |= row[w] != 0;
         if (!decided && !dirty) { verdict = H.vclean[cv]; decided = true; }  // the epilogue's clean path
+        uint32_t n_true = 0, the_atom = 0;
+        for (uint32_t w = 0; w < Aw; ++w) {
+            if (row[w]) the_atom = w * 32 + (uint32_t)__builtin_ctz(row[w]);
+            n_true += (uint32_t)__builtin_popcount(row[w]);
+        }
+        const bool single_true = n_true == 1;
+        if (!decided && single_true) { verdict = H.v1z[(size_t)cv * H.n_atoms + the_atom]; decided = true; }  // the single-atom table
         if (!decided) {
             uint32_t diff = 0, ndev = 0, dev_atom = 0;
             for (uint32_t w = 0; w < Aw; ++w) {
@@ -319,6 +326,7 @@ int pgwsim_evaluate_routed(void* h, const pgw_batch* b, uint32_t* out, uint16_t*
         if (svc_out) {
             uint32_t svc = kNoService;
             if ((verdict & 3u) == V_ALLOW && H.n_rules > H.n_waf_rules && !dirty) svc = H.sclean;
+            else if ((verdict & 3u) == V_ALLOW && H.n_rules > H.n_waf_rules && single_true) svc = H.s1z[the_atom];
             else if ((verdict & 3u) == V_ALLOW && H.n_rules > H.n_waf_rules) {
                 uint32_t diff = 0;
                 for (uint32_t w = 0; w < Aw; ++w) diff |= (row[w] ^ H.expect[w]) & H.care[w];
@@ -446,4 +454,26 @@ extern "C" int pgwsim_bank_stats(void* h, const pgw_batch* b, uint32_t unit, uin
     out[2] = lane_steps;
     out[3] = distinct;
     return 0;
+}
+
+// debug: level-1 pass rate of the gate of field `f` over every even-aligned window of the column
+// out[0] = windows, out[1] = level-1 passes, out[2] = exact-table hits
+extern "C" void pgwsim_gate_window_stats(void* h, const pgw_batch* b, int f, uint64_t* out) {
+    Sim* s = (Sim*)h;
+    const GateTables& G = s->H.gate[f];
+    const pgw_strcol* cols[5] = {&b->host, &b->url, &b->path, &b->method, &b->user_agent};
+    out[0] = out[1] = out[2] = 0;
+    if (!G.present) return;
+    const uint32_t total = cols[f]->offsets[b->n];
+    for (uint32_t j = 0; j + 4 <= total; j += 2) {
+        uint32_t w;
+        memcpy(&w, cols[f]->bytes + j, 4);
+        const uint32_t g = gate_fold(w), hh = g * kGateHash1, sh = 32 - G.k1;
+        const uint32_t word = G.b1[hh >> (sh + 5)];
+        out[0]++;
+        if ((word >> ((hh >> sh) & 31)) & (word >> ((hh >> (sh - 5)) & 31)) & 1u) {
+            out[1]++;
+            if (G.probe(w)) out[2]++;
+        }
+    }
 }
