@@ -86,7 +86,8 @@ struct Scratch {
     // carved out of `base`
     uint32_t* rows = nullptr;
     uint32_t* info = nullptr;
-    uint32_t* small = nullptr;       // [0, kSmallCounters): per-unit claim counters; [kSmallCounters, +5): candidate counters
+    uint32_t* small = nullptr;       // [0, kSmallCounters): per-unit claim counters; [kSmallCounters, +5): candidate counters; [+5]: multi count
+    uint32_t* multi = nullptr;       // multi list (request indices)
     uint32_t* cand[5][4] = {};       // per gated field: idx, start, end, unit mask
 };
 constexpr uint32_t kSmallCounters = 1024;   // scan units a program may have
@@ -159,7 +160,7 @@ Scratch* scratch_acquire(pgw_ruleset* rs, uint32_t n, cudaStream_t stream, std::
     cap = (cap + 31) & ~(size_t)31;
     size_t n_gated = 0;
     for (int f = 0; f < 5; ++f) n_gated += H.gate[f].present ? 1 : 0;
-    const size_t rows_b = cap * H.atom_words * 4, dirty_b = cap * 8 + 64, small_b = kSmallWords * 4, cand_b = n_gated * 4 * cap * 4;
+    const size_t rows_b = cap * H.atom_words * 4, dirty_b = cap * 8 + 64, small_b = kSmallWords * 4, cand_b = (n_gated * 4 + 1) * cap * 4;
     const size_t total = rows_b + dirty_b + small_b + cand_b + 1024;
     if (cudaMalloc((void**)&sc->base, total) != cudaSuccess || cudaEventCreateWithFlags(&sc->done, cudaEventDisableTiming) != cudaSuccess) {
         e = std::string("CUDA: scratch allocation failed (") + std::to_string(total >> 20) + " MiB): " + cudaGetErrorString(cudaGetLastError());
@@ -173,6 +174,7 @@ Scratch* scratch_acquire(pgw_ruleset* rs, uint32_t n, cudaStream_t stream, std::
     sc->rows = (uint32_t*)q; q += rows_b;
     sc->info = (uint32_t*)q; q += dirty_b;
     sc->small = (uint32_t*)q; q += small_b;
+    sc->multi = (uint32_t*)q; q += cap * 4;
     for (int f = 0; f < 5; ++f)
         if (H.gate[f].present)
             for (int k = 0; k < 4; ++k) { sc->cand[f][k] = (uint32_t*)q; q += cap * 4; }
@@ -439,6 +441,8 @@ static int launch_on(pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdict_out,
     P.rows = sc->rows;
     P.info = sc->info;
     P.counters = sc->small;
+    P.multi_count = sc->small + kSmallCounters + 5;
+    P.multi_list = sc->multi;
     GateParams G = rs->gate_base;
     G.n = b->n;
     for (uint32_t i = 0; i < G.n_fields; ++i) {

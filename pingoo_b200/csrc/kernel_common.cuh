@@ -126,6 +126,7 @@ __device__ __forceinline__ uint32_t lpm_lookup(const KParams& p, const uint8_t* 
 //   otherwise               -> the row is completed and the candidate rules are evaluated; requests of the warp that
 //                              deviate from the expected atom vector in the same way are evaluated once (verdict and
 //                              service are functions of the deviation and of `captcha_verified` alone), shared by shuffle.
+//   otherwise               -> the row is completed and the request is appended to the multi list (waf_multi_kernel)
 // Whatever the scan or this function wrote to the row / info words is written back to zero (the scratch invariant).
 __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, bool valid) {
     const uint32_t Aw = p.atom_words;
@@ -234,7 +235,6 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, b
     const bool multi = any_atom && !single;
     if (multi && valid && had_extra)  // complete the row (the scan's bits are in it already)
         extras([&](uint32_t a) { row[a >> 5] |= 1u << (a & 31); });
-    __syncwarp();
 
     const uint32_t cv = flags & RF_CAPTCHA_VERIFIED;
     uint32_t verdict = V_ALLOW | (kNoRule << 2);
@@ -264,88 +264,106 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, b
         svc = routes ? (uint32_t)__ldg(p.s1z + (amax - 1u)) : kNoService;
         decided = true;
     }
-
-    // several atoms: deviations from the expected atom vector: none -> v0 / s0, exactly one -> v1[atom] / s1[atom],
-    // otherwise the candidate rules (those that mention a deviating atom, plus the ones true by default) are evaluated
-    const bool look = multi && !decided;
-    if (__any_sync(FULL, look)) {
-        uint32_t ndev = 0, dev_atom = 0, sig = cv;
-        if (look)
-            for (uint32_t w = 0; w < Aw; ++w) {
-                const uint32_t x = (row[w] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
-                if (x) dev_atom = w * 32u + (uint32_t)__ffs(x) - 1u;
-                ndev += (uint32_t)__popc(x);
-                sig = sig * 0x9E3779B1u + x;
-            }
-        if (look) {
-            if (ndev == 0u) { verdict = p.v0[cv]; svc = p.s0; }
-            else if (ndev == 1u) { verdict = __ldg(p.v1 + cv * p.n_atoms + dev_atom); svc = routes ? (uint32_t)__ldg(p.s1 + dev_atom) : kNoService; }
-        }
-        const bool need_eval = look && ndev >= 2u;
-        if (__any_sync(FULL, need_eval)) {
-            const uint32_t lane = threadIdx.x & 31u;
-            const uint32_t peers = __match_any_sync(FULL, need_eval ? (sig & 0x7FFFFFFFu) : (0x80000000u | lane));
-            const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
-            bool same = true;  // equal signature: confirm that the deviation really is the leader's
-            for (uint32_t w = 0; w < Aw; ++w) {
-                const uint32_t x = need_eval ? (row[w] ^ __ldg(p.expect + w)) & __ldg(p.care + w) : 0u;
-                same &= __shfl_sync(FULL, x, leader) == x;
-            }
-            same &= __shfl_sync(FULL, cv, leader) == cv;
-            const bool do_eval = need_eval && (leader == lane || !same);
-            if (do_eval) {
-                const uint32_t tshift = 2 * cv;
-                uint32_t best = kNoRule, best_svc = kNoRule;
-                for (uint32_t w = 0; w < Aw; ++w) {
-                    uint32_t x = (row[w] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
-                    while (x) {
-                        uint32_t b = __ffs(x) - 1;
-                        x &= x - 1;
-                        uint32_t atom = w * 32 + b;
-                        uint32_t i0 = __ldg(p.ar_idx + atom), i1 = __ldg(p.ar_idx + atom + 1);
-                        for (uint32_t i = i0; i < i1; ++i) {
-                            uint32_t rule = __ldg(p.ar_rules + i);  // ascending; WAF rules first, then service routes
-                            if (rule < p.n_waf_rules) {
-                                if (rule >= best || ((__ldg(p.term + rule) >> tshift) & 3u) == 0) continue;
-                                if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row)) best = rule;
-                            } else {
-                                if (!routes || rule >= best_svc) break;
-                                if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row)) best_svc = rule;
-                            }
-                        }
-                    }
-                }
-                for (uint32_t i = 0; i < p.n_dflt[cv]; ++i) {
-                    uint32_t rule = __ldg(p.dflt[cv] + i);
-                    if (rule >= best) break;
-                    if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row)) best = rule;
-                }
-                if (routes)
-                    for (uint32_t i = 0; i < p.n_dflt_services; ++i) {
-                        uint32_t rule = __ldg(p.dflt_services + i);
-                        if (rule >= best_svc) break;
-                        if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row)) best_svc = rule;
-                    }
-                verdict = best == kNoRule ? (V_ALLOW | (kNoRule << 2)) : (((__ldg(p.term + best) >> tshift) & 3u) | (best << 2));
-                svc = best_svc == kNoRule ? kNoService : best_svc - p.n_waf_rules;
-            }
-            const uint32_t lv = __shfl_sync(FULL, verdict, leader), ls = __shfl_sync(FULL, svc, leader);
-            if (need_eval && same) { verdict = lv; svc = ls; }
-        }
+    // several atoms and no gate decided: the request goes to the multi list (one ballot + one atomicAdd per warp)
+    const bool to_list = valid && !decided;
+    const uint32_t lm = __ballot_sync(FULL, to_list);
+    if (lm) {
+        const uint32_t lane = threadIdx.x & 31u;
+        uint32_t base = 0;
+        if (lane == (uint32_t)__ffs(lm) - 1u) base = atomicAdd(p.multi_count, (uint32_t)__popc(lm));
+        base = __shfl_sync(FULL, base, __ffs(lm) - 1);
+        if (to_list) p.multi_list[base + (uint32_t)__popc(lm & ((1u << lane) - 1u))] = r;
     }
-    __syncwarp();  // every lane is done reading rows (the shadow lanes of the last warp read the last request's)
     if (!valid) return;
-    // scratch goes back all-zero: the scan's bits (one word if a single atom fired), the completed row, the info words
+    // scratch goes back all-zero: the info words, the scan's bit if a single atom fired, a completed row that is not
+    // handed to the multi kernel (which zeroes the rows it evaluates)
     if (inf.x != 0u) {
         *reinterpret_cast<uint2*>(p.info + 2u * (size_t)r) = make_uint2(0u, 0u);
-        if (inf.x - 1u == 0x4000u - inf.y) row[(inf.x - 1u) >> 5] = 0u;
+        if (inf.x - 1u == 0x4000u - inf.y && !to_list) row[(inf.x - 1u) >> 5] = 0u;
     }
-    if (multi)
+    if (multi && !to_list)
         for (uint32_t w = 0; w < Aw; ++w) row[w] = 0u;
+    if (to_list) return;
     p.verdict[r] = verdict;
     // http_listener.rs:266-272: only a request the rules let through reaches the services; the first service whose
     // route is absent or true takes it, none => 404 (kNoService)
     if (p.service) p.service[r] = (uint16_t)(((verdict & 3u) == V_ALLOW && routes) ? svc : kNoService);
+}
+
+// A request with several true atoms, evaluated by one WARP: lane w holds word w of the bitmap row (strided when the row
+// has more than 32 words), the row is staged in shared memory for the rule bytecode, candidate rules are evaluated one
+// per lane.  Deviations from the expected atom vector: none -> v0 / s0, exactly one -> v1[atom] / s1[atom], otherwise
+// the rules that mention a deviating atom plus the ones true by default, first terminal one wins (http_listener.rs:251-264).
+__device__ __forceinline__ void request_multi_warp(const KParams& p, uint32_t r, uint32_t* srow) {
+    const uint32_t Aw = p.atom_words, lane = threadIdx.x & 31u;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    uint32_t* const row = p.rows + (size_t)r * Aw;
+    const uint32_t flags = p.flags ? p.flags[r] : 0u;
+    const uint32_t cv = flags & RF_CAPTCHA_VERIFIED, tshift = 2u * cv;
+    const bool routes = p.service != nullptr && p.n_rules > p.n_waf_rules;
+    uint32_t ndev = 0, dev_atom = 0;
+    __syncwarp();
+    for (uint32_t w = lane; w < Aw; w += 32u) {
+        const uint32_t v = row[w];
+        srow[w] = v;
+        row[w] = 0u;  // scratch goes back all-zero
+        const uint32_t x = (v ^ __ldg(p.expect + w)) & __ldg(p.care + w);
+        if (x) dev_atom = w * 32u + (uint32_t)__ffs(x) - 1u;
+        ndev += (uint32_t)__popc(x);
+    }
+    __syncwarp();
+    for (int o = 16; o; o >>= 1) {
+        ndev += __shfl_xor_sync(FULL, ndev, o);
+        dev_atom = max(dev_atom, __shfl_xor_sync(FULL, dev_atom, o));  // meaningful when exactly one bit deviates
+    }
+    uint32_t verdict, svc;
+    if (ndev == 0u) { verdict = p.v0[cv]; svc = p.s0; }
+    else if (ndev == 1u) { verdict = __ldg(p.v1 + cv * p.n_atoms + dev_atom); svc = routes ? (uint32_t)__ldg(p.s1 + dev_atom) : kNoService; }
+    else {
+        uint32_t best = kNoRule, best_svc = kNoRule;
+        // rules that mention a deviating atom: every lane walks the atoms of its own words
+        for (uint32_t w = lane; w < Aw; w += 32u) {
+            uint32_t x = (srow[w] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
+            while (x) {
+                const uint32_t b = __ffs(x) - 1;
+                x &= x - 1;
+                const uint32_t atom = w * 32 + b;
+                const uint32_t i0 = __ldg(p.ar_idx + atom), i1 = __ldg(p.ar_idx + atom + 1);
+                for (uint32_t i = i0; i < i1; ++i) {
+                    const uint32_t rule = __ldg(p.ar_rules + i);  // ascending; WAF rules first, then service routes
+                    if (rule < p.n_waf_rules) {
+                        if (rule >= best || ((__ldg(p.term + rule) >> tshift) & 3u) == 0) continue;
+                        if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), srow)) best = rule;
+                    } else {
+                        if (!routes || rule >= best_svc) break;
+                        if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), srow)) best_svc = rule;
+                    }
+                }
+            }
+        }
+        // rules true by default (ascending): one per lane
+        for (uint32_t i = lane; i < p.n_dflt[cv]; i += 32u) {
+            const uint32_t rule = __ldg(p.dflt[cv] + i);
+            if (rule >= best) break;
+            if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), srow)) best = min(best, rule);
+        }
+        if (routes)
+            for (uint32_t i = lane; i < p.n_dflt_services; i += 32u) {
+                const uint32_t rule = __ldg(p.dflt_services + i);
+                if (rule >= best_svc) break;
+                if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), srow)) best_svc = min(best_svc, rule);
+            }
+        for (int o = 16; o; o >>= 1) {
+            best = min(best, __shfl_xor_sync(FULL, best, o));
+            best_svc = min(best_svc, __shfl_xor_sync(FULL, best_svc, o));
+        }
+        verdict = best == kNoRule ? (V_ALLOW | (kNoRule << 2)) : (((__ldg(p.term + best) >> tshift) & 3u) | (best << 2));
+        svc = best_svc == kNoRule ? kNoService : best_svc - p.n_waf_rules;
+    }
+    if (lane == 0) {
+        p.verdict[r] = verdict;
+        if (p.service) p.service[r] = (uint16_t)(((verdict & 3u) == V_ALLOW && routes) ? svc : kNoService);
+    }
 }
 
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {

@@ -61,26 +61,17 @@ __device__ __noinline__ void prefix_walk(const KParams& p, const UnitDesc& ud, u
     const uint32_t hot = img + ud.hot_off;
     uint32_t st = ud.start_state, latch = 0u;
     const Sink sink = sink_of(p, ridx);
-    bool done = false;
-    for (uint32_t base = s & ~15u; base < e && !done; base += 16u) {
-        const uint4 c = *reinterpret_cast<const uint4*>(col + base);
-#pragma unroll
-        for (int wi = 0; wi < 4; ++wi) {
-            const uint32_t w = wi == 0 ? c.x : wi == 1 ? c.y : wi == 2 ? c.z : c.w;
-#pragma unroll
-            for (int bi = 0; bi < 4; ++bi) {
-                const uint32_t pos = base + 4u * wi + bi;
-                if (done || pos < s || pos >= e) continue;
-                const uint32_t cls = lds_u8(img + ((w >> (8 * bi)) & 0xFFu));
-                st = lds_u16(hot + st * C2 + 2u * cls);
-                if (st >= acclo) {
-                    const uint32_t a1 = lds_u16(img + ud.acc1_off + 2u * (st - acclo));
-                    if (a1 != 0xFFFFu) fire_atom(sink, a1);
-                    else fs_fire_list(p.acc_idx, p.acc_events, ud.acc_base + st - acclo, sink, &latch);
-                }
-                done = st == abs0 || st == abs1;  // absorbing: nothing can change any more
-            }
+    // start-anchored patterns die (or are decided) within a few bytes: a plain byte loop that stops at an absorbing state
+#pragma unroll 1
+    for (uint32_t pos = s; pos < e; ++pos) {
+        const uint32_t cls = lds_u8(img + (uint32_t)__ldg(col + pos));
+        st = lds_u16(hot + st * C2 + 2u * cls);
+        if (st >= acclo) {
+            const uint32_t a1 = lds_u16(img + ud.acc1_off + 2u * (st - acclo));
+            if (a1 != 0xFFFFu) fire_atom(sink, a1);
+            else fs_fire_list(p.acc_idx, p.acc_events, ud.acc_base + st - acclo, sink, &latch);
         }
+        if (st == abs0 || st == abs1) break;  // absorbing: nothing can change any more
     }
     const uint32_t e1 = lds_u16(img + ud.end1_off + 2u * st);
     if (e1 != 0xFFFEu) {

@@ -29,6 +29,8 @@ struct KParams {
     uint32_t* rows;             // n x atom_words atom bitmaps; all zero between batches (the epilogue re-zeroes what was touched)
     uint32_t* info;             // 2 words per request, zero between batches: [0] = largest fired atom + 1 (0: none fired),
                                 // [1] = 0x4000 - smallest fired atom; one distinct atom fired <=> [0] - 1 == 0x4000 - [1]
+    uint32_t* multi_count;      // requests with several true atoms: list filled by the epilogue, evaluated by waf_multi_kernel
+    uint32_t* multi_list;
     uint32_t* counters;         // per scan unit: next unclaimed request / candidate (zeroed before each batch)
     const uint32_t* cand_count[5];  // gate candidates of a field (null: the field has no gate)
     const uint32_t* cand_idx[5];
