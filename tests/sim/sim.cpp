@@ -23,6 +23,7 @@ struct Sim {
     bool finalized = false;
     std::string last_error;
     uint64_t* stats = nullptr;  // optional: per field {requests gated, candidates}
+    uint64_t* atom_hist = nullptr;
 };
 
 int fail(Sim* s, const std::string& m, char* err, size_t cap) {
@@ -286,6 +287,7 @@ int pgwsim_evaluate_routed(void* h, const pgw_batch* b, uint32_t* out, uint16_t*
             n_true += (uint32_t)__builtin_popcount(row[w]);
         }
         const bool single_true = n_true == 1;
+        if (s->atom_hist) s->atom_hist[n_true < 3 ? n_true : 3]++;
         if (!decided && single_true) { verdict = H.v1z[(size_t)cv * H.n_atoms + the_atom]; decided = true; }  // the single-atom table
         if (!decided) {
             uint32_t diff = 0, ndev = 0, dev_atom = 0;
@@ -477,3 +479,6 @@ extern "C" void pgwsim_gate_window_stats(void* h, const pgw_batch* b, int f, uin
         }
     }
 }
+
+// debug: histogram of the number of true atoms per request (out[0..3] = 0, 1, 2, >=3) -- sizes the epilogue's paths
+extern "C" void pgwsim_set_atom_hist(void* h, uint64_t* out4) { ((Sim*)h)->atom_hist = out4; }
