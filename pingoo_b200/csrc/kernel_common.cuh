@@ -294,8 +294,6 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, b
 // has more than 32 words), the row is staged in shared memory for the rule bytecode, candidate rules are evaluated one
 // per lane.  Deviations from the expected atom vector: none -> v0 / s0, exactly one -> v1[atom] / s1[atom], otherwise
 // the rules that mention a deviating atom plus the ones true by default, first terminal one wins (http_listener.rs:251-264).
-constexpr uint32_t kMultiCands = 255;  // candidate rules gathered per request (with the row and a counter: one shared-memory slice per warp)
-
 __device__ __forceinline__ void request_multi_warp(const KParams& p, uint32_t r, uint32_t* srow) {
     const uint32_t Aw = p.atom_words, lane = threadIdx.x & 31u;
     const uint32_t FULL = 0xFFFFFFFFu;
@@ -323,61 +321,32 @@ __device__ __forceinline__ void request_multi_warp(const KParams& p, uint32_t r,
     else if (ndev == 1u) { verdict = __ldg(p.v1 + cv * p.n_atoms + dev_atom); svc = routes ? (uint32_t)__ldg(p.s1 + dev_atom) : kNoService; }
     else {
         uint32_t best = kNoRule, best_svc = kNoRule;
-        // rules that mention a deviating atom: the (atom -> rules) lists are gathered into a warp-shared candidate list,
-        // then evaluated one rule per lane
-        uint32_t* const cnt = srow + Aw;          // [0] = number of candidates
-        uint32_t* const cands = srow + Aw + 1;    // kMultiCands entries
-        if (lane == 0) *cnt = 0u;
-        __syncwarp();
-        bool overflow = false;
-        for (uint32_t w = lane; w < Aw; w += 32u) {
-            uint32_t x = (srow[w] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
-            while (x) {
-                const uint32_t b = __ffs(x) - 1;
-                x &= x - 1;
-                const uint32_t atom = w * 32 + b;
-                const uint32_t i0 = __ldg(p.ar_idx + atom), i1 = __ldg(p.ar_idx + atom + 1);
-                const uint32_t at = atomicAdd(cnt, i1 - i0);
-                if (at + (i1 - i0) > kMultiCands) { overflow = true; continue; }
-                for (uint32_t i = i0; i < i1; ++i) cands[at + i - i0] = __ldg(p.ar_rules + i);
-            }
-        }
-        overflow = __any_sync(FULL, overflow);
-        __syncwarp();
-        if (!overflow) {
-            const uint32_t nc = *cnt;
-            for (uint32_t k = lane; k < nc; k += 32u) {
-                const uint32_t rule = cands[k];
-                if (rule < p.n_waf_rules) {
-                    if (((__ldg(p.term + rule) >> tshift) & 3u) == 0) continue;
-                    if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), srow)) best = min(best, rule);
-                } else if (routes) {
-                    if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), srow)) best_svc = min(best_svc, rule);
-                }
-            }
-        } else {
-            // more candidate rules than the list holds (pathological): every lane walks the atoms of its own words
-            for (uint32_t w = lane; w < Aw; w += 32u) {
-                uint32_t x = (srow[w] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
+        // rules that mention a deviating atom: the deviating atoms are visited in a warp-uniform loop (word by word through a
+        // ballot, bit by bit), each atom's rule list is evaluated one rule per lane
+        for (uint32_t w0 = 0; w0 < Aw; w0 += 32u) {
+            const uint32_t w = w0 + lane;
+            const uint32_t xw = w < Aw ? (srow[w] ^ __ldg(p.expect + w)) & __ldg(p.care + w) : 0u;
+            uint32_t wm = __ballot_sync(FULL, xw != 0u);
+            while (wm) {
+                const uint32_t src = __ffs(wm) - 1;
+                wm &= wm - 1;
+                uint32_t x = __shfl_sync(FULL, xw, src);
                 while (x) {
-                    const uint32_t b = __ffs(x) - 1;
+                    const uint32_t atom = (w0 + src) * 32u + (uint32_t)__ffs(x) - 1u;
                     x &= x - 1;
-                    const uint32_t atom = w * 32 + b;
                     const uint32_t i0 = __ldg(p.ar_idx + atom), i1 = __ldg(p.ar_idx + atom + 1);
-                    for (uint32_t i = i0; i < i1; ++i) {
-                        const uint32_t rule = __ldg(p.ar_rules + i);  // ascending; WAF rules first, then service routes
+                    for (uint32_t i = i0 + lane; i < i1; i += 32u) {
+                        const uint32_t rule = __ldg(p.ar_rules + i);  // WAF rules first, then service routes
                         if (rule < p.n_waf_rules) {
                             if (rule >= best || ((__ldg(p.term + rule) >> tshift) & 3u) == 0) continue;
                             if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), srow)) best = rule;
-                        } else {
-                            if (!routes || rule >= best_svc) break;
+                        } else if (routes && rule < best_svc) {
                             if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), srow)) best_svc = rule;
                         }
                     }
                 }
             }
         }
-        __syncwarp();
         // rules true by default (ascending): one per lane
         for (uint32_t i = lane; i < p.n_dflt[cv]; i += 32u) {
             const uint32_t rule = __ldg(p.dflt[cv] + i);

@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(256) waf_epilogue_kernel(const __grid_constant
 // Requests with several true atoms (the multi list of the epilogue): one warp per request.
 __global__ void __launch_bounds__(256) waf_multi_kernel(const __grid_constant__ KParams p) {
     extern __shared__ uint32_t s_rows[];
-    uint32_t* srow = s_rows + (threadIdx.x >> 5) * (p.atom_words + 1u + kMultiCands);
+    uint32_t* srow = s_rows + (threadIdx.x >> 5) * p.atom_words;
     const uint32_t count = *p.multi_count;
     const uint32_t warps = gridDim.x * (blockDim.x >> 5), w0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     for (uint32_t i = w0; i < count; i += warps) request_multi_warp(p, p.multi_list[i], srow);

@@ -139,8 +139,8 @@ const char* waf_batch_launch(KParams& p, GateParams& g, const UnitDesc* all_unit
     ++nl;
     {
         // at most a few per cent of the requests; sized for the machine, the kernel reads the count from device memory
-        const int mb = sm_count * 4;
-        waf_multi_kernel<<<mb, 256, 8 * ((size_t)p.atom_words + 256) * 4, s>>>(p);
+        const int mb = sm_count * 8;
+        waf_multi_kernel<<<mb, 256, 8 * (size_t)p.atom_words * 4, s>>>(p);
         e = cudaGetLastError();
         if (e != cudaSuccess) return cudaGetErrorString(e);
         ++nl;
