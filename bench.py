@@ -1,13 +1,16 @@
 #!/usr/bin/env python
-"""Headline benchmark: WAF verdicts/sec on the BASELINE.json workload.
+"""Headline benchmark: WAF verdicts/sec on the BASELINE.json workloads.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5]
 
-A step = one pass of the fused verdict kernel over one batch of synthetic requests
-(config 2 by default: 1M requests x 128 OWASP-style rules per GPU).
-`value` is measured with the batch resident in HBM (inputs ~0.4 GB > 126 MB L2, so no L2
-flush is needed between iterations); `e2e` goes through the host-pointer C-ABI call with
-pinned host buffers, H2D/D2H copies inside the timed region.
+A step = one pass of the verdict path (pre-pass / candidate-gate kernel, DFA scan, epilogue) over one batch of
+synthetic requests.  Default workload: N = 1 -> BASELINE config 3 (10M requests x 512 rules + 100k-entry IP/CIDR
+blocklist + 500k-network GeoIP database resolved on the device), the largest single-GPU configuration; N > 1 ->
+the config-4 shard (12.5M requests x 1024 rules per GPU, weak scaling).  The N = 1 line also carries a nested
+`configs` block with config 2 (1M x 128) and the config-4 shard at N = 1.
+`value` is measured with the batch resident in HBM (inputs of several GB >> 126 MB L2, so no L2 flush is needed
+between iterations); `e2e` goes through the host-pointer C-ABI call with pinned host buffers, H2D/D2H copies inside
+the timed region.
 """
 import argparse
 import json
@@ -56,7 +59,7 @@ def build_workload(cfg_id, rank, n_override=None):
         csv, members = synth.make_blocklist(100_000, config_id=cfg_id)
         lists["blocked_ips"] = (ListType.Ip, csv)
         lists["bad_asns"] = (ListType.Int, ("\n".join(str(64512 + 13 * i) for i in range(2000)) + "\n").encode())
-        mmdb, _ = synth.make_geoip(20_000, config_id=cfg_id)
+        mmdb, _ = synth.make_geoip_large(500_000, config_id=cfg_id)  # ~500 k networks
     stream = synth.RequestStream(config_id=cfg_id, payloads=payloads, blocklist_ips=members, long_url_bytes=long_url)
     # a column is limited to 4 GiB of bytes: generate in chunks and keep them as separate batches
     chunk = n if not long_url else min(n, 250_000)
@@ -213,64 +216,26 @@ def cpu_baseline_run(rules, lists, mmdb, batch, sample, threads, repeats=1):
     return sub.n / best, sub.n, out
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
-    ap.add_argument("--requests", type=int, default=0, help="override requests per GPU (debug)")
-    ap.add_argument("--cpu-sample", type=int, default=200_000)
-    args = ap.parse_args()
+def traffic_for(cfg_id, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture of this workload (profiles/latest_traffic.json),
+    or None when no capture of this configuration has been committed."""
+    tpath = os.path.join(ROOT, "profiles", "latest_traffic.json")
+    if not os.path.exists(tpath):
+        return None
+    with open(tpath) as f:
+        tj = json.load(f)
+    e = tj.get(f"config {cfg_id}", {}).get(kernel)
+    return e["dram_bytes_per_launch"] if e else None
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    ncores = os.cpu_count() or 1
-    metric = "WAF verdicts/sec"
-    unit = "M req/s"
 
-    if args.impl == "reference":
-        # The reference's own CPU path cannot be built here (no Rust toolchain; bel/regex/maxminddb crates are not vendored):
-        # this arm times the C restatement of its semantics (oracle/) on all host cores.  Rank 0 only.
-        if rank != 0:
-            return
-        desc, rules, lists, mmdb, batches = build_workload(args.config, 0, args.requests or args.cpu_sample)
-        vals = []
-        for i in range(args.warmup + args.steps):
-            v, n_s, _ = cpu_baseline_run(rules, lists, mmdb, batches[0], args.cpu_sample, ncores)
-            if i >= args.warmup:
-                vals.append(v)
-            if i == 0 and n_s / v > 20:  # keep the whole arm within minutes
-                args.steps = min(args.steps, 3)
-                if i + 1 >= args.warmup + args.steps:
-                    vals = vals or [v]
-                    break
-        v = statistics.median(vals) / 1e6
-        sample = f"{min(args.cpu_sample, batches[0].n)} requests of config {args.config} per step"
-        print(json.dumps({
-            "impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
-            "ms_per_step": 1e3 * min(args.cpu_sample, batches[0].n) / (v * 1e6), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"config {args.config}: {CONFIGS[args.config][0]}", "requests_per_gpu": args.requests or CONFIGS[args.config][1],
-                       "rules": len(rules), "parallelism": f"dp{args.gpus}", "sample": sample},
-            "cpu_baseline": {"value": v, "unit": unit, "cores": ncores, "kind": "port", "sample": sample},
-            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
-        }))
-        return
-
+def run_config(cfg_id, args, rank, local_rank, world, dist, steps, with_e2e=True, with_cpu=True, sustain_s=0.0, n_override=None):
+    """Time one BASELINE configuration on this rank's GPU; returns the JSON fields (rank 0) or None (other ranks)."""
     import torch
-    import torch.distributed as dist
 
     from pingoo_b200 import WafEngine
 
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    desc, rules, lists, mmdb, batches = build_workload(args.config, rank, args.requests or None)
+    ncores = os.cpu_count() or 1
+    desc, rules, lists, mmdb, batches = build_workload(cfg_id, rank, n_override)
     eng = WafEngine(rules, lists, mmdb, device=local_rank)
     info = eng.info()
     n_local = sum(b.n for b in batches)
@@ -290,89 +255,202 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step()
     sync_all()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = eng.info().kernel_launches
-    eng.set_profiling(True)   # CUDA events around every scan-kernel launch of the timed region (ring of the 256 most recent)
+    eng.set_profiling(True)   # CUDA events around every kernel group of the timed region (ring of the 256 most recent batches)
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     ev1.record()
     sync_all()
     ms = ev0.elapsed_time(ev1)
     launches = eng.info().kernel_launches - launches0
-    scan_ms_sum, scan_launches = eng.profile()
+    kms, kbatches = eng.profile_kernels()
     eng.set_profiling(False)
     clocks = sampler.stop() if sampler else None
     t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_max = float(t_ms.item())
-    value = world * n_local * args.steps / (ms_max / 1e3) / 1e6
+    value = world * n_local * steps / (ms_max / 1e3) / 1e6
+
+    # ---- a sustained run (>= sustain_s seconds of back-to-back steps) with clocks sampled throughout ----
+    sustained = None
+    if sustain_s > 0:
+        sampler2 = ClockSampler(local_rank) if rank == 0 else None
+        reps = max(steps, int(sustain_s * 1e3 / max(ms / steps, 1e-3)) + 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        for _ in range(reps):
+            step()
+        e1.record()
+        sync_all()
+        sms = e0.elapsed_time(e1)
+        c2 = sampler2.stop() if sampler2 else None
+        sustained = {"seconds": sms / 1e3, "steps": reps, "value": n_local * reps / (sms / 1e3) / 1e6, "unit": "M req/s per GPU", "clocks": c2}
 
     # ---- end to end through the host-pointer C-ABI (pinned buffers, copies inside the timed region) ----
-    pinned = [pinned_copy(b) for b in batches]
-    for pb in pinned:
-        eng.evaluate_host(pb)
-    e2e_steps = max(3, min(args.steps, 10))
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    e2e = None
+    v_host = None
+    if with_e2e:
+        pinned = [pinned_copy(b) for b in batches]
         for pb in pinned:
             v_host = eng.evaluate_host(pb)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t_e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = world * n_local * e2e_steps / float(t_e.item()) / 1e6
-    i2 = eng.info()
-    h2d, d2h = int(i2.last_h2d_bytes) * len(batches) * world, int(i2.last_d2h_bytes) * len(batches) * world  # whole job
+        e2e_steps = 3 if n_local > 2_000_000 else max(3, min(steps, 10))
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            for pb in pinned:
+                v_host = eng.evaluate_host(pb)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        t_e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        i2 = eng.info()
+        e2e = {"value": world * n_local * e2e_steps / float(t_e.item()) / 1e6, "unit": "M req/s",
+               "h2d_bytes_per_step": int(i2.last_h2d_bytes) * len(batches) * world, "d2h_bytes_per_step": int(i2.last_d2h_bytes) * len(batches) * world}
+        del pinned
 
+    if rank != 0:
+        return None
+
+    # ---- parity spot check on the timed outputs + CPU baseline (rank 0) ----
+    cpu = None
+    mismatches = None
+    hist = np.bincount(outs[0].cpu().numpy().view(np.uint32) & 3, minlength=4).tolist()
+    if with_cpu:
+        cpu_v, cpu_n, cpu_out = cpu_baseline_run(rules, lists, mmdb, batches[0], args.cpu_sample, ncores)
+        gpu_out = outs[0][:cpu_n].cpu().numpy().view(np.uint32)
+        mismatches = int(np.count_nonzero(gpu_out != cpu_out))
+        if v_host is not None and len(batches) == 1:
+            mismatches += int(np.count_nonzero(v_host[:cpu_n] != cpu_out))
+        cpu = {"value": cpu_v / 1e6, "unit": "M req/s", "cores": ncores, "kind": "port",
+               "sample": f"first {cpu_n} requests of the rank-0 batch; naive C restatement of the reference semantics (oracle/: Pike-VM regex, tree-walking evaluator, linear list scans) on {ncores} threads"}
+
+    peak, peak_src = peaks()
+    nb = steps * len(batches)
+    path_ms = ms / nb
+    names = ("waf_gate_kernel", "waf_field_scan_kernel", "waf_epilogue_kernel+waf_multi_kernel")
+    per_kernel = {names[i]: (kms[i] / kbatches if kbatches else None) for i in range(3)}
+    dom = max(range(3), key=lambda i: kms[i]) if kbatches else 0
+    # algorithmic bytes of the dominant kernel: the pre-pass kernel reads every scanned string column once plus its offsets;
+    # the scan and the epilogue are accounted against the whole request (they read a subset of it)
+    n_all = sum(b.n for b in batches)
+    from pingoo_b200 import _ffi
+
+    col_bytes = sum(sum(b.total[f] for b in batches) + 4 * n_all for fi, f in enumerate(_ffi.FIELDS) if (info.scanned_fields_mask >> fi) & 1)
+    kernel_alg = (col_bytes if dom == 0 else alg_total) / len(batches)
+    kernel_ms = per_kernel[names[dom]] if kbatches else path_ms
+    achieved = kernel_alg / (kernel_ms / 1e3) / 1e9
+    path_achieved = (alg_total / len(batches)) / (path_ms / 1e3) / 1e9
+    res = {
+        "value": value, "ms_per_step": ms_max / steps,
+        "config": {"workload": f"config {cfg_id}: {desc}", "requests_per_gpu": n_local, "rules": len(rules),
+                   "avg_algorithmic_bytes_per_request": round(alg_per_req, 1), "l2": "inputs larger than L2 (no flush needed)",
+                   "scan_units": info.n_scan_units, "dfa_states": info.total_dfa_states, "gate_grams": info.gate_grams,
+                   "verdict_hist_allow_block_captcha_bypass": hist, "verdict_mismatches_vs_oracle": mismatches, "parallelism": f"dp{world}"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic_for(cfg_id, names[dom].split("+")[0]), "peak_source": peak_src, "kernel": names[dom], "kernel_ms": kernel_ms,
+                     "algorithmic_bytes_per_launch": kernel_alg, "kernel_ms_per_batch": per_kernel, "batches_timed": int(kbatches),
+                     "path_ms_per_batch": path_ms, "path_algorithmic_bytes_per_batch": alg_total / len(batches),
+                     "path_achieved": path_achieved, "path_frac": path_achieved / peak},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if sustained:
+        res["sustained"] = sustained
+    del dev, outs, eng
+    torch.cuda.empty_cache()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=0, choices=[0] + sorted(CONFIGS), help="0: config 3 at one GPU, the config-4 shard at several")
+    ap.add_argument("--requests", type=int, default=0, help="override requests per GPU (debug)")
+    ap.add_argument("--cpu-sample", type=int, default=200_000)
+    ap.add_argument("--no-nested", action="store_true", help="skip the nested configs block of the N = 1 line")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    ncores = os.cpu_count() or 1
+    metric = "WAF verdicts/sec"
+    unit = "M req/s"
+    cfg = args.config or (3 if max(world, args.gpus) == 1 else 4)
+
+    if args.impl == "reference":
+        # The reference's own CPU path cannot be built here (no Rust toolchain; bel/regex/maxminddb crates are not vendored):
+        # this arm times the C restatement of its semantics (oracle/) on all host cores.  Rank 0 only.
+        if rank != 0:
+            return
+        desc, rules, lists, mmdb, batches = build_workload(cfg, 0, args.requests or args.cpu_sample)
+        vals = []
+        for i in range(args.warmup + args.steps):
+            v, n_s, _ = cpu_baseline_run(rules, lists, mmdb, batches[0], args.cpu_sample, ncores)
+            if i >= args.warmup:
+                vals.append(v)
+            if i == 0 and n_s / v > 20:  # keep the whole arm within minutes
+                args.steps = min(args.steps, 3)
+            if i + 1 >= args.warmup + args.steps:
+                vals = vals or [v]
+                break
+        v = statistics.median(vals) / 1e6
+        sample = f"{min(args.cpu_sample, batches[0].n)} requests of config {cfg} per step"
+        print(json.dumps({
+            "impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
+            "ms_per_step": 1e3 * min(args.cpu_sample, batches[0].n) / (v * 1e6), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"config {cfg}: {CONFIGS[cfg][0]}", "requests_per_gpu": args.requests or CONFIGS[cfg][1],
+                       "rules": len(rules), "parallelism": f"dp{args.gpus}", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": unit, "cores": ncores, "kind": "port", "sample": sample,
+                             "note": "naive C restatement of the reference semantics (oracle/), not the Rust reference"},
+            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    main_res = run_config(cfg, args, rank, local_rank, world, dist, args.steps, sustain_s=2.0, n_override=args.requests or None)
+    nested = {}
+    if world == 1 and not args.no_nested and not args.requests:
+        for c in (2, 4):
+            if c == cfg:
+                continue
+            r = run_config(c, args, rank, local_rank, world, dist, max(args.steps, 20), with_e2e=(c == 2), with_cpu=(c == 2))
+            nested[str(c)] = {"value": r["value"], "unit": unit, "ms_per_step": r["ms_per_step"], "workload": r["config"]["workload"],
+                              "requests_per_gpu": r["config"]["requests_per_gpu"], "rules": r["config"]["rules"],
+                              "roofline_frac": r["roofline"]["frac"], "path_frac": r["roofline"]["path_frac"], "kernel": r["roofline"]["kernel"],
+                              "kernel_ms_per_batch": r["roofline"]["kernel_ms_per_batch"],
+                              "verdict_mismatches_vs_oracle": r["config"]["verdict_mismatches_vs_oracle"],
+                              "e2e": r["e2e"]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-
-    # ---- parity spot check on the timed outputs + CPU baseline (rank 0) ----
-    cpu_v, cpu_n, cpu_out = cpu_baseline_run(rules, lists, mmdb, batches[0], args.cpu_sample, ncores)
-    gpu_out = outs[0][:cpu_n].cpu().numpy().view(np.uint32)
-    mismatches = int(np.count_nonzero(gpu_out != cpu_out)) + int(np.count_nonzero(v_host[:cpu_n] != cpu_out)) if len(batches) == 1 else int(np.count_nonzero(gpu_out != cpu_out))
-    hist = np.bincount(gpu_out & 3, minlength=4).tolist()
-
-    peak, peak_src = peaks()
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "latest_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            tj = json.load(f)
-        if tj.get("workload") == f"config {args.config}":
-            traffic = tj["dram_bytes_per_launch"]
-    # dominant kernel: the field scan; its duration comes from the event pairs the library records around each of its
-    # launches in the timed region (falls back to the whole-path time if the hook returned nothing)
-    path_ms = ms / (args.steps * len(batches))
-    kernel_ms = scan_ms_sum / scan_launches if scan_launches else path_ms
-    achieved = (alg_total / len(batches)) / (kernel_ms / 1e3) / 1e9
-    out = {
-        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"config {args.config}: {desc}", "requests_per_gpu": n_local, "rules": len(rules),
-                   "avg_algorithmic_bytes_per_request": round(alg_per_req, 1), "l2": "inputs larger than L2 (no flush needed)",
-                   "tables_in_smem": bool(info.tables_in_smem), "scan_units": info.n_scan_units, "dfa_states": info.total_dfa_states,
-                   "verdict_hist_allow_block_captcha_bypass": hist, "verdict_mismatches_vs_oracle": mismatches, "parallelism": f"dp{world}"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "kernel": "waf_field_scan_kernel", "kernel_ms": kernel_ms,
-                     "kernel_launches_timed": int(scan_launches), "path_ms_per_batch": path_ms,
-                     "algorithmic_bytes_per_launch": alg_total / len(batches)},
-        "cpu_baseline": {"value": cpu_v / 1e6, "unit": unit, "cores": ncores, "kind": "port",
-                         "sample": f"first {cpu_n} requests of the rank-0 batch, oracle (C restatement) on {ncores} threads"},
-        "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": int(launches), "clocks": clocks,
-    }
+    out = {"metric": metric, "value": main_res["value"], "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+           "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+           "config": main_res["config"], "roofline": main_res["roofline"], "cpu_baseline": main_res["cpu_baseline"], "e2e": main_res["e2e"],
+           "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"], "sustained": main_res.get("sustained")}
+    if nested:
+        out["configs"] = nested
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -196,12 +196,15 @@ int pgw_shape_request(const pgw_request* req, const char* out_ptr[5], size_t out
 int pgw_captcha_client_id_batch(const pgw_batch* batch, uint8_t* out44_dev, void* stream);
 
 int pgw_ruleset_info(const pgw_ruleset* rs, pgw_info* out);
-/* Measurement hook (no reference counterpart): while enabled, every batch evaluated on the default kernel path is
- * bracketed by CUDA events around its scan kernel, on the stream the kernel is launched on (a ring of 256 pairs).
- * pgw_ruleset_profile synchronises those events and returns the summed scan-kernel time and the number of launches
- * it covers (at most the 256 most recent), then clears the ring. */
+/* Measurement hook (no reference counterpart): while enabled, every batch is bracketed by CUDA events around its
+ * kernels, on the stream they are launched on (a ring of 256 batches).  pgw_ruleset_profile synchronises those events
+ * and returns the summed pre-pass + scan time and the number of batches it covers (at most the 256 most recent), then
+ * clears the ring. */
 int pgw_ruleset_set_profiling(pgw_ruleset* rs, int enable);
 int pgw_ruleset_profile(pgw_ruleset* rs, double* scan_ms_sum, uint32_t* launches);
+/* The same ring, per kernel group: ms_sum[0] = pre-pass kernel (candidate gate + small early-exit units), [1] = DFA scan
+ * launches, [2] = epilogue + multi-atom kernels; `batches` = how many batches the sums cover. */
+int pgw_ruleset_profile_kernels(pgw_ruleset* rs, double ms_sum[3], uint32_t* batches);
 /* Human-readable compile summary / warnings (e.g. a regex that does not compile => that rule never matches). */
 size_t pgw_ruleset_describe(const pgw_ruleset* rs, char* buf, size_t cap);
 void pgw_ruleset_destroy(pgw_ruleset* rs);

@@ -79,7 +79,7 @@ EXPORTS = (
     "pgw_ruleset_finalize", "pgw_evaluate_batch", "pgw_evaluate_batch_host", "pgw_geoip_lookup_batch",
     "pgw_services_set", "pgw_evaluate_batch_routed", "pgw_evaluate_batch_routed_host",
     "pgw_captcha_client_id_batch", "pgw_queue_create", "pgw_queue_evaluate", "pgw_queue_submit", "pgw_queue_get_stats", "pgw_queue_destroy", "pgw_shape_request",
-    "pgw_host_alloc", "pgw_host_free", "pgw_ruleset_info", "pgw_ruleset_set_profiling", "pgw_ruleset_profile",
+    "pgw_host_alloc", "pgw_host_free", "pgw_ruleset_info", "pgw_ruleset_set_profiling", "pgw_ruleset_profile", "pgw_ruleset_profile_kernels",
     "pgw_ruleset_describe", "pgw_ruleset_destroy", "pgw_last_error",
 )
 
@@ -114,6 +114,7 @@ def declare(lib, prefix="pgw_"):
         "ruleset_info": (C.c_int, [p, C.POINTER(Info)]),
         "ruleset_set_profiling": (C.c_int, [p, C.c_int]),
         "ruleset_profile": (C.c_int, [p, C.POINTER(C.c_double), C.POINTER(C.c_uint32)]),
+        "ruleset_profile_kernels": (C.c_int, [p, C.POINTER(C.c_double), C.POINTER(C.c_uint32)]),
         "ruleset_describe": (C.c_size_t, [p, C.c_char_p, C.c_size_t]),
         "ruleset_destroy": (None, [p]),
         "last_error": (C.c_char_p, []),

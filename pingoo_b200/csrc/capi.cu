@@ -461,14 +461,13 @@ static int launch_on(pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdict_out,
         P.cand_start[f] = G.f[i].cand_start;
         P.cand_end[f] = G.f[i].cand_end;
     }
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t* ev = nullptr;
     if (rs->profiling) {
         const uint64_t k = rs->prof_n.fetch_add(1, std::memory_order_relaxed) % kProfRing;
-        ev0 = rs->prof_ev[2 * k];
-        ev1 = rs->prof_ev[2 * k + 1];
+        ev = &rs->prof_ev[4 * k];
     }
     uint32_t nl = 0;
-    const char* m = waf_batch_launch(P, G, rs->units.data(), sc->small, kSmallWords, rs->sm_count, rs->scan_smem, rs->gate_smem, stream, ev0, ev1, &nl);
+    const char* m = waf_batch_launch(P, G, rs->units.data(), sc->small, kSmallWords, rs->sm_count, rs->scan_smem, rs->gate_smem, stream, ev, &nl);
     scratch_release(rs, sc, cs);
     rs->launches.fetch_add(nl, std::memory_order_relaxed);
     if (m) { e = std::string("CUDA launch failed: ") + m; return 1; }
@@ -664,7 +663,7 @@ int pgw_ruleset_set_profiling(pgw_ruleset* rs, int enable) {
     if (!rs || !rs->finalized) return fail("ruleset is not finalized", nullptr, 0);
     cudaSetDevice(rs->device);
     if (enable && rs->prof_ev.empty()) {
-        rs->prof_ev.resize(2 * kProfRing, nullptr);
+        rs->prof_ev.resize(4 * kProfRing, nullptr);
         for (auto& ev : rs->prof_ev)
             if (cudaEventCreate(&ev) != cudaSuccess) return fail("CUDA: event creation failed", nullptr, 0);
     }
@@ -673,22 +672,32 @@ int pgw_ruleset_set_profiling(pgw_ruleset* rs, int enable) {
     return 0;
 }
 
-int pgw_ruleset_profile(pgw_ruleset* rs, double* scan_ms_sum, uint32_t* launches) {
-    if (!rs || !scan_ms_sum || !launches) return fail("null argument", nullptr, 0);
-    *scan_ms_sum = 0.0;
-    *launches = 0;
+int pgw_ruleset_profile_kernels(pgw_ruleset* rs, double ms_sum[3], uint32_t* batches) {
+    if (!rs || !ms_sum || !batches) return fail("null argument", nullptr, 0);
+    ms_sum[0] = ms_sum[1] = ms_sum[2] = 0.0;
+    *batches = 0;
     if (rs->prof_ev.empty()) return 0;
     cudaSetDevice(rs->device);
     const uint64_t n = rs->prof_n.load();
     const uint32_t have = (uint32_t)(n < kProfRing ? n : kProfRing);
-    for (uint32_t k = 0; k < have; ++k) {
-        float ms = 0.f;
-        if (cudaEventSynchronize(rs->prof_ev[2 * k + 1]) != cudaSuccess || cudaEventElapsedTime(&ms, rs->prof_ev[2 * k], rs->prof_ev[2 * k + 1]) != cudaSuccess)
-            return fail("CUDA: profiling events are not complete", nullptr, 0);
-        *scan_ms_sum += ms;
-    }
-    *launches = have;
+    for (uint32_t k = 0; k < have; ++k)
+        for (int j = 0; j < 3; ++j) {
+            float ms = 0.f;
+            if (cudaEventSynchronize(rs->prof_ev[4 * k + j + 1]) != cudaSuccess ||
+                cudaEventElapsedTime(&ms, rs->prof_ev[4 * k + j], rs->prof_ev[4 * k + j + 1]) != cudaSuccess)
+                return fail("CUDA: profiling events are not complete", nullptr, 0);
+            ms_sum[j] += ms;
+        }
+    *batches = have;
     rs->prof_n.store(0);
+    return 0;
+}
+
+int pgw_ruleset_profile(pgw_ruleset* rs, double* scan_ms_sum, uint32_t* launches) {
+    if (!scan_ms_sum) return fail("null argument", nullptr, 0);
+    double ms[3];
+    if (int rc = pgw_ruleset_profile_kernels(rs, ms, launches)) return rc;
+    *scan_ms_sum = ms[0] + ms[1];
     return 0;
 }
 

@@ -103,13 +103,13 @@ size_t waf_gate_smem_bytes(const GateParams& g) {
 size_t waf_gate_prefix_budget() { return 48u << 10; }
 
 const char* waf_batch_launch(KParams& p, GateParams& g, const UnitDesc* all_units, uint32_t* small, uint32_t small_words, int sm_count,
-                             size_t scan_smem, size_t gate_smem, void* stream, cudaEvent_t ev0, cudaEvent_t ev1, uint32_t* launches) {
+                             size_t scan_smem, size_t gate_smem, void* stream, cudaEvent_t* ev, uint32_t* launches) {
     if (p.n == 0) return nullptr;
     cudaStream_t s = (cudaStream_t)stream;
     uint32_t nl = 0;
     cudaError_t e = cudaMemsetAsync(small, 0, (size_t)small_words * 4, s);
     if (e != cudaSuccess) return cudaGetErrorString(e);
-    if (ev0) cudaEventRecord(ev0, s);
+    if (ev) cudaEventRecord(ev[0], s);
     if (g.n_fields) {
         // tiles of 32 requests, one per warp at a time
         const uint32_t tiles = (p.n + 31u) / 32u, want = (tiles + kGateThreads / 32 - 1) / (kGateThreads / 32);
@@ -119,6 +119,7 @@ const char* waf_batch_launch(KParams& p, GateParams& g, const UnitDesc* all_unit
         if (e != cudaSuccess) return cudaGetErrorString(e);
         ++nl;
     }
+    if (ev) cudaEventRecord(ev[1], s);
     for (uint32_t ub = 0; ub < p.n_units_total; ub += kMaxConstUnits) {
         p.unit_base = ub;
         p.n_units = p.n_units_total - ub < kMaxConstUnits ? p.n_units_total - ub : kMaxConstUnits;
@@ -130,7 +131,7 @@ const char* waf_batch_launch(KParams& p, GateParams& g, const UnitDesc* all_unit
         if (e != cudaSuccess) return cudaGetErrorString(e);
         ++nl;
     }
-    if (ev1) cudaEventRecord(ev1, s);
+    if (ev) cudaEventRecord(ev[2], s);
     int blocks = (int)((p.n + 255) / 256);
     if (blocks > sm_count * 8) blocks = sm_count * 8;
     waf_epilogue_kernel<<<blocks, 256, 0, s>>>(p);
@@ -145,6 +146,7 @@ const char* waf_batch_launch(KParams& p, GateParams& g, const UnitDesc* all_unit
         if (e != cudaSuccess) return cudaGetErrorString(e);
         ++nl;
     }
+    if (ev) cudaEventRecord(ev[3], s);
     if (launches) *launches = nl;
     return nullptr;
 }

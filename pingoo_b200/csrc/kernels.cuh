@@ -136,10 +136,10 @@ size_t waf_gate_smem_bytes(const GateParams& g);
 size_t waf_gate_prefix_budget();  // shared memory the prefix-unit images of one field may take
 // One batch: [gate] -> scan (one launch per kMaxConstUnits units) -> epilogue, all on `stream`.
 // `all_units` = the program's unit descriptors (host copy); `small` = the block of claim counters and candidate counters
-// to zero first (`small_words` words).  ev0 / ev1 (optional) bracket the gate + scan kernels.
+// to zero first (`small_words` words).  `ev` (optional): four events recorded before the pre-pass kernel, after it, after the
+// scan launches and after the epilogue + multi kernels.
 const char* waf_batch_launch(KParams& p, GateParams& g, const UnitDesc* all_units, uint32_t* small, uint32_t small_words, int sm_count,
-                             size_t scan_smem, size_t gate_smem, void* stream, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,
-                             uint32_t* launches = nullptr);
+                             size_t scan_smem, size_t gate_smem, void* stream, cudaEvent_t* ev = nullptr, uint32_t* launches = nullptr);
 const char* client_id_launch(const uint8_t* ip, const uint8_t* is_v6, const uint8_t* ua_bytes, const uint32_t* ua_off, const uint8_t* host_bytes,
                              const uint32_t* host_off, uint32_t n, uint8_t* out44, void* stream);
 const char* geoip_launch(const KParams& p, const uint8_t* ip, const uint8_t* is_v6, uint32_t n, uint32_t* asn_out,

@@ -94,6 +94,13 @@ class WafEngine:
             raise Error(self._lib.pgw_last_error().decode(errors="replace"))
         return ms.value, n.value
 
+    def profile_kernels(self) -> tuple[list, int]:
+        """([pre-pass ms, scan ms, epilogue ms] summed, batches covered) since profiling was enabled / last read."""
+        ms, n = (C.c_double * 3)(), C.c_uint32(0)
+        if self._lib.pgw_ruleset_profile_kernels(self._h, ms, C.byref(n)) != 0:
+            raise Error(self._lib.pgw_last_error().decode(errors="replace"))
+        return [ms[0], ms[1], ms[2]], n.value
+
     def describe(self) -> str:
         n = self._lib.pgw_ruleset_describe(self._h, None, 0)
         buf = C.create_string_buffer(n + 1)

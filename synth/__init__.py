@@ -45,6 +45,9 @@ def lib():
             getattr(L, fn).restype = p
             getattr(L, fn).argtypes = [p]
         L.synth_destroy.argtypes = [p]
+        L.synth_mmdb_tree.restype = C.c_uint32
+        L.synth_mmdb_tree.argtypes = [C.c_char_p, p, C.c_uint32, C.POINTER(p), C.POINTER(C.c_size_t)]
+        L.synth_free.argtypes = [p]
         _lib = L
     return _lib
 
@@ -477,3 +480,99 @@ def make_geoip(n_networks=2000, config_id=3, ip_version=6):
             rec = {"asn": f"AS{asn}", "country": cc}
         records.append((n, rec))
     return write_mmdb(records, ip_version=ip_version), records
+
+
+def make_geoip_large(n_networks=500_000, config_id=3):
+    """A GeoIP database of the size SURVEY.md 8(d) asks for (~500 k networks, ~70 k ASNs, 26 x 26 country codes), built
+    in seconds: disjoint networks are laid out along the address space (IPv4: /16 .. /32, mostly /24; IPv6: /32 .. /64
+    under 2000::/4 and 2600::/8), the search tree is written by the C helper (synth_mmdb_tree).
+    Returns (mmdb bytes, dict of numpy arrays: start (n x 16 bytes), plen, is_v6, asn, country (uint16 LE), kind) --
+    kind 0 = well-formed record, 1.. = the malformed variants of make_geoip (reference answers {0, "XX"} / asn 0)."""
+    rng = np.random.RandomState((BASE_SEED + config_id + 32452843) % (2 ** 32))
+    n6 = n_networks * 15 // 100
+    n4 = n_networks - n6
+    plens4 = rng.choice([16, 20, 22, 24, 26, 28, 32], size=n4, p=[0.02, 0.08, 0.15, 0.45, 0.15, 0.10, 0.05])
+    starts = np.zeros((n_networks, 16), dtype=np.uint8)
+    plen = np.zeros(n_networks, dtype=np.uint8)
+    is_v6 = np.zeros(n_networks, dtype=np.uint8)
+    cur = 1 << 24
+    gaps = rng.randint(0, 3, size=n4)
+    k = 0
+    for i in range(n4):
+        size = 1 << (32 - int(plens4[i]))
+        cur = (cur + size - 1) & ~(size - 1)
+        if (cur >> 24) == 127:
+            cur = 128 << 24
+        if cur + size > (224 << 24):
+            break
+        starts[k, 0:4] = (cur >> 24) & 255, (cur >> 16) & 255, (cur >> 8) & 255, cur & 255
+        plen[k] = plens4[i]
+        k += 1
+        cur += size * (1 + int(gaps[i]))
+    n4 = k
+    plens6 = rng.choice([32, 40, 48, 56, 64], size=n6, p=[0.1, 0.1, 0.5, 0.1, 0.2])
+    cur6 = 0x2001 << 112
+    for i in range(n6):
+        size = 1 << (128 - int(plens6[i]))
+        cur6 = (cur6 + size - 1) & ~(size - 1)
+        if i == n6 // 2:
+            cur6 = 0x2600 << 112
+        starts[k] = np.frombuffer(cur6.to_bytes(16, "big"), dtype=np.uint8)
+        plen[k] = plens6[i]
+        is_v6[k] = 1
+        k += 1
+        cur6 += size * (1 + int(rng.randint(0, 4)))
+    n = k
+    starts, plen, is_v6 = starts[:n], plen[:n], is_v6[:n]
+    asn = rng.randint(1, 70000, size=n).astype(np.uint32)
+    c0, c1 = rng.randint(0, 26, size=n), rng.randint(0, 26, size=n)
+    x = rng.randint(0, 1000, size=n)
+    kind = np.select([x < 5, x < 10, x < 15, x < 20, x < 30], [1, 2, 3, 4, 5], 0).astype(np.uint8)
+    # data section: one blob per distinct (asn, country, kind)
+    blobs, index, off, pos = [], {}, [], 0
+    data_off = np.zeros(n, dtype=np.uint32)
+    for i in range(n):
+        key = (int(asn[i]), int(c0[i]), int(c1[i]), int(kind[i]))
+        j = index.get(key)
+        if j is None:
+            cc = chr(65 + key[1]) + chr(65 + key[2])
+            a = key[0]
+            rec = [{"asn": f"AS{a}", "country": cc}, {"asn": a, "country": cc}, {"asn": f"AS{a}", "country": cc.lower()},
+                   {"asn": f"ASX{a}", "country": cc}, {"country": cc}, {"asn": f"ASAS{a}", "country": cc, "extra": {"a": [1, 2, "x"], "b": True}}][key[3]]
+            b = _mm_value(rec)
+            j = len(blobs)
+            index[key] = j
+            blobs.append(b)
+            off.append(pos)
+            pos += len(b)
+        data_off[i] = off[j]
+    nets17 = np.zeros((n, 17), dtype=np.uint8)
+    v4 = is_v6 == 0
+    nets17[v4, 12:16] = starts[v4, 0:4]          # IPv4 networks live under ::/96
+    nets17[~v4, 0:16] = starts[~v4]
+    nets17[:, 16] = np.where(v4, plen.astype(np.int32) + 96, plen)
+    L = lib()
+    out, out_len = C.c_void_p(), C.c_size_t()
+    raw = nets17.tobytes()
+    node_count = L.synth_mmdb_tree(raw, data_off.ctypes.data, n, C.byref(out), C.byref(out_len))
+    if not node_count:
+        raise MemoryError("synth_mmdb_tree")
+    tree = C.string_at(out, out_len.value)
+    L.synth_free(out)
+    meta = {"binary_format_major_version": 2, "binary_format_minor_version": 0, "build_epoch": 1790000000,
+            "database_type": "pingoo-synthetic-large", "description": {"en": "synthetic"}, "ip_version": 6,
+            "languages": ["en"], "node_count": node_count, "record_size": 28}
+    mbytes = _mm_ctrl(7, len(meta))
+    for kx, v in meta.items():
+        mbytes += _mm_str(kx)
+        if kx in ("binary_format_major_version", "binary_format_minor_version", "ip_version", "record_size"):
+            mbytes += _mm_uint(v, 5)
+        elif kx == "build_epoch":
+            mbytes += _mm_uint(v, 9)
+        elif kx == "node_count":
+            mbytes += _mm_uint(v, 6)
+        else:
+            mbytes += _mm_value(v)
+    mmdb = tree + b"\0" * 16 + b"".join(blobs) + b"\xab\xcd\xefMaxMind.com" + mbytes
+    country = (c0 + 65).astype(np.uint16) | ((c1 + 65).astype(np.uint16) << 8)
+    return mmdb, {"start": starts, "plen": plen, "is_v6": is_v6, "asn": asn, "country": country, "kind": kind}

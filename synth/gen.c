@@ -371,3 +371,63 @@ void synth_destroy(gen_t* g) {
     free(g->ip); free(g->is_v6); free(g->flags); free(g->port);
     free(g);
 }
+
+/* ---- MaxMind-DB search tree builder (format 2.0, record size 28, ip_version 6) -------------------------------
+ * Input: n networks, each 17 bytes = 16 address bytes (IPv4 networks already mapped under ::/96) + prefix length
+ * (1..128, already +96 for IPv4), and for each the byte offset of its record inside the data section.  Networks must
+ * be prefix-free.  Output: the tree section only (node_count * 7 bytes); the caller appends the 16-byte separator,
+ * the data section, the metadata marker and the metadata.  Returns node_count, or 0 on allocation failure. */
+typedef struct { uint32_t kid[2]; } mnode_t; /* 0 = empty, 1..: node index + 1 when < 0x80000000, else 0x80000000 | leaf */
+
+uint32_t synth_mmdb_tree(const uint8_t* nets17, const uint32_t* data_off, uint32_t n, uint8_t** out, size_t* out_len) {
+    size_t cap = (size_t)n * 24 + 1024, cnt = 1;
+    mnode_t* nodes = (mnode_t*)calloc(cap, sizeof(mnode_t));
+    if (!nodes) return 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint8_t* a = nets17 + (size_t)i * 17;
+        int plen = a[16];
+        size_t cur = 0;
+        for (int d = 0; d < plen; ++d) {
+            int bit = (a[d >> 3] >> (7 - (d & 7))) & 1;
+            if (d == plen - 1) {
+                nodes[cur].kid[bit] = 0x80000000u | i;
+            } else {
+                uint32_t k = nodes[cur].kid[bit];
+                if (k == 0 || (k & 0x80000000u)) {
+                    if (cnt == cap) {
+                        cap *= 2;
+                        mnode_t* nn = (mnode_t*)realloc(nodes, cap * sizeof(mnode_t));
+                        if (!nn) { free(nodes); return 0; }
+                        memset(nn + cnt, 0, (cap - cnt) * sizeof(mnode_t));
+                        nodes = nn;
+                    }
+                    nodes[cur].kid[bit] = (uint32_t)cnt + 1;
+                    k = (uint32_t)cnt + 1;
+                    ++cnt;
+                }
+                cur = k - 1;
+            }
+        }
+    }
+    uint32_t node_count = (uint32_t)cnt;
+    uint8_t* t = (uint8_t*)malloc((size_t)node_count * 7);
+    if (!t) { free(nodes); return 0; }
+    for (uint32_t i = 0; i < node_count; ++i) {
+        uint32_t rec[2];
+        for (int b = 0; b < 2; ++b) {
+            uint32_t k = nodes[i].kid[b];
+            if (k == 0) rec[b] = node_count;                                   /* no data */
+            else if (k & 0x80000000u) rec[b] = node_count + 16 + data_off[k & 0x7FFFFFFFu];
+            else rec[b] = k - 1;
+        }
+        uint8_t* o = t + (size_t)i * 7;
+        o[0] = (uint8_t)(rec[0] >> 16); o[1] = (uint8_t)(rec[0] >> 8); o[2] = (uint8_t)rec[0];
+        o[3] = (uint8_t)((((rec[0] >> 24) & 0xF) << 4) | ((rec[1] >> 24) & 0xF));
+        o[4] = (uint8_t)(rec[1] >> 16); o[5] = (uint8_t)(rec[1] >> 8); o[6] = (uint8_t)rec[1];
+    }
+    free(nodes);
+    *out = t;
+    *out_len = (size_t)node_count * 7;
+    return node_count;
+}
+void synth_free(void* p) { free(p); }
