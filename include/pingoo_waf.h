@@ -105,6 +105,17 @@ int pgw_validate_expression(const char* expression, char* err, size_t err_cap);
 /* Config rule compilation: the loop of pingoo/config/config.rs:255-269.  Rule order = array order. */
 int pgw_ruleset_create(const pgw_rule_desc* rules, uint32_t n_rules, const pgw_options* options, pgw_ruleset** out,
                        char* err, size_t err_cap);
+/* config::load_and_validate + the loading half of Server::run for the rule path (pingoo/config/config.rs:194-323, 378-422;
+ * config_file.rs:97-101, 180-265; server.rs:40-47; geoip.rs:44-58, 94-109), on a configuration DIRECTORY:
+ * <dir>/pingoo.yml (rules, services, listeners, lists), <dir>/rules/ (*.yml), list CSV files, geoip.mmdb[.zst] (first of
+ * `geoip_dirs`; n_geoip_dirs == 0: <dir> then /usr/share/pingoo; `.zst` needs the system libzstd).  Rule order = file
+ * order, then the rules folder; duplicate rule names, expressions / routes that do not compile, unknown actions and
+ * malformed services are errors with the reference's messages.  The services installed (pgw_services_set) are the ones
+ * an HTTP listener offers a request to: `listener` NULL = every service with http_proxy or static, in configuration
+ * order (config.rs:217-221); else the `services:` list of that listener, in its own order (server.rs:104-110).
+ * The ruleset comes back un-finalized: pgw_ruleset_finalize uploads it. */
+int pgw_ruleset_load_dir(const char* config_folder, const char* listener, const char* const* geoip_dirs, uint32_t n_geoip_dirs,
+                         const pgw_options* options, pgw_ruleset** out, char* err, size_t err_cap);
 /* pingoo::lists::load_list on an in-memory CSV                          (pingoo/lists.rs:62-113) */
 int pgw_lists_add(pgw_ruleset* rs, const char* name, int list_type, const uint8_t* csv, size_t csv_len, char* err,
                   size_t err_cap);

@@ -75,7 +75,7 @@ NO_SERVICE = 0xFFFF
 FLAG_CAPTCHA_VERIFIED, FLAG_PRE_BLOCK, FLAG_PRE_CAPTCHA, FLAG_BYPASS = 1, 2, 4, 8
 
 EXPORTS = (
-    "pgw_compile_expression", "pgw_validate_expression", "pgw_ruleset_create", "pgw_lists_add", "pgw_geoip_load",
+    "pgw_compile_expression", "pgw_validate_expression", "pgw_ruleset_create", "pgw_ruleset_load_dir", "pgw_lists_add", "pgw_geoip_load",
     "pgw_ruleset_finalize", "pgw_evaluate_batch", "pgw_evaluate_batch_host", "pgw_geoip_lookup_batch",
     "pgw_services_set", "pgw_evaluate_batch_routed", "pgw_evaluate_batch_routed_host",
     "pgw_captcha_client_id_batch", "pgw_queue_create", "pgw_queue_evaluate", "pgw_queue_submit", "pgw_queue_get_stats", "pgw_queue_destroy", "pgw_shape_request",
@@ -111,6 +111,7 @@ def declare(lib, prefix="pgw_"):
         "geoip_lookup_batch": (C.c_int, [p, p, p, C.c_uint32, p, p, p]),
         "host_alloc": (p, [C.c_size_t]),
         "host_free": (None, [p]),
+        "ruleset_load_dir": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(Options), C.POINTER(p), C.c_char_p, C.c_size_t]),
         "ruleset_info": (C.c_int, [p, C.POINTER(Info)]),
         "ruleset_set_profiling": (C.c_int, [p, C.c_int]),
         "ruleset_profile": (C.c_int, [p, C.POINTER(C.c_double), C.POINTER(C.c_uint32)]),

@@ -93,7 +93,12 @@ def _rules_from_mapping(mapping, where) -> List[Rule]:
     return out
 
 
-def load_config(folder: str = DEFAULT_CONFIG_FOLDER, geoip_dirs: Optional[List[str]] = None) -> LoadedConfig:
+def load_config(folder: str = DEFAULT_CONFIG_FOLDER, geoip_dirs: Optional[List[str]] = None, listener: Optional[str] = None) -> LoadedConfig:
+    """The rule-path inputs of a configuration directory.  `services` = what an HTTP listener offers a request to
+    (config.rs:217-244, server.rs:62-74, 104-110): `listener` None -> every service with `http_proxy` or `static`, in
+    configuration order (tcp_proxy services never carry a route and are not offered to HTTP requests); else the
+    `services:` list of that listener, in its own order.  The product-side loader with the same behaviour is the C ABI's
+    pgw_ruleset_load_dir (csrc/config_dir.cpp); this Python one feeds the oracle and the tests."""
     cfg_path = os.path.join(folder, "pingoo.yml")
     try:
         raw = open(cfg_path, "rb").read()
@@ -140,14 +145,37 @@ def load_config(folder: str = DEFAULT_CONFIG_FOLDER, geoip_dirs: Optional[List[s
             except Error as e:
                 raise Error(f"error parsing rules: {e}")
 
+    all_services = {}
     for name, cfg in (doc.get("services") or {}).items():
-        sv = Service.from_config(str(name), cfg or {})
+        cfg = cfg or {}
+        kinds = [k for k in ("http_proxy", "static", "tcp_proxy") if cfg.get(k) is not None]
+        if len(kinds) != 1:
+            raise Error(f"invalid service definition for {name}: services must have exactly 1 http_proxy, tcp_proxy or static field")
+        sv = Service.from_config(str(name), cfg)
+        if kinds[0] == "tcp_proxy" and sv.route is not None:
+            raise Error(f"Invalid service definition for {name}: TCP proxy can't have a route")
         if sv.route is not None:
             try:
                 compile_expression(sv.route)
             except Error as e:
                 raise Error(f"error parsing route for service {sv.name}: {e}")
-        out.services.append(sv)
+        all_services[str(name)] = (sv, kinds[0] != "tcp_proxy")
+    offered = None
+    if listener is not None:
+        lcfg = (doc.get("listeners") or {}).get(listener)
+        if lcfg is None:
+            raise Error(f"config: listeners: {listener}: no such listener")
+        if lcfg.get("services") is not None:
+            offered = []
+            for nm in lcfg["services"]:
+                if nm not in all_services:
+                    raise Error(f"config: listeners: {listener}: service {nm} doesn't exist")
+                if nm in [o.name for o in offered]:
+                    raise Error(f"config: listeners: {listener}: duplicate services are not allowed ({nm})")
+                if not all_services[nm][1]:
+                    raise Error(f"config: listeners: {listener}: service {nm} is not an HTTP service")
+                offered.append(all_services[nm][0])
+    out.services = offered if offered is not None else [sv for sv, is_http in all_services.values() if is_http]
 
     for name, lc in (doc.get("lists") or {}).items():
         try:

@@ -234,6 +234,30 @@ int pgw_ruleset_create(const pgw_rule_desc* rules, uint32_t n_rules, const pgw_o
     return 0;
 }
 
+int pgw_ruleset_load_dir(const char* config_folder, const char* listener, const char* const* geoip_dirs, uint32_t n_geoip_dirs,
+                         const pgw_options* options, pgw_ruleset** out, char* err, size_t err_cap) {
+    if (!out || !config_folder) return fail("null argument", err, err_cap);
+    *out = nullptr;
+    pgw_ruleset* rs = new pgw_ruleset();
+    memset(&rs->base, 0, sizeof rs->base);
+    if (options) {
+        if (options->max_dfa_states > 0) rs->builder.options.max_dfa_states = options->max_dfa_states;
+        if (options->max_unit_table_bytes > 0) rs->builder.options.max_unit_table_bytes = (size_t)options->max_unit_table_bytes;
+        rs->builder.options.eval_gates = options->eval_gates != 0;
+        rs->builder.options.candidate_gate = options->disable_candidate_gate == 0;
+    }
+    std::vector<std::string> dirs;
+    for (uint32_t i = 0; i < n_geoip_dirs; ++i) dirs.push_back(geoip_dirs[i]);
+    if (!n_geoip_dirs) { dirs.push_back(config_folder); dirs.push_back("/usr/share/pingoo"); }  // config.rs:31-36
+    std::string e;
+    if (!load_config_dir(config_folder, listener, dirs, &rs->builder, nullptr, e)) {
+        delete rs;
+        return fail(e, err, err_cap);
+    }
+    *out = rs;
+    return 0;
+}
+
 int pgw_lists_add(pgw_ruleset* rs, const char* name, int list_type, const uint8_t* csv, size_t csv_len, char* err,
                   size_t err_cap) {
     if (!rs || !name) return fail("null argument", err, err_cap);

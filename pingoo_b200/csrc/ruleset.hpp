@@ -46,4 +46,9 @@ class RulesetBuilder {
     bool finalized_ = false;
 };
 
+// config_dir.cpp: fill `builder` from a Pingoo configuration directory (rules, the services an HTTP listener offers,
+// lists, GeoIP database).  `listener` null: the default service set of an http / https listener.
+bool load_config_dir(const std::string& folder, const char* listener, const std::vector<std::string>& geoip_dirs, RulesetBuilder* builder,
+                     std::string* geoip_path, std::string& err);
+
 }  // namespace pgw

@@ -65,6 +65,28 @@ class WafEngine:
             raise Error(msg)
         self.device = device
 
+    @classmethod
+    def from_config_dir(cls, folder: str, listener: Optional[str] = None, geoip_dirs: Optional[Iterable[str]] = None, device: int = 0,
+                        eval_gates: bool = True, max_dfa_states: int = 0, max_unit_table_bytes: int = 0, candidate_gate: bool = True):
+        """pgw_ruleset_load_dir + finalize: a Pingoo configuration directory consumed by the engine's own (C++) loader."""
+        self = cls.__new__(cls)
+        self._lib = _ffi.load()
+        self._h = C.c_void_p()
+        self.rules, self.services, self._keep = [], [], []
+        opt = _ffi.Options(max_dfa_states, max_unit_table_bytes, 1 if eval_gates else 0, 0 if candidate_gate else 1)
+        err = C.create_string_buffer(2048)
+        dirs = [d.encode() for d in (geoip_dirs or [])]
+        arr = (C.c_char_p * max(1, len(dirs)))(*dirs)
+        if self._lib.pgw_ruleset_load_dir(folder.encode(), None if listener is None else listener.encode(), arr, len(dirs), C.byref(opt),
+                                          C.byref(self._h), err, len(err)):
+            raise Error(err.value.decode(errors="replace"))
+        if self._lib.pgw_ruleset_finalize(self._h, device, err, len(err)):
+            msg = err.value.decode(errors="replace")
+            self.close()
+            raise Error(msg)
+        self.device = device
+        return self
+
     # ---- lifecycle ---------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None) and self._h.value:

@@ -141,6 +141,11 @@ def sim_lib():
         lib.pgwsim_geoip_lookup.argtypes = [p, p, p, C.c_uint32, p, p]
         lib.pgwsim_destroy.argtypes = [p]
         lib.pgwsim_destroy.restype = None
+        lib.pgwsim_load_dir.restype = p
+        lib.pgwsim_load_dir.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
+        lib.pgwsim_yaml_dump.restype = C.c_size_t
+        lib.pgwsim_yaml_dump.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]
+        lib.pgwsim_evaluate_mt.argtypes = [p, C.POINTER(_ffi.Batch), p, C.c_int]
         lib.pgwsim_set_gate_stats.argtypes = [p, p]
         lib.pgwsim_set_gate_stats.restype = None
         _sim = lib
@@ -172,6 +177,20 @@ class Sim:
         if self.lib.pgwsim_finalize(self.h, err, len(err)):
             raise ValueError(err.value.decode(errors="replace"))
 
+    @classmethod
+    def from_config_dir(cls, folder, listener=None, geoip_dir=None):
+        """The engine's C++ configuration-directory loader (csrc/config_dir.cpp) feeding the table walk."""
+        self = cls.__new__(cls)
+        self.lib = sim_lib()
+        err = C.create_string_buffer(2048)
+        self.h = self.lib.pgwsim_load_dir(folder.encode(), None if listener is None else listener.encode(),
+                                          None if geoip_dir is None else geoip_dir.encode(), err, len(err))
+        if not self.h:
+            raise ValueError(err.value.decode(errors="replace"))
+        if self.lib.pgwsim_finalize(self.h, err, len(err)):
+            raise ValueError(err.value.decode(errors="replace"))
+        return self
+
     def gate_stats(self):
         """Start counting, per field, how many requests the gate saw and how many it made candidates."""
         self._stats = np.zeros(10, dtype=np.uint64)
@@ -188,6 +207,13 @@ class Sim:
         out = np.empty(batch.n, dtype=np.uint32)
         cb = batch.as_ctypes()
         if self.lib.pgwsim_evaluate(self.h, C.byref(cb), out.ctypes.data):
+            raise RuntimeError("sim evaluate failed")
+        return out
+
+    def evaluate_mt(self, batch: RequestBatch, threads: int) -> np.ndarray:
+        out = np.empty(batch.n, dtype=np.uint32)
+        cb = batch.as_ctypes()
+        if self.lib.pgwsim_evaluate_mt(self.h, C.byref(cb), out.ctypes.data, threads):
             raise RuntimeError("sim evaluate failed")
         return out
 
@@ -216,3 +242,14 @@ def fmt_verdict(v):
     act = ["allow", "block", "captcha", "bypass"][int(v) & 3]
     r = int(v) >> 2
     return f"{act}@{'-' if r == _ffi.NO_RULE else r}"
+
+
+def yaml_dump(text: str):
+    """(ok, canonical dump or error text) from the engine's YAML subset reader (csrc/yaml.cpp)."""
+    lib = sim_lib()
+    raw = text.encode()
+    ok = C.c_int(0)
+    n = lib.pgwsim_yaml_dump(raw, len(raw), None, 0, C.byref(ok))
+    buf = C.create_string_buffer(n + 1)
+    lib.pgwsim_yaml_dump(raw, len(raw), buf, n + 1, C.byref(ok))
+    return bool(ok.value), buf.value.decode(errors="replace")

@@ -8,10 +8,12 @@
 // to establish kernel == tables.  The product library never links this file.
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pingoo_waf.h"
 #include "../../pingoo_b200/csrc/ruleset.hpp"
+#include "../../pingoo_b200/csrc/yaml.hpp"
 
 using namespace pgw;
 
@@ -161,15 +163,36 @@ int pgwsim_services_set(void* h, const pgw_service_desc* sv, uint32_t n, char* e
 
 int pgwsim_evaluate_routed(void* h, const pgw_batch* b, uint32_t* out, uint16_t* svc_out);
 int pgwsim_evaluate(void* h, const pgw_batch* b, uint32_t* out) { return pgwsim_evaluate_routed(h, b, out, nullptr); }
+static int evaluate_range(Sim* s, const pgw_batch* b, uint32_t* out, uint16_t* svc_out, uint32_t r_lo, uint32_t r_hi);
 
 int pgwsim_evaluate_routed(void* h, const pgw_batch* b, uint32_t* out, uint16_t* svc_out) {
     Sim* s = (Sim*)h;
     if (!s->finalized) return 1;
+    return evaluate_range(s, b, out, svc_out, 0, b->n);
+}
+
+// the same walk on `threads` host threads (contiguous ranges): the table-driven CPU leg of bench.py
+int pgwsim_evaluate_mt(void* h, const pgw_batch* b, uint32_t* out, int threads) {
+    Sim* s = (Sim*)h;
+    if (!s->finalized || s->stats || s->atom_hist) return 1;
+    if (threads < 1) threads = 1;
+    std::vector<std::thread> th;
+    std::vector<int> rc((size_t)threads, 0);
+    for (int t = 0; t < threads; ++t) {
+        const uint32_t lo = (uint32_t)((uint64_t)b->n * t / threads), hi = (uint32_t)((uint64_t)b->n * (t + 1) / threads);
+        th.emplace_back([=, &rc]() { rc[t] = evaluate_range(s, b, out, nullptr, lo, hi); });
+    }
+    for (auto& x : th) x.join();
+    for (int v : rc) if (v) return v;
+    return 0;
+}
+
+static int evaluate_range(Sim* s, const pgw_batch* b, uint32_t* out, uint16_t* svc_out, uint32_t r_lo, uint32_t r_hi) {
     const HostProgram& H = s->H;
     const pgw_strcol* cols[5] = {&b->host, &b->url, &b->path, &b->method, &b->user_agent};
     const uint32_t Aw = H.atom_words;
     std::vector<uint32_t> row(Aw);
-    for (uint32_t r = 0; r < b->n; ++r) {
+    for (uint32_t r = r_lo; r < r_hi; ++r) {
         std::fill(row.begin(), row.end(), 0);
         // candidate gate (gate.hpp): every even-aligned 4-byte window of the column that overlaps the field
         uint32_t cand[N_FIELDS] = {0, 0, 0, 0, 0};  // per field: mask of the gated units the request is a candidate for
@@ -389,6 +412,21 @@ void pgwsim_set_gate_stats(void* h, uint64_t* stats10) { ((Sim*)h)->stats = stat
 
 void pgwsim_destroy(void* h) { delete (Sim*)h; }
 
+// the configuration-directory loader (config_dir.cpp) on the simulator's builder: the CPU half of pgw_ruleset_load_dir
+void* pgwsim_load_dir(const char* folder, const char* listener, const char* geoip_dir, char* err, size_t cap) {
+    Sim* s = new Sim();
+    std::vector<std::string> dirs;
+    if (geoip_dir) dirs.push_back(geoip_dir);
+    else { dirs.push_back(folder); dirs.push_back("/usr/share/pingoo"); }
+    std::string e;
+    if (!load_config_dir(folder, listener, dirs, &s->builder, nullptr, e)) {
+        fail(nullptr, e, err, cap);
+        delete s;
+        return nullptr;
+    }
+    return s;
+}
+
 }  // extern "C"
 
 // Analysis tool (no product counterpart): shared-memory wavefronts of the scan's row look-ups for one unit, emulating
@@ -482,3 +520,18 @@ extern "C" void pgwsim_gate_window_stats(void* h, const pgw_batch* b, int f, uin
 
 // debug: histogram of the number of true atoms per request (out[0..3] = 0, 1, 2, >=3) -- sizes the epilogue's paths
 extern "C" void pgwsim_set_atom_hist(void* h, uint64_t* out4) { ((Sim*)h)->atom_hist = out4; }
+
+// the YAML subset reader, canonical dump (compared with PyYAML by tests/test_config_formats.py); returns the length needed
+extern "C" size_t pgwsim_yaml_dump(const char* text, size_t len, char* buf, size_t cap, int* ok) {
+    YNode root;
+    std::string err;
+    std::string out;
+    if (yaml_parse(std::string(text, len), &root, err)) { *ok = 1; out = yaml_dump(root); }
+    else { *ok = 0; out = err; }
+    if (buf && cap) {
+        size_t n = out.size() < cap - 1 ? out.size() : cap - 1;
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return out.size();
+}

@@ -7,7 +7,11 @@ import numpy as np
 import pytest
 
 import synth
-from helpers import Oracle, Sim
+import json
+
+import yaml
+
+from helpers import Oracle, Sim, yaml_dump
 from pingoo_b200 import Action, Error, ListType
 from pingoo_b200.config import load_config, zstd_decode_all
 
@@ -15,7 +19,12 @@ PINGOO_YML = """
 listeners:
   http:
     address: http://0.0.0.0:8080
+    services: ["webapp", "api"]
+  raw:
+    address: tcp://0.0.0.0:5432
 services:
+  db:                       # a TCP service listed first: never offered to HTTP requests (config.rs:217-221)
+    tcp_proxy: ["10.0.0.5:5432"]
   api:
     route: http_request.host.starts_with("api.")
     http_proxy: []
@@ -94,6 +103,40 @@ def test_directory_is_loaded_like_the_reference_does(tmp_path):
     got_v, got_s = Sim(cfg.rules, cfg.lists, cfg.geoip_mmdb, services=cfg.services).evaluate_routed(batch)
     assert np.array_equal(got_v, want_v) and np.array_equal(got_s, want_s)
     assert len(set((want_v & 3).tolist())) >= 2 and 2 in set(want_s.tolist())  # blocked / captcha / allowed, catch-all service used
+    # the engine's own (C++) loader reads the same directory to the same program
+    nat = Sim.from_config_dir(str(tmp_path), geoip_dir=str(tmp_path))
+    nat_v, nat_s = nat.evaluate_routed(batch)
+    assert np.array_equal(nat_v, want_v) and np.array_equal(nat_s, want_s)
+    assert nat.describe() == Sim(cfg.rules, cfg.lists, cfg.geoip_mmdb, services=cfg.services).describe()
+    # a listener's own `services:` list, in its order: webapp (no route) shadows api
+    lis = load_config(str(tmp_path), geoip_dirs=[str(tmp_path)], listener="http")
+    assert [s.name for s in lis.services] == ["webapp", "api"]
+    lv, ls = Oracle(lis.rules, lis.lists, lis.geoip_mmdb, services=lis.services).evaluate_routed(batch, threads=4)
+    nv, ns = Sim.from_config_dir(str(tmp_path), listener="http", geoip_dir=str(tmp_path)).evaluate_routed(batch)
+    assert np.array_equal(nv, lv) and np.array_equal(ns, ls) and set(ls[(lv & 3) == 0].tolist()) == {0}
+
+
+@pytest.mark.gpu
+def test_engine_loads_a_configuration_directory_through_the_c_abi(tmp_path):
+    """pgw_ruleset_load_dir (csrc/config_dir.cpp) -> finalize -> evaluate: the documented example directory, GeoIP from the
+    compressed database, both service sets (default and the listener's own list), against the oracle fed by the Python loader."""
+    from pingoo_b200 import WafEngine
+
+    members, mmdb = _write_tree(tmp_path)
+    d = str(tmp_path)
+    stream = synth.RequestStream(config_id=3, payloads=[], blocklist_ips=members, blocklist_rate=0.1)
+    batch = stream.generate(0, 20_000)
+    batch.asn = None
+    batch.country = None
+    for listener in (None, "http"):
+        cfg = load_config(d, geoip_dirs=[d], listener=listener)
+        want_v, want_s = Oracle(cfg.rules, cfg.lists, cfg.geoip_mmdb, services=cfg.services).evaluate_routed(batch, threads=os.cpu_count() or 1)
+        eng = WafEngine.from_config_dir(d, listener=listener, geoip_dirs=[d], device=0)
+        got_v, got_s = eng.evaluate_host_routed(batch)
+        assert np.array_equal(got_v, want_v) and np.array_equal(got_s, want_s), listener
+        assert eng.info().n_rules == 4 and eng.info().geoip_loaded == 1
+    with pytest.raises(Error, match="error reading config file"):
+        WafEngine.from_config_dir(str(tmp_path / "nope"))
 
 
 def test_configuration_errors(tmp_path):
@@ -115,6 +158,83 @@ def test_configuration_errors(tmp_path):
         load_config(str(tmp_path), geoip_dirs=[str(tmp_path)])
     with pytest.raises(Error, match="error reading config file"):
         load_config(str(tmp_path / "nope"))
+
+
+def test_native_loader_reports_the_same_configuration_errors(tmp_path):
+    _write_tree(tmp_path, geo_zst=False)
+    d = str(tmp_path)
+    Sim.from_config_dir(d, geoip_dir=d)
+    cases = [
+        ("rules/b.yml", "captcha_bots: {actions: []}", "duplicate rule name: captcha_bots"),
+        ("rules/b.yml", 'broken: {expression: "http_request.path ==", actions: []}', "error parsing rules: Expression is not valid"),
+        ("rules/b.yml", "x: {actions: [{action: drop}]}", "unknown variant `drop`, expected `block` or `captcha`"),
+        ("rules/b.yml", "x: {expression: \"true\"}", "missing field `actions`"),
+        ("rules/b.yml", "x: [1, 2", "error parsing rules file"),
+    ]
+    for rel, text, msg in cases:
+        (tmp_path / rel).write_text(text)
+        with pytest.raises(ValueError, match=msg):
+            Sim.from_config_dir(d, geoip_dir=d)
+        with pytest.raises(Error, match=msg.replace("rules file", "rules file")):
+            load_config(d, geoip_dirs=[d])
+    os.remove(tmp_path / "rules" / "b.yml")
+    base = (tmp_path / "pingoo.yml").read_text()
+    for patch, msg in [
+        (("    http_proxy: []", "    http_proxy: []\n    static: {root: /x}"), "services must have exactly 1 http_proxy, tcp_proxy or static field"),
+        (('    tcp_proxy: ["10.0.0.5:5432"]', '    tcp_proxy: ["10.0.0.5:5432"]\n    route: "true"'), "TCP proxy can't have a route"),
+        (('http_request.path.ends_with(".png")', 'http_request.path.ends_with('), "error parsing route for service images"),
+        (("type: Int", "type: Float"), "unknown variant `Float`, expected one of `String`, `Int`, `Ip`"),
+        (('services: ["webapp", "api"]', 'services: ["webapp", "nope"]'), "service nope doesn't exist"),
+    ]:
+        (tmp_path / "pingoo.yml").write_text(base.replace(*patch))
+        with pytest.raises(ValueError, match=msg):
+            Sim.from_config_dir(d, listener="http", geoip_dir=d)
+        with pytest.raises(Error, match=msg):
+            load_config(d, geoip_dirs=[d], listener="http")
+    (tmp_path / "pingoo.yml").write_text(base)
+    (tmp_path / "geoip.mmdb.zst").write_bytes(b"not zstd")
+    os.remove(tmp_path / "geoip.mmdb")
+    with pytest.raises(ValueError, match="error decompressing geoip database"):
+        Sim.from_config_dir(d, geoip_dir=d)
+    with pytest.raises(ValueError, match="error reading config file .*No such file or directory \\(os error 2\\)"):
+        Sim.from_config_dir(str(tmp_path / "nope"))
+
+
+def _canon(x):
+    if isinstance(x, dict):
+        return "{" + ",".join(json.dumps(str(k)) + ":" + _canon(v) for k, v in x.items()) + "}"
+    if isinstance(x, list):
+        return "[" + ",".join(_canon(v) for v in x) + "]"
+    if x is None:
+        return "null"
+    if isinstance(x, bool):
+        return json.dumps("true" if x else "false")
+    return json.dumps(str(x), ensure_ascii=False)
+
+
+YAML_SAMPLES = [
+    PINGOO_YML.format(blocked="/tmp/b.csv", asns="/tmp/a.csv"),
+    RULES_A,
+    "a: 1\nb:\n  - x\n  - y: 2\n    z: [p, 'q r', \"s\\tt\"]\n  -\n    - nested\n    - seq\nc: {k: v, l: [1, 2]}\nd: ~\ne:\n",
+    "key: |\n  line one\n    indented\n\n  line three\nfold: >-\n  a b\n  c\n\n  d\nkeep: |+\n  x\n\nafter: 'it''s'\n",
+    "# comment\n---\nrules:\n  r1:   # trailing comment\n    expression: http_request.url.contains(\"#not a comment\")\n    actions:\n    - action: block\n    - action: captcha\n",
+    "plain: multi\n  line scalar\n  continues\nurl: http://x/y#frag\n\"quoted key\": [a,\n  b,\n  c]\n",
+    "seq_at_same_indent:\n- a\n- b\nother: 3\n",
+    "",
+]
+
+
+@pytest.mark.parametrize("text", YAML_SAMPLES)
+def test_yaml_reader_agrees_with_pyyaml(text):
+    ok, out = yaml_dump(text)
+    assert ok, out
+    assert out == _canon(yaml.safe_load(text))
+
+
+@pytest.mark.parametrize("text", ["a: [1, 2", "a: 'x", "a: &anchor 1", "a: *alias", "a:\n    b: 1\n  c: 2\n", "- a\nb: 1\n", "a: 1\na: 2\n", "? complex\n: key\n", "next: value with: colon inside\n"])
+def test_yaml_reader_rejects_what_it_does_not_read(text):
+    ok, out = yaml_dump(text)
+    assert not ok and out.startswith("line "), out
 
 
 def test_zstd_round_trip():
