@@ -224,8 +224,10 @@ static int enqueue(pgw_queue* q, std::unique_lock<std::mutex>& lk, const pgw_req
     if (q->stop) return 2;
     Side* s = &q->side[q->fill];
     const uint32_t i = s->n;
-    for (int f = 0; f < 5; ++f) {
+    // every column is grown before any of them is touched: a failed allocation leaves the side exactly as it was
+    for (int f = 0; f < 5; ++f)
         if (!grow(*s, f, s->used[f] + sh.n[f])) return 3;
+    for (int f = 0; f < 5; ++f) {
         s->offs[f][i] = (uint32_t)s->used[f];
         if (sh.n[f]) memcpy(s->bytes[f] + s->used[f], sh.p[f], sh.n[f]);
         s->used[f] += sh.n[f];
