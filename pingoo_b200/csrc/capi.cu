@@ -86,12 +86,17 @@ struct Scratch {
     // carved out of `base`
     uint32_t* rows = nullptr;
     uint32_t* info = nullptr;
-    uint32_t* small = nullptr;       // [0, kSmallCounters): per-unit claim counters; [kSmallCounters, +5): candidate counters; [+5]: multi count
+    uint32_t* small = nullptr;       // [0, kSmallCounters): per-unit claim counters; [kSmallCounters, +5): candidate counters; [+5]: multi count;
+                                     // [+8, +13): hit-queue overflow flags per field; [+16 + 256 f, ..): hit-queue segment counts of field f
     uint32_t* multi = nullptr;       // multi list (request indices)
     uint32_t* cand[5][4] = {};       // per gated field: idx, start, end, unit mask
+    uint32_t* reqmask = nullptr;     // candidate word per request
+    uint32_t* hq[5] = {};            // per gated field: hit queue (kHitQueuePerRequest entries per request of capacity)
 };
 constexpr uint32_t kSmallCounters = 1024;   // scan units a program may have
-constexpr uint32_t kSmallWords = kSmallCounters + 8;
+constexpr uint32_t kMaxGateSegments = 256;  // CTAs of the gate kernel (one per SM)
+constexpr uint32_t kSmallWords = kSmallCounters + 16 + 5 * kMaxGateSegments;
+constexpr uint32_t kHitQueuePerRequest = 2; // benign traffic queues ~0.2 chunks per request and field; beyond the capacity the gate degrades to "every request is a candidate"
 
 struct HostStage {   // device staging of one host-pointer call (pgw_evaluate_batch_host), pooled so that calls may overlap
     Staging cols[5], offs[5], ip, v6, port, asn, country, flags, verdict, service;
@@ -126,7 +131,7 @@ struct pgw_ruleset {
     DevMem mem;
     KParams base;  // program pointers filled in, batch fields zero
     GateParams gate_base;  // bitmaps and shifts filled in
-    int gate_field[kMaxGateFields] = {0, 0, 0, 0, 0};
+    int gate_field[kMaxGateFields] = {0, 0, 0};
     std::vector<UnitDesc> units;   // with the image fields filled in
     size_t scan_smem = 0, gate_smem = 0;
     uint32_t hot_states_total = 0;
@@ -160,7 +165,8 @@ Scratch* scratch_acquire(pgw_ruleset* rs, uint32_t n, cudaStream_t stream, std::
     cap = (cap + 31) & ~(size_t)31;
     size_t n_gated = 0;
     for (int f = 0; f < 5; ++f) n_gated += H.gate[f].present ? 1 : 0;
-    const size_t rows_b = cap * H.atom_words * 4, dirty_b = cap * 8 + 64, small_b = kSmallWords * 4, cand_b = (n_gated * 4 + 1) * cap * 4;
+    const size_t rows_b = cap * H.atom_words * 4, dirty_b = cap * 8 + 64, small_b = kSmallWords * 4,
+                 cand_b = (n_gated * (4 + kHitQueuePerRequest) + 2) * cap * 4;
     const size_t total = rows_b + dirty_b + small_b + cand_b + 1024;
     if (cudaMalloc((void**)&sc->base, total) != cudaSuccess || cudaEventCreateWithFlags(&sc->done, cudaEventDisableTiming) != cudaSuccess) {
         e = std::string("CUDA: scratch allocation failed (") + std::to_string(total >> 20) + " MiB): " + cudaGetErrorString(cudaGetLastError());
@@ -175,9 +181,12 @@ Scratch* scratch_acquire(pgw_ruleset* rs, uint32_t n, cudaStream_t stream, std::
     sc->info = (uint32_t*)q; q += dirty_b;
     sc->small = (uint32_t*)q; q += small_b;
     sc->multi = (uint32_t*)q; q += cap * 4;
+    sc->reqmask = (uint32_t*)q; q += cap * 4;
     for (int f = 0; f < 5; ++f)
-        if (H.gate[f].present)
+        if (H.gate[f].present) {
             for (int k = 0; k < 4; ++k) { sc->cand[f][k] = (uint32_t*)q; q += cap * 4; }
+            sc->hq[f] = (uint32_t*)q; q += (size_t)kHitQueuePerRequest * cap * 4;
+        }
     sc->cap_requests = cap;
     sc->busy = true;
     rs->pool.push_back(sc);
@@ -332,39 +341,45 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
             if (P.n_start_end >= 8) return fail("too many scan units with patterns that match an empty field", err, err_cap);
             P.start_end_unit[P.n_start_end++] = (uint32_t)u;
         }
-    // pre-pass kernel: candidate gate tables, and the small early-exit units (start-anchored patterns) of each field --
-    // those are walked there, one lane per request, instead of costing a pass of the scan kernel each
-    GateParams& G = rs->gate_base;
-    memset(&G, 0, sizeof G);
-    static const int kPrepassOrder[5] = {F_URL, F_USER_AGENT, F_PATH, F_HOST, F_METHOD};
-    size_t image_area = 0;
-    for (int fo = 0; fo < 5; ++fo) {
-        const int f = kPrepassOrder[fo];
-        GateField gf;
-        memset(&gf, 0, sizeof gf);
+    // small early-exit units (start-anchored patterns, whole table in shared memory): walked by the epilogue kernel, one
+    // thread per request, instead of costing a pass of the scan kernel each; their images sit next to each other in its
+    // shared memory
+    P.n_prefix = 0;
+    {
         size_t used = 0;
-        for (size_t u = 0; u < units.size(); ++u) {
+        for (size_t u = 0; u < units.size() && P.n_prefix < kMaxPrefixUnits; ++u) {
             UnitDesc& ud = units[u];
-            if ((int)ud.field != f || ud.mode != UM_ALL || ud.abs0 == 0xFFFFFFFFu || ud.hot_states != ud.n_states) continue;
+            if (ud.mode != UM_ALL || ud.abs0 == 0xFFFFFFFFu || ud.hot_states != ud.n_states) continue;
             const size_t need = ((size_t)ud.img_bytes + 255) & ~(size_t)255;
-            if (gf.n_prefix >= kMaxPrefixUnits || used + need > waf_gate_prefix_budget()) continue;
+            if (used + need > waf_prefix_budget()) continue;
             ud.mode = UM_PREPASS;
-            gf.prefix_img[gf.n_prefix] = (uint32_t)used;
-            gf.prefix[gf.n_prefix++] = ud;
+            P.prefix_img[P.n_prefix] = (uint32_t)used;
+            P.pdesc[P.n_prefix++] = ud;
             used += need;
         }
-        if (used > image_area) image_area = used;
-        if (H.gate[f].present) {
-            gf.b1 = (const uint32_t*)chk(M.upload(H.gate[f].b1));
-            gf.slots = (const uint32_t*)chk(M.upload(H.gate[f].slots));
-            gf.k1 = H.gate[f].k1;
-            gf.kt = H.gate[f].kt;
-        }
-        if (!gf.b1 && !gf.n_prefix) continue;
+        P.prefix_area = (uint32_t)used;
+    }
+    // candidate gate: the level-1 bitmaps of all gated fields are resident in the gate kernel's shared memory together
+    GateParams& G = rs->gate_base;
+    memset(&G, 0, sizeof G);
+    static const int kGateOrder[3] = {F_URL, F_USER_AGENT, F_PATH};
+    size_t bloom_used = 0;
+    for (int fo = 0; fo < 3; ++fo) {
+        const int f = kGateOrder[fo];
+        if (!H.gate[f].present) continue;
+        GateField gf;
+        memset(&gf, 0, sizeof gf);
+        gf.b1 = (const uint32_t*)chk(M.upload(H.gate[f].b1));
+        gf.slots = (const uint32_t*)chk(M.upload(H.gate[f].slots));
+        gf.k1 = H.gate[f].k1;
+        gf.kt = H.gate[f].kt;
+        gf.bloom_off = (uint32_t)bloom_used;
+        bloom_used += ((size_t)1 << gf.k1) / 8;
+        gf.mask_shift = kGateShift[f];
+        gf.mask_bits = (1u << kGateWidth[f]) - 1u;
         rs->gate_field[G.n_fields] = f;
         G.f[G.n_fields++] = gf;
     }
-    G.image_area = (uint32_t)image_area;
     // the scan kernel reads the unit descriptors from the host copy (parameter bank) and the epilogue from P.units: both
     // must see the UM_PREPASS marks
     P.units = (const UnitDesc*)chk(M.upload(units));
@@ -469,11 +484,22 @@ static int launch_on(pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdict_out,
     P.multi_list = sc->multi;
     GateParams G = rs->gate_base;
     G.n = b->n;
+    G.reqmask = sc->reqmask;
+    {
+        // one gate CTA per SM; small batches take fewer (each stages the level-1 bitmaps)
+        uint32_t seg = (b->n + 127u) / 128u;
+        if (seg > (uint32_t)rs->sm_count) seg = (uint32_t)rs->sm_count;
+        if (seg > kMaxGateSegments) seg = kMaxGateSegments;
+        G.n_seg = seg ? seg : 1u;
+    }
     for (uint32_t i = 0; i < G.n_fields; ++i) {
         const int f = rs->gate_field[i];
         G.f[i].col = cols[f]->bytes;
         G.f[i].off = cols[f]->offsets;
-        if (!G.f[i].b1) continue;
+        G.f[i].hq = sc->hq[f];
+        G.f[i].hq_cap = (uint32_t)(((size_t)kHitQueuePerRequest * sc->cap_requests) / G.n_seg);
+        G.f[i].hq_count = sc->small + kSmallCounters + 16 + (size_t)f * kMaxGateSegments;
+        G.f[i].overflow = sc->small + kSmallCounters + 8 + f;
         G.f[i].cand_count = sc->small + kSmallCounters + f;
         G.f[i].cand_idx = sc->cand[f][0];
         G.f[i].cand_start = sc->cand[f][1];

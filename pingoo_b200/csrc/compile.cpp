@@ -426,19 +426,19 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
                 return false;
             }
             if (cls == UC_GATED) {
-                // a gram leads to the units whose patterns it came from (bit = unit index among the field's gated units, mod 32)
+                // a gram leads to the units whose patterns it came from (bit = unit index among the field's gated units, mod kGateWidth)
                 std::vector<uint32_t> grams, masks;
                 for (size_t g = 0; g < groups.dfas.size(); ++g)
                     for (int bi : groups.members[g])
-                        for (uint32_t x : gated_grams[bi].grams) { grams.push_back(x); masks.push_back(1u << (g & 31)); }
-                gate_build_tables(grams, masks, &H.gate[f]);
+                        for (uint32_t x : gated_grams[bi].grams) { grams.push_back(x); masks.push_back(1u << (g % kGateWidth[f])); }
+                gate_build_tables(grams, masks, f == F_URL ? kGateMaxLog2 : kGateMaxLog2 - 2, &H.gate[f]);
             }
             for (size_t g = 0; g < groups.dfas.size(); ++g) {
                 Pending pd;
                 pd.dfa = std::move(groups.dfas[g]);
                 pd.field = f;
                 pd.mode = cls == UC_GATED ? UM_CANDIDATES : UM_ALL;
-                pd.gate_bit = (uint32_t)(g & 31);
+                pd.gate_bit = cls == UC_GATED ? (uint32_t)(g % kGateWidth[f]) : 0u;
                 // latch numbering is local to the unit
                 pd.latch_of_event.assign(M.events.size(), 0);
                 int next_latch = 0;

@@ -12,7 +12,7 @@ constexpr int kWild = 256;     // "any byte" symbol in a padded prefix
 constexpr int kPrefix = 5;     // padded prefixes are 5 symbols long: windows m[0..4) and m[1..5)
 constexpr size_t kMaxPrefixes = 4096;
 
-inline bool is_folded(int v) { return !((v & 0x40) && !(v & 0x20)); }
+inline bool is_folded(int v) { return !(v & 0x20); }  // gate_fold clears bit 5
 
 // Enumerates the padded 5-byte prefixes (forward) or suffixes (backward) of a pattern's matches over folded bytes.
 struct Walker {
@@ -99,7 +99,7 @@ struct Walker {
         }
         for (int v = 0; v < 256 && !overflow; ++v) {
             if (!is_folded(v)) continue;
-            const int alt = ((v & 0x60) == 0x60) ? v - 0x20 : -1;  // the other byte folding to v
+            const int alt = v | 0x20;  // the other byte folding to v
             next.clear();
             if (!backward) {
                 for (int c : cur) {
@@ -140,11 +140,11 @@ struct Walker {
     }
 };
 
-// number of concrete grams a 4-symbol sequence expands to (192 folded values per wildcard)
+// number of concrete grams a 4-symbol sequence expands to (128 folded values per wildcard)
 size_t expansion(const std::array<int, 4>& s) {
     size_t n = 1;
     for (int x : s)
-        if (x == kWild) n *= 192;
+        if (x == kWild) n *= 128;
     return n;
 }
 
@@ -288,7 +288,7 @@ bool gate_grams_for_pattern(const Nfa& nfa, int start, size_t cap, std::vector<u
     return true;
 }
 
-void gate_build_tables(const std::vector<uint32_t>& grams, const std::vector<uint32_t>& masks, GateTables* out) {
+void gate_build_tables(const std::vector<uint32_t>& grams, const std::vector<uint32_t>& masks, uint32_t max_log2, GateTables* out) {
     std::vector<std::pair<uint32_t, uint32_t>> gm;
     gm.reserve(grams.size());
     for (size_t i = 0; i < grams.size(); ++i) gm.emplace_back(grams[i], masks[i]);
@@ -304,18 +304,17 @@ void gate_build_tables(const std::vector<uint32_t>& grams, const std::vector<uin
     T.n_grams = (uint32_t)u.size();
     // level 1: two bits per gram in one word; density <= 1/64 -> false-positive rate <= 2.5e-4 per window
     uint32_t k = 12;
-    while (k < kGateMaxLog2 && ((size_t)1 << k) < u.size() * 128) ++k;
+    while (k < max_log2 && k < kGateMaxLog2 && ((size_t)1 << k) < u.size() * 128) ++k;
     T.k1 = k;
     T.b1.assign(((size_t)1 << T.k1) / 32, 0u);
-    const uint32_t sh = 32 - T.k1;
     // level 2: load factor <= 1/2
     T.kt = 4;
     while (((size_t)1 << T.kt) < u.size() * 2) ++T.kt;
     T.slots.assign(((size_t)2 << T.kt), 0u);
     const uint32_t tm = (1u << T.kt) - 1u;
     for (auto& x : u) {
-        const uint32_t g = x.first, h = g * kGateHash1;
-        T.b1[h >> (sh + 5)] |= (1u << ((h >> sh) & 31)) | (1u << ((h >> (sh - 5)) & 31));
+        const uint32_t g = x.first;
+        gate_l1_set(T.b1.data(), T.k1, g);
         uint32_t s = (g * kGateHash2) >> (32 - T.kt);
         while (T.slots[2 * s + 1] != 0) s = (s + 1) & tm;
         T.slots[2 * s] = g;

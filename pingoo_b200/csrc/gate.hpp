@@ -16,8 +16,8 @@
 //       B  = the smaller of  { (any, m[0..3)) padded }  and  { m[1..5) padded }
 //   with "padded" / "any" positions expanded over every folded byte value.  Assertions (^ $ \b) are treated as
 //   always true, which only enlarges the sets.
-// Folding: bytes 0x40-0x5F and 0xC0-0xDF get bit 5 set (upper case -> lower case; a few punctuation marks
-// alias), the same operation the kernel applies to the window: g | ((g & 0x40404040) >> 1).
+// Folding: bit 5 of every byte is cleared (lower case -> upper case; digits and punctuation alias with control bytes
+// that never occur in a request), the same single AND the kernel applies to each word: g & 0xDFDFDFDF.
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -26,12 +26,27 @@
 
 namespace pgw {
 
-constexpr uint32_t kGateHash1 = 0x9E3779B1u, kGateHash2 = 0x85EBCA6Bu;
+// Level-1 hashes (pipe rates measured by tools/microbench_int.cu: IMAD and the ALU ops SHF / LOP3 issue every 2 cycles
+// per scheduler on different pipes, IMAD.HI every 4): the Bloom WORD is chosen by the top bits of the low product
+// g * K (one IMAD + one SHF; a low-byte change of g moves the top bits of the low product a lot, so the 128 grams of a
+// wildcard expansion land in 128 different words), the two BIT positions are the low five bits of the high products
+// hi(g * B) and hi(g * C) (IMAD.HI: no shift needed, a rotate takes its amount mod 32).  Level 2 uses g * kGateHash2.
+constexpr uint32_t kGateHashK = 0x9E3779B1u, kGateHashB = 0x85EBCA6Bu, kGateHashC = 0xC2B2AE35u, kGateHash2 = 0x85EBCA6Bu;
 constexpr uint32_t kGateMaxLog2 = 20;  // largest first-level bitmap: 2^20 bits = 128 KB of shared memory
+constexpr uint32_t kGateFoldMask = 0xDFDFDFDFu;
 
-inline uint32_t gate_fold(uint32_t g) { return g | ((g & 0x40404040u) >> 1); }
+inline uint32_t gate_fold(uint32_t g) { return g & kGateFoldMask; }
+inline uint32_t gate_mulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+// level 1 of a folded gram on bitmap `b1` of 2^k1 bits (k1 >= 12)
+inline bool gate_l1_test(const uint32_t* b1, uint32_t k1, uint32_t g) {
+    const uint32_t word = b1[(g * kGateHashK) >> (32 - (k1 - 5))];
+    return ((word >> (gate_mulhi(g, kGateHashB) & 31)) & (word >> (gate_mulhi(g, kGateHashC) & 31)) & 1u) != 0;
+}
+inline void gate_l1_set(uint32_t* b1, uint32_t k1, uint32_t g) {
+    b1[(g * kGateHashK) >> (32 - (k1 - 5))] |= (1u << (gate_mulhi(g, kGateHashB) & 31)) | (1u << (gate_mulhi(g, kGateHashC) & 31));
+}
 
-// Two levels.  Level 1 (shared memory, probed for every window): a blocked Bloom filter -- the hash selects one
+// Two levels.  Level 1 (shared memory, probed for every window): a blocked Bloom filter -- the hashes select one
 // 32-bit word and two bit positions in it, both must be set (false-positive rate = density^2, a few 1e-4).
 // Level 2 (global memory, probed only for level-1 survivors): an exact open-addressing table folded gram -> mask of
 // the field's gated scan units whose patterns contain the gram, so a candidate is only walked by those units.
@@ -45,9 +60,7 @@ struct GateTables {
     // unit mask of the window (0: not a candidate window)
     uint32_t probe(uint32_t window_le) const {
         const uint32_t g = gate_fold(window_le);
-        const uint32_t h = g * kGateHash1, sh = 32 - k1;
-        const uint32_t word = b1[h >> (sh + 5)];
-        if (!((word >> ((h >> sh) & 31)) & (word >> ((h >> (sh - 5)) & 31)) & 1u)) return 0;
+        if (!gate_l1_test(b1.data(), k1, g)) return 0;
         const uint32_t tm = (1u << kt) - 1u;
         for (uint32_t s = (g * kGateHash2) >> (32 - kt);; s = (s + 1) & tm) {
             if (slots[2 * s + 1] == 0) return 0;
@@ -65,6 +78,7 @@ bool pattern_is_start_anchored(const Nfa& nfa, int start);
 bool gate_grams_for_pattern(const Nfa& nfa, int start, size_t cap, std::vector<uint32_t>* out);
 
 // `grams[i]` belongs to the units in `masks[i]` (duplicates are merged by OR)
-void gate_build_tables(const std::vector<uint32_t>& grams, const std::vector<uint32_t>& masks, GateTables* out);
+// `max_log2`: largest level-1 bitmap the field may use (all gated fields' bitmaps are resident in shared memory together)
+void gate_build_tables(const std::vector<uint32_t>& grams, const std::vector<uint32_t>& masks, uint32_t max_log2, GateTables* out);
 
 }  // namespace pgw

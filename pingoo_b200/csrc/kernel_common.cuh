@@ -46,6 +46,35 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint8_t* p) {
     return r;
 }
 
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32_v(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint16_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
 // ---- what a scan reports ----
 __device__ __forceinline__ void red_or(uint32_t* addr, uint32_t v) { asm volatile("red.global.or.b32 [%0], %1;" ::"l"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void red_max(uint32_t* addr, uint32_t v) { asm volatile("red.global.max.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory"); }
@@ -63,21 +92,26 @@ __device__ __forceinline__ void fire_atom(const Sink& k, uint32_t at) {
     red_max(k.inf + 1, 0x4000u - at);
 }
 
-// events of CSR row `ci` applied to a request's sink; true if all of them were plain FIREs
-__device__ __forceinline__ bool fs_fire_list(const uint32_t* idx, const uint32_t* events, uint32_t ci, const Sink& row, uint32_t* latch) {
+// events of CSR row `ci` applied through `fire(atom)`; true if all of them were plain FIREs
+template <class Fire>
+__device__ __forceinline__ bool fs_apply_list(const uint32_t* idx, const uint32_t* events, uint32_t ci, Fire&& fire, uint32_t* latch) {
     uint32_t a = __ldg(idx + ci), b = __ldg(idx + ci + 1);
     uint32_t l = *latch;
     bool pure = true;
     for (uint32_t i = a; i < b; ++i) {
         const uint32_t e = __ldg(events + i);
         const uint32_t kind = e >> kEvKindShift, lb = 1u << ((e >> kEvLatchShift) & 31u), at = e & kEvAtomMask;
-        if (kind == 0u || (kind == 1u && (l & lb))) fire_atom(row, at);
+        if (kind == 0u || (kind == 1u && (l & lb))) fire(at);
         else if (kind == 2u) l &= ~lb;
         else if (kind == 3u) l |= lb;
         pure &= kind == 0u;
     }
     *latch = l;
     return pure;
+}
+// ... to a request's sink in global memory (the scan kernel)
+__device__ __forceinline__ bool fs_fire_list(const uint32_t* idx, const uint32_t* events, uint32_t ci, const Sink& row, uint32_t* latch) {
+    return fs_apply_list(idx, events, ci, [&](uint32_t at) { fire_atom(row, at); }, latch);
 }
 
 __device__ __forceinline__ bool eval_rule(const uint16_t* __restrict__ code, uint32_t a, uint32_t b, const uint32_t* row) {
@@ -117,18 +151,44 @@ __device__ __forceinline__ uint32_t lpm_lookup(const KParams& p, const uint8_t* 
     return __ldg(p.v6_leaf + l);
 }
 
-// Per-request predicates outside the byte scan + the verdict (http_listener.rs:196-264).
+// One request's field walked on a small early-exit DFA whose whole table is in shared memory at `img` (class map,
+// rows, acc1, end1: the unit image of compile.hpp): start-anchored patterns (starts_with, ==, ^...) are decided within
+// the first few bytes, the walk stops at an absorbing state.  Fired atoms are reported through `fire(atom)`.
+template <class Fire>
+__device__ __forceinline__ void prefix_walk(const KParams& p, const UnitDesc& ud, uint32_t img, const uint8_t* __restrict__ col, uint32_t s, uint32_t e,
+                                            Fire&& fire) {
+    const uint32_t C2 = 2u * ud.n_classes, acclo = ud.acc_lo, abs0 = ud.abs0, abs1 = ud.abs1;
+    const uint32_t hot = img + ud.hot_off;
+    uint32_t st = ud.start_state, latch = 0u;
+#pragma unroll 1
+    for (uint32_t pos = s; pos < e; ++pos) {
+        const uint32_t cls = lds_u8(img + (uint32_t)__ldg(col + pos));
+        st = lds_u16(hot + st * C2 + 2u * cls);
+        if (st >= acclo) {
+            const uint32_t a1 = lds_u16(img + ud.acc1_off + 2u * (st - acclo));
+            if (a1 != 0xFFFFu) fire(a1);
+            else fs_apply_list(p.acc_idx, p.acc_events, ud.acc_base + st - acclo, fire, &latch);
+        }
+        if (st == abs0 || st == abs1) break;  // absorbing: nothing can change any more
+    }
+    const uint32_t e1 = lds_u16(img + ud.end1_off + 2u * st);
+    if (e1 != 0xFFFEu) {
+        if (e1 != 0xFFFFu) fire(e1);
+        else if (ud.end_any) fs_apply_list(p.end_idx, p.end_events, ud.end_base + st, fire, &latch);
+    }
+}
+
+// Per-request work outside the gate and the scan + the verdict (http_listener.rs:196-264): the small early-exit units
+// (KParams::pdesc, tables in shared memory at `a_img`), end-of-field events of empty fields, the integer / list /
+// country predicates, the gates, the verdict and the service.
 // The scan left, per request, two info words (KParams::info) and the bits of the fired atoms in the request's bitmap
 // row.  Called by all 32 lanes of a converged warp (`valid` false for lanes past the end of the batch, which shadow the
 // last request without storing anything).
 //   no atom true            -> the precomputed verdict `vclean` (the row is never read)
 //   one distinct atom true  -> the tabulated verdict `v1z[atom]`
-//   otherwise               -> the row is completed and the candidate rules are evaluated; requests of the warp that
-//                              deviate from the expected atom vector in the same way are evaluated once (verdict and
-//                              service are functions of the deviation and of `captcha_verified` alone), shared by shuffle.
 //   otherwise               -> the row is completed and the request is appended to the multi list (waf_multi_kernel)
 // Whatever the scan or this function wrote to the row / info words is written back to zero (the scratch invariant).
-__device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, bool valid) {
+__device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, bool valid, uint32_t a_img) {
     const uint32_t Aw = p.atom_words;
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t flags = p.flags ? p.flags[r] : 0u;
@@ -155,9 +215,16 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, b
     if (p.asn) asn = p.asn[r];
     if (p.country) country = p.country[r];
 
-    // atoms that are true outside the byte scan: end-of-field events of EMPTY fields (they never reach the scan) and
-    // the integer / set predicates.  Walked twice at most: once to count, once more to complete the row.
+    // atoms that become true here, outside the scan kernel
     auto extras = [&](auto&& fn) {
+        // small early-exit units: one walk over the first bytes of the field
+        for (uint32_t k = 0; k < p.n_prefix; ++k) {
+            const UnitDesc& ud = p.pdesc[k];
+            const uint32_t* o = p.off[ud.field] + r;
+            const uint32_t s0 = o[0], e0 = o[1];
+            if (e0 > s0) prefix_walk(p, ud, a_img + p.prefix_img[k], p.col[ud.field], s0, e0, fn);
+        }
+        // end-of-field events of EMPTY fields (they reach neither the scan nor a prefix walk)
         for (uint32_t k = 0; k < p.n_start_end; ++k) {
             const UnitDesc& ud = p.units[p.start_end_unit[k]];
             const uint32_t* o = p.off[ud.field] + r;
@@ -224,17 +291,30 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, b
 
     const uint2 inf = *reinterpret_cast<const uint2*>(p.info + 2u * (size_t)r);
     uint32_t amax = inf.x, binv = inf.y;  // largest true atom + 1 (0: none), 0x4000 - smallest true atom
-    bool had_extra = false;
+    // the atoms found here, packed 16 bits each (up to four; a request with more walks `extras` a second time)
+    uint64_t xl = 0;
+    uint32_t nx = 0, xlast = 0xFFFFFFFFu;
     extras([&](uint32_t a) {
+        if (a == xlast) return;   // a sticky accepting state fires at every byte
+        xlast = a;
         amax = max(amax, a + 1u);
         binv = max(binv, 0x4000u - a);
-        had_extra = true;
+        if (nx < 4u) xl |= (uint64_t)a << (16u * nx);
+        ++nx;
     });
     const bool any_atom = amax != 0u;
     const bool single = any_atom && (amax - 1u == 0x4000u - binv);
     const bool multi = any_atom && !single;
-    if (multi && valid && had_extra)  // complete the row (the scan's bits are in it already)
-        extras([&](uint32_t a) { row[a >> 5] |= 1u << (a & 31); });
+    if (multi && valid && nx) {  // complete the row (the scan's bits are in it already)
+        if (nx <= 4u) {
+            for (uint32_t k = 0; k < nx; ++k) {
+                const uint32_t a = (uint32_t)(xl >> (16u * k)) & 0xFFFFu;
+                row[a >> 5] |= 1u << (a & 31);
+            }
+        } else {
+            extras([&](uint32_t a) { row[a >> 5] |= 1u << (a & 31); });
+        }
+    }
 
     const uint32_t cv = flags & RF_CAPTCHA_VERIFIED;
     uint32_t verdict = V_ALLOW | (kNoRule << 2);
@@ -290,114 +370,62 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, b
     if (p.service) p.service[r] = (uint16_t)(((verdict & 3u) == V_ALLOW && routes) ? svc : kNoService);
 }
 
-// A request with several true atoms, evaluated by one WARP: lane w holds word w of the bitmap row (strided when the row
-// has more than 32 words), the row is staged in shared memory for the rule bytecode, candidate rules are evaluated one
-// per lane.  Deviations from the expected atom vector: none -> v0 / s0, exactly one -> v1[atom] / s1[atom], otherwise
-// the rules that mention a deviating atom plus the ones true by default, first terminal one wins (http_listener.rs:251-264).
-__device__ __forceinline__ void request_multi_warp(const KParams& p, uint32_t r, uint32_t* srow) {
-    const uint32_t Aw = p.atom_words, lane = threadIdx.x & 31u;
-    const uint32_t FULL = 0xFFFFFFFFu;
+// A request with several true atoms, evaluated by one THREAD of waf_multi_kernel (the work is a chain of dependent
+// look-ups -- deviating atom -> its rules -> their bytecode -- so what counts is how many requests are in flight, not
+// how many lanes share one).  Deviations from the expected atom vector: none -> v0 / s0, exactly one -> v1[atom] /
+// s1[atom], otherwise the rules that mention a deviating atom plus the ones true by default, first terminal one wins
+// (http_listener.rs:251-264).  The bitmap row is read in place and goes back all-zero.
+__device__ __forceinline__ void request_multi_thread(const KParams& p, uint32_t r) {
+    const uint32_t Aw = p.atom_words;
     uint32_t* const row = p.rows + (size_t)r * Aw;
     const uint32_t flags = p.flags ? p.flags[r] : 0u;
     const uint32_t cv = flags & RF_CAPTCHA_VERIFIED, tshift = 2u * cv;
     const bool routes = p.service != nullptr && p.n_rules > p.n_waf_rules;
     uint32_t ndev = 0, dev_atom = 0;
-    __syncwarp();
-    for (uint32_t w = lane; w < Aw; w += 32u) {
-        const uint32_t v = row[w];
-        srow[w] = v;
-        row[w] = 0u;  // scratch goes back all-zero
-        const uint32_t x = (v ^ __ldg(p.expect + w)) & __ldg(p.care + w);
+    for (uint32_t w = 0; w < Aw; ++w) {
+        const uint32_t x = (row[w] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
         if (x) dev_atom = w * 32u + (uint32_t)__ffs(x) - 1u;
         ndev += (uint32_t)__popc(x);
-    }
-    __syncwarp();
-    for (int o = 16; o; o >>= 1) {
-        ndev += __shfl_xor_sync(FULL, ndev, o);
-        dev_atom = max(dev_atom, __shfl_xor_sync(FULL, dev_atom, o));  // meaningful when exactly one bit deviates
     }
     uint32_t verdict, svc;
     if (ndev == 0u) { verdict = p.v0[cv]; svc = p.s0; }
     else if (ndev == 1u) { verdict = __ldg(p.v1 + cv * p.n_atoms + dev_atom); svc = routes ? (uint32_t)__ldg(p.s1 + dev_atom) : kNoService; }
     else {
         uint32_t best = kNoRule, best_svc = kNoRule;
-        // rules that mention a deviating atom: the deviating atoms are visited in a warp-uniform loop (word by word through a
-        // ballot, bit by bit), each atom's rule list is evaluated one rule per lane
-        for (uint32_t w0 = 0; w0 < Aw; w0 += 32u) {
-            const uint32_t w = w0 + lane;
-            const uint32_t xw = w < Aw ? (srow[w] ^ __ldg(p.expect + w)) & __ldg(p.care + w) : 0u;
-            uint32_t wm = __ballot_sync(FULL, xw != 0u);
-            while (wm) {
-                const uint32_t src = __ffs(wm) - 1;
-                wm &= wm - 1;
-                uint32_t x = __shfl_sync(FULL, xw, src);
-                while (x) {
-                    const uint32_t atom = (w0 + src) * 32u + (uint32_t)__ffs(x) - 1u;
-                    x &= x - 1;
-                    const uint32_t i0 = __ldg(p.ar_idx + atom), i1 = __ldg(p.ar_idx + atom + 1);
-                    for (uint32_t i = i0 + lane; i < i1; i += 32u) {
-                        const uint32_t rule = __ldg(p.ar_rules + i);  // WAF rules first, then service routes
-                        if (rule < p.n_waf_rules) {
-                            if (rule >= best || ((__ldg(p.term + rule) >> tshift) & 3u) == 0) continue;
-                            if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), srow)) best = rule;
-                        } else if (routes && rule < best_svc) {
-                            if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), srow)) best_svc = rule;
-                        }
+        for (uint32_t w = 0; w < Aw; ++w) {
+            uint32_t x = (row[w] ^ __ldg(p.expect + w)) & __ldg(p.care + w);
+            while (x) {
+                const uint32_t atom = w * 32u + (uint32_t)__ffs(x) - 1u;
+                x &= x - 1u;
+                const uint32_t i0 = __ldg(p.ar_idx + atom), i1 = __ldg(p.ar_idx + atom + 1);
+                for (uint32_t i = i0; i < i1; ++i) {
+                    const uint32_t rule = __ldg(p.ar_rules + i);  // ascending: WAF rules first, then service routes
+                    if (rule < p.n_waf_rules) {
+                        if (rule >= best || ((__ldg(p.term + rule) >> tshift) & 3u) == 0) continue;
+                        if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row)) best = rule;
+                    } else if (routes && rule < best_svc) {
+                        if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row)) best_svc = rule;
                     }
                 }
             }
         }
-        // rules true by default (ascending): one per lane
-        for (uint32_t i = lane; i < p.n_dflt[cv]; i += 32u) {
+        // rules true by default (ascending): the first one that still holds
+        for (uint32_t i = 0; i < p.n_dflt[cv]; ++i) {
             const uint32_t rule = __ldg(p.dflt[cv] + i);
             if (rule >= best) break;
-            if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), srow)) best = min(best, rule);
+            if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row)) { best = rule; break; }
         }
         if (routes)
-            for (uint32_t i = lane; i < p.n_dflt_services; i += 32u) {
+            for (uint32_t i = 0; i < p.n_dflt_services; ++i) {
                 const uint32_t rule = __ldg(p.dflt_services + i);
                 if (rule >= best_svc) break;
-                if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), srow)) best_svc = min(best_svc, rule);
+                if (eval_rule(p.code, __ldg(p.rule_off + rule), __ldg(p.rule_off + rule + 1), row)) { best_svc = rule; break; }
             }
-        for (int o = 16; o; o >>= 1) {
-            best = min(best, __shfl_xor_sync(FULL, best, o));
-            best_svc = min(best_svc, __shfl_xor_sync(FULL, best_svc, o));
-        }
         verdict = best == kNoRule ? (V_ALLOW | (kNoRule << 2)) : (((__ldg(p.term + best) >> tshift) & 3u) | (best << 2));
         svc = best_svc == kNoRule ? kNoService : best_svc - p.n_waf_rules;
     }
-    if (lane == 0) {
-        p.verdict[r] = verdict;
-        if (p.service) p.service[r] = (uint16_t)(((verdict & 3u) == V_ALLOW && routes) ? svc : kNoService);
-    }
-}
-
-__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
-    uint32_t v;
-    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t v;
-    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_u32_v(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
-    uint16_t v;
-    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
-    return v;
-}
-
-__device__ __forceinline__ void cp_async4(uint32_t saddr, const void* g) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_wait() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    for (uint32_t w = 0; w < Aw; ++w) row[w] = 0u;  // scratch goes back all-zero
+    p.verdict[r] = verdict;
+    if (p.service) p.service[r] = (uint16_t)(((verdict & 3u) == V_ALLOW && routes) ? svc : kNoService);
 }
 

@@ -320,21 +320,29 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
     }
 }
 
-// Verdicts once every unit has been scanned: one thread per request.
-__global__ void __launch_bounds__(256) waf_epilogue_kernel(const __grid_constant__ KParams p) {
+// Verdicts once every unit has been scanned: one thread per request (request_epilogue).  The tables of the small
+// early-exit units it walks are staged into the CTA's shared memory first.
+constexpr int kEpiThreads = 512;
+__global__ void __launch_bounds__(kEpiThreads) waf_epilogue_kernel(const __grid_constant__ KParams p) {
+    extern __shared__ __align__(256) uint8_t esm[];
+    uint8_t* img = esm + ((0u - smem_u32(esm)) & 255u);   // class maps sit on 256-byte boundaries
+    for (uint32_t k = 0; k < p.n_prefix; ++k) {
+        uint4* d = reinterpret_cast<uint4*>(img + p.prefix_img[k]);
+        const uint4* s = reinterpret_cast<const uint4*>(p.images + p.pdesc[k].img_off);
+        for (uint32_t i = threadIdx.x; i < p.pdesc[k].img_bytes / 16u; i += kEpiThreads) d[i] = __ldg(s + i);
+    }
+    __syncthreads();
+    const uint32_t a_img = smem_u32(img);
     // warp-uniform trip count: every lane of a warp goes through request_epilogue together
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < p.n; base += gridDim.x * blockDim.x) {
         const uint32_t rr = base + (threadIdx.x & 31u);
         const bool valid = rr < p.n;
-        request_epilogue(p, valid ? rr : p.n - 1u, valid);
+        request_epilogue(p, valid ? rr : p.n - 1u, valid, a_img);
     }
 }
 
-// Requests with several true atoms (the multi list of the epilogue): one warp per request.
+// Requests with several true atoms (the multi list of the epilogue): one thread per request.
 __global__ void __launch_bounds__(256) waf_multi_kernel(const __grid_constant__ KParams p) {
-    extern __shared__ uint32_t s_rows[];
-    uint32_t* srow = s_rows + (threadIdx.x >> 5) * p.atom_words;
     const uint32_t count = *p.multi_count;
-    const uint32_t warps = gridDim.x * (blockDim.x >> 5), w0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    for (uint32_t i = w0; i < count; i += warps) request_multi_warp(p, p.multi_list[i], srow);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) request_multi_thread(p, p.multi_list[i]);
 }

@@ -82,6 +82,8 @@ const char* waf_configure(int device, size_t* max_smem_optin, int* sm_count) {
     if (e != cudaSuccess) return cudaGetErrorString(e);
     e = cudaFuncSetAttribute(waf_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*max_smem_optin);
     if (e != cudaSuccess) return cudaGetErrorString(e);
+    e = cudaFuncSetAttribute(waf_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(waf_prefix_budget() + 512));
+    if (e != cudaSuccess) return cudaGetErrorString(e);
     return nullptr;
 }
 
@@ -94,13 +96,13 @@ size_t waf_scan_smem_bytes(uint32_t max_image_bytes) { return 256 + kFsFront + r
 size_t waf_gate_smem_bytes(const GateParams& g) {
     size_t m = 0;
     for (uint32_t i = 0; i < g.n_fields; ++i) {
-        size_t b = g.f[i].b1 ? ((size_t)1 << g.f[i].k1) / 8 : 0;
-        if (b > m) m = b;
+        const size_t end = g.f[i].bloom_off + (((size_t)1 << g.f[i].k1) / 8);
+        if (end > m) m = end;
     }
-    return m + g.image_area + (kGateThreads / 32) * kGateWarpSmem + 256;
+    return kGateCtrBytes + m + 128;
 }
 
-size_t waf_gate_prefix_budget() { return 48u << 10; }
+size_t waf_prefix_budget() { return 64u << 10; }
 
 const char* waf_batch_launch(KParams& p, GateParams& g, const UnitDesc* all_units, uint32_t* small, uint32_t small_words, int sm_count,
                              size_t scan_smem, size_t gate_smem, void* stream, cudaEvent_t* ev, uint32_t* launches) {
@@ -111,19 +113,30 @@ const char* waf_batch_launch(KParams& p, GateParams& g, const UnitDesc* all_unit
     if (e != cudaSuccess) return cudaGetErrorString(e);
     if (ev) cudaEventRecord(ev[0], s);
     if (g.n_fields) {
-        // tiles of 32 requests, one per warp at a time
-        const uint32_t tiles = (p.n + 31u) / 32u, want = (tiles + kGateThreads / 32 - 1) / (kGateThreads / 32);
-        const int grid = (int)(want < (uint32_t)sm_count ? want : (uint32_t)sm_count);
-        waf_gate_kernel<<<grid, kGateThreads, gate_smem, s>>>(g, p);
+        e = cudaMemsetAsync(g.reqmask, 0, (size_t)p.n * 4, s);
+        if (e != cudaSuccess) return cudaGetErrorString(e);
+        // flat stream over the gated columns: one CTA per SM (g.n_seg, fixed by the caller with the hit-queue layout)
+        waf_gate_kernel<<<(int)g.n_seg, kGateThreads, gate_smem, s>>>(g);
         e = cudaGetLastError();
         if (e != cudaSuccess) return cudaGetErrorString(e);
-        ++nl;
+        waf_gate_resolve_kernel<<<dim3(g.n_seg * kResolveParts, g.n_fields), kResolveThreads, 0, s>>>(g);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cudaGetErrorString(e);
+        uint32_t fb = (p.n + 255u) / 256u;
+        if (fb > (uint32_t)sm_count * 8u) fb = (uint32_t)sm_count * 8u;
+        waf_gate_finalize_kernel<<<dim3(fb, g.n_fields), 256, 0, s>>>(g);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cudaGetErrorString(e);
+        nl += 3;
     }
     if (ev) cudaEventRecord(ev[1], s);
     for (uint32_t ub = 0; ub < p.n_units_total; ub += kMaxConstUnits) {
         p.unit_base = ub;
         p.n_units = p.n_units_total - ub < kMaxConstUnits ? p.n_units_total - ub : kMaxConstUnits;
         memcpy(p.udesc, all_units + ub, p.n_units * sizeof(UnitDesc));
+        bool any = false;
+        for (uint32_t u = 0; u < p.n_units; ++u) any |= p.udesc[u].mode != UM_PREPASS;
+        if (!any) continue;   // every unit of this group is walked by the epilogue kernel
         const uint32_t want = (p.n + kFsThreads - 1) / kFsThreads;
         const int grid = (int)(want < (uint32_t)sm_count ? want : (uint32_t)sm_count);
         waf_field_scan_kernel<<<grid, kFsThreads, scan_smem, s>>>(p);
@@ -132,16 +145,18 @@ const char* waf_batch_launch(KParams& p, GateParams& g, const UnitDesc* all_unit
         ++nl;
     }
     if (ev) cudaEventRecord(ev[2], s);
-    int blocks = (int)((p.n + 255) / 256);
-    if (blocks > sm_count * 8) blocks = sm_count * 8;
-    waf_epilogue_kernel<<<blocks, 256, 0, s>>>(p);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return cudaGetErrorString(e);
-    ++nl;
+    {
+        uint32_t blocks = (p.n + kEpiThreads - 1) / kEpiThreads;
+        if (blocks > (uint32_t)sm_count * 4u) blocks = (uint32_t)sm_count * 4u;
+        waf_epilogue_kernel<<<(int)blocks, kEpiThreads, p.prefix_area + 256, s>>>(p);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cudaGetErrorString(e);
+        ++nl;
+    }
     {
         // at most a few per cent of the requests; sized for the machine, the kernel reads the count from device memory
         const int mb = sm_count * 8;
-        waf_multi_kernel<<<mb, 256, 8 * (size_t)p.atom_words * 4, s>>>(p);
+        waf_multi_kernel<<<mb, 256, 0, s>>>(p);
         e = cudaGetLastError();
         if (e != cudaSuccess) return cudaGetErrorString(e);
         ++nl;

@@ -10,8 +10,8 @@ namespace pgw {
 constexpr uint32_t kMaxConstNs = 16;
 constexpr uint32_t kMaxConstUnits = 64;  // scan units per scan-kernel launch (their descriptors ride in the parameter bank);
                                          // rule sets with more units are scanned by several launches
-constexpr uint32_t kMaxGateFields = 5;   // fields the pre-pass kernel visits (gate bitmaps and / or small early-exit units)
-constexpr uint32_t kMaxPrefixUnits = 2;  // early-exit units of one field walked inside the pre-pass kernel
+constexpr uint32_t kMaxGateFields = 3;   // gated fields: url, user_agent, path
+constexpr uint32_t kMaxPrefixUnits = 8;  // small early-exit units walked inside the per-request (epilogue) kernel
 
 struct KParams {
     // ---- batch (device pointers, SoA) ----
@@ -95,37 +95,43 @@ struct KParams {
     uint32_t lpm_present;
     uint32_t geo_loaded;
     uint32_t need_lpm;          // any ip-set atom, or geo columns needed and resolved on device
+    // ---- small early-exit units walked by the epilogue kernel (UM_PREPASS): descriptors here, tables in its shared memory ----
+    uint32_t n_prefix;
+    uint32_t prefix_area;                     // bytes of shared memory their images take (multiple of 256)
+    uint32_t prefix_img[kMaxPrefixUnits];     // offset of unit k's image inside that area
+    UnitDesc pdesc[kMaxPrefixUnits];
     // ---- unit descriptors of this launch in the parameter (constant) bank: the scan kernel reads them with a
     //      warp-uniform index, which keeps the per-unit parameters out of the vector register file ----
     UnitDesc udesc[kMaxConstUnits];
     NsAtom nsd[kMaxConstNs];    // likewise for the first non-scan atoms (read by every request's epilogue)
 };
 
-// candidate gate (kernel_gate.cuh)
+// candidate gate (kernel_gate.cuh): one entry per gated field
 struct GateField {
     const uint8_t* col;      // field bytes
     const uint32_t* off;     // n + 1 offsets
-    const uint32_t* b1;      // level 1: blocked Bloom filter (2^k1 bits), global memory copy (staged into shared memory);
-                             // null: the field has no gate (it is visited for its prefix units only)
+    const uint32_t* b1;      // level 1: blocked Bloom filter (2^k1 bits), global memory copy (staged into shared memory)
     const uint32_t* slots;   // level 2: exact table, 2^kt slots of {gram, unit mask}
     uint32_t k1, kt;
+    uint32_t bloom_off;      // byte offset of the field's bitmap in the gate kernel's shared memory (all fields resident)
+    uint32_t mask_shift, mask_bits;  // the field's bits in a request's candidate word (kGateShift / kGateWidth)
+    uint32_t* hq;            // hit queue: indices of 16-byte chunks with a level-1 hit, one segment of hq_cap entries per gate CTA
+    uint32_t* hq_count;      // entries per segment
+    uint32_t hq_cap;
+    uint32_t* overflow;      // set when a segment overflowed: every request becomes a candidate
     uint32_t* cand_count;    // candidate list of the field: one counter ...
     uint32_t* cand_idx;      // ... and request index / field start / field end / unit mask per candidate
     uint32_t* cand_start;
     uint32_t* cand_end;
     uint32_t* cand_mask;
-    // small early-exit units of the field (start-anchored patterns): walked here, one lane per request, right after the
-    // tile's bytes went through the cache, instead of costing a pass of the scan kernel each
-    uint32_t n_prefix;
-    uint32_t prefix_img[kMaxPrefixUnits];   // offset of the unit's image inside the kernel's image area (shared memory)
-    UnitDesc prefix[kMaxPrefixUnits];
 };
 
 struct GateParams {
     GateField f[kMaxGateFields];
     uint32_t n_fields;
     uint32_t n;              // requests
-    uint32_t image_area;     // bytes of shared memory reserved for prefix-unit images (multiple of 256)
+    uint32_t n_seg;          // hit-queue segments = CTAs of the gate kernel
+    uint32_t* reqmask;       // one candidate word per request (zeroed before each batch)
 };
 
 // host-callable wrappers (kernels.cu)
@@ -133,11 +139,11 @@ size_t waf_scan_smem_bytes(uint32_t max_image_bytes);
 size_t waf_scan_image_budget(size_t max_smem_optin);  // bytes a unit image may take
 int waf_scan_threads();
 size_t waf_gate_smem_bytes(const GateParams& g);
-size_t waf_gate_prefix_budget();  // shared memory the prefix-unit images of one field may take
-// One batch: [gate] -> scan (one launch per kMaxConstUnits units) -> epilogue, all on `stream`.
-// `all_units` = the program's unit descriptors (host copy); `small` = the block of claim counters and candidate counters
-// to zero first (`small_words` words).  `ev` (optional): four events recorded before the pre-pass kernel, after it, after the
-// scan launches and after the epilogue + multi kernels.
+size_t waf_prefix_budget();  // shared memory the images of all early-exit units walked by the epilogue kernel may take
+// One batch: [gate -> resolve -> finalize] -> scan (one launch per kMaxConstUnits units) -> epilogue -> multi, all on
+// `stream`.  `all_units` = the program's unit descriptors (host copy); `small` = the block of claim counters, candidate
+// counters and hit-queue counters to zero first (`small_words` words).  `ev` (optional): four events recorded before the
+// gate kernels, after them, after the scan launches and after the epilogue + multi kernels.
 const char* waf_batch_launch(KParams& p, GateParams& g, const UnitDesc* all_units, uint32_t* small, uint32_t small_words, int sm_count,
                              size_t scan_smem, size_t gate_smem, void* stream, cudaEvent_t* ev = nullptr, uint32_t* launches = nullptr);
 const char* client_id_launch(const uint8_t* ip, const uint8_t* is_v6, const uint8_t* ua_bytes, const uint32_t* ua_off, const uint8_t* host_bytes,

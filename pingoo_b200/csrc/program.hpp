@@ -28,6 +28,11 @@ enum ReqFlags : uint8_t {
 constexpr uint32_t kEvKindShift = 30, kEvLatchShift = 24, kEvAtomMask = 0x3FFF;
 constexpr uint32_t kMaxLatchesPerUnit = 32;
 
+// Candidate masks: one 32-bit word per request holds, for each gated field, the set of the field's gated scan units some
+// gram hit asks for (unit g of the field -> bit kGateShift[field] + g % kGateWidth[field]).  Index = Field enum.
+constexpr uint32_t kGateShift[5] = {0, 0, 24, 0, 16};
+constexpr uint32_t kGateWidth[5] = {0, 16, 8, 0, 8};   // only url, path and user_agent are gated
+
 // rule bytecode (uint16): 0x0000..0x3FFF push atom, else opcode
 enum RuleOp : uint16_t { OP_NOT = 0x4000, OP_AND = 0x4001, OP_OR = 0x4002, OP_PUSH0 = 0x4003, OP_PUSH1 = 0x4004 };
 
@@ -59,14 +64,15 @@ struct UnitDesc {
     uint32_t img_off;      // byte offset of this unit's shared-memory image in the image buffer (256-byte aligned)
     uint32_t img_bytes;    // size of that image: class map (offset 0), hot rows + trap row (hot_off), acc1, end1
     uint32_t start_end;    // 1 if the start state has end-of-field events (empty fields are finished by the epilogue)
-    uint32_t gate_bit;     // UM_CANDIDATES: this unit's bit in a candidate's unit mask
+    uint32_t gate_bit;     // UM_CANDIDATES: this unit's bit in a candidate's unit mask (unit index among the field's gated units % kGateWidth)
 };
 
 // which requests a scan unit walks
 enum UnitMode : uint32_t {
     UM_ALL = 0,        // every request (patterns the gate cannot cover; start-anchored patterns, which finish early)
     UM_CANDIDATES = 1, // only the requests the candidate gate flagged for the unit's field
-    UM_PREPASS = 2     // every request, but inside the pre-pass kernel (small early-exit units; set at finalize, not by the compiler)
+    UM_PREPASS = 2     // every request, but inside the per-request (epilogue) kernel: small early-exit units whose tables fit its
+                       // shared memory next to each other (set at finalize, not by the compiler)
 };
 
 // predicates evaluated once per request outside the byte scan

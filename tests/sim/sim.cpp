@@ -508,10 +508,9 @@ extern "C" void pgwsim_gate_window_stats(void* h, const pgw_batch* b, int f, uin
     for (uint32_t j = 0; j + 4 <= total; j += 2) {
         uint32_t w;
         memcpy(&w, cols[f]->bytes + j, 4);
-        const uint32_t g = gate_fold(w), hh = g * kGateHash1, sh = 32 - G.k1;
-        const uint32_t word = G.b1[hh >> (sh + 5)];
+        const uint32_t g = gate_fold(w);
         out[0]++;
-        if ((word >> ((hh >> sh) & 31)) & (word >> ((hh >> (sh - 5)) & 31)) & 1u) {
+        if (gate_l1_test(G.b1.data(), G.k1, g)) {
             out[1]++;
             if (G.probe(w)) out[2]++;
         }
