@@ -87,16 +87,14 @@ struct Scratch {
     uint32_t* rows = nullptr;
     uint32_t* info = nullptr;
     uint32_t* small = nullptr;       // [0, kSmallCounters): per-unit claim counters; [kSmallCounters, +5): candidate counters; [+5]: multi count;
-                                     // [+8, +13): hit-queue overflow flags per field; [+16 + 256 f, ..): hit-queue segment counts of field f
+                                     // [+8, +13): counters of the gate's "maybe" lists
     uint32_t* multi = nullptr;       // multi list (request indices)
-    uint32_t* cand[5][4] = {};       // per gated field: idx, start, end, unit mask
-    uint32_t* reqmask = nullptr;     // candidate word per request
-    uint32_t* hq[5] = {};            // per gated field: hit queue (kHitQueuePerRequest entries per request of capacity)
+    uint32_t* cand[5][5] = {};       // per gated field: idx, start, end, unit mask; [4] = the "maybe" list (request indices)
+    uint32_t* bitmap[5] = {};        // per gated field: hit bitmap, one bit per 16-byte chunk of the column
 };
 constexpr uint32_t kSmallCounters = 1024;   // scan units a program may have
-constexpr uint32_t kMaxGateSegments = 256;  // CTAs of the gate kernel (one per SM)
-constexpr uint32_t kSmallWords = kSmallCounters + 16 + 5 * kMaxGateSegments;
-constexpr uint32_t kHitQueuePerRequest = 2; // benign traffic queues ~0.2 chunks per request and field; beyond the capacity the gate degrades to "every request is a candidate"
+constexpr uint32_t kSmallWords = kSmallCounters + 16;
+constexpr size_t kHitBitmapBytes = (size_t)32 << 20;  // a column holds less than 4 GiB (32-bit offsets): 2^28 chunks of 16 bytes
 
 struct HostStage {   // device staging of one host-pointer call (pgw_evaluate_batch_host), pooled so that calls may overlap
     Staging cols[5], offs[5], ip, v6, port, asn, country, flags, verdict, service;
@@ -166,7 +164,7 @@ Scratch* scratch_acquire(pgw_ruleset* rs, uint32_t n, cudaStream_t stream, std::
     size_t n_gated = 0;
     for (int f = 0; f < 5; ++f) n_gated += H.gate[f].present ? 1 : 0;
     const size_t rows_b = cap * H.atom_words * 4, dirty_b = cap * 8 + 64, small_b = kSmallWords * 4,
-                 cand_b = (n_gated * (4 + kHitQueuePerRequest) + 2) * cap * 4;
+                 cand_b = (n_gated * 5 + 1) * cap * 4 + n_gated * kHitBitmapBytes;
     const size_t total = rows_b + dirty_b + small_b + cand_b + 1024;
     if (cudaMalloc((void**)&sc->base, total) != cudaSuccess || cudaEventCreateWithFlags(&sc->done, cudaEventDisableTiming) != cudaSuccess) {
         e = std::string("CUDA: scratch allocation failed (") + std::to_string(total >> 20) + " MiB): " + cudaGetErrorString(cudaGetLastError());
@@ -181,11 +179,10 @@ Scratch* scratch_acquire(pgw_ruleset* rs, uint32_t n, cudaStream_t stream, std::
     sc->info = (uint32_t*)q; q += dirty_b;
     sc->small = (uint32_t*)q; q += small_b;
     sc->multi = (uint32_t*)q; q += cap * 4;
-    sc->reqmask = (uint32_t*)q; q += cap * 4;
     for (int f = 0; f < 5; ++f)
         if (H.gate[f].present) {
-            for (int k = 0; k < 4; ++k) { sc->cand[f][k] = (uint32_t*)q; q += cap * 4; }
-            sc->hq[f] = (uint32_t*)q; q += (size_t)kHitQueuePerRequest * cap * 4;
+            for (int k = 0; k < 5; ++k) { sc->cand[f][k] = (uint32_t*)q; q += cap * 4; }
+            sc->bitmap[f] = (uint32_t*)q; q += kHitBitmapBytes;
         }
     sc->cap_requests = cap;
     sc->busy = true;
@@ -375,8 +372,6 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
         gf.kt = H.gate[f].kt;
         gf.bloom_off = (uint32_t)bloom_used;
         bloom_used += ((size_t)1 << gf.k1) / 8;
-        gf.mask_shift = kGateShift[f];
-        gf.mask_bits = (1u << kGateWidth[f]) - 1u;
         rs->gate_field[G.n_fields] = f;
         G.f[G.n_fields++] = gf;
     }
@@ -412,6 +407,7 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     P.sclean = H.sclean;
     P.v1z = (const uint32_t*)chk(M.upload(H.v1z));
     P.s1z = (const uint16_t*)chk(M.upload(H.s1z));
+    P.atom_sig = (const uint64_t*)chk(M.upload(H.atom_sig));
     P.dflt_services = (const uint32_t*)chk(M.upload(H.dflt_services));
     P.n_dflt_services = (uint32_t)H.dflt_services.size();
     P.service = nullptr;
@@ -436,6 +432,7 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
         P.v6_hi = (const uint64_t*)chk(M.upload(H.lpm.v6_hi));
         P.v6_lo = (const uint64_t*)chk(M.upload(H.lpm.v6_lo));
         P.v6_leaf = (const uint32_t*)chk(M.upload(H.lpm.v6_leaf));
+        P.v6_top = (const uint32_t*)chk(M.upload(H.lpm.v6_top));
         P.n_v6 = (uint32_t)H.lpm.v6_leaf.size();
     }
     if (!ok) {
@@ -484,22 +481,13 @@ static int launch_on(pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdict_out,
     P.multi_list = sc->multi;
     GateParams G = rs->gate_base;
     G.n = b->n;
-    G.reqmask = sc->reqmask;
-    {
-        // one gate CTA per SM; small batches take fewer (each stages the level-1 bitmaps)
-        uint32_t seg = (b->n + 127u) / 128u;
-        if (seg > (uint32_t)rs->sm_count) seg = (uint32_t)rs->sm_count;
-        if (seg > kMaxGateSegments) seg = kMaxGateSegments;
-        G.n_seg = seg ? seg : 1u;
-    }
     for (uint32_t i = 0; i < G.n_fields; ++i) {
         const int f = rs->gate_field[i];
         G.f[i].col = cols[f]->bytes;
         G.f[i].off = cols[f]->offsets;
-        G.f[i].hq = sc->hq[f];
-        G.f[i].hq_cap = (uint32_t)(((size_t)kHitQueuePerRequest * sc->cap_requests) / G.n_seg);
-        G.f[i].hq_count = sc->small + kSmallCounters + 16 + (size_t)f * kMaxGateSegments;
-        G.f[i].overflow = sc->small + kSmallCounters + 8 + f;
+        G.f[i].bitmap = sc->bitmap[f];
+        G.f[i].maybe_count = sc->small + kSmallCounters + 8 + f;
+        G.f[i].maybe_idx = sc->cand[f][4];
         G.f[i].cand_count = sc->small + kSmallCounters + f;
         G.f[i].cand_idx = sc->cand[f][0];
         G.f[i].cand_start = sc->cand[f][1];

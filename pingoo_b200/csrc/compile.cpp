@@ -338,6 +338,23 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
         }
     }
 
+    // Two true atoms, the second most common case after none and one: when no rule mentions both and neither is mentioned
+    // by a rule that is true on the all-false vector, the rules true under {a, b} are exactly those true under {a} alone or
+    // {b} alone, so the verdict is the earlier of v1z[a] and v1z[b].  The device tests "no common rule" conservatively on
+    // 64-bit signatures (one bit per rule, hashed); an atom a zero-true rule mentions gets an all-ones signature.
+    {
+        std::vector<uint8_t> zeros(H.n_atoms, 0);
+        H.atom_sig.assign(H.n_atoms, 0);
+        for (uint32_t a = 0; a < H.n_atoms; ++a)
+            for (uint32_t r : atom_rules[a]) {
+                H.atom_sig[a] |= 1ull << ((r * 0x9E3779B97F4A7C15ull) >> 58);
+                if (M.pool.eval(M.rules[r].formula, zeros)) H.atom_sig[a] = ~0ull;
+            }
+        for (uint32_t a = 0; a < H.n_atoms; ++a)
+            for (uint32_t r : atom_rules[a])
+                if (M.pool.eval(M.rules[r].formula, zeros)) H.atom_sig[a] = ~0ull;
+    }
+
     // ---- scan units: DFA groups per field ------------------------------------------
     // The string atoms of a field fall into three classes:
     //   anchored  every triggering pattern is tied to the start of the field (starts_with, ==, ^...): decided by a prefix,

@@ -27,6 +27,7 @@ struct LpmTables {
     // IPv6: sorted, disjoint, covering ranges; range i = [start_i, start_{i+1})
     std::vector<uint64_t> v6_hi, v6_lo;
     std::vector<uint32_t> v6_leaf;
+    std::vector<uint32_t> v6_top;   // [65537]: index on the first 16 address bits (lpm.cpp)
 };
 
 struct HostProgram {
@@ -43,6 +44,7 @@ struct HostProgram {
     uint32_t ns_begin[N_INT_FEATS + 2] = {0};  // group g = ns_atoms[ns_begin[g], ns_begin[g + 1]); group N_INT_FEATS = the sets
     // quick reject per integer feature: lo <= x <= hi and (x < vmin or x > vmax) => every predicate on the feature is false
     int64_t ns_lo[N_INT_FEATS], ns_hi[N_INT_FEATS], ns_vmin[N_INT_FEATS], ns_vmax[N_INT_FEATS];
+    std::vector<uint64_t> atom_sig;          // per atom: hashed set of the rules that mention it (all ones: never pair-independent)
     std::vector<uint16_t> code;
     std::vector<uint32_t> rule_off;  // n_rules + 1
     std::vector<uint8_t> term;       // per rule: terminal action for cv=0 (bits 0-1) and cv=1 (bits 2-3)

@@ -139,8 +139,9 @@ __device__ __forceinline__ uint32_t lpm_lookup(const KParams& p, const uint8_t* 
     const uint32_t* w = reinterpret_cast<const uint32_t*>(ip16);
     uint64_t hi = ((uint64_t)__byte_perm(w[0], 0, 0x0123) << 32) | __byte_perm(w[1], 0, 0x0123);
     uint64_t lo = ((uint64_t)__byte_perm(w[2], 0, 0x0123) << 32) | __byte_perm(w[3], 0, 0x0123);
-    // last range whose start <= (hi,lo); range 0 starts at 0
-    uint32_t l = 0, r = p.n_v6;
+    // last range whose start <= (hi,lo), searched inside the address's 16-bit bucket (lpm.cpp: v6_top)
+    const uint32_t t = (uint32_t)(hi >> 48);
+    uint32_t l = __ldg(p.v6_top + t), r = __ldg(p.v6_top + t + 1u) + 1u;
     while (r - l > 1) {
         uint32_t m = (l + r) >> 1;
         uint64_t mh = __ldg(p.v6_hi + m), ml = __ldg(p.v6_lo + m);
@@ -191,7 +192,25 @@ __device__ __forceinline__ void prefix_walk(const KParams& p, const UnitDesc& ud
 __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, bool valid, uint32_t a_img) {
     const uint32_t Aw = p.atom_words;
     const uint32_t FULL = 0xFFFFFFFFu;
+    // everything that does not depend on another load is requested first: the flags, the scan's info words, and the
+    // extents of the fields the early-exit units walk, whose first bytes are then prefetched into L1 -- the walks further
+    // down would otherwise each wait for DRAM in turn (offset -> first byte -> ...)
     const uint32_t flags = p.flags ? p.flags[r] : 0u;
+    const uint2 inf = *reinterpret_cast<const uint2*>(p.info + 2u * (size_t)r);
+    constexpr uint32_t kPre = 4;   // units whose extents are kept in registers (a program rarely has more)
+    uint32_t ps[kPre], pe[kPre];
+#pragma unroll
+    for (uint32_t k = 0; k < kPre; ++k) {
+        ps[k] = pe[k] = 0u;
+        if (k < p.n_prefix) {
+            const uint32_t* o = p.off[p.pdesc[k].field] + r;
+            ps[k] = o[0];
+            pe[k] = o[1];
+        }
+    }
+#pragma unroll
+    for (uint32_t k = 0; k < kPre; ++k)
+        if (k < p.n_prefix && pe[k] > ps[k]) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.col[p.pdesc[k].field] + ps[k]));
     uint32_t* const row = p.rows + (size_t)r * Aw;
     int64_t asn = 0;
     uint32_t country = (uint32_t)'X' | ((uint32_t)'X' << 8);
@@ -218,7 +237,10 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, b
     // atoms that become true here, outside the scan kernel
     auto extras = [&](auto&& fn) {
         // small early-exit units: one walk over the first bytes of the field
-        for (uint32_t k = 0; k < p.n_prefix; ++k) {
+#pragma unroll
+        for (uint32_t k = 0; k < kPre; ++k)
+            if (k < p.n_prefix && pe[k] > ps[k]) prefix_walk(p, p.pdesc[k], a_img + p.prefix_img[k], p.col[p.pdesc[k].field], ps[k], pe[k], fn);
+        for (uint32_t k = kPre; k < p.n_prefix; ++k) {
             const UnitDesc& ud = p.pdesc[k];
             const uint32_t* o = p.off[ud.field] + r;
             const uint32_t s0 = o[0], e0 = o[1];
@@ -289,7 +311,6 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, b
         }
     };
 
-    const uint2 inf = *reinterpret_cast<const uint2*>(p.info + 2u * (size_t)r);
     uint32_t amax = inf.x, binv = inf.y;  // largest true atom + 1 (0: none), 0x4000 - smallest true atom
     // the atoms found here, packed 16 bits each (up to four; a request with more walks `extras` a second time)
     uint64_t xl = 0;
@@ -305,7 +326,26 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, b
     const bool any_atom = amax != 0u;
     const bool single = any_atom && (amax - 1u == 0x4000u - binv);
     const bool multi = any_atom && !single;
-    if (multi && valid && nx) {  // complete the row (the scan's bits are in it already)
+    // exactly two distinct true atoms (the smallest and the largest) whose rule sets are disjoint: their single-atom
+    // table entries combine (compile.cpp: atom_sig), no rule is evaluated
+    bool pair = false;
+    const uint32_t a_lo = 0x4000u - binv, a_hi = amax - 1u;
+    if (multi && nx <= 4u) {
+        pair = true;
+        for (uint32_t k = 0; k < nx; ++k) {
+            const uint32_t a = (uint32_t)(xl >> (16u * k)) & 0xFFFFu;
+            pair &= a == a_lo || a == a_hi;
+        }
+        if (pair && inf.x != 0u)   // atoms the scan fired: their bits are in the row
+            for (uint32_t w = 0; w < Aw; ++w) {
+                uint32_t v = row[w];
+                if (w == (a_lo >> 5)) v &= ~(1u << (a_lo & 31));
+                if (w == (a_hi >> 5)) v &= ~(1u << (a_hi & 31));
+                if (v) { pair = false; break; }
+            }
+        if (pair) pair = (__ldg(p.atom_sig + a_lo) & __ldg(p.atom_sig + a_hi)) == 0ull;
+    }
+    if (multi && !pair && valid && nx) {  // complete the row (the scan's bits are in it already)
         if (nx <= 4u) {
             for (uint32_t k = 0; k < nx; ++k) {
                 const uint32_t a = (uint32_t)(xl >> (16u * k)) & 0xFFFFu;
@@ -329,7 +369,8 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, b
     if (!decided) {
         bool bypass = flags & RF_BYPASS;
         if (p.eval_gates && p.gate_atom >= 0) {
-            if (single) bypass |= amax - 1u == (uint32_t)p.gate_atom;
+            if (single) bypass |= a_hi == (uint32_t)p.gate_atom;
+            else if (pair) bypass |= a_lo == (uint32_t)p.gate_atom || a_hi == (uint32_t)p.gate_atom;
             else if (multi) bypass |= (row[p.gate_atom >> 5] >> (p.gate_atom & 31)) & 1u;
         }
         if (bypass) { verdict = V_BYPASS | (kNoRule << 2); decided = true; }
@@ -340,8 +381,15 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, b
     uint32_t svc = kNoService;
     if (!decided && !any_atom) { verdict = p.vclean[cv]; svc = p.sclean; decided = true; }
     if (!decided && single) {
-        verdict = __ldg(p.v1z + cv * p.n_atoms + (amax - 1u));
-        svc = routes ? (uint32_t)__ldg(p.s1z + (amax - 1u)) : kNoService;
+        verdict = __ldg(p.v1z + cv * p.n_atoms + a_hi);
+        svc = routes ? (uint32_t)__ldg(p.s1z + a_hi) : kNoService;
+        decided = true;
+    }
+    if (!decided && pair) {
+        // first match over the union of the two rule sets: the entry with the smaller rule index (kNoRule is the largest)
+        const uint32_t va = __ldg(p.v1z + cv * p.n_atoms + a_lo), vb = __ldg(p.v1z + cv * p.n_atoms + a_hi);
+        verdict = (va >> 2) <= (vb >> 2) ? va : vb;
+        svc = routes ? min((uint32_t)__ldg(p.s1z + a_lo), (uint32_t)__ldg(p.s1z + a_hi)) : kNoService;
         decided = true;
     }
     // several atoms and no gate decided: the request goes to the multi list (one ballot + one atomicAdd per warp)

@@ -86,14 +86,66 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
-    // CTAs start on different units (and wrap around), so that the latency tails of the units -- a long field is walked
-    // by one lane, byte after byte -- overlap instead of adding up; a unit whose work has all been claimed is skipped
-    uint32_t staged = 0;
+    // Plan: every CTA computes the same assignment of CTAs to units from the units' work (entries x mean field length,
+    // known on the device only: candidate counts): each unit with work gets one CTA plus a share of the rest in
+    // proportion to its work, CTA b's HOME unit follows from the cumulative shares.  A CTA stages its home unit's image
+    // once and works there until the unit's entries are all claimed; afterwards it goes round the other units and
+    // joins one only if a worthwhile amount of work is left there (or nobody is at home).
+    constexpr uint32_t kJoinMin = 4096;
     volatile uint32_t* s_skip = reinterpret_cast<volatile uint32_t*>(s_img + 16);
+    volatile uint32_t* s_plan = reinterpret_cast<volatile uint32_t*>(s_img + 20);   // [0] home unit, [1..2] units that have a home CTA
+    if (tid == 0) {
+        uint64_t work[kMaxConstUnits];
+        uint64_t total = 0;
+        uint32_t k = 0;
+        for (uint32_t u = 0; u < p.n_units; ++u) {
+            const UnitDesc& d = p.udesc[u];
+            work[u] = 0;
+            if (d.mode == UM_PREPASS) continue;
+            const uint32_t N = d.mode == UM_CANDIDATES ? __ldg(p.cand_count[d.field]) : p.n;
+            if (!N) continue;
+            const uint64_t bytes = (uint64_t)(__ldg(p.off[d.field] + p.n) - __ldg(p.off[d.field]));
+            work[u] = (uint64_t)N * bytes / p.n + N;
+            total += work[u];
+            ++k;
+        }
+        uint32_t home = 0, mask_lo = 0, mask_hi = 0;
+        if (k) {
+            const uint32_t G = gridDim.x, spare = G > k ? G - k : 0u;
+            // shares: one CTA each (while CTAs last), the spare ones in proportion; what rounding leaves goes to the largest unit
+            uint32_t given = 0, big = 0;
+            uint32_t share[kMaxConstUnits];
+            uint32_t seen = 0;
+            for (uint32_t u = 0; u < p.n_units; ++u) {
+                share[u] = 0;
+                if (!work[u]) continue;
+                if (seen < G) share[u] = 1u + (uint32_t)((uint64_t)spare * work[u] / total);
+                ++seen;
+                given += share[u];
+                if (work[u] > work[big] || !work[big]) big = u;
+            }
+            if (given < G) share[big] += G - given;
+            uint32_t cum = 0;
+            bool placed = false;
+            for (uint32_t u = 0; u < p.n_units; ++u) {
+                if (!share[u]) continue;
+                if (u < 32u) mask_lo |= 1u << u; else mask_hi |= 1u << (u - 32u);
+                if (!placed && blockIdx.x < cum + share[u]) { home = u; placed = true; }
+                cum += share[u];
+            }
+            if (!placed) home = blockIdx.x % p.n_units;
+        }
+        s_plan[0] = home;
+        s_plan[1] = mask_lo;
+        s_plan[2] = mask_hi;
+    }
+    __syncthreads();
+    const uint32_t u_home = s_plan[0], home_lo = s_plan[1], home_hi = s_plan[2];
+    uint32_t staged = 0;
     for (uint32_t uk = 0; uk < p.n_units; ++uk) {
-        const uint32_t u = (uk + blockIdx.x) % p.n_units;
+        const uint32_t u = (uk + u_home) % p.n_units;
         const UnitDesc& cu = p.udesc[u];   // constant bank, uniform index
-        if (cu.mode == UM_PREPASS) continue;  // walked by the pre-pass kernel
+        if (cu.mode == UM_PREPASS) continue;  // walked by the per-request kernel
         const bool cand = cu.mode == UM_CANDIDATES;
         const uint32_t N = cand ? __ldg(p.cand_count[cu.field]) : p.n;
         uint32_t* ctr = p.counters + p.unit_base + u;
@@ -101,7 +153,9 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
         __syncthreads();
         if (tid == 0) {
             const uint32_t taken = *reinterpret_cast<volatile uint32_t*>(ctr);
-            const uint32_t skip_unit = taken >= N ? 1u : 0u;
+            const uint32_t left = taken >= N ? 0u : N - taken;
+            const bool has_home = ((u < 32u ? home_lo >> u : home_hi >> (u - 32u)) & 1u) != 0u;
+            const uint32_t skip_unit = (left == 0u || (uk != 0u && has_home && left < kJoinMin)) ? 1u : 0u;
             *s_skip = skip_unit;
             if (!skip_unit) {
                 const uint32_t bytes = cu.img_bytes;
@@ -217,6 +271,14 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                     pb ^= 1u;
                     pool_next = ah_base;
                     pool_end = min(ah_base + 32u, N);
+                    if (cand) {
+                        // candidates are scattered over the column: pull this pool's strings towards L2 before lanes adopt them
+                        const uint32_t sa = a_pool + pb * kFsPoolBytes + lane * 4u;
+                        const uint32_t s0 = lds_u32_v(sa), e0 = lds_u32_v(sa + 128u);
+                        if (ah_base + lane < N)
+                            for (uint32_t a = s0 & ~127u, k = 0; a < e0 && k < 4u; a += 128u, ++k)
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(col + a));
+                    }
                     claim_ahead();
                 }
                 const uint32_t idx = pool_next + __popc(need & lt_mask);
@@ -323,7 +385,7 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
 // Verdicts once every unit has been scanned: one thread per request (request_epilogue).  The tables of the small
 // early-exit units it walks are staged into the CTA's shared memory first.
 constexpr int kEpiThreads = 512;
-__global__ void __launch_bounds__(kEpiThreads) waf_epilogue_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(kEpiThreads, 3) waf_epilogue_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(256) uint8_t esm[];
     uint8_t* img = esm + ((0u - smem_u32(esm)) & 255u);   // class maps sit on 256-byte boundaries
     for (uint32_t k = 0; k < p.n_prefix; ++k) {

@@ -7,19 +7,17 @@
 //   waf_gate_kernel      streams every gated field column as ONE flat byte range: a warp takes 512 consecutive bytes per
 //                        iteration, every lane one coalesced 16-byte load.  Each lane tests the eight even-aligned
 //                        4-byte windows that start in its 16 bytes against the field's level-1 blocked Bloom filter in
-//                        shared memory (all gated fields' filters are resident together).  A lane that saw a level-1
-//                        hit (about 1 % of the chunks on benign traffic) appends the chunk's index to its CTA's segment
-//                        of the hit queue -- nothing else happens in the streaming loop.
-//   waf_gate_resolve_kernel  one thread per queued chunk: the eight windows again, now against the exact gram table
-//                        (gram -> mask of scan units), the requests a hit window overlaps (binary search over the
-//                        field's offsets), their unit masks (atomicOr into one word per request) and, for the first
-//                        marker of a request, its entry in the field's candidate list.
-//   waf_gate_finalize_kernel copies each candidate's final unit mask next to its list entry for the scan kernel.
-//
-// A hit queue segment that overflows (adversarial input: every chunk hits) sets the field's overflow flag; the resolve
-// kernel then lists every request as a candidate of every gated unit of the field -- the ungated behaviour, still exact.
+//                        shared memory (all gated fields' filters are resident together).  The warp's 32 verdicts are
+//                        one word of the field's HIT BITMAP (one bit per 16-byte chunk of the column): one ballot, one
+//                        store -- nothing else happens in the streaming loop, whatever the input looks like.
+//   waf_gate_maybe_kernel    one thread per request: the bits of the chunks its field overlaps (one or two words, read
+//                        coalesced); requests with a bit set (a few per cent) are listed per field.
+//   waf_gate_resolve_kernel  one thread per listed request: its hit chunks' windows again, now against the exact gram
+//                        table (gram -> mask of scan units); requests with a confirmed gram become the field's
+//                        candidates (request, field start, field end, unit mask) for the scan kernel.
+// Both lists are built with one block-wide scan and one atomicAdd per 1024 requests, in request order.
 constexpr int kGateThreads = 1024;
-constexpr uint32_t kGateCtrBytes = 64;   // front of the shared window: one hit counter per gated field
+constexpr uint32_t kGateCtrBytes = 64;   // front of the shared window (alignment pad)
 
 __device__ __forceinline__ uint32_t shf_wrap_r(uint32_t x, uint32_t n) { return __funnelshift_r(x, x, n); }  // rotate: amount taken mod 32
 
@@ -53,11 +51,9 @@ __global__ void __launch_bounds__(kGateThreads, 1) waf_gate_kernel(const __grid_
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t warps_total = gridDim.x * (kGateThreads / 32), warp_global = blockIdx.x * (kGateThreads / 32) + (tid >> 5);
-    uint32_t* const s_cnt = reinterpret_cast<uint32_t*>(gsm);
     uint8_t* const blooms = gsm + kGateCtrBytes;
 
     // every gated field's level-1 bitmap is staged once
-    if (tid < kMaxGateFields) s_cnt[tid] = 0u;
     for (uint32_t fi = 0; fi < gp.n_fields; ++fi) {
         const GateField& F = gp.f[fi];
         uint4* d1 = reinterpret_cast<uint4*>(blooms + F.bloom_off);
@@ -72,12 +68,11 @@ __global__ void __launch_bounds__(kGateThreads, 1) waf_gate_kernel(const __grid_
         const uint32_t* const t1 = reinterpret_cast<const uint32_t*>(blooms + F.bloom_off);
         const uint32_t wmask = 32u - (F.k1 - 5u);   // the Bloom word = the top k1 - 5 bits of the low product
         const uint8_t* col = F.col;
-        // the batch's bytes of this column: [off[0], off[n]) (a batch may be a window of a longer column); chunks of 16
-        // bytes from the one holding off[0]; the column is readable up to round_up(off[n], 32) (pgw_strcol contract)
-        const uint32_t first = __ldg(F.off) & ~15u, total = __ldg(F.off + gp.n);
+        // the batch's bytes of this column: [off[0], off[n]) (a batch may be a window of a longer column); blocks of 512
+        // bytes (one word of the hit bitmap) from the one holding off[0]; the column is readable up to
+        // round_up(off[n], 32) (pgw_strcol contract)
+        const uint32_t first = __ldg(F.off) & ~511u, total = __ldg(F.off + gp.n);
         const uint32_t limit = (total + 15u) & ~15u;
-        uint32_t* const hq = F.hq + (size_t)blockIdx.x * F.hq_cap;
-        const uint32_t a_cnt = smem_u32(s_cnt + fi);
 
         // a warp walks blocks of 512 bytes, warps_total blocks apart; loads run two blocks ahead
         uint32_t pos = first + warp_global * 512u + lane * 16u;
@@ -110,12 +105,9 @@ __global__ void __launch_bounds__(kGateThreads, 1) waf_gate_kernel(const __grid_
             acc |= gate_l1(t1, wmask, __funnelshift_r(f2, f3, 16));
             acc |= gate_l1(t1, wmask, f3);
             acc |= gate_l1(t1, wmask, __funnelshift_r(f3, f4, 16));
-            if ((acc & 1u) && pos < limit) {
-                uint32_t slot;
-                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(a_cnt) : "memory");
-                if (slot < F.hq_cap) hq[slot] = pos >> 4;
-                else *F.overflow = 1u;
-            }
+            // one word of the hit bitmap per warp and iteration: bit = lane = chunk (pos >> 4) & 31
+            const uint32_t hits = __ballot_sync(FULL, (acc & 1u) && pos < limit);
+            if (lane == 0) F.bitmap[pos >> 9] = hits;
             if ((uint64_t)pos - lane * 16u + stride >= limit) break;   // warp-uniform
             pos += stride;
             cur = nx1;
@@ -124,94 +116,117 @@ __global__ void __launch_bounds__(kGateThreads, 1) waf_gate_kernel(const __grid_
             la_nx1 = la_nx2;
         }
     }
+}
+
+// Block-wide append of the threads with `has` to a list: one scan, one atomicAdd; returns this thread's slot.
+// Every thread of the block must call it (barriers inside).
+__device__ __forceinline__ uint32_t block_append_slot(bool has, uint32_t* counter, uint32_t* s_warp, uint32_t* s_base) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, FULL = 0xFFFFFFFFu;
+    const uint32_t bal = __ballot_sync(FULL, has);
+    if (lane == 0) s_warp[warp] = (uint32_t)__popc(bal);
     __syncthreads();
-    if (tid < gp.n_fields) {
-        const GateField& F = gp.f[tid];
-        F.hq_count[blockIdx.x] = min(s_cnt[tid], F.hq_cap);
+    if (warp == 0) {
+        const uint32_t c = lane < (blockDim.x >> 5) ? s_warp[lane] : 0u;
+        uint32_t x = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, x, o);
+            if ((int)lane >= o) x += y;
+        }
+        s_warp[lane] = x - c;   // exclusive prefix of the warp counts
+        if (lane == 31u) *s_base = x ? atomicAdd(counter, x) : 0u;
+    }
+    __syncthreads();
+    const uint32_t k = *s_base + s_warp[warp] + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+    __syncthreads();   // s_warp / s_base may be reused by the caller's next list
+    return k;
+}
+
+// chunks (16 bytes, index = column position >> 4) holding an even-aligned window [j, j + 4) that overlaps the field [s, e)
+__device__ __forceinline__ void field_chunks(uint32_t s, uint32_t e, uint32_t* c_lo, uint32_t* c_hi) {
+    uint32_t j0 = s >= 3u ? s - 3u : 0u;   // first window with j + 4 > s ...
+    j0 += j0 & 1u;                         // ... at an even position
+    *c_lo = j0 >> 4;
+    *c_hi = ((e - 1u) & ~1u) >> 4;         // last even j < e
+}
+
+constexpr uint32_t kListThreads = 1024;
+
+// Requests whose field overlaps a chunk with a level-1 hit.  One thread per request.
+__global__ void __launch_bounds__(kListThreads) waf_gate_maybe_kernel(const __grid_constant__ GateParams gp) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_base;
+    const uint32_t n = gp.n;
+    for (uint32_t blk = blockIdx.x * kListThreads; blk < n; blk += gridDim.x * kListThreads) {
+        const uint32_t r = blk + threadIdx.x;
+        for (uint32_t fi = 0; fi < gp.n_fields; ++fi) {
+            const GateField& F = gp.f[fi];
+            bool has = false;
+            if (r < n) {
+                const uint32_t s = __ldg(F.off + r), e = __ldg(F.off + r + 1u);
+                if (e > s) {
+                    uint32_t c_lo, c_hi;
+                    field_chunks(s, e, &c_lo, &c_hi);
+                    for (uint32_t wi = c_lo >> 5; wi <= (c_hi >> 5) && !has; ++wi) {
+                        uint32_t bits = F.bitmap[wi];
+                        if (wi == (c_lo >> 5)) bits &= 0xFFFFFFFFu << (c_lo & 31u);
+                        if (wi == (c_hi >> 5)) bits &= 0xFFFFFFFFu >> (31u - (c_hi & 31u));
+                        has = bits != 0u;
+                    }
+                }
+            }
+            const uint32_t k = block_append_slot(has, F.maybe_count, s_warp, &s_base);
+            if (has) F.maybe_idx[k] = r;
+        }
     }
 }
 
-// One thread per queued chunk.  grid = (segments * kResolveParts, gated fields); block b of a field works on segment
-// b % segments, interleaved with the other kResolveParts - 1 blocks of that segment.
-constexpr uint32_t kResolveParts = 4, kResolveThreads = 256;
-
-__global__ void __launch_bounds__(kResolveThreads) waf_gate_resolve_kernel(const __grid_constant__ GateParams gp) {
+// The listed requests' hit chunks against the exact gram table.  grid.y = gated fields; one thread per listed request.
+__global__ void __launch_bounds__(kListThreads) waf_gate_resolve_kernel(const __grid_constant__ GateParams gp) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_base;
     const GateField& F = gp.f[blockIdx.y];
-    const uint32_t n = gp.n, lane = threadIdx.x & 31u;
-    const uint32_t fshift = F.mask_shift, fmask = F.mask_bits;   // this field's bits in a request's candidate word
-    const uint32_t* __restrict__ off = F.off;
-
-    // appends request r (field bytes [s, e)) to the field's candidate list; called under divergence: the lanes that are
-    // here together share one atomicAdd
-    auto append = [&](uint32_t r, uint32_t s, uint32_t e) {
-        const uint32_t act = __activemask();
-        const uint32_t leader = __ffs(act) - 1u;
-        uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(F.cand_count, (uint32_t)__popc(act));
-        base = __shfl_sync(act, base, leader);
-        const uint32_t k = base + (uint32_t)__popc(act & ((1u << lane) - 1u));
-        F.cand_idx[k] = r;
-        F.cand_start[k] = s;
-        F.cand_end[k] = e;
-    };
-
-    if (*reinterpret_cast<volatile uint32_t*>(F.overflow)) {
-        // the hit queue overflowed: every request is a candidate of every gated unit of the field
-        const uint32_t stride = gridDim.x * kResolveThreads;
-        for (uint32_t r = blockIdx.x * kResolveThreads + threadIdx.x; r < n; r += stride) {
-            atomicOr(gp.reqmask + r, fmask << fshift);
-            F.cand_idx[r] = r;
-            F.cand_start[r] = __ldg(off + r);
-            F.cand_end[r] = __ldg(off + r + 1u);
-        }
-        if (blockIdx.x == 0 && threadIdx.x == 0) *F.cand_count = n;
-        return;
-    }
-
-    const uint32_t seg = blockIdx.x % gp.n_seg, part = blockIdx.x / gp.n_seg, parts = gridDim.x / gp.n_seg;
-    const uint32_t count = F.hq_count[seg];
-    const uint32_t* hq = F.hq + (size_t)seg * F.hq_cap;
-    const uint32_t first_byte = __ldg(off), total = __ldg(off + n);
+    const uint32_t count = *F.maybe_count;
+    const uint32_t total = __ldg(F.off + gp.n);
     const uint32_t limit = (total + 15u) & ~15u;
-    for (uint32_t i = part * kResolveThreads + threadIdx.x; i < count; i += parts * kResolveThreads) {
-        const uint32_t pos = hq[i] << 4;
-        const uint4 c = ld_nc_v4(F.col + pos);
-        const uint32_t la = pos + 16u < limit ? ld_nc_u32(F.col + pos + 16u) : 0u;
-        const uint32_t f0 = c.x & kGateFoldMask, f1 = c.y & kGateFoldMask, f2 = c.z & kGateFoldMask, f3 = c.w & kGateFoldMask, f4 = la & kGateFoldMask;
-        uint32_t g[8];
-        g[0] = f0; g[1] = __funnelshift_r(f0, f1, 16); g[2] = f1; g[3] = __funnelshift_r(f1, f2, 16);
-        g[4] = f2; g[5] = __funnelshift_r(f2, f3, 16); g[6] = f3; g[7] = __funnelshift_r(f3, f4, 16);
-        uint32_t m[8];
+    for (uint32_t blk = blockIdx.x * kListThreads; blk < count; blk += gridDim.x * kListThreads) {
+        const uint32_t k = blk + threadIdx.x;
+        uint32_t r = 0, s = 0, e = 0, mask = 0;
+        if (k < count) {
+            r = F.maybe_idx[k];
+            s = __ldg(F.off + r);
+            e = __ldg(F.off + r + 1u);
+            uint32_t c_lo, c_hi;
+            field_chunks(s, e, &c_lo, &c_hi);
+            for (uint32_t wi = c_lo >> 5; wi <= (c_hi >> 5); ++wi) {
+                uint32_t bits = F.bitmap[wi];
+                if (wi == (c_lo >> 5)) bits &= 0xFFFFFFFFu << (c_lo & 31u);
+                if (wi == (c_hi >> 5)) bits &= 0xFFFFFFFFu >> (31u - (c_hi & 31u));
+                while (bits) {
+                    const uint32_t pos = (wi * 32u + (uint32_t)__ffs(bits) - 1u) << 4;
+                    bits &= bits - 1u;
+                    const uint4 c = ld_nc_v4(F.col + pos);
+                    const uint32_t la = pos + 16u < limit ? ld_nc_u32(F.col + pos + 16u) : 0u;
+                    const uint32_t f0 = c.x & kGateFoldMask, f1 = c.y & kGateFoldMask, f2 = c.z & kGateFoldMask, f3 = c.w & kGateFoldMask,
+                                   f4 = la & kGateFoldMask;
+                    uint32_t g[8];
+                    g[0] = f0; g[1] = __funnelshift_r(f0, f1, 16); g[2] = f1; g[3] = __funnelshift_r(f1, f2, 16);
+                    g[4] = f2; g[5] = __funnelshift_r(f2, f3, 16); g[6] = f3; g[7] = __funnelshift_r(f3, f4, 16);
 #pragma unroll
-        for (int w = 0; w < 8; ++w) m[w] = gate_l2(reinterpret_cast<const uint2*>(F.slots), F.kt, g[w]);
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            if (!m[w]) continue;
-            const uint32_t j = pos + 2u * (uint32_t)w;
-            if (j >= total || j + 4u <= first_byte) continue;   // the window lies outside the batch's bytes
-            // largest r with off[r] <= j (0 when the window starts before the batch's first byte)
-            uint32_t lo = 0, hi = n;   // invariant: off[lo] <= j or lo == 0; off[hi] > j
-            while (hi - lo > 1u) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (__ldg(off + mid) <= j) lo = mid;
-                else hi = mid;
-            }
-            for (uint32_t r = lo; r < n; ++r) {
-                const uint32_t s = __ldg(off + r);
-                if (s >= j + 4u) break;
-                const uint32_t e = __ldg(off + r + 1u);
-                if (e <= s || e <= j) continue;   // empty field, or the window starts at or after the field's end
-                const uint32_t old = atomicOr(gp.reqmask + r, (m[w] & fmask) << fshift);
-                if (((old >> fshift) & fmask) == 0u) append(r, s, e);
+                    for (int w = 0; w < 8; ++w) {
+                        const uint32_t j = pos + 2u * (uint32_t)w;
+                        // the window must overlap the field (and lie inside the batch's bytes: j < e <= total)
+                        if (j + 4u > s && j < e) mask |= gate_l2(reinterpret_cast<const uint2*>(F.slots), F.kt, g[w]);
+                    }
+                }
             }
         }
+        const bool has = mask != 0u;
+        const uint32_t q = block_append_slot(has, F.cand_count, s_warp, &s_base);
+        if (has) {
+            F.cand_idx[q] = r;
+            F.cand_start[q] = s;
+            F.cand_end[q] = e;
+            F.cand_mask[q] = mask;
+        }
     }
-}
-
-// The candidates' final unit masks, next to their list entries.  grid.y = gated fields.
-__global__ void __launch_bounds__(256) waf_gate_finalize_kernel(const __grid_constant__ GateParams gp) {
-    const GateField& F = gp.f[blockIdx.y];
-    const uint32_t count = *F.cand_count;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x)
-        F.cand_mask[k] = (gp.reqmask[F.cand_idx[k]] >> F.mask_shift) & F.mask_bits;
 }

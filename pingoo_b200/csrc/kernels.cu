@@ -113,18 +113,18 @@ const char* waf_batch_launch(KParams& p, GateParams& g, const UnitDesc* all_unit
     if (e != cudaSuccess) return cudaGetErrorString(e);
     if (ev) cudaEventRecord(ev[0], s);
     if (g.n_fields) {
-        e = cudaMemsetAsync(g.reqmask, 0, (size_t)p.n * 4, s);
-        if (e != cudaSuccess) return cudaGetErrorString(e);
-        // flat stream over the gated columns: one CTA per SM (g.n_seg, fixed by the caller with the hit-queue layout)
-        waf_gate_kernel<<<(int)g.n_seg, kGateThreads, gate_smem, s>>>(g);
+        // flat stream over the gated columns: one CTA per SM (fewer for small batches: each stages the level-1 bitmaps)
+        uint32_t gg = (p.n + 127u) / 128u;
+        if (gg > (uint32_t)sm_count) gg = (uint32_t)sm_count;
+        waf_gate_kernel<<<(int)gg, kGateThreads, gate_smem, s>>>(g);
         e = cudaGetLastError();
         if (e != cudaSuccess) return cudaGetErrorString(e);
-        waf_gate_resolve_kernel<<<dim3(g.n_seg * kResolveParts, g.n_fields), kResolveThreads, 0, s>>>(g);
+        uint32_t lb = (p.n + kListThreads - 1u) / kListThreads;
+        if (lb > (uint32_t)sm_count * 2u) lb = (uint32_t)sm_count * 2u;
+        waf_gate_maybe_kernel<<<lb, kListThreads, 0, s>>>(g);
         e = cudaGetLastError();
         if (e != cudaSuccess) return cudaGetErrorString(e);
-        uint32_t fb = (p.n + 255u) / 256u;
-        if (fb > (uint32_t)sm_count * 8u) fb = (uint32_t)sm_count * 8u;
-        waf_gate_finalize_kernel<<<dim3(fb, g.n_fields), 256, 0, s>>>(g);
+        waf_gate_resolve_kernel<<<dim3(lb, g.n_fields), kListThreads, 0, s>>>(g);
         e = cudaGetLastError();
         if (e != cudaSuccess) return cudaGetErrorString(e);
         nl += 3;

@@ -70,6 +70,8 @@ struct KParams {
     uint32_t sclean;            // its service
     const uint32_t* v1z;        // [cv][atom] verdict when exactly that atom is true and every other one false
     const uint16_t* s1z;        // [atom] service in that case
+    const uint64_t* atom_sig;   // [atom] hashed set of the rules mentioning the atom: two true atoms with disjoint signatures combine
+                                // their v1z / s1z entries (compile.cpp)
     // service routes (rules [n_waf_rules, n_rules)); `service` null: not requested for this batch
     uint32_t n_waf_rules;
     uint32_t s0;
@@ -91,6 +93,7 @@ struct KParams {
     const uint64_t* v6_hi;
     const uint64_t* v6_lo;
     const uint32_t* v6_leaf;
+    const uint32_t* v6_top;     // [65537] range index on the first 16 address bits
     uint32_t n_v6;
     uint32_t lpm_present;
     uint32_t geo_loaded;
@@ -114,12 +117,11 @@ struct GateField {
     const uint32_t* slots;   // level 2: exact table, 2^kt slots of {gram, unit mask}
     uint32_t k1, kt;
     uint32_t bloom_off;      // byte offset of the field's bitmap in the gate kernel's shared memory (all fields resident)
-    uint32_t mask_shift, mask_bits;  // the field's bits in a request's candidate word (kGateShift / kGateWidth)
-    uint32_t* hq;            // hit queue: indices of 16-byte chunks with a level-1 hit, one segment of hq_cap entries per gate CTA
-    uint32_t* hq_count;      // entries per segment
-    uint32_t hq_cap;
-    uint32_t* overflow;      // set when a segment overflowed: every request becomes a candidate
-    uint32_t* cand_count;    // candidate list of the field: one counter ...
+    uint32_t* bitmap;        // hit bitmap: one bit per 16-byte chunk of the column (index = column position >> 4); the gate
+                             // kernel writes every word that covers the batch's bytes
+    uint32_t* maybe_count;   // requests whose field overlaps a hit chunk: one counter ...
+    uint32_t* maybe_idx;     // ... and the request indices
+    uint32_t* cand_count;    // candidate list of the field (confirmed by the exact gram table): one counter ...
     uint32_t* cand_idx;      // ... and request index / field start / field end / unit mask per candidate
     uint32_t* cand_start;
     uint32_t* cand_end;
@@ -130,8 +132,6 @@ struct GateParams {
     GateField f[kMaxGateFields];
     uint32_t n_fields;
     uint32_t n;              // requests
-    uint32_t n_seg;          // hit-queue segments = CTAs of the gate kernel
-    uint32_t* reqmask;       // one candidate word per request (zeroed before each batch)
 };
 
 // host-callable wrappers (kernels.cu)
@@ -140,9 +140,9 @@ size_t waf_scan_image_budget(size_t max_smem_optin);  // bytes a unit image may 
 int waf_scan_threads();
 size_t waf_gate_smem_bytes(const GateParams& g);
 size_t waf_prefix_budget();  // shared memory the images of all early-exit units walked by the epilogue kernel may take
-// One batch: [gate -> resolve -> finalize] -> scan (one launch per kMaxConstUnits units) -> epilogue -> multi, all on
+// One batch: [gate -> maybe -> resolve] -> scan (one launch per kMaxConstUnits units) -> epilogue -> multi, all on
 // `stream`.  `all_units` = the program's unit descriptors (host copy); `small` = the block of claim counters, candidate
-// counters and hit-queue counters to zero first (`small_words` words).  `ev` (optional): four events recorded before the
+// counters and list counters to zero first (`small_words` words).  `ev` (optional): four events recorded before the
 // gate kernels, after them, after the scan launches and after the epilogue + multi kernels.
 const char* waf_batch_launch(KParams& p, GateParams& g, const UnitDesc* all_units, uint32_t* small, uint32_t small_words, int sm_count,
                              size_t scan_smem, size_t gate_smem, void* stream, cudaEvent_t* ev = nullptr, uint32_t* launches = nullptr);

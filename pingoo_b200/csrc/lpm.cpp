@@ -438,6 +438,19 @@ bool build_lpm(const std::vector<std::vector<IpNet>>& ip_sets, const std::vector
         T.v6_leaf.push_back(lf);
     }
     if (T.v6_leaf.empty()) { T.v6_hi.push_back(0); T.v6_lo.push_back(0); T.v6_leaf.push_back(0); }
+    // top-level index on the first 16 address bits: the range holding the first address of bucket t.  A lookup then
+    // searches ranges [v6_top[t], v6_top[t + 1]] only -- a handful instead of log2(all ranges) dependent probes.
+    T.v6_top.assign(65537, 0);
+    {
+        size_t i = 0;
+        const size_t n = T.v6_leaf.size();
+        for (uint32_t t = 0; t < 65536; ++t) {
+            const uint64_t key = (uint64_t)t << 48;
+            while (i + 1 < n && (T.v6_hi[i + 1] < key || (T.v6_hi[i + 1] == key && T.v6_lo[i + 1] == 0))) ++i;
+            T.v6_top[t] = (uint32_t)i;
+        }
+        T.v6_top[65536] = (uint32_t)(n - 1);
+    }
     return true;
 }
 

@@ -28,10 +28,9 @@ enum ReqFlags : uint8_t {
 constexpr uint32_t kEvKindShift = 30, kEvLatchShift = 24, kEvAtomMask = 0x3FFF;
 constexpr uint32_t kMaxLatchesPerUnit = 32;
 
-// Candidate masks: one 32-bit word per request holds, for each gated field, the set of the field's gated scan units some
-// gram hit asks for (unit g of the field -> bit kGateShift[field] + g % kGateWidth[field]).  Index = Field enum.
-constexpr uint32_t kGateShift[5] = {0, 0, 24, 0, 16};
-constexpr uint32_t kGateWidth[5] = {0, 16, 8, 0, 8};   // only url, path and user_agent are gated
+// Candidate unit masks: a gram of a gated field leads to the field's gated scan units whose patterns contain it
+// (unit g of the field -> bit g % kGateWidth[field] of the mask).  Index = Field enum.
+constexpr uint32_t kGateWidth[5] = {0, 32, 32, 0, 32};   // only url, path and user_agent are gated
 
 // rule bytecode (uint16): 0x0000..0x3FFF push atom, else opcode
 enum RuleOp : uint16_t { OP_NOT = 0x4000, OP_AND = 0x4001, OP_OR = 0x4002, OP_PUSH0 = 0x4003, OP_PUSH1 = 0x4004 };

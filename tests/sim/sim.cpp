@@ -312,6 +312,23 @@ static int evaluate_range(Sim* s, const pgw_batch* b, uint32_t* out, uint16_t* s
         const bool single_true = n_true == 1;
         if (s->atom_hist) s->atom_hist[n_true < 3 ? n_true : 3]++;
         if (!decided && single_true) { verdict = H.v1z[(size_t)cv * H.n_atoms + the_atom]; decided = true; }  // the single-atom table
+        // exactly two true atoms with disjoint rule signatures: the epilogue's pair path (compile.cpp: atom_sig)
+        bool pair_true = false;
+        uint32_t pa = 0, pb = 0;
+        if (n_true == 2) {
+            bool first = true;
+            for (uint32_t w = 0; w < Aw; ++w)
+                for (uint32_t x = row[w]; x; x &= x - 1) {
+                    const uint32_t at = w * 32 + (uint32_t)__builtin_ctz(x);
+                    if (first) { pa = at; first = false; } else pb = at;
+                }
+            pair_true = (H.atom_sig[pa] & H.atom_sig[pb]) == 0;
+        }
+        if (!decided && pair_true) {
+            const uint32_t va = H.v1z[(size_t)cv * H.n_atoms + pa], vb = H.v1z[(size_t)cv * H.n_atoms + pb];
+            verdict = (va >> 2) <= (vb >> 2) ? va : vb;
+            decided = true;
+        }
         if (!decided) {
             uint32_t diff = 0, ndev = 0, dev_atom = 0;
             for (uint32_t w = 0; w < Aw; ++w) {
@@ -352,6 +369,7 @@ static int evaluate_range(Sim* s, const pgw_batch* b, uint32_t* out, uint16_t* s
             uint32_t svc = kNoService;
             if ((verdict & 3u) == V_ALLOW && H.n_rules > H.n_waf_rules && !dirty) svc = H.sclean;
             else if ((verdict & 3u) == V_ALLOW && H.n_rules > H.n_waf_rules && single_true) svc = H.s1z[the_atom];
+            else if ((verdict & 3u) == V_ALLOW && H.n_rules > H.n_waf_rules && pair_true) svc = std::min<uint32_t>(H.s1z[pa], H.s1z[pb]);
             else if ((verdict & 3u) == V_ALLOW && H.n_rules > H.n_waf_rules) {
                 uint32_t diff = 0;
                 for (uint32_t w = 0; w < Aw; ++w) diff |= (row[w] ^ H.expect[w]) & H.care[w];
