@@ -215,7 +215,10 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, b
     int64_t asn = 0;
     uint32_t country = (uint32_t)'X' | ((uint32_t)'X' << 8);
     uint32_t set_mask = 0;
-    if (p.need_lpm) {
+#ifndef PGW_EXP_EPI
+#define PGW_EXP_EPI 0
+#endif
+    if (p.need_lpm && !(PGW_EXP_EPI & 2)) {
         const uint8_t* ip16 = p.ip + (size_t)r * 16;
         const bool v6 = p.is_v6[r] != 0;
         const LpmLeaf lf = p.leaves[lpm_lookup(p, ip16, v6)];
@@ -239,7 +242,7 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, b
         // small early-exit units: one walk over the first bytes of the field
 #pragma unroll
         for (uint32_t k = 0; k < kPre; ++k)
-            if (k < p.n_prefix && pe[k] > ps[k]) prefix_walk(p, p.pdesc[k], a_img + p.prefix_img[k], p.col[p.pdesc[k].field], ps[k], pe[k], fn);
+            if (!(PGW_EXP_EPI & 1) && k < p.n_prefix && pe[k] > ps[k]) prefix_walk(p, p.pdesc[k], a_img + p.prefix_img[k], p.col[p.pdesc[k].field], ps[k], pe[k], fn);
         for (uint32_t k = kPre; k < p.n_prefix; ++k) {
             const UnitDesc& ud = p.pdesc[k];
             const uint32_t* o = p.off[ud.field] + r;
@@ -261,7 +264,7 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, b
 #pragma unroll 1
         for (uint32_t fe = 0; fe < 7u; ++fe) {
             const uint32_t b0 = p.ns_begin[fe], b1 = p.ns_begin[fe + 1u];
-            if (b0 == b1) continue;
+            if (b0 == b1 || (PGW_EXP_EPI & 4)) continue;
             int64_t x;
             if (fe == 0u) x = p.port ? (int64_t)p.port[r] : 0;
             else if (fe == 1u) x = asn;
@@ -295,7 +298,7 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, b
                 if (v) fn(a.atom);
             }
         }
-        for (uint32_t i = p.ns_begin[7]; i < p.n_ns; ++i) {
+        for (uint32_t i = p.ns_begin[7]; i < p.n_ns && !(PGW_EXP_EPI & 8); ++i) {
             const NsAtom a = p.n_ns <= kMaxConstNs ? p.nsd[i] : p.ns[i];
             bool v = false;
             if (a.kind == 3) {  // IP_SET

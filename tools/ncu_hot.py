@@ -28,9 +28,11 @@ for r in rows[hdr_i + 1:]:
         n = int(r[inst] or 0)
     except ValueError:
         continue
-    tot_s += s
-    tot_i += n
+    if any(a == r[0] for _, _, _, a in items[-400:]):
+        continue
     items.append((s, n, r[ix.get("Source", 1)][:150], r[0]))
+tot_s = sum(i[0] for i in items)
+tot_i = sum(i[1] for i in items)
 print(f"total samples {tot_s}, instructions executed {tot_i}")
 for s, n, src, a in sorted(items, reverse=True)[:top]:
     print(f"{100.0 * s / max(tot_s, 1):6.2f}%  inst {100.0 * n / max(tot_i, 1):6.2f}%  {a[-5:]}  {src}")
