@@ -390,6 +390,8 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     P.care = (const uint32_t*)chk(M.upload(H.care));
     P.ns = (const NsAtom*)chk(M.upload(H.ns_atoms));
     P.n_ns = (uint32_t)H.ns_atoms.size();
+    P.n_rare = H.n_rare;
+    P.rare_begin = P.n_ns - H.n_rare;
     for (int g = 0; g < 9; ++g) P.ns_begin[g] = H.ns_begin[g];
     for (int f = 0; f < 7; ++f) { P.ns_lo[f] = H.ns_lo[f]; P.ns_hi[f] = H.ns_hi[f]; P.ns_vmin[f] = H.ns_vmin[f]; P.ns_vmax[f] = H.ns_vmax[f]; }
     memset(P.nsd, 0, sizeof P.nsd);
@@ -420,6 +422,7 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     }
     P.iset_vals = (const int64_t*)chk(M.upload(H.iset_vals));
     P.iset_off = (const uint32_t*)chk(M.upload(H.iset_off));
+    P.iexpr = (const int64_t*)chk(M.upload(H.iexpr));
     P.cset = (const uint32_t*)chk(M.upload(H.cset_words));
     P.gate_atom = H.gate_bypass_atom;
     P.eval_gates = H.eval_gates ? 1u : 0u;

@@ -553,6 +553,12 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
             }
             H.cset_words.push_back(v);
         }
+    std::vector<uint32_t> iexpr_off;
+    for (auto& prog : M.int_progs) {
+        iexpr_off.push_back((uint32_t)H.iexpr.size());
+        H.iexpr.insert(H.iexpr.end(), prog.begin(), prog.end());
+    }
+    if (H.iexpr.empty()) H.iexpr.push_back(0);
     for (uint32_t a = 0; a < H.n_atoms; ++a) {
         const AtomDesc& d = M.atoms[a];
         if (d.kind == AtomDesc::STR_PATTERN) continue;
@@ -564,6 +570,25 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
         n.op = (uint32_t)d.op;
         n.cval = d.cval;
         n.set_id = (uint32_t)std::max(0, d.set_id);
+        if (d.kind == AtomDesc::INT_EXPR) {
+            // the program's tokens go to the flat token array once per program; features it reads must be supplied
+            n.set_id = iexpr_off[d.set_id];
+            const std::vector<int64_t>& prog = M.int_progs[d.set_id];
+            for (size_t i = 0; i < prog.size(); ++i) {
+                const uint32_t op = (uint32_t)((uint64_t)prog[i] >> 56);
+                if (op == IT_CONST64) { ++i; continue; }
+                if (op != IT_FEAT) continue;
+                const int f = (int)(prog[i] & 0xFF);
+                if (f == IF_PORT) H.needs_port = true;
+                else if (f == IF_ASN) H.needs_geo_cols = true;
+                else len_feat_used[f - IF_LEN0] = true;
+            }
+        }
+        if (d.kind == AtomDesc::FIELD_CMP) {
+            n.feat = (uint32_t)d.field;
+            n.set_id = (uint32_t)d.feat;
+            H.scanned_fields_mask |= (1u << d.field) | (1u << d.feat);   // both fields' bytes are read (by the per-request kernel)
+        }
         H.ns_atoms.push_back(n);
         if (d.kind == AtomDesc::INT_CMP || d.kind == AtomDesc::INT_SET) {
             if (d.feat == IF_PORT) H.needs_port = true;
@@ -575,10 +600,22 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
     }
     // group the predicates by feature and derive the per-feature quick reject (most requests satisfy none of them)
     {
-        auto group = [](const NsAtom& a) { return (a.kind == AtomDesc::INT_CMP || a.kind == AtomDesc::INT_SET) ? (int)a.feat : (int)N_INT_FEATS; };
+        // integer predicates by feature, then the ip / country sets, then the rare kinds (INT_EXPR, FIELD_CMP) at the very end
+        auto group = [](const NsAtom& a) {
+            return (a.kind == AtomDesc::INT_CMP || a.kind == AtomDesc::INT_SET) ? (int)a.feat
+                   : (a.kind == AtomDesc::INT_EXPR || a.kind == AtomDesc::FIELD_CMP) ? (int)N_INT_FEATS + 1 : (int)N_INT_FEATS;
+        };
         std::stable_sort(H.ns_atoms.begin(), H.ns_atoms.end(), [&](const NsAtom& x, const NsAtom& y) { return group(x) < group(y); });
         for (int g = 0; g <= N_INT_FEATS + 1; ++g) H.ns_begin[g] = 0;
-        for (auto& a : H.ns_atoms) H.ns_begin[group(a) + 1]++;
+        H.n_rare = 0;
+        for (auto& a : H.ns_atoms) {
+            if (group(a) > N_INT_FEATS) { H.n_rare++; continue; }
+            H.ns_begin[group(a) + 1]++;
+        }
+        if (H.n_rare > 32) {
+            err = "more than 32 integer-expression / field-comparison predicates";
+            return false;
+        }
         for (int g = 0; g <= N_INT_FEATS; ++g) H.ns_begin[g + 1] += H.ns_begin[g];
         for (int f = 0; f < N_INT_FEATS; ++f) {
             int64_t lo = INT64_MIN, hi = INT64_MAX, vmin = INT64_MAX, vmax = INT64_MIN;

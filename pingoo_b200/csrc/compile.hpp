@@ -44,6 +44,8 @@ struct HostProgram {
     uint32_t ns_begin[N_INT_FEATS + 2] = {0};  // group g = ns_atoms[ns_begin[g], ns_begin[g + 1]); group N_INT_FEATS = the sets
     // quick reject per integer feature: lo <= x <= hi and (x < vmin or x > vmax) => every predicate on the feature is false
     int64_t ns_lo[N_INT_FEATS], ns_hi[N_INT_FEATS], ns_vmin[N_INT_FEATS], ns_vmax[N_INT_FEATS];
+    uint32_t n_rare = 0;                     // INT_EXPR / FIELD_CMP predicates: the last n_rare entries of ns_atoms
+    std::vector<int64_t> iexpr;              // INT_EXPR programs, flattened (program.hpp IntTok); NsAtom::set_id = offset
     std::vector<uint64_t> atom_sig;          // per atom: hashed set of the rules that mention it (all ones: never pair-independent)
     std::vector<uint16_t> code;
     std::vector<uint32_t> rule_off;  // n_rules + 1

@@ -152,26 +152,143 @@ __device__ __forceinline__ uint32_t lpm_lookup(const KParams& p, const uint8_t* 
     return __ldg(p.v6_leaf + l);
 }
 
+// INT_EXPR (program.hpp IntTok): both operand expressions of a comparison, evaluated with checked i64 arithmetic.
+// Returns false when the evaluation errors (overflow, division by zero, INT64_MIN / -1).
+__device__ __noinline__ bool int_expr_eval(const KParams& p, uint32_t off, uint32_t r, int64_t asn, int64_t* lhs, int64_t* rhs) {
+    int64_t st[kIntExprStack];
+    int sp = 0;
+    for (const int64_t* t = p.iexpr + off;; ++t) {
+        const int64_t w = __ldg(t);
+        const uint32_t op = (uint32_t)((uint64_t)w >> 56);
+        if (op == IT_END) break;
+        if (op == IT_CONST) { st[sp++] = (w << 8) >> 8; continue; }   // sign-extend the 56-bit operand
+        if (op == IT_CONST64) { st[sp++] = __ldg(++t); continue; }
+        if (op == IT_FEAT) {
+            const uint32_t f = (uint32_t)(w & 0xFF);
+            int64_t x;
+            if (f == 0u) x = p.port ? (int64_t)p.port[r] : 0;
+            else if (f == 1u) x = asn;
+            else { const uint32_t* o = p.off[f - 2u] + r; x = (int64_t)(o[1] - o[0]); }
+            st[sp++] = x;
+            continue;
+        }
+        if (op == IT_NEG) {
+            if (st[sp - 1] == INT64_MIN) return false;
+            st[sp - 1] = -st[sp - 1];
+            continue;
+        }
+        const int64_t b = st[--sp], a = st[sp - 1];
+        int64_t v;
+        if (op == IT_ADD) {
+            v = (int64_t)((uint64_t)a + (uint64_t)b);
+            if (((a ^ v) & (b ^ v)) < 0) return false;   // both operands differ in sign from the result
+        } else if (op == IT_SUB) {
+            v = (int64_t)((uint64_t)a - (uint64_t)b);
+            if (((a ^ b) & (a ^ v)) < 0) return false;
+        }
+        else if (op == IT_MUL) {
+            // checked multiply without a 128-bit product
+            v = (int64_t)((uint64_t)a * (uint64_t)b);
+            if (a != 0 && ((a == -1 && b == INT64_MIN) || (b == -1 && a == INT64_MIN) || v / a != b)) return false;
+        } else {
+            if (b == 0 || (a == INT64_MIN && b == -1)) return false;
+            v = op == IT_DIV ? a / b : a % b;
+        }
+        st[sp - 1] = v;
+    }
+    *lhs = st[0];
+    *rhs = st[1];
+    return true;
+}
+
+// FIELD_CMP: one http_request field against another (0 ==, 1 starts_with, 2 ends_with, 3 contains)
+__device__ __noinline__ bool field_cmp_eval(const KParams& p, uint32_t f1, uint32_t f2, uint32_t op, uint32_t r) {
+    const uint32_t s1 = p.off[f1][r], n1 = p.off[f1][r + 1] - s1, s2 = p.off[f2][r], n2 = p.off[f2][r + 1] - s2;
+    const uint8_t* a = p.col[f1] + s1;
+    const uint8_t* b = p.col[f2] + s2;
+    if (op == 0u && n1 != n2) return false;
+    if (n2 > n1) return false;
+    auto same = [&](uint32_t at) {
+        for (uint32_t i = 0; i < n2; ++i)
+            if (__ldg(a + at + i) != __ldg(b + i)) return false;
+        return true;
+    };
+    if (op == 0u || op == 1u) return same(0);
+    if (op == 2u) return same(n1 - n2);
+    for (uint32_t at = 0; at + n2 <= n1; ++at)
+        if (same(at)) return true;
+    return false;
+}
+
+// The INT_EXPR / FIELD_CMP predicates of a program (ns[rare_begin .. rare_begin + n_rare), at most 32): bit k = predicate k holds
+__device__ __noinline__ uint32_t rare_atoms(const KParams& p, uint32_t r, int64_t asn) {
+    uint32_t m = 0;
+    for (uint32_t k = 0; k < p.n_rare; ++k) {
+        const NsAtom a = p.ns[p.rare_begin + k];
+        bool v = false;
+        if (a.kind == 5) {  // (lhs <op> rhs), or "the evaluation errors"
+            int64_t x = 0, y = 0;
+            const bool ok = int_expr_eval(p, a.set_id, r, asn, &x, &y);
+            if (a.op == kIntExprIsError) v = !ok;
+            else if (ok) {
+                switch (a.op) {
+                    case 0: v = x == y; break;
+                    case 1: v = x != y; break;
+                    case 2: v = x < y; break;
+                    case 3: v = x <= y; break;
+                    case 4: v = x > y; break;
+                    default: v = x >= y; break;
+                }
+            }
+        } else {
+            v = field_cmp_eval(p, a.feat, a.set_id, a.op, r);
+        }
+        if (v) m |= 1u << k;
+    }
+    return m;
+}
+
 // One request's field walked on a small early-exit DFA whose whole table is in shared memory at `img` (class map,
 // rows, acc1, end1: the unit image of compile.hpp): start-anchored patterns (starts_with, ==, ^...) are decided within
 // the first few bytes, the walk stops at an absorbing state.  Fired atoms are reported through `fire(atom)`.
+// The first eight bytes come from three aligned word loads issued together (their class look-ups are independent of the
+// state, so only the row look-ups form a chain); longer undecided fields continue byte by byte.
 template <class Fire>
 __device__ __forceinline__ void prefix_walk(const KParams& p, const UnitDesc& ud, uint32_t img, const uint8_t* __restrict__ col, uint32_t s, uint32_t e,
                                             Fire&& fire) {
     const uint32_t C2 = 2u * ud.n_classes, acclo = ud.acc_lo, abs0 = ud.abs0, abs1 = ud.abs1;
     const uint32_t hot = img + ud.hot_off;
     uint32_t st = ud.start_state, latch = 0u;
-#pragma unroll 1
-    for (uint32_t pos = s; pos < e; ++pos) {
-        const uint32_t cls = lds_u8(img + (uint32_t)__ldg(col + pos));
+    bool done = false;
+    auto step = [&](uint32_t byte) {
+        const uint32_t cls = lds_u8(img + byte);
         st = lds_u16(hot + st * C2 + 2u * cls);
         if (st >= acclo) {
             const uint32_t a1 = lds_u16(img + ud.acc1_off + 2u * (st - acclo));
             if (a1 != 0xFFFFu) fire(a1);
             else fs_apply_list(p.acc_idx, p.acc_events, ud.acc_base + st - acclo, fire, &latch);
         }
-        if (st == abs0 || st == abs1) break;  // absorbing: nothing can change any more
+        done = st == abs0 || st == abs1;  // absorbing: nothing can change any more
+    };
+    {
+        // words are read only while they start before the field's end: a word that starts inside the column ends inside
+        // its readable range (pgw_strcol: round_up(length, 32))
+        const uint32_t base = s & ~3u, sh = (s & 3u) * 8u, n = e - s;
+        const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(col + base));
+        const uint32_t w1 = base + 4u < e ? __ldg(reinterpret_cast<const uint32_t*>(col + base + 4u)) : 0u;
+        const uint32_t w2 = base + 8u < e ? __ldg(reinterpret_cast<const uint32_t*>(col + base + 8u)) : 0u;
+        const uint32_t a = __funnelshift_r(w0, w1, sh), b = __funnelshift_r(w1, w2, sh);
+#pragma unroll
+        for (uint32_t k = 0; k < 4u; ++k)
+            if (k < n && !done) step((a >> (8u * k)) & 0xFFu);
+        if (n > 4u && !done) {
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; ++k)
+                if (k + 4u < n && !done) step((b >> (8u * k)) & 0xFFu);
+        }
     }
+#pragma unroll 1
+    for (uint32_t pos = s + 8u; pos < e && !done; ++pos) step((uint32_t)__ldg(col + pos));
     const uint32_t e1 = lds_u16(img + ud.end1_off + 2u * st);
     if (e1 != 0xFFFEu) {
         if (e1 != 0xFFFFu) fire(e1);
@@ -298,7 +415,7 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, b
                 if (v) fn(a.atom);
             }
         }
-        for (uint32_t i = p.ns_begin[7]; i < p.n_ns && !(PGW_EXP_EPI & 8); ++i) {
+        for (uint32_t i = p.ns_begin[7]; i < p.rare_begin && !(PGW_EXP_EPI & 8); ++i) {
             const NsAtom a = p.n_ns <= kMaxConstNs ? p.nsd[i] : p.ns[i];
             bool v = false;
             if (a.kind == 3) {  // IP_SET
@@ -311,6 +428,15 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, b
                 }
             }
             if (v) fn(a.atom);
+        }
+        // integer expressions and field-against-field predicates (rare in rule sets): one out-of-line call
+        if (p.n_rare) {
+            uint32_t m = rare_atoms(p, r, asn);
+            while (m) {
+                const uint32_t k = (uint32_t)__ffs(m) - 1u;
+                m &= m - 1u;
+                fn((p.n_ns <= kMaxConstNs ? p.nsd[p.rare_begin + k] : p.ns[p.rare_begin + k]).atom);
+            }
         }
     };
 

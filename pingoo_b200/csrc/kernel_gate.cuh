@@ -151,32 +151,57 @@ __device__ __forceinline__ void field_chunks(uint32_t s, uint32_t e, uint32_t* c
 
 constexpr uint32_t kListThreads = 1024;
 
-// Requests whose field overlaps a chunk with a level-1 hit.  One thread per request.
+// Requests whose field overlaps a chunk with a level-1 hit.  One thread per request; the (up to three) fields' lists are
+// appended with ONE block-wide scan: the per-field counts ride in 10-bit lanes of one word.
 __global__ void __launch_bounds__(kListThreads) waf_gate_maybe_kernel(const __grid_constant__ GateParams gp) {
     __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_base;
-    const uint32_t n = gp.n;
+    __shared__ uint32_t s_base[kMaxGateFields];
+    const uint32_t n = gp.n, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, FULL = 0xFFFFFFFFu;
+    static_assert(kMaxGateFields <= 3 && kListThreads <= 1024, "three 10-bit (+carry) counters per word");
     for (uint32_t blk = blockIdx.x * kListThreads; blk < n; blk += gridDim.x * kListThreads) {
         const uint32_t r = blk + threadIdx.x;
-        for (uint32_t fi = 0; fi < gp.n_fields; ++fi) {
-            const GateField& F = gp.f[fi];
-            bool has = false;
-            if (r < n) {
+        uint32_t has = 0;   // bit fi: the request goes to field fi's list
+        if (r < n)
+            for (uint32_t fi = 0; fi < gp.n_fields; ++fi) {
+                const GateField& F = gp.f[fi];
                 const uint32_t s = __ldg(F.off + r), e = __ldg(F.off + r + 1u);
-                if (e > s) {
-                    uint32_t c_lo, c_hi;
-                    field_chunks(s, e, &c_lo, &c_hi);
-                    for (uint32_t wi = c_lo >> 5; wi <= (c_hi >> 5) && !has; ++wi) {
-                        uint32_t bits = F.bitmap[wi];
-                        if (wi == (c_lo >> 5)) bits &= 0xFFFFFFFFu << (c_lo & 31u);
-                        if (wi == (c_hi >> 5)) bits &= 0xFFFFFFFFu >> (31u - (c_hi & 31u));
-                        has = bits != 0u;
-                    }
+                if (e <= s) continue;
+                uint32_t c_lo, c_hi;
+                field_chunks(s, e, &c_lo, &c_hi);
+                bool any = false;
+                for (uint32_t wi = c_lo >> 5; wi <= (c_hi >> 5) && !any; ++wi) {
+                    uint32_t bits = F.bitmap[wi];
+                    if (wi == (c_lo >> 5)) bits &= 0xFFFFFFFFu << (c_lo & 31u);
+                    if (wi == (c_hi >> 5)) bits &= 0xFFFFFFFFu >> (31u - (c_hi & 31u));
+                    any = bits != 0u;
                 }
+                if (any) has |= 1u << fi;
             }
-            const uint32_t k = block_append_slot(has, F.maybe_count, s_warp, &s_base);
-            if (has) F.maybe_idx[k] = r;
+        // per-field ballots; counts packed 11 bits apart (a block appends at most 1024 per field)
+        const uint32_t b0 = __ballot_sync(FULL, has & 1u), b1 = __ballot_sync(FULL, has & 2u), b2 = __ballot_sync(FULL, has & 4u);
+        if (lane == 0) s_warp[warp] = (uint32_t)__popc(b0) | ((uint32_t)__popc(b1) << 11) | ((uint32_t)__popc(b2) << 22);
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t c = s_warp[lane];
+            uint32_t x = c;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(FULL, x, o);
+                if ((int)lane >= o) x += y;
+            }
+            s_warp[lane] = x - c;   // exclusive prefixes of the warp counts, still packed
+            if (lane == 31u)
+                for (uint32_t fi = 0; fi < gp.n_fields; ++fi) {
+                    // exclusive prefix + own count: the top lane has 10 bits, a full block (1024) would not fit as one number
+                    const uint32_t tot = (((x - c) >> (11u * fi)) & 0x7FFu) + ((c >> (11u * fi)) & 0x7FFu);
+                    s_base[fi] = tot ? atomicAdd(gp.f[fi].maybe_count, tot) : 0u;
+                }
         }
+        __syncthreads();
+        const uint32_t pre = s_warp[warp], lt = (1u << lane) - 1u;
+        if (has & 1u) gp.f[0].maybe_idx[s_base[0] + (pre & 0x7FFu) + (uint32_t)__popc(b0 & lt)] = r;
+        if (has & 2u) gp.f[1].maybe_idx[s_base[1] + ((pre >> 11) & 0x7FFu) + (uint32_t)__popc(b1 & lt)] = r;
+        if (has & 4u) gp.f[2].maybe_idx[s_base[2] + ((pre >> 22) & 0x7FFu) + (uint32_t)__popc(b2 & lt)] = r;
+        __syncthreads();   // s_warp / s_base are reused by the next block of requests
     }
 }
 

@@ -14,6 +14,7 @@
 
 #include "dfa.hpp"
 #include "model.hpp"
+#include "program.hpp"
 
 namespace pgw {
 
@@ -111,8 +112,9 @@ struct BV {
 struct Sym {
     enum K : uint8_t {
         ERR, NUL, BOOL, INT_C, UINT_C, FLOAT_C, STR_C, BYTES_C, LIST_C, LIST_REF, MAP_C,
-        MAP_LISTS, MAP_HTTP, MAP_CLIENT, STR_FIELD, INT_FEAT, IP_VAR, COUNTRY_VAR
+        MAP_LISTS, MAP_HTTP, MAP_CLIENT, STR_FIELD, INT_FEAT, INT_EXPR, IP_VAR, COUNTRY_VAR
     } k = ERR;
+    std::vector<int64_t> prog;   // INT_EXPR: postfix tokens (program.hpp IntTok)
     BV bv;
     int64_t i = 0;
     double f = 0;
@@ -324,6 +326,150 @@ struct Lowerer {
         return boolean(P.atom(add_atom(std::move(a))));
     }
 
+    // ---- integer expressions over request variables (client.remote_port + 1, path.length() * 2, asn % 10 ...) --------
+    static bool is_int_value(const Sym& s) { return s.k == Sym::INT_C || s.k == Sym::INT_FEAT || s.k == Sym::INT_EXPR; }
+    static int64_t tok(uint32_t op, int64_t v = 0) { return (int64_t)(((uint64_t)op << 56) | ((uint64_t)v & 0x00FFFFFFFFFFFFFFull)); }
+    static void append_int(std::vector<int64_t>& out, const Sym& s) {
+        if (s.k == Sym::INT_C) {
+            if (s.i >= -(1ll << 55) && s.i < (1ll << 55)) out.push_back(tok(IT_CONST, s.i));
+            else { out.push_back(tok(IT_CONST64)); out.push_back(s.i); }
+        } else if (s.k == Sym::INT_FEAT) out.push_back(tok(IT_FEAT, s.feat));
+        else out.insert(out.end(), s.prog.begin(), s.prog.end());
+    }
+    static int prog_depth(const std::vector<int64_t>& p) {
+        int d = 0, mx = 0;
+        for (size_t i = 0; i < p.size(); ++i) {
+            const uint32_t op = (uint32_t)((uint64_t)p[i] >> 56);
+            if (op == IT_CONST || op == IT_FEAT) ++d;
+            else if (op == IT_CONST64) { ++d; ++i; }
+            else if (op == IT_NEG) {}
+            else --d;
+            mx = std::max(mx, d);
+        }
+        return mx;
+    }
+    static bool prog_can_error(const std::vector<int64_t>& p) {
+        for (size_t i = 0; i < p.size(); ++i) {
+            const uint32_t op = (uint32_t)((uint64_t)p[i] >> 56);
+            if (op == IT_CONST64) { ++i; continue; }
+            if (op >= IT_ADD) return true;
+        }
+        return false;
+    }
+    Sym int_arith(const Expr& e, uint32_t op, const Sym& a, const Sym& b) {
+        Sym r;
+        r.k = Sym::INT_EXPR;
+        append_int(r.prog, a);
+        append_int(r.prog, b);
+        r.prog.push_back(tok(op));
+        if (prog_depth(r.prog) > (int)kIntExprStack) unsupported(e, "integer expression nested deeper than the evaluator's operand stack");
+        return r;
+    }
+    // (a <op> b) on two integer values at least one of which depends on the request: a true-atom and, if the arithmetic can
+    // fail, an error-atom on the same program
+    Sym int_expr_cmp(const Expr& e, int op, const Sym& a, const Sym& b) {
+        std::vector<int64_t> prog;
+        append_int(prog, a);
+        append_int(prog, b);
+        prog.push_back(tok(IT_END));
+        if (prog_depth(prog) > (int)kIntExprStack) unsupported(e, "integer expression nested deeper than the evaluator's operand stack");
+        int pid = -1;
+        for (size_t k = 0; k < M.int_progs.size(); ++k)
+            if (M.int_progs[k] == prog) pid = (int)k;
+        if (pid < 0) { M.int_progs.push_back(prog); pid = (int)M.int_progs.size() - 1; }
+        auto mk = [&](int o) {
+            AtomDesc d;
+            d.kind = AtomDesc::INT_EXPR;
+            d.op = o;
+            d.set_id = pid;
+            d.key = "IX|" + std::to_string(pid) + "|" + std::to_string(o);
+            return P.atom(add_atom(std::move(d)));
+        };
+        const int er = prog_can_error(prog) ? mk((int)kIntExprIsError) : 0;
+        int t;
+        if (op == CMP_NE) t = P.mk_and(P.mk_not(mk(CMP_EQ)), P.mk_not(er));   // the "==" atom is false on an error as well
+        else t = mk(op);
+        return boolean(t, er);
+    }
+
+    // one http_request field against another: 0 ==, 1 starts_with, 2 ends_with, 3 contains
+    Sym field_cmp_atom(int f1, int f2, int op) {
+        AtomDesc d;
+        d.kind = AtomDesc::FIELD_CMP;
+        d.field = f1;
+        d.feat = f2;
+        d.op = op;
+        d.key = "FC|" + std::to_string(f1) + "|" + std::to_string(f2) + "|" + std::to_string(op);
+        return boolean(P.atom(add_atom(std::move(d))));
+    }
+
+    // http_request.<field> <op> "literal" for the ordering operators: byte-wise lexicographic order (Rust str::cmp), a regular
+    // language anchored at the start of the field: after the common prefix lit[0..i) either the field ends (less), or its next
+    // byte is smaller / greater than lit[i]
+    Sym str_order_atom(int field, const std::string& lit, int op) {
+        if (lit.empty()) {   // against "": only the length matters
+            if (op == CMP_GE) return const_bool(true);
+            if (op == CMP_LT) return const_bool(false);
+            return int_cmp_atom(IF_LEN0 + field, op == CMP_GT ? CMP_GT : CMP_EQ, 0);
+        }
+        std::string key = std::string("S|") + std::to_string(field) + "|ord" + std::to_string(op) + "|" + lenpfx(lit);
+        auto it = M.atom_index.find(key);
+        if (it != M.atom_index.end()) return boolean(P.atom(it->second));
+        AtomDesc a;
+        a.kind = AtomDesc::STR_PATTERN;
+        a.field = field;
+        a.key = key;
+        const int id = (int)M.atoms.size();
+        a.event_base = (int)M.events.size();
+        Nfa& nfa = M.nfa[field];
+        auto add = [&](NfaKind k) { NfaNode n; n.kind = k; nfa.nodes.push_back(n); return (int)nfa.nodes.size() - 1; };
+        const int m = add(N_MATCH);
+        nfa.nodes[m].pattern = a.event_base;
+        const bool less = op == CMP_LT || op == CMP_LE, or_equal = op == CMP_LE || op == CMP_GE;
+        auto eol_to_match = [&]() { int x = add(N_ASSERT); nfa.nodes[x].assert_kind = A_EOL_TEXT; nfa.nodes[x].out = m; return x; };
+        auto alt = [&](int x, int y) { if (x < 0) return y; if (y < 0) return x; int sp = add(N_SPLIT); nfa.nodes[sp].out = x; nfa.nodes[sp].out1 = y; return sp; };
+        // node for "the first |lit| bytes all matched": == decides <= / >=, a longer field is greater
+        int next = -1;
+        if (or_equal) next = less ? eol_to_match() : m;   // >=: anything from here on (end or more bytes) is >= lit
+        else if (!less) {                                  // >: at least one more byte
+            ByteSet any;
+            any.negate();
+            next = add(N_CHAR);
+            nfa.nodes[next].set = nfa.add_set(any);
+            nfa.nodes[next].out = m;
+        }
+        for (size_t k = lit.size(); k-- > 0;) {
+            const unsigned c = (unsigned char)lit[k];
+            int here = -1;
+            if (less) here = eol_to_match();   // the field ends inside the literal: a proper prefix is smaller
+            ByteSet diff;
+            for (unsigned v = 0; v < 256; ++v)
+                if (less ? v < c : v > c) diff.set(v);
+            if (!diff.empty()) {
+                int d = add(N_CHAR);
+                nfa.nodes[d].set = nfa.add_set(diff);
+                nfa.nodes[d].out = m;
+                here = alt(here, d);
+            }
+            if (next >= 0) {
+                ByteSet same;
+                same.set(c);
+                int sm = add(N_CHAR);
+                nfa.nodes[sm].set = nfa.add_set(same);
+                nfa.nodes[sm].out = next;
+                here = alt(here, sm);
+            }
+            next = here;
+        }
+        if (next < 0) return const_bool(false);   // e.g. field < "": nothing is smaller than the empty string
+        const int bol = add(N_ASSERT);
+        nfa.nodes[bol].assert_kind = A_BOL_TEXT;
+        nfa.nodes[bol].out = next;
+        a.nfa_starts.push_back(bol);
+        M.events.push_back(PatternEvent{EV_FIRE, id});
+        return boolean(P.atom(add_atom(std::move(a))));
+    }
+
     Sym ip_set_atom(const Sym& list) {
         // list is LIST_REF of type Ip
         if (list.list->nets.empty()) return const_bool(false);
@@ -457,7 +603,13 @@ struct Lowerer {
                     return const_int(-x.i);
                 }
                 if (x.k == Sym::FLOAT_C) { x.f = -x.f; return x; }
-                if (x.k == Sym::INT_FEAT) unsupported(e, "arithmetic on request variables");
+                if (x.k == Sym::INT_FEAT || x.k == Sym::INT_EXPR) {
+                    Sym r;
+                    r.k = Sym::INT_EXPR;
+                    append_int(r.prog, x);
+                    r.prog.push_back(tok(IT_NEG));
+                    return r;
+                }
                 return err();
             }
             case Expr::BINARY: return binary(e);
@@ -630,6 +782,7 @@ struct Lowerer {
             if (recv.k == Sym::STR_FIELD) {
                 if (a.k == Sym::STR_FIELD || a.k == Sym::COUNTRY_VAR) {
                     if (fn != "matches" && a.k == Sym::STR_FIELD && a.field == recv.field) return const_bool(true);
+                    if (fn != "matches" && a.k == Sym::STR_FIELD) return field_cmp_atom(recv.field, a.field, fn == "starts_with" ? 1 : fn == "ends_with" ? 2 : 3);
                     unsupported(e, fn + "() between two request variables");
                 }
                 if (a.k != Sym::STR_C) return err();
@@ -725,13 +878,15 @@ struct Lowerer {
         switch (a.k) {
             case Sym::STR_FIELD:
                 if (b.k == Sym::STR_C) {
-                    if (ordering) unsupported(e, "lexicographic ordering comparison on an http_request field");
+                    if (ordering) return str_order_atom(a.field, b.s, op);
                     Sym eq = str_literal_atom(a.field, b.s, true, true);
                     return op == CMP_EQ ? eq : boolean(P.mk_not(eq.bv.t));
                 }
                 if (b.k == Sym::STR_FIELD) {
                     if (b.field == a.field) return const_bool(op == CMP_EQ || op == CMP_LE || op == CMP_GE);
-                    unsupported(e, "comparison between two http_request fields");
+                    if (ordering) unsupported(e, "lexicographic ordering between two http_request fields");
+                    Sym eq = field_cmp_atom(a.field, b.field, 0);
+                    return op == CMP_EQ ? eq : boolean(P.mk_not(eq.bv.t));
                 }
                 if (b.k == Sym::COUNTRY_VAR) unsupported(e, "comparison between two request variables");
                 return err();
@@ -742,10 +897,11 @@ struct Lowerer {
                 return err();
             case Sym::INT_FEAT:
                 if (b.k == Sym::INT_C) return int_cmp_atom(a.feat, op, b.i);
-                if (b.k == Sym::INT_FEAT) {
-                    if (b.feat == a.feat) return const_bool(op == CMP_EQ || op == CMP_LE || op == CMP_GE);
-                    unsupported(e, "comparison between two integer request variables");
-                }
+                if (b.k == Sym::INT_FEAT && b.feat == a.feat) return const_bool(op == CMP_EQ || op == CMP_LE || op == CMP_GE);
+                if (is_int_value(b)) return int_expr_cmp(e, op, a, b);
+                return err();
+            case Sym::INT_EXPR:
+                if (is_int_value(b)) return int_expr_cmp(e, op, a, b);
                 return err();
             case Sym::IP_VAR:
                 if (b.k == Sym::IP_VAR && !ordering) return const_bool(op == CMP_EQ);
@@ -790,7 +946,17 @@ struct Lowerer {
         }
         // arithmetic
         if (a.k == Sym::ERR || b.k == Sym::ERR) return err();
-        if (a.k == Sym::INT_FEAT || b.k == Sym::INT_FEAT) unsupported(e, "arithmetic on request variables");
+        if ((a.k == Sym::INT_FEAT || a.k == Sym::INT_EXPR || b.k == Sym::INT_FEAT || b.k == Sym::INT_EXPR)) {
+            if (!is_int_value(a) || !is_int_value(b)) return err();   // no implicit conversions: Int with Float / String is an error
+            switch (e.op) {
+                case Expr::OP_ADD: return int_arith(e, IT_ADD, a, b);
+                case Expr::OP_SUB: return int_arith(e, IT_SUB, a, b);
+                case Expr::OP_MUL: return int_arith(e, IT_MUL, a, b);
+                case Expr::OP_DIV: return int_arith(e, IT_DIV, a, b);
+                case Expr::OP_MOD: return int_arith(e, IT_MOD, a, b);
+                default: return err();
+            }
+        }
         if (a.k == Sym::STR_FIELD || b.k == Sym::STR_FIELD || a.k == Sym::COUNTRY_VAR || b.k == Sym::COUNTRY_VAR)
             if (e.op == Expr::OP_ADD) unsupported(e, "string concatenation with request variables");
         if (a.k == Sym::INT_C && b.k == Sym::INT_C) {

@@ -80,7 +80,9 @@ struct AtomDesc {
         INT_CMP,       // int feature <op> constant
         INT_SET,       // int feature in a sorted constant set
         IP_SET,        // client.ip contained in any network of a set
-        COUNTRY_SET    // client.country in a 26x26 bitmap
+        COUNTRY_SET,   // client.country in a 26x26 bitmap
+        INT_EXPR,      // comparison of two integer expressions over request variables (prog), or "the expression errors" (op 6)
+        FIELD_CMP      // one http_request field against another: op 0 ==, 1 starts_with, 2 ends_with, 3 contains (field, feat = second field)
     } kind;
     int field = -1;        // STR_PATTERN
     std::vector<int> nfa_starts;  // STR_PATTERN: start node(s) in Model::nfa[field]; pattern id of part k = event_base + k
@@ -91,7 +93,7 @@ struct AtomDesc {
     int feat = -1;         // INT_*
     int op = 0;            // INT_CMP
     int64_t cval = 0;      // INT_CMP
-    int set_id = -1;       // INT_SET / IP_SET / COUNTRY_SET
+    int set_id = -1;       // INT_SET / IP_SET / COUNTRY_SET; INT_EXPR: index into Model::int_progs
     int pos_refs = 0, neg_refs = 0;  // polarity statistics -> expected value heuristic
     std::string key;       // dedupe key / debug description
 };
@@ -122,6 +124,8 @@ struct Model {
     std::unordered_map<std::string, int> atom_index;
     Nfa nfa[N_FIELDS];
     std::vector<std::vector<int64_t>> int_sets;
+    // INT_EXPR programs (postfix, one int64 token each; program.hpp IntTok): two operand expressions, compared by the atom's op
+    std::vector<std::vector<int64_t>> int_progs;
     std::vector<std::vector<IpNet>> ip_sets;
     std::vector<std::bitset<676>> country_sets;
     std::vector<RuleModel> rules;    // WAF rules first, then service routes

@@ -74,6 +74,13 @@ enum UnitMode : uint32_t {
                        // shared memory next to each other (set at finalize, not by the compiler)
 };
 
+// INT_EXPR programs: postfix tokens, one int64 each: opcode in the top byte, operand in the low 56 bits (sign-extended
+// constants that do not fit use IT_CONST64 followed by a full word).  Arithmetic is checked i64 (overflow, division by
+// zero, INT64_MIN / -1 are errors: the comparison is false and the "errors" atom true), as bel's Int (SEMANTICS.md A4).
+enum IntTok : uint32_t { IT_END = 0, IT_CONST = 1, IT_CONST64 = 2, IT_FEAT = 3, IT_ADD = 4, IT_SUB = 5, IT_MUL = 6, IT_DIV = 7, IT_MOD = 8, IT_NEG = 9 };
+constexpr uint32_t kIntExprIsError = 6;   // NsAtom::op for "the program errors" (0..5 = CmpOp on the two results)
+constexpr uint32_t kIntExprStack = 8;     // deepest operand stack a program may need
+
 // predicates evaluated once per request outside the byte scan
 struct NsAtom {
     uint32_t kind;     // AtomDesc::Kind
@@ -81,7 +88,8 @@ struct NsAtom {
     uint32_t feat;     // IntFeat
     uint32_t op;       // CmpOp
     int64_t cval;
-    uint32_t set_id;   // int set / ip set bit / country set
+    uint32_t set_id;   // int set / ip set bit / country set; INT_EXPR: offset of the program in the token array;
+                       // FIELD_CMP: the second field (feat = the first, op = 0 ==, 1 starts_with, 2 ends_with, 3 contains)
     uint32_t pad;
 };
 

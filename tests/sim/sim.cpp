@@ -277,6 +277,60 @@ static int evaluate_range(Sim* s, const pgw_batch* b, uint32_t* out, uint16_t* s
                 }
             } else if (a.kind == AtomDesc::IP_SET) {
                 v = (set_mask >> a.set_id) & 1u;
+            } else if (a.kind == AtomDesc::INT_EXPR) {
+                // program.hpp IntTok: both operands with checked i64 arithmetic
+                int64_t st[kIntExprStack];
+                int sp = 0;
+                bool ok = true;
+                for (size_t t = a.set_id; ok; ++t) {
+                    const int64_t w = H.iexpr[t];
+                    const uint32_t op = (uint32_t)((uint64_t)w >> 56);
+                    if (op == IT_END) break;
+                    if (op == IT_CONST) { st[sp++] = (int64_t)((uint64_t)w << 8) >> 8; continue; }
+                    if (op == IT_CONST64) { st[sp++] = H.iexpr[++t]; continue; }
+                    if (op == IT_FEAT) {
+                        const int f = (int)(w & 0xFF);
+                        int64_t x;
+                        if (f == IF_PORT) x = b->remote_port ? b->remote_port[r] : 0;
+                        else if (f == IF_ASN) x = asn;
+                        else { int ff = f - IF_LEN0; x = (int64_t)(cols[ff]->offsets[r + 1] - cols[ff]->offsets[r]); }
+                        st[sp++] = x;
+                        continue;
+                    }
+                    if (op == IT_NEG) { if (st[sp - 1] == INT64_MIN) ok = false; else st[sp - 1] = -st[sp - 1]; continue; }
+                    const int64_t y = st[--sp], x = st[sp - 1];
+                    int64_t z = 0;
+                    if (op == IT_ADD) ok = !__builtin_add_overflow(x, y, &z);
+                    else if (op == IT_SUB) ok = !__builtin_sub_overflow(x, y, &z);
+                    else if (op == IT_MUL) ok = !__builtin_mul_overflow(x, y, &z);
+                    else if (y == 0 || (x == INT64_MIN && y == -1)) ok = false;
+                    else z = op == IT_DIV ? x / y : x % y;
+                    st[sp - 1] = z;
+                }
+                if (a.op == kIntExprIsError) v = !ok;
+                else if (ok) {
+                    const int64_t x = st[0], y = st[1];
+                    switch (a.op) {
+                        case CMP_EQ: v = x == y; break;
+                        case CMP_NE: v = x != y; break;
+                        case CMP_LT: v = x < y; break;
+                        case CMP_LE: v = x <= y; break;
+                        case CMP_GT: v = x > y; break;
+                        default: v = x >= y; break;
+                    }
+                }
+            } else if (a.kind == AtomDesc::FIELD_CMP) {
+                const uint32_t f1 = a.feat, f2 = a.set_id;
+                const uint32_t s1 = cols[f1]->offsets[r], n1 = cols[f1]->offsets[r + 1] - s1, s2 = cols[f2]->offsets[r], n2 = cols[f2]->offsets[r + 1] - s2;
+                const uint8_t* x = cols[f1]->bytes + s1;
+                const uint8_t* y = cols[f2]->bytes + s2;
+                if (a.op == 0) v = n1 == n2 && memcmp(x, y, n1) == 0;
+                else if (n2 > n1) v = false;
+                else if (a.op == 1) v = memcmp(x, y, n2) == 0;
+                else if (a.op == 2) v = memcmp(x + n1 - n2, y, n2) == 0;
+                else {
+                    for (uint32_t at = 0; at + n2 <= n1 && !v; ++at) v = memcmp(x + at, y, n2) == 0;
+                }
             } else {
                 uint32_t c0 = (country & 0xFF) - 'A', c1 = ((country >> 8) & 0xFF) - 'A';
                 if (c0 < 26 && c1 < 26) {

@@ -276,3 +276,29 @@ def test_host_entry_point_is_thread_safe():
     [t.start() for t in th]
     [t.join() for t in th]
     assert not errs, errs
+
+
+def test_lowered_field_comparisons_arithmetic_and_ordering():
+    """Comparisons between two request fields, integer arithmetic on request variables (overflow / division errors make
+    the rule "no match"), lexicographic ordering on a field: valid in the reference's language (rules/rules.rs:45-53 accepts
+    whatever bel compiles), evaluated by the per-request kernel / as start-anchored patterns."""
+    from test_compiler_vs_oracle import _lowered_constructs_case
+
+    rule_sets, batch = _lowered_constructs_case()
+    for rules in rule_sets[::3] + [rule_sets[-1]]:
+        _check(rules, batch)
+
+
+def test_adversarial_input_for_the_gate():
+    """Every 16-byte chunk of the url column is a level-1 hit (the gate's hit bitmap is all ones): nothing overflows, the
+    verdicts stay exact."""
+    rules, payloads, _ = synth.make_ruleset(128)
+    base = synth.RequestStream(config_id=2, payloads=payloads).generate(0, 3_000)
+    reqs = []
+    grams = ["select", "union ", "<script", "../../", "/etc/passwd", "curl/"]
+    for i in range(base.n):
+        g = grams[i % len(grams)]
+        url = "/" + (g * 40)[: 150 + (i % 90)]
+        reqs.append(dict(host=base.field("host", i).decode(), url=url, path="/" + g.strip("/ <")[:8], method="GET",
+                         user_agent=(g * 8)[:60] or "x", ip="10.1.%d.%d" % (i // 250, i % 250), remote_port=1000 + i))
+    _check(rules, pack_requests(reqs))
