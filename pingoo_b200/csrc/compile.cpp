@@ -436,6 +436,9 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
             any = true;
             DfaGroups groups;
             int failed = -1;
+            // (Capping gated units at the shared-memory budget so that each is wholly resident -- 8 url units instead of 2 at 512
+            // rules, 16 instead of 4 at 1 024 -- was measured: no gain at 512 rules, 25 % slower scan at 1 024: candidates walk
+            // more units and CTAs stage more images; the cold-row path is not what limits the candidate scan.)
             if (!build_dfa_groups(M.nfa[f], bundles[cls], opt.max_dfa_states, opt.max_unit_table_bytes, (int)kMaxLatchesPerUnit, &groups, &failed)) {
                 std::string which = failed >= 0 ? M.atoms[bundle_atom[cls][failed]].key : "?";
                 err = "pattern on http_request." + std::string(kFieldNames[f]) + " needs a DFA larger than " +

@@ -270,6 +270,7 @@ __device__ __forceinline__ void prefix_walk(const KParams& p, const UnitDesc& ud
         }
         done = st == abs0 || st == abs1;  // absorbing: nothing can change any more
     };
+#ifndef PGW_EXP_BYTEWALK
     {
         // words are read only while they start before the field's end: a word that starts inside the column ends inside
         // its readable range (pgw_strcol: round_up(length, 32))
@@ -287,8 +288,12 @@ __device__ __forceinline__ void prefix_walk(const KParams& p, const UnitDesc& ud
                 if (k + 4u < n && !done) step((b >> (8u * k)) & 0xFFu);
         }
     }
+    const uint32_t pos0 = s + 8u;
+#else
+    const uint32_t pos0 = s;
+#endif
 #pragma unroll 1
-    for (uint32_t pos = s + 8u; pos < e && !done; ++pos) step((uint32_t)__ldg(col + pos));
+    for (uint32_t pos = pos0; pos < e && !done; ++pos) step((uint32_t)__ldg(col + pos));
     const uint32_t e1 = lds_u16(img + ud.end1_off + 2u * st);
     if (e1 != 0xFFFEu) {
         if (e1 != 0xFFFFu) fire(e1);
@@ -296,45 +301,36 @@ __device__ __forceinline__ void prefix_walk(const KParams& p, const UnitDesc& ud
     }
 }
 
-// Per-request work outside the gate and the scan + the verdict (http_listener.rs:196-264): the small early-exit units
-// (KParams::pdesc, tables in shared memory at `a_img`), end-of-field events of empty fields, the integer / list /
-// country predicates, the gates, the verdict and the service.
-// The scan left, per request, two info words (KParams::info) and the bits of the fired atoms in the request's bitmap
-// row.  Called by all 32 lanes of a converged warp (`valid` false for lanes past the end of the batch, which shadow the
-// last request without storing anything).
-//   no atom true            -> the precomputed verdict `vclean` (the row is never read)
-//   one distinct atom true  -> the tabulated verdict `v1z[atom]`
-//   otherwise               -> the row is completed and the request is appended to the multi list (waf_multi_kernel)
-// Whatever the scan or this function wrote to the row / info words is written back to zero (the scratch invariant).
-__device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, bool valid, uint32_t a_img) {
-    const uint32_t Aw = p.atom_words;
-    const uint32_t FULL = 0xFFFFFFFFu;
-    // everything that does not depend on another load is requested first: the flags, the scan's info words, and the
-    // extents of the fields the early-exit units walk, whose first bytes are then prefetched into L1 -- the walks further
-    // down would otherwise each wait for DRAM in turn (offset -> first byte -> ...)
-    const uint32_t flags = p.flags ? p.flags[r] : 0u;
-    const uint2 inf = *reinterpret_cast<const uint2*>(p.info + 2u * (size_t)r);
-    constexpr uint32_t kPre = 4;   // units whose extents are kept in registers (a program rarely has more)
-    uint32_t ps[kPre], pe[kPre];
-#pragma unroll
-    for (uint32_t k = 0; k < kPre; ++k) {
-        ps[k] = pe[k] = 0u;
-        if (k < p.n_prefix) {
-            const uint32_t* o = p.off[p.pdesc[k].field] + r;
-            ps[k] = o[0];
-            pe[k] = o[1];
-        }
-    }
-#pragma unroll
-    for (uint32_t k = 0; k < kPre; ++k)
-        if (k < p.n_prefix && pe[k] > ps[k]) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.col[p.pdesc[k].field] + ps[k]));
-    uint32_t* const row = p.rows + (size_t)r * Aw;
-    int64_t asn = 0;
-    uint32_t country = (uint32_t)'X' | ((uint32_t)'X' << 8);
-    uint32_t set_mask = 0;
+// What the per-request kernel finds true outside the scan kernel: up to four atoms packed 16 bits each (`n` counts all of
+// them, also those beyond four), and the running largest / smallest true atom in the info-word encoding.
+struct Extras {
+    uint64_t xl;
+    uint32_t n, amax, binv;
+};
+
+// The atoms that become true in the per-request kernel: client address -> {asn, country, ip-set mask} (DIR-24-8 / IPv6
+// index), the small early-exit units (KParams::pdesc, tables in shared memory at `a_img`), end-of-field events of empty
+// fields, the integer / list / country predicates, the rare expression kinds.  With `row` == nullptr the atoms are
+// collected into `ex` (its amax / binv come in initialised from the scan's info words); with a row they are ORed into it
+// (second pass of the few requests with more than four such atoms: collect_extras_row, out of line).
+__device__ __forceinline__ void collect_extras(const KParams& p, uint32_t r, uint32_t a_img, Extras* ex, uint32_t* row) {
 #ifndef PGW_EXP_EPI
 #define PGW_EXP_EPI 0
 #endif
+    uint64_t xl = 0;
+    uint32_t nx = 0, xlast = 0xFFFFFFFFu, amax = ex->amax, binv = ex->binv;
+    auto fn = [&](uint32_t a) {
+        if (row) { row[a >> 5] |= 1u << (a & 31); return; }
+        if (a == xlast) return;   // a sticky accepting state fires at every byte
+        xlast = a;
+        amax = max(amax, a + 1u);
+        binv = max(binv, 0x4000u - a);
+        if (nx < 4u) xl |= (uint64_t)a << (16u * nx);
+        ++nx;
+    };
+    int64_t asn = 0;
+    uint32_t country = (uint32_t)'X' | ((uint32_t)'X' << 8);
+    uint32_t set_mask = 0;
     if (p.need_lpm && !(PGW_EXP_EPI & 2)) {
         const uint8_t* ip16 = p.ip + (size_t)r * 16;
         const bool v6 = p.is_v6[r] != 0;
@@ -354,104 +350,129 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, b
     if (p.asn) asn = p.asn[r];
     if (p.country) country = p.country[r];
 
-    // atoms that become true here, outside the scan kernel
-    auto extras = [&](auto&& fn) {
-        // small early-exit units: one walk over the first bytes of the field
-#pragma unroll
-        for (uint32_t k = 0; k < kPre; ++k)
-            if (!(PGW_EXP_EPI & 1) && k < p.n_prefix && pe[k] > ps[k]) prefix_walk(p, p.pdesc[k], a_img + p.prefix_img[k], p.col[p.pdesc[k].field], ps[k], pe[k], fn);
-        for (uint32_t k = kPre; k < p.n_prefix; ++k) {
-            const UnitDesc& ud = p.pdesc[k];
-            const uint32_t* o = p.off[ud.field] + r;
-            const uint32_t s0 = o[0], e0 = o[1];
-            if (e0 > s0) prefix_walk(p, ud, a_img + p.prefix_img[k], p.col[ud.field], s0, e0, fn);
+    // small early-exit units: one walk over the first bytes of the field
+    for (uint32_t k = 0; k < p.n_prefix && !(PGW_EXP_EPI & 1); ++k) {
+        const UnitDesc& ud = p.pdesc[k];
+        const uint32_t* o = p.off[ud.field] + r;
+        const uint32_t s0 = o[0], e0 = o[1];
+        if (e0 > s0) prefix_walk(p, ud, a_img + p.prefix_img[k], p.col[ud.field], s0, e0, fn);
+    }
+    // end-of-field events of EMPTY fields (they reach neither the scan nor a prefix walk)
+    for (uint32_t k = 0; k < p.n_start_end; ++k) {
+        const UnitDesc& ud = p.units[p.start_end_unit[k]];
+        const uint32_t* o = p.off[ud.field] + r;
+        if (o[0] != o[1]) continue;
+        const uint32_t a = __ldg(p.end_idx + ud.end_base + ud.start_state), b = __ldg(p.end_idx + ud.end_base + ud.start_state + 1);
+        for (uint32_t i = a; i < b; ++i) {
+            const uint32_t e = __ldg(p.end_events + i);
+            if ((e >> kEvKindShift) == 0u) fn(e & kEvAtomMask);  // latch kinds cannot fire on an empty field
         }
-        // end-of-field events of EMPTY fields (they reach neither the scan nor a prefix walk)
-        for (uint32_t k = 0; k < p.n_start_end; ++k) {
-            const UnitDesc& ud = p.units[p.start_end_unit[k]];
-            const uint32_t* o = p.off[ud.field] + r;
-            if (o[0] != o[1]) continue;
-            const uint32_t a = __ldg(p.end_idx + ud.end_base + ud.start_state), b = __ldg(p.end_idx + ud.end_base + ud.start_state + 1);
-            for (uint32_t i = a; i < b; ++i) {
-                const uint32_t e = __ldg(p.end_events + i);
-                if ((e >> kEvKindShift) == 0u) fn(e & kEvAtomMask);  // latch kinds cannot fire on an empty field
-            }
-        }
-        // integer predicates, one feature at a time: the feature's quick reject (compile.hpp) settles almost every request
+    }
+    // integer predicates, one feature at a time: the feature's quick reject (compile.hpp) settles almost every request
 #pragma unroll 1
-        for (uint32_t fe = 0; fe < 7u; ++fe) {
-            const uint32_t b0 = p.ns_begin[fe], b1 = p.ns_begin[fe + 1u];
-            if (b0 == b1 || (PGW_EXP_EPI & 4)) continue;
-            int64_t x;
-            if (fe == 0u) x = p.port ? (int64_t)p.port[r] : 0;
-            else if (fe == 1u) x = asn;
-            else {
-                const uint32_t* o = p.off[fe - 2u] + r;
-                x = (int64_t)(o[1] - o[0]);
-            }
-            if (x >= p.ns_lo[fe] && x <= p.ns_hi[fe] && (x < p.ns_vmin[fe] || x > p.ns_vmax[fe])) continue;
-            for (uint32_t i = b0; i < b1; ++i) {
-                const NsAtom a = p.n_ns <= kMaxConstNs ? p.nsd[i] : p.ns[i];
-                bool v = false;
-                if (a.kind == 1) {
-                    switch (a.op) {
-                        case 0: v = x == a.cval; break;
-                        case 1: v = x != a.cval; break;
-                        case 2: v = x < a.cval; break;
-                        case 3: v = x <= a.cval; break;
-                        case 4: v = x > a.cval; break;
-                        default: v = x >= a.cval; break;
-                    }
-                } else {
-                    uint32_t l = p.iset_off[a.set_id], h = p.iset_off[a.set_id + 1];
-                    while (l < h) {
-                        uint32_t m = (l + h) >> 1;
-                        int64_t mv = __ldg(p.iset_vals + m);
-                        if (mv == x) { v = true; break; }
-                        if (mv < x) l = m + 1;
-                        else h = m;
-                    }
-                }
-                if (v) fn(a.atom);
-            }
+    for (uint32_t fe = 0; fe < 7u; ++fe) {
+        const uint32_t b0 = p.ns_begin[fe], b1 = p.ns_begin[fe + 1u];
+        if (b0 == b1 || (PGW_EXP_EPI & 4)) continue;
+        int64_t x;
+        if (fe == 0u) x = p.port ? (int64_t)p.port[r] : 0;
+        else if (fe == 1u) x = asn;
+        else {
+            const uint32_t* o = p.off[fe - 2u] + r;
+            x = (int64_t)(o[1] - o[0]);
         }
-        for (uint32_t i = p.ns_begin[7]; i < p.rare_begin && !(PGW_EXP_EPI & 8); ++i) {
+        if (x >= p.ns_lo[fe] && x <= p.ns_hi[fe] && (x < p.ns_vmin[fe] || x > p.ns_vmax[fe])) continue;
+        for (uint32_t i = b0; i < b1; ++i) {
             const NsAtom a = p.n_ns <= kMaxConstNs ? p.nsd[i] : p.ns[i];
             bool v = false;
-            if (a.kind == 3) {  // IP_SET
-                v = (set_mask >> a.set_id) & 1u;
-            } else {  // COUNTRY_SET
-                uint32_t c0 = (country & 0xFFu) - 'A', c1 = ((country >> 8) & 0xFFu) - 'A';
-                if (c0 < 26u && c1 < 26u) {
-                    uint32_t bit = c0 * 26u + c1;
-                    v = (__ldg(p.cset + a.set_id * kCountryWords + (bit >> 5)) >> (bit & 31)) & 1u;
+            if (a.kind == 1) {
+                switch (a.op) {
+                    case 0: v = x == a.cval; break;
+                    case 1: v = x != a.cval; break;
+                    case 2: v = x < a.cval; break;
+                    case 3: v = x <= a.cval; break;
+                    case 4: v = x > a.cval; break;
+                    default: v = x >= a.cval; break;
+                }
+            } else {
+                uint32_t l = p.iset_off[a.set_id], h = p.iset_off[a.set_id + 1];
+                while (l < h) {
+                    uint32_t m = (l + h) >> 1;
+                    int64_t mv = __ldg(p.iset_vals + m);
+                    if (mv == x) { v = true; break; }
+                    if (mv < x) l = m + 1;
+                    else h = m;
                 }
             }
             if (v) fn(a.atom);
         }
-        // integer expressions and field-against-field predicates (rare in rule sets): one out-of-line call
-        if (p.n_rare) {
-            uint32_t m = rare_atoms(p, r, asn);
-            while (m) {
-                const uint32_t k = (uint32_t)__ffs(m) - 1u;
-                m &= m - 1u;
-                fn((p.n_ns <= kMaxConstNs ? p.nsd[p.rare_begin + k] : p.ns[p.rare_begin + k]).atom);
+    }
+    for (uint32_t i = p.ns_begin[7]; i < p.rare_begin && !(PGW_EXP_EPI & 8); ++i) {
+        const NsAtom a = p.n_ns <= kMaxConstNs ? p.nsd[i] : p.ns[i];
+        bool v = false;
+        if (a.kind == 3) {  // IP_SET
+            v = (set_mask >> a.set_id) & 1u;
+        } else {  // COUNTRY_SET
+            uint32_t c0 = (country & 0xFFu) - 'A', c1 = ((country >> 8) & 0xFFu) - 'A';
+            if (c0 < 26u && c1 < 26u) {
+                uint32_t bit = c0 * 26u + c1;
+                v = (__ldg(p.cset + a.set_id * kCountryWords + (bit >> 5)) >> (bit & 31)) & 1u;
             }
         }
-    };
+        if (v) fn(a.atom);
+    }
+    // integer expressions and field-against-field predicates (rare in rule sets): one out-of-line call
+    if (p.n_rare) {
+        uint32_t m = rare_atoms(p, r, asn);
+        while (m) {
+            const uint32_t k = (uint32_t)__ffs(m) - 1u;
+            m &= m - 1u;
+            fn((p.n_ns <= kMaxConstNs ? p.nsd[p.rare_begin + k] : p.ns[p.rare_begin + k]).atom);
+        }
+    }
+    ex->xl = xl;
+    ex->n = nx;
+    ex->amax = amax;
+    ex->binv = binv;
+}
 
-    uint32_t amax = inf.x, binv = inf.y;  // largest true atom + 1 (0: none), 0x4000 - smallest true atom
-    // the atoms found here, packed 16 bits each (up to four; a request with more walks `extras` a second time)
-    uint64_t xl = 0;
-    uint32_t nx = 0, xlast = 0xFFFFFFFFu;
-    extras([&](uint32_t a) {
-        if (a == xlast) return;   // a sticky accepting state fires at every byte
-        xlast = a;
-        amax = max(amax, a + 1u);
-        binv = max(binv, 0x4000u - a);
-        if (nx < 4u) xl |= (uint64_t)a << (16u * nx);
-        ++nx;
-    });
+__device__ __noinline__ void collect_extras_row(const KParams& p, uint32_t r, uint32_t a_img, uint32_t* row) {
+    Extras ex;
+    ex.amax = ex.binv = 0u;
+    collect_extras(p, r, a_img, &ex, row);
+}
+
+// Per-request work outside the gate and the scan + the verdict (http_listener.rs:196-264): collect_extras, the gates,
+// the verdict and the service.
+// The scan left, per request, two info words (KParams::info) and the bits of the fired atoms in the request's bitmap
+// row.  Called by all 32 lanes of a converged warp (`valid` false for lanes past the end of the batch, which shadow the
+// last request without storing anything).
+//   no atom true            -> the precomputed verdict `vclean` (the row is never read)
+//   one distinct atom true  -> the tabulated verdict `v1z[atom]`
+//   two, disjoint rule sets -> the earlier of their `v1z` entries
+//   otherwise               -> the row is completed and the request is appended to the multi list (waf_multi_kernel)
+// Whatever the scan or this function wrote to the row / info words is written back to zero (the scratch invariant).
+__device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, bool valid, uint32_t a_img) {
+    const uint32_t Aw = p.atom_words;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    // everything that does not depend on another load is requested first: the flags, the scan's info words, and the
+    // extents of the fields the early-exit units walk, whose first bytes are prefetched -- the walks would otherwise each
+    // wait for DRAM in turn (offset -> first byte -> ...)
+    const uint32_t flags = p.flags ? p.flags[r] : 0u;
+    const uint2 inf = *reinterpret_cast<const uint2*>(p.info + 2u * (size_t)r);
+#pragma unroll
+    for (uint32_t k = 0; k < 4u; ++k)
+        if (k < p.n_prefix) {
+            const uint32_t* o = p.off[p.pdesc[k].field] + r;
+            const uint32_t s0 = o[0];
+            if (o[1] > s0) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.col[p.pdesc[k].field] + s0));
+        }
+    uint32_t* const row = p.rows + (size_t)r * Aw;
+    Extras ex;
+    ex.amax = inf.x;   // largest true atom + 1 (0: none), 0x4000 - smallest true atom
+    ex.binv = inf.y;
+    collect_extras(p, r, a_img, &ex, nullptr);
+    const uint32_t amax = ex.amax, binv = ex.binv, nx = ex.n;
+    const uint64_t xl = ex.xl;
     const bool any_atom = amax != 0u;
     const bool single = any_atom && (amax - 1u == 0x4000u - binv);
     const bool multi = any_atom && !single;
@@ -481,7 +502,7 @@ __device__ __forceinline__ void request_epilogue(const KParams& p, uint32_t r, b
                 row[a >> 5] |= 1u << (a & 31);
             }
         } else {
-            extras([&](uint32_t a) { row[a >> 5] |= 1u << (a & 31); });
+            collect_extras_row(p, r, a_img, row);
         }
     }
 

@@ -170,6 +170,11 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
         if (*s_skip) continue;
         mbar_wait(s_bar, staged & 1u);
         ++staged;
+#ifdef PGW_EXP_SCANLOG
+        unsigned long long t_unit0 = 0;
+        uint32_t n_strings = 0, n_cold = 0, n_iter = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_unit0));
+#endif
 
         const uint32_t C2 = 2u * cu.n_classes, D0 = cu.start_state, trap = cu.hot_states, lim = cu.lim, acclo = cu.acc_lo;
         const uint32_t abs0 = cu.abs0, abs1 = cu.abs1;
@@ -304,6 +309,9 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                 if (!__any_sync(FULL, pend) && pool_next == pool_end && !ah_valid) break;
                 continue;
             }
+#ifdef PGW_EXP_SCANLOG
+            ++n_iter;
+#endif
 
             // ---- walk the bytes of this chunk that belong to the field (no per-word vote: some lane almost always has
             //      bytes in every word, the vote cost more than the words it skipped) ----
@@ -377,8 +385,22 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
                 }
                 have = false;
                 state = 0;  // an idle lane must not look like it sits in a cold or accepting state
+#ifdef PGW_EXP_SCANLOG
+                ++n_strings;
+#endif
             }
         }
+#ifdef PGW_EXP_SCANLOG
+        {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            // per warp: lane 0 reports; strings summed over the warp
+            for (int o = 16; o; o >>= 1) n_strings += __shfl_xor_sync(FULL, n_strings, o);
+            if (lane == 0 && (tid >> 5) % 8 == 0)
+                printf("SCANLOG cta %u warp %u unit %u uk %u N %u us %llu..%llu strings %u iters %u\n", blockIdx.x, tid >> 5, u, uk, N, t_unit0 / 1000ull % 100000000ull,
+                       t1 / 1000ull % 100000000ull, n_strings, n_iter);
+        }
+#endif
     }
 }
 
