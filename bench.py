@@ -216,16 +216,16 @@ def cpu_baseline_run(rules, lists, mmdb, batch, sample, threads, repeats=1):
     return sub.n / best, sub.n, out
 
 
-def traffic_for(cfg_id, kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture of this workload (profiles/latest_traffic.json),
-    or None when no capture of this configuration has been committed."""
+def traffic_for(cfg_id, kernel, requests):
+    """DRAM bytes per launch of `kernel`: per-request traffic from the committed ncu capture of this workload
+    (profiles/latest_traffic.json) x the requests of one batch, or None when no capture of this configuration is committed."""
     tpath = os.path.join(ROOT, "profiles", "latest_traffic.json")
     if not os.path.exists(tpath):
         return None
     with open(tpath) as f:
         tj = json.load(f)
     e = tj.get(f"config {cfg_id}", {}).get(kernel)
-    return e["dram_bytes_per_launch"] if e else None
+    return e["dram_bytes_per_request"] * requests if e else None
 
 
 def run_config(cfg_id, args, rank, local_rank, world, dist, steps, with_e2e=True, with_cpu=True, sustain_s=0.0, n_override=None):
@@ -397,7 +397,7 @@ def run_config(cfg_id, args, rank, local_rank, world, dist, steps, with_e2e=True
                    "scan_units": info.n_scan_units, "dfa_states": info.total_dfa_states, "gate_grams": info.gate_grams,
                    "verdict_hist_allow_block_captcha_bypass": hist, "verdict_mismatches_vs_oracle": mismatches, "parallelism": f"dp{world}"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic_for(cfg_id, names[dom].split("+")[0]), "peak_source": peak_src, "kernel": names[dom], "kernel_ms": kernel_ms,
+                     "traffic": traffic_for(cfg_id, names[dom].split("+")[0], n_all / len(batches)), "peak_source": peak_src, "kernel": names[dom], "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_launch": kernel_alg, "kernel_ms_per_batch": per_kernel, "batches_timed": int(kbatches),
                      "path_ms_per_batch": path_ms, "path_algorithmic_bytes_per_batch": alg_total / len(batches),
                      "path_achieved": path_achieved, "path_frac": path_achieved / peak},

@@ -94,7 +94,7 @@ typedef struct pgw_info {
     uint64_t last_h2d_bytes, last_d2h_bytes; /* bytes moved by the last pgw_evaluate_batch_host call */
     uint32_t gated_fields_mask;   /* fields in front of whose DFAs the candidate gate runs */
     uint32_t gate_grams;          /* 4-byte grams in the gate bitmaps, all fields */
-    uint64_t gate_smem_bytes;     /* shared memory of the gate kernel (largest field's two bitmaps) */
+    uint64_t gate_smem_bytes;     /* shared memory of the gate kernel (the level-1 bitmaps of all gated fields) */
 } pgw_info;
 
 /* rules::compile_expression(&str) -> Result<CompiledExpression, Error>   (rules/rules.rs:45-53) */

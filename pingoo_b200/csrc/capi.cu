@@ -393,6 +393,9 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     P.n_rare = H.n_rare;
     P.rare_begin = P.n_ns - H.n_rare;
     for (int g = 0; g < 9; ++g) P.ns_begin[g] = H.ns_begin[g];
+    P.n_feat_used = 0;
+    for (uint32_t g = 0; g < 7; ++g)
+        if (H.ns_begin[g] < H.ns_begin[g + 1]) P.feat_used[P.n_feat_used++] = g;
     for (int f = 0; f < 7; ++f) { P.ns_lo[f] = H.ns_lo[f]; P.ns_hi[f] = H.ns_hi[f]; P.ns_vmin[f] = H.ns_vmin[f]; P.ns_vmax[f] = H.ns_vmax[f]; }
     memset(P.nsd, 0, sizeof P.nsd);
     for (size_t i = 0; i < H.ns_atoms.size() && i < kMaxConstNs; ++i) P.nsd[i] = H.ns_atoms[i];
@@ -633,6 +636,11 @@ int pgw_evaluate_batch_routed_host(pgw_ruleset* rs, const pgw_batch* b, uint32_t
     if (H.needs_port) up(d.remote_port, b->remote_port, 0, (size_t)n * 4);
     if (geo_cols) { up(d.asn, b->asn, 0, (size_t)n * 8); up(d.country, b->country, 0, (size_t)n * 2); }
     if (b->flags) up(d.flags, b->flags, 0, n);
+    // the kernels read whole 16-byte chunks up to round_up(total, 32): the bytes past the column's end are never
+    // interpreted as request data, but they are read -- give them a defined value
+    for (int f = 0; f < 5; ++f)
+        if (H.field_slot[f] >= 0 && ((H.scanned_fields_mask >> f) & 1) && ce == cudaSuccess)
+            ce = cudaMemsetAsync((uint8_t*)dc[f]->bytes + hc[f]->offsets[n], 0, 64, cs);
     for (uint32_t a = 0; a < n; a += per, ++k) {
         const uint32_t z = a + per < n ? a + per : n, m = z - a;
         for (int f = 0; f < 5; ++f)

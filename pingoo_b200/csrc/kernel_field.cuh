@@ -407,7 +407,10 @@ __global__ void __launch_bounds__(kFsThreads, 1) waf_field_scan_kernel(const __g
 // Verdicts once every unit has been scanned: one thread per request (request_epilogue).  The tables of the small
 // early-exit units it walks are staged into the CTA's shared memory first.
 constexpr int kEpiThreads = 512;
-__global__ void __launch_bounds__(kEpiThreads, 3) waf_epilogue_kernel(const __grid_constant__ KParams p) {
+#ifndef PGW_EPI_CTAS
+#define PGW_EPI_CTAS 3
+#endif
+__global__ void __launch_bounds__(kEpiThreads, PGW_EPI_CTAS) waf_epilogue_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(256) uint8_t esm[];
     uint8_t* img = esm + ((0u - smem_u32(esm)) & 255u);   // class maps sit on 256-byte boundaries
     for (uint32_t k = 0; k < p.n_prefix; ++k) {
