@@ -437,7 +437,12 @@ def main():
         # this arm times the C restatement of its semantics (oracle/) on all host cores.  Rank 0 only.
         if rank != 0:
             return
-        desc, rules, lists, mmdb, batches = build_workload(cfg, 0, args.requests or args.cpu_sample)
+        # a step = a bounded sample of the workload (about 10 s of CPU work): the naive oracle scans the 100 k-entry list
+        # linearly per evaluation on config 3 and walks 8 KB URIs with a Pike VM on config 5
+        sample_n = {3: 50_000, 5: 10_000}.get(cfg, args.cpu_sample)
+        sample_n = min(sample_n, args.cpu_sample)
+        desc, rules, lists, mmdb, batches = build_workload(cfg, 0, args.requests or sample_n)
+        args.cpu_sample = sample_n
         vals = []
         for i in range(args.warmup + args.steps):
             v, n_s, _ = cpu_baseline_run(rules, lists, mmdb, batches[0], args.cpu_sample, ncores)

@@ -307,24 +307,19 @@ __device__ __forceinline__ void collect_extras(const KParams& p, uint32_t r, uin
     int64_t asn = 0;
     uint32_t country = (uint32_t)'X' | ((uint32_t)'X' << 8);
     uint32_t set_mask = 0;
-    if (p.need_lpm && !(PGW_EXP_EPI & 2)) {
-        const uint8_t* ip16 = p.ip + (size_t)r * 16;
-        const bool v6 = p.is_v6[r] != 0;
-        const LpmLeaf lf = p.leaves[lpm_lookup(p, ip16, v6)];
-        set_mask = lf.set_mask;
-        if (p.geo_loaded) {
-            // geoip.rs:74-76: loopback / multicast are never looked up
-            bool skip;
-            if (!v6) skip = ip16[0] == 127 || (ip16[0] >> 4) == 0xE;
-            else {
-                const uint32_t* w = reinterpret_cast<const uint32_t*>(ip16);
-                skip = ip16[0] == 0xFF || (w[0] == 0 && w[1] == 0 && w[2] == 0 && w[3] == 0x01000000u);
-            }
-            if (!skip) { asn = lf.asn; country = lf.country; }
+    // client address -> leaf, in two steps around the early-exit walks: the DIR-24-8 word (or, for IPv6, nothing yet) is
+    // requested first, so that its DRAM latency passes while the walks run; the leaf is fetched after them
+    const bool lpm = p.need_lpm && !(PGW_EXP_EPI & 2);
+    const uint8_t* ip16 = p.ip + (size_t)r * 16;
+    bool v6 = false;
+    uint32_t dir_e = 0, ip_host = 0;
+    if (lpm) {
+        v6 = p.is_v6[r] != 0;
+        if (!v6) {
+            ip_host = __byte_perm(*reinterpret_cast<const uint32_t*>(ip16), 0, 0x0123);  // network order -> host integer
+            dir_e = __ldg(p.dir24 + (ip_host >> 8));
         }
     }
-    if (p.asn) asn = p.asn[r];
-    if (p.country) country = p.country[r];
 
     // small early-exit units: one walk over the first bytes of the field
     for (uint32_t k = 0; k < p.n_prefix && !(PGW_EXP_EPI & 1); ++k) {
@@ -344,6 +339,25 @@ __device__ __forceinline__ void collect_extras(const KParams& p, uint32_t r, uin
             if ((e >> kEvKindShift) == 0u) fn(e & kEvAtomMask);  // latch kinds cannot fire on an empty field
         }
     }
+    if (lpm) {
+        uint32_t leaf;
+        if (!v6) leaf = (dir_e & 0x80000000u) ? __ldg(p.tbl8 + ((dir_e & 0x7FFFFFFFu) << 8) + (ip_host & 0xFFu)) : dir_e;
+        else leaf = lpm_lookup(p, ip16, true);
+        const LpmLeaf lf = p.leaves[leaf];
+        set_mask = lf.set_mask;
+        if (p.geo_loaded) {
+            // geoip.rs:74-76: loopback / multicast are never looked up
+            bool skip;
+            if (!v6) skip = ip16[0] == 127 || (ip16[0] >> 4) == 0xE;
+            else {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(ip16);
+                skip = ip16[0] == 0xFF || (w[0] == 0 && w[1] == 0 && w[2] == 0 && w[3] == 0x01000000u);
+            }
+            if (!skip) { asn = lf.asn; country = lf.country; }
+        }
+    }
+    if (p.asn) asn = p.asn[r];
+    if (p.country) country = p.country[r];
     // integer predicates, one feature at a time: the feature's quick reject (compile.hpp) settles almost every request
 #pragma unroll 1
     for (uint32_t j = 0; j < p.n_feat_used && !(PGW_EXP_EPI & 4); ++j) {
