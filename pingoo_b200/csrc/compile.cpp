@@ -615,8 +615,8 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
             if (group(a) > N_INT_FEATS) { H.n_rare++; continue; }
             H.ns_begin[group(a) + 1]++;
         }
-        if (H.n_rare > 32) {
-            err = "more than 32 integer-expression / field-comparison predicates";
+        if (H.n_rare > 64) {
+            err = "more than 64 integer-expression / field-comparison predicates";
             return false;
         }
         for (int g = 0; g <= N_INT_FEATS; ++g) H.ns_begin[g + 1] += H.ns_begin[g];

@@ -220,9 +220,9 @@ __device__ __noinline__ bool field_cmp_eval(const KParams& p, uint32_t f1, uint3
     return false;
 }
 
-// The INT_EXPR / FIELD_CMP predicates of a program (ns[rare_begin .. rare_begin + n_rare), at most 32): bit k = predicate k holds
-__device__ __noinline__ uint32_t rare_atoms(const KParams& p, uint32_t r, int64_t asn) {
-    uint32_t m = 0;
+// The INT_EXPR / FIELD_CMP predicates of a program (ns[rare_begin .. rare_begin + n_rare), at most 64): bit k = predicate k holds
+__device__ __noinline__ uint64_t rare_atoms(const KParams& p, uint32_t r, int64_t asn) {
+    uint64_t m = 0;
     for (uint32_t k = 0; k < p.n_rare; ++k) {
         const NsAtom a = p.ns[p.rare_begin + k];
         bool v = false;
@@ -243,7 +243,7 @@ __device__ __noinline__ uint32_t rare_atoms(const KParams& p, uint32_t r, int64_
         } else {
             v = field_cmp_eval(p, a.feat, a.set_id, a.op, r);
         }
-        if (v) m |= 1u << k;
+        if (v) m |= 1ull << k;
     }
     return m;
 }
@@ -412,10 +412,10 @@ __device__ __forceinline__ void collect_extras(const KParams& p, uint32_t r, uin
     }
     // integer expressions and field-against-field predicates (rare in rule sets): one out-of-line call
     if (p.n_rare) {
-        uint32_t m = rare_atoms(p, r, asn);
+        uint64_t m = rare_atoms(p, r, asn);
         while (m) {
-            const uint32_t k = (uint32_t)__ffs(m) - 1u;
-            m &= m - 1u;
+            const uint32_t k = (uint32_t)__ffsll((long long)m) - 1u;
+            m &= m - 1ull;
             fn((p.n_ns <= kMaxConstNs ? p.nsd[p.rare_begin + k] : p.ns[p.rare_begin + k]).atom);
         }
     }

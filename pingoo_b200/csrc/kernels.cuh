@@ -55,7 +55,7 @@ struct KParams {
     uint32_t n_ns;
     uint32_t ns_begin[9];       // group g = ns[ns_begin[g], ns_begin[g + 1]); groups 0..6 = IntFeat, 7 = sets
     uint32_t n_feat_used, feat_used[7];   // the integer features that have predicates (groups with ns_begin[g] < ns_begin[g + 1])
-    uint32_t rare_begin, n_rare;  // the INT_EXPR / FIELD_CMP predicates: the last n_rare (<= 32) entries of ns
+    uint32_t rare_begin, n_rare;  // the INT_EXPR / FIELD_CMP predicates: the last n_rare (<= 64) entries of ns
     int64_t ns_lo[7], ns_hi[7], ns_vmin[7], ns_vmax[7];  // quick reject of a whole integer group (compile.hpp)
     const uint16_t* code;
     const uint32_t* rule_off;

@@ -112,7 +112,8 @@ struct BV {
 struct Sym {
     enum K : uint8_t {
         ERR, NUL, BOOL, INT_C, UINT_C, FLOAT_C, STR_C, BYTES_C, LIST_C, LIST_REF, MAP_C,
-        MAP_LISTS, MAP_HTTP, MAP_CLIENT, STR_FIELD, INT_FEAT, INT_EXPR, IP_VAR, COUNTRY_VAR
+        MAP_LISTS, MAP_HTTP, MAP_CLIENT, STR_FIELD, INT_FEAT, INT_EXPR, IP_VAR, COUNTRY_VAR,
+        CHOICE   // c ? x : y with non-boolean branches on a request-dependent condition: bv = the condition, items = {x, y}
     } k = ERR;
     std::vector<int64_t> prog;   // INT_EXPR: postfix tokens (program.hpp IntTok)
     BV bv;
@@ -559,32 +560,14 @@ struct Lowerer {
                 else return err();  // undeclared reference -> runtime error
                 return s;
             }
-            case Expr::MEMBER: return member(lower(*e.kids[0]), e.name);
+            case Expr::MEMBER: {
+                Sym b0 = lower(*e.kids[0]);
+                return lift1(b0, [&](const Sym& b) { return member(b, e.name); });
+            }
             case Expr::INDEX: {
-                Sym base = lower(*e.kids[0]);
-                Sym ix = lower(*e.kids[1]);
-                if (base.k == Sym::ERR || ix.k == Sym::ERR) return err();
-                if (base.k == Sym::MAP_HTTP || base.k == Sym::MAP_CLIENT || base.k == Sym::MAP_LISTS) {
-                    if (ix.k != Sym::STR_C) {
-                        if (!is_const(ix)) unsupported(e, "map index by a request variable");
-                        return err();
-                    }
-                    return member(base, ix.s);
-                }
-                if (base.k == Sym::LIST_C || base.k == Sym::LIST_REF) {
-                    if (ix.k != Sym::INT_C) {
-                        if (!is_const(ix)) unsupported(e, "list index by a request variable");
-                        return err();
-                    }
-                    return list_elem(base, ix.i);
-                }
-                if (base.k == Sym::MAP_C) {
-                    if (!is_const(ix)) unsupported(e, "map index by a request variable");
-                    for (size_t k = 0; k + 1 < base.items.size(); k += 2)
-                        if (const_equal(base.items[k], ix) == 1) return base.items[k + 1];
-                    return err();
-                }
-                return err();
+                Sym base0 = lower(*e.kids[0]);
+                Sym ix0 = lower(*e.kids[1]);
+                return lift2(base0, ix0, [&](const Sym& base, const Sym& ix) { return index_on(e, base, ix); });
             }
             case Expr::CALL: {
                 for (auto& k : e.kids) (void)lower(*k);  // surface unsupported constructs in arguments
@@ -592,44 +575,16 @@ struct Lowerer {
             }
             case Expr::METHOD: return method(e);
             case Expr::UNARY: {
-                Sym x = lower(*e.kids[0]);
-                if (e.op == Expr::OP_NOT) {
-                    BV b = as_bool(x);
-                    return boolean(P.mk_and(P.mk_not(b.t), P.mk_not(b.e)), b.e);
-                }
-                // negation
-                if (x.k == Sym::INT_C) {
-                    if (x.i == INT64_MIN) return err();
-                    return const_int(-x.i);
-                }
-                if (x.k == Sym::FLOAT_C) { x.f = -x.f; return x; }
-                if (x.k == Sym::INT_FEAT || x.k == Sym::INT_EXPR) {
-                    Sym r;
-                    r.k = Sym::INT_EXPR;
-                    append_int(r.prog, x);
-                    r.prog.push_back(tok(IT_NEG));
-                    return r;
-                }
-                return err();
+                Sym x0 = lower(*e.kids[0]);
+                if (x0.k == Sym::CHOICE) return lift1(x0, [&](const Sym& v) { return unary_on(e, v); });
+                return unary_on(e, x0);
             }
             case Expr::BINARY: return binary(e);
             case Expr::TERNARY: {
                 Sym c = lower(*e.kids[0]);
                 Sym x = lower(*e.kids[1]);
                 Sym y = lower(*e.kids[2]);
-                BV cb = as_bool(c);
-                if (P.is_const(cb.t) && P.is_const(cb.e)) {
-                    if (P.const_value(cb.e)) return err();
-                    return P.const_value(cb.t) ? x : y;
-                }
-                if ((x.k == Sym::BOOL || x.k == Sym::ERR) && (y.k == Sym::BOOL || y.k == Sym::ERR)) {
-                    BV xb = as_bool(x), yb = as_bool(y);
-                    int cf = P.mk_and(P.mk_not(cb.t), P.mk_not(cb.e));
-                    int t = P.mk_or(P.mk_and(cb.t, xb.t), P.mk_and(cf, yb.t));
-                    int er = P.mk_or(cb.e, P.mk_or(P.mk_and(cb.t, xb.e), P.mk_and(cf, yb.e)));
-                    return boolean(t, er);
-                }
-                unsupported(e, "conditional (?:) selecting non-boolean values on a request-dependent condition");
+                return lift1(c, [&](const Sym& cc) { return select(as_bool(cc), x, y); });
             }
             case Expr::LIST: {
                 Sym l;
@@ -655,6 +610,88 @@ struct Lowerer {
             }
         }
         return err();
+    }
+
+    Sym index_on(const Expr& e, const Sym& base, const Sym& ix) {
+        if (base.k == Sym::ERR || ix.k == Sym::ERR) return err();
+        if (base.k == Sym::MAP_HTTP || base.k == Sym::MAP_CLIENT || base.k == Sym::MAP_LISTS) {
+            if (ix.k != Sym::STR_C) {
+                if (!is_const(ix)) unsupported(e, "map index by a request variable");
+                return err();
+            }
+            return member(base, ix.s);
+        }
+        if (base.k == Sym::LIST_C || base.k == Sym::LIST_REF) {
+            if (ix.k != Sym::INT_C) {
+                if (!is_const(ix)) unsupported(e, "list index by a request variable");
+                return err();
+            }
+            return list_elem(base, ix.i);
+        }
+        if (base.k == Sym::MAP_C) {
+            if (!is_const(ix)) unsupported(e, "map index by a request variable");
+            for (size_t k = 0; k + 1 < base.items.size(); k += 2)
+                if (const_equal(base.items[k], ix) == 1) return base.items[k + 1];
+            return err();
+        }
+        return err();
+    }
+
+    Sym unary_on(const Expr& e, Sym x) {
+        if (e.op == Expr::OP_NOT) {
+            BV b = as_bool(x);
+            return boolean(P.mk_and(P.mk_not(b.t), P.mk_not(b.e)), b.e);
+        }
+        // negation
+        if (x.k == Sym::INT_C) {
+            if (x.i == INT64_MIN) return err();
+            return const_int(-x.i);
+        }
+        if (x.k == Sym::FLOAT_C) { x.f = -x.f; return x; }
+        if (x.k == Sym::INT_FEAT || x.k == Sym::INT_EXPR) {
+            Sym r;
+            r.k = Sym::INT_EXPR;
+            append_int(r.prog, x);
+            r.prog.push_back(tok(IT_NEG));
+            return r;
+        }
+        return err();
+    }
+
+    // c ? x : y.  Boolean (or erroneous) branches fold into formulas at once; other values stay a CHOICE until the operation
+    // that consumes them has been applied to both branches (lift1 / lift2): the condition decides which branch is evaluated,
+    // an error in the branch not taken does not count (SEMANTICS.md A5 / A8).
+    Sym select(const BV& cb, const Sym& x, const Sym& y) {
+        if (P.is_const(cb.t) && P.is_const(cb.e)) {
+            if (P.const_value(cb.e)) return err();
+            return P.const_value(cb.t) ? x : y;
+        }
+        if ((x.k == Sym::BOOL || x.k == Sym::ERR) && (y.k == Sym::BOOL || y.k == Sym::ERR)) {
+            BV xb = as_bool(x), yb = as_bool(y);
+            if (x.k == Sym::ERR) { xb.t = 0; xb.e = 1; }
+            if (y.k == Sym::ERR) { yb.t = 0; yb.e = 1; }
+            const int cf = P.mk_and(P.mk_not(cb.t), P.mk_not(cb.e));
+            const int t = P.mk_or(P.mk_and(cb.t, xb.t), P.mk_and(cf, yb.t));
+            const int er = P.mk_or(cb.e, P.mk_or(P.mk_and(cb.t, xb.e), P.mk_and(cf, yb.e)));
+            return boolean(t, er);
+        }
+        Sym c;
+        c.k = Sym::CHOICE;
+        c.bv = cb;
+        c.items.push_back(x);
+        c.items.push_back(y);
+        return c;
+    }
+    template <class F>
+    Sym lift1(const Sym& a, F&& f) {
+        if (a.k != Sym::CHOICE) return f(a);
+        return select(a.bv, lift1(a.items[0], f), lift1(a.items[1], f));
+    }
+    template <class F>
+    Sym lift2(const Sym& a, const Sym& b, F&& f) {
+        if (a.k == Sym::CHOICE) return select(a.bv, lift2(a.items[0], b, f), lift2(a.items[1], b, f));
+        if (b.k == Sym::CHOICE) return select(b.bv, lift2(a, b.items[0], f), lift2(a, b.items[1], f));
+        return f(a, b);
     }
 
     Sym member(const Sym& base, const std::string& name) {
@@ -719,9 +756,21 @@ struct Lowerer {
     }
 
     Sym method(const Expr& e) {
-        Sym recv = lower(*e.kids[0]);
-        std::vector<Sym> args;
-        for (size_t k = 1; k < e.kids.size(); ++k) args.push_back(lower(*e.kids[k]));
+        Sym recv0 = lower(*e.kids[0]);
+        std::vector<Sym> args0;
+        for (size_t k = 1; k < e.kids.size(); ++k) args0.push_back(lower(*e.kids[k]));
+        // a conditional value as receiver or (single) argument: the method is applied to both branches
+        if (recv0.k == Sym::CHOICE || (args0.size() == 1 && args0[0].k == Sym::CHOICE)) {
+            if (args0.size() > 1) unsupported(e, "conditional (?:) value passed to a method with several arguments");
+            if (args0.empty()) return lift1(recv0, [&](const Sym& r) { return method_on(e, r, {}); });
+            return lift2(recv0, args0[0], [&](const Sym& r, const Sym& a) { return method_on(e, r, std::vector<Sym>(1, a)); });
+        }
+        for (auto& a : args0)
+            if (a.k == Sym::CHOICE) unsupported(e, "conditional (?:) value passed to a method with several arguments");
+        return method_on(e, recv0, args0);
+    }
+
+    Sym method_on(const Expr& e, const Sym& recv, const std::vector<Sym>& args) {
         if (recv.k == Sym::ERR) return err();
         for (auto& a : args) if (a.k == Sym::ERR) return err();
         const std::string& fn = e.name;
@@ -923,8 +972,13 @@ struct Lowerer {
     }
 
     Sym binary(const Expr& e) {
-        Sym a = lower(*e.kids[0]);
-        Sym b = lower(*e.kids[1]);
+        Sym a0 = lower(*e.kids[0]);
+        Sym b0 = lower(*e.kids[1]);
+        if (a0.k == Sym::CHOICE || b0.k == Sym::CHOICE) return lift2(a0, b0, [&](const Sym& x, const Sym& y) { return binary_on(e, x, y); });
+        return binary_on(e, a0, b0);
+    }
+
+    Sym binary_on(const Expr& e, const Sym& a, const Sym& b) {
         switch (e.op) {
             case Expr::OP_AND: {
                 BV x = as_bool(a), y = as_bool(b);
@@ -996,8 +1050,10 @@ struct Lowerer {
 
 int lower_rule_expression(Model& model, const Expr& e, const std::string& rule_name) {
     Lowerer L(model, rule_name);
-    Sym r = L.lower(e);
-    // Rule::match_request: matched iff execute() == Ok(Bool(true))  (pingoo/rules.rs:36-52)
+    Sym r0 = L.lower(e);
+    // Rule::match_request: matched iff execute() == Ok(Bool(true))  (pingoo/rules.rs:36-52); a conditional whose taken
+    // branch is not a Bool is "no match" like any other non-bool value
+    Sym r = L.lift1(r0, [&](const Sym& v) { return v.k == Sym::BOOL ? v : L.boolean(0, 0); });
     if (r.k != Sym::BOOL) return model.pool.constant(false);
     return r.bv.t;
 }

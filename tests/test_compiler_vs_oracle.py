@@ -189,6 +189,15 @@ def _lowered_constructs_case():
         'http_request.host > ""',
         'http_request.host <= ""',
         '!(http_request.path < "/m") && http_request.method == "POST"',
+        # conditionals selecting non-boolean values on a request-dependent condition
+        'http_request.path.starts_with(client.remote_port > 1024 ? "/a" : "/b")',
+        '(http_request.method == "POST" ? http_request.path : http_request.host) == "/b"',
+        '(client.remote_port == 80 ? 1 : 2) + client.remote_port > 82',
+        '(http_request.method == "GET" ? "x" : true)',
+        '(client.remote_port > 100 ? http_request.host : http_request.path).length() > 3',
+        '(client.remote_port > 100 ? 7 : http_request.host) == 7',
+        '((client.remote_port > 100 ? (http_request.method == "PUT" ? "/a" : "/b") : "/zzz") == http_request.path)',
+        '(client.remote_port / (client.remote_port - 80) > 0 ? http_request.path : http_request.host).contains("a")',
     ]
     # one rule set per expression (first-match would let the early rules shadow the later ones), plus all of them together
     rule_sets = [[Rule(f"r{i}", e, [Action.BLOCK])] for i, e in enumerate(exprs)]
