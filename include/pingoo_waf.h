@@ -194,6 +194,9 @@ int pgw_queue_evaluate(pgw_queue* q, const pgw_request* req, uint32_t* verdict, 
 typedef void (*pgw_done_fn)(void* user, uint32_t verdict, uint16_t service, int rc);
 int pgw_queue_submit(pgw_queue* q, const pgw_request* req, pgw_done_fn done, void* user);
 int pgw_queue_get_stats(pgw_queue* q, pgw_queue_stats* out);
+/* Message of the most recent batch that failed (rc 4 of pgw_queue_evaluate / the callback): the batch is evaluated on the
+ * queue's dispatcher thread, whose pgw_last_error() the callers cannot see.  Returns the message length. */
+size_t pgw_queue_last_error(pgw_queue* q, char* buf, size_t cap);
 /* Flushes what is pending; no thread may be inside pgw_queue_evaluate any more. */
 void pgw_queue_destroy(pgw_queue* q);
 /* The shaping alone (no device needed): pointers into the request's own strings, Field order host,url,path,method,user_agent. */

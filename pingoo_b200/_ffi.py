@@ -78,7 +78,7 @@ EXPORTS = (
     "pgw_compile_expression", "pgw_validate_expression", "pgw_ruleset_create", "pgw_ruleset_load_dir", "pgw_lists_add", "pgw_geoip_load",
     "pgw_ruleset_finalize", "pgw_evaluate_batch", "pgw_evaluate_batch_host", "pgw_geoip_lookup_batch",
     "pgw_services_set", "pgw_evaluate_batch_routed", "pgw_evaluate_batch_routed_host",
-    "pgw_captcha_client_id_batch", "pgw_queue_create", "pgw_queue_evaluate", "pgw_queue_submit", "pgw_queue_get_stats", "pgw_queue_destroy", "pgw_shape_request",
+    "pgw_captcha_client_id_batch", "pgw_queue_create", "pgw_queue_evaluate", "pgw_queue_submit", "pgw_queue_get_stats", "pgw_queue_last_error", "pgw_queue_destroy", "pgw_shape_request",
     "pgw_host_alloc", "pgw_host_free", "pgw_ruleset_info", "pgw_ruleset_set_profiling", "pgw_ruleset_profile", "pgw_ruleset_profile_kernels",
     "pgw_ruleset_describe", "pgw_ruleset_destroy", "pgw_last_error",
 )
@@ -106,6 +106,7 @@ def declare(lib, prefix="pgw_"):
         "queue_evaluate": (C.c_int, [p, C.POINTER(Request), C.POINTER(C.c_uint32), C.POINTER(C.c_uint16)]),
         "queue_submit": (C.c_int, [p, C.POINTER(Request), DONE_FN, p]),
         "queue_get_stats": (C.c_int, [p, C.POINTER(QueueStats)]),
+        "queue_last_error": (C.c_size_t, [p, C.c_char_p, C.c_size_t]),
         "queue_destroy": (None, [p]),
         "shape_request": (C.c_int, [C.POINTER(Request), C.POINTER(C.c_char_p), C.POINTER(C.c_size_t)]),
         "geoip_lookup_batch": (C.c_int, [p, p, p, C.c_uint32, p, p, p]),

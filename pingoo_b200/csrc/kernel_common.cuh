@@ -290,9 +290,6 @@ struct Extras {
 // collected into `ex` (its amax / binv come in initialised from the scan's info words); with a row they are ORed into it
 // (second pass of the few requests with more than four such atoms: collect_extras_row, out of line).
 __device__ __forceinline__ void collect_extras(const KParams& p, uint32_t r, uint32_t a_img, Extras* ex, uint32_t* row) {
-#ifndef PGW_EXP_EPI
-#define PGW_EXP_EPI 0
-#endif
     uint64_t xl = 0;
     uint32_t nx = 0, xlast = 0xFFFFFFFFu, amax = ex->amax, binv = ex->binv;
     auto fn = [&](uint32_t a) {
@@ -309,7 +306,7 @@ __device__ __forceinline__ void collect_extras(const KParams& p, uint32_t r, uin
     uint32_t set_mask = 0;
     // client address -> leaf, in two steps around the early-exit walks: the DIR-24-8 word (or, for IPv6, nothing yet) is
     // requested first, so that its DRAM latency passes while the walks run; the leaf is fetched after them
-    const bool lpm = p.need_lpm && !(PGW_EXP_EPI & 2);
+    const bool lpm = p.need_lpm;
     const uint8_t* ip16 = p.ip + (size_t)r * 16;
     bool v6 = false;
     uint32_t dir_e = 0, ip_host = 0;
@@ -322,7 +319,7 @@ __device__ __forceinline__ void collect_extras(const KParams& p, uint32_t r, uin
     }
 
     // small early-exit units: one walk over the first bytes of the field
-    for (uint32_t k = 0; k < p.n_prefix && !(PGW_EXP_EPI & 1); ++k) {
+    for (uint32_t k = 0; k < p.n_prefix; ++k) {
         const UnitDesc& ud = p.pdesc[k];
         const uint32_t* o = p.off[ud.field] + r;
         const uint32_t s0 = o[0], e0 = o[1];
@@ -360,7 +357,7 @@ __device__ __forceinline__ void collect_extras(const KParams& p, uint32_t r, uin
     if (p.country) country = p.country[r];
     // integer predicates, one feature at a time: the feature's quick reject (compile.hpp) settles almost every request
 #pragma unroll 1
-    for (uint32_t j = 0; j < p.n_feat_used && !(PGW_EXP_EPI & 4); ++j) {
+    for (uint32_t j = 0; j < p.n_feat_used; ++j) {
         const uint32_t fe = p.feat_used[j];
         const uint32_t b0 = p.ns_begin[fe], b1 = p.ns_begin[fe + 1u];
         int64_t x;
@@ -396,7 +393,7 @@ __device__ __forceinline__ void collect_extras(const KParams& p, uint32_t r, uin
             if (v) fn(a.atom);
         }
     }
-    for (uint32_t i = p.ns_begin[7]; i < p.rare_begin && !(PGW_EXP_EPI & 8); ++i) {
+    for (uint32_t i = p.ns_begin[7]; i < p.rare_begin; ++i) {
         const NsAtom a = p.n_ns <= kMaxConstNs ? p.nsd[i] : p.ns[i];
         bool v = false;
         if (a.kind == 3) {  // IP_SET

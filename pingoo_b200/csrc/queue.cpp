@@ -147,6 +147,7 @@ struct pgw_queue {
     std::thread worker;
     std::atomic<bool> stop{false};
     pgw_queue_stats st{};
+    std::string last_error;   // message of the most recent failed batch (pgw_last_error is thread-local to the dispatcher)
 };
 
 extern "C" {
@@ -222,6 +223,7 @@ static void dispatcher(pgw_queue* q) {
         for (uint32_t i = 0; i < n; ++i)
             if (s->fn[i]) s->fn[i](s->user[i], s->verdict[i], s->service[i], rc ? 4 : 0);
         lk.lock();
+        if (rc) q->last_error = pgw_last_error();
         s->rc = rc;
         s->readers_left = blocking;
         s->done = true;
@@ -497,6 +499,17 @@ int pgw_queue_get_stats(pgw_queue* q, pgw_queue_stats* out) {
     std::lock_guard<std::mutex> lk(q->mu);
     *out = q->st;
     return 0;
+}
+
+size_t pgw_queue_last_error(pgw_queue* q, char* buf, size_t cap) {
+    if (!q) return 0;
+    std::lock_guard<std::mutex> lk(q->mu);
+    if (buf && cap) {
+        const size_t n = q->last_error.size() < cap - 1 ? q->last_error.size() : cap - 1;
+        memcpy(buf, q->last_error.data(), n);
+        buf[n] = 0;
+    }
+    return q->last_error.size();
 }
 
 void pgw_queue_destroy(pgw_queue* q) {

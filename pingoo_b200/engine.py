@@ -247,7 +247,9 @@ class RequestQueue:
         v, s = C.c_uint32(0), C.c_uint16(0)
         rc = self._lib.pgw_queue_evaluate(self._q, C.byref(req), C.byref(v), C.byref(s))
         if rc:
-            raise Error(f"pgw_queue_evaluate failed ({rc}): " + self._lib.pgw_last_error().decode(errors="replace"))
+            buf = C.create_string_buffer(512)
+            self._lib.pgw_queue_last_error(self._q, buf, len(buf))
+            raise Error(f"pgw_queue_evaluate failed ({rc}): " + buf.value.decode(errors="replace"))
         return v.value, s.value
 
     def stats(self) -> _ffi.QueueStats:

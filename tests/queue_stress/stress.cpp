@@ -22,6 +22,7 @@ static std::atomic<int> g_eval_calls{0};
 extern "C" {
 void* pgw_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 void pgw_host_free(void* p) { free(p); }
+const char* pgw_last_error(void) { return "stub"; }
 // stub of the batch evaluation: checks the batch is well formed and derives verdict/service from the packed bytes
 int pgw_evaluate_batch_routed_host(pgw_ruleset*, const pgw_batch* b, uint32_t* verdict, uint16_t* service) {
     g_eval_calls++;
