@@ -61,8 +61,10 @@ typedef struct pgw_options {
                                       (same verdicts; kept for measurements and tests) */
 } pgw_options;
 
-/* One string column: concatenated bytes + n+1 offsets.  `bytes` must be 32-byte
- * aligned and readable up to round_up(offsets[n], 32) (the kernels load aligned 16-byte chunks). */
+/* One string column: concatenated bytes + n+1 offsets.  `bytes` must be 32-byte aligned and readable up to
+ * round_up(offsets[n], 32) (the kernels load aligned 16-byte chunks; what lies behind offsets[n] is read but never
+ * interpreted as request data).  A column holds less than 4 GiB - 4 KiB (32-bit offsets); callers split larger batches.
+ * A batch may be a window of a longer column: offsets are absolute positions in `bytes`, offsets[0] need not be 0. */
 typedef struct pgw_strcol {
     const uint8_t* bytes;
     const uint32_t* offsets;
