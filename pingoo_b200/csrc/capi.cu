@@ -368,6 +368,9 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
         memset(&gf, 0, sizeof gf);
         gf.b1 = (const uint32_t*)chk(M.upload(H.gate[f].b1));
         gf.slots = (const uint32_t*)chk(M.upload(H.gate[f].slots));
+        gf.lit_cand = (const uint32_t*)chk(M.upload(H.gate[f].lit_cand));
+        gf.lits = (const LitDesc*)chk(M.upload(H.gate[f].lits));
+        gf.lit_bytes = (const uint8_t*)chk(M.upload(H.gate[f].lit_bytes));
         gf.k1 = H.gate[f].k1;
         gf.kt = H.gate[f].kt;
         gf.bloom_off = (uint32_t)bloom_used;
@@ -487,6 +490,9 @@ static int launch_on(pgw_ruleset* rs, const pgw_batch* b, uint32_t* verdict_out,
     P.multi_list = sc->multi;
     GateParams G = rs->gate_base;
     G.n = b->n;
+    G.rows = sc->rows;
+    G.info = sc->info;
+    G.atom_words = H.atom_words;
     for (uint32_t i = 0; i < G.n_fields; ++i) {
         const int f = rs->gate_field[i];
         G.f[i].col = cols[f]->bytes;

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <functional>
 #include <iterator>
+#include <set>
 #include <sstream>
 
 #include "dfa.hpp"
@@ -76,7 +77,11 @@ std::string HostProgram::summary() const {
         o << " [" << kFieldNames[units[u].field] << (units[u].mode == UM_CANDIDATES ? "/gated" : units[u].abs0 != 0xFFFFFFFFu ? "/early-exit" : "")
           << ": states=" << units[u].n_states << " classes=" << units[u].n_classes << "]";
     for (int f = 0; f < N_FIELDS; ++f)
-        if (gate[f].present) o << " gate(" << kFieldNames[f] << ": grams=" << gate[f].n_grams << " bloom=2^" << gate[f].k1 << " table=2^" << gate[f].kt << ")";
+        if (gate[f].present) {
+            o << " gate(" << kFieldNames[f] << ": grams=" << gate[f].n_grams << " bloom=2^" << gate[f].k1 << " table=2^" << gate[f].kt;
+            if (gate[f].lits.size() > 1 || gate[f].lits[0].len) o << " literals=" << gate[f].lits.size();
+            o << ")";
+        }
     o << " ns_atoms=" << ns_atoms.size() << " lpm=" << (lpm.present ? 1 : 0);
     return o.str();
 }
@@ -374,6 +379,9 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
         std::vector<uint32_t> bundle_atom[N_UC];
         struct GatedGrams { std::vector<uint32_t> grams; };
         std::vector<GatedGrams> gated_grams;
+        // atoms whose pattern is a small finite set of strings: confirmed by the gate's resolve kernel, no automaton (gate.hpp)
+        std::vector<GateLiteral> literals;
+        std::vector<uint32_t> literal_grams;   // distinct grams the literals put into the field's budget
         for (uint32_t a = 0; a < H.n_atoms; ++a)
             if (M.atoms[a].kind == AtomDesc::STR_PATTERN && M.atoms[a].field == f) {
                 // atoms no rule refers to any more (replaced by their complement) are not scanned
@@ -394,7 +402,26 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
                         if (all_gate && !gate_grams_for_pattern(M.nfa[f], b.starts[k], opt.gate_pattern_cap, &gg.grams)) all_gate = false;
                     }
                     if (all_anch) cls = UC_ANCH;
-                    else if (all_gate) { cls = UC_GATED; gated_grams.push_back(std::move(gg)); }
+                    else {
+                        std::vector<LitString> strs;
+                        if (opt.literal_confirm && b.starts.size() == 1 && !b.has_latch && M.events[M.atoms[a].event_base].kind == EV_FIRE &&
+                            (int)a != H.gate_bypass_atom && gate_finite_language(M.nfa[f], b.starts[0], &strs)) {
+                            std::vector<uint32_t> lg = literal_grams;
+                            for (const LitString& ls : strs) {
+                                std::vector<std::pair<uint32_t, int>> pg;
+                                gate_grams_for_literal(ls, &pg);
+                                for (auto& pr : pg) lg.push_back(pr.first);
+                            }
+                            std::sort(lg.begin(), lg.end());
+                            lg.erase(std::unique(lg.begin(), lg.end()), lg.end());
+                            if (lg.size() <= opt.gate_field_cap / 2) {   // half of the field's gram budget at most
+                                literal_grams.swap(lg);
+                                for (const LitString& ls : strs) literals.push_back(GateLiteral{ls, a});
+                                continue;   // no DFA for this atom
+                            }
+                        }
+                        if (all_gate) { cls = UC_GATED; gated_grams.push_back(std::move(gg)); }
+                    }
                 }
                 if (getenv("PGW_DEBUG_CLASSES") && cls == UC_GATED && gated_grams.back().grams.size() > 300) fprintf(stderr, "gated field %s grams %zu: %s\n", kFieldNames[f], gated_grams.back().grams.size(), M.atoms[a].key.c_str());
                 bundles[cls].push_back(std::move(b));
@@ -406,7 +433,7 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
             std::vector<size_t> order(gated_grams.size());
             for (size_t i = 0; i < order.size(); ++i) order[i] = i;
             std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return gated_grams[x].grams.size() < gated_grams[y].grams.size(); });
-            std::vector<uint32_t> all;
+            std::vector<uint32_t> all = literal_grams;   // sorted, distinct
             std::vector<char> keep(gated_grams.size(), 0);
             for (size_t i : order) {
                 std::vector<uint32_t> g = gated_grams[i].grams, merged;
@@ -430,7 +457,8 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
             bundles[UC_GATED].swap(kept_b);
             bundle_atom[UC_GATED].swap(kept_a);
         }
-        bool any = false;
+        bool any = !literals.empty();
+        std::vector<uint32_t> field_grams, field_masks;
         for (int cls = 0; cls < N_UC; ++cls) {
             if (bundles[cls].empty()) continue;
             any = true;
@@ -447,11 +475,9 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
             }
             if (cls == UC_GATED) {
                 // a gram leads to the units whose patterns it came from (bit = unit index among the field's gated units, mod kGateWidth)
-                std::vector<uint32_t> grams, masks;
                 for (size_t g = 0; g < groups.dfas.size(); ++g)
                     for (int bi : groups.members[g])
-                        for (uint32_t x : gated_grams[bi].grams) { grams.push_back(x); masks.push_back(1u << (g % kGateWidth[f])); }
-                gate_build_tables(grams, masks, f == F_URL ? kGateMaxLog2 : kGateMaxLog2 - 2, &H.gate[f]);
+                        for (uint32_t x : gated_grams[bi].grams) { field_grams.push_back(x); field_masks.push_back(1u << (g % kGateWidth[f])); }
             }
             for (size_t g = 0; g < groups.dfas.size(); ++g) {
                 Pending pd;
@@ -470,6 +496,10 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
                 }
                 pend.push_back(std::move(pd));
             }
+        }
+        if (!field_grams.empty() || !literals.empty()) {
+            gate_build_tables(field_grams, field_masks, literals, f == F_URL ? kGateMaxLog2 : kGateMaxLog2 - 2, &H.gate[f]);
+            H.n_literal_atoms += (uint32_t)std::set<uint32_t>([&] { std::vector<uint32_t> v; for (auto& l : literals) v.push_back(l.atom); return std::set<uint32_t>(v.begin(), v.end()); }()).size();
         }
         if (any) H.scanned_fields_mask |= 1u << f;
     }

@@ -14,6 +14,7 @@ struct CompileOptions {
     size_t max_unit_table_bytes = 8u << 20;    // per scan unit transition table (hot rows go to shared memory, the rest stays in L2)
     bool eval_gates = true;                    // evaluate http_listener.rs:196-204 gates inside the engine
     bool candidate_gate = true;                // gram prefilter in front of the DFA scan of url / user_agent / path (gate.hpp)
+    bool literal_confirm = true;               // finite-string patterns of gated fields are confirmed by the gate, not walked by a DFA
     size_t gate_pattern_cap = 4096;            // grams one pattern may contribute before it is left to an ungated unit
     size_t gate_field_cap = 12288;             // grams per field (bitmaps of at most 2^19 bits each)
 };
@@ -44,6 +45,7 @@ struct HostProgram {
     uint32_t ns_begin[N_INT_FEATS + 2] = {0};  // group g = ns_atoms[ns_begin[g], ns_begin[g + 1]); group N_INT_FEATS = the sets
     // quick reject per integer feature: lo <= x <= hi and (x < vmin or x > vmax) => every predicate on the feature is false
     int64_t ns_lo[N_INT_FEATS], ns_hi[N_INT_FEATS], ns_vmin[N_INT_FEATS], ns_vmax[N_INT_FEATS];
+    uint32_t n_literal_atoms = 0;            // atoms confirmed by the gate's resolve kernel (finite string sets)
     uint32_t n_rare = 0;                     // INT_EXPR / FIELD_CMP predicates: the last n_rare entries of ns_atoms
     std::vector<int64_t> iexpr;              // INT_EXPR programs, flattened (program.hpp IntTok); NsAtom::set_id = offset
     std::vector<uint64_t> atom_sig;          // per atom: hashed set of the rules that mention it (all ones: never pair-independent)

@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <cstring>
+#include <map>
 
 namespace pgw {
 namespace {
@@ -288,38 +290,151 @@ bool gate_grams_for_pattern(const Nfa& nfa, int start, size_t cap, std::vector<u
     return true;
 }
 
-void gate_build_tables(const std::vector<uint32_t>& grams, const std::vector<uint32_t>& masks, uint32_t max_log2, GateTables* out) {
-    std::vector<std::pair<uint32_t, uint32_t>> gm;
-    gm.reserve(grams.size());
-    for (size_t i = 0; i < grams.size(); ++i) gm.emplace_back(grams[i], masks[i]);
-    std::sort(gm.begin(), gm.end());
-    std::vector<std::pair<uint32_t, uint32_t>> u;
-    for (auto& x : gm) {
-        if (!u.empty() && u.back().first == x.first) u.back().second |= x.second;
-        else u.push_back(x);
+namespace {
+
+struct LangWalker {
+    const Nfa& nfa;
+    std::vector<LitString>* out;
+    bool fail = false;
+    int steps = 0;
+
+    // `ended`: a `$` has been crossed -- nothing may be consumed any more
+    void walk(int n, LitString cur, bool ended, int eps_depth) {
+        if (fail) return;
+        if (++steps > 200000 || eps_depth > 4096) { fail = true; return; }
+        if (n < 0) return;
+        const NfaNode& nd = nfa.nodes[n];
+        switch (nd.kind) {
+            case N_MATCH:
+                cur.anch_end = ended;
+                out->push_back(cur);
+                if (out->size() > kLitMaxStrings * 4) fail = true;   // duplicates are removed later; a real blow-up stops here
+                return;
+            case N_JUMP: walk(nd.out, cur, ended, eps_depth + 1); return;
+            case N_SPLIT:
+                walk(nd.out, cur, ended, eps_depth + 1);
+                walk(nd.out1, cur, ended, eps_depth + 1);
+                return;
+            case N_ASSERT:
+                if (nd.assert_kind == A_BOL_TEXT) {
+                    if (!cur.bytes.empty()) return;   // `^` after a consumed byte: this path never matches
+                    cur.anch_start = true;
+                    walk(nd.out, cur, ended, eps_depth + 1);
+                } else if (nd.assert_kind == A_EOL_TEXT) {
+                    walk(nd.out, cur, true, eps_depth + 1);
+                } else fail = true;   // line anchors, word boundaries: left to the automata
+                return;
+            case N_CHAR: {
+                if (ended) return;    // a byte after `$`: this path never matches
+                if (cur.bytes.size() >= kLitMaxLen) { fail = true; return; }
+                const ByteSet& bs = nfa.sets[nd.set];
+                int members[5], nm = 0;
+                for (int v = 0; v < 256 && nm <= 4; ++v)
+                    if (bs.test((unsigned)v)) members[nm++] = v;
+                if (nm == 0) return;
+                if (nm > 4) { fail = true; return; }
+                const size_t k = cur.bytes.size();
+                auto is_letter = [](int v) { return (v >= 'A' && v <= 'Z') || (v >= 'a' && v <= 'z'); };
+                if (nm == 2 && is_letter(members[0]) && members[1] == (members[0] ^ 0x20)) {
+                    LitString nx = cur;
+                    nx.bytes.push_back((char)(members[0] & 0xDF));
+                    nx.ci_mask |= 1ull << k;
+                    walk(nd.out, nx, false, 0);
+                    return;
+                }
+                for (int i = 0; i < nm; ++i) {
+                    LitString nx = cur;
+                    nx.bytes.push_back((char)members[i]);
+                    walk(nd.out, nx, false, 0);
+                }
+                return;
+            }
+        }
     }
+};
+
+}  // namespace
+
+bool gate_finite_language(const Nfa& nfa, int start, std::vector<LitString>* out) {
+    out->clear();
+    LangWalker W{nfa, out};
+    W.walk(start, LitString(), false, 0);
+    if (W.fail || out->empty()) return false;
+    std::sort(out->begin(), out->end());
+    out->erase(std::unique(out->begin(), out->end()), out->end());
+    if (out->size() > kLitMaxStrings) return false;
+    for (const LitString& s : *out)
+        if (s.bytes.size() < kLitMinLen) return false;
+    return true;
+}
+
+void gate_grams_for_literal(const LitString& s, std::vector<std::pair<uint32_t, int>>* out) {
+    const size_t n = s.bytes.size();
+    auto f = [&](size_t k) -> int { return k < n ? ((unsigned char)s.bytes[k] & 0xDF) : kWild; };
+    auto emit = [&](std::array<int, 4> w, int delta) {
+        std::vector<uint32_t> g;
+        expand(w, &g);
+        for (uint32_t x : g) out->emplace_back(x, delta);
+    };
+    // a literal anchored at the field end may be followed by the next field's bytes: the padding is a wildcard either way
+    emit({f(0), f(1), f(2), f(3)}, 0);                       // the match starts at an even position: window = m[0..4)
+    if (n >= 5) emit({f(1), f(2), f(3), f(4)}, -1);          // odd position: window [p + 1, p + 5) = m[1..5)
+    else emit({kWild, f(0), f(1), f(2)}, +1);                // odd position: window [p - 1, p + 3) = (any, m[0..3))
+}
+
+void gate_build_tables(const std::vector<uint32_t>& grams, const std::vector<uint32_t>& masks, const std::vector<GateLiteral>& literals,
+                       uint32_t max_log2, GateTables* out) {
+    struct Ent { uint32_t mask = 0; std::vector<uint32_t> cand; };
+    std::map<uint32_t, Ent> byg;
+    for (size_t i = 0; i < grams.size(); ++i) byg[grams[i]].mask |= masks[i];
     GateTables& T = *out;
     T = GateTables();
     T.present = true;
-    T.n_grams = (uint32_t)u.size();
+    for (size_t li = 0; li < literals.size(); ++li) {
+        const LitString& ls = literals[li].str;
+        LitDesc d;
+        d.off = (uint32_t)T.lit_bytes.size();
+        d.len = (uint16_t)ls.bytes.size();
+        d.flags = (uint16_t)((ls.anch_start ? 1 : 0) | (ls.anch_end ? 2 : 0));
+        d.atom = literals[li].atom;
+        d.pad = 0;
+        d.ci_mask = ls.ci_mask;
+        T.lits.push_back(d);
+        T.lit_bytes.insert(T.lit_bytes.end(), ls.bytes.begin(), ls.bytes.end());
+        std::vector<std::pair<uint32_t, int>> lg;
+        gate_grams_for_literal(ls, &lg);
+        for (auto& pr : lg) {
+            const uint32_t c = ((uint32_t)li << 2) | (uint32_t)(pr.second + 1);
+            std::vector<uint32_t>& v = byg[pr.first].cand;
+            if (std::find(v.begin(), v.end(), c) == v.end()) v.push_back(c);
+        }
+    }
+    while (T.lit_bytes.size() % 16) T.lit_bytes.push_back(0);
+    T.n_grams = (uint32_t)byg.size();
     // level 1: two bits per gram in one word; density <= 1/64 -> false-positive rate <= 2.5e-4 per window
     uint32_t k = 12;
-    while (k < max_log2 && k < kGateMaxLog2 && ((size_t)1 << k) < u.size() * 128) ++k;
+    while (k < max_log2 && k < kGateMaxLog2 && ((size_t)1 << k) < byg.size() * 128) ++k;
     T.k1 = k;
     T.b1.assign(((size_t)1 << T.k1) / 32, 0u);
     // level 2: load factor <= 1/2
     T.kt = 4;
-    while (((size_t)1 << T.kt) < u.size() * 2) ++T.kt;
-    T.slots.assign(((size_t)2 << T.kt), 0u);
+    while (((size_t)1 << T.kt) < byg.size() * 2) ++T.kt;
+    T.slots.assign(((size_t)4 << T.kt), 0u);
     const uint32_t tm = (1u << T.kt) - 1u;
-    for (auto& x : u) {
-        const uint32_t g = x.first;
+    for (auto& kv : byg) {
+        const uint32_t g = kv.first;
         gate_l1_set(T.b1.data(), T.k1, g);
         uint32_t s = (g * kGateHash2) >> (32 - T.kt);
-        while (T.slots[2 * s + 1] != 0) s = (s + 1) & tm;
-        T.slots[2 * s] = g;
-        T.slots[2 * s + 1] = x.second;
+        while (T.slots[4 * s + 1] != 0 || T.slots[4 * s + 3] != 0) s = (s + 1) & tm;
+        T.slots[4 * s] = g;
+        T.slots[4 * s + 1] = kv.second.mask;
+        T.slots[4 * s + 2] = (uint32_t)T.lit_cand.size();
+        T.slots[4 * s + 3] = (uint32_t)kv.second.cand.size();
+        T.lit_cand.insert(T.lit_cand.end(), kv.second.cand.begin(), kv.second.cand.end());
     }
+    if (T.lit_cand.empty()) T.lit_cand.push_back(0);
+    if (T.lits.empty()) { LitDesc d; memset(&d, 0, sizeof d); T.lits.push_back(d); }
+    if (T.lit_bytes.empty()) T.lit_bytes.assign(16, 0);
 }
 
 }  // namespace pgw

@@ -20,6 +20,8 @@
 // that never occur in a request), the same single AND the kernel applies to each word: g & 0xDFDFDFDF.
 #pragma once
 #include <cstdint>
+#include <string>
+#include <tuple>
 #include <vector>
 
 #include "regex.hpp"
@@ -50,22 +52,70 @@ inline void gate_l1_set(uint32_t* b1, uint32_t k1, uint32_t g) {
 // 32-bit word and two bit positions in it, both must be set (false-positive rate = density^2, a few 1e-4).
 // Level 2 (global memory, probed only for level-1 survivors): an exact open-addressing table folded gram -> mask of
 // the field's gated scan units whose patterns contain the gram, so a candidate is only walked by those units.
+// A pattern whose language is a small finite set of byte strings (alternations of literals, `contains`, `ends_with`,
+// optional / case-insensitive letters) needs no automaton: every occurrence covers a gate window whose gram is known,
+// so the resolve kernel CONFIRMS it by comparing the string at the hit position and fires the atom itself -- the request
+// becomes a scan candidate only for the grams of real regex patterns.  (What Rust `regex` does when a pattern is a
+// literal alternation: it never builds an automaton for it either.)
+struct LitString {
+    std::string bytes;        // case-insensitive positions hold the upper-case letter
+    uint64_t ci_mask = 0;     // bit k: byte k matches either case
+    bool anch_start = false;  // must start at the first byte of the field
+    bool anch_end = false;    // must end at the last byte of the field
+    bool operator<(const LitString& o) const {
+        return std::tie(bytes, ci_mask, anch_start, anch_end) < std::tie(o.bytes, o.ci_mask, o.anch_start, o.anch_end);
+    }
+    bool operator==(const LitString& o) const { return bytes == o.bytes && ci_mask == o.ci_mask && anch_start == o.anch_start && anch_end == o.anch_end; }
+};
+constexpr size_t kLitMaxStrings = 48, kLitMaxLen = 64, kLitMinLen = 3;
+
+// device / table form of one literal (program.hpp style POD)
+struct LitDesc {
+    uint32_t off;       // into the byte pool
+    uint16_t len;
+    uint16_t flags;     // 1: anchored at the field start, 2: anchored at the field end
+    uint32_t atom;
+    uint32_t pad;
+    uint64_t ci_mask;
+};
+
 struct GateTables {
     bool present = false;
     uint32_t k1 = 0;                  // log2(bits) of the level-1 bitmap
     std::vector<uint32_t> b1;         // 2^k1 / 32 words
     uint32_t kt = 0;                  // log2(slots) of the level-2 table
-    std::vector<uint32_t> slots;      // 2 words per slot: {gram, unit mask}; mask 0 = empty slot
+    std::vector<uint32_t> slots;      // 4 words per slot: {gram, unit mask, first literal candidate, number of them}; mask 0 and
+                                      // count 0 = empty slot
     uint32_t n_grams = 0;
-    // unit mask of the window (0: not a candidate window)
-    uint32_t probe(uint32_t window_le) const {
+    // literal candidates of a gram: (literal index << 2) | (delta + 1), the literal would start at window position + delta
+    std::vector<uint32_t> lit_cand;
+    std::vector<LitDesc> lits;
+    std::vector<uint8_t> lit_bytes;
+    // unit mask of the window (0: no scan unit asks for it); `lit` (optional) receives the gram's literal candidates
+    uint32_t probe(uint32_t window_le, uint32_t* lit_begin = nullptr, uint32_t* lit_count = nullptr) const {
+        if (lit_count) *lit_count = 0;
         const uint32_t g = gate_fold(window_le);
         if (!gate_l1_test(b1.data(), k1, g)) return 0;
         const uint32_t tm = (1u << kt) - 1u;
         for (uint32_t s = (g * kGateHash2) >> (32 - kt);; s = (s + 1) & tm) {
-            if (slots[2 * s + 1] == 0) return 0;
-            if (slots[2 * s] == g) return slots[2 * s + 1];
+            if (slots[4 * s + 1] == 0 && slots[4 * s + 3] == 0) return 0;
+            if (slots[4 * s] == g) {
+                if (lit_begin) *lit_begin = slots[4 * s + 2];
+                if (lit_count) *lit_count = slots[4 * s + 3];
+                return slots[4 * s + 1];
+            }
         }
+    }
+    // does literal `d` occur at column position `at` of the field [s, e) of column `col`?
+    bool lit_matches(const LitDesc& d, const uint8_t* col, uint32_t s, uint32_t e, int64_t at) const {
+        if (at < (int64_t)s || at + d.len > (int64_t)e) return false;
+        if ((d.flags & 1) && at != (int64_t)s) return false;
+        if ((d.flags & 2) && at + d.len != (int64_t)e) return false;
+        for (uint32_t k = 0; k < d.len; ++k) {
+            const uint8_t b = col[at + k], want = lit_bytes[d.off + k];
+            if (b != want && !(((d.ci_mask >> k) & 1) && (uint8_t)(b ^ 0x20) == want)) return false;
+        }
+        return true;
     }
 };
 
@@ -77,8 +127,24 @@ bool pattern_is_start_anchored(const Nfa& nfa, int start);
 // (matches shorter than 3 bytes, or more than `cap` grams).
 bool gate_grams_for_pattern(const Nfa& nfa, int start, size_t cap, std::vector<uint32_t>* out);
 
-// `grams[i]` belongs to the units in `masks[i]` (duplicates are merged by OR)
+// The finite language of the pattern starting at NFA node `start`, if it is one the literal path can take: at most
+// kLitMaxStrings strings of kLitMinLen..kLitMaxLen bytes, every byte a single value or a letter in both cases, `^` only in
+// front and `$` only behind, no other assertion, no loop.
+bool gate_finite_language(const Nfa& nfa, int start, std::vector<LitString>* out);
+
+// A literal of a gated field and the grams that announce it: (folded gram, delta) with the literal starting at
+// window position + delta (gate.hpp soundness argument: A = m[0..4) at delta 0; B = m[1..5) at delta -1 when the literal
+// has five bytes, else (any, m[0..3)) at delta +1).
+void gate_grams_for_literal(const LitString& s, std::vector<std::pair<uint32_t, int>>* out);
+
+struct GateLiteral {
+    LitString str;
+    uint32_t atom;
+};
+
+// `grams[i]` belongs to the units in `masks[i]` (duplicates are merged by OR); `literals` are confirmed by the resolve kernel
 // `max_log2`: largest level-1 bitmap the field may use (all gated fields' bitmaps are resident in shared memory together)
-void gate_build_tables(const std::vector<uint32_t>& grams, const std::vector<uint32_t>& masks, uint32_t max_log2, GateTables* out);
+void gate_build_tables(const std::vector<uint32_t>& grams, const std::vector<uint32_t>& masks, const std::vector<GateLiteral>& literals,
+                       uint32_t max_log2, GateTables* out);
 
 }  // namespace pgw

@@ -28,16 +28,30 @@ __device__ __forceinline__ uint32_t gate_l1(const uint32_t* __restrict__ sb, uin
     return shf_wrap_r(word, __umulhi(g, kGateHashB)) & shf_wrap_r(word, __umulhi(g, kGateHashC));
 }
 
-// level 2: exact table in global memory; unit mask of the gram or 0
-__device__ __forceinline__ uint32_t gate_l2(const uint2* __restrict__ slots, uint32_t kt, uint32_t g) {
+// level 2: exact table in global memory; {gram, unit mask, first literal candidate, their number} of the gram, or zeros
+__device__ __forceinline__ uint4 gate_l2(const uint4* __restrict__ slots, uint32_t kt, uint32_t g) {
     const uint32_t tm = (1u << kt) - 1u;
     uint32_t s = (g * kGateHash2) >> (32u - kt);
     for (;;) {
-        const uint2 e = __ldg(slots + s);
-        if (e.y == 0u) return 0u;
-        if (e.x == g) return e.y;
+        const uint4 e = __ldg(slots + s);
+        if (e.y == 0u && e.w == 0u) return make_uint4(0, 0, 0, 0);
+        if (e.x == g) return e;
         s = (s + 1u) & tm;
     }
+}
+
+// does literal `d` occur at column position `at` of the field [s, e)?  (GateTables::lit_matches on the device)
+__device__ __noinline__ bool lit_matches(const GateField& F, const LitDesc& d, uint32_t s, uint32_t e, int64_t at) {
+    if (at < (int64_t)s || at + d.len > (int64_t)e) return false;
+    if ((d.flags & 1u) && at != (int64_t)s) return false;
+    if ((d.flags & 2u) && at + d.len != (int64_t)e) return false;
+    const uint8_t* col = F.col + at;
+    const uint8_t* lit = F.lit_bytes + d.off;
+    for (uint32_t k = 0; k < d.len; ++k) {
+        const uint32_t b = __ldg(col + k), want = __ldg(lit + k);
+        if (b != want && !(((d.ci_mask >> k) & 1ull) && (b ^ 0x20u) == want)) return false;
+    }
+    return true;
 }
 
 __device__ __forceinline__ uint32_t ld_nc_u32(const uint8_t* p) {
@@ -240,7 +254,16 @@ __global__ void __launch_bounds__(kListThreads) waf_gate_resolve_kernel(const __
                     for (int w = 0; w < 8; ++w) {
                         const uint32_t j = pos + 2u * (uint32_t)w;
                         // the window must overlap the field (and lie inside the batch's bytes: j < e <= total)
-                        if (j + 4u > s && j < e) mask |= gate_l2(reinterpret_cast<const uint2*>(F.slots), F.kt, g[w]);
+                        if (!(j + 4u > s && j < e)) continue;
+                        const uint4 en = gate_l2(reinterpret_cast<const uint4*>(F.slots), F.kt, g[w]);
+                        mask |= en.y;
+                        // finite-string patterns announced by this gram: compared in place, their atoms fired here
+                        for (uint32_t c = 0; c < en.w; ++c) {
+                            const uint32_t cd = __ldg(F.lit_cand + en.z + c);
+                            const LitDesc d = F.lits[cd >> 2];
+                            if (lit_matches(F, d, s, e, (int64_t)j + (int64_t)(cd & 3u) - 1))
+                                fire_atom(Sink{gp.rows + (size_t)r * gp.atom_words, gp.info + 2u * (size_t)r}, d.atom);
+                        }
                     }
                 }
             }

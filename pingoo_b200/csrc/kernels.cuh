@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "gate.hpp"
 #include "program.hpp"
 
 namespace pgw {
@@ -117,7 +118,10 @@ struct GateField {
     const uint8_t* col;      // field bytes
     const uint32_t* off;     // n + 1 offsets
     const uint32_t* b1;      // level 1: blocked Bloom filter (2^k1 bits), global memory copy (staged into shared memory)
-    const uint32_t* slots;   // level 2: exact table, 2^kt slots of {gram, unit mask}
+    const uint32_t* slots;   // level 2: exact table, 2^kt slots of {gram, unit mask, first literal candidate, their number}
+    const uint32_t* lit_cand;   // literal candidates of the grams: (literal << 2) | (delta + 1)
+    const LitDesc* lits;        // finite-string patterns confirmed by the resolve kernel (gate.hpp)
+    const uint8_t* lit_bytes;
     uint32_t k1, kt;
     uint32_t bloom_off;      // byte offset of the field's bitmap in the gate kernel's shared memory (all fields resident)
     uint32_t* bitmap;        // hit bitmap: one bit per 16-byte chunk of the column (index = column position >> 4); the gate
@@ -135,6 +139,10 @@ struct GateParams {
     GateField f[kMaxGateFields];
     uint32_t n_fields;
     uint32_t n;              // requests
+    // where a confirmed literal's atom goes: the request's bitmap row and info words (as KParams)
+    uint32_t* rows;
+    uint32_t* info;
+    uint32_t atom_words;
 };
 
 // host-callable wrappers (kernels.cu)

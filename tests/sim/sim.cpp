@@ -207,7 +207,14 @@ static int evaluate_range(Sim* s, const pgw_batch* b, uint32_t* out, uint16_t* s
                 uint32_t w = 0;
                 for (uint32_t k = 0; k < 4; ++k)
                     if (j + k < total) w |= (uint32_t)bytes[j + k] << (8 * k);  // past the column: zeros
-                cand[f] |= G.probe(w);
+                uint32_t lb = 0, lc = 0;
+                cand[f] |= G.probe(w, &lb, &lc);
+                // finite-string patterns announced by the window's gram: compared in place (the resolve kernel's job)
+                for (uint32_t c = 0; c < lc; ++c) {
+                    const uint32_t cd = G.lit_cand[lb + c];
+                    const LitDesc& d = G.lits[cd >> 2];
+                    if (G.lit_matches(d, bytes, a, e, (int64_t)j + (int64_t)(cd & 3u) - 1)) row[d.atom >> 5] |= 1u << (d.atom & 31);
+                }
             }
             if (s->stats) { s->stats[2 * f] += 1; s->stats[2 * f + 1] += cand[f] ? 1 : 0; }
         }

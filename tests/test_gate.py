@@ -43,7 +43,9 @@ RULES = [
 
 def test_units_are_classified():
     d = Sim(RULES).describe()
-    assert "url/gated" in d and "user_agent/gated" in d and "path/gated" in d and "gate(url:" in d
+    assert "url/gated" in d and "gate(url:" in d and "gate(user_agent:" in d and "gate(path:" in d
+    # the user-agent and path patterns of this set are finite string sets: confirmed by the gate, no gated unit left
+    assert "literals=" in d and "user_agent/gated" not in d and "path/gated" not in d
     assert "[url:" in d  # the one-byte pattern keeps an ungated url unit
     off = Sim(RULES, candidate_gate=False).describe()
     assert "gated" not in off and "gate(" not in off
