@@ -58,7 +58,9 @@ typedef struct pgw_options {
                                       http_listener.rs:196-204 inside the engine; 0: rules only */
     int32_t disable_candidate_gate; /* 0 (default): url / user_agent / path patterns are prefiltered by the gram gate and
                                       only candidate requests are walked by their DFAs; 1: every request is walked
-                                      (same verdicts; kept for measurements and tests) */
+                                      (same verdicts; kept for measurements and tests); 2: the gate stays, but finite-string
+                                      patterns are walked by the DFAs like every other pattern instead of being confirmed by
+                                      the gate's resolve kernel (same verdicts; measurements and tests) */
 } pgw_options;
 
 /* One string column: concatenated bytes + n+1 offsets.  `bytes` must be 32-byte aligned and readable up to

@@ -227,7 +227,8 @@ int pgw_ruleset_create(const pgw_rule_desc* rules, uint32_t n_rules, const pgw_o
         if (options->max_dfa_states > 0) rs->builder.options.max_dfa_states = options->max_dfa_states;
         if (options->max_unit_table_bytes > 0) rs->builder.options.max_unit_table_bytes = (size_t)options->max_unit_table_bytes;
         rs->builder.options.eval_gates = options->eval_gates != 0;
-        rs->builder.options.candidate_gate = options->disable_candidate_gate == 0;
+        rs->builder.options.candidate_gate = (options->disable_candidate_gate & 1) == 0;
+        rs->builder.options.literal_confirm = (options->disable_candidate_gate & 2) == 0;
     }
     for (uint32_t i = 0; i < n_rules; ++i) {
         std::string e;
@@ -250,7 +251,8 @@ int pgw_ruleset_load_dir(const char* config_folder, const char* listener, const 
         if (options->max_dfa_states > 0) rs->builder.options.max_dfa_states = options->max_dfa_states;
         if (options->max_unit_table_bytes > 0) rs->builder.options.max_unit_table_bytes = (size_t)options->max_unit_table_bytes;
         rs->builder.options.eval_gates = options->eval_gates != 0;
-        rs->builder.options.candidate_gate = options->disable_candidate_gate == 0;
+        rs->builder.options.candidate_gate = (options->disable_candidate_gate & 1) == 0;
+        rs->builder.options.literal_confirm = (options->disable_candidate_gate & 2) == 0;
     }
     std::vector<std::string> dirs;
     for (uint32_t i = 0; i < n_geoip_dirs; ++i) dirs.push_back(geoip_dirs[i]);
@@ -383,6 +385,14 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     P.units = (const UnitDesc*)chk(M.upload(units));
     rs->gate_smem = waf_gate_smem_bytes(G);
     if (rs->gate_smem > rs->max_smem) return fail("candidate-gate bitmaps do not fit shared memory", err, err_cap);
+    // bit-parallel NFA units: descriptors and tables in global memory; the kernel stages a unit's tables when they fit
+    P.n_bitset = (uint32_t)H.bitset_units.size();
+    if (P.n_bitset > 65535u) return fail("too many patterns that need the bit-parallel NFA unit", err, err_cap);
+    P.bitset_units = (const BitsetUnitDesc*)chk(M.upload(H.bitset_units));
+    P.bitset_blob = (const uint32_t*)chk(M.upload(H.bitset_blob));
+    P.bitset_smem_words = 0;
+    for (const BitsetUnitDesc& b : H.bitset_units)
+        if ((size_t)b.blob_words * 4 <= waf_bitset_smem_budget() && b.blob_words > P.bitset_smem_words) P.bitset_smem_words = b.blob_words;
     P.acc_idx = (const uint32_t*)chk(M.upload(H.acc_idx));
     P.acc_events = (const uint32_t*)chk(M.upload(H.acc_events));
     P.end_idx = (const uint32_t*)chk(M.upload(H.end_idx));

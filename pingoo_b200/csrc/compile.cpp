@@ -9,11 +9,13 @@
 #include <cstring>
 #include <functional>
 #include <iterator>
+#include <map>
 #include <set>
 #include <sstream>
 
 #include "dfa.hpp"
 #include "gate.hpp"
+#include "nfa_bits.hpp"
 
 namespace pgw {
 namespace {
@@ -76,6 +78,8 @@ std::string HostProgram::summary() const {
     for (size_t u = 0; u < units.size(); ++u)
         o << " [" << kFieldNames[units[u].field] << (units[u].mode == UM_CANDIDATES ? "/gated" : units[u].abs0 != 0xFFFFFFFFu ? "/early-exit" : "")
           << ": states=" << units[u].n_states << " classes=" << units[u].n_classes << "]";
+    for (const BitsetUnitDesc& b : bitset_units)
+        o << " [" << kFieldNames[b.field] << "/bitset-nfa: positions=" << b.n_pos << " contexts=" << b.n_tables << " classes=" << b.n_classes << "]";
     for (int f = 0; f < N_FIELDS; ++f)
         if (gate[f].present) {
             o << " gate(" << kFieldNames[f] << ": grams=" << gate[f].n_grams << " bloom=2^" << gate[f].k1 << " table=2^" << gate[f].kt;
@@ -382,6 +386,7 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
         // atoms whose pattern is a small finite set of strings: confirmed by the gate's resolve kernel, no automaton (gate.hpp)
         std::vector<GateLiteral> literals;
         std::vector<uint32_t> literal_grams;   // distinct grams the literals put into the field's budget
+        std::map<uint32_t, uint32_t> literal_list_len;   // gram -> literals it announces so far
         for (uint32_t a = 0; a < H.n_atoms; ++a)
             if (M.atoms[a].kind == AtomDesc::STR_PATTERN && M.atoms[a].field == f) {
                 // atoms no rule refers to any more (replaced by their complement) are not scanned
@@ -407,15 +412,26 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
                         if (opt.literal_confirm && b.starts.size() == 1 && !b.has_latch && M.events[M.atoms[a].event_base].kind == EV_FIRE &&
                             (int)a != H.gate_bypass_atom && gate_finite_language(M.nfa[f], b.starts[0], &strs)) {
                             std::vector<uint32_t> lg = literal_grams;
+                            // a gram announces at most kLitListCap literals: the resolve kernel compares them one after the other, so a
+                            // family of strings that share their first bytes (`sqlmap1`, `sqlmap2`, ...) is what a DFA is for
+                            std::map<uint32_t, uint32_t> add;
                             for (const LitString& ls : strs) {
                                 std::vector<std::pair<uint32_t, int>> pg;
                                 gate_grams_for_literal(ls, &pg);
-                                for (auto& pr : pg) lg.push_back(pr.first);
+                                std::sort(pg.begin(), pg.end());
+                                pg.erase(std::unique(pg.begin(), pg.end()), pg.end());
+                                for (auto& pr : pg) { lg.push_back(pr.first); add[pr.first]++; }
+                            }
+                            bool short_lists = true;
+                            for (auto& kv : add) {
+                                auto it = literal_list_len.find(kv.first);
+                                if ((it == literal_list_len.end() ? 0u : it->second) + kv.second > kLitListCap) { short_lists = false; break; }
                             }
                             std::sort(lg.begin(), lg.end());
                             lg.erase(std::unique(lg.begin(), lg.end()), lg.end());
-                            if (lg.size() <= opt.gate_field_cap / 2) {   // half of the field's gram budget at most
+                            if (short_lists && lg.size() <= opt.gate_field_cap / 2) {   // half of the field's gram budget at most
                                 literal_grams.swap(lg);
+                                for (auto& kv : add) literal_list_len[kv.first] += kv.second;
                                 for (const LitString& ls : strs) literals.push_back(GateLiteral{ls, a});
                                 continue;   // no DFA for this atom
                             }
@@ -463,15 +479,30 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
             if (bundles[cls].empty()) continue;
             any = true;
             DfaGroups groups;
-            int failed = -1;
+            std::vector<int> too_big;
             // (Capping gated units at the shared-memory budget so that each is wholly resident -- 8 url units instead of 2 at 512
             // rules, 16 instead of 4 at 1 024 -- was measured: no gain at 512 rules, 25 % slower scan at 1 024: candidates walk
             // more units and CTAs stage more images; the cold-row path is not what limits the candidate scan.)
-            if (!build_dfa_groups(M.nfa[f], bundles[cls], opt.max_dfa_states, opt.max_unit_table_bytes, (int)kMaxLatchesPerUnit, &groups, &failed)) {
-                std::string which = failed >= 0 ? M.atoms[bundle_atom[cls][failed]].key : "?";
-                err = "pattern on http_request." + std::string(kFieldNames[f]) + " needs a DFA larger than " +
-                      std::to_string(opt.max_dfa_states) + " states: " + which;
-                return false;
+            build_dfa_groups(M.nfa[f], bundles[cls], opt.max_dfa_states, opt.max_unit_table_bytes, (int)kMaxLatchesPerUnit, &groups, &too_big);
+            // a bundle no DFA of acceptable size exists for is simulated as a bit-parallel NFA over every request (nfa_bits.hpp):
+            // where Rust `regex` would leave its lazy DFA for the PikeVM, not a configuration error
+            for (int bi : too_big) {
+                const AtomDesc& ad = M.atoms[bundle_atom[cls][bi]];
+                std::vector<int> pids;
+                std::vector<uint32_t> words;
+                for (size_t k = 0; k < ad.nfa_starts.size(); ++k) {
+                    const PatternEvent& ev = M.events[ad.event_base + k];
+                    pids.push_back(ad.event_base + (int)k);
+                    words.push_back(((uint32_t)ev.kind << kEvKindShift) | (uint32_t)ev.atom);   // latch 0: one bundle per unit
+                }
+                BitsetUnitDesc bd;
+                std::string berr;
+                if (!build_bitset_unit(M.nfa[f], bundles[cls][bi].starts, pids, words, f, &H.bitset_blob, &bd, berr)) {
+                    err = "pattern on http_request." + std::string(kFieldNames[f]) + " needs a DFA larger than " + std::to_string(opt.max_dfa_states) +
+                          " states and " + berr + ": " + ad.key;
+                    return false;
+                }
+                H.bitset_units.push_back(bd);
             }
             if (cls == UC_GATED) {
                 // a gram leads to the units whose patterns it came from (bit = unit index among the field's gated units, mod kGateWidth)

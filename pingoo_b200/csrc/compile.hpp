@@ -10,7 +10,7 @@
 namespace pgw {
 
 struct CompileOptions {
-    int max_dfa_states = 16384;                // per scan unit, after minimisation
+    int max_dfa_states = 16384;                // per scan unit, after minimisation; a pattern above it alone -> bit-parallel NFA unit
     size_t max_unit_table_bytes = 8u << 20;    // per scan unit transition table (hot rows go to shared memory, the rest stays in L2)
     bool eval_gates = true;                    // evaluate http_listener.rs:196-204 gates inside the engine
     bool candidate_gate = true;                // gram prefilter in front of the DFA scan of url / user_agent / path (gate.hpp)
@@ -34,6 +34,8 @@ struct LpmTables {
 struct HostProgram {
     std::vector<UnitDesc> units;
     std::vector<uint8_t> arena;  // class maps then transition tables (16-byte aligned pieces)
+    std::vector<BitsetUnitDesc> bitset_units;   // bundles too large for any DFA unit: bit-parallel NFA, every request (nfa_bits.hpp)
+    std::vector<uint32_t> bitset_blob;          // their tables
     std::vector<uint32_t> acc_idx;
     std::vector<uint32_t> acc_events;  // event words (program.hpp), sorted by kind within each list
     std::vector<uint32_t> end_idx;

@@ -291,7 +291,7 @@ struct Grouper {
     size_t max_bytes;
     int max_latches;
     DfaGroups* out;
-    int failed = -1;
+    std::vector<int>* too_big;
 
     bool try_build(const std::vector<int>& idx, Dfa* d) {
         std::vector<int> s;
@@ -313,7 +313,7 @@ struct Grouper {
             out->members.push_back(idx);
             return true;
         }
-        if (idx.size() == 1) { failed = idx[0]; return false; }
+        if (idx.size() == 1) { too_big->push_back(idx[0]); return true; }
         size_t h = idx.size() / 2;
         std::vector<int> a(idx.begin(), idx.begin() + h), b(idx.begin() + h, idx.end());
         return split(a) && split(b);
@@ -322,18 +322,16 @@ struct Grouper {
 
 }  // namespace
 
-bool build_dfa_groups(const Nfa& nfa, const std::vector<PatternBundle>& bundles, int max_states, size_t max_table_bytes,
-                      int max_latches, DfaGroups* out, int* failed_index) {
+void build_dfa_groups(const Nfa& nfa, const std::vector<PatternBundle>& bundles, int max_states, size_t max_table_bytes,
+                      int max_latches, DfaGroups* out, std::vector<int>* too_big) {
     out->dfas.clear();
     out->members.clear();
-    if (bundles.empty()) return true;
-    Grouper G{nfa, bundles, max_states, max_table_bytes, max_latches, out};
+    too_big->clear();
+    if (bundles.empty()) return;
+    Grouper G{nfa, bundles, max_states, max_table_bytes, max_latches, out, too_big};
     std::vector<int> all(bundles.size());
     for (size_t i = 0; i < all.size(); ++i) all[i] = (int)i;
-    if (!G.split(all)) {
-        if (failed_index) *failed_index = G.failed;
-        return false;
-    }
+    G.split(all);
     // greedy merge of neighbouring groups (halving can leave mergeable fragments)
     bool merged = true;
     while (merged && out->dfas.size() > 1) {
@@ -353,7 +351,6 @@ bool build_dfa_groups(const Nfa& nfa, const std::vector<PatternBundle>& bundles,
             }
         }
     }
-    return true;
 }
 
 }  // namespace pgw

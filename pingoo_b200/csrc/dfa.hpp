@@ -43,8 +43,9 @@ struct DfaGroups {
 };
 
 // Partition bundles into as few DFAs as possible subject to the caps (and at most `max_latches` latch
-// bundles per DFA).  Returns false (with *failed_index set) if a single bundle alone exceeds the caps.
-bool build_dfa_groups(const Nfa& nfa, const std::vector<PatternBundle>& bundles, int max_states, size_t max_table_bytes,
-                      int max_latches, DfaGroups* out, int* failed_index);
+// bundles per DFA).  A bundle that exceeds the caps on its own lands in `too_big` (indices into `bundles`) and in no
+// group: the caller hands it to the bit-parallel NFA unit (nfa_bits.hpp), as Rust `regex` leaves its DFA for the PikeVM.
+void build_dfa_groups(const Nfa& nfa, const std::vector<PatternBundle>& bundles, int max_states, size_t max_table_bytes,
+                      int max_latches, DfaGroups* out, std::vector<int>* too_big);
 
 }  // namespace pgw

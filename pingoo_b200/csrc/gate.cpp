@@ -398,6 +398,7 @@ void gate_build_tables(const std::vector<uint32_t>& grams, const std::vector<uin
         d.flags = (uint16_t)((ls.anch_start ? 1 : 0) | (ls.anch_end ? 2 : 0));
         d.atom = literals[li].atom;
         d.pad = 0;
+        d.pad2 = 0;
         d.ci_mask = ls.ci_mask;
         T.lits.push_back(d);
         T.lit_bytes.insert(T.lit_bytes.end(), ls.bytes.begin(), ls.bytes.end());

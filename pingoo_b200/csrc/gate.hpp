@@ -68,6 +68,7 @@ struct LitString {
     bool operator==(const LitString& o) const { return bytes == o.bytes && ci_mask == o.ci_mask && anch_start == o.anch_start && anch_end == o.anch_end; }
 };
 constexpr size_t kLitMaxStrings = 48, kLitMaxLen = 64, kLitMinLen = 3;
+constexpr uint32_t kLitListCap = 4;   // literals one gram may announce (compile.cpp: the rest stays with the DFA units)
 
 // device / table form of one literal (program.hpp style POD)
 struct LitDesc {
@@ -77,7 +78,9 @@ struct LitDesc {
     uint32_t atom;
     uint32_t pad;
     uint64_t ci_mask;
+    uint64_t pad2;      // 32 bytes: the resolve kernel reads a descriptor as two 16-byte loads
 };
+static_assert(sizeof(LitDesc) == 32, "LitDesc is read as two uint4");
 
 struct GateTables {
     bool present = false;
@@ -111,7 +114,7 @@ struct GateTables {
         if (at < (int64_t)s || at + d.len > (int64_t)e) return false;
         if ((d.flags & 1) && at != (int64_t)s) return false;
         if ((d.flags & 2) && at + d.len != (int64_t)e) return false;
-        for (uint32_t k = 0; k < d.len; ++k) {
+        for (uint32_t k = d.len; k-- > 0;) {   // last byte first: the bytes behind the announcing gram tell candidates apart
             const uint8_t b = col[at + k], want = lit_bytes[d.off + k];
             if (b != want && !(((d.ci_mask >> k) & 1) && (uint8_t)(b ^ 0x20) == want)) return false;
         }

@@ -13,6 +13,8 @@
 //   kernel_field.cuh    waf_field_scan_kernel -- DFA scan: unit-major, lane-owned strings, pooled claims, per-unit
 //                       shared-memory images, early exit on absorbing states, bitmaps + dirty bits in global memory;
 //                       waf_epilogue_kernel -- verdicts (one thread per request, warp-shared evaluation)
+//   kernel_bitset.cuh   waf_bitset_nfa_kernel -- bit-parallel NFA simulation (active-position bit vectors, tables in shared
+//                       memory) for the patterns whose DFA would exceed the scan-unit caps
 //   kernel_misc.cuh     geoip_lookup_kernel (geoip.rs:73-91), captcha_client_id_kernel (captcha.rs:409-421)
 //   kernels.cu          this file: launch wrappers, host-callable, no CUDA types in their signatures beyond the stream
 //
@@ -46,6 +48,7 @@ namespace {
 #include "kernel_common.cuh"
 #include "kernel_gate.cuh"
 #include "kernel_field.cuh"
+#include "kernel_bitset.cuh"
 #include "kernel_misc.cuh"
 
 }  // namespace
@@ -84,6 +87,8 @@ const char* waf_configure(int device, size_t* max_smem_optin, int* sm_count) {
     if (e != cudaSuccess) return cudaGetErrorString(e);
     e = cudaFuncSetAttribute(waf_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(waf_prefix_budget() + 512));
     if (e != cudaSuccess) return cudaGetErrorString(e);
+    e = cudaFuncSetAttribute(waf_bitset_nfa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)waf_bitset_smem_budget());
+    if (e != cudaSuccess) return cudaGetErrorString(e);
     return nullptr;
 }
 
@@ -103,6 +108,8 @@ size_t waf_gate_smem_bytes(const GateParams& g) {
 }
 
 size_t waf_prefix_budget() { return 64u << 10; }
+
+size_t waf_bitset_smem_budget() { return 96u << 10; }
 
 const char* waf_batch_launch(KParams& p, GateParams& g, const UnitDesc* all_units, uint32_t* small, uint32_t small_words, int sm_count,
                              size_t scan_smem, size_t gate_smem, void* stream, cudaEvent_t* ev, uint32_t* launches) {
@@ -124,7 +131,9 @@ const char* waf_batch_launch(KParams& p, GateParams& g, const UnitDesc* all_unit
         waf_gate_maybe_kernel<<<lb, kListThreads, 0, s>>>(g);
         e = cudaGetLastError();
         if (e != cudaSuccess) return cudaGetErrorString(e);
-        waf_gate_resolve_kernel<<<dim3(lb, g.n_fields), kListThreads, 0, s>>>(g);
+        uint32_t rb = (p.n + kResolveThreads - 1u) / kResolveThreads;
+        if (rb > (uint32_t)sm_count * 8u) rb = (uint32_t)sm_count * 8u;
+        waf_gate_resolve_kernel<<<dim3(rb, g.n_fields), kResolveThreads, 0, s>>>(g);
         e = cudaGetLastError();
         if (e != cudaSuccess) return cudaGetErrorString(e);
         nl += 3;
@@ -140,6 +149,23 @@ const char* waf_batch_launch(KParams& p, GateParams& g, const UnitDesc* all_unit
         const uint32_t want = (p.n + kFsThreads - 1) / kFsThreads;
         const int grid = (int)(want < (uint32_t)sm_count ? want : (uint32_t)sm_count);
         waf_field_scan_kernel<<<grid, kFsThreads, scan_smem, s>>>(p);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cudaGetErrorString(e);
+        ++nl;
+    }
+    if (p.n_bitset) {
+        BitsetParams bp;
+        for (int f = 0; f < 5; ++f) { bp.col[f] = p.col[f]; bp.off[f] = p.off[f]; }
+        bp.n = p.n;
+        bp.rows = p.rows;
+        bp.info = p.info;
+        bp.atom_words = p.atom_words;
+        bp.units = p.bitset_units;
+        bp.blob = p.bitset_blob;
+        bp.smem_words = p.bitset_smem_words;
+        uint32_t blocks = (p.n + kBitsetThreads - 1) / kBitsetThreads;
+        if (blocks > (uint32_t)sm_count * 8u) blocks = (uint32_t)sm_count * 8u;
+        waf_bitset_nfa_kernel<<<dim3(blocks, p.n_bitset), kBitsetThreads, (size_t)p.bitset_smem_words * 4, s>>>(bp);
         e = cudaGetLastError();
         if (e != cudaSuccess) return cudaGetErrorString(e);
         ++nl;

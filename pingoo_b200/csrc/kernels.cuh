@@ -102,6 +102,11 @@ struct KParams {
     uint32_t lpm_present;
     uint32_t geo_loaded;
     uint32_t need_lpm;          // any ip-set atom, or geo columns needed and resolved on device
+    // ---- bit-parallel NFA units (nfa_bits.hpp): bundles no DFA unit can hold; one extra kernel, only when present ----
+    const BitsetUnitDesc* bitset_units;
+    const uint32_t* bitset_blob;
+    uint32_t n_bitset;
+    uint32_t bitset_smem_words;   // dynamic shared memory of that kernel: the largest unit table that fits the budget
     // ---- small early-exit units walked by the epilogue kernel (UM_PREPASS): descriptors here, tables in its shared memory ----
     uint32_t n_prefix;
     uint32_t prefix_area;                     // bytes of shared memory their images take (multiple of 256)
@@ -150,8 +155,9 @@ size_t waf_scan_smem_bytes(uint32_t max_image_bytes);
 size_t waf_scan_image_budget(size_t max_smem_optin);  // bytes a unit image may take
 int waf_scan_threads();
 size_t waf_gate_smem_bytes(const GateParams& g);
+size_t waf_bitset_smem_budget();   // bytes of shared memory a bit-parallel NFA unit's tables may take (larger ones stay in global memory)
 size_t waf_prefix_budget();  // shared memory the images of all early-exit units walked by the epilogue kernel may take
-// One batch: [gate -> maybe -> resolve] -> scan (one launch per kMaxConstUnits units) -> epilogue -> multi, all on
+// One batch: [gate -> maybe -> resolve] -> scan (one launch per kMaxConstUnits units) [-> bitset NFA] -> epilogue -> multi, all on
 // `stream`.  `all_units` = the program's unit descriptors (host copy); `small` = the block of claim counters, candidate
 // counters and list counters to zero first (`small_words` words).  `ev` (optional): four events recorded before the
 // gate kernels, after them, after the scan launches and after the epilogue + multi kernels.

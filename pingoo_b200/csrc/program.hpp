@@ -66,6 +66,20 @@ struct UnitDesc {
     uint32_t gate_bit;     // UM_CANDIDATES: this unit's bit in a candidate's unit mask (unit index among the field's gated units % kGateWidth)
 };
 
+// one bit-parallel NFA unit (nfa_bits.hpp): a bundle of patterns too large for any DFA unit, walked for every request
+struct BitsetUnitDesc {
+    uint32_t field;        // Field enum
+    uint32_t n_pos;        // P: byte-consuming NFA positions; row P of the tables = the start nodes
+    uint32_t words;        // W = ceil(P / 32): state words per request
+    uint32_t n_tables;     // T: distinct look-around contexts
+    uint32_t n_classes;
+    uint32_t n_patterns;   // <= 32
+    uint32_t blob_off;     // word offset of the unit's tables in the blob
+    uint32_t blob_words;
+    uint32_t follow_off, accept_off, bmask_off;   // word offsets inside the unit's tables (layout: nfa_bits.hpp)
+    uint32_t stop_mask;    // all patterns, if every event is a plain FIRE: the walk stops once they have all fired; else 0
+};
+
 // which requests a scan unit walks
 enum UnitMode : uint32_t {
     UM_ALL = 0,        // every request (patterns the gate cannot cover; start-anchored patterns, which finish early)

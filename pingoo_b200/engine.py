@@ -21,7 +21,7 @@ class WafEngine:
     def __init__(self, rules: Iterable[Rule], lists: Optional[Dict[str, Tuple[ListType, bytes]]] = None,
                  geoip_mmdb: Optional[bytes] = None, device: int = 0, eval_gates: bool = True,
                  max_dfa_states: int = 0, max_unit_table_bytes: int = 0, services: Optional[Iterable[Service]] = None,
-                 candidate_gate: bool = True):
+                 candidate_gate: bool = True, literal_confirm: bool = True):
         self._lib = _ffi.load()
         self._h = C.c_void_p()
         self.rules = list(rules)
@@ -34,7 +34,7 @@ class WafEngine:
             descs[i].expression = None if r.expression is None else r.expression.encode()
             descs[i].actions = C.cast(acts, C.POINTER(C.c_uint8))
             descs[i].n_actions = len(r.actions)
-        opt = _ffi.Options(max_dfa_states, max_unit_table_bytes, 1 if eval_gates else 0, 0 if candidate_gate else 1)
+        opt = _ffi.Options(max_dfa_states, max_unit_table_bytes, 1 if eval_gates else 0, (0 if candidate_gate else 1) | (0 if literal_confirm else 2))
         err = C.create_string_buffer(1024)
         if self._lib.pgw_ruleset_create(descs, len(self.rules), C.byref(opt), C.byref(self._h), err, len(err)):
             raise Error(err.value.decode(errors="replace"))
@@ -67,13 +67,14 @@ class WafEngine:
 
     @classmethod
     def from_config_dir(cls, folder: str, listener: Optional[str] = None, geoip_dirs: Optional[Iterable[str]] = None, device: int = 0,
-                        eval_gates: bool = True, max_dfa_states: int = 0, max_unit_table_bytes: int = 0, candidate_gate: bool = True):
+                        eval_gates: bool = True, max_dfa_states: int = 0, max_unit_table_bytes: int = 0, candidate_gate: bool = True,
+                        literal_confirm: bool = True):
         """pgw_ruleset_load_dir + finalize: a Pingoo configuration directory consumed by the engine's own (C++) loader."""
         self = cls.__new__(cls)
         self._lib = _ffi.load()
         self._h = C.c_void_p()
         self.rules, self.services, self._keep = [], [], []
-        opt = _ffi.Options(max_dfa_states, max_unit_table_bytes, 1 if eval_gates else 0, 0 if candidate_gate else 1)
+        opt = _ffi.Options(max_dfa_states, max_unit_table_bytes, 1 if eval_gates else 0, (0 if candidate_gate else 1) | (0 if literal_confirm else 2))
         err = C.create_string_buffer(2048)
         dirs = [d.encode() for d in (geoip_dirs or [])]
         arr = (C.c_char_p * max(1, len(dirs)))(*dirs)

@@ -156,11 +156,11 @@ class Sim:
     """CPU walk over the tables the product compiler emits (compiler check without a GPU)."""
 
     def __init__(self, rules, lists=None, geoip_mmdb=None, eval_gates=True, max_dfa_states=0, max_unit_table_bytes=0, services=None,
-                 candidate_gate=True):
+                 candidate_gate=True, literal_confirm=True):
         self.lib = sim_lib()
         descs, keep, n = _descs(rules)
         err = C.create_string_buffer(2048)
-        opt = _ffi.Options(max_dfa_states, max_unit_table_bytes, 1 if eval_gates else 0, 0 if candidate_gate else 1)
+        opt = _ffi.Options(max_dfa_states, max_unit_table_bytes, 1 if eval_gates else 0, (0 if candidate_gate else 1) | (0 if literal_confirm else 2))
         self.h = self.lib.pgwsim_create(descs, n, C.byref(opt), err, len(err))
         if not self.h:
             raise ValueError(err.value.decode(errors="replace"))

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/pingoo_waf.h"
+#include "../../pingoo_b200/csrc/nfa_bits.hpp"
 #include "../../pingoo_b200/csrc/ruleset.hpp"
 #include "../../pingoo_b200/csrc/yaml.hpp"
 
@@ -26,6 +27,7 @@ struct Sim {
     std::string last_error;
     uint64_t* stats = nullptr;  // optional: per field {requests gated, candidates}
     uint64_t* atom_hist = nullptr;
+    uint64_t* lit_stats = nullptr;  // optional: {windows with a gram that has literal candidates, candidates compared, confirmed, largest candidate list}
 };
 
 int fail(Sim* s, const std::string& m, char* err, size_t cap) {
@@ -89,7 +91,8 @@ void* pgwsim_create(const pgw_rule_desc* rules, uint32_t n, const pgw_options* o
         if (opt->max_dfa_states > 0) s->builder.options.max_dfa_states = opt->max_dfa_states;
         if (opt->max_unit_table_bytes > 0) s->builder.options.max_unit_table_bytes = (size_t)opt->max_unit_table_bytes;
         s->builder.options.eval_gates = opt->eval_gates != 0;
-        s->builder.options.candidate_gate = opt->disable_candidate_gate == 0;
+        s->builder.options.candidate_gate = (opt->disable_candidate_gate & 1) == 0;
+        s->builder.options.literal_confirm = (opt->disable_candidate_gate & 2) == 0;
     }
     for (uint32_t i = 0; i < n; ++i) {
         std::string e;
@@ -210,10 +213,11 @@ static int evaluate_range(Sim* s, const pgw_batch* b, uint32_t* out, uint16_t* s
                 uint32_t lb = 0, lc = 0;
                 cand[f] |= G.probe(w, &lb, &lc);
                 // finite-string patterns announced by the window's gram: compared in place (the resolve kernel's job)
+                if (s->lit_stats && lc) { s->lit_stats[0]++; s->lit_stats[1] += lc; if (lc > s->lit_stats[3]) s->lit_stats[3] = lc; }
                 for (uint32_t c = 0; c < lc; ++c) {
                     const uint32_t cd = G.lit_cand[lb + c];
                     const LitDesc& d = G.lits[cd >> 2];
-                    if (G.lit_matches(d, bytes, a, e, (int64_t)j + (int64_t)(cd & 3u) - 1)) row[d.atom >> 5] |= 1u << (d.atom & 31);
+                    if (G.lit_matches(d, bytes, a, e, (int64_t)j + (int64_t)(cd & 3u) - 1)) { row[d.atom >> 5] |= 1u << (d.atom & 31); if (s->lit_stats) s->lit_stats[2]++; }
                 }
             }
             if (s->stats) { s->stats[2 * f] += 1; s->stats[2 * f + 1] += cand[f] ? 1 : 0; }
@@ -242,6 +246,10 @@ static int evaluate_range(Sim* s, const pgw_batch* b, uint32_t* out, uint16_t* s
             }
             if (u.end_any) run_events(H.end_idx, H.end_events, u.end_base + st);
         }
+        // bit-parallel NFA units (kernel_bitset.cuh): every request, whole field
+        for (const BitsetUnitDesc& bu : H.bitset_units)
+            bitset_walk_host(bu, H.bitset_blob.data() + bu.blob_off, cols[bu.field]->bytes, cols[bu.field]->offsets[r], cols[bu.field]->offsets[r + 1],
+                             [&](uint32_t at) { row[at >> 5] |= 1u << (at & 31); });
         // per-request predicates
         uint32_t flags = b->flags ? b->flags[r] : 0;
         int64_t asn = 0;
@@ -595,6 +603,9 @@ extern "C" void pgwsim_gate_window_stats(void* h, const pgw_batch* b, int f, uin
         }
     }
 }
+
+// debug: literal-confirmation work {windows whose gram has literal candidates, candidates compared, confirmed, longest list}
+extern "C" void pgwsim_set_lit_stats(void* h, uint64_t* out4) { ((Sim*)h)->lit_stats = out4; }
 
 // debug: histogram of the number of true atoms per request (out[0..3] = 0, 1, 2, >=3) -- sizes the epilogue's paths
 extern "C" void pgwsim_set_atom_hist(void* h, uint64_t* out4) { ((Sim*)h)->atom_hist = out4; }
