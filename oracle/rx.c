@@ -10,7 +10,8 @@
 
 /* ---- AST ------------------------------------------------------------------------ */
 enum { N_EMPTY, N_SET, N_ASSERT, N_CAT, N_ALT, N_REP };
-enum { AS_BOT, AS_EOT, AS_BOL, AS_EOL, AS_WB, AS_NWB };
+/* AS_WS .. AS_WEH: \b{start} = \<, \b{end} = \>, \b{start-half}, \b{end-half} (regex 1.10+, docs "Empty matches / word boundaries") */
+enum { AS_BOT, AS_EOT, AS_BOL, AS_EOL, AS_WB, AS_NWB, AS_WS, AS_WE, AS_WSH, AS_WEH };
 
 typedef struct node {
     int kind;
@@ -78,6 +79,103 @@ static void perl_set(uint8_t* s, int k) {
         for (unsigned c = 0; c < 128; ++c)
             if (is_word((int)c)) set_add(s, c);
     }
+}
+
+/* \p{..} on ASCII haystacks (oracle.h: request strings are ASCII; a byte >= 0x80 is one opaque character).  Written from
+ * the code charts, member by member: the ASCII characters of each general category, then the names that select them.
+ * Returns 1 if the (normalised: lower case, no ' ', '_', '-') name is known and fills `s` with its ASCII members. */
+static void set_chars(uint8_t* s, const char* chars) {
+    for (; *chars; ++chars) set_add(s, (unsigned char)*chars);
+}
+static int uni_gc(const char* v, uint8_t* s) {
+    static const char* PO = "!\"#%&'*,./:;?@\\";
+#define V(x) (strcmp(v, x) == 0)
+    if (V("l") || V("letter") || V("lc") || V("casedletter")) { set_range(s, 'A', 'Z'); set_range(s, 'a', 'z'); }
+    else if (V("lu") || V("uppercaseletter")) set_range(s, 'A', 'Z');
+    else if (V("ll") || V("lowercaseletter")) set_range(s, 'a', 'z');
+    else if (V("n") || V("number") || V("nd") || V("decimalnumber") || V("digit")) set_range(s, '0', '9');
+    else if (V("p") || V("punctuation") || V("punct")) { set_chars(s, PO); set_chars(s, "_-([{)]}"); }
+    else if (V("pc") || V("connectorpunctuation")) set_chars(s, "_");
+    else if (V("pd") || V("dashpunctuation")) set_chars(s, "-");
+    else if (V("ps") || V("openpunctuation")) set_chars(s, "([{");
+    else if (V("pe") || V("closepunctuation")) set_chars(s, ")]}");
+    else if (V("po") || V("otherpunctuation")) set_chars(s, PO);
+    else if (V("s") || V("symbol")) set_chars(s, "+<=>|~$^`");
+    else if (V("sm") || V("mathsymbol")) set_chars(s, "+<=>|~");
+    else if (V("sc") || V("currencysymbol")) set_chars(s, "$");
+    else if (V("sk") || V("modifiersymbol")) set_chars(s, "^`");
+    else if (V("z") || V("separator") || V("zs") || V("spaceseparator")) set_chars(s, " ");
+    else if (V("c") || V("other") || V("cc") || V("control") || V("cntrl")) { set_range(s, 0, 31); set_add(s, 127); }
+    else if (V("lt") || V("titlecaseletter") || V("lm") || V("modifierletter") || V("lo") || V("otherletter") || V("m") || V("mark") ||
+             V("combiningmark") || V("mn") || V("nonspacingmark") || V("mc") || V("spacingmark") || V("me") || V("enclosingmark") || V("nl") ||
+             V("letternumber") || V("no") || V("othernumber") || V("pi") || V("initialpunctuation") || V("pf") || V("finalpunctuation") ||
+             V("so") || V("othersymbol") || V("zl") || V("lineseparator") || V("zp") || V("paragraphseparator") || V("cf") || V("format") ||
+             V("cs") || V("surrogate") || V("co") || V("privateuse") || V("cn") || V("unassigned")) { /* no ASCII member */ }
+    else return 0;
+    return 1;
+}
+static int uni_script(const char* v, uint8_t* s) {
+    static const char* none[] = {"greek", "grek", "cyrillic", "cyrl", "han", "hani", "arabic", "arab", "hebrew", "hebr", "hiragana", "hira", "katakana",
+                                 "kana", "thai", "devanagari", "deva", "hangul", "hang", "armenian", "armn", "georgian", "geor", "ethiopic", "ethi",
+                                 "bengali", "beng", "tamil", "taml", "telugu", "telu", "gujarati", "gujr", "gurmukhi", "guru", "kannada", "knda",
+                                 "malayalam", "mlym", "sinhala", "sinh", "khmer", "khmr", "lao", "laoo", "tibetan", "tibt", "myanmar", "mymr", "mongolian",
+                                 "mong", "syriac", "syrc", "thaana", "thaa", "coptic", "copt", "cherokee", "cher", "bopomofo", "bopo", "braille", "brai",
+                                 "inherited", "zinh", "qaai", NULL};
+    if (V("latin") || V("latn")) { set_range(s, 'A', 'Z'); set_range(s, 'a', 'z'); return 1; }
+    if (V("common") || V("zyyy")) {
+        for (unsigned c = 0; c < 128; ++c)
+            if (!((c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z'))) set_add(s, c);
+        return 1;
+    }
+    for (int i = 0; none[i]; ++i)
+        if (strcmp(v, none[i]) == 0) return 1;
+    return 0;
+}
+/* 0 ok, 1 unknown name, 2 malformed */
+static int uni_class(const char* raw, size_t len, uint8_t* s, int* negated) {
+    char key[64], val[64];
+    size_t nk = 0, nv = 0;
+    int neg = 0, have_key = 0;
+    memset(s, 0, 32);
+    size_t i = 0;
+    if (i < len && raw[i] == '^') { neg = 1; ++i; }
+    for (; i < len; ++i) {
+        char ch = raw[i];
+        if (!have_key && (ch == '=' || ch == ':')) {
+            if (ch == '=' && nv > 0 && val[nv - 1] == '!') { neg = !neg; --nv; }
+            memcpy(key, val, nv);
+            nk = nv;
+            nv = 0;
+            have_key = 1;
+            continue;
+        }
+        if (ch == ' ' || ch == '_' || ch == '-') continue;
+        if (ch >= 'A' && ch <= 'Z') ch = (char)(ch + 32);
+        if (nv + 1 >= sizeof val) return 1;
+        val[nv++] = ch;
+    }
+    key[nk] = 0;
+    val[nv] = 0;
+    if (nv == 0) return 2;
+    const char* v = val;
+    int ok;
+    if (have_key) {
+        if (!strcmp(key, "gc") || !strcmp(key, "generalcategory")) ok = uni_gc(val, s);
+        else if (!strcmp(key, "sc") || !strcmp(key, "script") || !strcmp(key, "scx") || !strcmp(key, "scriptextensions")) ok = uni_script(val, s);
+        else return 1;
+    } else if (V("any")) { memset(s, 0xFF, 32); ok = 1; }
+    else if (V("ascii")) { set_range(s, 0, 127); ok = 1; }
+    else if (V("assigned")) { memset(s, 0xFF, 32); ok = 1; }
+    else if (V("alphabetic") || V("alpha") || V("cased")) { set_range(s, 'A', 'Z'); set_range(s, 'a', 'z'); ok = 1; }
+    else if (V("uppercase") || V("upper")) { set_range(s, 'A', 'Z'); ok = 1; }
+    else if (V("lowercase") || V("lower")) { set_range(s, 'a', 'z'); ok = 1; }
+    else if (V("whitespace") || V("wspace") || V("space")) { set_add(s, ' '); set_range(s, 9, 13); ok = 1; }
+    else if (V("hexdigit") || V("hex") || V("asciihexdigit") || V("ahex")) { set_range(s, '0', '9'); set_range(s, 'A', 'F'); set_range(s, 'a', 'f'); ok = 1; }
+    else ok = uni_gc(val, s) || uni_script(val, s);
+#undef V
+    if (!ok) return 1;
+    *negated = neg; /* applied by the caller AFTER case folding (regex-syntax: fold, then negate) */
+    return 0;
 }
 
 static int at_end(parser* P) { return P->pos >= P->n; }
@@ -175,14 +273,61 @@ static esc_t parse_escape(parser* P, int in_class, const flags_t* f) {
         case 'f': e.cp = 12; return e;
         case 'v': e.cp = 11; return e;
         case 'x': case 'u': case 'U': e.cp = parse_hex(P, c); return e;
-        case 'p': case 'P': pfail(P, RX_UNSUPPORTED, "Unicode classes are not supported");
+        case 'p': case 'P': {
+            /* \pL, \p{Letter}, \p{^L}, \p{gc=Lu}, \p{sc:Latin}; \P negates */
+            const char* nm;
+            size_t len;
+            if (at_end(P)) pfail(P, RX_INVALID, "incomplete Unicode class");
+            if (P->p[P->pos] == '{') {
+                size_t q = P->pos + 1;
+                while (q < P->n && P->p[q] != '}') ++q;
+                if (q >= P->n) pfail(P, RX_INVALID, "unclosed Unicode class");
+                nm = (const char*)P->p + P->pos + 1;
+                len = q - P->pos - 1;
+                P->pos = q + 1;
+            } else {
+                nm = (const char*)P->p + P->pos;
+                len = 1;
+                P->pos++;
+            }
+            int neg = 0;
+            int rc = uni_class(nm, len, e.set, &neg);
+            if (rc == 2) pfail(P, RX_INVALID, "malformed Unicode class");
+            if (rc == 1) pfail(P, RX_UNSUPPORTED, "Unicode property outside the known set");
+            if (f->i) set_fold(e.set);
+            if (neg != (c == 'P')) set_not(e.set);
+            e.kind = E_SET;
+            return e;
+        }
         case 'A': case 'z': case 'b': case 'B':
             if (in_class) pfail(P, RX_INVALID, "unrecognized escape sequence in class");
-            if ((c == 'b') && peekc(P) == '{') pfail(P, RX_UNSUPPORTED, "\\b{...} is not supported");
             e.kind = E_ASSERT;
             e.as = c == 'A' ? AS_BOT : c == 'z' ? AS_EOT : c == 'b' ? AS_WB : AS_NWB;
+            if (c == 'b' && peekc(P) == '{') {
+                /* a name made of letters and '-' up to the closing brace; a digit after the brace would be a counted
+                 * repetition of \b itself, which neither this oracle nor the engine implements */
+                size_t q = P->pos + 1, q0 = q;
+                if (q >= P->n || !((P->p[q] | 32) >= 'a' && (P->p[q] | 32) <= 'z') ) {
+                    if (q < P->n && P->p[q] == '-') { /* falls through to the name scan below */ }
+                    else pfail(P, RX_UNSUPPORTED, "a counted repetition of \\b is not supported");
+                }
+                while (q < P->n && ((((P->p[q] | 32) >= 'a') && ((P->p[q] | 32) <= 'z')) || P->p[q] == '-')) ++q;
+                if (q >= P->n || P->p[q] != '}') pfail(P, RX_INVALID, "unclosed or malformed special word boundary");
+                size_t len = q - q0;
+                const char* nm = (const char*)P->p + q0;
+                if (len == 5 && !memcmp(nm, "start", 5)) e.as = AS_WS;
+                else if (len == 3 && !memcmp(nm, "end", 3)) e.as = AS_WE;
+                else if (len == 10 && !memcmp(nm, "start-half", 10)) e.as = AS_WSH;
+                else if (len == 8 && !memcmp(nm, "end-half", 8)) e.as = AS_WEH;
+                else pfail(P, RX_INVALID, "unrecognized special word boundary assertion");
+                P->pos = q + 1;
+            }
             return e;
-        case '<': case '>': pfail(P, RX_UNSUPPORTED, "\\< and \\> are not supported");
+        case '<': case '>':
+            if (in_class) pfail(P, RX_INVALID, "unrecognized escape sequence in class");
+            e.kind = E_ASSERT;
+            e.as = c == '<' ? AS_WS : AS_WE;
+            return e;
         case ' ':
             if (f->x) { e.cp = ' '; return e; }
             pfail(P, RX_INVALID, "unrecognized escape sequence");
@@ -707,6 +852,10 @@ static int addthread(const rx_prog* p, sset* list, int* stack, int pc0, const ui
                     case AS_EOL: ok = pos == n || s[pos] == '\n'; break;
                     case AS_WB: ok = prev_w != next_w; break;
                     case AS_NWB: ok = prev_w == next_w; break;
+                    case AS_WS: ok = !prev_w && next_w; break;
+                    case AS_WE: ok = prev_w && !next_w; break;
+                    case AS_WSH: ok = !prev_w; break;
+                    case AS_WEH: ok = !next_w; break;
                 }
                 if (ok) stack[sp++] = in->x;
                 break;

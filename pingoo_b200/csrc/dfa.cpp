@@ -69,6 +69,10 @@ struct Builder {
                         case A_EOL_LINE: ok = next < 0 || next == '\n'; break;
                         case A_WORD_B: ok = prev_word != next_word; break;
                         case A_NOT_WORD_B: ok = prev_word == next_word; break;
+                        case A_WORD_START: ok = !prev_word && next_word; break;
+                        case A_WORD_END: ok = prev_word && !next_word; break;
+                        case A_WORD_START_HALF: ok = !prev_word; break;
+                        case A_WORD_END_HALF: ok = !next_word; break;
                     }
                     if (ok) stack.push_back(nd.out);
                     break;
@@ -97,7 +101,7 @@ bool build_dfa(const Nfa& nfa, const std::vector<int>& starts, int max_raw_state
         const NfaNode& nd = nfa.nodes[n];
         if (nd.kind == N_CHAR) used_sets.push_back(nd.set);
         if (nd.kind == N_ASSERT) {
-            if (nd.assert_kind == A_WORD_B || nd.assert_kind == A_NOT_WORD_B) B.use_word = true;
+            if (assert_looks_at_words(nd.assert_kind)) B.use_word = true;
             if (nd.assert_kind == A_BOL_LINE || nd.assert_kind == A_EOL_LINE) B.use_line = true;
             if (nd.assert_kind == A_BOL_TEXT || nd.assert_kind == A_BOL_LINE) B.use_bol = true;
         }

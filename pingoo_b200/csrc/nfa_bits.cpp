@@ -50,6 +50,10 @@ struct Closure {
                         case A_EOL_LINE: ok = at_end || next_nl; break;
                         case A_WORD_B: ok = prev_word != next_word; break;
                         case A_NOT_WORD_B: ok = prev_word == next_word; break;
+                        case A_WORD_START: ok = !prev_word && next_word; break;
+                        case A_WORD_END: ok = prev_word && !next_word; break;
+                        case A_WORD_START_HALF: ok = !prev_word; break;
+                        case A_WORD_END_HALF: ok = !next_word; break;
                     }
                     if (ok) stack.push_back(nd.out);
                     break;
@@ -89,7 +93,7 @@ bool build_bitset_unit(const Nfa& nfa, const std::vector<int>& starts, const std
             const NfaNode& nd = nfa.nodes[n];
             if (nd.kind == N_CHAR) { pos_of_node[n] = (int)node_of_pos.size(); node_of_pos.push_back(n); }
             if (nd.kind == N_ASSERT) {
-                if (nd.assert_kind == A_WORD_B || nd.assert_kind == A_NOT_WORD_B) use_word = true;
+                if (assert_looks_at_words(nd.assert_kind)) use_word = true;
                 if (nd.assert_kind == A_BOL_LINE || nd.assert_kind == A_EOL_LINE) use_line = true;
             }
             if (nd.kind == N_MATCH) {

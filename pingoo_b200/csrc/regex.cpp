@@ -1,6 +1,7 @@
 // Rust-`regex` syntax subset -> AST -> Thompson NFA (see regex.hpp).
 #include "regex.hpp"
 
+#include <cctype>
 #include <cstring>
 #include <functional>
 
@@ -34,6 +35,105 @@ struct ParseFail {
 
 static bool is_word_byte(unsigned c) {
     return (c >= '0' && c <= '9') || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || c == '_';
+}
+
+// ---- Unicode properties (\p{..}) on ASCII haystacks (SEMANTICS.md A9) ------------------------------------------------------
+// Rust `regex` is Unicode-aware by default; with request strings that are ASCII, a property class is its ASCII members
+// (bytes >= 0x80 stay one opaque character that only negated classes match).  General category of every ASCII code point
+// (UnicodeData.txt, stable since Unicode 1.1), then the property names regex-syntax accepts (loose matching: case, spaces,
+// '-' and '_' are ignored) mapped to sets of categories; scripts: Latin = the letters, Common = every other ASCII code point,
+// any other known script has no ASCII member.
+enum Gc : uint32_t { GC_Cc = 1u << 0, GC_Zs = 1u << 1, GC_Po = 1u << 2, GC_Sc = 1u << 3, GC_Ps = 1u << 4, GC_Pe = 1u << 5, GC_Sm = 1u << 6,
+                     GC_Pd = 1u << 7, GC_Nd = 1u << 8, GC_Lu = 1u << 9, GC_Ll = 1u << 10, GC_Sk = 1u << 11, GC_Pc = 1u << 12 };
+static uint32_t ascii_gc(unsigned c) {
+    if (c < 0x20 || c == 0x7F) return GC_Cc;
+    if (c == ' ') return GC_Zs;
+    if (c >= '0' && c <= '9') return GC_Nd;
+    if (c >= 'A' && c <= 'Z') return GC_Lu;
+    if (c >= 'a' && c <= 'z') return GC_Ll;
+    switch (c) {
+        case '$': return GC_Sc;
+        case '(': case '[': case '{': return GC_Ps;
+        case ')': case ']': case '}': return GC_Pe;
+        case '+': case '<': case '=': case '>': case '|': case '~': return GC_Sm;
+        case '-': return GC_Pd;
+        case '^': case '`': return GC_Sk;
+        case '_': return GC_Pc;
+        default: return GC_Po;   // ! " # % & ' * , . / : ; ? @ backslash
+    }
+}
+struct PropName { const char* name; uint32_t gcs; };
+static const PropName kGcNames[] = {
+    {"l", GC_Lu | GC_Ll}, {"letter", GC_Lu | GC_Ll}, {"lu", GC_Lu}, {"uppercaseletter", GC_Lu}, {"ll", GC_Ll}, {"lowercaseletter", GC_Ll},
+    {"lc", GC_Lu | GC_Ll}, {"casedletter", GC_Lu | GC_Ll}, {"lt", 0}, {"titlecaseletter", 0}, {"lm", 0}, {"modifierletter", 0}, {"lo", 0}, {"otherletter", 0},
+    {"m", 0}, {"mark", 0}, {"combiningmark", 0}, {"mn", 0}, {"nonspacingmark", 0}, {"mc", 0}, {"spacingmark", 0}, {"me", 0}, {"enclosingmark", 0},
+    {"n", GC_Nd}, {"number", GC_Nd}, {"nd", GC_Nd}, {"decimalnumber", GC_Nd}, {"digit", GC_Nd}, {"nl", 0}, {"letternumber", 0}, {"no", 0}, {"othernumber", 0},
+    {"p", GC_Pc | GC_Pd | GC_Ps | GC_Pe | GC_Po}, {"punctuation", GC_Pc | GC_Pd | GC_Ps | GC_Pe | GC_Po}, {"punct", GC_Pc | GC_Pd | GC_Ps | GC_Pe | GC_Po},
+    {"pc", GC_Pc}, {"connectorpunctuation", GC_Pc}, {"pd", GC_Pd}, {"dashpunctuation", GC_Pd}, {"ps", GC_Ps}, {"openpunctuation", GC_Ps},
+    {"pe", GC_Pe}, {"closepunctuation", GC_Pe}, {"pi", 0}, {"initialpunctuation", 0}, {"pf", 0}, {"finalpunctuation", 0}, {"po", GC_Po}, {"otherpunctuation", GC_Po},
+    {"s", GC_Sm | GC_Sc | GC_Sk}, {"symbol", GC_Sm | GC_Sc | GC_Sk}, {"sm", GC_Sm}, {"mathsymbol", GC_Sm}, {"sc", GC_Sc}, {"currencysymbol", GC_Sc},
+    {"sk", GC_Sk}, {"modifiersymbol", GC_Sk}, {"so", 0}, {"othersymbol", 0},
+    {"z", GC_Zs}, {"separator", GC_Zs}, {"zs", GC_Zs}, {"spaceseparator", GC_Zs}, {"zl", 0}, {"lineseparator", 0}, {"zp", 0}, {"paragraphseparator", 0},
+    {"c", GC_Cc}, {"other", GC_Cc}, {"cc", GC_Cc}, {"control", GC_Cc}, {"cntrl", GC_Cc}, {"cf", 0}, {"format", 0}, {"cs", 0}, {"surrogate", 0},
+    {"co", 0}, {"privateuse", 0}, {"cn", 0}, {"unassigned", 0},
+};
+static const char* const kOtherScripts[] = {   // known scripts without an ASCII member (long and ISO 15924 names)
+    "greek", "grek", "cyrillic", "cyrl", "han", "hani", "arabic", "arab", "hebrew", "hebr", "hiragana", "hira", "katakana", "kana", "thai", "devanagari", "deva",
+    "hangul", "hang", "armenian", "armn", "georgian", "geor", "ethiopic", "ethi", "bengali", "beng", "tamil", "taml", "telugu", "telu", "gujarati", "gujr",
+    "gurmukhi", "guru", "kannada", "knda", "malayalam", "mlym", "sinhala", "sinh", "khmer", "khmr", "lao", "laoo", "tibetan", "tibt", "myanmar", "mymr",
+    "mongolian", "mong", "syriac", "syrc", "thaana", "thaa", "coptic", "copt", "cherokee", "cher", "bopomofo", "bopo", "braille", "brai", "inherited", "zinh",
+    "zinh", "qaai",
+};
+// 0: ok, 1: not a name this engine knows (loud), 2: malformed
+static int unicode_property_ascii(const std::string& raw, ByteSet* out, bool* negated) {
+    std::string key, val;
+    bool have_key = false, neg = false;
+    auto norm = [](const std::string& t) {
+        std::string r;
+        for (char ch : t)
+            if (ch != ' ' && ch != '_' && ch != '-') r.push_back((char)std::tolower((unsigned char)ch));
+        return r;
+    };
+    std::string body = raw;
+    if (!body.empty() && body[0] == '^') { neg = true; body.erase(0, 1); }
+    size_t eq = body.find_first_of("=:");
+    if (eq != std::string::npos) {
+        have_key = true;
+        size_t kend = eq;
+        if (body[eq] == '=' && eq > 0 && body[eq - 1] == '!') { neg = !neg; kend = eq - 1; }
+        key = norm(body.substr(0, kend));
+        val = norm(body.substr(eq + 1));
+    } else val = norm(body);
+    if (val.empty()) return 2;
+    ByteSet s;
+    auto by_gc = [&](uint32_t gcs) { for (unsigned c = 0; c < 128; ++c) if (ascii_gc(c) & gcs) s.set(c); };
+    auto script = [&](const std::string& v) -> bool {
+        if (v == "latin" || v == "latn") { by_gc(GC_Lu | GC_Ll); return true; }
+        if (v == "common" || v == "zyyy") { by_gc(~(uint32_t)(GC_Lu | GC_Ll)); return true; }
+        for (const char* o : kOtherScripts) if (v == o) return true;
+        return false;
+    };
+    auto gc = [&](const std::string& v) -> bool {
+        for (const PropName& pn : kGcNames) if (v == pn.name) { by_gc(pn.gcs); return true; }
+        return false;
+    };
+    bool ok = false;
+    if (have_key) {
+        if (key == "gc" || key == "generalcategory") ok = gc(val);
+        else if (key == "sc" || key == "script" || key == "scx" || key == "scriptextensions") ok = script(val);
+        else return 1;
+    } else if (val == "any") { s.negate(); ok = true; }   // every code point, the opaque one included
+    else if (val == "ascii" || val == "assigned") { s.set_range(0, 127); ok = true; if (val == "assigned") { for (unsigned c = 128; c < 256; ++c) s.set(c); } }
+    else if (val == "alphabetic" || val == "alpha" || val == "cased") { by_gc(GC_Lu | GC_Ll); ok = true; }
+    else if (val == "uppercase" || val == "upper") { by_gc(GC_Lu); ok = true; }
+    else if (val == "lowercase" || val == "lower") { by_gc(GC_Ll); ok = true; }
+    else if (val == "whitespace" || val == "wspace" || val == "space") { s.set(' '); s.set_range(9, 13); ok = true; }
+    else if (val == "hexdigit" || val == "hex" || val == "asciihexdigit" || val == "ahex") { s.set_range('0', '9'); s.set_range('A', 'F'); s.set_range('a', 'f'); ok = true; }
+    else ok = gc(val) || script(val);
+    if (!ok) return 1;
+    *out = s;
+    *negated = neg;   // the caller folds case first and negates afterwards, as regex-syntax does (hir/translate.rs unicode_fold_and_negate)
+    return 0;
 }
 
 static ByteSet perl_class(char k) {
@@ -102,7 +202,7 @@ class Parser {
     int mk_assert(AssertKind a) {
         int n = mk(Ast::ASSERT);
         pool_[n].ak = a;
-        if (a == A_WORD_B || a == A_NOT_WORD_B) info_->uses_word_boundary = true;
+        if (assert_looks_at_words(a)) info_->uses_word_boundary = true;
         if (a == A_BOL_LINE || a == A_EOL_LINE) info_->uses_multiline = true;
         if (a == A_BOL_TEXT || a == A_BOL_LINE) info_->uses_bol = true;
         return n;
@@ -297,7 +397,28 @@ class Parser {
             case 'f': e.cp = 0x0C; return e;
             case 'v': e.cp = 0x0B; return e;
             case 'x': case 'u': case 'U': e.cp = parse_hex(c); return e;
-            case 'p': case 'P': fail(RX_UNSUPPORTED, "Unicode classes (\\p) are not supported");
+            case 'p': case 'P': {
+                // \pL, \p{Letter}, \p{^L}, \p{gc=Lu}, \p{sc:Latin}, \P{..} (regex-syntax ast/parse.rs parse_unicode_class)
+                if (eof()) fail(RX_INVALID, "incomplete Unicode class");
+                std::string name;
+                if (peek() == '{') {
+                    const size_t close = p_.find('}', pos_);
+                    if (close == std::string::npos) fail(RX_INVALID, "unclosed Unicode class");
+                    name = p_.substr(pos_ + 1, close - pos_ - 1);
+                    pos_ = close + 1;
+                } else {
+                    name = std::string(1, (char)peek());
+                    ++pos_;
+                }
+                bool neg = false;
+                const int rc = unicode_property_ascii(name, &e.set, &neg);
+                if (rc == 2) fail(RX_INVALID, "malformed Unicode class");
+                if (rc == 1) fail(RX_UNSUPPORTED, "Unicode property \\p{" + name + "} is not one this engine knows");
+                if (f.i) fold_case(e.set);            // `(?i)\p{Lu}` matches `a`; folding comes BEFORE negation
+                if (neg != (c == 'P')) e.set.negate();
+                e.kind = Esc::CLASS;
+                return e;
+            }
             case 'A':
                 if (in_class) fail(RX_INVALID, "unrecognized escape sequence in class");
                 e.kind = Esc::ASSERTION; e.ak = A_BOL_TEXT; return e;
@@ -306,16 +427,31 @@ class Parser {
                 e.kind = Esc::ASSERTION; e.ak = A_EOL_TEXT; return e;
             case 'b':
                 if (in_class) fail(RX_INVALID, "unrecognized escape sequence in class");
+                e.kind = Esc::ASSERTION; e.ak = A_WORD_B;
                 if (!eof() && peek() == '{') {
-                    // \b{start}, \b{end}, ... (regex >= 1.10); a literal `\b{` repetition is invalid anyway
-                    fail(RX_UNSUPPORTED, "\\b{...} word-boundary forms are not supported");
+                    // \b{start}, \b{end}, \b{start-half}, \b{end-half} (regex >= 1.10, regex-syntax ast/parse.rs
+                    // maybe_parse_special_word_boundary): a name of letters and '-' between the braces; anything that does not
+                    // start like a name is a counted repetition of a plain \b, which this engine leaves alone (loudly)
+                    size_t q = pos_ + 1;
+                    auto namech = [&](size_t i) { return i < p_.size() && (std::isalpha((unsigned char)p_[i]) || p_[i] == '-'); };
+                    if (!namech(q)) fail(RX_UNSUPPORTED, "a counted repetition of \\b is not supported");
+                    while (namech(q)) ++q;
+                    if (q >= p_.size() || p_[q] != '}') fail(RX_INVALID, "special word boundary assertion is either unclosed or contains an invalid character");
+                    const std::string name = p_.substr(pos_ + 1, q - pos_ - 1);
+                    if (name == "start") e.ak = A_WORD_START;
+                    else if (name == "end") e.ak = A_WORD_END;
+                    else if (name == "start-half") e.ak = A_WORD_START_HALF;
+                    else if (name == "end-half") e.ak = A_WORD_END_HALF;
+                    else fail(RX_INVALID, "unrecognized special word boundary assertion");
+                    pos_ = q + 1;
                 }
-                e.kind = Esc::ASSERTION; e.ak = A_WORD_B; return e;
+                return e;
             case 'B':
                 if (in_class) fail(RX_INVALID, "unrecognized escape sequence in class");
                 e.kind = Esc::ASSERTION; e.ak = A_NOT_WORD_B; return e;
             case '<': case '>':
-                fail(RX_UNSUPPORTED, "\\< and \\> word boundaries are not supported");
+                if (in_class) fail(RX_INVALID, "unrecognized escape sequence in class");   // an assertion, as \b is (regex >= 1.10)
+                e.kind = Esc::ASSERTION; e.ak = c == '<' ? A_WORD_START : A_WORD_END; return e;
             case ' ':
                 if (f.x) { e.cp = ' '; return e; }
                 fail(RX_INVALID, "unrecognized escape sequence");
@@ -580,7 +716,8 @@ class Parser {
                 Esc e = parse_escape(false, f);
                 if (e.kind == Esc::ASSERTION) return mk_assert(e.ak);
                 if (e.kind == Esc::CLASS) {
-                    // Perl classes are not affected by (?i) (already case-closed); keep bytes >= 0x80 of negations
+                    // Perl classes are not affected by (?i) (already case-closed; \p classes were folded by parse_escape); keep
+                    // bytes >= 0x80 of negations
                     int n = mk(Ast::SET);
                     pool_[n].set = e.set;
                     return n;

@@ -32,8 +32,13 @@ enum AssertKind : uint8_t {
     A_BOL_LINE = 2,   // ^ with (?m)
     A_EOL_LINE = 3,   // $ with (?m)
     A_WORD_B = 4,     // \b
-    A_NOT_WORD_B = 5  // \B
+    A_NOT_WORD_B = 5, // \B
+    A_WORD_START = 6,       // \b{start}, \<      : no word byte before, a word byte after
+    A_WORD_END = 7,         // \b{end}, \>        : a word byte before, no word byte after
+    A_WORD_START_HALF = 8,  // \b{start-half}     : no word byte before
+    A_WORD_END_HALF = 9     // \b{end-half}       : no word byte after
 };
+inline bool assert_looks_at_words(int a) { return a >= A_WORD_B && a <= A_WORD_END_HALF; }
 
 enum NfaKind : uint8_t { N_CHAR, N_SPLIT, N_ASSERT, N_MATCH, N_JUMP };
 

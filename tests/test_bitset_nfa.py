@@ -117,6 +117,27 @@ def test_gap_split_and_complement_patterns_through_the_bitset_unit():
     assert len(set(want.tolist())) > 6
 
 
+def test_special_word_boundaries_on_both_kinds_of_unit():
+    """\\b{start}, \\b{end}, their halves and \\< \\> (regex 1.10): same verdicts from the DFA units and from the bitset unit."""
+    rules = [Rule("ws", 'http_request.url.matches("\\\\b{start}cat")', [Action.BLOCK]),
+             Rule("we", 'http_request.url.matches("dog\\\\b{end}")', [Action.CAPTCHA]),
+             Rule("angle", 'http_request.url.matches("\\\\<a[ab]{2}\\\\>")', [Action.BLOCK]),
+             Rule("half", 'http_request.url.matches("\\\\b{start-half}=[ab]+\\\\b{end-half}")', [Action.CAPTCHA, Action.BLOCK]),
+             Rule("both", 'http_request.user_agent.matches("(?i)\\\\b{start}bot\\\\b{end}")', [Action.BLOCK])]
+    rng = random.Random(3)
+    words = ["cat", "dog", "concat", "dogs", "aab", "abb", "xaab", "=ab", "=a", "a=b", " ", "-", "_", ".", "bot", "Bot", "robot", "bots", "\n"]
+    reqs = []
+    for i in range(4000):
+        url = "".join(rng.choice(words) for _ in range(rng.randint(0, 6)))
+        ua = "Mozilla/5.0 " + "".join(rng.choice(words[10:18]) for _ in range(rng.randint(0, 4)))
+        reqs.append(dict(host="h", url=url, path="/p", method="GET", user_agent=ua, ip="1.2.3.4", remote_port=1, flags=i % 2))
+    batch = pack_requests(reqs)
+    _, want = _sim_check(rules, batch)
+    assert len(set((want >> 2).tolist())) >= 6
+    sim, _ = _sim_check(rules, batch, max_dfa_states=1, candidate_gate=False)
+    assert sim.describe().count("bitset-nfa") >= 5
+
+
 def test_position_limit_is_reported():
     rules = [Rule("huge", 'http_request.url.matches("a[ab]{2100}c")', [Action.BLOCK])]
     with pytest.raises(ValueError) as ei:
@@ -154,15 +175,15 @@ def test_gpu_exploding_patterns():
 @pytest.mark.gpu
 def test_gpu_tables_larger_than_shared_memory():
     """1 202 positions: 38 state words per request and 180 KB of follow rows -- read from global memory, state in local memory."""
-    rules = [Rule("huge", 'http_request.url.matches("q[ab]{1200}z")', [Action.BLOCK]),
+    rules = [Rule("huge", 'http_request.url.matches("a[ab]{1200}z")', [Action.BLOCK]),
              Rule("k15", 'http_request.url.matches("a[ab]{15}c")', [Action.CAPTCHA])]
     rng = random.Random(11)
     reqs = []
     for i in range(600):
         n = rng.choice([1199, 1200, 1200, 1201, 50, 0])
-        url = rng.choice(["", "q", "zq"]) + "q" + "".join(rng.choice("ab") for _ in range(n)) + rng.choice(["z", "", "qz", "c"])
+        url = rng.choice(["", "q", "zb"]) + "a" + "".join(rng.choice("ab") for _ in range(n)) + rng.choice(["z", "", "qz", "c"])
         reqs.append(dict(host="h", url=url, path="/p", method="GET", user_agent="Mozilla/5.0", ip="10.0.0.1", remote_port=1, flags=0))
-    eng, want = _gpu_check(rules, pack_requests(reqs))
+    eng, want = _gpu_check(rules, pack_requests(reqs), max_dfa_states=256)   # (a small cap only shortens the doomed DFA attempt)
     assert "positions=1202" in eng.describe()
     hist = np.bincount(want & 3, minlength=4)
     assert hist[1] > 50 and hist[0] > 50, hist

@@ -158,6 +158,18 @@ def random_pattern(rng, depth=0):
             atom = rng.choice(["\\b", "\\B"])
             parts.append(atom)
             continue
+        elif r < 0.24:
+            # Unicode properties: on ASCII haystacks the `regex` module (full Unicode tables) is the independent reference
+            atom = rng.choice(["\\p{L}", "\\pL", "\\p{Lu}", "\\p{Ll}", "\\p{N}", "\\p{Nd}", "\\p{P}", "\\p{Po}", "\\p{Pd}", "\\p{Pc}", "\\p{S}", "\\p{Sm}", "\\p{Z}",
+                               "\\P{L}", "\\P{N}", "\\PL", "\\p{^Lu}", "\\p{Latin}", "\\p{Greek}", "\\P{Greek}", "\\p{Common}", "\\p{Alphabetic}", "\\p{White_Space}",
+                               "\\p{Uppercase}", "\\p{Cc}", "[\\p{Lu}\\d]", "[^\\p{L}_]", "\\p{gc=Ll}", "\\p{sc=Latin}"])
+            parts.append(atom + rng.choice(QUANT))
+            continue
+        elif r < 0.28:
+            # the special word boundaries of regex >= 1.10
+            atom = rng.choice(["\\b{start}", "\\b{end}", "\\b{start-half}", "\\b{end-half}", "\\<", "\\>"])
+            parts.append(atom)
+            continue
         else:
             atom = rng.choice(ATOMS)
         parts.append(atom + rng.choice(QUANT))
@@ -187,8 +199,16 @@ def to_python(p):
     while i < len(p):
         c = p[i]
         if c == "\\":
-            out.append(p[i:i + 2])
-            i += 2
+            # \b{start} = \< and \b{end} = \>: the `regex` module spells them \m and \M; the half forms are look-arounds
+            for rust, py in (("\\b{start-half}", "(?<![0-9A-Za-z_])"), ("\\b{end-half}", "(?![0-9A-Za-z_])"), ("\\b{start}", "\\m"),
+                             ("\\b{end}", "\\M"), ("\\<", "\\m"), ("\\>", "\\M")):
+                if p.startswith(rust, i) and not in_class:
+                    out.append(py)
+                    i += len(rust)
+                    break
+            else:
+                out.append(p[i:i + 2])
+                i += 2
             continue
         if c == "[":
             in_class = True
@@ -259,9 +279,17 @@ REGEX_KAT = [
     ("[a&&b]", "a", 0), ("[a-z&&[^b]]", "b", 0), ("[a-z--b]", "c", 1), ("\\x{41}", "A", 1), ("\\u0041", "A", 1), ("é", "cafe", 0),
     ("[^é]", "e", 1), ("(?P<n>a)(?<m>b)", "ab", 1), ("a|", "zzz", 1), ("(|a)b", "b", 1), ("[]a]", "]", 1), ("[^]a]", "]", 0), ("[a-]", "-", 1),
     ("\\$\\{jndi:(ldap|rmi|dns)://", "${jndi:ldap://x}", 1), ("}", "}", 1), ("]", "]", 1),
+    # Unicode properties on ASCII text
+    ("\\p{Lu}\\p{Ll}+", "xx Abc", 1), ("^\\P{L}+$", "12-34", 1), ("^\\P{L}+$", "12a34", 0), ("(?i)\\p{Lu}", "a", 1), ("(?i)\\p{^Lu}", "a", 0), ("(?i)\\P{Lu}", "A", 0), ("(?i)\\P{^Lu}", "a", 1), ("\\p{Greek}", "abc xyz", 0),
+    ("\\p{Sc}\\p{Nd}", "cost $5", 1), ("\\p{Ps}\\p{Pe}", "f()", 1), ("\\p{ Script = Latin }", "1a", 1), ("\\p{gc!=L}", "a", 0), ("\\p{Any}", "", 0),
+    # special word boundaries (regex 1.10): start / end of a word, and their one-sided halves
+    ("\\b{start}cat", "a cat", 1), ("\\b{start}cat", "concat", 0), ("cat\\b{end}", "cat!", 1), ("cat\\b{end}", "cats", 0),
+    ("\\<cat\\>", "a cat.", 1), ("\\<cat\\>", "cat", 1), ("\\<cat\\>", "xcat", 0), ("\\b{start}", "", 0), ("\\b{end}", "!", 0),
+    ("\\b{start-half}!", "a !", 1), ("\\b{start-half}!", "a!", 0), ("\\b{start-half}", "", 1), ("!\\b{end-half}", "!a", 0), ("!\\b{end-half}", "! a", 1),
+    ("a\\b{end-half}$", "ba", 1), ("\\b{end}\\b{start}", "ab", 0), ("\\b{start-half}\\b{end-half}", "a b", 0), ("\\b{start-half}\\b{end-half}", "a  b", 1),
 ]
 REGEX_BAD = [("(", -1), (")", -1), ("a{", -1), ("{", -1), ("*a", -1), ("a{,2}", -1), ("a{2,1}", -1), ("[a", -1), ("[]", -1), ("\\1", -1), ("\\Z", -1),
-             ("(?=a)", -1), ("(?<!a)b", -1), ("(?P=n)", -1), ("\\8", -1), ("\\q", -1), ("[z-a]", -1), ("(?y)a", -1), ("\\pL", -2), ("\\b{start}", -2),
+             ("(?=a)", -1), ("(?<!a)b", -1), ("(?P=n)", -1), ("\\8", -1), ("\\q", -1), ("[z-a]", -1), ("(?y)a", -1), ("\\p{Klingon}", -2), ("\\p{", -1), ("\\p{}", -1), ("\\b{2}", -2), ("\\b{foo}", -1), ("\\b{start", -1), ("\\b{st art}", -1), ("[\\<]", -1),
              ("(?R)a", -2), ("(a{1000}){1000}", -3)]
 
 
