@@ -201,11 +201,19 @@ __device__ __noinline__ bool int_expr_eval(const KParams& p, uint32_t off, uint3
     return true;
 }
 
-// FIELD_CMP: one http_request field against another (0 ==, 1 starts_with, 2 ends_with, 3 contains)
+// FIELD_CMP: one http_request field against another (0 ==, 1 starts_with, 2 ends_with, 3 contains, 4 <, 5 <=, 6 >, 7 >=)
 __device__ __noinline__ bool field_cmp_eval(const KParams& p, uint32_t f1, uint32_t f2, uint32_t op, uint32_t r) {
     const uint32_t s1 = p.off[f1][r], n1 = p.off[f1][r + 1] - s1, s2 = p.off[f2][r], n2 = p.off[f2][r + 1] - s2;
     const uint8_t* a = p.col[f1] + s1;
     const uint8_t* b = p.col[f2] + s2;
+    if (op >= 4u) {
+        // byte-wise lexicographic order (Rust str::cmp): the first differing byte decides, else the shorter string is smaller
+        const uint32_t m = n1 < n2 ? n1 : n2;
+        int c = 0;
+        for (uint32_t i = 0; i < m && c == 0; ++i) c = (int)__ldg(a + i) - (int)__ldg(b + i);
+        if (c == 0) c = n1 < n2 ? -1 : n1 > n2 ? 1 : 0;
+        return op == 4u ? c < 0 : op == 5u ? c <= 0 : op == 6u ? c > 0 : c >= 0;
+    }
     if (op == 0u && n1 != n2) return false;
     if (n2 > n1) return false;
     auto same = [&](uint32_t at) {

@@ -393,7 +393,7 @@ struct Lowerer {
         return boolean(t, er);
     }
 
-    // one http_request field against another: 0 ==, 1 starts_with, 2 ends_with, 3 contains
+    // one http_request field against another: 0 ==, 1 starts_with, 2 ends_with, 3 contains, 4 <, 5 <=, 6 >, 7 >= (byte-wise order)
     Sym field_cmp_atom(int f1, int f2, int op) {
         AtomDesc d;
         d.kind = AtomDesc::FIELD_CMP;
@@ -592,7 +592,9 @@ struct Lowerer {
                 for (auto& k : e.kids) {
                     Sym it = lower(*k);
                     if (it.k == Sym::ERR) return err();
-                    if (!is_const(it)) unsupported(e, "list literal containing request variables");
+                    // request variables may be elements: [http_request.method, "x"].contains("GET"), [..][0], .length() work on such a
+                    // list; what cannot (whole-list comparison) says so where it is attempted
+                    if (it.k == Sym::CHOICE) unsupported(e, "conditional (?:) value as a list element");
                     l.items.push_back(std::move(it));
                 }
                 return l;
@@ -800,8 +802,18 @@ struct Lowerer {
             }
             if (recv.k == Sym::MAP_LISTS || recv.k == Sym::MAP_HTTP || recv.k == Sym::MAP_CLIENT || recv.k == Sym::MAP_C) {
                 if (fn != "contains") return err();
+                if (a.k == Sym::STR_FIELD || a.k == Sym::COUNTRY_VAR) {
+                    // key presence with a request string: membership in the (constant) key set
+                    std::vector<std::string> keys;
+                    if (recv.k == Sym::MAP_HTTP) for (int f = 0; f < N_FIELDS; ++f) keys.push_back(kFieldNames[f]);
+                    else if (recv.k == Sym::MAP_CLIENT) keys = {"ip", "remote_port", "asn", "country"};
+                    else if (recv.k == Sym::MAP_LISTS) for (auto& kv : M.lists) keys.push_back(kv.first);
+                    else for (size_t k = 0; k + 1 < recv.items.size(); k += 2) if (recv.items[k].k == Sym::STR_C) keys.push_back(recv.items[k].s);
+                    if (a.k == Sym::COUNTRY_VAR) return country_atom([&](const std::string& code) { return std::find(keys.begin(), keys.end(), code) != keys.end(); });
+                    return str_set_atom(e, a.field, keys);
+                }
                 if (a.k != Sym::STR_C) {
-                    if (!is_const(a)) unsupported(e, "map.contains() with a request variable");
+                    if (!is_const(a)) return const_bool(false);   // an integer / address value is never a key
                     return const_bool(false);
                 }
                 return const_bool(member(recv, a.s).k != Sym::ERR);
@@ -825,7 +837,22 @@ struct Lowerer {
                     bool r = str_pred(recv.s, a.s, &er);
                     return er ? err() : const_bool(r);
                 }
-                if (a.k == Sym::STR_FIELD || a.k == Sym::COUNTRY_VAR) unsupported(e, "constant." + fn + "(request variable)");
+                if (a.k == Sym::STR_FIELD || a.k == Sym::COUNTRY_VAR) {
+                    // "GET POST".contains(http_request.method): the variable must be one of the constant's substrings / prefixes /
+                    // suffixes -- a finite set of strings, i.e. a membership test (the empty string is a member of all three)
+                    if (fn == "matches") unsupported(e, "matches() with a variable pattern");
+                    const std::string& c = recv.s;
+                    if (a.k == Sym::COUNTRY_VAR) {
+                        bool er;
+                        return country_atom([&](const std::string& code) { return str_pred(c, code, &er); });
+                    }
+                    if (fn == "contains" && c.size() > 96) unsupported(e, "constant.contains(request variable) on a constant longer than 96 bytes");
+                    std::vector<std::string> set(1, std::string());
+                    if (fn == "starts_with") for (size_t n = 1; n <= c.size(); ++n) set.push_back(c.substr(0, n));
+                    else if (fn == "ends_with") for (size_t n = 1; n <= c.size(); ++n) set.push_back(c.substr(c.size() - n));
+                    else for (size_t i = 0; i < c.size(); ++i) for (size_t n = 1; i + n <= c.size(); ++n) set.push_back(c.substr(i, n));
+                    return str_set_atom(e, a.field, set);
+                }
                 return err();
             }
             if (recv.k == Sym::STR_FIELD) {
@@ -859,6 +886,22 @@ struct Lowerer {
     }
 
     Sym list_contains(const Expr& e, const Sym& list, const Sym& x) {
+        if (list.k == Sym::LIST_C && !is_const(list)) {
+            // a list literal with request variables among its elements: one equality per element; an element of another type is
+            // simply not equal (SEMANTICS.md A2), errors can only come from evaluating the elements or the argument
+            if (x.k == Sym::CHOICE) unsupported(e, "conditional (?:) value looked up in a list of request variables");
+            int t = P.constant(false), er = P.constant(false);
+            for (const Sym& it : list.items) {
+                const bool it_int = is_int_value(it), x_int = is_int_value(x);
+                if ((it.k == Sym::INT_EXPR && prog_can_error(it.prog) && !x_int) || (x.k == Sym::INT_EXPR && prog_can_error(x.prog) && !it_int))
+                    unsupported(e, "list.contains() mixing a fallible integer expression with values of another type");
+                Sym c = (is_const(it) && is_const(x)) ? const_bool(const_equal(it, x) == 1) : compare(e, CMP_EQ, it, x);
+                if (c.k != Sym::BOOL) continue;
+                t = P.mk_or(t, c.bv.t);
+                er = P.mk_or(er, c.bv.e);
+            }
+            return boolean(P.mk_and(t, P.mk_not(er)), er);
+        }
         switch (x.k) {
             case Sym::IP_VAR:
                 if (list.k == Sym::LIST_REF && list.list->type == LT_IP) return ip_set_atom(list);
@@ -870,6 +913,20 @@ struct Lowerer {
             }
             case Sym::INT_FEAT: return int_set_atom(x.feat, list_ints(list));
             default: break;
+        }
+        if (x.k == Sym::INT_EXPR) {
+            // [80, 443].contains(client.remote_port + 1): one comparison of the expression per integer element; all of them
+            // share the expression's error condition.  (An empty or non-integer list still evaluates the expression: `x != x`
+            // is false and carries the error.)
+            const std::vector<int64_t> ints = list_ints(list);
+            if (ints.size() > 16) unsupported(e, "list.contains(<integer expression>) on a list with more than 16 integers");
+            if (ints.empty()) return int_expr_cmp(e, CMP_NE, x, x);
+            Sym acc = int_expr_cmp(e, CMP_EQ, x, const_int(ints[0]));
+            for (size_t k = 1; k < ints.size(); ++k) {
+                Sym c = int_expr_cmp(e, CMP_EQ, x, const_int(ints[k]));
+                acc = boolean(P.mk_or(acc.bv.t, c.bv.t), P.mk_or(acc.bv.e, c.bv.e));
+            }
+            return acc;
         }
         if (!is_const(x)) unsupported(e, "list.contains() of this value");
         if (list.k == Sym::LIST_C) {
@@ -933,7 +990,7 @@ struct Lowerer {
                 }
                 if (b.k == Sym::STR_FIELD) {
                     if (b.field == a.field) return const_bool(op == CMP_EQ || op == CMP_LE || op == CMP_GE);
-                    if (ordering) unsupported(e, "lexicographic ordering between two http_request fields");
+                    if (ordering) return field_cmp_atom(a.field, b.field, op == CMP_LT ? 4 : op == CMP_LE ? 5 : op == CMP_GT ? 6 : 7);   // byte-wise, as Rust's str::cmp
                     Sym eq = field_cmp_atom(a.field, b.field, 0);
                     return op == CMP_EQ ? eq : boolean(P.mk_not(eq.bv.t));
                 }
@@ -967,6 +1024,8 @@ struct Lowerer {
                 return err();
             case Sym::MAP_HTTP: case Sym::MAP_CLIENT: case Sym::MAP_LISTS:
                 unsupported(e, "comparison of whole maps");
+            case Sym::LIST_C:
+                unsupported(e, "comparison of a whole list that holds request variables");
             default: return err();
         }
     }

@@ -82,7 +82,7 @@ struct AtomDesc {
         IP_SET,        // client.ip contained in any network of a set
         COUNTRY_SET,   // client.country in a 26x26 bitmap
         INT_EXPR,      // comparison of two integer expressions over request variables (prog), or "the expression errors" (op 6)
-        FIELD_CMP      // one http_request field against another: op 0 ==, 1 starts_with, 2 ends_with, 3 contains (field, feat = second field)
+        FIELD_CMP      // one http_request field against another: op 0 ==, 1 starts_with, 2 ends_with, 3 contains, 4 <, 5 <=, 6 >, 7 >= (field, feat = second field)
     } kind;
     int field = -1;        // STR_PATTERN
     std::vector<int> nfa_starts;  // STR_PATTERN: start node(s) in Model::nfa[field]; pattern id of part k = event_base + k

@@ -103,7 +103,7 @@ struct NsAtom {
     uint32_t op;       // CmpOp
     int64_t cval;
     uint32_t set_id;   // int set / ip set bit / country set; INT_EXPR: offset of the program in the token array;
-                       // FIELD_CMP: the second field (feat = the first, op = 0 ==, 1 starts_with, 2 ends_with, 3 contains)
+                       // FIELD_CMP: the second field (feat = the first, op = 0 ==, 1 starts_with, 2 ends_with, 3 contains, 4 <, 5 <=, 6 >, 7 >=)
     uint32_t pad;
 };
 

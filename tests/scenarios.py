@@ -129,3 +129,36 @@ def services(n=20_000, catch_all=True):
         svcs.append(Service("shadowed", 'http_request.method == "GET"'))
     batch = synth.RequestStream(config_id=2, payloads=payloads, attack_rate=0.05).generate(7_000, n)
     return rules, lists, svcs, batch
+
+
+def value_constructs():
+    """Constructs whose operands swap the usual roles: a constant receiver with a request variable as argument, list literals that
+    hold request variables, integer expressions looked up in lists, byte-wise ordering between two fields."""
+    exprs = [
+        '"GET POST".contains(http_request.method)',
+        '"/admin/x".starts_with(http_request.path)',
+        '"example.com".ends_with(http_request.host)',
+        '"USFR".contains(client.country) && client.remote_port == 80',
+        '[80, 443].contains(client.remote_port + 1)',
+        'lists["ports"].contains(client.remote_port * 2 - 80)',
+        '[0].contains(client.remote_port / (client.remote_port - 442))',          # division by zero at port 442: an error, no match
+        '!([7].contains(100 / (client.remote_port - 443))) && client.remote_port > 441',   # the error wins over the negation
+        'http_request.path < http_request.url',
+        'http_request.path >= http_request.host',
+        'http_request.method <= http_request.host && http_request.method > http_request.path',
+        '[http_request.method, "x"].contains("PUT")',
+        '[http_request.method, client.remote_port, "GET"].contains(http_request.host)',
+        '[client.remote_port - 1, 79].contains(client.remote_port + 0)',
+        '[http_request.path, http_request.url][1] == "/adm"',
+        '[http_request.path, 5].length() == 2 && http_request.method == ""',
+        '{"GET": 1, "ET": 2}.contains(http_request.method) && client.remote_port == 79',
+        'http_request.contains(http_request.method)',
+        'lists.contains(http_request.host)',
+    ]
+    rules = [Rule(f"c{i}", ex, [Action.BLOCK if i % 3 else Action.CAPTCHA]) for i, ex in enumerate(exprs)]
+    reqs = [dict(host=h, url=u, path=p, method=m, user_agent="Mozilla/5.0", ip="1.2.3.4", remote_port=port, flags=(len(h) + port) % 2, country=c, asn=1)
+            for h in ["example.com", "com", "", "US", "a.example.com", "ports", "GET", "host"]
+            for (u, p) in [("/admin/x?y", "/admin/x"), ("/", ""), ("/adm", "/adm"), ("", ""), ("/zz/GET", "/zz")]
+            for m in ["GET", "POST", "PUT", "ET", "", "host", "zz"] for port in [79, 80, 442, 443] for c in ["US", "FR", "XX"]]
+    lists = {"ports": (ListType.Int, b"80\n443\n806\n")}
+    return rules, lists, pack_requests(reqs)

@@ -339,7 +339,12 @@ static int evaluate_range(Sim* s, const pgw_batch* b, uint32_t* out, uint16_t* s
                 const uint32_t s1 = cols[f1]->offsets[r], n1 = cols[f1]->offsets[r + 1] - s1, s2 = cols[f2]->offsets[r], n2 = cols[f2]->offsets[r + 1] - s2;
                 const uint8_t* x = cols[f1]->bytes + s1;
                 const uint8_t* y = cols[f2]->bytes + s2;
-                if (a.op == 0) v = n1 == n2 && memcmp(x, y, n1) == 0;
+                if (a.op >= 4) {
+                    const uint32_t m = n1 < n2 ? n1 : n2;
+                    int c = m ? memcmp(x, y, m) : 0;
+                    if (c == 0) c = n1 < n2 ? -1 : n1 > n2 ? 1 : 0;
+                    v = a.op == 4 ? c < 0 : a.op == 5 ? c <= 0 : a.op == 6 ? c > 0 : c >= 0;
+                } else if (a.op == 0) v = n1 == n2 && memcmp(x, y, n1) == 0;
                 else if (n2 > n1) v = false;
                 else if (a.op == 1) v = memcmp(x, y, n2) == 0;
                 else if (a.op == 2) v = memcmp(x + n1 - n2, y, n2) == 0;

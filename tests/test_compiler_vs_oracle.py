@@ -223,3 +223,13 @@ def test_lowered_field_comparisons_arithmetic_and_ordering():
         hist = np.bincount(want & 3, minlength=4)
         both += int(hist[0] > 0 and hist[0] < batch.n)
     assert both >= len(rule_sets) - 4   # nearly every expression is true for some requests and false for others
+
+
+def test_constant_receivers_dynamic_lists_and_field_ordering():
+    rules, lists, batch = scenarios.value_constructs()
+    _check(rules, batch, lists, eval_gates=False)
+    # one rule at a time as well (the first-match loop hides a rule behind earlier ones); every rule matches some requests, not all
+    for r in rules:
+        want = _check([r], batch, lists, eval_gates=False)
+        hits = int(np.count_nonzero(want & 3))
+        assert 0 < hits < batch.n, (r.expression, hits)

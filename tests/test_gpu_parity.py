@@ -302,3 +302,13 @@ def test_adversarial_input_for_the_gate():
         reqs.append(dict(host=base.field("host", i).decode(), url=url, path="/" + g.strip("/ <")[:8], method="GET",
                          user_agent=(g * 8)[:60] or "x", ip="10.1.%d.%d" % (i // 250, i % 250), remote_port=1000 + i))
     _check(rules, pack_requests(reqs))
+
+
+@pytest.mark.gpu
+def test_constant_receivers_dynamic_lists_and_field_ordering():
+    """`"GET POST".contains(method)`, list literals holding request variables, integer expressions looked up in lists and the
+    byte-wise ordering of two fields (FIELD_CMP ops 4-7 in the per-request kernel) -- tests/scenarios.py value_constructs."""
+    rules, lists, batch = scenarios.value_constructs()
+    _check(rules, batch, lists, eval_gates=False)
+    for r in rules[8:11]:   # the ordering predicates one at a time: nothing in front of them in the first-match loop
+        _check([r], batch, lists, eval_gates=False)
