@@ -9,7 +9,8 @@ from helpers import Oracle, Sim, fmt_verdict
 from pingoo_b200 import Action, ListType, Rule, Service, WafEngine, pack_requests
 
 WORDS = ["admin", "login", ".php", "select", "union", "/api", "wp-", "etc/passwd", "<script", "x", "", "a=b", "../", "%00", "curl", "bot", "Mozilla/"]
-REGEX = [r"(?i)union\s+select", r"\.(php|asp)$", r"^/api/v[0-9]+/", r"a+b", r"[0-9]{3,}", r"(?i)<script[^>]*>", r"\bcat\b", r"^$", r"x*", r"(", r"wp-(admin|login)", r"%[0-9a-fA-F]{2}"]
+REGEX = [r"(?i)union\s+select", r"\.(php|asp)$", r"^/api/v[0-9]+/", r"a+b", r"[0-9]{3,}", r"(?i)<script[^>]*>", r"\bcat\b", r"^$", r"x*", r"(", r"wp-(admin|login)", r"%[0-9a-fA-F]{2}",
+         r"\b{start}admin", r"\p{Lu}{3,}", r"\P{L}\p{Nd}+$", r"login\>"]
 FIELDS = ["host", "url", "path", "method", "user_agent"]
 HOSTS = ["example.com", "api.example.com", "evil.example", "", "h"]
 METHODS = ["GET", "POST", "PUT", "DELETE", ""]
@@ -22,7 +23,7 @@ def lit(rng):
 
 def predicate(rng):
     f = "http_request." + rng.choice(FIELDS)
-    k = rng.randrange(22)
+    k = rng.randrange(30)
     if k < 4:
         return f'{f}.contains({lit(rng)})'
     if k < 6:
@@ -50,6 +51,29 @@ def predicate(rng):
         return rng.choice(["true", "false", "1 == 1", '"a" < "b"', "1 + 1"])  # the last one is not a Bool
     if k == 20:
         return f'lists["names"].contains({lit(rng)})'
+    if k == 21:
+        return f'{f}.contains({lit(rng)}) == {rng.choice(["true", "false"])}'
+    g = "http_request." + rng.choice(FIELDS)
+    if k == 22:   # one field against another
+        return rng.choice([f'{f} == {g}', f'{f} != {g}', f'{f}.contains({g})', f'{f}.starts_with({g})', f'{f}.ends_with({g})', f'{f} < {g}', f'{f} >= {g}'])
+    if k == 23:   # integer arithmetic on request values, with its overflow / division errors
+        return rng.choice(['client.remote_port + 1 > http_request.url.length() * 2', 'client.remote_port / (client.asn - 7) == 0',
+                           'client.remote_port % 7 == client.asn % 7', '-client.remote_port < 0 - http_request.host.length()',
+                           'client.remote_port * 140737488355328 * 65536 > 0'])
+    if k == 24:   # a constant receiver, the request variable as argument
+        return rng.choice(['"GET POST".contains(http_request.method)', '"api.example.com".ends_with(http_request.host)', f'{lit(rng)}.starts_with({f})',
+                           '"FRDE".contains(client.country)', f'{lit(rng)}.contains({f})'])
+    if k == 25:   # list literals that hold request variables
+        return rng.choice([f'[{f}, "x"].contains({lit(rng)})', f'[{f}, client.remote_port, "GET"].contains({g})', '[client.remote_port + 1, 80].contains(client.asn)',
+                           f'[{f}, {g}][1] == {lit(rng)}', f'[{f}].length() == 1'])
+    if k == 26:   # integer expressions looked up in lists
+        return rng.choice(['lists["ports"].contains(client.remote_port + 363)', '[81, 444].contains(client.remote_port + 1)',
+                           '[0].contains(client.remote_port / (client.asn - 7))', 'lists["names"].contains(client.remote_port + 1)'])
+    if k == 27:   # key presence
+        return rng.choice([f'http_request.contains({f})', f'lists.contains({f})', f'{{"GET": 1, "admin": 2}}.contains({f})'])
+    if k == 28:   # conditional with non-boolean branches
+        return rng.choice([f'(client.remote_port > 100 ? {f} : {g}) == {lit(rng)}', f'(client.asn == 7 ? "GET" : "POST") == http_request.method',
+                           f'(client.remote_port == 80 ? 1 : client.asn) > 5'])
     return f'{f}.contains({lit(rng)}) == {rng.choice(["true", "false"])}'
 
 
@@ -72,7 +96,7 @@ def make_case(seed, n_rules=12, n_services=4, n_requests=300):
     rules = [Rule(f"r{i}", None if rng.random() < 0.03 else expr(rng, 3), rng.choice(acts)) for i in range(n_rules)]
     svcs = [Service(f"s{i}", None if rng.random() < 0.1 else expr(rng, 2)) for i in range(n_services)]
     lists = {"nets": (ListType.Ip, b"10.0.0.0/8\n192.168.1.7\n2001:db8::/32\n"), "ports": (ListType.Int, b"80\n443\n"),
-             "names": (ListType.String, b"evil.example\nadmin\n")}
+             "names": (ListType.String, b"evil.example\nadmin\n")}  # (ports + 363: 443 - 80)
     reqs = []
     for _ in range(n_requests):
         parts = [rng.choice(WORDS + ["/", "?q=", "123", "aab", " cat ", "UNION  SELECT", "%2e"]) for _ in range(rng.randrange(0, 6))]
