@@ -52,7 +52,8 @@ typedef struct pgw_rule_desc {
 } pgw_rule_desc;
 
 typedef struct pgw_options {
-    int32_t max_dfa_states;        /* per scan unit; 0 = default (16384) */
+    int32_t max_dfa_states;        /* per scan unit; 0 = default (16384); a pattern that needs more on its own is not refused:
+                                      it runs as a bit-parallel NFA (up to 2048 positions) over every request */
     uint64_t max_unit_table_bytes; /* per scan unit; 0 = default (8 MiB) */
     int32_t eval_gates;            /* 1 (default): evaluate the user-agent and captcha-path gates of
                                       http_listener.rs:196-204 inside the engine; 0: rules only */
@@ -99,6 +100,8 @@ typedef struct pgw_info {
     uint32_t gated_fields_mask;   /* fields in front of whose DFAs the candidate gate runs */
     uint32_t gate_grams;          /* 4-byte grams in the gate bitmaps, all fields */
     uint64_t gate_smem_bytes;     /* shared memory of the gate kernel (the level-1 bitmaps of all gated fields) */
+    uint32_t n_bitset_units;      /* patterns simulated as bit-parallel NFAs because no DFA unit can hold them */
+    uint32_t bitset_positions;    /* NFA positions of those units, all together */
 } pgw_info;
 
 /* rules::compile_expression(&str) -> Result<CompiledExpression, Error>   (rules/rules.rs:45-53) */

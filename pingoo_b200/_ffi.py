@@ -64,6 +64,7 @@ class Info(C.Structure):
         ("total_dfa_states", C.c_uint32), ("lpm_present", C.c_uint32), ("geoip_loaded", C.c_uint32),
         ("kernel_launches", C.c_uint64), ("last_h2d_bytes", C.c_uint64), ("last_d2h_bytes", C.c_uint64),
         ("gated_fields_mask", C.c_uint32), ("gate_grams", C.c_uint32), ("gate_smem_bytes", C.c_uint64),
+        ("n_bitset_units", C.c_uint32), ("bitset_positions", C.c_uint32),
     ]
 
 

@@ -373,6 +373,7 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
         gf.lit_cand = (const uint32_t*)chk(M.upload(H.gate[f].lit_cand));
         gf.lits = (const LitDesc*)chk(M.upload(H.gate[f].lits));
         gf.lit_bytes = (const uint8_t*)chk(M.upload(H.gate[f].lit_bytes));
+        if (H.gate[f].slot_words == 4) G.wide_slots = 1u;
         gf.k1 = H.gate[f].k1;
         gf.kt = H.gate[f].kt;
         gf.bloom_off = (uint32_t)bloom_used;
@@ -791,6 +792,8 @@ int pgw_ruleset_info(const pgw_ruleset* rs, pgw_info* out) {
     for (int f = 0; f < 5; ++f)
         if (H.gate[f].present) { out->gated_fields_mask |= 1u << f; out->gate_grams += H.gate[f].n_grams; }
     out->gate_smem_bytes = rs->gate_smem;
+    out->n_bitset_units = (uint32_t)H.bitset_units.size();
+    for (auto& b : H.bitset_units) out->bitset_positions += b.n_pos;
     out->lpm_present = H.lpm.present;
     out->geoip_loaded = H.lpm.geo_loaded;
     out->kernel_launches = rs->launches.load();

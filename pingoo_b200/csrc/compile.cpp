@@ -84,6 +84,7 @@ std::string HostProgram::summary() const {
         if (gate[f].present) {
             o << " gate(" << kFieldNames[f] << ": grams=" << gate[f].n_grams << " bloom=2^" << gate[f].k1 << " table=2^" << gate[f].kt;
             if (gate[f].lits.size() > 1 || gate[f].lits[0].len) o << " literals=" << gate[f].lits.size();
+            if (gate[f].slot_words == 4) o << " wide-slots";
             o << ")";
         }
     o << " ns_atoms=" << ns_atoms.size() << " lpm=" << (lpm.present ? 1 : 0);
@@ -376,6 +377,7 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
     // arena: all class maps first, then the tables
     struct Pending { Dfa dfa; int field; uint32_t mode; uint32_t gate_bit = 0; std::vector<int> latch_of_event; };
     std::vector<Pending> pend;
+    struct GateInput { bool present = false; std::vector<uint32_t> grams, masks; std::vector<GateLiteral> literals; } gate_in[N_FIELDS];
     for (int fo = 0; fo < N_FIELDS; ++fo) {
         int f = kFieldOrder[fo];
         const bool gate_field = opt.candidate_gate && (f == F_URL || f == F_USER_AGENT || f == F_PATH);
@@ -386,7 +388,48 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
         // atoms whose pattern is a small finite set of strings: confirmed by the gate's resolve kernel, no automaton (gate.hpp)
         std::vector<GateLiteral> literals;
         std::vector<uint32_t> literal_grams;   // distinct grams the literals put into the field's budget
-        std::map<uint32_t, uint32_t> literal_list_len;   // gram -> literals it announces so far
+        // What the gate knows about each atom of the field, computed once: the grams of its triggering parts (FIRE, and SET of a
+        // gap-split pattern: TEST needs an earlier SET, CLEAR never fires) and, if its language is a small finite set of strings,
+        // those strings with the grams that announce them.
+        struct Pre {
+            bool used = false, all_anch = true, all_gate = true, lit_ok = false;
+            std::vector<uint32_t> grams;       // gate_grams_for_pattern over the triggering parts
+            std::vector<LitString> strs;
+            std::vector<uint32_t> lit_grams;   // sorted, distinct
+        };
+        std::vector<Pre> pre(H.n_atoms);
+        std::map<uint32_t, uint32_t> gram_owners;   // gram -> atoms of this field that have it in either set
+        if (gate_field)
+            for (uint32_t a = 0; a < H.n_atoms; ++a) {
+                const AtomDesc& ad = M.atoms[a];
+                if (ad.kind != AtomDesc::STR_PATTERN || ad.field != f) continue;
+                if (ad.pos_refs + ad.neg_refs == 0 && (int)a != H.gate_bypass_atom) continue;
+                Pre& pr = pre[a];
+                pr.used = true;
+                for (size_t k = 0; k < ad.nfa_starts.size(); ++k) {
+                    const uint8_t kind = M.events[ad.event_base + k].kind;
+                    if (kind != EV_FIRE && kind != EV_SET) continue;
+                    if (!pattern_is_start_anchored(M.nfa[f], ad.nfa_starts[k])) pr.all_anch = false;
+                    if (pr.all_gate && !gate_grams_for_pattern(M.nfa[f], ad.nfa_starts[k], opt.gate_pattern_cap, &pr.grams)) pr.all_gate = false;
+                }
+                if (pr.all_anch) continue;   // early-exit class: the gate is not involved
+                if (opt.literal_confirm && ad.nfa_starts.size() == 1 && !ad.has_latch && M.events[ad.event_base].kind == EV_FIRE &&
+                    (int)a != H.gate_bypass_atom && gate_finite_language(M.nfa[f], ad.nfa_starts[0], &pr.strs)) {
+                    pr.lit_ok = true;
+                    for (const LitString& ls : pr.strs) {
+                        std::vector<std::pair<uint32_t, int>> pg;
+                        gate_grams_for_literal(ls, &pg);
+                        for (auto& x : pg) pr.lit_grams.push_back(x.first);
+                    }
+                    std::sort(pr.lit_grams.begin(), pr.lit_grams.end());
+                    pr.lit_grams.erase(std::unique(pr.lit_grams.begin(), pr.lit_grams.end()), pr.lit_grams.end());
+                }
+                std::vector<uint32_t> all = pr.lit_grams;
+                if (pr.all_gate) all.insert(all.end(), pr.grams.begin(), pr.grams.end());
+                std::sort(all.begin(), all.end());
+                all.erase(std::unique(all.begin(), all.end()), all.end());
+                for (uint32_t g : all) gram_owners[g]++;
+            }
         for (uint32_t a = 0; a < H.n_atoms; ++a)
             if (M.atoms[a].kind == AtomDesc::STR_PATTERN && M.atoms[a].field == f) {
                 // atoms no rule refers to any more (replaced by their complement) are not scanned
@@ -396,47 +439,26 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
                 b.has_latch = M.atoms[a].has_latch;
                 int cls = UC_FULL;
                 if (gate_field) {
-                    // the parts whose match can make the atom true: FIRE, and SET of a gap-split pattern (TEST needs an
-                    // earlier SET, CLEAR never fires)
-                    bool all_anch = true, all_gate = true;
-                    GatedGrams gg;
-                    for (size_t k = 0; k < b.starts.size(); ++k) {
-                        const uint8_t kind = M.events[M.atoms[a].event_base + k].kind;
-                        if (kind != EV_FIRE && kind != EV_SET) continue;
-                        if (!pattern_is_start_anchored(M.nfa[f], b.starts[k])) all_anch = false;
-                        if (all_gate && !gate_grams_for_pattern(M.nfa[f], b.starts[k], opt.gate_pattern_cap, &gg.grams)) all_gate = false;
-                    }
-                    if (all_anch) cls = UC_ANCH;
+                    Pre& pr = pre[a];
+                    if (pr.all_anch) cls = UC_ANCH;
                     else {
-                        std::vector<LitString> strs;
-                        if (opt.literal_confirm && b.starts.size() == 1 && !b.has_latch && M.events[M.atoms[a].event_base].kind == EV_FIRE &&
-                            (int)a != H.gate_bypass_atom && gate_finite_language(M.nfa[f], b.starts[0], &strs)) {
-                            std::vector<uint32_t> lg = literal_grams;
-                            // a gram announces at most kLitListCap literals: the resolve kernel compares them one after the other, so a
-                            // family of strings that share their first bytes (`sqlmap1`, `sqlmap2`, ...) is what a DFA is for
-                            std::map<uint32_t, uint32_t> add;
-                            for (const LitString& ls : strs) {
-                                std::vector<std::pair<uint32_t, int>> pg;
-                                gate_grams_for_literal(ls, &pg);
-                                std::sort(pg.begin(), pg.end());
-                                pg.erase(std::unique(pg.begin(), pg.end()), pg.end());
-                                for (auto& pr : pg) { lg.push_back(pr.first); add[pr.first]++; }
-                            }
-                            bool short_lists = true;
-                            for (auto& kv : add) {
-                                auto it = literal_list_len.find(kv.first);
-                                if ((it == literal_list_len.end() ? 0u : it->second) + kv.second > kLitListCap) { short_lists = false; break; }
-                            }
-                            std::sort(lg.begin(), lg.end());
-                            lg.erase(std::unique(lg.begin(), lg.end()), lg.end());
-                            if (short_lists && lg.size() <= opt.gate_field_cap / 2) {   // half of the field's gram budget at most
+                        // Literal confirmation pays when a window that carries one of the atom's grams costs ONE comparison and
+                        // nothing else (measured: a comparison in the resolve kernel costs about 2/3 of walking a candidate,
+                        // profiles/README.md): the atom's grams must be its own -- no other atom of the field, confirmed or walked by
+                        // a DFA, may share one.  Families of strings with a common prefix (`sqlmap1`, `sqlmap2`, ...) are what an
+                        // automaton is for and stay with the DFA units.
+                        bool exclusive = pr.lit_ok;
+                        for (size_t k = 0; exclusive && k < pr.lit_grams.size(); ++k) exclusive = gram_owners[pr.lit_grams[k]] == 1;
+                        if (exclusive) {
+                            std::vector<uint32_t> lg;
+                            std::set_union(literal_grams.begin(), literal_grams.end(), pr.lit_grams.begin(), pr.lit_grams.end(), std::back_inserter(lg));
+                            if (lg.size() <= opt.gate_field_cap / 2) {   // half of the field's gram budget at most
                                 literal_grams.swap(lg);
-                                for (auto& kv : add) literal_list_len[kv.first] += kv.second;
-                                for (const LitString& ls : strs) literals.push_back(GateLiteral{ls, a});
+                                for (const LitString& ls : pr.strs) literals.push_back(GateLiteral{ls, a});
                                 continue;   // no DFA for this atom
                             }
                         }
-                        if (all_gate) { cls = UC_GATED; gated_grams.push_back(std::move(gg)); }
+                        if (pr.all_gate) { cls = UC_GATED; gated_grams.push_back(GatedGrams{std::move(pr.grams)}); }
                     }
                 }
                 if (getenv("PGW_DEBUG_CLASSES") && cls == UC_GATED && gated_grams.back().grams.size() > 300) fprintf(stderr, "gated field %s grams %zu: %s\n", kFieldNames[f], gated_grams.back().grams.size(), M.atoms[a].key.c_str());
@@ -529,11 +551,22 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
             }
         }
         if (!field_grams.empty() || !literals.empty()) {
-            gate_build_tables(field_grams, field_masks, literals, f == F_URL ? kGateMaxLog2 : kGateMaxLog2 - 2, &H.gate[f]);
-            H.n_literal_atoms += (uint32_t)std::set<uint32_t>([&] { std::vector<uint32_t> v; for (auto& l : literals) v.push_back(l.atom); return std::set<uint32_t>(v.begin(), v.end()); }()).size();
+            std::set<uint32_t> lit_atoms;
+            for (auto& l : literals) lit_atoms.insert(l.atom);
+            H.n_literal_atoms += (uint32_t)lit_atoms.size();
+            gate_in[f].present = true;
+            gate_in[f].grams.swap(field_grams);
+            gate_in[f].masks.swap(field_masks);
+            gate_in[f].literals.swap(literals);
         }
         if (any) H.scanned_fields_mask |= 1u << f;
     }
+    // the exact tables of all gated fields have one slot layout (the resolve kernel is one launch over the fields): the wide one,
+    // with literal candidate lists, only if some field confirms literals
+    for (int f = 0; f < N_FIELDS; ++f)
+        if (gate_in[f].present)
+            gate_build_tables(gate_in[f].grams, gate_in[f].masks, gate_in[f].literals, H.n_literal_atoms != 0, f == F_URL ? kGateMaxLog2 : kGateMaxLog2 - 2,
+                              &H.gate[f]);
     // class maps
     std::vector<uint32_t> cls_offs;
     for (auto& p : pend) {

@@ -383,7 +383,7 @@ void gate_grams_for_literal(const LitString& s, std::vector<std::pair<uint32_t, 
 }
 
 void gate_build_tables(const std::vector<uint32_t>& grams, const std::vector<uint32_t>& masks, const std::vector<GateLiteral>& literals,
-                       uint32_t max_log2, GateTables* out) {
+                       bool wide_slots, uint32_t max_log2, GateTables* out) {
     struct Ent { uint32_t mask = 0; std::vector<uint32_t> cand; };
     std::map<uint32_t, Ent> byg;
     for (size_t i = 0; i < grams.size(); ++i) byg[grams[i]].mask |= masks[i];
@@ -420,17 +420,21 @@ void gate_build_tables(const std::vector<uint32_t>& grams, const std::vector<uin
     // level 2: load factor <= 1/2
     T.kt = 4;
     while (((size_t)1 << T.kt) < byg.size() * 2) ++T.kt;
-    T.slots.assign(((size_t)4 << T.kt), 0u);
+    const uint32_t W = (wide_slots || !literals.empty()) ? 4u : 2u;
+    T.slot_words = W;
+    T.slots.assign(((size_t)W << T.kt), 0u);
     const uint32_t tm = (1u << T.kt) - 1u;
     for (auto& kv : byg) {
         const uint32_t g = kv.first;
         gate_l1_set(T.b1.data(), T.k1, g);
         uint32_t s = (g * kGateHash2) >> (32 - T.kt);
-        while (T.slots[4 * s + 1] != 0 || T.slots[4 * s + 3] != 0) s = (s + 1) & tm;
-        T.slots[4 * s] = g;
-        T.slots[4 * s + 1] = kv.second.mask;
-        T.slots[4 * s + 2] = (uint32_t)T.lit_cand.size();
-        T.slots[4 * s + 3] = (uint32_t)kv.second.cand.size();
+        while (T.slots[W * s + 1] != 0 || (W == 4 && T.slots[W * s + 3] != 0)) s = (s + 1) & tm;
+        T.slots[W * s] = g;
+        T.slots[W * s + 1] = kv.second.mask;
+        if (W == 4) {
+            T.slots[W * s + 2] = (uint32_t)T.lit_cand.size();
+            T.slots[W * s + 3] = (uint32_t)kv.second.cand.size();
+        }
         T.lit_cand.insert(T.lit_cand.end(), kv.second.cand.begin(), kv.second.cand.end());
     }
     if (T.lit_cand.empty()) T.lit_cand.push_back(0);

@@ -68,7 +68,6 @@ struct LitString {
     bool operator==(const LitString& o) const { return bytes == o.bytes && ci_mask == o.ci_mask && anch_start == o.anch_start && anch_end == o.anch_end; }
 };
 constexpr size_t kLitMaxStrings = 48, kLitMaxLen = 64, kLitMinLen = 3;
-constexpr uint32_t kLitListCap = 4;   // literals one gram may announce (compile.cpp: the rest stays with the DFA units)
 
 // device / table form of one literal (program.hpp style POD)
 struct LitDesc {
@@ -87,8 +86,9 @@ struct GateTables {
     uint32_t k1 = 0;                  // log2(bits) of the level-1 bitmap
     std::vector<uint32_t> b1;         // 2^k1 / 32 words
     uint32_t kt = 0;                  // log2(slots) of the level-2 table
-    std::vector<uint32_t> slots;      // 4 words per slot: {gram, unit mask, first literal candidate, number of them}; mask 0 and
-                                      // count 0 = empty slot
+    uint32_t slot_words = 2;          // 2: {gram, unit mask}, mask 0 = empty slot; 4 (some field of the rule set confirms literals):
+                                      // {gram, unit mask, first literal candidate, number of them}, mask 0 and count 0 = empty slot
+    std::vector<uint32_t> slots;
     uint32_t n_grams = 0;
     // literal candidates of a gram: (literal index << 2) | (delta + 1), the literal would start at window position + delta
     std::vector<uint32_t> lit_cand;
@@ -100,12 +100,13 @@ struct GateTables {
         const uint32_t g = gate_fold(window_le);
         if (!gate_l1_test(b1.data(), k1, g)) return 0;
         const uint32_t tm = (1u << kt) - 1u;
+        const uint32_t W = slot_words;
         for (uint32_t s = (g * kGateHash2) >> (32 - kt);; s = (s + 1) & tm) {
-            if (slots[4 * s + 1] == 0 && slots[4 * s + 3] == 0) return 0;
-            if (slots[4 * s] == g) {
-                if (lit_begin) *lit_begin = slots[4 * s + 2];
-                if (lit_count) *lit_count = slots[4 * s + 3];
-                return slots[4 * s + 1];
+            if (slots[W * s + 1] == 0 && (W == 2 || slots[W * s + 3] == 0)) return 0;
+            if (slots[W * s] == g) {
+                if (W == 4 && lit_begin) *lit_begin = slots[W * s + 2];
+                if (W == 4 && lit_count) *lit_count = slots[W * s + 3];
+                return slots[W * s + 1];
             }
         }
     }
@@ -147,7 +148,8 @@ struct GateLiteral {
 
 // `grams[i]` belongs to the units in `masks[i]` (duplicates are merged by OR); `literals` are confirmed by the resolve kernel
 // `max_log2`: largest level-1 bitmap the field may use (all gated fields' bitmaps are resident in shared memory together)
+// `wide_slots`: the 4-word slot layout (required when `literals` is not empty; chosen for every field of a rule set alike)
 void gate_build_tables(const std::vector<uint32_t>& grams, const std::vector<uint32_t>& masks, const std::vector<GateLiteral>& literals,
-                       uint32_t max_log2, GateTables* out);
+                       bool wide_slots, uint32_t max_log2, GateTables* out);
 
 }  // namespace pgw

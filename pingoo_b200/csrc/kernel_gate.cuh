@@ -28,7 +28,18 @@ __device__ __forceinline__ uint32_t gate_l1(const uint32_t* __restrict__ sb, uin
     return shf_wrap_r(word, __umulhi(g, kGateHashB)) & shf_wrap_r(word, __umulhi(g, kGateHashC));
 }
 
-// level 2: exact table in global memory; {gram, unit mask, first literal candidate, their number} of the gram, or zeros
+// level 2: exact table in global memory, narrow slots {gram, unit mask}: the unit mask of the gram, or 0
+__device__ __forceinline__ uint32_t gate_l2(const uint2* __restrict__ slots, uint32_t kt, uint32_t g) {
+    const uint32_t tm = (1u << kt) - 1u;
+    uint32_t s = (g * kGateHash2) >> (32u - kt);
+    for (;;) {
+        const uint2 e = __ldg(slots + s);
+        if (e.y == 0u) return 0u;
+        if (e.x == g) return e.y;
+        s = (s + 1u) & tm;
+    }
+}
+// ... wide slots {gram, unit mask, first literal candidate, their number} (rule sets that confirm literals): the slot, or zeros
 __device__ __forceinline__ uint4 gate_l2(const uint4* __restrict__ slots, uint32_t kt, uint32_t g) {
     const uint32_t tm = (1u << kt) - 1u;
     uint32_t s = (g * kGateHash2) >> (32u - kt);
@@ -222,12 +233,63 @@ __global__ void __launch_bounds__(kListThreads) waf_gate_maybe_kernel(const __gr
     }
 }
 
-// The listed requests' hit chunks against the exact gram table.  grid.y = gated fields; one thread per listed request, and
-// every WARP on its own: no block-wide barrier, so a lane with many windows or literal candidates holds up 31 neighbours at
-// most (with a block-wide append one such lane in 1 024 stalled the whole CTA: measured 5.9 instead of 2.1 ms per 10 M
-// requests for the gate group when literal confirmation went in).  Candidates are appended warp by warp (one atomicAdd per
-// warp that has any): the list is in request order within a warp's 32 entries only, which is all the scan's pools need.
-__global__ void __launch_bounds__(kResolveThreads) waf_gate_resolve_kernel(const __grid_constant__ GateParams gp) {
+// The listed requests' hit chunks against the exact gram table (narrow slots).  grid.y = gated fields; one thread per listed request.
+__global__ void __launch_bounds__(kListThreads) waf_gate_resolve_kernel(const __grid_constant__ GateParams gp) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_base;
+    const GateField& F = gp.f[blockIdx.y];
+    const uint32_t count = *F.maybe_count;
+    const uint32_t total = __ldg(F.off + gp.n);
+    const uint32_t limit = (total + 15u) & ~15u;
+    for (uint32_t blk = blockIdx.x * kListThreads; blk < count; blk += gridDim.x * kListThreads) {
+        const uint32_t k = blk + threadIdx.x;
+        uint32_t r = 0, s = 0, e = 0, mask = 0;
+        if (k < count) {
+            r = F.maybe_idx[k];
+            s = __ldg(F.off + r);
+            e = __ldg(F.off + r + 1u);
+            uint32_t c_lo, c_hi;
+            field_chunks(s, e, &c_lo, &c_hi);
+            for (uint32_t wi = c_lo >> 5; wi <= (c_hi >> 5); ++wi) {
+                uint32_t bits = F.bitmap[wi];
+                if (wi == (c_lo >> 5)) bits &= 0xFFFFFFFFu << (c_lo & 31u);
+                if (wi == (c_hi >> 5)) bits &= 0xFFFFFFFFu >> (31u - (c_hi & 31u));
+                while (bits) {
+                    const uint32_t pos = (wi * 32u + (uint32_t)__ffs(bits) - 1u) << 4;
+                    bits &= bits - 1u;
+                    const uint4 c = ld_nc_v4(F.col + pos);
+                    const uint32_t la = pos + 16u < limit ? ld_nc_u32(F.col + pos + 16u) : 0u;
+                    const uint32_t f0 = c.x & kGateFoldMask, f1 = c.y & kGateFoldMask, f2 = c.z & kGateFoldMask, f3 = c.w & kGateFoldMask,
+                                   f4 = la & kGateFoldMask;
+                    uint32_t g[8];
+                    g[0] = f0; g[1] = __funnelshift_r(f0, f1, 16); g[2] = f1; g[3] = __funnelshift_r(f1, f2, 16);
+                    g[4] = f2; g[5] = __funnelshift_r(f2, f3, 16); g[6] = f3; g[7] = __funnelshift_r(f3, f4, 16);
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+                        const uint32_t j = pos + 2u * (uint32_t)w;
+                        // the window must overlap the field (and lie inside the batch's bytes: j < e <= total)
+                        if (j + 4u > s && j < e) mask |= gate_l2(reinterpret_cast<const uint2*>(F.slots), F.kt, g[w]);
+                    }
+                }
+            }
+        }
+        const bool has = mask != 0u;
+        const uint32_t q = block_append_slot(has, F.cand_count, s_warp, &s_base);
+        if (has) {
+            F.cand_idx[q] = r;
+            F.cand_start[q] = s;
+            F.cand_end[q] = e;
+            F.cand_mask[q] = mask;
+        }
+    }
+}
+
+// The same for rule sets that confirm literals (wide slots, gate.hpp): besides collecting unit masks, a gram's literal candidates
+// are compared in place and their atoms fired here.  Every WARP works on its own -- no block-wide barrier, so a lane with many
+// windows or candidates holds up 31 neighbours at most (with the block-wide append of the kernel above one such lane in 1 024
+// stalled the whole CTA: measured 5.9 instead of 2.1 ms per 10 M requests for the gate group); candidates are appended warp by
+// warp (one atomicAdd per warp that has any): the list is in request order within 32 entries, which is all the scan's pools need.
+__global__ void __launch_bounds__(kResolveThreads) waf_gate_resolve_lit_kernel(const __grid_constant__ GateParams gp) {
     const GateField& F = gp.f[blockIdx.y];
     const uint32_t count = *F.maybe_count;
     const uint32_t total = __ldg(F.off + gp.n);
@@ -267,7 +329,7 @@ __global__ void __launch_bounds__(kResolveThreads) waf_gate_resolve_kernel(const
                         en[w] = (j + 4u > s && j < e) ? gate_l2(reinterpret_cast<const uint4*>(F.slots), F.kt, g[w]) : make_uint4(0, 0, 0, 0);
                         mask |= en[w].y;
                     }
-                    // finite-string patterns announced by a gram (at most kLitListCap per gram): compared in place, their atoms fired here
+                    // finite-string patterns announced by a gram (one, for an atom whose grams are its own: compile.cpp): compared in place, their atoms fired here
 #pragma unroll 1
                     for (int w = 0; w < 8; ++w) {
                         const uint32_t nc = en[w].w;

@@ -131,9 +131,11 @@ const char* waf_batch_launch(KParams& p, GateParams& g, const UnitDesc* all_unit
         waf_gate_maybe_kernel<<<lb, kListThreads, 0, s>>>(g);
         e = cudaGetLastError();
         if (e != cudaSuccess) return cudaGetErrorString(e);
-        uint32_t rb = (p.n + kResolveThreads - 1u) / kResolveThreads;
-        if (rb > (uint32_t)sm_count * 8u) rb = (uint32_t)sm_count * 8u;
-        waf_gate_resolve_kernel<<<dim3(rb, g.n_fields), kResolveThreads, 0, s>>>(g);
+        if (g.wide_slots) {
+            uint32_t rb = (p.n + kResolveThreads - 1u) / kResolveThreads;
+            if (rb > (uint32_t)sm_count * 8u) rb = (uint32_t)sm_count * 8u;
+            waf_gate_resolve_lit_kernel<<<dim3(rb, g.n_fields), kResolveThreads, 0, s>>>(g);
+        } else waf_gate_resolve_kernel<<<dim3(lb, g.n_fields), kListThreads, 0, s>>>(g);
         e = cudaGetLastError();
         if (e != cudaSuccess) return cudaGetErrorString(e);
         nl += 3;

@@ -123,7 +123,8 @@ struct GateField {
     const uint8_t* col;      // field bytes
     const uint32_t* off;     // n + 1 offsets
     const uint32_t* b1;      // level 1: blocked Bloom filter (2^k1 bits), global memory copy (staged into shared memory)
-    const uint32_t* slots;   // level 2: exact table, 2^kt slots of {gram, unit mask, first literal candidate, their number}
+    const uint32_t* slots;   // level 2: exact table, 2^kt slots of {gram, unit mask} or, with GateParams::wide_slots,
+                             // {gram, unit mask, first literal candidate, their number}
     const uint32_t* lit_cand;   // literal candidates of the grams: (literal << 2) | (delta + 1)
     const LitDesc* lits;        // finite-string patterns confirmed by the resolve kernel (gate.hpp)
     const uint8_t* lit_bytes;
@@ -144,6 +145,7 @@ struct GateParams {
     GateField f[kMaxGateFields];
     uint32_t n_fields;
     uint32_t n;              // requests
+    uint32_t wide_slots;     // the rule set confirms literals in the resolve step (gate.hpp): 4-word slots, waf_gate_resolve_lit_kernel
     // where a confirmed literal's atom goes: the request's bitmap row and info words (as KParams)
     uint32_t* rows;
     uint32_t* info;

@@ -27,7 +27,7 @@ struct Sim {
     std::string last_error;
     uint64_t* stats = nullptr;  // optional: per field {requests gated, candidates}
     uint64_t* atom_hist = nullptr;
-    uint64_t* lit_stats = nullptr;  // optional: {windows with a gram that has literal candidates, candidates compared, confirmed, largest candidate list}
+    uint64_t* lit_stats = nullptr;  // optional: {windows with a gram that has literal candidates, candidates compared, confirmed, largest candidate list, out of bounds, anchor misses}
 };
 
 int fail(Sim* s, const std::string& m, char* err, size_t cap) {
@@ -217,6 +217,11 @@ static int evaluate_range(Sim* s, const pgw_batch* b, uint32_t* out, uint16_t* s
                 for (uint32_t c = 0; c < lc; ++c) {
                     const uint32_t cd = G.lit_cand[lb + c];
                     const LitDesc& d = G.lits[cd >> 2];
+                    if (s->lit_stats) {
+                        const int64_t at = (int64_t)j + (int64_t)(cd & 3u) - 1;
+                        if (at < (int64_t)a || at + d.len > (int64_t)e) s->lit_stats[4]++;
+                        else if (((d.flags & 1) && at != (int64_t)a) || ((d.flags & 2) && at + d.len != (int64_t)e)) s->lit_stats[5]++;
+                    }
                     if (G.lit_matches(d, bytes, a, e, (int64_t)j + (int64_t)(cd & 3u) - 1)) { row[d.atom >> 5] |= 1u << (d.atom & 31); if (s->lit_stats) s->lit_stats[2]++; }
                 }
             }

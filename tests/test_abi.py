@@ -37,7 +37,7 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_ffi.Batch) == 8 + 5 * 16 + 6 * 8
     assert C.sizeof(_ffi.Options) == 24  # 4 (+4 pad) + 8 + 4 + 4
     assert C.sizeof(_ffi.ServiceDesc) == 16
-    assert C.sizeof(_ffi.Info) == 9 * 4 + 4 + 2 * 8 + 4 * 4 + 3 * 4 + 4 + 3 * 8 + 2 * 4 + 8
+    assert C.sizeof(_ffi.Info) == 9 * 4 + 4 + 2 * 8 + 4 * 4 + 3 * 4 + 4 + 3 * 8 + 2 * 4 + 8 + 2 * 4
 
 
 def test_compile_and_validate_expression_need_no_gpu():

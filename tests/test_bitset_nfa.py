@@ -195,5 +195,5 @@ def test_gpu_every_pattern_forced_through_the_bitset_kernel():
     _gpu_check(rules, pack_requests(reqs), max_dfa_states=1, candidate_gate=False)
     rules, lists, mmdb, batch, _ = scenarios.config2_sample(20_000, attack_rate=0.2)
     eng, want = _gpu_check(rules, batch, max_dfa_states=1, candidate_gate=False)
-    assert eng.info().n_scan_units == 0 and eng.describe().count("bitset-nfa") > 100
+    assert eng.info().n_scan_units == 0 and eng.info().n_bitset_units > 100 and eng.info().bitset_positions > 1000
     _gpu_check(rules, batch.slice(0, 8000), max_dfa_states=1)   # gate + literal confirmation in front, bitset units behind

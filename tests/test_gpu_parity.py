@@ -312,3 +312,27 @@ def test_constant_receivers_dynamic_lists_and_field_ordering():
     _check(rules, batch, lists, eval_gates=False)
     for r in rules[8:11]:   # the ordering predicates one at a time: nothing in front of them in the first-match loop
         _check([r], batch, lists, eval_gates=False)
+
+
+@pytest.mark.gpu
+def test_gate_resolve_with_and_without_literal_confirmation():
+    """tests/test_gate.py's rule set on its alignment / boundary inputs: the user-agent and path atoms are strings with grams of
+    their own, confirmed by `waf_gate_resolve_lit_kernel` (wide slots); with literal confirmation switched off the same rules run
+    through `waf_gate_resolve_kernel` (narrow slots) and the DFA units.  Both against the oracle."""
+    import test_gate
+
+    reqs = []
+    for frag in ["union", "../", ".php", ";nc", "'or 1=1", "<svg>", "select from", "3.env", "curl/", "bot", ".git", ".GIT/", ".env"]:
+        for pre in range(0, 9):
+            for post in range(0, 5):
+                url = "q" * pre + frag + "r" * post
+                reqs.append(dict(host="h", url=url, path="/" + "p" * (pre % 3) + (frag if post % 2 else ""), method="GET",
+                                 user_agent=("Mozilla/5.0 z" if pre % 2 else "x" * pre) + (frag if post < 2 else "") + "y" * post, ip="1.2.3.4", remote_port=1, flags=0))
+    batch = pack_requests(reqs * 8)
+    eng, want = _check(test_gate.RULES, batch)
+    d = eng.describe()
+    assert "literals=" in d and "wide-slots" in d, d
+    assert len(set(want.tolist())) > 8
+    eng2, _ = _check(test_gate.RULES, batch, literal_confirm=False)
+    d2 = eng2.describe()
+    assert "literals=" not in d2 and "wide-slots" not in d2 and "user_agent/gated" in d2, d2
