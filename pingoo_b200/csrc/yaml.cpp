@@ -156,9 +156,23 @@ class Parser {
         n.quoted = true;
         n.line = line;
         char q = t[p++];
+        // A line break inside a quoted scalar (multi-line scalars reach this function with their '\n' in place) is folded as YAML
+        // folds flow scalars: white space around the break is dropped, one break becomes a space, k > 1 breaks become k - 1 newlines.
+        auto fold_break = [&]() {
+            while (!n.s.empty() && (n.s.back() == ' ' || n.s.back() == '\t')) n.s.pop_back();
+            int breaks = 1;
+            for (;;) {
+                while (p < t.size() && (t[p] == ' ' || t[p] == '\t')) ++p;
+                if (p < t.size() && t[p] == '\n') { ++breaks; ++p; continue; }
+                break;
+            }
+            if (breaks == 1) n.s += ' ';
+            else n.s.append((size_t)breaks - 1, '\n');
+        };
         for (;;) {
             if (p >= t.size()) fail(line, "unterminated quoted scalar");
             char c = t[p++];
+            if (c == '\n') { fold_break(); continue; }
             if (q == '\'') {
                 if (c == '\'') {
                     if (p < t.size() && t[p] == '\'') { n.s += '\''; ++p; continue; }
@@ -170,6 +184,10 @@ class Parser {
                 if (c != '\\') { n.s += c; continue; }
                 if (p >= t.size()) fail(line, "unterminated escape");
                 char e = t[p++];
+                if (e == '\n') {   // escaped line break: the break disappears, the white space in front of it stays
+                    while (p < t.size() && (t[p] == ' ' || t[p] == '\t')) ++p;
+                    continue;
+                }
                 switch (e) {
                     case 'n': n.s += '\n'; break;
                     case 't': n.s += '\t'; break;
@@ -267,7 +285,8 @@ class Parser {
         return n;
     }
 
-    static bool balanced(const std::string& t) {
+    // bracket depth of `t` and whether it ends inside a quoted scalar
+    static void flow_state(const std::string& t, int* depth_out, bool* in_quote) {
         int depth = 0;
         char q = 0;
         for (size_t i = 0; i < t.size(); ++i) {
@@ -275,11 +294,28 @@ class Parser {
             if (q) {
                 if (q == '"' && c == '\\') { ++i; continue; }
                 if (c == q) q = 0;
-            } else if (c == '"' || c == '\'') q = c;
-            else if (c == '[' || c == '{') ++depth;
+            } else if (c == '"' || c == '\'') {
+                // a quote opens a scalar only where a scalar can begin; inside a plain one (it's) it is an ordinary character
+                size_t b = i;
+                while (b > 0 && (t[b - 1] == ' ' || t[b - 1] == '\t' || t[b - 1] == '\n')) --b;
+                if (b == 0 || t[b - 1] == '[' || t[b - 1] == '{' || t[b - 1] == ',' || t[b - 1] == ':') q = c;
+            } else if (c == '[' || c == '{') ++depth;
             else if (c == ']' || c == '}') --depth;
         }
-        return depth <= 0 && !q;
+        *depth_out = depth;
+        *in_quote = q != 0;
+    }
+    static bool balanced(const std::string& t) {
+        int d;
+        bool q;
+        flow_state(t, &d, &q);
+        return d <= 0 && !q;
+    }
+    static bool open_quote(const std::string& t) {
+        int d;
+        bool q;
+        flow_state(t, &d, &q);
+        return q;
     }
 
     // literal / folded block scalar whose header (`|`, `>`, with indicators) is `hdr`; content = following lines more
@@ -348,6 +384,13 @@ class Parser {
         if (v[0] == '|' || v[0] == '>') return block_scalar(v, i, parent_indent, line);
         if (v[0] == '[' || v[0] == '{') {
             while (!balanced(v)) {
+                if (open_quote(v)) {
+                    // the collection breaks off inside a quoted scalar: the next line (blank ones included) continues the scalar
+                    if (i >= lines_.size()) fail(line, "unterminated quoted scalar");
+                    v += "\n" + lines_[i].raw;
+                    ++i;
+                    continue;
+                }
                 size_t j = next(i);
                 if (j >= lines_.size()) fail(line, "unterminated flow collection");
                 v += " " + lines_[j].text;
@@ -374,7 +417,7 @@ class Parser {
                 }
                 if (closed) break;
                 if (i >= lines_.size()) fail(line, "unterminated quoted scalar");
-                v += " " + ltrim(rtrim(lines_[i].raw));
+                v += "\n" + lines_[i].raw;   // folded by quoted()
                 ++i;
             }
             size_t p = 0;

@@ -11,7 +11,7 @@ from pingoo_b200.batch import RequestBatch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
-SIM_SO = os.path.join(ROOT, "tests", "sim", "libpgw_sim.so")
+SIM_SO = os.environ.get("PGW_SIM_SO") or os.path.join(ROOT, "tests", "sim", "libpgw_sim.so")   # PGW_SIM_SO: e.g. a sanitizer build (tools/README.md)
 
 
 def _ensure(path, make_dir):

@@ -231,6 +231,45 @@ def test_yaml_reader_agrees_with_pyyaml(text):
     assert out == _canon(yaml.safe_load(text))
 
 
+YAML_WORDS = ['http_request.url.contains("x")', "block", "captcha", "a b", "it's", "x: y", "# no", "-dash", "1", "true", "null", "~", "", " lead", "trail ",
+              "multi\nline", "tab\there", "100%", "[a]", "{b}", "a,b", '"q"', "k#v", "path/to/file.csv", "0x1F", "1e3", "\u00e9", "yes", "No", "*star", "&amp", "!bang",
+              "|pipe", ">gt", "@at", "`tick", "%pct", "?q", ":colon", "a: ", "- x"]
+YAML_KEYS = ["rules", "services", "lists", "name", "expression", "actions", "action", "route", "http_proxy", "static", "root", "file", "type", "listeners", "address",
+             "a b", "k-1", "x_y", "K"]
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_yaml_reader_agrees_with_pyyaml_on_random_documents(seed):
+    """Random nested documents written by PyYAML in block, flow and mixed styles, narrow and wide, with plain / quoted / literal /
+    folded scalars (multi-line quoted scalars, apostrophes in plain scalars, indicator characters, empty collections): the
+    engine's reader must read what PyYAML reads.  Styles that make PyYAML emit tags (`!!int "1"`) are refused by design."""
+    import random
+
+    rng = random.Random(seed)
+
+    def val(d):
+        r = rng.random()
+        if d <= 0 or r < 0.45:
+            return rng.choice(YAML_WORDS) if rng.random() < 0.8 else rng.choice([1, 0, -3, True, False, None, 2.5])
+        if r < 0.75:
+            return {rng.choice(YAML_KEYS) + (str(rng.randrange(3)) if rng.random() < 0.5 else ""): val(d - 1) for _ in range(rng.randrange(0, 4))}
+        return [val(d - 1) for _ in range(rng.randrange(0, 4))]
+
+    read = refused = 0
+    for _ in range(150):
+        doc = {rng.choice(YAML_KEYS) + str(k): val(3) for k in range(rng.randrange(1, 4))}
+        text = yaml.safe_dump(doc, default_flow_style=rng.choice([True, False, None]), default_style=rng.choice([None, None, None, '"', "'", "|", ">"]),
+                              width=rng.choice([20, 80, 1000]), indent=rng.choice([2, 4]), allow_unicode=rng.random() < 0.5, sort_keys=False)
+        ok, out = yaml_dump(text)
+        if not ok:
+            assert "tags are not supported" in out and "!!" in text, (out, text)
+            refused += 1
+            continue
+        assert out == _canon(yaml.safe_load(text)), text
+        read += 1
+    assert read > 80
+
+
 @pytest.mark.parametrize("text", ["a: [1, 2", "a: 'x", "a: &anchor 1", "a: *alias", "a:\n    b: 1\n  c: 2\n", "- a\nb: 1\n", "a: 1\na: 2\n", "? complex\n: key\n", "next: value with: colon inside\n"])
 def test_yaml_reader_rejects_what_it_does_not_read(text):
     ok, out = yaml_dump(text)
