@@ -663,12 +663,20 @@ int bel_parse_ipnet(const char* s, bel_ipnet* out) {
     if (slash) {
         const char* pf = slash + 1;
         size_t pl = strlen(pf);
-        int digits = pl > 0 && pl <= 3;
-        for (size_t i = 0; i < pl; ++i) if (!isdigit((unsigned char)pf[i])) digits = 0;
-        if (digits) {
-            int v = atoi(pf);
-            if (v > (out->v6 ? 128 : 32)) return 0;
-            out->prefix = v;
+        /* parse_prefix = `s.parse::<u8>()` then `<= max`: Rust's integer FromStr takes an optional '+', any number of leading
+         * zeros, nothing else, and fails on overflow of the type (255) */
+        size_t d0 = (pl > 0 && pf[0] == '+') ? 1 : 0;
+        int digits = pl > d0;
+        unsigned v = 0;
+        for (size_t i = d0; i < pl && digits; ++i) {
+            if (!isdigit((unsigned char)pf[i])) digits = 0;
+            else { v = v * 10 + (unsigned)(pf[i] - '0'); if (v > 255) digits = 0; }
+        }
+        int numeric = pl > d0;
+        for (size_t i = d0; i < pl; ++i) if (!isdigit((unsigned char)pf[i])) numeric = 0;
+        if (numeric) {
+            if (!digits || v > (unsigned)(out->v6 ? 128 : 32)) return 0;
+            out->prefix = (int)v;
         } else if (!out->v6) {
             uint8_t m[4];
             if (!parse_v4(pf, pl, m)) return 0;

@@ -94,6 +94,8 @@ bool parse_ipv6(const std::string& s, uint8_t out[16]) {
 
 }  // namespace
 
+// `IpNetwork::from_str` (ipnetwork 0.21, reached by lists.rs:100 `item_value.parse()`) tries the IPv4 and then the IPv6 network
+// parser and reports ANY failure -- address, prefix or netmask -- as InvalidAddr(<the whole string>): "invalid address: <s>".
 bool parse_ip_network(const std::string& s, IpNet* out, std::string& err) {
     IpNet n;
     size_t slash = s.find('/');
@@ -110,23 +112,27 @@ bool parse_ip_network(const std::string& s, IpNet* out, std::string& err) {
         return false;
     }
     if (slash != std::string::npos) {
-        bool digits = !pfx.empty() && pfx.size() <= 3;
-        for (char c : pfx) if (!isdigit((unsigned char)c)) digits = false;
-        if (digits) {
-            int v = atoi(pfx.c_str());
-            if (v > (n.v6 ? 128 : 32)) { err = "invalid prefix"; return false; }
-            n.prefix = v;
+        // the prefix goes through `str::parse::<u8>()` (ipnetwork parse_prefix): an optional '+', digits (leading zeros allowed),
+        // a value that fits the type; then <= 32 / 128
+        const size_t d0 = (!pfx.empty() && pfx[0] == '+') ? 1 : 0;
+        bool numeric = pfx.size() > d0;
+        for (size_t k = d0; k < pfx.size(); ++k) if (!isdigit((unsigned char)pfx[k])) numeric = false;
+        if (numeric) {
+            unsigned v = 0;
+            for (size_t k = d0; k < pfx.size() && v <= 255; ++k) v = v * 10 + (unsigned)(pfx[k] - '0');
+            if (v > (n.v6 ? 128u : 32u)) { err = "invalid address: " + s; return false; }
+            n.prefix = (int)v;
         } else if (!n.v6) {
             // dotted netmask, must be contiguous ones
             uint8_t m[4];
-            if (!parse_ipv4(pfx, m)) { err = "invalid prefix"; return false; }
+            if (!parse_ipv4(pfx, m)) { err = "invalid address: " + s; return false; }
             uint32_t mask = (uint32_t)m[0] << 24 | (uint32_t)m[1] << 16 | (uint32_t)m[2] << 8 | m[3];
             int len = 0;
             while (len < 32 && (mask & (0x80000000u >> len))) ++len;
-            if (len < 32 && (mask << len) != 0) { err = "invalid prefix"; return false; }
+            if (len < 32 && (mask << len) != 0) { err = "invalid address: " + s; return false; }
             n.prefix = len;
         } else {
-            err = "invalid prefix";
+            err = "invalid address: " + s;
             return false;
         }
     }

@@ -233,3 +233,51 @@ def test_constant_receivers_dynamic_lists_and_field_ordering():
         want = _check([r], batch, lists, eval_gates=False)
         hits = int(np.count_nonzero(want & 3))
         assert 0 < hits < batch.n, (r.expression, hits)
+
+
+def test_list_csv_forms_engine_vs_oracle():
+    """Random list files (quoting, CRLF, blank lines, comments column, malformed entries, every IpNetwork / i64 form) through the
+    engine's CSV + entry parsers and the oracle's: same acceptance, same error text, same membership."""
+    import random
+
+    from pingoo_b200 import Action, ListType, Rule
+
+    atoms = {ListType.Ip: ["1.2.3.4", "10.0.0.0/8", "192.168.1.7/32", "2001:db8::/32", "::1", "1.2.3", "1.2.3.4/33", "300.1.1.1", "fe80::1%eth0", "0.0.0.0/0", "::/0",
+                           "1.2.3.4/", " 8.8.8.8 ", "::ffff:1.2.3.4", "1.2.3.4/24", "01.2.3.4", "2001:db8::1/129", "1.2.3.0/255.255.255.0", "1.2.3.0/255.0.255.0",
+                           "10.0.0.0/08", "10.0.0.0/+8", "10.0.0.0/ 8", "1.2.3.4/0032", "2001:db8::/ffff::", "10.1.2.3/0.0.0.0", "1.2.3.4/-1", "1.2.3.4/8/9", "2001:DB8::1"],
+             ListType.Int: ["1", "-3", "+5", " 64500 ", "1x", "0x10", "", "9223372036854775807", "9223372036854775808", "-9223372036854775808", "1.0", "\u0661"],
+             ListType.String: ["example.com", " spaced ", "a,b", 'q"x', "", "\u00e9vil", "UPPER", "x" * 300, "tab\there", "#c"]}
+    probes = [dict(host=h, url="/", path="/", method="GET", user_agent="Mozilla/5.0", ip=ip, remote_port=1, flags=0, asn=asn, country="US")
+              for h in ["example.com", "spaced", "a,b", 'q"x', "", "UPPER", "tab\there", "#c"]
+              for ip, asn in [("1.2.3.4", 1), ("10.9.9.9", -3), ("8.8.8.8", 5), ("2001:db8::5", 64500), ("::1", 16), ("192.168.1.7", 0), ("::ffff:1.2.3.4", 9223372036854775807)]]
+    batch = pack_requests(probes)
+    exprs = {ListType.Ip: 'lists["l"].contains(client.ip)', ListType.Int: 'lists["l"].contains(client.asn)', ListType.String: 'lists["l"].contains(http_request.host)'}
+    rng = random.Random(7)
+    accepted = refused = 0
+    for _ in range(250):
+        t = rng.choice([ListType.Ip, ListType.Int, ListType.String])
+        eol = rng.choice(["\n", "\r\n"])
+        rows = []
+        for _ in range(rng.randrange(0, 6)):
+            a = rng.choice(atoms[t])
+            if rng.random() < 0.2:
+                a = '"' + a.replace('"', '""') + '"'
+            if rng.random() < 0.3:
+                a += "," + rng.choice(["comment", '"quoted, comment"', "", " x "])
+            if rng.random() < 0.05:
+                a += ",third"
+            rows.append(a)
+        text = eol.join(rows) + (eol if rng.random() < 0.7 else "")
+        if rng.random() < 0.2:
+            text = eol + text
+        rules = [Rule("r", exprs[t], [Action.BLOCK])]
+        res = []
+        for cls in (Oracle, Sim):
+            try:
+                res.append(("ok", cls(rules, {"l": (t, text.encode())}, eval_gates=False).evaluate(batch).tolist()))
+            except ValueError as e:
+                res.append(("error", str(e)))
+        assert res[0] == res[1], (t, text)
+        accepted += res[0][0] == "ok"
+        refused += res[0][0] == "error"
+    assert accepted > 40 and refused > 40

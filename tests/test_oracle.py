@@ -340,7 +340,9 @@ def test_ipnetwork_against_python_ipaddress():
 
 
 @pytest.mark.parametrize("text", ["1.2.3", "1.2.3.4.5", "01.2.3.4", "256.1.1.1", "1.2.3.4/33", "::1/129", "1::2::3", ":1", "1:", "12345::", "g::1", "1.2.3.4/255.0.255.0",
-                                  "", " 1.2.3.4", "1.2.3.4/", "::ffff:1.2.3", "1:2:3:4:5:6:7:8:9"])
+                                  "", " 1.2.3.4", "1.2.3.4/", "::ffff:1.2.3", "1:2:3:4:5:6:7:8:9",
+                                  # the prefix is `str::parse::<u8>()`: no sign but '+', no blanks, no overflow of the type
+                                  "1.2.3.4/-1", "1.2.3.4/ 8", "1.2.3.4/256", "1.2.3.4/0x8", "1.2.3.4/8/9", "1.2.3.4/+", "2001:db8::/ffff::", "2001:db8::/+129"])
 def test_ipnetwork_rejections(text):
     assert oracle_lib().orc_ipnet_contains(text.encode(), b"\0" * 16, 0) == -1
 
@@ -348,7 +350,10 @@ def test_ipnetwork_rejections(text):
 @pytest.mark.parametrize("text,probe,v6,want", [
     ("::ffff:1.2.3.4", ipaddress.IPv6Address("::ffff:102:304").packed, 1, 1), ("::", b"\0" * 16, 1, 1), ("1::", ipaddress.IPv6Address("1::").packed, 1, 1),
     ("::1.2.3.4/96", ipaddress.IPv6Address("::5.6.7.8").packed, 1, 1), ("10.1.2.3/8", bytes([10, 9, 9, 9]) + b"\0" * 12, 0, 1),
-    ("1.2.3.4/255.255.255.0", bytes([1, 2, 3, 200]) + b"\0" * 12, 0, 1), ("0.0.0.0/0", bytes([9, 9, 9, 9]) + b"\0" * 12, 0, 1)])
+    ("1.2.3.4/255.255.255.0", bytes([1, 2, 3, 200]) + b"\0" * 12, 0, 1), ("0.0.0.0/0", bytes([9, 9, 9, 9]) + b"\0" * 12, 0, 1),
+    # Rust's integer FromStr takes an optional '+' and leading zeros
+    ("10.0.0.0/+8", bytes([10, 9, 9, 9]) + b"\0" * 12, 0, 1), ("10.0.0.0/0008", bytes([10, 9, 9, 9]) + b"\0" * 12, 0, 1),
+    ("10.0.0.0/0008", bytes([11, 9, 9, 9]) + b"\0" * 12, 0, 0), ("2001:db8::/0032", ipaddress.IPv6Address("2001:db8:5::1").packed, 1, 1)])
 def test_ipnetwork_forms(text, probe, v6, want):
     assert oracle_lib().orc_ipnet_contains(text.encode(), probe, v6) == want
 
