@@ -115,12 +115,26 @@ static int uni_gc(const char* v, uint8_t* s) {
     return 1;
 }
 static int uni_script(const char* v, uint8_t* s) {
-    static const char* none[] = {"greek", "grek", "cyrillic", "cyrl", "han", "hani", "arabic", "arab", "hebrew", "hebr", "hiragana", "hira", "katakana",
-                                 "kana", "thai", "devanagari", "deva", "hangul", "hang", "armenian", "armn", "georgian", "geor", "ethiopic", "ethi",
-                                 "bengali", "beng", "tamil", "taml", "telugu", "telu", "gujarati", "gujr", "gurmukhi", "guru", "kannada", "knda",
-                                 "malayalam", "mlym", "sinhala", "sinh", "khmer", "khmr", "lao", "laoo", "tibetan", "tibt", "myanmar", "mymr", "mongolian",
-                                 "mong", "syriac", "syrc", "thaana", "thaa", "coptic", "copt", "cherokee", "cher", "bopomofo", "bopo", "braille", "brai",
-                                 "inherited", "zinh", "qaai", NULL};
+    /* every Unicode script except Latin and Common: no ASCII member (checked against the `regex` module by tests/test_oracle.py) */
+    static const char* none[] = {
+        "adlam", "ahom", "anatolianhieroglyphs", "arabic", "armenian", "avestan", "balinese", "bamum", "bassavah", "batak", "bengali", "bhaiksuki",
+        "bopomofo", "brahmi", "braille", "buginese", "buhid", "canadianaboriginal", "carian", "caucasianalbanian", "chakma", "cham", "cherokee", "chorasmian",
+        "coptic", "cuneiform", "cypriot", "cyprominoan", "cyrillic", "deseret", "devanagari", "divesakuru", "dogra", "duployan", "egyptianhieroglyphs", "elbasan",
+        "elymaic", "ethiopic", "georgian", "glagolitic", "gothic", "grantha", "greek", "gujarati", "gunjalagondi", "gurmukhi", "han", "hangul",
+        "hanifirohingya", "hanunoo", "hatran", "hebrew", "hiragana", "imperialaramaic", "inherited", "inscriptionalpahlavi", "inscriptionalparthian", "javanese", "kaithi", "kannada",
+        "katakana", "kawi", "kayahli", "kharoshthi", "khitansmallscript", "khmer", "khojki", "khudawadi", "lao", "lepcha", "limbu", "lineara",
+        "linearb", "lisu", "lycian", "lydian", "mahajani", "makasar", "malayalam", "mandaic", "manichaean", "marchen", "masaramgondi", "medefaidrin",
+        "meeteimayek", "mendekikakui", "meroiticcursive", "meroitichieroglyphs", "miao", "modi", "mongolian", "mro", "multani", "myanmar", "nabataean", "nagmundari",
+        "nandinagari", "newa", "newtailue", "nko", "nushu", "nyiakengpuachuehmong", "ogham", "olchiki", "oldhungarian", "olditalic", "oldnortharabian", "oldpermic",
+        "oldpersian", "oldsogdian", "oldsoutharabian", "oldturkic", "olduyghur", "oriya", "osage", "osmanya", "pahawhhmong", "palmyrene", "paucinhau", "phagspa",
+        "phoenician", "psalterpahlavi", "rejang", "runic", "samaritan", "saurashtra", "sharada", "shavian", "siddham", "signwriting", "sinhala", "sogdian",
+        "sorasompeng", "soyombo", "sundanese", "sylotinagri", "syriac", "tagalog", "tagbanwa", "taile", "taitham", "taiviet", "takri", "tamil",
+        "tangsa", "tangut", "telugu", "thaana", "thai", "tibetan", "tifinagh", "tirhuta", "toto", "ugaritic", "vai", "vithkuqi",
+        "wancho", "warangciti", "yezidi", "yi", "zanabazarsquare", "grek", "cyrl", "hani", "arab", "hebr", "hira", "kana",
+        "deva", "hang", "armn", "geor", "ethi", "beng", "taml", "telu", "gujr", "guru", "knda", "mlym",
+        "sinh", "khmr", "laoo", "tibt", "mymr", "mong", "syrc", "thaa", "copt", "cher", "bopo", "brai",
+        "zinh", "qaai",
+        NULL};
     if (V("latin") || V("latn")) { set_range(s, 'A', 'Z'); set_range(s, 'a', 'z'); return 1; }
     if (V("common") || V("zyyy")) {
         for (unsigned c = 0; c < 128; ++c)

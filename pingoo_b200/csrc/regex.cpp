@@ -77,12 +77,21 @@ static const PropName kGcNames[] = {
     {"c", GC_Cc}, {"other", GC_Cc}, {"cc", GC_Cc}, {"control", GC_Cc}, {"cntrl", GC_Cc}, {"cf", 0}, {"format", 0}, {"cs", 0}, {"surrogate", 0},
     {"co", 0}, {"privateuse", 0}, {"cn", 0}, {"unassigned", 0},
 };
-static const char* const kOtherScripts[] = {   // known scripts without an ASCII member (long and ISO 15924 names)
-    "greek", "grek", "cyrillic", "cyrl", "han", "hani", "arabic", "arab", "hebrew", "hebr", "hiragana", "hira", "katakana", "kana", "thai", "devanagari", "deva",
-    "hangul", "hang", "armenian", "armn", "georgian", "geor", "ethiopic", "ethi", "bengali", "beng", "tamil", "taml", "telugu", "telu", "gujarati", "gujr",
-    "gurmukhi", "guru", "kannada", "knda", "malayalam", "mlym", "sinhala", "sinh", "khmer", "khmr", "lao", "laoo", "tibetan", "tibt", "myanmar", "mymr",
-    "mongolian", "mong", "syriac", "syrc", "thaana", "thaa", "coptic", "copt", "cherokee", "cher", "bopomofo", "bopo", "braille", "brai", "inherited", "zinh",
-    "zinh", "qaai",
+static const char* const kOtherScripts[] = {   // every Unicode script but Latin and Common (names normalised; some ISO 15924 codes): none has an ASCII member
+    "adlam", "ahom", "anatolianhieroglyphs", "arabic", "armenian", "avestan", "balinese", "bamum", "bassavah", "batak", "bengali", "bhaiksuki", "bopomofo", "brahmi",
+    "braille", "buginese", "buhid", "canadianaboriginal", "carian", "caucasianalbanian", "chakma", "cham", "cherokee", "chorasmian", "coptic", "cuneiform", "cypriot", "cyprominoan",
+    "cyrillic", "deseret", "devanagari", "divesakuru", "dogra", "duployan", "egyptianhieroglyphs", "elbasan", "elymaic", "ethiopic", "georgian", "glagolitic", "gothic", "grantha",
+    "greek", "gujarati", "gunjalagondi", "gurmukhi", "han", "hangul", "hanifirohingya", "hanunoo", "hatran", "hebrew", "hiragana", "imperialaramaic", "inherited", "inscriptionalpahlavi",
+    "inscriptionalparthian", "javanese", "kaithi", "kannada", "katakana", "kawi", "kayahli", "kharoshthi", "khitansmallscript", "khmer", "khojki", "khudawadi", "lao", "lepcha",
+    "limbu", "lineara", "linearb", "lisu", "lycian", "lydian", "mahajani", "makasar", "malayalam", "mandaic", "manichaean", "marchen", "masaramgondi", "medefaidrin",
+    "meeteimayek", "mendekikakui", "meroiticcursive", "meroitichieroglyphs", "miao", "modi", "mongolian", "mro", "multani", "myanmar", "nabataean", "nagmundari", "nandinagari", "newa",
+    "newtailue", "nko", "nushu", "nyiakengpuachuehmong", "ogham", "olchiki", "oldhungarian", "olditalic", "oldnortharabian", "oldpermic", "oldpersian", "oldsogdian", "oldsoutharabian", "oldturkic",
+    "olduyghur", "oriya", "osage", "osmanya", "pahawhhmong", "palmyrene", "paucinhau", "phagspa", "phoenician", "psalterpahlavi", "rejang", "runic", "samaritan", "saurashtra",
+    "sharada", "shavian", "siddham", "signwriting", "sinhala", "sogdian", "sorasompeng", "soyombo", "sundanese", "sylotinagri", "syriac", "tagalog", "tagbanwa", "taile",
+    "taitham", "taiviet", "takri", "tamil", "tangsa", "tangut", "telugu", "thaana", "thai", "tibetan", "tifinagh", "tirhuta", "toto", "ugaritic",
+    "vai", "vithkuqi", "wancho", "warangciti", "yezidi", "yi", "zanabazarsquare", "grek", "cyrl", "hani", "arab", "hebr", "hira", "kana",
+    "deva", "hang", "armn", "geor", "ethi", "beng", "taml", "telu", "gujr", "guru", "knda", "mlym", "sinh", "khmr",
+    "laoo", "tibt", "mymr", "mong", "syrc", "thaa", "copt", "cher", "bopo", "brai", "zinh", "qaai",
 };
 // 0: ok, 1: not a name this engine knows (loud), 2: malformed
 static int unicode_property_ascii(const std::string& raw, ByteSet* out, bool* negated) {

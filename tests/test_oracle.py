@@ -438,3 +438,31 @@ def _geo_no_skip(records, ip_obj):
 def test_geoip_rejects_garbage():
     with pytest.raises(ValueError, match="mmdb file is not valid"):
         Oracle([], geoip_mmdb=b"not a database")
+
+
+def test_unicode_script_names_are_known_and_have_no_ascii_member():
+    """Every Unicode script name the `regex` module knows (its own Unicode tables) is accepted by the oracle and by the engine's
+    front-end, and -- Latin and Common apart -- matches no ASCII character, as in the `regex` module."""
+    L = oracle_lib()
+    ascii_all = "".join(chr(c) for c in range(128)).encode()
+    names = """Adlam Ahom Anatolian_Hieroglyphs Arabic Armenian Avestan Balinese Bamum Bassa_Vah Batak Bengali Bhaiksuki Bopomofo Brahmi Braille Buginese Buhid
+    Canadian_Aboriginal Carian Caucasian_Albanian Chakma Cham Cherokee Chorasmian Coptic Cuneiform Cypriot Cyrillic Deseret Devanagari Dives_Akuru Dogra Duployan
+    Egyptian_Hieroglyphs Elbasan Elymaic Ethiopic Georgian Glagolitic Gothic Grantha Greek Gujarati Gunjala_Gondi Gurmukhi Han Hangul Hanifi_Rohingya Hanunoo Hatran
+    Hebrew Hiragana Imperial_Aramaic Inherited Inscriptional_Pahlavi Inscriptional_Parthian Javanese Kaithi Kannada Katakana Kayah_Li Kharoshthi Khitan_Small_Script
+    Khmer Khojki Khudawadi Lao Lepcha Limbu Linear_A Linear_B Lisu Lycian Lydian Mahajani Makasar Malayalam Mandaic Manichaean Marchen Masaram_Gondi Medefaidrin
+    Meetei_Mayek Mende_Kikakui Meroitic_Cursive Meroitic_Hieroglyphs Miao Modi Mongolian Mro Multani Myanmar Nabataean Nandinagari New_Tai_Lue Newa Nko Nushu
+    Nyiakeng_Puachue_Hmong Ogham Ol_Chiki Old_Hungarian Old_Italic Old_North_Arabian Old_Permic Old_Persian Old_Sogdian Old_South_Arabian Old_Turkic Oriya Osage
+    Osmanya Pahawh_Hmong Palmyrene Pau_Cin_Hau Phags_Pa Phoenician Psalter_Pahlavi Rejang Runic Samaritan Saurashtra Sharada Shavian Siddham SignWriting Sinhala
+    Sogdian Sora_Sompeng Soyombo Sundanese Syloti_Nagri Syriac Tagalog Tagbanwa Tai_Le Tai_Tham Tai_Viet Takri Tamil Tangut Telugu Thaana Thai Tibetan Tifinagh
+    Tirhuta Ugaritic Vai Wancho Warang_Citi Yezidi Yi Zanabazar_Square Cypro_Minoan Old_Uyghur Tangsa Toto Vithkuqi Kawi Nag_Mundari Latin Common""".split()
+    rules = []
+    for n in names:
+        ref = _regex.search(r"\p{%s}" % n, ascii_all.decode()) is not None
+        for form in (r"\p{%s}" % n, r"\p{sc=%s}" % n.lower().replace("_", " ")):
+            pb = form.encode()
+            assert L.orc_regex_is_match(pb, len(pb), ascii_all, len(ascii_all)) == (1 if ref else 0), form
+        rules.append(Rule(n, "http_request.url.matches(" + json.dumps(r"\p{%s}" % n) + ")", [Action.BLOCK]))
+    # the engine's front-end: all of them in one rule set; only Latin and Common can block
+    sim = Sim(rules, eval_gates=False)
+    got = sim.evaluate(pack_requests([req(url="az"), req(url="09-"), req(url="")]))
+    assert [fmt_verdict(v) for v in got] == ["block@%d" % names.index("Latin"), "block@%d" % names.index("Common"), "allow@-"]
