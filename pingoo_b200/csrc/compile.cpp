@@ -461,7 +461,6 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
                         if (pr.all_gate) { cls = UC_GATED; gated_grams.push_back(GatedGrams{std::move(pr.grams)}); }
                     }
                 }
-                if (getenv("PGW_DEBUG_CLASSES") && cls == UC_GATED && gated_grams.back().grams.size() > 300) fprintf(stderr, "gated field %s grams %zu: %s\n", kFieldNames[f], gated_grams.back().grams.size(), M.atoms[a].key.c_str());
                 bundles[cls].push_back(std::move(b));
                 bundle_atom[cls].push_back(a);
             }
