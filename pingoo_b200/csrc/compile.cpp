@@ -658,6 +658,12 @@ bool compile_program(Model& M, const CompileOptions& opt, const std::vector<uint
     for (uint32_t a = 0; a < H.n_atoms; ++a) {
         const AtomDesc& d = M.atoms[a];
         if (d.kind == AtomDesc::STR_PATTERN) continue;
+        // A predicate no rule refers to (its rule folded to a constant, e.g. behind an operand that always errors) is not
+        // evaluated at all -- like the unreferenced string atoms, which are not scanned.  This is more than an economy: the
+        // two-atom verdict shortcut (atom_sig, above) relies on every atom that can be TRUE being mentioned by some rule; an
+        // unmentioned one has an empty signature, which is "disjoint" from anything, including the all-ones signature of an
+        // atom that a rule true on the all-false vector negates.
+        if (!((H.care[a >> 5] >> (a & 31)) & 1u)) continue;
         NsAtom n;
         memset(&n, 0, sizeof n);
         n.kind = d.kind;

@@ -162,3 +162,17 @@ def value_constructs():
             for m in ["GET", "POST", "PUT", "ET", "", "host", "zz"] for port in [79, 80, 442, 443] for c in ["US", "FR", "XX"]]
     lists = {"ports": (ListType.Int, b"80\n443\n806\n")}
     return rules, lists, pack_requests(reqs)
+
+
+def unreferenced_predicates():
+    """A predicate whose rule folds to a constant (here: behind a `||` operand that always errors) used to be evaluated
+    anyway; being mentioned by no rule it had an empty rule signature, and the two-atom verdict shortcut paired it with an atom
+    that a route true on the all-false vector negates -- the wrong service (found by the expression fuzz, seed 3736)."""
+    rules = [Rule("dead", '(1 + 1 || lists["nets"].contains(client.ip)) ? http_request.host >= http_request.url : http_request.nope == "x"', []),
+             Rule("port", "client.remote_port == 81", [Action.BLOCK])]
+    services = [Service("s0", "!(http_request.path < http_request.url)"), Service("s1", 'http_request.method == "GET"'), Service("s2", None)]
+    lists = {"nets": (ListType.Ip, b"10.0.0.0/8\n")}
+    reqs = [dict(host=h, url=u, path=p, method=m, user_agent="Mozilla/5.0", ip=ip, remote_port=port, flags=0)
+            for h in ["", "zz", "a"] for (u, p) in [("selectcurlaab/", "selectcurlaab"), ("a", "b"), ("/x", "/x")] for m in ["GET", "DELETE"]
+            for ip in ["8.8.8.8", "10.1.1.1"] for port in [80, 81]]
+    return rules, services, lists, pack_requests(reqs)

@@ -281,3 +281,12 @@ def test_list_csv_forms_engine_vs_oracle():
         accepted += res[0][0] == "ok"
         refused += res[0][0] == "error"
     assert accepted > 40 and refused > 40
+
+
+def test_unreferenced_predicates_are_not_evaluated():
+    rules, services, lists, batch = scenarios.unreferenced_predicates()
+    want_v, want_s = Oracle(rules, lists, services=services).evaluate_routed(batch, threads=4)
+    sim = Sim(rules, lists, services=services)
+    got_v, got_s = sim.evaluate_routed(batch)
+    assert np.array_equal(got_v, want_v) and np.array_equal(got_s, want_s)
+    assert len(set(want_s.tolist())) >= 3 and "ns_atoms=2" in sim.describe()   # the port predicate and the route's field comparison only

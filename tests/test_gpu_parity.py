@@ -336,3 +336,13 @@ def test_gate_resolve_with_and_without_literal_confirmation():
     eng2, _ = _check(test_gate.RULES, batch, literal_confirm=False)
     d2 = eng2.describe()
     assert "literals=" not in d2 and "wide-slots" not in d2 and "user_agent/gated" in d2, d2
+
+
+@pytest.mark.gpu
+def test_unreferenced_predicates_are_not_evaluated():
+    """tests/scenarios.py unreferenced_predicates: the service of a request must not depend on a predicate no rule mentions."""
+    rules, services, lists, batch = scenarios.unreferenced_predicates()
+    want_v, want_s = Oracle(rules, lists, services=services).evaluate_routed(batch, threads=THREADS)
+    eng = WafEngine(rules, lists, device=0, services=services)
+    got_v, got_s = eng.evaluate_host_routed(batch)
+    assert np.array_equal(got_v, want_v) and np.array_equal(got_s, want_s)
