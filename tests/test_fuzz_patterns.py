@@ -51,3 +51,60 @@ def test_random_pattern_sets_on_every_unit_kind(seed):
     for _ in range(4):
         problems = one_round(rng)
         assert not problems, "\n".join(problems)
+
+
+VOC = ["curl", "curl/", "curl/8", "sqlmap", "sqlmap1", "sqlmaP2", "nikto", "nik", ".php", ".php5", ".phtml", "php", "../", "..", "/etc/passwd", "/etc/", "passwd", "wp-admin",
+       "wp-", "admin", "Admin", "ADMIN", "bot", "Bot/", "robot", "abc", "abcd", "abcde", "bcde", "cde", "xyz", "xy", "yz", "-", "_", "/", "%2e", "%2E", "aaa", "aaaa", "aab",
+       "baa", "a", "b", "zz"]
+
+
+def literal_round(rng, n_requests=250):
+    """Rule sets made of strings that share prefixes, suffixes and grams (what decides which atoms the gate may confirm itself),
+    anchored and case-insensitive variants, negations; requests assembled from the same vocabulary at every alignment."""
+    def esc(t):
+        return "".join("\\\\" + c if c in ".+*?()[]{}|^$/\\" else c for c in t)
+
+    rules = []
+    for i in range(rng.randint(3, 14)):
+        f = rng.choice(["url", "user_agent", "path"])
+        k, lit = rng.randrange(8), rng.choice(VOC)
+        if k < 3:
+            ex = f"http_request.{f}.{['contains', 'ends_with', 'starts_with'][k]}(" + json.dumps(lit) + ")"
+        elif k == 3:
+            ex = f'http_request.{f}.matches("(?i)(' + "|".join(esc(rng.choice(VOC)) for _ in range(rng.randint(1, 4))) + ')")'
+        elif k == 4:
+            ex = f'http_request.{f}.matches("(' + "|".join(esc(rng.choice(VOC)) for _ in range(rng.randint(1, 3))) + ')$")'
+        elif k == 5:
+            ex = f'http_request.{f}.matches("^' + esc(lit) + '")'
+        elif k == 6:
+            ex = f'http_request.{f}.matches("' + esc(lit) + rng.choice(["[0-9]?", "s?"]) + esc(rng.choice(VOC)) + '")'
+        else:
+            ex = f"http_request.{f} == " + json.dumps(lit)
+        if rng.random() < 0.15:
+            ex = "!(" + ex + ")"
+        rules.append(Rule(f"r{i}", ex, [Action.BLOCK if i % 2 else Action.CAPTCHA]))
+
+    def mk():
+        return "".join(rng.choice(VOC + ["q", "Q", " ", "="]) for _ in range(rng.randint(0, 7)))
+
+    reqs = [dict(host="h", url=mk(), path="/" + mk(), method="GET", user_agent=(mk().strip() or "m") + "z", ip="1.2.3.4", remote_port=1, flags=i % 2)
+            for i in range(n_requests)]
+    batch = pack_requests(reqs)
+    want = Oracle(rules, eval_gates=False).evaluate(batch, threads=8)
+    problems = []
+    for label, opts in VARIANTS[:4]:
+        got = Sim(rules, eval_gates=False, **opts).evaluate(batch)
+        d = np.nonzero(got != want)[0]
+        if len(d):
+            i = int(d[0])
+            problems.append(f"{label}: {len(d)} differ, e.g. url={batch.field('url', i)!r} ua={batch.field('user_agent', i)!r} path={batch.field('path', i)!r} "
+                            f"oracle {int(want[i]):#x} tables {int(got[i]):#x} rules={[r.expression for r in rules]}")
+    return problems
+
+
+@pytest.mark.parametrize("seed", [301, 302, 303])
+def test_literal_heavy_rule_sets(seed):
+    rng = random.Random(seed)
+    for _ in range(12):
+        problems = literal_round(rng)
+        assert not problems, "\n".join(problems)
