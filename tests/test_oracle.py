@@ -179,7 +179,9 @@ def random_pattern(rng, depth=0):
             p = "^" + p
         if rng.random() < 0.2:
             p = p + "$"
-        if rng.random() < 0.25:
+        # Rust folds a cased property under (?i) (`(?i)\p{Lu}` matches `a`: regex-syntax hir/translate.rs unicode_fold_and_negate),
+        # the `regex` module does not: such combinations have known answers below instead of this cross-check
+        if rng.random() < 0.25 and not any(k in p for k in ("Lu", "Ll", "Uppercase", "Lowercase")):
             p = "(?i)" + p
     return p
 
