@@ -221,6 +221,7 @@ int pgw_ruleset_create(const pgw_rule_desc* rules, uint32_t n_rules, const pgw_o
                        char* err, size_t err_cap) {
     if (!out) return fail("out is null", err, err_cap);
     *out = nullptr;
+    if (n_rules && !rules) return fail("rules is null", err, err_cap);
     pgw_ruleset* rs = new pgw_ruleset();
     memset(&rs->base, 0, sizeof rs->base);
     if (options) {

@@ -35,6 +35,7 @@ bool RulesetBuilder::add_rule(const char* name, const char* expression, const ui
     if (finalized_) { err = "ruleset already finalized"; return false; }
     RuleSource r;
     r.name = name ? name : "";
+    if (n_actions && !actions) { err = "error parsing rules: rule '" + r.name + "': actions is null"; return false; }
     for (uint32_t i = 0; i < n_actions; ++i) {
         if (actions[i] != ACT_BLOCK && actions[i] != ACT_CAPTCHA) {
             err = "error parsing rules: rule '" + r.name + "': unknown action code " + std::to_string((int)actions[i]);

@@ -68,3 +68,53 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_ffi, "LIB_PATH", "/nonexistent/libpingoo_waf.so")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _ffi.load()
+
+
+def test_null_and_invalid_arguments_are_errors_not_crashes():
+    """Every entry point that works without a device, called with null pointers / absurd values: an error code and a message,
+    never a crash (a proxy must survive a bad configuration reload)."""
+    L = _ffi.load()
+    err = C.create_string_buffer(256)
+    p = C.c_void_p
+    sigs = {
+        "pgw_compile_expression": [C.c_char_p, C.c_char_p, C.c_size_t], "pgw_validate_expression": [C.c_char_p, C.c_char_p, C.c_size_t],
+        "pgw_ruleset_create": [p, C.c_uint32, p, p, C.c_char_p, C.c_size_t], "pgw_lists_add": [p, C.c_char_p, C.c_int, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t],
+        "pgw_geoip_load": [p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t], "pgw_ruleset_finalize": [p, C.c_int, C.c_char_p, C.c_size_t],
+        "pgw_ruleset_info": [p, p], "pgw_evaluate_batch": [p, p, p, p], "pgw_evaluate_batch_host": [p, p, p], "pgw_services_set": [p, p, C.c_uint32, C.c_char_p, C.c_size_t],
+        "pgw_queue_create": [p, C.c_uint32, C.c_uint32, p, C.c_char_p, C.c_size_t], "pgw_ruleset_load_dir": [C.c_char_p, C.c_char_p, p, C.c_uint32, p, p, C.c_char_p, C.c_size_t],
+        "pgw_shape_request": [p, p, p], "pgw_geoip_lookup_batch": [p, p, p, C.c_uint32, p, p, p], "pgw_captcha_client_id_batch": [p, p, p],
+        "pgw_ruleset_destroy": [p], "pgw_queue_destroy": [p], "pgw_host_free": [p],
+    }
+    for name, at in sigs.items():
+        getattr(L, name).argtypes = at
+    L.pgw_ruleset_describe.argtypes, L.pgw_ruleset_describe.restype = [p, C.c_char_p, C.c_size_t], C.c_size_t
+    assert L.pgw_compile_expression(None, err, 256) != 0 and L.pgw_validate_expression(None, None, 0) != 0
+    assert L.pgw_compile_expression(b"true", None, 0) == 0
+    h = C.c_void_p()
+    assert L.pgw_ruleset_create(None, 3, None, C.byref(h), err, 256) != 0 and b"rules is null" in err.value
+    assert L.pgw_ruleset_create(None, 0, None, None, err, 256) != 0
+    bad = (_ffi.RuleDesc * 1)()
+    bad[0].name, bad[0].expression, bad[0].actions, bad[0].n_actions = None, b"true", None, 2
+    assert L.pgw_ruleset_create(bad, 1, None, C.byref(h), err, 256) != 0 and b"actions is null" in err.value
+    assert L.pgw_ruleset_create(None, 0, None, C.byref(h), err, 256) == 0 and h.value
+    assert L.pgw_lists_add(h, None, 0, b"x", 1, err, 256) != 0 and L.pgw_lists_add(None, b"l", 0, b"", 0, err, 256) != 0
+    assert L.pgw_lists_add(h, b"l", 7, b"x", 1, err, 256) != 0 and b"not a valid ListType" in err.value
+    assert L.pgw_lists_add(h, b"l", 0, None, 0, err, 256) == 0   # an empty list file
+    assert L.pgw_geoip_load(h, None, 0, err, 256) != 0 and L.pgw_geoip_load(None, b"x", 1, err, 256) != 0
+    assert L.pgw_services_set(h, None, 2, err, 256) != 0 and L.pgw_services_set(None, None, 0, err, 256) != 0
+    assert L.pgw_ruleset_finalize(None, 0, err, 256) != 0
+    assert L.pgw_ruleset_info(None, None) != 0 and L.pgw_ruleset_info(h, None) != 0
+    assert L.pgw_ruleset_describe(None, None, 0) == 0 and L.pgw_ruleset_describe(h, None, 0) > 0
+    b = _ffi.Batch()
+    assert L.pgw_evaluate_batch(None, None, None, None) != 0 and L.pgw_evaluate_batch(h, C.byref(b), None, None) != 0   # not finalized
+    assert L.pgw_evaluate_batch_host(h, C.byref(b), None) != 0
+    q = C.c_void_p()
+    assert L.pgw_queue_create(None, 16, 100, C.byref(q), err, 256) != 0 and L.pgw_queue_create(h, 0, 100, C.byref(q), err, 256) != 0
+    assert L.pgw_ruleset_load_dir(None, None, None, 0, None, C.byref(q), err, 256) != 0
+    assert L.pgw_ruleset_load_dir(b"/nonexistent-dir", None, None, 0, None, C.byref(q), err, 256) != 0 and b"error reading config file" in err.value
+    assert L.pgw_shape_request(None, None, None) != 0
+    assert L.pgw_geoip_lookup_batch(None, None, None, 0, None, None, None) != 0 and L.pgw_captcha_client_id_batch(None, None, None) != 0
+    L.pgw_ruleset_destroy(None)
+    L.pgw_queue_destroy(None)
+    L.pgw_host_free(None)
+    L.pgw_ruleset_destroy(h)
