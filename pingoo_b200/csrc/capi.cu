@@ -317,10 +317,6 @@ int pgw_ruleset_finalize(pgw_ruleset* rs, int device, char* err, size_t err_cap)
     std::vector<uint8_t> image;
     std::vector<UnitDesc>& units = rs->units;
     size_t image_budget = waf_scan_image_budget(rs->max_smem);
-    if (const char* ev = getenv("PGW_SMEM_IMAGE_KB")) {  // tuning knob
-        size_t v = (size_t)atoi(ev) << 10;
-        if (v >= 4096 && v < image_budget) image_budget = v;
-    }
     build_unit_images(H, image_budget, &image, &units);
     uint32_t max_img = 0;
     for (auto& u : units) {
@@ -631,8 +627,7 @@ int pgw_evaluate_batch_routed_host(pgw_ruleset* rs, const pgw_batch* b, uint32_t
     // The batch is cut into slices of whole requests: slice k is copied on the copy stream while slice k-1 is evaluated
     // on the compute stream, so that only the first copy and the last kernel are exposed.  Offsets stay absolute (the
     // column base does not move), a slice is just a window of the offset arrays.
-    uint32_t slice = 262144;
-    if (const char* e = getenv("PGW_HOST_SLICE")) { long v = atol(e); if (v >= 1024) slice = (uint32_t)v; }
+    const uint32_t slice = 262144;
     uint32_t n_slices = (n + slice / 2) / slice;
     if (n_slices < 1) n_slices = 1;
     if (n_slices > kHostSlices) n_slices = kHostSlices;
