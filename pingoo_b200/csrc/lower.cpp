@@ -113,7 +113,9 @@ struct Sym {
     enum K : uint8_t {
         ERR, NUL, BOOL, INT_C, UINT_C, FLOAT_C, STR_C, BYTES_C, LIST_C, LIST_REF, MAP_C,
         MAP_LISTS, MAP_HTTP, MAP_CLIENT, STR_FIELD, INT_FEAT, INT_EXPR, IP_VAR, COUNTRY_VAR,
-        CHOICE   // c ? x : y with non-boolean branches on a request-dependent condition: bv = the condition, items = {x, y}
+        CHOICE,  // c ? x : y with non-boolean branches on a request-dependent condition: bv = the condition, items = {x, y}
+        CONCAT   // a + b + ... on strings with at least one http_request field among them: items = the parts (STR_C / STR_FIELD, no
+                 // empty and no two adjacent constants)
     } k = ERR;
     std::vector<int64_t> prog;   // INT_EXPR: postfix tokens (program.hpp IntTok)
     BV bv;
@@ -757,6 +759,146 @@ struct Lowerer {
         return v;
     }
 
+    // ---- string concatenation with request fields ------------------------------------------------------------------------------
+    // `http_request.host + http_request.path == "example.com/admin"`, `(method + " " + path).starts_with("POST /api")`: the value
+    // stays symbolic (the parts); a comparison with a CONSTANT is decided by the finitely many ways the constant can be cut along
+    // the parts -- each cut is a conjunction of `field == piece` / `field.starts_with(piece)` / ... atoms the engine already has.
+    static bool is_stringy(const Sym& s) { return s.k == Sym::STR_C || s.k == Sym::STR_FIELD || s.k == Sym::CONCAT; }
+    Sym concat(const Sym& a, const Sym& b) {
+        std::vector<Sym> parts;
+        auto take = [&](const Sym& x) {
+            if (x.k == Sym::CONCAT) { for (const Sym& y : x.items) parts.push_back(y); }
+            else parts.push_back(x);
+        };
+        take(a);
+        take(b);
+        std::vector<Sym> merged;
+        for (Sym& x : parts) {
+            if (x.k == Sym::STR_C && x.s.empty()) continue;
+            if (x.k == Sym::STR_C && !merged.empty() && merged.back().k == Sym::STR_C) merged.back().s += x.s;
+            else merged.push_back(std::move(x));
+        }
+        if (merged.empty()) return const_str("");
+        if (merged.size() == 1) return merged[0];
+        Sym r;
+        r.k = Sym::CONCAT;
+        r.items = std::move(merged);
+        return r;
+    }
+    struct ConcatCuts {
+        Lowerer& L;
+        const Expr& e;
+        const std::vector<Sym>& parts;
+        const std::string& C;
+        size_t leaves = 0;
+        std::map<std::pair<size_t, size_t>, int> memo_eq, memo_sw, memo_ew;
+        int leaf(const Sym& r) {
+            if (++leaves > 2048) L.unsupported(e, "concatenation compared with a constant that can be cut in too many ways");
+            return r.bv.t;
+        }
+        // parts[i..] == C[pos..]
+        int eq(size_t i, size_t pos) {
+            if (i == parts.size()) return L.P.constant(pos == C.size());
+            auto key = std::make_pair(i, pos);
+            auto it = memo_eq.find(key);
+            if (it != memo_eq.end()) return it->second;
+            int r = L.P.constant(false);
+            const Sym& p = parts[i];
+            if (p.k == Sym::STR_C) {
+                if (pos + p.s.size() <= C.size() && C.compare(pos, p.s.size(), p.s) == 0) r = eq(i + 1, pos + p.s.size());
+            } else {
+                for (size_t l = 0; pos + l <= C.size(); ++l) {
+                    const int rest = eq(i + 1, pos + l);
+                    if (L.P.is_const(rest) && !L.P.const_value(rest)) continue;
+                    r = L.P.mk_or(r, L.P.mk_and(leaf(L.str_literal_atom(p.field, C.substr(pos, l), true, true)), rest));
+                }
+            }
+            return memo_eq[key] = r;
+        }
+        // parts[i..] starts with C[pos..]
+        int sw(size_t i, size_t pos) {
+            if (pos == C.size()) return L.P.constant(true);
+            if (i == parts.size()) return L.P.constant(false);
+            auto key = std::make_pair(i, pos);
+            auto it = memo_sw.find(key);
+            if (it != memo_sw.end()) return it->second;
+            int r = L.P.constant(false);
+            const Sym& p = parts[i];
+            const size_t left = C.size() - pos;
+            if (p.k == Sym::STR_C) {
+                const size_t m = std::min(p.s.size(), left);
+                if (C.compare(pos, m, p.s, 0, m) == 0) r = m == left ? L.P.constant(true) : sw(i + 1, pos + p.s.size());
+            } else {
+                r = leaf(L.str_literal_atom(p.field, C.substr(pos), true, false));   // the rest of C lies inside this field
+                for (size_t l = 0; l < left; ++l) {
+                    const int rest = sw(i + 1, pos + l);
+                    if (L.P.is_const(rest) && !L.P.const_value(rest)) continue;
+                    r = L.P.mk_or(r, L.P.mk_and(leaf(L.str_literal_atom(p.field, C.substr(pos, l), true, true)), rest));
+                }
+            }
+            return memo_sw[key] = r;
+        }
+        // parts[..n) ends with C[..end)
+        int ew(size_t n, size_t end) {
+            if (end == 0) return L.P.constant(true);
+            if (n == 0) return L.P.constant(false);
+            auto key = std::make_pair(n, end);
+            auto it = memo_ew.find(key);
+            if (it != memo_ew.end()) return it->second;
+            int r = L.P.constant(false);
+            const Sym& p = parts[n - 1];
+            if (p.k == Sym::STR_C) {
+                const size_t m = std::min(p.s.size(), end);
+                if (C.compare(end - m, m, p.s, p.s.size() - m, m) == 0) r = m == end ? L.P.constant(true) : ew(n - 1, end - p.s.size());
+            } else {
+                r = leaf(L.str_literal_atom(p.field, C.substr(0, end), false, true));   // C[..end) lies inside this field
+                for (size_t l = 0; l < end; ++l) {
+                    const int rest = ew(n - 1, end - l);
+                    if (L.P.is_const(rest) && !L.P.const_value(rest)) continue;
+                    r = L.P.mk_or(r, L.P.mk_and(leaf(L.str_literal_atom(p.field, C.substr(end - l, l), true, true)), rest));
+                }
+            }
+            return memo_ew[key] = r;
+        }
+        int contains() {
+            if (C.empty()) return L.P.constant(true);
+            int r = L.P.constant(false);
+            for (const Sym& p : parts) {   // inside one part
+                if (p.k == Sym::STR_C) { if (p.s.find(C) != std::string::npos) return L.P.constant(true); }
+                else r = L.P.mk_or(r, leaf(L.str_literal_atom(p.field, C, false, false)));
+            }
+            for (size_t b = 1; b < parts.size(); ++b)   // across the boundary in front of part b: C[..l) ends there, C[l..) starts there
+                for (size_t l = 1; l < C.size(); ++l) {
+                    const int left = ew(b, l);
+                    if (L.P.is_const(left) && !L.P.const_value(left)) continue;
+                    // sw() works on C from `pos`: the right-hand piece is C[l..)
+                    r = L.P.mk_or(r, L.P.mk_and(left, sw(b, l)));
+                }
+            return r;
+        }
+    };
+    Sym concat_length(const Expr& e, const Sym& c) {
+        Sym acc = const_int(0);
+        bool first = true;
+        for (const Sym& p : c.items) {
+            Sym term;
+            if (p.k == Sym::STR_C) term = const_int((int64_t)utf8_len(p.s));
+            else { term.k = Sym::INT_FEAT; term.feat = IF_LEN0 + p.field; }
+            if (first) { acc = term; first = false; }
+            else if (acc.k == Sym::INT_C && term.k == Sym::INT_C) acc = const_int(acc.i + term.i);
+            else acc = int_arith(e, IT_ADD, acc, term);
+        }
+        return acc;
+    }
+    // CONCAT <fn> constant, fn in {"==", "contains", "starts_with", "ends_with"}
+    Sym concat_pred(const Expr& e, const Sym& c, const std::string& fn, const std::string& C) {
+        ConcatCuts cc{*this, e, c.items, C};
+        if (fn == "==") return boolean(cc.eq(0, 0));
+        if (fn == "starts_with") return boolean(cc.sw(0, 0));
+        if (fn == "ends_with") return boolean(cc.ew(c.items.size(), C.size()));
+        return boolean(cc.contains());
+    }
+
     Sym method(const Expr& e) {
         Sym recv0 = lower(*e.kids[0]);
         std::vector<Sym> args0;
@@ -782,6 +924,7 @@ struct Lowerer {
             switch (recv.k) {
                 case Sym::STR_C: return const_int((int64_t)utf8_len(recv.s));
                 case Sym::STR_FIELD: { Sym s; s.k = Sym::INT_FEAT; s.feat = IF_LEN0 + recv.field; return s; }
+                case Sym::CONCAT: return concat_length(e, recv);
                 case Sym::COUNTRY_VAR: return const_int(2);
                 case Sym::LIST_C: case Sym::LIST_REF: return const_int((int64_t)list_size(recv));
                 case Sym::MAP_C: return const_int((int64_t)recv.items.size() / 2);
@@ -817,6 +960,19 @@ struct Lowerer {
                     return const_bool(false);
                 }
                 return const_bool(member(recv, a.s).k != Sym::ERR);
+            }
+            // a concatenation on either side
+            if (recv.k == Sym::CONCAT) {
+                if (a.k == Sym::STR_C) {
+                    if (fn == "matches") unsupported(e, "matches() on a concatenation of request variables");
+                    return concat_pred(e, recv, fn, a.s);
+                }
+                if (is_stringy(a) || a.k == Sym::COUNTRY_VAR) unsupported(e, fn + "() between a concatenation and a request variable");
+                return err();
+            }
+            if (a.k == Sym::CONCAT) {
+                if (recv.k == Sym::STR_C || recv.k == Sym::STR_FIELD || recv.k == Sym::COUNTRY_VAR) unsupported(e, fn + "() with a concatenation of request variables as argument");
+                return err();
             }
             // string receivers
             auto str_pred = [&](const std::string& hay, const std::string& arg, bool* is_err) -> bool {
@@ -980,6 +1136,17 @@ struct Lowerer {
         }
         // variable on the right: swap
         if (is_const(a) && !is_const(b)) return compare(e, flip_cmp(op), b, a);
+        if (a.k == Sym::CONCAT || b.k == Sym::CONCAT) {
+            const Sym& c = a.k == Sym::CONCAT ? a : b;
+            const Sym& o = a.k == Sym::CONCAT ? b : a;
+            if (o.k == Sym::STR_C) {
+                if (ordering) unsupported(e, "lexicographic ordering of a concatenation of request variables");
+                Sym eq = concat_pred(e, c, "==", o.s);
+                return op == CMP_EQ ? eq : boolean(P.mk_not(eq.bv.t));
+            }
+            if (is_stringy(o) || o.k == Sym::COUNTRY_VAR) unsupported(e, "comparison of a concatenation with a request variable");
+            return err();   // a String against a value of another type
+        }
         // a is a variable
         switch (a.k) {
             case Sym::STR_FIELD:
@@ -1070,8 +1237,13 @@ struct Lowerer {
                 default: return err();
             }
         }
-        if (a.k == Sym::STR_FIELD || b.k == Sym::STR_FIELD || a.k == Sym::COUNTRY_VAR || b.k == Sym::COUNTRY_VAR)
-            if (e.op == Expr::OP_ADD) unsupported(e, "string concatenation with request variables");
+        if (e.op == Expr::OP_ADD && (a.k == Sym::STR_FIELD || b.k == Sym::STR_FIELD || a.k == Sym::CONCAT || b.k == Sym::CONCAT)) {
+            if (is_stringy(a) && is_stringy(b)) return concat(a, b);
+            if (a.k == Sym::COUNTRY_VAR || b.k == Sym::COUNTRY_VAR) unsupported(e, "string concatenation with client.country");
+            return err();   // String + a value of another type
+        }
+        if (a.k == Sym::COUNTRY_VAR || b.k == Sym::COUNTRY_VAR)
+            if (e.op == Expr::OP_ADD) unsupported(e, "string concatenation with client.country");
         if (a.k == Sym::INT_C && b.k == Sym::INT_C) {
             int64_t r = 0;
             switch (e.op) {

@@ -154,6 +154,13 @@ def value_constructs():
         '{"GET": 1, "ET": 2}.contains(http_request.method) && client.remote_port == 79',
         'http_request.contains(http_request.method)',
         'lists.contains(http_request.host)',
+        # string concatenation with request fields: decided by the ways the constant can be cut along the parts
+        'http_request.host + http_request.path == "example.com/admin/x"',
+        '(http_request.method + " " + http_request.path).starts_with("GET /adm")',
+        '(http_request.host + "|" + http_request.method).ends_with("m|PUT")',
+        '(http_request.host + http_request.path).contains("m/a") && http_request.method != "GET"',
+        '(http_request.method + http_request.method) == "ETET"',
+        '(http_request.host + "ab" + http_request.path).length() == 17 && client.remote_port == 443',
     ]
     rules = [Rule(f"c{i}", ex, [Action.BLOCK if i % 3 else Action.CAPTCHA]) for i, ex in enumerate(exprs)]
     reqs = [dict(host=h, url=u, path=p, method=m, user_agent="Mozilla/5.0", ip="1.2.3.4", remote_port=port, flags=(len(h) + port) % 2, country=c, asn=1)

@@ -23,7 +23,7 @@ def lit(rng):
 
 def predicate(rng):
     f = "http_request." + rng.choice(FIELDS)
-    k = rng.randrange(30)
+    k = rng.randrange(31)
     if k < 4:
         return f'{f}.contains({lit(rng)})'
     if k < 6:
@@ -74,6 +74,10 @@ def predicate(rng):
     if k == 28:   # conditional with non-boolean branches
         return rng.choice([f'(client.remote_port > 100 ? {f} : {g}) == {lit(rng)}', f'(client.asn == 7 ? "GET" : "POST") == http_request.method',
                            f'(client.remote_port == 80 ? 1 : client.asn) > 5'])
+    if k == 29:   # string concatenation with request fields, compared with constants
+        cat = "(" + " + ".join(rng.choice([f, g, lit(rng), '"/"', "http_request.method"]) for _ in range(rng.randint(2, 3))) + " + " + f + ")"
+        return rng.choice([f'{cat} == {lit(rng)}', f'{cat}.contains({lit(rng)})', f'{cat}.starts_with({lit(rng)})', f'{cat}.ends_with({lit(rng)})',
+                           f'{cat}.length() > {rng.randrange(0, 60)}', f'{cat} != "GETGET"', f'(http_request.method + " " + http_request.path).starts_with("GET /api")'])
     return f'{f}.contains({lit(rng)}) == {rng.choice(["true", "false"])}'
 
 
