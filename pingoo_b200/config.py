@@ -79,6 +79,11 @@ def zstd_decode_all(data: bytes) -> bytes:
     return bytes(out)
 
 
+def _os_error(e: OSError) -> str:
+    """std::io::Error's Display: `No such file or directory (os error 2)`."""
+    return f"{e.strerror} (os error {e.errno})"
+
+
 def _rules_from_mapping(mapping, where) -> List[Rule]:
     if mapping is None:
         return []
@@ -89,7 +94,11 @@ def _rules_from_mapping(mapping, where) -> List[Rule]:
         if not isinstance(cfg, dict) or "actions" not in cfg:
             raise Error(f"error parsing {where}: {name}: missing field `actions`")
         expr = cfg.get("expression")
-        out.append(Rule(name=str(name), expression=None if expr is None else str(expr), actions=Rule.from_config(str(name), cfg).actions))
+        try:
+            actions = Rule.from_config(str(name), cfg).actions
+        except Error as e:   # serde reports an unknown action while the file is being deserialised: part of the parse error
+            raise Error(f"error parsing {where}: {name}: {e}")
+        out.append(Rule(name=str(name), expression=None if expr is None else str(expr), actions=actions))
     return out
 
 
@@ -103,7 +112,7 @@ def load_config(folder: str = DEFAULT_CONFIG_FOLDER, geoip_dirs: Optional[List[s
     try:
         raw = open(cfg_path, "rb").read()
     except OSError as e:
-        raise Error(f"error reading config file ({cfg_path}): {e}")
+        raise Error(f"error reading config file ({cfg_path}): {_os_error(e)}")
     try:
         doc = yaml.safe_load(raw) or {}
     except yaml.YAMLError as e:
@@ -122,12 +131,12 @@ def load_config(folder: str = DEFAULT_CONFIG_FOLDER, geoip_dirs: Optional[List[s
                 try:
                     content = open(ent.path, "rb").read()
                 except OSError as e:
-                    raise Error(f"error reading rules file {ent.path!r}: {e}")
+                    raise Error(f'error reading rules file "{ent.path}": {_os_error(e)}')
                 try:
                     mapping = yaml.safe_load(content)
                 except yaml.YAMLError as e:
-                    raise Error(f"error parsing rules file {ent.path!r}: {e}")
-                new = _rules_from_mapping(mapping, f"rules file {ent.path!r}")
+                    raise Error(f'error parsing rules file "{ent.path}": {e}')
+                new = _rules_from_mapping(mapping, f'rules file "{ent.path}"')
                 seen = {r.name for r in folder_rules}
                 for r in new:
                     if r.name in seen:
@@ -138,12 +147,6 @@ def load_config(folder: str = DEFAULT_CONFIG_FOLDER, geoip_dirs: Optional[List[s
         if r.name in names:
             raise Error(f"duplicate rule name: {r.name}")
     out.rules += folder_rules
-    for r in out.rules:  # config.rs:255-269: compile errors are fatal
-        if r.expression is not None:
-            try:
-                compile_expression(r.expression)
-            except Error as e:
-                raise Error(f"error parsing rules: {e}")
 
     all_services = {}
     for name, cfg in (doc.get("services") or {}).items():
@@ -176,6 +179,13 @@ def load_config(folder: str = DEFAULT_CONFIG_FOLDER, geoip_dirs: Optional[List[s
                     raise Error(f"config: listeners: {listener}: service {nm} is not an HTTP service")
                 offered.append(all_services[nm][0])
     out.services = offered if offered is not None else [sv for sv, is_http in all_services.values() if is_http]
+    # the rules are compiled after the services were parsed (routes included) and the listeners validated (config.rs:217-269)
+    for r in out.rules:  # config.rs:255-269: compile errors are fatal
+        if r.expression is not None:
+            try:
+                compile_expression(r.expression)
+            except Error as e:
+                raise Error(f"error parsing rules: {e}")
 
     for name, lc in (doc.get("lists") or {}).items():
         try:
@@ -186,7 +196,7 @@ def load_config(folder: str = DEFAULT_CONFIG_FOLDER, geoip_dirs: Optional[List[s
         try:
             out.lists[str(name)] = (ltype, open(path, "rb").read())
         except OSError as e:
-            raise Error(f"error reading list file {path}: {e}")
+            raise Error(f"error reading list {path}: {_os_error(e)}")   # lists.rs:62-66
 
     for d in (geoip_dirs if geoip_dirs is not None else [folder, "/usr/share/pingoo"]):
         for nm in GEOIP_DATABASE_NAMES:
@@ -195,7 +205,7 @@ def load_config(folder: str = DEFAULT_CONFIG_FOLDER, geoip_dirs: Optional[List[s
                 try:
                     data = open(p, "rb").read()
                 except OSError as e:
-                    raise Error(f"error reading geoip database ({p}): {e}")
+                    raise Error(f"error reading geoip database ({p}): {_os_error(e)}")
                 if p.endswith(".zst"):
                     try:
                         data = zstd_decode_all(data)

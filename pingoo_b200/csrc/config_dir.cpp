@@ -189,6 +189,12 @@ bool load_config_dir(const std::string& folder, const char* listener, const std:
                 s.route = rt->s;
             }
             if (tp && s.has_route) { err = "Invalid service definition for " + s.name + ": TCP proxy can't have a route"; return false; }
+            // parse_service compiles the route right here (config_file.rs:257-265), service by service, before the listeners are
+            // validated and before any rule is compiled (config.rs:217-269): with several mistakes in a file, this is the one reported
+            if (s.has_route) {
+                std::string cerr;
+                if (!RulesetBuilder::compile_expression(s.route, cerr)) { err = "error parsing route for service " + s.name + ": " + cerr; return false; }
+            }
             s.http = hp || st;
             services.push_back(std::move(s));
         }
@@ -223,13 +229,6 @@ bool load_config_dir(const std::string& folder, const char* listener, const std:
     // hand everything to the builder; compile errors are fatal with the reference's texts (config.rs:255-269, config_file.rs:257-265)
     for (auto& r : rules)
         if (!B->add_rule(r.name.c_str(), r.has_expression ? r.expression.c_str() : nullptr, r.actions.data(), (uint32_t)r.actions.size(), err)) return false;
-    for (auto& s : services) {
-        // every route must compile, also the ones this listener does not offer (parse_service runs on all of them)
-        if (s.has_route) {
-            std::string cerr;
-            if (!RulesetBuilder::compile_expression(s.route, cerr)) { err = "error parsing route for service " + s.name + ": " + cerr; return false; }
-        }
-    }
     for (const Svc* s : offered)
         if (!B->add_service(s->name.c_str(), s->has_route ? s->route.c_str() : nullptr, err)) return false;
 
@@ -247,8 +246,13 @@ bool load_config_dir(const std::string& folder, const char* listener, const std:
             else if (ty->s == "Ip") type = LT_IP;
             else { err = "error parsing config file (" + cfg_path + "): lists." + kv.first + ": unknown variant `" + ty->s + "`, expected one of `String`, `Int`, `Ip`"; return false; }
             std::string csv;
-            if (!read_file(fl->s, &csv, &en)) { err = "error reading list file " + fl->s + ": " + os_error(en); return false; }
-            if (!B->add_list(kv.first.c_str(), type, (const uint8_t*)csv.data(), csv.size(), err)) return false;
+            // lists.rs:62-66 and :82-109 name the list by its PATH in every message
+            if (!read_file(fl->s, &csv, &en)) { err = "error reading list " + fl->s + ": " + os_error(en); return false; }
+            if (!B->add_list(kv.first.c_str(), type, (const uint8_t*)csv.data(), csv.size(), err)) {
+                const std::string by_name = "error parsing list " + kv.first + " at line";
+                if (err.compare(0, by_name.size(), by_name) == 0) err = "error parsing list " + fl->s + " at line" + err.substr(by_name.size());
+                return false;
+            }
         }
     }
 

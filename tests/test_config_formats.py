@@ -279,3 +279,81 @@ def test_yaml_reader_rejects_what_it_does_not_read(text):
 def test_zstd_round_trip():
     data = bytes(range(256)) * 4000 + b"tail"
     assert zstd_decode_all(_zstd_compress(data)) == data
+
+
+CFG_EXPRS = ['http_request.path.starts_with("/a")', 'http_request.url.contains("x: y")', "client.remote_port == 80", 'lists["l1"].contains(client.ip)',
+             'http_request.host == "it\'s"', 'http_request.url.matches("a|b")', '!(http_request.method == "GET")', "http_request.path ==", "1 +",
+             'http_request.user_agent.contains("# not a comment")', 'lists["nope"].contains(client.ip)', "true", '"multi\nline" == http_request.host']
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_directories_python_and_native_loader_agree(seed, tmp_path):
+    """Random configuration directories -- rules in the file and in rules/*.yml, services of every kind, lists, a listener's own
+    service list, written by PyYAML in assorted styles, with the usual mistakes sprinkled in (unknown action, duplicate rule,
+    route that does not compile, TCP service with a route, two service kinds, missing list file, malformed list entry): the
+    Python loader and the engine's C++ loader produce the same program, or fail with the same message (the reference's order of
+    checks: file, rules folder, duplicates, services with their routes, listeners, rules; config.rs:194-269)."""
+    import random
+    import re
+    import shutil
+
+    rng = random.Random(seed)
+    acts = ["block", "captcha", "Block", "allow", ""]
+
+    def rule():
+        r = {}
+        if rng.random() < 0.9:
+            r["expression"] = rng.choice(CFG_EXPRS)
+        if rng.random() < 0.9:
+            r["actions"] = [{"action": rng.choice(acts[:2] if rng.random() < 0.93 else acts)} for _ in range(rng.randrange(0, 3))]
+        return r
+
+    def service():
+        sv = {}
+        if rng.random() < 0.6:
+            sv["route"] = rng.choice(CFG_EXPRS[:7] + CFG_EXPRS[9:])
+        for k in rng.sample(["http_proxy", "static", "tcp_proxy"], 1 if rng.random() < 0.93 else rng.choice([0, 2])):
+            sv[k] = ["10.0.0.1:80"] if k != "static" else {"root": "/var/www"}
+        return sv
+
+    agree_ok = agree_err = 0
+    for k in range(60):
+        d = tmp_path / f"c{k}"
+        d.mkdir()
+        doc = {}
+        names = [f"r{i}" for i in range(6)]
+        if rng.random() < 0.9:
+            doc["rules"] = {rng.choice(names): rule() for _ in range(rng.randrange(0, 4))}
+        if rng.random() < 0.8:
+            doc["services"] = {f"s{i}": service() for i in range(rng.randrange(0, 4))}
+        if rng.random() < 0.7:
+            (d / "l1.csv").write_text(rng.choice(['10.0.0.0/8\n1.2.3.4,"c"\n', "10.0.0.0/8\n", "bad\n", ""]))
+            doc["lists"] = {"l1": {"type": rng.choice(["Ip", "Ip", "Ip", "String", "Int", "ip"]), "file": str(d / ("l1.csv" if rng.random() < 0.9 else "missing.csv"))}}
+        if rng.random() < 0.3:
+            doc["listeners"] = {"http": {"address": "http://0.0.0.0:80", "services": [rng.choice(["s0", "s1", "zz"])]}}
+        style = dict(default_flow_style=rng.choice([False, None, True]), default_style=rng.choice([None, None, None, '"', "'"]), width=rng.choice([30, 80, 1000]),
+                     indent=rng.choice([2, 4]), sort_keys=False)
+        (d / "pingoo.yml").write_text(yaml.safe_dump(doc, **style))
+        if rng.random() < 0.6:
+            (d / "rules").mkdir()
+            for fn in rng.sample(["a.yml", "b.yml", "c.yaml", "d.txt"], rng.randrange(1, 3)):
+                (d / "rules" / fn).write_text(yaml.safe_dump({rng.choice(names): rule() for _ in range(rng.randrange(0, 3))}, **style))
+        listener = rng.choice([None, None, "http"])
+        res = []
+        try:
+            cfg = load_config(str(d), geoip_dirs=[str(d)], listener=listener)
+            res.append(("ok", Sim(cfg.rules, cfg.lists, cfg.geoip_mmdb, services=cfg.services).describe()))
+        except (Error, ValueError) as e:
+            res.append(("error", str(e)))
+        try:
+            res.append(("ok", Sim.from_config_dir(str(d), listener=listener, geoip_dir=str(d)).describe()))
+        except (Error, ValueError) as e:
+            res.append(("error", str(e)))
+        # a malformed list entry is reported by the engine when the list is added: the native loader knows the file's path (as
+        # lists.rs does), the Python path only the list's name
+        norm = [(kind, re.sub(r"error parsing list \S+ at line", "error parsing list <l> at line", text)) for kind, text in res]
+        assert norm[0] == norm[1], (d / "pingoo.yml").read_text()
+        agree_ok += res[0][0] == "ok"
+        agree_err += res[0][0] == "error"
+        shutil.rmtree(d)
+    assert agree_ok >= 5 and agree_err >= 5
