@@ -342,14 +342,12 @@ static esc_t parse_escape(parser* P, int in_class, const flags_t* f) {
             e.kind = E_ASSERT;
             e.as = c == '<' ? AS_WS : AS_WE;
             return e;
-        case ' ':
-            if (f->x) { e.cp = ' '; return e; }
-            pfail(P, RX_INVALID, "unrecognized escape sequence");
         default: break;
     }
     if (c >= '0' && c <= '9') pfail(P, RX_INVALID, "backreferences are not supported");
-    if (c > 0x20 && c < 0x7F && !((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'))) {
-        e.cp = (uint32_t)c; /* escaped punctuation */
+    /* regex-syntax `is_escapeable_character`: any ASCII character but letters and digits (`<` `>` are assertions, above) */
+    if (c < 0x80 && !((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'))) {
+        e.cp = (uint32_t)c;
         return e;
     }
     pfail(P, RX_INVALID, "unrecognized escape sequence");

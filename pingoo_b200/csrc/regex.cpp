@@ -461,14 +461,13 @@ class Parser {
             case '<': case '>':
                 if (in_class) fail(RX_INVALID, "unrecognized escape sequence in class");   // an assertion, as \b is (regex >= 1.10)
                 e.kind = Esc::ASSERTION; e.ak = c == '<' ? A_WORD_START : A_WORD_END; return e;
-            case ' ':
-                if (f.x) { e.cp = ' '; return e; }
-                fail(RX_INVALID, "unrecognized escape sequence");
             default: break;
         }
         if (c >= '0' && c <= '9') fail(RX_INVALID, "backreferences are not supported");
-        if (c < 0x80 && !((c >= '0' && c <= '9') || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z')) && c > 0x20 && c != 0x7F) {
-            e.cp = c;  // escaped punctuation
+        // regex-syntax is_escapeable_character: every ASCII character that is not a letter or a digit (and not `<` `>`, taken
+        // above) may be escaped and stands for itself -- punctuation, the blank, control characters
+        if (c < 0x80 && !((c >= '0' && c <= '9') || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z'))) {
+            e.cp = c;
             return e;
         }
         fail(RX_INVALID, "unrecognized escape sequence");

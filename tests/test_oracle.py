@@ -281,6 +281,8 @@ REGEX_KAT = [
     ("[a&&b]", "a", 0), ("[a-z&&[^b]]", "b", 0), ("[a-z--b]", "c", 1), ("\\x{41}", "A", 1), ("\\u0041", "A", 1), ("é", "cafe", 0),
     ("[^é]", "e", 1), ("(?P<n>a)(?<m>b)", "ab", 1), ("a|", "zzz", 1), ("(|a)b", "b", 1), ("[]a]", "]", 1), ("[^]a]", "]", 0), ("[a-]", "-", 1),
     ("\\$\\{jndi:(ldap|rmi|dns)://", "${jndi:ldap://x}", 1), ("}", "}", 1), ("]", "]", 1),
+    # any ASCII character that is not a letter or a digit may be escaped (regex-syntax is_escapeable_character)
+    ("a\\ b", "xa bx", 1), ("a\\ b", "ab", 0), ("\\\t", "a\tb", 1), ("\\_\\-\\/\\%\\@\\~", "_-/%@~", 1), ("[\\ \\_]+$", "a _", 1),
     # Unicode properties on ASCII text
     ("\\p{Lu}\\p{Ll}+", "xx Abc", 1), ("^\\P{L}+$", "12-34", 1), ("^\\P{L}+$", "12a34", 0), ("(?i)\\p{Lu}", "a", 1), ("(?i)\\p{^Lu}", "a", 0), ("(?i)\\P{Lu}", "A", 0), ("(?i)\\P{^Lu}", "a", 1), ("\\p{Greek}", "abc xyz", 0),
     ("\\p{Sc}\\p{Nd}", "cost $5", 1), ("\\p{Ps}\\p{Pe}", "f()", 1), ("\\p{ Script = Latin }", "1a", 1), ("\\p{gc!=L}", "a", 0), ("\\p{Any}", "", 0),
@@ -300,6 +302,14 @@ def test_regex_known_answers(pat, hay, want):
     L = oracle_lib()
     pb, hb = pat.encode(), hay.encode()
     assert L.orc_regex_is_match(pb, len(pb), hb, len(hb)) == want
+
+
+def test_regex_known_answers_through_the_engine_front_end():
+    """The same table through the product's regex front-end and DFA construction (tests/sim walks the compiled tables)."""
+    for pat, hay, want in REGEX_KAT:
+        rules = [Rule("r", "http_request.url.matches(" + json.dumps(pat) + ")", [Action.BLOCK])]
+        got = Sim(rules, eval_gates=False).evaluate(pack_requests([req(url=hay)]))
+        assert int(got[0] & 3) == want, (pat, hay)
 
 
 @pytest.mark.parametrize("pat,want", REGEX_BAD)
