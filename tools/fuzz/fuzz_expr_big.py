@@ -1,0 +1,19 @@
+import sys, collections
+import os; R=os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0,R); sys.path.insert(0,os.path.join(R,'tests'))
+import numpy as np
+from helpers import Oracle, Sim
+import test_fuzz_expressions as t
+lo, hi = int(sys.argv[1]), int(sys.argv[2])
+bad=0; ok=0; ref=0
+for seed in range(lo, hi):
+    rules, svcs, lists, batch = t.make_case(seed, n_rules=45, n_services=9, n_requests=400)
+    want_v, want_s = Oracle(rules, lists, services=svcs).evaluate_routed(batch, threads=2)
+    try:
+        sim = Sim(rules, lists, services=svcs)
+        got_v, got_s = sim.evaluate_routed(batch)
+    except Exception as e:
+        ref+=1; print("REFUSED", seed, str(e)[-120:]); continue
+    ok+=1
+    d=np.nonzero((got_v != want_v) | (got_s != want_s))[0]
+    if len(d): bad+=1; print("MISMATCH seed", seed, len(d))
+print(lo, hi, "ok", ok, "bad", bad, "refused", ref)
