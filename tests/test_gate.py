@@ -105,3 +105,18 @@ def test_baseline_rule_sets(n_rules, cfg):
     batch = synth.RequestStream(config_id=cfg, payloads=payloads, attack_rate=0.25).generate(1_000, 12_000)
     want = _same(rules, batch)
     assert len(set((want >> 2).tolist())) > n_rules // 8
+
+
+def test_literal_confirmation_is_exclusive():
+    """An atom is confirmed by the gate only if no other atom of the field shares one of its grams (one comparison per gram hit,
+    DESIGN.md section 5): the synthetic BASELINE rule sets are families of strings with common prefixes, so configs 3 and 4 confirm
+    nothing (narrow table slots, the block-append resolve kernel -- the measured-best state), config 2 one user-agent atom."""
+    for n_rules, cfg, want_literals in ((128, 2, True), (512, 3, False), (1024, 4, False)):
+        rules, _, _ = synth.make_ruleset(n_rules, config_id=cfg)
+        d = Sim(rules).describe()
+        assert ("literals=" in d) == want_literals and ("wide-slots" in d) == want_literals, (cfg, d[-400:])
+    # a family: the second member shares the grams of the first -> both stay with the DFA unit; a loner is confirmed
+    fam = [Rule("a", 'http_request.user_agent.contains("sqlmap")', [Action.BLOCK]), Rule("b", 'http_request.user_agent.contains("sqlmap/2")', [Action.BLOCK]),
+           Rule("c", 'http_request.user_agent.contains("nikto")', [Action.CAPTCHA])]
+    d = Sim(fam).describe()
+    assert "literals=1" in d and "user_agent/gated" in d, d
